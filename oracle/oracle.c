@@ -1,0 +1,974 @@
+/*
+  oracle/oracle.c -- TEST INFRASTRUCTURE ONLY (see oracle.h).
+
+  CPU restatement of ImageMagick 7.1.1-45's per-pixel hot path on raw float
+  buffers.  Arithmetic is kept in the reference's evaluation order (double
+  accumulate, mul then add, no FMA contraction: build with -ffp-contract=off)
+  so that results are bit-identical to the compiled reference; this is checked
+  by tests/test_oracle_vs_ref.py and by the golden vectors in tests/golden/.
+*/
+#include "oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define EPS   ORC_MAGICK_EPSILON
+#define QR    ORC_QUANTUM_RANGE
+#define QS    ORC_QUANTUM_SCALE
+/* image-private.h:44-51 */
+#define PI_     3.1415926535897932384626433832795028841971693993751058209749445923078164062
+#define PI2_    1.57079632679489661923132169163975144209858469968755
+#define TWOPI_  6.28318530717958647692528676655900576839433879875020
+#define SQ2PI_  2.50662827463100024161235523934010416269302368164062
+
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+  omp_set_num_threads(n > 0 ? n : 1);
+#else
+  (void) n;
+#endif
+}
+
+/* pixel-accessor.h:242-254 PerceptibleReciprocal */
+static double precip(double x)
+{
+  double s = x < 0.0 ? -1.0 : 1.0;
+  if (s * x >= EPS) return 1.0 / x;
+  return s / EPS;
+}
+
+static long clampl(long v, long lo, long hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* ------------------------------------------------------------------ kernels */
+
+/* gem.c:262-300 GetOptimalKernelWidth1D */
+size_t orc_optimal_kernel_width_1d(double radius, double sigma)
+{
+  double g, a, b;
+  size_t width;
+  if (radius > EPS) return (size_t) (2.0 * ceil(radius) + 1.0);
+  g = fabs(sigma);
+  if (g <= EPS) return 3;
+  a = precip(2.0 * g * g);
+  b = precip(SQ2PI_ * g);
+  for (width = 5;; width += 2) {
+    long j = (long) (width - 1) / 2, i;
+    double norm = 0.0, value;
+    for (i = -j; i <= j; i++) norm += exp(-((double) (i * i)) * a) * b;
+    value = exp(-((double) (j * j)) * a) * b / norm;
+    if (value < QS || value < EPS) break;
+  }
+  return width - 2;
+}
+
+/* gem.c:302-342 GetOptimalKernelWidth2D */
+size_t orc_optimal_kernel_width_2d(double radius, double sigma)
+{
+  double g, a, b;
+  size_t width;
+  if (radius > EPS) return (size_t) (2.0 * ceil(radius) + 1.0);
+  g = fabs(sigma);
+  if (g <= EPS) return 3;
+  a = precip(2.0 * g * g);
+  b = precip(TWOPI_ * g * g);
+  for (width = 5;; width += 2) {
+    long j = (long) (width - 1) / 2, u, v;
+    double norm = 0.0, value;
+    for (v = -j; v <= j; v++)
+      for (u = -j; u <= j; u++) norm += exp(-((double) (u * u + v * v)) * a) * b;
+    value = exp(-((double) (j * j)) * a) * b / norm;
+    if (value < QS || value < EPS) break;
+  }
+  return width - 2;
+}
+
+/* morphology.c:2485-2504 CalcKernelMetaData */
+static void kernel_meta(orc_kernel *k)
+{
+  size_t i, n = k->width * k->height;
+  k->minimum = k->maximum = 0.0;
+  k->negative_range = k->positive_range = 0.0;
+  for (i = 0; i < n; i++) {
+    if (fabs(k->values[i]) < EPS) k->values[i] = 0.0;
+    if (k->values[i] < 0) k->negative_range += k->values[i];
+    else k->positive_range += k->values[i];
+    if (k->values[i] < k->minimum) k->minimum = k->values[i];
+    if (k->values[i] > k->maximum) k->maximum = k->values[i];
+  }
+}
+
+/* morphology.c:4571-4632 ScaleKernelInfo(kernel, factor, CorrelateNormalizeValue) */
+static void kernel_scale_correlate_normalize(orc_kernel *k, double factor)
+{
+  size_t i, n = k->width * k->height;
+  double pos = fabs(k->positive_range) >= EPS ? k->positive_range : 1.0;
+  double neg = fabs(k->negative_range) >= EPS ? -k->negative_range : 1.0;
+  pos = factor / pos;
+  neg = factor / neg;
+  for (i = 0; i < n; i++)
+    if (!isnan(k->values[i])) k->values[i] *= (k->values[i] >= 0) ? pos : neg;
+  k->positive_range *= pos;
+  k->negative_range *= neg;
+  k->maximum *= (k->maximum >= 0.0) ? pos : neg;
+  k->minimum *= (k->minimum >= 0.0) ? pos : neg;
+}
+
+static int kernel_alloc(orc_kernel *k, size_t w, size_t h)
+{
+  k->width = w; k->height = h;
+  k->values = (double *) calloc((w * h) != 0 ? w * h : 1, sizeof(double));
+  return k->values ? 0 : -1;
+}
+
+void orc_kernel_free(orc_kernel *k)
+{
+  if (k && k->values) { free(k->values); k->values = NULL; }
+}
+
+int orc_kernel_user(size_t w, size_t h, long x, long y, const double *values, orc_kernel *k)
+{
+  size_t i;
+  memset(k, 0, sizeof(*k));
+  if (kernel_alloc(k, w, h)) return -1;
+  k->x = x; k->y = y; k->type = ORC_K_USER;
+  /* morphology.c:318-339 ParseKernelArray range bookkeeping */
+  k->minimum = 1.79769313486231570e308; k->maximum = -k->minimum;
+  for (i = 0; i < w * h; i++) {
+    k->values[i] = values[i];
+    if (isnan(values[i])) continue;
+    if (values[i] < 0) k->negative_range += values[i]; else k->positive_range += values[i];
+    if (values[i] < k->minimum) k->minimum = values[i];
+    if (values[i] > k->maximum) k->maximum = values[i];
+  }
+  return 0;
+}
+
+/* morphology.c:950-1650 AcquireKernelBuiltIn */
+int orc_kernel_builtin(int type, double rho, double sigma_arg, double xi, double psi, orc_kernel *k)
+{
+  long u, v;
+  size_t i;
+  const double nan_ = sqrt(-1.0);
+  memset(k, 0, sizeof(*k));
+  k->type = type;
+  switch (type) {
+  case ORC_K_GAUSSIAN: {           /* :1045-1139 (Gaussian only) */
+    double sigma = fabs(sigma_arg), A, B;
+    size_t w = rho >= 1.0 ? (size_t) rho * 2 + 1 : orc_optimal_kernel_width_2d(rho, sigma);
+    if (kernel_alloc(k, w, w)) return -1;
+    k->x = k->y = (long) (w - 1) / 2;
+    if (sigma > EPS) {
+      A = 1.0 / (2.0 * sigma * sigma);
+      B = (double) (1.0 / (TWOPI_ * sigma * sigma));
+      for (i = 0, v = -k->y; v <= k->y; v++)
+        for (u = -k->x; u <= k->x; u++, i++)
+          k->values[i] = exp(-((double) (u * u + v * v)) * A) * B;
+    } else
+      k->values[k->x + k->y * (long) w] = 1.0;
+    kernel_meta(k);
+    kernel_scale_correlate_normalize(k, 1.0);
+    return 0;
+  }
+  case ORC_K_BLUR: {               /* :1140-1227; xi = rotation angle */
+    double sigma = fabs(sigma_arg), alpha, beta, angle;
+    size_t w = rho >= 1.0 ? (size_t) rho * 2 + 1 : orc_optimal_kernel_width_1d(rho, sigma);
+    if (kernel_alloc(k, w, 1)) return -1;
+    k->x = (long) (w - 1) / 2; k->y = 0;
+    v = (long) (w * 3 - 1) / 2;                 /* KernelRank 3 */
+    if (sigma > EPS) {
+      sigma *= 3;
+      alpha = 1.0 / (2.0 * sigma * sigma);
+      beta = (double) (1.0 / (SQ2PI_ * sigma));
+      for (u = -v; u <= v; u++)
+        k->values[(u + v) / 3] += exp(-((double) (u * u)) * alpha) * beta;
+    } else
+      k->values[k->x] = 1.0;
+    kernel_meta(k);
+    kernel_scale_correlate_normalize(k, 1.0);
+    /* :4258-4364 RotateKernelInfo for a BlurKernel: only +-90 transposes */
+    angle = fmod(xi, 360.0);
+    if (angle < 0) angle += 360.0;
+    if (337.5 < angle || angle <= 22.5) return 0;
+    if (135.0 < angle && angle <= 225.0) return 0;
+    if (225.0 < angle && angle <= 315.0) angle -= 180;
+    if (45.0 < fmod(angle, 180.0) && fmod(angle, 180.0) <= 135.0) {
+      size_t t = k->width; long tt = k->x;
+      k->width = k->height; k->height = t;
+      k->x = k->y; k->y = tt;
+    }
+    return 0;
+  }
+  case ORC_K_DISK: {               /* :1625-1650; sigma_arg = scale (default 1) */
+    long limit = (long) (rho * rho);
+    size_t w;
+    if (rho < 0.4) { w = 9; limit = 18; } else w = (size_t) fabs(rho) * 2 + 1;
+    if (kernel_alloc(k, w, w)) return -1;
+    k->x = k->y = (long) (w - 1) / 2;
+    for (i = 0, v = -k->y; v <= k->y; v++)
+      for (u = -k->x; u <= k->x; u++, i++)
+        if (u * u + v * v <= limit) k->positive_range += k->values[i] = sigma_arg;
+        else k->values[i] = nan_;
+    k->minimum = k->maximum = sigma_arg;
+    return 0;
+  }
+  case ORC_K_DIAMOND:              /* :1537-1559 */
+  case ORC_K_OCTAGON:              /* :1601-1624 */
+  case ORC_K_PLUS:                 /* :1651-1672 */
+  case ORC_K_CROSS: {              /* :1673-1694 */
+    size_t w;
+    if (rho < 1.0) w = (type == ORC_K_DIAMOND) ? 3 : 5; else w = ((size_t) rho) * 2 + 1;
+    if (kernel_alloc(k, w, w)) return -1;
+    k->x = k->y = (long) (w - 1) / 2;
+    for (i = 0, v = -k->y; v <= k->y; v++)
+      for (u = -k->x; u <= k->x; u++, i++) {
+        int in;
+        if (type == ORC_K_DIAMOND) in = labs(u) + labs(v) <= k->x;
+        else if (type == ORC_K_OCTAGON) in = labs(u) + labs(v) <= k->x + k->x / 2;
+        else if (type == ORC_K_PLUS) in = (u == 0 || v == 0);
+        else in = (u == v || u == -v);
+        if (in) { k->values[i] = sigma_arg; if (type == ORC_K_DIAMOND || type == ORC_K_OCTAGON) k->positive_range += sigma_arg; }
+        else k->values[i] = nan_;
+      }
+    k->minimum = k->maximum = sigma_arg;
+    if (type == ORC_K_PLUS || type == ORC_K_CROSS)
+      k->positive_range = sigma_arg * (k->width * 2.0 - 1.0);
+    return 0;
+  }
+  case ORC_K_SQUARE:               /* :1560-1599 */
+  case ORC_K_RECTANGLE: {
+    double scale;
+    size_t w, h, n;
+    if (type == ORC_K_SQUARE) {
+      w = h = rho < 1.0 ? 3 : (size_t) (2 * rho + 1);
+      k->x = k->y = (long) (w - 1) / 2;
+      scale = sigma_arg;
+    } else {
+      if (rho < 1.0 || sigma_arg < 1.0) return -1;
+      w = (size_t) rho; h = (size_t) sigma_arg;
+      if (xi < 0.0 || xi > (double) w || psi < 0.0 || psi > (double) h) return -1;
+      k->x = (long) xi; k->y = (long) psi;
+      scale = 1.0;
+    }
+    if (kernel_alloc(k, w, h)) return -1;
+    n = w * h;
+    for (i = 0; i < n; i++) k->values[i] = scale;
+    k->minimum = k->maximum = scale;
+    k->positive_range = scale * (long) n;
+    return 0;
+  }
+  default:
+    return -1;
+  }
+}
+
+/* morphology.c:4370-4398: 180 degree rotation == reversal + reflected origin */
+static int kernel_reflect(const orc_kernel *in, orc_kernel *out)
+{
+  size_t n = in->width * in->height, i;
+  *out = *in;
+  out->values = (double *) malloc(n * sizeof(double));
+  if (!out->values) return -1;
+  /* RotateKernelInfo(...,180) is a no-op for these built-in types (:4281-4305) */
+  if (in->type == ORC_K_GAUSSIAN || in->type == ORC_K_DISK || in->type == ORC_K_SQUARE ||
+      in->type == ORC_K_DIAMOND || in->type == ORC_K_PLUS || in->type == ORC_K_CROSS ||
+      in->type == ORC_K_BLUR) {
+    memcpy(out->values, in->values, n * sizeof(double));
+    return 0;
+  }
+  for (i = 0; i < n; i++) out->values[i] = in->values[n - 1 - i];
+  out->x = (long) in->width - in->x - 1;
+  out->y = (long) in->height - in->y - 1;
+  return 0;
+}
+
+/* --------------------------------------------------------- MorphologyPrimitive */
+
+static int is_blend_channel(int ch, int i) { return (ch == 2 || ch == 4) && i != ch - 1; }
+static int update_channels(int ch) { return ch; }   /* image-private.h:147 all carry Update */
+
+/* morphology.c:2566-3227 */
+long orc_morphology_primitive(const float *src, float *dst, size_t w, size_t h, int ch,
+                              int method, const orc_kernel *k, double bias)
+{
+  const long W = (long) w, H = (long) h, kw = (long) k->width, kh = (long) k->height;
+  const int alpha_i = ch - 1;
+  long ox, oy, changed = 0;
+  if (method == ORC_CONVOLVE || method == ORC_DILATE) {   /* reflected (:2612-2626) */
+    ox = kw - k->x - 1; oy = kh - k->y - 1;
+  } else if (method == ORC_ERODE) {
+    ox = k->x; oy = k->y;
+  } else
+    return -1;
+
+  if (method == ORC_CONVOLVE && kw == 1) {
+    /* column fast path, :2654-2807 */
+    long x;
+#pragma omp parallel for schedule(static) reduction(+:changed)
+    for (x = 0; x < W; x++) {
+      long r;
+      for (r = 0; r < H; r++) {
+        int i;
+        for (i = 0; i < ch; i++) {
+          double pixel = bias, gamma = 1.0;
+          size_t count = 0;
+          long v;
+          const double centre = (double) src[((size_t) r * w + x) * ch + i];
+          if (!is_blend_channel(ch, i)) {
+            for (v = 0; v < kh; v++) {
+              double kv = k->values[kh - 1 - v];
+              if (!isnan(kv)) {
+                long yy = clampl(r - oy + v, 0, H - 1);
+                pixel += kv * (double) src[((size_t) yy * w + x) * ch + i];
+                count++;
+              }
+            }
+          } else {
+            gamma = 0.0;
+            for (v = 0; v < kh; v++) {
+              double kv = k->values[kh - 1 - v];
+              if (!isnan(kv)) {
+                long yy = clampl(r - oy + v, 0, H - 1);
+                const float *p = src + ((size_t) yy * w + x) * ch;
+                double alpha = (double) (QS * (double) p[alpha_i]);
+                pixel += alpha * kv * (double) p[i];
+                gamma += alpha * kv;
+                count++;
+              }
+            }
+          }
+          if (fabs(pixel - centre) >= EPS) changed++;
+          gamma = precip(gamma);
+          if (count != 0) gamma *= (double) kh / count;
+          dst[((size_t) r * w + x) * ch + i] = (float) (gamma * pixel);
+        }
+      }
+    }
+    return changed / update_channels(ch);
+  }
+
+  {
+    long y;
+#pragma omp parallel for schedule(static) reduction(+:changed)
+    for (y = 0; y < H; y++) {
+      long x;
+      for (x = 0; x < W; x++) {
+        int i;
+        for (i = 0; i < ch; i++) {
+          const double centre = (double) src[((size_t) y * w + x) * ch + i];
+          double pixel, gamma = 1.0;
+          long u, v;
+          if (method == ORC_CONVOLVE) pixel = bias;
+          else if (method == ORC_DILATE) pixel = 0.0;
+          else pixel = centre;
+          if (method == ORC_CONVOLVE) {
+            const int blend = is_blend_channel(ch, i);
+            if (blend) gamma = 0.0;
+            for (v = 0; v < kh; v++) {
+              long yy = clampl(y - oy + v, 0, H - 1);
+              for (u = 0; u < kw; u++) {
+                double kv = k->values[kw * kh - 1 - (v * kw + u)];
+                if (!isnan(kv)) {
+                  long xx = clampl(x - ox + u, 0, W - 1);
+                  const float *p = src + ((size_t) yy * w + xx) * ch;
+                  if (!blend)
+                    pixel += kv * (double) p[i];
+                  else {
+                    double alpha = (double) (QS * (double) p[alpha_i]);
+                    pixel += alpha * kv * (double) p[i];
+                    gamma += alpha * kv;
+                  }
+                }
+              }
+            }
+          } else if (method == ORC_ERODE) {          /* :2980-3006, not reflected */
+            for (v = 0; v < kh; v++) {
+              long yy = clampl(y - oy + v, 0, H - 1);
+              for (u = 0; u < kw; u++) {
+                double kv = k->values[v * kw + u];
+                if (!isnan(kv) && kv >= 0.5) {
+                  long xx = clampl(x - ox + u, 0, W - 1);
+                  double p = (double) src[((size_t) yy * w + xx) * ch + i];
+                  if (p < pixel) pixel = p;
+                }
+              }
+            }
+          } else {                                   /* Dilate :3007-3036, reflected */
+            for (v = 0; v < kh; v++) {
+              long yy = clampl(y - oy + v, 0, H - 1);
+              for (u = 0; u < kw; u++) {
+                double kv = k->values[kw * kh - 1 - (v * kw + u)];
+                if (!isnan(kv) && kv > 0.5) {
+                  long xx = clampl(x - ox + u, 0, W - 1);
+                  double p = (double) src[((size_t) yy * w + xx) * ch + i];
+                  if (p > pixel) pixel = p;
+                }
+              }
+            }
+          }
+          gamma = precip(gamma);
+          dst[((size_t) y * w + x) * ch + i] = (float) (gamma * pixel);
+          if (fabs(pixel - centre) >= EPS) changed++;
+        }
+      }
+    }
+  }
+  return changed / update_channels(ch);
+}
+
+/* morphology.c:3634-4077 MorphologyApply, compose == None (re-iterate) */
+int orc_morphology_apply(const float *src, float *dst, size_t w, size_t h, int ch,
+                         int method, long iterations, const orc_kernel *kernels, int nk,
+                         double bias)
+{
+  const size_t n = w * h * (size_t) ch;
+  size_t kernel_limit, stage_limit = 1;
+  float *cur, *work, *tmp;
+  orc_kernel *refl = NULL;
+  int kn, rc = 0;
+  if (iterations == 0) return -1;
+  kernel_limit = iterations < 0 ? (w > h ? w : h) : (size_t) iterations;
+  switch (method) {
+    case ORC_SMOOTH: stage_limit = 4; break;
+    case ORC_OPEN: case ORC_CLOSE: stage_limit = 2; break;
+    case ORC_CONVOLVE: case ORC_CORRELATE: case ORC_ERODE: case ORC_DILATE: break;
+    default: return -1;
+  }
+  cur = (float *) malloc(n * sizeof(float));
+  work = (float *) malloc(n * sizeof(float));
+  if (!cur || !work) { free(cur); free(work); return -1; }
+  memcpy(cur, src, n * sizeof(float));
+  if (method == ORC_CORRELATE || method == ORC_CLOSE || method == ORC_SMOOTH) {
+    refl = (orc_kernel *) calloc((size_t) nk, sizeof(orc_kernel));
+    for (kn = 0; kn < nk; kn++) kernel_reflect(&kernels[kn], &refl[kn]);
+  }
+  for (kn = 0; kn < nk && rc == 0; kn++) {
+    size_t stage;
+    for (stage = 1; stage <= stage_limit && rc == 0; stage++) {
+      const orc_kernel *kk = &kernels[kn];
+      int prim = method;
+      size_t loop = 0;
+      long changed = 1;
+      switch (method) {                       /* :3813-3893 */
+        case ORC_OPEN: prim = stage == 2 ? ORC_DILATE : ORC_ERODE; break;
+        case ORC_CLOSE: kk = &refl[kn]; prim = stage == 2 ? ORC_ERODE : ORC_DILATE; break;
+        case ORC_SMOOTH:
+          if (stage == 1) prim = ORC_ERODE;
+          else if (stage == 2) prim = ORC_DILATE;
+          else if (stage == 3) { kk = &refl[kn]; prim = ORC_DILATE; }
+          else { kk = &refl[kn]; prim = ORC_ERODE; }
+          break;
+        case ORC_CORRELATE: kk = &refl[kn]; prim = ORC_CONVOLVE; break;
+        default: break;
+      }
+      while (loop < kernel_limit && changed > 0) {      /* :3919-3962 */
+        loop++;
+        changed = orc_morphology_primitive(cur, work, w, h, ch, prim, kk, bias);
+        if (changed < 0) { rc = -1; break; }
+        tmp = cur; cur = work; work = tmp;
+      }
+    }
+  }
+  if (rc == 0) memcpy(dst, cur, n * sizeof(float));
+  if (refl) { for (kn = 0; kn < nk; kn++) orc_kernel_free(&refl[kn]); free(refl); }
+  free(cur); free(work);
+  return rc;
+}
+
+/* effect.c:765-796: "blur:RxS;blur:RxS+90" -> ConvolveImage */
+int orc_blur(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma)
+{
+  orc_kernel k[2];
+  int rc;
+  if (orc_kernel_builtin(ORC_K_BLUR, radius, sigma, 0.0, 0.0, &k[0])) return -1;
+  if (orc_kernel_builtin(ORC_K_BLUR, radius, sigma, 90.0, 0.0, &k[1])) { orc_kernel_free(&k[0]); return -1; }
+  rc = orc_morphology_apply(src, dst, w, h, ch, ORC_CONVOLVE, 1, k, 2, 0.0);
+  orc_kernel_free(&k[0]); orc_kernel_free(&k[1]);
+  return rc;
+}
+
+/* effect.c:1709-1735: "gaussian:RxS" */
+int orc_gaussian_blur(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma)
+{
+  orc_kernel k;
+  int rc;
+  if (orc_kernel_builtin(ORC_K_GAUSSIAN, radius, sigma, 0.0, 0.0, &k)) return -1;
+  rc = orc_morphology_apply(src, dst, w, h, ch, ORC_CONVOLVE, 1, &k, 1, 0.0);
+  orc_kernel_free(&k);
+  return rc;
+}
+
+/* effect.c:4256-4391 */
+int orc_unsharp(const float *src, float *dst, size_t w, size_t h, int ch,
+                double radius, double sigma, double gain, double threshold)
+{
+  const size_t n = w * h * (size_t) ch;
+  const double qt = (double) QR * threshold;
+  long i;
+  if (orc_blur(src, dst, w, h, ch, radius, sigma)) return -1;
+#pragma omp parallel for schedule(static)
+  for (i = 0; i < (long) n; i++) {
+    double pixel = (double) src[i] - (double) dst[i];
+    if (fabs(2.0 * pixel) < qt) pixel = (double) src[i];
+    else pixel = (double) src[i] + gain * pixel;
+    dst[i] = (float) pixel;
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------ resize */
+
+enum { FN_BOX, FN_TRIANGLE, FN_CUBICBC, FN_HANN, FN_HAMMING, FN_BLACKMAN, FN_GAUSSIAN,
+       FN_QUADRATIC, FN_SINC, FN_SINCFAST, FN_WELCH, FN_BOHMAN, FN_LAGRANGE, FN_COSINE,
+       FN_CUBICSPLINE, FN_MKS2013, FN_MKS2021, FN_UNSUPPORTED };
+
+typedef struct { int fn; double support, scale, B, C; } fn_entry;
+
+/* resize.c:888-942 `filters[]` (function, support, window scale, B, C) */
+static const fn_entry fn_table[ORC_F_SENTINEL] = {
+  { FN_BOX, 0.5, 0.5, 0, 0 }, { FN_BOX, 0.0, 0.5, 0, 0 }, { FN_BOX, 0.5, 0.5, 0, 0 },
+  { FN_TRIANGLE, 1.0, 1.0, 0, 0 }, { FN_CUBICBC, 1.0, 1.0, 0, 0 }, { FN_HANN, 1.0, 1.0, 0, 0 },
+  { FN_HAMMING, 1.0, 1.0, 0, 0 }, { FN_BLACKMAN, 1.0, 1.0, 0, 0 }, { FN_GAUSSIAN, 2.0, 1.5, 0, 0 },
+  { FN_QUADRATIC, 1.5, 1.5, 0, 0 }, { FN_CUBICBC, 2.0, 2.0, 1.0, 0.0 }, { FN_CUBICBC, 2.0, 1.0, 0.0, 0.5 },
+  { FN_CUBICBC, 2.0, 8.0 / 7.0, 1. / 3., 1. / 3. }, { FN_UNSUPPORTED, 3.0, 1.2196698912665045, 0, 0 },
+  { FN_SINC, 4.0, 1.0, 0, 0 }, { FN_SINCFAST, 4.0, 1.0, 0, 0 }, { FN_UNSUPPORTED, 1.0, 1.0, 0, 0 },
+  { FN_WELCH, 1.0, 1.0, 0, 0 }, { FN_CUBICBC, 2.0, 2.0, 1.0, 0.0 }, { FN_BOHMAN, 1.0, 1.0, 0, 0 },
+  { FN_TRIANGLE, 1.0, 1.0, 0, 0 }, { FN_LAGRANGE, 2.0, 1.0, 0, 0 }, { FN_SINCFAST, 3.0, 1.0, 0, 0 },
+  { FN_SINCFAST, 3.0, 1.0, 0, 0 }, { FN_SINCFAST, 2.0, 1.0, 0, 0 }, { FN_SINCFAST, 2.0, 1.0, 0, 0 },
+  { FN_CUBICBC, 2.0, 1.1685777620836932, 0.37821575509399867, 0.31089212245300067 },
+  { FN_CUBICBC, 2.0, 1.105822933719019, 0.2620145123990142, 0.3689927438004929 },
+  { FN_COSINE, 1.0, 1.0, 0, 0 }, { FN_CUBICBC, 2.0, 2.0, 1.0, 0.0 }, { FN_SINCFAST, 3.0, 1.0, 0, 0 },
+  { FN_CUBICSPLINE, 2.0, 0.5, 0, 0 }, { FN_MKS2013, 2.5, 1.0, 0, 0 }, { FN_MKS2021, 4.5, 1.0, 0, 0 },
+};
+
+/* resize.c:835-876 `mapping[]`: filter -> (weighting filter, window filter) */
+static const int map_filter[ORC_F_SENTINEL] = {
+  ORC_F_UNDEFINED, ORC_F_POINT, ORC_F_BOX, ORC_F_TRIANGLE, ORC_F_HERMITE, ORC_F_SINCFAST, ORC_F_SINCFAST,
+  ORC_F_SINCFAST, ORC_F_GAUSSIAN, ORC_F_QUADRATIC, ORC_F_CUBIC, ORC_F_CATROM, ORC_F_MITCHELL, ORC_F_JINC,
+  ORC_F_SINC, ORC_F_SINCFAST, ORC_F_SINCFAST, ORC_F_LANCZOS, ORC_F_SINCFAST, ORC_F_SINCFAST, ORC_F_SINCFAST,
+  ORC_F_LAGRANGE, ORC_F_LANCZOS, ORC_F_LANCZOS_SHARP, ORC_F_LANCZOS2, ORC_F_LANCZOS2_SHARP, ORC_F_ROBIDOUX,
+  ORC_F_ROBIDOUX_SHARP, ORC_F_LANCZOS, ORC_F_SPLINE, ORC_F_LANCZOS_RADIUS, ORC_F_CUBIC_SPLINE,
+  ORC_F_MKS2013, ORC_F_MKS2021 };
+static const int map_window[ORC_F_SENTINEL] = {
+  ORC_F_BOX, ORC_F_BOX, ORC_F_BOX, ORC_F_BOX, ORC_F_BOX, ORC_F_HANN, ORC_F_HAMMING,
+  ORC_F_BLACKMAN, ORC_F_BOX, ORC_F_BOX, ORC_F_BOX, ORC_F_BOX, ORC_F_BOX, ORC_F_BOX,
+  ORC_F_BOX, ORC_F_BOX, ORC_F_KAISER, ORC_F_WELCH, ORC_F_CUBIC, ORC_F_BOHMAN, ORC_F_TRIANGLE,
+  ORC_F_BOX, ORC_F_LANCZOS, ORC_F_LANCZOS_SHARP, ORC_F_LANCZOS2, ORC_F_LANCZOS2_SHARP, ORC_F_BOX,
+  ORC_F_BOX, ORC_F_COSINE, ORC_F_BOX, ORC_F_LANCZOS, ORC_F_BOX, ORC_F_BOX, ORC_F_BOX };
+
+typedef struct {
+  int filter_fn, window_fn;
+  double support, window_support, scale, blur, coef[7];
+} rfilter;
+
+/* resize.c:803-1226 AcquireResizeFilter with no "filter:*" artifacts, not cylindrical */
+static int rfilter_init(rfilter *rf, int filter)
+{
+  int ft, wt;
+  double B = 0.0, C = 0.0;
+  if (filter <= ORC_F_UNDEFINED || filter >= ORC_F_SENTINEL) return -1;
+  ft = map_filter[filter]; wt = map_window[filter];
+  memset(rf, 0, sizeof(*rf));
+  rf->blur = 1.0;
+  rf->filter_fn = fn_table[ft].fn;
+  rf->support = fn_table[ft].support;
+  rf->window_fn = fn_table[wt].fn;
+  rf->scale = fn_table[wt].scale;
+  if (rf->filter_fn == FN_UNSUPPORTED || rf->window_fn == FN_UNSUPPORTED) return -1;
+  if (ft == ORC_F_LANCZOS_SHARP) rf->blur *= 0.9812505644269356;       /* :1064-1076 */
+  if (ft == ORC_F_LANCZOS2_SHARP) rf->blur *= 0.9549963639785485;
+  if (rf->filter_fn == FN_GAUSSIAN || rf->window_fn == FN_GAUSSIAN) {   /* :1083-1097 */
+    double value = 0.5;
+    rf->coef[0] = value;
+    rf->coef[1] = precip(2.0 * value * value);
+    rf->coef[2] = precip(TWOPI_ * value * value);
+  }
+  if (rf->blur < EPS) rf->blur = EPS;
+  rf->window_support = rf->support;
+  rf->scale *= precip(rf->window_support);                              /* :1177 */
+  if (rf->filter_fn == FN_CUBICBC || rf->window_fn == FN_CUBICBC) {     /* :1181-1226 */
+    B = fn_table[ft].B; C = fn_table[ft].C;
+    if (fn_table[wt].fn == FN_CUBICBC) { B = fn_table[wt].B; C = fn_table[wt].C; }
+    {
+      const double twoB = B + B;
+      rf->coef[0] = 1.0 - (1.0 / 3.0) * B;
+      rf->coef[1] = -3.0 + twoB + C;
+      rf->coef[2] = 2.0 - 1.5 * B - C;
+      rf->coef[3] = (4.0 / 3.0) * B + 4.0 * C;
+      rf->coef[4] = -8.0 * C - twoB;
+      rf->coef[5] = B + 5.0 * C;
+      rf->coef[6] = (-1.0 / 6.0) * B - C;
+    }
+  }
+  return 0;
+}
+
+/* resize.c:493-587 SincFast, Q16 branch (:547-563) */
+static double sinc_fast(double x)
+{
+  static const double c[10] = {
+    0.173611107357320220183368594093166520811e-2L, -0.384240921114946632192116762889211361285e-3L,
+    0.394201182359318128221229891724947048771e-4L, -0.250963301609117217660068889165550534856e-5L,
+    0.111902032818095784414237782071368805120e-6L, -0.372895101408779549368465614321137048875e-8L,
+    0.957694196677572570319816780188718518330e-10L, -0.187208577776590710853865174371617338991e-11L,
+    0.253524321426864752676094495396308636823e-13L, -0.177084805010701112639035485248501049364e-15L };
+  if (x > 4.0) {
+    const double alpha = (double) (PI_ * x);
+    return sin((double) alpha) / alpha;
+  }
+  {
+    const double xx = x * x;
+    const double p = c[0] + xx * (c[1] + xx * (c[2] + xx * (c[3] + xx * (c[4] + xx * (c[5] + xx *
+                     (c[6] + xx * (c[7] + xx * (c[8] + xx * c[9]))))))));
+    return (xx - 1.0) * (xx - 4.0) * (xx - 9.0) * (xx - 16.0) * p;
+  }
+}
+
+static double eval_fn(int fn, double x, const rfilter *rf)
+{
+  switch (fn) {
+  case FN_BOX: return 1.0;                                              /* :166-178 */
+  case FN_TRIANGLE: return x < 1.0 ? 1.0 - x : 0.0;                     /* :589-602 */
+  case FN_CUBICBC:                                                      /* :209-247 */
+    if (x < 1.0) return rf->coef[0] + x * (x * (rf->coef[1] + x * rf->coef[2]));
+    if (x < 2.0) return rf->coef[3] + x * (rf->coef[4] + x * (rf->coef[5] + x * rf->coef[6]));
+    return 0.0;
+  case FN_HANN: { const double c = cos((double) (PI_ * x)); return 0.5 + 0.5 * c; }      /* :322-333 */
+  case FN_HAMMING: { const double c = cos((double) (PI_ * x)); return 0.54 + 0.46 * c; } /* :335-346 */
+  case FN_BLACKMAN: { const double c = cos((double) (PI_ * x)); return 0.34 + c * (0.5 + c * 0.16); } /* :132-145 */
+  case FN_GAUSSIAN: return exp((double) (-rf->coef[1] * x * x));        /* :288-320 */
+  case FN_QUADRATIC:                                                    /* :460-474 */
+    if (x < 0.5) return 0.75 - x * x;
+    if (x < 1.5) return 0.5 * (x - 1.5) * (x - 1.5);
+    return 0.0;
+  case FN_SINC:                                                         /* :476-491 */
+    if (x != 0.0) { const double a = (double) (PI_ * x); return sin((double) a) / a; }
+    return 1.0;
+  case FN_SINCFAST: return sinc_fast(x);
+  case FN_WELCH: return x < 1.0 ? 1.0 - x * x : 0.0;                    /* :604-615 */
+  case FN_BOHMAN: {                                                     /* :147-164 */
+    const double c = cos((double) (PI_ * x));
+    const double s = sqrt(1.0 - c * c);
+    return (1.0 - x) * c + (1.0 / PI_) * s;
+  }
+  case FN_COSINE: return cos((double) (PI2_ * x));                      /* :180-190 */
+  case FN_LAGRANGE: {                                                   /* :388-420 */
+    double value;
+    long i, n, order;
+    if (x > rf->support) return 0.0;
+    order = (long) (2.0 * rf->window_support);
+    n = (long) (rf->window_support + x);
+    value = 1.0f;
+    for (i = 0; i < order; i++)
+      if (i != n) value *= (n - i - x) / (n - i);
+    return value;
+  }
+  case FN_CUBICSPLINE:                                                  /* :249-286, 2 lobes */
+    if (x < 1.0) return ((x - 9.0 / 5.0) * x - 1.0 / 5.0) * x + 1.0;
+    if (x < 2.0) return ((-1.0 / 3.0 * (x - 1.0) + 4.0 / 5.0) * (x - 1.0) - 7.0 / 15.0) * (x - 1.0);
+    return 0.0;
+  case FN_MKS2013:                                                      /* :422-438 */
+    if (x < 0.5) return 0.625 + 1.75 * (0.5 - x) * (0.5 + x);
+    if (x < 1.5) return (1.0 - x) * (1.75 - x);
+    if (x < 2.5) return -0.125 * (2.5 - x) * (2.5 - x);
+    return 0.0;
+  case FN_MKS2021:                                                      /* :440-458 */
+    if (x < 0.5) return 577.0 / 576.0 - 239.0 / 144.0 * x * x;
+    if (x < 1.5) return 35.0 / 36.0 * (x - 1.0) * (x - 239.0 / 140.0);
+    if (x < 2.5) return 1.0 / 6.0 * (x - 2.0) * (65.0 / 24.0 - x);
+    if (x < 3.5) return 1.0 / 36.0 * (x - 3.0) * (x - 3.75);
+    if (x < 4.5) return -1.0 / 288.0 * (x - 4.5) * (x - 4.5);
+    return 0.0;
+  default: return 0.0;
+  }
+}
+
+/* resize.c:1690-1714 GetResizeFilterWeight */
+static double rfilter_weight(const rfilter *rf, double x)
+{
+  double scale, xb = fabs((double) x) * precip(rf->blur);
+  if (rf->window_support < EPS || rf->window_fn == FN_BOX) scale = 1.0;
+  else scale = eval_fn(rf->window_fn, xb * rf->scale, rf);
+  return scale * eval_fn(rf->filter_fn, xb, rf);
+}
+
+double orc_filter_weight(int f, double x)
+{
+  rfilter rf;
+  if (rfilter_init(&rf, f)) return NAN;
+  return rfilter_weight(&rf, x);
+}
+
+double orc_filter_support(int f)
+{
+  rfilter rf;
+  if (rfilter_init(&rf, f)) return NAN;
+  return rf.support * rf.blur;                       /* :1656-1661 */
+}
+
+/* One axis of resize.c:3333-3547 (HorizontalFilter) / :3549-3759 (VerticalFilter).
+   axis 0: filter along x (src w -> dst ow, rows unchanged); axis 1: along y. */
+static int resize_axis(const rfilter *rf, const float *src, size_t w, size_t h, int ch,
+                       float *dst, size_t on, double factor, int axis)
+{
+  const long in_n = axis == 0 ? (long) w : (long) h;
+  const size_t ow = axis == 0 ? on : w, oh = axis == 0 ? h : on;
+  const long lines = axis == 0 ? (long) h : (long) w;
+  const int alpha_i = ch - 1;
+  double scale = fmax(1.0 / factor + EPS, 1.0);
+  double support = scale * (rf->support * rf->blur);
+  long o;
+  if (support < 0.5) { support = 0.5; scale = 1.0; }
+  scale = precip(scale);
+#pragma omp parallel for schedule(static)
+  for (o = 0; o < (long) on; o++) {
+    double bisect = (double) (o + 0.5) / factor + EPS;
+    long start = (long) fmax(bisect - support + 0.5, 0.0);
+    long stop = (long) fmin(bisect + support + 0.5, (double) in_n);
+    long n = stop - start, j, l;
+    double density = 0.0;
+    double *wt;
+    if (n <= 0) continue;
+    wt = (double *) malloc((size_t) n * sizeof(double));
+    for (j = 0; j < n; j++) {
+      wt[j] = rfilter_weight(rf, scale * ((double) (start + j) - bisect + 0.5));
+      density += wt[j];
+    }
+    if (density != 0.0 && density != 1.0) {
+      density = precip(density);
+      for (j = 0; j < n; j++) wt[j] *= density;
+    }
+    for (l = 0; l < lines; l++) {
+      int i;
+      for (i = 0; i < ch; i++) {
+        double pixel = 0.0;
+#define SRC(jj) (axis == 0 ? src + ((size_t) l * w + (size_t) (start + (jj))) * ch \
+                           : src + ((size_t) (start + (jj)) * w + (size_t) l) * ch)
+        float *q = axis == 0 ? dst + ((size_t) l * ow + (size_t) o) * ch
+                             : dst + ((size_t) o * ow + (size_t) l) * ch;
+        (void) oh;
+        if (!is_blend_channel(ch, i)) {
+          for (j = 0; j < n; j++) {
+            double alpha = wt[j];
+            pixel += alpha * (double) SRC(j)[i];
+          }
+          q[i] = (float) pixel;
+        } else {
+          double gamma = 0.0;
+          for (j = 0; j < n; j++) {
+            const float *p = SRC(j);
+            double alpha = wt[j] * QS * (double) p[alpha_i];
+            pixel += alpha * (double) p[i];
+            gamma += alpha;
+          }
+          gamma = precip(gamma);
+          q[i] = (float) (gamma * pixel);
+        }
+#undef SRC
+      }
+    }
+    free(wt);
+  }
+  return 0;
+}
+
+/* resize.c:3761-3874 ResizeImage */
+int orc_resize(const float *src, size_t w, size_t h, int ch,
+               float *dst, size_t ow, size_t oh, int filter)
+{
+  rfilter rf;
+  double xf, yf;
+  float *tmp;
+  int ft = ORC_F_LANCZOS;
+  if (ow == 0 || oh == 0) return -1;
+  if (ow == w && oh == h && filter == ORC_F_UNDEFINED) {
+    memcpy(dst, src, w * h * (size_t) ch * sizeof(float));
+    return 0;
+  }
+  xf = (double) (ow * precip((double) w));
+  yf = (double) (oh * precip((double) h));
+  if (filter != ORC_F_UNDEFINED) ft = filter;
+  else if (xf == 1.0 && yf == 1.0) ft = ORC_F_POINT;
+  else if ((ch == 2 || ch == 4) || (xf * yf) > 1.0) ft = ORC_F_MITCHELL;
+  if (rfilter_init(&rf, ft)) return -1;
+  if (xf > yf) {
+    tmp = (float *) malloc(ow * h * (size_t) ch * sizeof(float));
+    if (!tmp) return -1;
+    resize_axis(&rf, src, w, h, ch, tmp, ow, xf, 0);
+    resize_axis(&rf, tmp, ow, h, ch, dst, oh, yf, 1);
+  } else {
+    tmp = (float *) malloc(w * oh * (size_t) ch * sizeof(float));
+    if (!tmp) return -1;
+    resize_axis(&rf, src, w, h, ch, tmp, oh, yf, 1);
+    resize_axis(&rf, tmp, w, oh, ch, dst, ow, xf, 0);
+  }
+  free(tmp);
+  return 0;
+}
+
+/* -------------------------------------------------------------- colorspace */
+
+/* pixel.c:260-316 DecodeGamma: x^2.4 via Chebyshev on the frexp mantissa */
+static double decode_gamma(double x)
+{
+  static const double cf[9] = { 1.7917488588043277509, 0.82045614371976854984, 0.027694100686325412819,
+    -0.00094244335181762134018, 0.000064355540911469709545, -5.7224404636060757485e-06,
+    5.8767669437311184313e-07, -6.6139920053589721168e-08, 7.9323242696227458163e-09 };
+  static const double p2[5] = { 1.0, 2.6390158215457883983, 6.9644045063689921093,
+    1.8379173679952558018e+01, 4.8502930128332728543e+01 };
+  double t[9], p;
+  int e, quot, rem, i;
+  t[0] = 1.0;
+  t[1] = 4.0 * frexp(x, &e) - 3.0;
+  for (i = 2; i < 9; i++) t[i] = 2.0 * t[1] * t[i - 1] - t[i - 2];
+  p = cf[0] * t[0] + cf[1] * t[1] + cf[2] * t[2] + cf[3] * t[3] + cf[4] * t[4] + cf[5] * t[5] +
+      cf[6] * t[6] + cf[7] * t[7] + cf[8] * t[8];
+  quot = (e - 1) / 5; rem = (e - 1) % 5;
+  if (rem < 0) { quot -= 1; rem += 5; }
+  return x * ldexp(p2[rem] * p, 7 * quot);
+}
+
+/* pixel.c:318-324 */
+static double decode_pixel_gamma(double pixel)
+{
+  if (pixel <= (0.0404482362771076 * (double) QR)) return pixel / 12.92;
+  return (double) QR * decode_gamma((double) (QS * pixel + 0.055) / 1.055);
+}
+
+/* pixel.c:380-443 EncodeGamma: x^(1/2.4) */
+static double encode_gamma(double x)
+{
+  static const double cf[9] = { 1.1758200232996901923, 0.16665763094889061230, -0.0083154894939042125035,
+    0.00075187976780420279038, -0.000083240178519391795367, 0.000010229209410070008679,
+    -1.3400466409860246e-06, 1.8333422241635376682e-07, -2.5878596761348859722e-08 };
+  static const double p2[12] = { 1.0, 1.3348398541700343678, 1.7817974362806785482, 2.3784142300054420538,
+    3.1748021039363991669, 4.2378523774371812394, 5.6568542494923805819, 7.5509945014535482244,
+    1.0079368399158985525e1, 1.3454342644059433809e1, 1.7959392772949968275e1, 2.3972913230026907883e1 };
+  double t[9], p;
+  int e, quot, rem, i;
+  t[0] = 1.0;
+  t[1] = 4.0 * frexp(x, &e) - 3.0;
+  for (i = 2; i < 9; i++) t[i] = 2.0 * t[1] * t[i - 1] - t[i - 2];
+  p = cf[0] * t[0] + cf[1] * t[1] + cf[2] * t[2] + cf[3] * t[3] + cf[4] * t[4] + cf[5] * t[5] +
+      cf[6] * t[6] + cf[7] * t[7] + cf[8] * t[8];
+  quot = (e - 1) / 12; rem = (e - 1) % 12;
+  if (rem < 0) { quot -= 1; rem += 12; }
+  return ldexp(p2[rem] * p, 5 * quot);
+}
+
+/* pixel.c:445-451 */
+static double encode_pixel_gamma(double pixel)
+{
+  if (pixel <= (0.0031306684425005883 * (double) QR)) return 12.92 * pixel;
+  return (double) QR * (1.055 * encode_gamma((double) QS * pixel) - 0.055);
+}
+
+#define ILL_X 0.95047        /* colorspace-private.h:32-46, D65 */
+#define ILL_Y 1.00000
+#define ILL_Z 1.08883
+#define CIE_EPS (216.0 / 24389.0)
+#define CIE_K   (24389.0 / 27.0)
+
+/* colorspace-private.h:759-779 */
+static void rgb_to_xyz(double red, double green, double blue, double *X, double *Y, double *Z)
+{
+  double r = QS * decode_pixel_gamma(red), g = QS * decode_pixel_gamma(green), b = QS * decode_pixel_gamma(blue);
+  *X = (0.4123955889674142161 * r) + (0.3575834307637148171 * g) + (0.1804926473817015735 * b);
+  *Y = (0.2125862307855955516 * r) + (0.7151703037034108499 * g) + (0.07220049864333622685 * b);
+  *Z = (0.01929721549174694484 * r) + (0.1191838645808485318 * g) + (0.9504971251315797660 * b);
+}
+
+/* colorspace-private.h:72-94 */
+static void xyz_to_rgb(double X, double Y, double Z, double *red, double *green, double *blue)
+{
+  double r = (3.240969941904521 * X) + (-1.537383177570093 * Y) + (-0.498610760293 * Z);
+  double g = (-0.96924363628087 * X) + (1.87596750150772 * Y) + (0.041555057407175 * Z);
+  double b = (0.055630079696993 * X) + (-0.20397695888897 * Y) + (1.056971514242878 * Z);
+  /* MagickMin is a plain (x<y?x:y) macro */
+  double m = r < (g < b ? g : b) ? r : (g < b ? g : b);
+  if (m < 0.0) { r -= m; g -= m; b -= m; }
+  *red = encode_pixel_gamma((double) QR * r);
+  *green = encode_pixel_gamma((double) QR * g);
+  *blue = encode_pixel_gamma((double) QR * b);
+}
+
+/* colorspace-private.h:1066-1089 */
+static void xyz_to_lab(double X, double Y, double Z, double *L, double *a, double *b)
+{
+  double x, y, z;
+  if ((X / ILL_X) > CIE_EPS) x = pow(X / ILL_X, 1.0 / 3.0); else x = (CIE_K * X / ILL_X + 16.0) / 116.0;
+  if ((Y / ILL_Y) > CIE_EPS) y = pow(Y / ILL_Y, 1.0 / 3.0); else y = (CIE_K * Y / ILL_Y + 16.0) / 116.0;
+  if ((Z / ILL_Z) > CIE_EPS) z = pow(Z / ILL_Z, 1.0 / 3.0); else z = (CIE_K * Z / ILL_Z + 16.0) / 116.0;
+  *L = ((116.0 * y) - 16.0) / 100.0;
+  *a = (500.0 * (x - y)) / 255.0 + 0.5;
+  *b = (200.0 * (y - z)) / 255.0 + 0.5;
+}
+
+/* colorspace-private.h:531-557 */
+static void lab_to_xyz(double L, double a, double b, double *X, double *Y, double *Z)
+{
+  double x, y, z;
+  y = (L + 16.0) / 116.0;
+  x = y + a / 500.0;
+  z = y - b / 200.0;
+  if ((x * x * x) > CIE_EPS) x = (x * x * x); else x = (116.0 * x - 16.0) / CIE_K;
+  if (L > (CIE_K * CIE_EPS)) y = (y * y * y); else y = L / CIE_K;
+  if ((z * z * z) > CIE_EPS) z = (z * z * z); else z = (116.0 * z - 16.0) / CIE_K;
+  *X = ILL_X * x; *Y = ILL_Y * y; *Z = ILL_Z * z;
+}
+
+/* colorspace.c:1751-1783; forward generic branch :958-1054, linear :1164-1225;
+   inverse generic :2296-2390, linear RGB->sRGB :2494-2550 */
+int orc_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to)
+{
+  const long n = (long) (w * h);
+  long i;
+  if (ch < 3) return -1;
+  if (from == to) return 0;
+  if (from != ORC_CS_SRGB) {
+    if (from != ORC_CS_LAB && from != ORC_CS_XYZ && from != ORC_CS_RGB) return -1;
+#pragma omp parallel for schedule(static)
+    for (i = 0; i < n; i++) {
+      float *q = buf + (size_t) i * ch;
+      double r, g, b;
+      if (from == ORC_CS_RGB) {
+        r = encode_pixel_gamma((double) q[0]);
+        g = encode_pixel_gamma((double) q[1]);
+        b = encode_pixel_gamma((double) q[2]);
+      } else {
+        double X = QS * q[0], Y = QS * q[1], Z = QS * q[2];
+        if (from == ORC_CS_LAB) {
+          double x2, y2, z2;
+          lab_to_xyz(100.0 * X, 255.0 * (Y - 0.5), 255.0 * (Z - 0.5), &x2, &y2, &z2);
+          X = x2; Y = y2; Z = z2;
+        }
+        xyz_to_rgb(X, Y, Z, &r, &g, &b);
+      }
+      q[0] = (float) r; q[1] = (float) g; q[2] = (float) b;
+    }
+  }
+  if (to == ORC_CS_SRGB) return 0;
+  if (to != ORC_CS_LAB && to != ORC_CS_XYZ && to != ORC_CS_RGB) return -1;
+#pragma omp parallel for schedule(static)
+  for (i = 0; i < n; i++) {
+    float *q = buf + (size_t) i * ch;
+    if (to == ORC_CS_RGB) {
+      double r = decode_pixel_gamma((double) q[0]), g = decode_pixel_gamma((double) q[1]),
+             b = decode_pixel_gamma((double) q[2]);
+      q[0] = (float) r; q[1] = (float) g; q[2] = (float) b;
+    } else {
+      double X, Y, Z;
+      rgb_to_xyz((double) q[0], (double) q[1], (double) q[2], &X, &Y, &Z);
+      if (to == ORC_CS_LAB) {
+        double L, a, b;
+        xyz_to_lab(X, Y, Z, &L, &a, &b);
+        X = L; Y = a; Z = b;
+      }
+      q[0] = (float) ((double) QR * X); q[1] = (float) ((double) QR * Y); q[2] = (float) ((double) QR * Z);
+    }
+  }
+  return 0;
+}
