@@ -1,0 +1,253 @@
+"""Host-side mirror of the MagickCore entry points of the hot path.
+
+Same names, argument meaning and error behaviour as the reference operators
+(MagickCore/effect.c, morphology.c, resize.c, colorspace.c), on top of the C-ABI in
+include/magick_b200.h:
+
+    BlurImage, GaussianBlurImage, ConvolveImage, UnsharpMaskImage   effect.c:765/1709/1170/4256
+    MorphologyImage, AcquireKernelInfo                              morphology.c:4129/485
+    ResizeImage                                                     resize.c:3761
+    TransformImageColorspace                                        colorspace.c:1751
+
+An `Image` wraps the pixel cache: an (rows, columns, channels) float32 array of raw
+Quantum values (0..65535), either a NumPy array (host; every call stages through
+HBM and back -- the end-to-end path) or a CUDA torch tensor (device-resident; the
+kernels run on torch's current stream and the result stays in HBM).
+
+Operators that return `Image *` in the reference return a NEW Image here and never
+modify their input; TransformImageColorspace works in place and returns True, like
+the reference.  Failures raise MagickB200Error (the reference returns NULL / MagickFalse
+and fills an ExceptionInfo); MB200_EUNSUPPORTED is the "decline" signal on which the
+MagickCore shim falls back to the stock CPU path.  Nothing here computes pixels on
+the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Union
+
+import numpy as np
+
+from . import _lib
+from ._lib import KernelPtr, MagickB200Error, check
+
+# MagickCore/morphology.h:69-99
+UndefinedMorphology, ConvolveMorphology, CorrelateMorphology, ErodeMorphology, DilateMorphology = 0, 1, 2, 3, 4
+OpenMorphology, CloseMorphology, SmoothMorphology = 8, 9, 12
+EdgeInMorphology, EdgeOutMorphology, EdgeMorphology, TopHatMorphology, BottomHatMorphology = 13, 14, 15, 16, 17
+
+# MagickCore/resample.h:32-69
+(UndefinedFilter, PointFilter, BoxFilter, TriangleFilter, HermiteFilter, HannFilter, HammingFilter,
+ BlackmanFilter, GaussianFilter, QuadraticFilter, CubicFilter, CatromFilter, MitchellFilter, JincFilter,
+ SincFilter, SincFastFilter, KaiserFilter, WelchFilter, ParzenFilter, BohmanFilter, BartlettFilter,
+ LagrangeFilter, LanczosFilter, LanczosSharpFilter, Lanczos2Filter, Lanczos2SharpFilter, RobidouxFilter,
+ RobidouxSharpFilter, CosineFilter, SplineFilter, LanczosRadiusFilter, CubicSplineFilter,
+ MagicKernelSharp2013Filter, MagicKernelSharp2021Filter, SentinelFilter) = range(35)
+
+# MagickCore/colorspace.h:27-67
+LabColorspace, RGBColorspace, sRGBColorspace, XYZColorspace = 11, 21, 23, 26
+
+# kernel types of include/magick_b200.h
+(UserDefinedKernel, BlurKernel, GaussianKernel, DiskKernel, SquareKernel, DiamondKernel, OctagonKernel,
+ PlusKernel, CrossKernel, RectangleKernel, UnityKernel, DoGKernel, LoGKernel, BinomialKernel) = range(14)
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class Image:
+    """The pixel cache of one image: rows x columns x channels float32 Quantum."""
+
+    def __init__(self, pixels, colorspace: int = sRGBColorspace):
+        if _is_torch(pixels):
+            import torch
+            if not pixels.is_cuda:
+                raise ValueError("torch pixel caches must live on a CUDA device (use NumPy for host buffers)")
+            if pixels.dtype != torch.float32 or pixels.dim() != 3:
+                raise ValueError("pixels must be float32 of shape (rows, columns, channels)")
+            pixels = pixels.contiguous()
+        else:
+            pixels = np.ascontiguousarray(pixels, dtype=np.float32)
+            if pixels.ndim != 3:
+                raise ValueError("pixels must have shape (rows, columns, channels)")
+        if not 1 <= pixels.shape[2] <= 4:
+            raise ValueError("1..4 channels (Gray, Gray+Alpha, RGB, RGBA)")
+        self.pixels = pixels
+        self.colorspace = colorspace
+
+    rows = property(lambda self: int(self.pixels.shape[0]))
+    columns = property(lambda self: int(self.pixels.shape[1]))
+    channels = property(lambda self: int(self.pixels.shape[2]))
+    on_device = property(lambda self: _is_torch(self.pixels))
+
+    def _ptr(self) -> int:
+        return self.pixels.data_ptr() if self.on_device else self.pixels.ctypes.data
+
+    def _new_like(self, rows: Optional[int] = None, columns: Optional[int] = None) -> "Image":
+        shape = (rows or self.rows, columns or self.columns, self.channels)
+        if self.on_device:
+            import torch
+            out = torch.empty(shape, dtype=torch.float32, device=self.pixels.device)
+        else:
+            out = np.empty(shape, dtype=np.float32)
+        return Image(out, self.colorspace)
+
+
+def _stream(image: Image):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(image.pixels.device).cuda_stream)
+
+
+def _activate(image: Image) -> None:
+    if image.on_device:
+        import torch
+        dev = image.pixels.device.index
+        if dev is None:
+            dev = torch.cuda.current_device()
+        check(_lib.load().mb200_set_device(dev))
+
+
+class KernelInfo:
+    """Owning handle of a KernelInfo list (MagickCore/morphology.h:102-130)."""
+
+    def __init__(self, ptr: KernelPtr):
+        if not ptr:
+            raise MagickB200Error(_lib.EINVAL, "kernel could not be parsed / built")
+        self._ptr = ptr
+
+    def __del__(self):
+        ptr, self._ptr = getattr(self, "_ptr", None), None
+        if ptr:
+            try:
+                _lib.load().mb200_destroy_kernel_info(ptr)
+            except Exception:
+                pass
+
+    def __iter__(self):
+        p = self._ptr
+        while p:
+            yield p.contents
+            p = p.contents.next
+
+    def arrays(self):
+        """[(values(h,w) float64, x, y), ...] for every kernel of the list."""
+        out = []
+        for k in self:
+            n = k.width * k.height
+            vals = np.ctypeslib.as_array(k.values, shape=(n,)).copy().reshape(k.height, k.width)
+            out.append((vals, int(k.x), int(k.y)))
+        return out
+
+
+def AcquireKernelInfo(kernel_string: str) -> KernelInfo:
+    """MagickCore/morphology.c:485."""
+    return KernelInfo(_lib.load().mb200_acquire_kernel_info(kernel_string.encode()))
+
+
+def AcquireKernelBuiltIn(kernel_type: int, rho: float = 0.0, sigma: float = 0.0, xi: float = 0.0,
+                         psi: float = 0.0) -> KernelInfo:
+    """MagickCore/morphology.c:950 (GeometryInfo rho, sigma, xi, psi)."""
+    return KernelInfo(_lib.load().mb200_acquire_kernel_builtin(kernel_type, rho, sigma, xi, psi))
+
+
+def _as_kernel(kernel: Union[str, KernelInfo]) -> KernelInfo:
+    return AcquireKernelInfo(kernel) if isinstance(kernel, str) else kernel
+
+
+def _same_size_op(image: Image, dev_fn: str, host_fn: str, *args) -> Image:
+    lib = _lib.load()
+    out = image._new_like()
+    if image.on_device:
+        _activate(image)
+        check(getattr(lib, dev_fn)(image._ptr(), out._ptr(), image.columns, image.rows, image.channels, *args,
+                                   _stream(image)))
+    else:
+        check(getattr(lib, host_fn)(image._ptr(), out._ptr(), image.columns, image.rows, image.channels, *args))
+    return out
+
+
+def BlurImage(image: Image, radius: float, sigma: float) -> Image:
+    """MagickCore/effect.c:765 -- separable Gaussian ("blur:RxS;blur:RxS+90")."""
+    return _same_size_op(image, "mb200_blur_image_dev", "mb200_blur_image", float(radius), float(sigma))
+
+
+def GaussianBlurImage(image: Image, radius: float, sigma: float) -> Image:
+    """MagickCore/effect.c:1709 -- true 2-D "gaussian:RxS" kernel."""
+    return _same_size_op(image, "mb200_gaussian_blur_image_dev", "mb200_gaussian_blur_image", float(radius),
+                         float(sigma))
+
+
+def ConvolveImage(image: Image, kernel_info: Union[str, KernelInfo]) -> Image:
+    """MagickCore/effect.c:1170."""
+    k = _as_kernel(kernel_info)
+    return _same_size_op(image, "mb200_convolve_image_dev", "mb200_convolve_image", k._ptr)
+
+
+def MorphologyImage(image: Image, method: int, iterations: int, kernel: Union[str, KernelInfo],
+                    bias: float = 0.0) -> Image:
+    """MagickCore/morphology.c:4129 (bias == the "convolve:bias" artifact)."""
+    k = _as_kernel(kernel)
+    return _same_size_op(image, "mb200_morphology_image_dev", "mb200_morphology_image", int(method),
+                         int(iterations), k._ptr, float(bias))
+
+
+def UnsharpMaskImage(image: Image, radius: float, sigma: float, gain: float, threshold: float) -> Image:
+    """MagickCore/effect.c:4256."""
+    return _same_size_op(image, "mb200_unsharp_mask_image_dev", "mb200_unsharp_mask_image", float(radius),
+                         float(sigma), float(gain), float(threshold))
+
+
+def ResizeImage(image: Image, columns: int, rows: int, filter: int = UndefinedFilter) -> Image:
+    """MagickCore/resize.c:3761."""
+    if columns <= 0 or rows <= 0:
+        raise MagickB200Error(_lib.EINVAL, "NegativeOrZeroImageSize")
+    lib = _lib.load()
+    out = image._new_like(rows=rows, columns=columns)
+    if image.on_device:
+        _activate(image)
+        check(lib.mb200_resize_image_dev(image._ptr(), image.columns, image.rows, image.channels, out._ptr(),
+                                         columns, rows, int(filter), _stream(image)))
+    else:
+        check(lib.mb200_resize_image(image._ptr(), image.columns, image.rows, image.channels, out._ptr(), columns,
+                                     rows, int(filter)))
+    return out
+
+
+def TransformImageColorspace(image: Image, colorspace: int) -> bool:
+    """MagickCore/colorspace.c:1751 -- in place; updates image.colorspace."""
+    lib = _lib.load()
+    if image.colorspace == colorspace:
+        return True
+    if image.on_device:
+        _activate(image)
+        check(lib.mb200_transform_colorspace_dev(image._ptr(), image.columns, image.rows, image.channels,
+                                                 image.colorspace, colorspace, _stream(image)))
+    else:
+        check(lib.mb200_transform_colorspace(image._ptr(), image.columns, image.rows, image.channels,
+                                             image.colorspace, colorspace))
+    image.colorspace = colorspace
+    return True
+
+
+def MorphologyPrimitive(image: Image, method: int, kernel: Union[str, KernelInfo], bias: float = 0.0):
+    """One MorphologyPrimitive pass (MagickCore/morphology.c:2566): returns (Image, changed).
+    Device-resident images only (the primitive has no host-buffer entry point)."""
+    if not image.on_device:
+        raise ValueError("MorphologyPrimitive needs a device-resident Image")
+    k = _as_kernel(kernel)
+    out = image._new_like()
+    changed = C.c_longlong(0)
+    _activate(image)
+    check(_lib.load().mb200_morphology_primitive_dev(image._ptr(), out._ptr(), image.columns, image.rows,
+                                                     image.channels, int(method), k._ptr, float(bias),
+                                                     C.byref(changed), _stream(image)))
+    return out, int(changed.value)
+
+
+def launch_count() -> int:
+    return int(_lib.load().mb200_launch_count())
+
+
+def device_count() -> int:
+    return int(_lib.load().mb200_device_count())

@@ -1,0 +1,455 @@
+// api.cu -- the C-ABI operators (include/magick_b200.h): the host-side control flow of
+// the hot path around the CUDA kernels.
+//
+// Mirrors the drivers in the reference (behaviour, not code):
+//   MorphologyImage / MorphologyApply  MagickCore/morphology.c:4129, :3634  (kernel lists are
+//     re-iterated, compound Open/Close/Smooth staging :3813-3893, `changed`-driven iteration :3919)
+//   BlurImage :765, ConvolveImage :1170, GaussianBlurImage :1709, UnsharpMaskImage :4256
+//     (MagickCore/effect.c)
+//   ResizeImage MagickCore/resize.c:3761 (pass order :3846-3861, default filter :3806-3816)
+//   TransformImageColorspace MagickCore/colorspace.c:1751
+// Intermediates live in HBM as float Quantum, exactly like the reference's intermediate
+// images (the rounding between passes is part of the semantics).
+#include "mb200_internal.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+using namespace mb200;
+
+namespace {
+
+struct StreamAlloc {           // stream-ordered temporary; freed (stream-ordered) on scope exit
+  void *ptr = nullptr;
+  cudaStream_t s;
+  explicit StreamAlloc(cudaStream_t stream) : s(stream) {}
+  int alloc(size_t bytes) {
+    cudaError_t e = cudaMallocAsync(&ptr, bytes ? bytes : 1, s);
+    if (e != cudaSuccess) { ptr = nullptr; return cuda_fail(e, "cudaMallocAsync"); }
+    return MB200_OK;
+  }
+  ~StreamAlloc() { if (ptr) cudaFreeAsync(ptr, s); }
+  StreamAlloc(const StreamAlloc &) = delete;
+  StreamAlloc &operator=(const StreamAlloc &) = delete;
+};
+
+int prepare(void *stream, cudaStream_t *out) {
+  int rc = ensure_device();
+  if (rc) return rc;
+  static thread_local int pool_configured_for = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (pool_configured_for != dev) {   // keep freed temporaries cached in the pool across calls
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long threshold = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    pool_configured_for = dev;
+  }
+  *out = stream ? static_cast<cudaStream_t>(stream) : static_cast<cudaStream_t>(default_stream());
+  return MB200_OK;
+}
+
+bool valid_image(size_t w, size_t h, int ch) { return w > 0 && h > 0 && ch >= 1 && ch <= 4; }
+
+// One MorphologyPrimitive launch.  d_counter may be null.
+int primitive(const float *src, float *dst, size_t w, size_t h, int ch, int method,
+              const mb200_kernel_info *k, double bias, unsigned long long *d_counter, cudaStream_t s) {
+  const int kw = static_cast<int>(k->width), kh = static_cast<int>(k->height);
+  const size_t n = k->width * k->height;
+  std::vector<double> win(n);
+  int ox, oy;
+  bool has_nan = false;
+  if (method == MB200_ConvolveMorphology || method == MB200_DilateMorphology) {   // reflected, :2612-2626
+    for (size_t i = 0; i < n; ++i) win[i] = k->values[n - 1 - i];
+    ox = kw - static_cast<int>(k->x) - 1;
+    oy = kh - static_cast<int>(k->y) - 1;
+  } else if (method == MB200_ErodeMorphology) {
+    for (size_t i = 0; i < n; ++i) win[i] = k->values[i];
+    ox = static_cast<int>(k->x);
+    oy = static_cast<int>(k->y);
+  } else {
+    return fail(MB200_EUNSUPPORTED, "morphology primitive %d is not implemented on the GPU path", method);
+  }
+  for (double v : win) if (std::isnan(v)) has_nan = true;
+  if (ox < 0 || oy < 0 || ox >= kw || oy >= kh) return fail(MB200_EINVAL, "kernel origin outside the kernel");
+  if (method == MB200_ConvolveMorphology && !has_nan && (kw == 1 || kh == 1)) {
+    // width-1 kernels take the reference's column path (:2654); for all-finite taps its extra
+    // gamma*(height/count) factor is exactly 1.
+    const int axis = (kw == 1) ? 1 : 0;
+    const int rc = launch_conv1d(src, dst, w, h, ch, axis, win.data(), axis == 1 ? kh : kw, axis == 1 ? oy : ox,
+                                 bias, 1.0, d_counter, s);
+    if (rc != MB200_EUNSUPPORTED) return rc;
+  }
+  double gamma_scale = 1.0;
+  if (method == MB200_ConvolveMorphology && kw == 1) {
+    size_t count = 0;
+    for (double v : win) if (!std::isnan(v)) ++count;
+    if (count != 0) gamma_scale = static_cast<double>(kh) / static_cast<double>(count);
+  }
+  return launch_morph2d(src, dst, w, h, ch, method, win.data(), kw, kh, ox, oy, bias, gamma_scale, d_counter, s);
+}
+
+// Reads back a device counter (synchronises the stream) and converts it to the reference's
+// `changed` = per-channel changes / number of Update channels (image-private.h:147).
+int read_changed(unsigned long long *d_counter, int channels, long long *out, cudaStream_t s) {
+  unsigned long long hostv = 0;
+  cudaError_t e = cudaMemcpyAsync(&hostv, d_counter, sizeof(hostv), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return cuda_fail(e, "changed readback");
+  *out = static_cast<long long>(hostv / static_cast<unsigned long long>(channels));
+  return MB200_OK;
+}
+
+// 180-degree reflection used by Correlate/Close/Smooth (:3779-3793, RotateKernelInfo :4258)
+mb200_kernel_info *reflected_clone(const mb200_kernel_info *kernel) {
+  mb200_kernel_info *r = mb200_clone_kernel_info(kernel);
+  if (r) rotate_kernel_info(r, 180.0);
+  return r;
+}
+
+struct Stage { int primitive; const mb200_kernel_info *kernel; };
+
+int morphology_apply(const float *src, float *dst, size_t w, size_t h, int ch, int method, long iterations,
+                     const mb200_kernel_info *kernel, double bias, cudaStream_t s) {
+  if (iterations == 0) return fail(MB200_EINVAL, "iterations == 0 is a null operation (reference returns NULL)");
+  size_t kernel_limit = iterations < 0 ? (w > h ? w : h) : static_cast<size_t>(iterations);
+  int stage_limit = 1;
+  switch (method) {
+    case MB200_SmoothMorphology: stage_limit = 4; break;
+    case MB200_OpenMorphology: case MB200_CloseMorphology: stage_limit = 2; break;
+    case MB200_ConvolveMorphology: case MB200_CorrelateMorphology:
+    case MB200_ErodeMorphology: case MB200_DilateMorphology: break;
+    default:
+      return fail(MB200_EUNSUPPORTED, "morphology method %d needs CompositeImage or a sequential primitive; "
+                  "not on the GPU path", method);
+  }
+  mb200_kernel_info *reflected = nullptr;
+  if (method == MB200_CorrelateMorphology || method == MB200_CloseMorphology || method == MB200_SmoothMorphology) {
+    reflected = reflected_clone(kernel);
+    if (!reflected) return fail(MB200_ENOMEM, "kernel clone failed");
+  }
+  std::vector<Stage> stages;
+  const mb200_kernel_info *rk = reflected;
+  for (const mb200_kernel_info *nk = kernel; nk; nk = nk->next, rk = rk ? rk->next : nullptr) {
+    for (int stage = 1; stage <= stage_limit; ++stage) {
+      Stage st{method, nk};
+      switch (method) {
+        case MB200_OpenMorphology: st.primitive = stage == 2 ? MB200_DilateMorphology : MB200_ErodeMorphology; break;
+        case MB200_CloseMorphology: st.kernel = rk; st.primitive = stage == 2 ? MB200_ErodeMorphology : MB200_DilateMorphology; break;
+        case MB200_SmoothMorphology:
+          if (stage == 1) st.primitive = MB200_ErodeMorphology;
+          else if (stage == 2) st.primitive = MB200_DilateMorphology;
+          else if (stage == 3) { st.kernel = rk; st.primitive = MB200_DilateMorphology; }
+          else { st.kernel = rk; st.primitive = MB200_ErodeMorphology; }
+          break;
+        case MB200_CorrelateMorphology: st.kernel = rk; st.primitive = MB200_ConvolveMorphology; break;
+        default: break;
+      }
+      stages.push_back(st);
+    }
+  }
+  const size_t bytes = w * h * static_cast<size_t>(ch) * sizeof(float);
+  int rc = MB200_OK;
+  if (kernel_limit == 1) {
+    // Every stage runs exactly once: ping-pong between one temporary and dst so that the last
+    // primitive writes dst (no trailing copy).
+    const size_t total = stages.size();
+    StreamAlloc tmp(s);
+    if (total > 1) { rc = tmp.alloc(bytes); }
+    const float *cur = src;
+    for (size_t i = 0; i < total && rc == MB200_OK; ++i) {
+      float *out = ((total - 1 - i) % 2 == 0) ? dst : static_cast<float *>(tmp.ptr);
+      rc = primitive(cur, out, w, h, ch, stages[i].primitive, stages[i].kernel, bias, nullptr, s);
+      cur = out;
+    }
+  } else {
+    // `changed`-driven iteration (:3919-3962): needs the count after every primitive.
+    StreamAlloc a(s), b(s), counter(s);
+    rc = a.alloc(bytes);
+    if (!rc) rc = b.alloc(bytes);
+    if (!rc) rc = counter.alloc(sizeof(unsigned long long));
+    const float *cur = src;
+    float *bufs[2] = {static_cast<float *>(a.ptr), static_cast<float *>(b.ptr)};
+    int next = 0;
+    for (size_t i = 0; i < stages.size() && rc == MB200_OK; ++i) {
+      size_t loop = 0;
+      long long changed = 1;
+      while (loop < kernel_limit && changed > 0 && rc == MB200_OK) {
+        ++loop;
+        cudaMemsetAsync(counter.ptr, 0, sizeof(unsigned long long), s);
+        rc = primitive(cur, bufs[next], w, h, ch, stages[i].primitive, stages[i].kernel, bias,
+                       static_cast<unsigned long long *>(counter.ptr), s);
+        if (rc) break;
+        rc = read_changed(static_cast<unsigned long long *>(counter.ptr), ch, &changed, s);
+        cur = bufs[next];
+        next ^= 1;
+      }
+    }
+    if (rc == MB200_OK) {
+      cudaError_t e = cudaMemcpyAsync(dst, cur, bytes, cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) rc = cuda_fail(e, "result copy");
+    }
+  }
+  mb200_destroy_kernel_info(reflected);
+  return rc;
+}
+
+// Runs `op(d_src, d_dst, stream)` on staged copies of host buffers.
+template <typename Op>
+int with_staging(const float *src, size_t src_bytes, float *dst, size_t dst_bytes, Op op) {
+  cudaStream_t s;
+  int rc = prepare(nullptr, &s);
+  if (rc) return rc;
+  StreamAlloc d_src(s), d_dst(s);
+  rc = d_src.alloc(src_bytes);
+  if (!rc) rc = d_dst.alloc(dst_bytes);
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpyAsync(d_src.ptr, src, src_bytes, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cuda_fail(e, "H2D");
+  rc = op(static_cast<const float *>(d_src.ptr), static_cast<float *>(d_dst.ptr), s);
+  if (rc) { cudaStreamSynchronize(s); return rc; }
+  e = cudaMemcpyAsync(dst, d_dst.ptr, dst_bytes, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return cuda_fail(e, "D2H");
+  return MB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mb200_morphology_primitive_dev(const float *src, float *dst, size_t width, size_t height, int channels,
+                                   int method, const mb200_kernel_info *kernel, double bias, long long *changed,
+                                   void *stream) {
+  if (!src || !dst || !kernel || !kernel->values || !valid_image(width, height, channels))
+    return fail(MB200_EINVAL, "morphology_primitive: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  if (!changed) return primitive(src, dst, width, height, channels, method, kernel, bias, nullptr, s);
+  StreamAlloc counter(s);
+  rc = counter.alloc(sizeof(unsigned long long));
+  if (rc) return rc;
+  cudaMemsetAsync(counter.ptr, 0, sizeof(unsigned long long), s);
+  rc = primitive(src, dst, width, height, channels, method, kernel, bias,
+                 static_cast<unsigned long long *>(counter.ptr), s);
+  if (rc) return rc;
+  return read_changed(static_cast<unsigned long long *>(counter.ptr), channels, changed, s);
+}
+
+int mb200_morphology_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
+                               int method, long iterations, const mb200_kernel_info *kernel, double bias,
+                               void *stream) {
+  if (!src || !dst || src == dst || !kernel || !valid_image(width, height, channels))
+    return fail(MB200_EINVAL, "morphology_image: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  return morphology_apply(src, dst, width, height, channels, method, iterations, kernel, bias, s);
+}
+
+int mb200_convolve_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
+                             const mb200_kernel_info *kernel, void *stream) {
+  return mb200_morphology_image_dev(src, dst, width, height, channels, MB200_ConvolveMorphology, 1, kernel, 0.0,
+                                    stream);
+}
+
+int mb200_blur_image_dev(const float *src, float *dst, size_t width, size_t height, int channels, double radius,
+                         double sigma, void *stream) {
+  // effect.c:788: "blur:RxS;blur:RxS+90"
+  mb200_kernel_info *k = mb200_acquire_kernel_builtin(MB200_BlurKernel, radius, sigma, 0.0, 0.0);
+  if (!k) return fail(MB200_ENOMEM, "blur kernel");
+  k->next = mb200_acquire_kernel_builtin(MB200_BlurKernel, radius, sigma, 90.0, 0.0);
+  if (!k->next) { mb200_destroy_kernel_info(k); return fail(MB200_ENOMEM, "blur kernel"); }
+  const int rc = mb200_convolve_image_dev(src, dst, width, height, channels, k, stream);
+  mb200_destroy_kernel_info(k);
+  return rc;
+}
+
+int mb200_gaussian_blur_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
+                                  double radius, double sigma, void *stream) {
+  mb200_kernel_info *k = mb200_acquire_kernel_builtin(MB200_GaussianKernel, radius, sigma, 0.0, 0.0);
+  if (!k) return fail(MB200_ENOMEM, "gaussian kernel");
+  const int rc = mb200_convolve_image_dev(src, dst, width, height, channels, k, stream);
+  mb200_destroy_kernel_info(k);
+  return rc;
+}
+
+int mb200_unsharp_mask_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
+                                 double radius, double sigma, double gain, double threshold, void *stream) {
+  int rc = mb200_blur_image_dev(src, dst, width, height, channels, radius, sigma, stream);
+  if (rc) return rc;
+  cudaStream_t s;
+  rc = prepare(stream, &s);
+  if (rc) return rc;
+  return launch_unsharp_combine(src, dst, width * height * static_cast<size_t>(channels), gain,
+                                65535.0 * threshold, s);
+}
+
+int mb200_resize_image_dev(const float *src, size_t width, size_t height, int channels, float *dst,
+                           size_t out_width, size_t out_height, int filter, void *stream) {
+  if (!src || !dst || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "resize: bad arguments");
+  if (out_width == 0 || out_height == 0) return fail(MB200_EINVAL, "NegativeOrZeroImageSize");   // :3791
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  const size_t px = static_cast<size_t>(channels) * sizeof(float);
+  if (out_width == width && out_height == height && filter == MB200_UndefinedFilter) {            // :3793-3795
+    cudaError_t e = cudaMemcpyAsync(dst, src, width * height * px, cudaMemcpyDeviceToDevice, s);
+    return e == cudaSuccess ? MB200_OK : cuda_fail(e, "resize: clone");
+  }
+  auto reciprocal = [](double x) { return std::fabs(x) >= 1.0e-12 ? 1.0 / x : (x < 0 ? -1.0e12 : 1.0e12); };
+  const double x_factor = static_cast<double>(out_width) * reciprocal(static_cast<double>(width));
+  const double y_factor = static_cast<double>(out_height) * reciprocal(static_cast<double>(height));
+  int filter_type = MB200_LanczosFilter;                                                           // :3806-3816
+  if (filter != MB200_UndefinedFilter) filter_type = filter;
+  else if (x_factor == 1.0 && y_factor == 1.0) filter_type = MB200_PointFilter;
+  else if (has_alpha(channels) || (x_factor * y_factor) > 1.0) filter_type = MB200_MitchellFilter;
+
+  struct Axis { size_t in_n, out_n; double factor; long taps; std::vector<long> start; std::vector<int> istart, count; std::vector<double> w, wt; };
+  auto build = [&](Axis &ax) -> int {
+    ax.taps = mb200_resize_contributions(filter_type, ax.in_n, ax.out_n, ax.factor, nullptr, nullptr, nullptr, 0);
+    if (ax.taps < 0) return static_cast<int>(ax.taps);
+    ax.start.resize(ax.out_n); ax.count.resize(ax.out_n); ax.istart.resize(ax.out_n);
+    ax.w.resize(ax.out_n * static_cast<size_t>(ax.taps));
+    const long r = mb200_resize_contributions(filter_type, ax.in_n, ax.out_n, ax.factor, ax.start.data(),
+                                              ax.count.data(), ax.w.data(), static_cast<size_t>(ax.taps));
+    if (r < 0) return static_cast<int>(r);
+    // tap-major transpose for coalesced weight loads
+    ax.wt.resize(ax.w.size());
+    for (size_t o = 0; o < ax.out_n; ++o) {
+      ax.istart[o] = static_cast<int>(ax.start[o]);
+      for (long j = 0; j < ax.taps; ++j) ax.wt[static_cast<size_t>(j) * ax.out_n + o] = ax.w[o * ax.taps + j];
+    }
+    return MB200_OK;
+  };
+  Axis ax_x{width, out_width, x_factor}, ax_y{height, out_height, y_factor};
+  rc = build(ax_x);
+  if (!rc) rc = build(ax_y);
+  if (rc) return rc;
+
+  auto upload = [&](Axis &ax, StreamAlloc &ds, StreamAlloc &dc, StreamAlloc &dw) -> int {
+    int r = ds.alloc(ax.out_n * sizeof(int));
+    if (!r) r = dc.alloc(ax.out_n * sizeof(int));
+    if (!r) r = dw.alloc(ax.wt.size() * sizeof(double));
+    if (r) return r;
+    cudaError_t e = cudaMemcpyAsync(ds.ptr, ax.istart.data(), ax.out_n * sizeof(int), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dc.ptr, ax.count.data(), ax.out_n * sizeof(int), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dw.ptr, ax.wt.data(), ax.wt.size() * sizeof(double), cudaMemcpyHostToDevice, s);
+    return e == cudaSuccess ? MB200_OK : cuda_fail(e, "resize: table upload");
+  };
+  StreamAlloc xs(s), xc(s), xw(s), ys(s), yc(s), yw(s), tmp(s);
+  rc = upload(ax_x, xs, xc, xw);
+  if (!rc) rc = upload(ax_y, ys, yc, yw);
+  if (rc) return rc;
+  // pageable host tables: cudaMemcpyAsync has staged them before returning, so the vectors may die.
+  if (x_factor > y_factor) {                                                                       // :3846-3853
+    rc = tmp.alloc(out_width * height * px);
+    if (rc) return rc;
+    rc = launch_resize_axis(src, width, height, channels, static_cast<float *>(tmp.ptr), out_width, 0,
+                            static_cast<int *>(xs.ptr), static_cast<int *>(xc.ptr), static_cast<double *>(xw.ptr),
+                            static_cast<int>(ax_x.taps), 0, s);
+    if (rc) return rc;
+    rc = launch_resize_axis(static_cast<float *>(tmp.ptr), out_width, height, channels, dst, out_height, 1,
+                            static_cast<int *>(ys.ptr), static_cast<int *>(yc.ptr), static_cast<double *>(yw.ptr),
+                            static_cast<int>(ax_y.taps), 0, s);
+  } else {                                                                                         // :3854-3861
+    rc = tmp.alloc(width * out_height * px);
+    if (rc) return rc;
+    rc = launch_resize_axis(src, width, height, channels, static_cast<float *>(tmp.ptr), out_height, 1,
+                            static_cast<int *>(ys.ptr), static_cast<int *>(yc.ptr), static_cast<double *>(yw.ptr),
+                            static_cast<int>(ax_y.taps), 0, s);
+    if (rc) return rc;
+    rc = launch_resize_axis(static_cast<float *>(tmp.ptr), width, out_height, channels, dst, out_width, 0,
+                            static_cast<int *>(xs.ptr), static_cast<int *>(xc.ptr), static_cast<double *>(xw.ptr),
+                            static_cast<int>(ax_x.taps), 0, s);
+  }
+  return rc;
+}
+
+int mb200_transform_colorspace_dev(float *buf, size_t width, size_t height, int channels, int from, int to,
+                                   void *stream) {
+  if (!buf || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "colorspace: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  return launch_colorspace(buf, width * height, channels, from, to, s);
+}
+
+// ------------------------------------------------------------ host buffers
+
+int mb200_blur_image(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma) {
+  if (!src || !dst || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "blur: bad arguments");
+  const size_t bytes = w * h * ch * sizeof(float);
+  return with_staging(src, bytes, dst, bytes, [&](const float *s, float *d, cudaStream_t st) {
+    return mb200_blur_image_dev(s, d, w, h, ch, radius, sigma, st);
+  });
+}
+
+int mb200_gaussian_blur_image(const float *src, float *dst, size_t w, size_t h, int ch, double radius,
+                              double sigma) {
+  if (!src || !dst || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "gaussian blur: bad arguments");
+  const size_t bytes = w * h * ch * sizeof(float);
+  return with_staging(src, bytes, dst, bytes, [&](const float *s, float *d, cudaStream_t st) {
+    return mb200_gaussian_blur_image_dev(s, d, w, h, ch, radius, sigma, st);
+  });
+}
+
+int mb200_convolve_image(const float *src, float *dst, size_t w, size_t h, int ch, const mb200_kernel_info *kernel) {
+  if (!src || !dst || !kernel || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "convolve: bad arguments");
+  const size_t bytes = w * h * ch * sizeof(float);
+  return with_staging(src, bytes, dst, bytes, [&](const float *s, float *d, cudaStream_t st) {
+    return mb200_convolve_image_dev(s, d, w, h, ch, kernel, st);
+  });
+}
+
+int mb200_morphology_image(const float *src, float *dst, size_t w, size_t h, int ch, int method, long iterations,
+                           const mb200_kernel_info *kernel, double bias) {
+  if (!src || !dst || !kernel || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "morphology: bad arguments");
+  const size_t bytes = w * h * ch * sizeof(float);
+  return with_staging(src, bytes, dst, bytes, [&](const float *s, float *d, cudaStream_t st) {
+    return mb200_morphology_image_dev(s, d, w, h, ch, method, iterations, kernel, bias, st);
+  });
+}
+
+int mb200_unsharp_mask_image(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma,
+                             double gain, double threshold) {
+  if (!src || !dst || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "unsharp: bad arguments");
+  const size_t bytes = w * h * ch * sizeof(float);
+  return with_staging(src, bytes, dst, bytes, [&](const float *s, float *d, cudaStream_t st) {
+    return mb200_unsharp_mask_image_dev(s, d, w, h, ch, radius, sigma, gain, threshold, st);
+  });
+}
+
+int mb200_resize_image(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh, int filter) {
+  if (!src || !dst || !valid_image(w, h, ch) || ow == 0 || oh == 0) return fail(MB200_EINVAL, "resize: bad arguments");
+  return with_staging(src, w * h * ch * sizeof(float), dst, ow * oh * ch * sizeof(float),
+                      [&](const float *s, float *d, cudaStream_t st) {
+                        return mb200_resize_image_dev(s, w, h, ch, d, ow, oh, filter, st);
+                      });
+}
+
+int mb200_transform_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to) {
+  if (!buf || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "colorspace: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(nullptr, &s);
+  if (rc) return rc;
+  const size_t bytes = w * h * ch * sizeof(float);
+  StreamAlloc d(s);
+  rc = d.alloc(bytes);
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpyAsync(d.ptr, buf, bytes, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cuda_fail(e, "H2D");
+  rc = launch_colorspace(static_cast<float *>(d.ptr), w * h, ch, from, to, s);
+  if (rc) { cudaStreamSynchronize(s); return rc; }
+  e = cudaMemcpyAsync(buf, d.ptr, bytes, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  return e == cudaSuccess ? MB200_OK : cuda_fail(e, "D2H");
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+// colorspace.cu -- in-place per-pixel colourspace transforms.
+//
+// Semantics: TransformImageColorspace (MagickCore/colorspace.c:1751-1783):
+//   forward  sRGBTransformImage generic branch :958-1054 (Lab, XYZ) and linear-RGB
+//            branch :1164-1225;   inverse TransformsRGBImage generic :2296-2390 and
+//            linear-RGB :2494-2550.
+//   helpers  ConvertRGBToXYZ colorspace-private.h:759, ConvertXYZToLab :1066,
+//            ConvertLabToXYZ :531, ConvertXYZToRGB :72 (D65, :32-46),
+//            DecodePixelGamma / EncodePixelGamma pixel.c:318 / :445 whose x^2.4 and
+//            x^(1/2.4) are 9-term Chebyshev series on the frexp mantissa (pixel.c:260, :380).
+// All arithmetic is FP64 in the reference's operation order; the only libm call in the
+// reference, pow(t,1/3), is evaluated with cbrt() (difference < 1 ulp of double, far
+// below the float Quantum the result is rounded to).  Alpha is untouched.
+// One thread per pixel, float4 access for RGBA; the kernel is FP64-pipe bound.
+#include "mb200_internal.h"
+
+#include <cuda_runtime.h>
+
+namespace mb200 {
+namespace {
+
+constexpr double QR = 65535.0;
+constexpr double QS = 1.0 / 65535.0;
+
+__device__ __forceinline__ double cheb9(const double *cf, double t1) {
+  // term[i] = 2*t1*term[i-1] - term[i-2]; p = sum cf[i]*term[i] (left to right, pixel.c:299-309)
+  double tm2 = 1.0, tm1 = t1;
+  double p = cf[0] * tm2 + cf[1] * tm1;
+#pragma unroll
+  for (int i = 2; i < 9; ++i) {
+    const double t = 2.0 * t1 * tm1 - tm2;
+    p = p + cf[i] * t;
+    tm2 = tm1; tm1 = t;
+  }
+  return p;
+}
+
+__device__ double decode_gamma(double x) {            // pixel.c:260-316
+  const double cf[9] = {1.7917488588043277509, 0.82045614371976854984, 0.027694100686325412819,
+                        -0.00094244335181762134018, 0.000064355540911469709545, -5.7224404636060757485e-06,
+                        5.8767669437311184313e-07, -6.6139920053589721168e-08, 7.9323242696227458163e-09};
+  const double p2[5] = {1.0, 2.6390158215457883983, 6.9644045063689921093, 1.8379173679952558018e+01,
+                        4.8502930128332728543e+01};
+  int e;
+  const double mant = frexp(x, &e);
+  const double p = cheb9(cf, 4.0 * mant - 3.0);
+  int quot = (e - 1) / 5, rem = (e - 1) % 5;
+  if (rem < 0) { quot -= 1; rem += 5; }
+  return x * ldexp(p2[rem] * p, 7 * quot);
+}
+
+__device__ double encode_gamma(double x) {            // pixel.c:380-443
+  const double cf[9] = {1.1758200232996901923, 0.16665763094889061230, -0.0083154894939042125035,
+                        0.00075187976780420279038, -0.000083240178519391795367, 0.000010229209410070008679,
+                        -1.3400466409860246e-06, 1.8333422241635376682e-07, -2.5878596761348859722e-08};
+  const double p2[12] = {1.0, 1.3348398541700343678, 1.7817974362806785482, 2.3784142300054420538,
+                         3.1748021039363991669, 4.2378523774371812394, 5.6568542494923805819,
+                         7.5509945014535482244, 1.0079368399158985525e1, 1.3454342644059433809e1,
+                         1.7959392772949968275e1, 2.3972913230026907883e1};
+  int e;
+  const double mant = frexp(x, &e);
+  const double p = cheb9(cf, 4.0 * mant - 3.0);
+  int quot = (e - 1) / 12, rem = (e - 1) % 12;
+  if (rem < 0) { quot -= 1; rem += 12; }
+  return ldexp(p2[rem] * p, 5 * quot);
+}
+
+__device__ __forceinline__ double decode_pixel_gamma(double pixel) {   // pixel.c:318
+  if (pixel <= (0.0404482362771076 * QR)) return pixel / 12.92;
+  return QR * decode_gamma((QS * pixel + 0.055) / 1.055);
+}
+
+__device__ __forceinline__ double encode_pixel_gamma(double pixel) {   // pixel.c:445
+  if (pixel <= (0.0031306684425005883 * QR)) return 12.92 * pixel;
+  return QR * (1.055 * encode_gamma(QS * pixel) - 0.055);
+}
+
+constexpr double kIllX = 0.95047, kIllY = 1.00000, kIllZ = 1.08883;   // D65
+constexpr double kCieEps = 216.0 / 24389.0, kCieK = 24389.0 / 27.0;
+
+__device__ __forceinline__ double lab_f(double t) {   // colorspace-private.h:1075-1086
+  if (t > kCieEps) return cbrt(t);
+  return (kCieK * t + 16.0) / 116.0;
+}
+
+__device__ __forceinline__ void rgb_to_xyz(double R, double G, double B, double &X, double &Y, double &Z) {
+  const double r = QS * decode_pixel_gamma(R), g = QS * decode_pixel_gamma(G), b = QS * decode_pixel_gamma(B);
+  X = (0.4123955889674142161 * r) + (0.3575834307637148171 * g) + (0.1804926473817015735 * b);
+  Y = (0.2125862307855955516 * r) + (0.7151703037034108499 * g) + (0.07220049864333622685 * b);
+  Z = (0.01929721549174694484 * r) + (0.1191838645808485318 * g) + (0.9504971251315797660 * b);
+}
+
+__device__ __forceinline__ void xyz_to_rgb(double X, double Y, double Z, double &R, double &G, double &B) {
+  double r = (3.240969941904521 * X) + (-1.537383177570093 * Y) + (-0.498610760293 * Z);
+  double g = (-0.96924363628087 * X) + (1.87596750150772 * Y) + (0.041555057407175 * Z);
+  double b = (0.055630079696993 * X) + (-0.20397695888897 * Y) + (1.056971514242878 * Z);
+  const double gb = g < b ? g : b;
+  const double m = r < gb ? r : gb;
+  if (m < 0.0) { r -= m; g -= m; b -= m; }
+  R = encode_pixel_gamma(QR * r);
+  G = encode_pixel_gamma(QR * g);
+  B = encode_pixel_gamma(QR * b);
+}
+
+enum Mode { kToLab, kToXyz, kToLinear, kFromLab, kFromXyz, kFromLinear };
+
+template <int CH, int MODE>
+__global__ void __launch_bounds__(256) colorspace_kernel(float *buf, size_t npixels) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= npixels) return;
+  float *q = buf + i * CH;
+  float in0, in1, in2, in3 = 0.f;
+  if (CH == 4) { const float4 t = *reinterpret_cast<const float4 *>(q); in0 = t.x; in1 = t.y; in2 = t.z; in3 = t.w; }
+  else { in0 = q[0]; in1 = q[1]; in2 = q[2]; }
+  double o0, o1, o2;
+  if (MODE == kToLinear) {
+    o0 = decode_pixel_gamma(in0); o1 = decode_pixel_gamma(in1); o2 = decode_pixel_gamma(in2);
+  } else if (MODE == kFromLinear) {
+    o0 = encode_pixel_gamma(in0); o1 = encode_pixel_gamma(in1); o2 = encode_pixel_gamma(in2);
+  } else if (MODE == kToLab || MODE == kToXyz) {
+    double X, Y, Z;
+    rgb_to_xyz(in0, in1, in2, X, Y, Z);
+    if (MODE == kToLab) {
+      const double x = lab_f(X / kIllX), y = lab_f(Y / kIllY), z = lab_f(Z / kIllZ);
+      X = ((116.0 * y) - 16.0) / 100.0;
+      Y = (500.0 * (x - y)) / 255.0 + 0.5;
+      Z = (200.0 * (y - z)) / 255.0 + 0.5;
+    }
+    o0 = QR * X; o1 = QR * Y; o2 = QR * Z;
+  } else {
+    double X = QS * in0, Y = QS * in1, Z = QS * in2;
+    if (MODE == kFromLab) {                                  // colorspace-private.h:559-570, :531-557
+      const double L = 100.0 * X, a = 255.0 * (Y - 0.5), b = 255.0 * (Z - 0.5);
+      double y = (L + 16.0) / 116.0;
+      double x = y + a / 500.0;
+      double z = y - b / 200.0;
+      if ((x * x * x) > kCieEps) x = (x * x * x); else x = (116.0 * x - 16.0) / kCieK;
+      if (L > (kCieK * kCieEps)) y = (y * y * y); else y = L / kCieK;
+      if ((z * z * z) > kCieEps) z = (z * z * z); else z = (116.0 * z - 16.0) / kCieK;
+      X = kIllX * x; Y = kIllY * y; Z = kIllZ * z;
+    }
+    xyz_to_rgb(X, Y, Z, o0, o1, o2);
+  }
+  if (CH == 4) *reinterpret_cast<float4 *>(q) = make_float4(static_cast<float>(o0), static_cast<float>(o1), static_cast<float>(o2), in3);
+  else { q[0] = static_cast<float>(o0); q[1] = static_cast<float>(o1); q[2] = static_cast<float>(o2); }
+}
+
+template <int MODE>
+int launch_mode(float *buf, size_t npixels, int channels, cudaStream_t s) {
+  const unsigned blocks = static_cast<unsigned>((npixels + 255) / 256);
+  if (channels == 4) colorspace_kernel<4, MODE><<<blocks, 256, 0, s>>>(buf, npixels);
+  else colorspace_kernel<3, MODE><<<blocks, 256, 0, s>>>(buf, npixels);
+  count_launch();
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "colorspace launch");
+  return MB200_OK;
+}
+
+}  // namespace
+
+int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to, void *stream) {
+  if (channels != 3 && channels != 4) return fail(MB200_EUNSUPPORTED, "colorspace: %d channels", channels);
+  if (npixels == 0) return MB200_OK;
+  if (npixels > 0xffffffffull * 256) return fail(MB200_EINVAL, "colorspace: image too large");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto known = [](int cs) { return cs == MB200_sRGBColorspace || cs == MB200_LabColorspace ||
+                                   cs == MB200_XYZColorspace || cs == MB200_RGBColorspace; };
+  if (!known(from) || !known(to)) return fail(MB200_EUNSUPPORTED, "colorspace %d -> %d not implemented", from, to);
+  if (from == to) return MB200_OK;
+  int rc = MB200_OK;
+  if (from != MB200_sRGBColorspace) {          // colorspace.c:1773-1774: back to sRGB first
+    if (from == MB200_LabColorspace) rc = launch_mode<kFromLab>(buf, npixels, channels, s);
+    else if (from == MB200_XYZColorspace) rc = launch_mode<kFromXyz>(buf, npixels, channels, s);
+    else rc = launch_mode<kFromLinear>(buf, npixels, channels, s);
+    if (rc) return rc;
+  }
+  if (to == MB200_LabColorspace) rc = launch_mode<kToLab>(buf, npixels, channels, s);
+  else if (to == MB200_XYZColorspace) rc = launch_mode<kToXyz>(buf, npixels, channels, s);
+  else if (to == MB200_RGBColorspace) rc = launch_mode<kToLinear>(buf, npixels, channels, s);
+  return rc;
+}
+
+}  // namespace mb200

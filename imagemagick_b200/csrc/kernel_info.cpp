@@ -1,0 +1,600 @@
+// kernel_info.cpp -- host side of the convolution / morphology path: builds the
+// tap arrays the CUDA kernels consume.
+//
+// Mirrors (behaviour, not code) MagickCore/morphology.c:
+//   AcquireKernelInfo :485, ParseKernelName :372, ParseKernelArray :213,
+//   AcquireKernelBuiltIn :950 (Unity :1032, Gaussian/DoG/LoG :1045, Blur :1140,
+//   Binomial :1333, Diamond :1537, Square/Rectangle :1560, Octagon :1601, Disk :1625,
+//   Plus :1651, Cross :1673), CalcKernelMetaData :2485, ScaleKernelInfo :4571,
+//   RotateKernelInfo :4258 and MagickCore/gem.c:262/302 GetOptimalKernelWidth1D/2D.
+//
+// Taps are generated on the host in double with the host libm `exp`, i.e. with the
+// very same arithmetic the reference uses, so they are bit-identical to the
+// reference's KernelInfo (tests/test_kernel_info.py checks this against the
+// compiled reference).  Nothing here touches the GPU.
+#include "mb200_internal.h"
+
+#include <cctype>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr double kEps = 1.0e-12;                 // MagickEpsilon, magick-type.h:114
+constexpr double kQuantumScale = 1.0 / 65535.0;  // magick-type.h:119
+constexpr double k2Pi = 6.28318530717958647692528676655900576839433879875020;   // image-private.h:44
+constexpr double kSq2Pi = 2.50662827463100024161235523934010416269302368164062; // image-private.h:51
+constexpr double kPi = 3.1415926535897932384626433832795028841971693993751058209749445923078164062;
+
+inline double perceptible_reciprocal(double x) {  // pixel-accessor.h:242
+  const double sign = x < 0.0 ? -1.0 : 1.0;
+  return (sign * x) >= kEps ? 1.0 / x : sign / kEps;
+}
+
+mb200_kernel_info *new_kernel(int type, size_t w, size_t h) {
+  auto *k = static_cast<mb200_kernel_info *>(std::calloc(1, sizeof(mb200_kernel_info)));
+  if (!k) return nullptr;
+  k->type = type;
+  k->width = w;
+  k->height = h;
+  k->values = static_cast<double *>(std::calloc(w * h != 0 ? w * h : 1, sizeof(double)));
+  if (!k->values) { std::free(k); return nullptr; }
+  return k;
+}
+
+void centre_origin(mb200_kernel_info *k) {
+  k->x = static_cast<long>((k->width - 1) / 2);
+  k->y = static_cast<long>((k->height - 1) / 2);
+}
+
+// morphology.c:2485 -- zero tiny taps, accumulate the positive / negative ranges
+void calc_meta(mb200_kernel_info *k) {
+  k->minimum = k->maximum = 0.0;
+  k->negative_range = k->positive_range = 0.0;
+  const size_t n = k->width * k->height;
+  for (size_t i = 0; i < n; ++i) {
+    double &v = k->values[i];
+    if (std::fabs(v) < kEps) v = 0.0;
+    if (v < 0) k->negative_range += v; else k->positive_range += v;
+    if (v < k->minimum) k->minimum = v;
+    if (v > k->maximum) k->maximum = v;
+  }
+}
+
+// Flat ("shape") kernels: every in-shape cell gets `scale`, the rest NaN.
+template <typename Pred>
+mb200_kernel_info *shape_kernel(int type, size_t w, double scale, Pred inside, bool sum_range) {
+  mb200_kernel_info *k = new_kernel(type, w, w);
+  if (!k) return nullptr;
+  centre_origin(k);
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  size_t i = 0;
+  for (long v = -k->y; v <= k->y; ++v)
+    for (long u = -k->x; u <= k->x; ++u, ++i) {
+      if (inside(u, v, k)) {
+        k->values[i] = scale;
+        if (sum_range) k->positive_range += scale;
+      } else {
+        k->values[i] = nan;
+      }
+    }
+  k->minimum = k->maximum = scale;
+  return k;
+}
+
+// Simplified ParseGeometry (geometry.c:922) for kernel arguments:
+//   rho [x|,|/] sigma [+|-|,] xi [+|-|,] psi ; flags '@' '>' '<' '!' '%' recorded.
+struct Geometry {
+  double rho = 0, sigma = 0, xi = 0, psi = 0;
+  bool has_rho = false, has_sigma = false, has_xi = false, has_psi = false;
+  bool area = false, greater = false, less = false, aspect = false, percent = false;
+  bool ok = true;
+};
+
+Geometry parse_geometry(const std::string &text) {
+  Geometry g;
+  std::string s;
+  for (char c : text) {
+    if (std::isspace(static_cast<unsigned char>(c))) continue;
+    switch (c) {
+      case '@': g.area = true; break;
+      case '>': g.greater = true; break;
+      case '<': g.less = true; break;
+      case '!': g.aspect = true; break;
+      case '%': g.percent = true; break;
+      case '(': case ')': break;
+      default: s.push_back(c);
+    }
+  }
+  const char *p = s.c_str();
+  auto number = [&](double *out) -> bool {
+    char *end = nullptr;
+    // "0x4" must not be read as a hexadecimal literal (geometry.c:1107)
+    if ((p[0] == '0') && (p[1] == 'x' || p[1] == 'X')) { *out = 0.0; p += 1; return true; }
+    const double v = std::strtod(p, &end);
+    if (end == p) return false;
+    *out = v; p = end; return true;
+  };
+  if (*p == '\0') return g;
+  if (*p != '+' && *p != '-' && *p != ',' && *p != 'x' && *p != 'X') {
+    if (number(&g.rho)) g.has_rho = true; else { g.ok = false; return g; }
+  } else if ((*p == '+' || *p == '-') ) {
+    // a leading sign: StringToDouble would consume it as part of rho only if the
+    // number is followed by a separator; "+90" alone is an offset (xi)
+    const char *save = p; double v;
+    char *end = nullptr; v = std::strtod(p, &end);
+    if (end != p && (*end == 'x' || *end == 'X' || *end == ',' || *end == '/' || *end == '\0')) {
+      g.rho = v; g.has_rho = true; p = end;
+    } else p = save;
+  }
+  if (*p == 'x' || *p == 'X' || *p == ',' || *p == '/') {
+    const char sep = *p++;
+    if (!((sep == 'x' || sep == 'X') && (*p == '+' || *p == '-'))) {
+      if (number(&g.sigma)) g.has_sigma = true;
+    }
+  }
+  auto signed_value = [&](double *out, bool *has) {
+    if (*p == ',' || *p == '/') ++p;
+    bool neg = false;
+    while (*p == '+' || *p == '-') { if (*p == '-') neg = !neg; ++p; }
+    double v;
+    if (number(&v)) { *out = neg ? -v : v; *has = true; }
+  };
+  if (*p == '+' || *p == '-' || *p == ',' || *p == '/') {
+    signed_value(&g.xi, &g.has_xi);
+    if (*p == '+' || *p == '-' || *p == ',' || *p == '/') signed_value(&g.psi, &g.has_psi);
+  }
+  if (*p != '\0') g.ok = false;
+  return g;
+}
+
+std::string lower(std::string s) {
+  for (char &c : s) c = static_cast<char>(std::tolower(static_cast<unsigned char>(c)));
+  return s;
+}
+
+// morphology.c:213 ParseKernelArray: "WxH+X+Y:v,v,.." or old style "v,v,v,..."
+mb200_kernel_info *parse_user_kernel(const std::string &def) {
+  std::string body = def;
+  size_t w = 0, h = 0; long ox = -1, oy = -1;
+  const size_t colon = def.find(':');
+  bool have_geometry = false;
+  if (colon != std::string::npos) {
+    Geometry g = parse_geometry(def.substr(0, colon));
+    if (!g.ok) return nullptr;
+    if (g.area || g.greater || g.less) return nullptr;   // rotation expansion: not supported
+    if (!g.has_rho) g.rho = g.sigma;
+    if (g.rho < 1.0) g.rho = 1.0;
+    if (g.sigma < 1.0) g.sigma = g.rho;
+    w = static_cast<size_t>(g.rho); h = static_cast<size_t>(g.sigma);
+    if (g.xi < 0.0 || g.psi < 0.0) return nullptr;
+    ox = g.has_xi ? static_cast<long>(g.xi) : static_cast<long>((w - 1) / 2);
+    oy = g.has_psi ? static_cast<long>(g.psi) : static_cast<long>((h - 1) / 2);
+    if (ox >= static_cast<long>(w) || oy >= static_cast<long>(h)) return nullptr;
+    body = def.substr(colon + 1);
+    have_geometry = true;
+  }
+  std::vector<double> vals;
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  size_t i = 0;
+  while (i < body.size()) {
+    const char c = body[i];
+    if (std::isspace(static_cast<unsigned char>(c)) || c == ',' || c == '\'') { ++i; continue; }
+    size_t j = i;
+    while (j < body.size() && !std::isspace(static_cast<unsigned char>(body[j])) && body[j] != ',' && body[j] != '\'') ++j;
+    const std::string tok = lower(body.substr(i, j - i));
+    if (tok == "nan" || tok == "-") vals.push_back(nan);
+    else {
+      char *end = nullptr;
+      const double v = std::strtod(tok.c_str(), &end);
+      if (end == tok.c_str() || *end != '\0') return nullptr;
+      vals.push_back(v);
+    }
+    i = j;
+  }
+  if (!have_geometry) {
+    // old odd-square form: size = sqrt(count+1)
+    w = h = static_cast<size_t>(std::sqrt(static_cast<double>(vals.size()) + 1.0));
+    ox = oy = static_cast<long>((w - 1) / 2);
+  }
+  if (w * h == 0 || vals.size() != w * h) return nullptr;
+  mb200_kernel_info *k = new_kernel(MB200_UserDefinedKernel, w, h);
+  if (!k) return nullptr;
+  k->x = ox; k->y = oy;
+  k->minimum = std::numeric_limits<double>::max();
+  k->maximum = -std::numeric_limits<double>::max();
+  bool any = false;
+  for (size_t n = 0; n < w * h; ++n) {
+    k->values[n] = vals[n];
+    if (std::isnan(vals[n])) continue;
+    any = true;
+    if (vals[n] < 0) k->negative_range += vals[n]; else k->positive_range += vals[n];
+    if (vals[n] < k->minimum) k->minimum = vals[n];
+    if (vals[n] > k->maximum) k->maximum = vals[n];
+  }
+  if (!any) { mb200_destroy_kernel_info(k); return nullptr; }
+  return k;
+}
+
+struct NamedKernel { const char *name; int type; };
+const NamedKernel kNames[] = {
+  {"blur", MB200_BlurKernel}, {"gaussian", MB200_GaussianKernel}, {"dog", MB200_DoGKernel},
+  {"log", MB200_LoGKernel}, {"disk", MB200_DiskKernel}, {"square", MB200_SquareKernel},
+  {"diamond", MB200_DiamondKernel}, {"octagon", MB200_OctagonKernel}, {"plus", MB200_PlusKernel},
+  {"cross", MB200_CrossKernel}, {"rectangle", MB200_RectangleKernel}, {"unity", MB200_UnityKernel},
+  {"binomial", MB200_BinomialKernel},
+};
+
+// morphology.c:372 ParseKernelName (+ the per-type argument defaults :426-470)
+mb200_kernel_info *parse_named_kernel(const std::string &def, bool *was_named) {
+  size_t i = 0;
+  while (i < def.size() && std::isspace(static_cast<unsigned char>(def[i]))) ++i;
+  size_t j = i;
+  while (j < def.size() && std::isalpha(static_cast<unsigned char>(def[j]))) ++j;
+  const std::string name = lower(def.substr(i, j - i));
+  int type = -1;
+  for (const NamedKernel &n : kNames) if (name == n.name) type = n.type;
+  *was_named = (type >= 0);
+  if (type < 0) return nullptr;
+  while (j < def.size() && (std::isspace(static_cast<unsigned char>(def[j])) || def[j] == ',' || def[j] == ':')) ++j;
+  Geometry g = parse_geometry(def.substr(j));
+  if (!g.ok) return nullptr;
+  if (g.area || g.greater || g.less) return nullptr;     // rotated kernel lists: unsupported
+  switch (type) {
+    case MB200_UnityKernel: if (!g.has_rho) g.rho = 1.0; break;
+    case MB200_SquareKernel: case MB200_DiamondKernel: case MB200_OctagonKernel:
+    case MB200_DiskKernel: case MB200_PlusKernel: case MB200_CrossKernel:
+      if (!g.has_sigma) g.sigma = 1.0; break;
+    case MB200_RectangleKernel:
+      if (!g.has_rho) g.rho = g.sigma;
+      if (g.rho < 1.0) g.rho = 3;
+      if (g.sigma < 1.0) g.sigma = g.rho;
+      if (!g.has_xi) g.xi = static_cast<double>((static_cast<long>(g.rho) - 1) / 2);
+      if (!g.has_psi) g.psi = static_cast<double>((static_cast<long>(g.sigma) - 1) / 2);
+      break;
+    default: break;
+  }
+  return mb200_acquire_kernel_builtin(type, g.rho, g.sigma, g.xi, g.psi);
+}
+
+// morphology.c:4258 RotateKernelInfo, restricted to what a single kernel needs:
+// +-90 transposes of 1-D kernels / 90-degree turns of squares, and 180 reflection.
+void rotate_kernel(mb200_kernel_info *k, double angle) {
+  angle = std::fmod(angle, 360.0);
+  if (angle < 0) angle += 360.0;
+  if (337.5 < angle || angle <= 22.5) return;
+  switch (k->type) {
+    case MB200_GaussianKernel: case MB200_DoGKernel: case MB200_LoGKernel: case MB200_DiskKernel:
+    case MB200_SquareKernel: case MB200_DiamondKernel: case MB200_PlusKernel: case MB200_CrossKernel:
+      return;
+    case MB200_BlurKernel:
+      if (135.0 < angle && angle <= 225.0) return;
+      if (225.0 < angle && angle <= 315.0) angle -= 180;
+      break;
+    default: break;
+  }
+  if (45.0 < std::fmod(angle, 180.0) && std::fmod(angle, 180.0) <= 135.0) {
+    if (k->width == 1 || k->height == 1) {
+      std::swap(k->width, k->height);
+      std::swap(k->x, k->y);
+      if (k->width == 1) { angle = std::fmod(angle + 270.0, 360.0); k->angle = std::fmod(k->angle + 90.0, 360.0); }
+      else { angle = std::fmod(angle + 90.0, 360.0); k->angle = std::fmod(k->angle + 270.0, 360.0); }
+    } else if (k->width == k->height) {
+      const long W = static_cast<long>(k->width), H = static_cast<long>(k->height);
+      double *v = k->values;
+      for (long i = 0, x = W - 1; i <= x; ++i, --x)
+        for (long j = 0, y = H - 1; j < y; ++j, --y) {
+          const double t = v[i + j * W];
+          v[i + j * W] = v[j + x * W];
+          v[j + x * W] = v[x + y * W];
+          v[x + y * W] = v[y + i * W];
+          v[y + i * W] = t;
+        }
+      const long x = k->x * 2 - W + 1, y = k->y * 2 - H + 1;
+      k->x = (-y + W - 1) / 2;
+      k->y = (+x + H - 1) / 2;
+      angle = std::fmod(angle + 270.0, 360.0);
+      k->angle = std::fmod(k->angle + 90.0, 360.0);
+    }
+  }
+  if (135.0 < angle && angle <= 225.0) {
+    const size_t n = k->width * k->height;
+    for (size_t i = 0, j = n - 1; i < j; ++i, --j) std::swap(k->values[i], k->values[j]);
+    k->x = static_cast<long>(k->width) - k->x - 1;
+    k->y = static_cast<long>(k->height) - k->y - 1;
+    k->angle = std::fmod(k->angle + 180.0, 360.0);
+  }
+}
+
+}  // namespace
+
+namespace mb200 {
+void rotate_kernel_info(mb200_kernel_info *k, double angle) {
+  for (; k; k = k->next) rotate_kernel(k, angle);
+}
+}  // namespace mb200
+
+extern "C" {
+
+size_t mb200_optimal_kernel_width_1d(double radius, double sigma) {   // gem.c:262
+  if (radius > kEps) return static_cast<size_t>(2.0 * std::ceil(radius) + 1.0);
+  const double gamma = std::fabs(sigma);
+  if (gamma <= kEps) return 3;
+  const double alpha = perceptible_reciprocal(2.0 * gamma * gamma);
+  const double beta = perceptible_reciprocal(kSq2Pi * gamma);
+  size_t width = 5;
+  for (;; width += 2) {
+    const long j = static_cast<long>(width - 1) / 2;
+    double normalize = 0.0;
+    for (long i = -j; i <= j; ++i) normalize += std::exp(-(static_cast<double>(i * i)) * alpha) * beta;
+    const double value = std::exp(-(static_cast<double>(j * j)) * alpha) * beta / normalize;
+    if (value < kQuantumScale || value < kEps) break;
+  }
+  return width - 2;
+}
+
+size_t mb200_optimal_kernel_width_2d(double radius, double sigma) {   // gem.c:302
+  if (radius > kEps) return static_cast<size_t>(2.0 * std::ceil(radius) + 1.0);
+  const double gamma = std::fabs(sigma);
+  if (gamma <= kEps) return 3;
+  const double alpha = perceptible_reciprocal(2.0 * gamma * gamma);
+  const double beta = perceptible_reciprocal(k2Pi * gamma * gamma);
+  size_t width = 5;
+  for (;; width += 2) {
+    const long j = static_cast<long>(width - 1) / 2;
+    double normalize = 0.0;
+    for (long v = -j; v <= j; ++v)
+      for (long u = -j; u <= j; ++u)
+        normalize += std::exp(-(static_cast<double>(u * u + v * v)) * alpha) * beta;
+    const double value = std::exp(-(static_cast<double>(j * j)) * alpha) * beta / normalize;
+    if (value < kQuantumScale || value < kEps) break;
+  }
+  return width - 2;
+}
+
+void mb200_scale_kernel_info(mb200_kernel_info *kernel, double scaling_factor, int flags) {  // :4571
+  if (!kernel) return;
+  if (kernel->next) mb200_scale_kernel_info(kernel->next, scaling_factor, flags);
+  double pos_scale = 1.0, neg_scale;
+  if (flags & 1) {
+    if (std::fabs(kernel->positive_range + kernel->negative_range) >= kEps)
+      pos_scale = std::fabs(kernel->positive_range + kernel->negative_range);
+    else
+      pos_scale = kernel->positive_range;
+  }
+  if (flags & 2) {
+    pos_scale = std::fabs(kernel->positive_range) >= kEps ? kernel->positive_range : 1.0;
+    neg_scale = std::fabs(kernel->negative_range) >= kEps ? -kernel->negative_range : 1.0;
+  } else {
+    neg_scale = pos_scale;
+  }
+  pos_scale = scaling_factor / pos_scale;
+  neg_scale = scaling_factor / neg_scale;
+  const size_t n = kernel->width * kernel->height;
+  for (size_t i = 0; i < n; ++i)
+    if (!std::isnan(kernel->values[i])) kernel->values[i] *= (kernel->values[i] >= 0) ? pos_scale : neg_scale;
+  kernel->positive_range *= pos_scale;
+  kernel->negative_range *= neg_scale;
+  kernel->maximum *= (kernel->maximum >= 0.0) ? pos_scale : neg_scale;
+  kernel->minimum *= (kernel->minimum >= 0.0) ? pos_scale : neg_scale;
+  if (scaling_factor < kEps) {
+    std::swap(kernel->positive_range, kernel->negative_range);
+    kernel->maximum = kernel->minimum;
+    kernel->minimum = 1;
+  }
+}
+
+mb200_kernel_info *mb200_acquire_kernel_builtin(int type, double rho, double sigma_arg, double xi,
+                                               double psi) {
+  switch (type) {
+    case MB200_UnityKernel: {                                   // :1032
+      mb200_kernel_info *k = new_kernel(type, 1, 1);
+      if (!k) return nullptr;
+      k->maximum = k->values[0] = rho;
+      return k;
+    }
+    case MB200_GaussianKernel: case MB200_DoGKernel: case MB200_LoGKernel: {   // :1045
+      double sigma = std::fabs(sigma_arg);
+      const double sigma2 = std::fabs(xi);
+      size_t w;
+      if (rho >= 1.0) w = static_cast<size_t>(rho) * 2 + 1;
+      else if (type != MB200_DoGKernel || sigma >= sigma2) w = mb200_optimal_kernel_width_2d(rho, sigma);
+      else w = mb200_optimal_kernel_width_2d(rho, sigma2);
+      mb200_kernel_info *k = new_kernel(type, w, w);
+      if (!k) return nullptr;
+      centre_origin(k);
+      const long cx = k->x, cy = k->y, W = static_cast<long>(w);
+      auto fill = [&](double s, double sign) {
+        if (s > kEps) {
+          const double A = 1.0 / (2.0 * s * s);
+          const double B = 1.0 / (k2Pi * s * s);
+          size_t i = 0;
+          for (long v = -cy; v <= cy; ++v)
+            for (long u = -cx; u <= cx; ++u, ++i) {
+              const double g = std::exp(-(static_cast<double>(u * u + v * v)) * A) * B;
+              if (sign > 0) k->values[i] = g; else k->values[i] -= g;
+            }
+        } else {
+          if (sign > 0) { std::memset(k->values, 0, w * w * sizeof(double)); k->values[cx + cy * W] = 1.0; }
+          else k->values[cx + cy * W] -= 1.0;
+        }
+      };
+      if (type == MB200_GaussianKernel || type == MB200_DoGKernel) fill(sigma, +1.0);
+      if (type == MB200_DoGKernel) fill(sigma2, -1.0);
+      if (type == MB200_LoGKernel) {
+        if (sigma > kEps) {
+          const double A = 1.0 / (2.0 * sigma * sigma);
+          const double B = 1.0 / (kPi * sigma * sigma * sigma * sigma);
+          size_t i = 0;
+          for (long v = -cy; v <= cy; ++v)
+            for (long u = -cx; u <= cx; ++u, ++i) {
+              const double R = (static_cast<double>(u * u + v * v)) * A;
+              k->values[i] = (1 - R) * std::exp(-R) * B;
+            }
+        } else {
+          std::memset(k->values, 0, w * w * sizeof(double));
+          k->values[cx + cy * W] = 1.0;
+        }
+      }
+      calc_meta(k);
+      mb200_scale_kernel_info(k, 1.0, 2);
+      return k;
+    }
+    case MB200_BlurKernel: {                                    // :1140
+      double sigma = std::fabs(sigma_arg);
+      const size_t w = rho >= 1.0 ? static_cast<size_t>(rho) * 2 + 1 : mb200_optimal_kernel_width_1d(rho, sigma);
+      mb200_kernel_info *k = new_kernel(type, w, 1);
+      if (!k) return nullptr;
+      k->x = static_cast<long>((w - 1) / 2);
+      k->y = 0;
+      constexpr long kRank = 3;                                 // oversampling, :1161
+      const long v = static_cast<long>(w * kRank - 1) / 2;
+      if (sigma > kEps) {
+        sigma *= kRank;
+        const double alpha = 1.0 / (2.0 * sigma * sigma);
+        const double beta = 1.0 / (kSq2Pi * sigma);
+        for (long u = -v; u <= v; ++u)
+          k->values[(u + v) / kRank] += std::exp(-(static_cast<double>(u * u)) * alpha) * beta;
+      } else {
+        k->values[k->x] = 1.0;
+      }
+      calc_meta(k);
+      mb200_scale_kernel_info(k, 1.0, 2);
+      rotate_kernel(k, xi);
+      return k;
+    }
+    case MB200_BinomialKernel: {                                // :1333
+      const size_t w = rho < 1.0 ? 3 : static_cast<size_t>(rho) * 2 + 1;
+      mb200_kernel_info *k = new_kernel(type, w, w);
+      if (!k) return nullptr;
+      centre_origin(k);
+      // Pascal's triangle row (w-1), outer product, as the reference's fact() ratio
+      auto fact = [](size_t n) { size_t f = 1; for (size_t l = 2; l <= n; ++l) f = f * l; return f; };
+      const size_t order_f = fact(w - 1);
+      size_t i = 0;
+      for (size_t v = 0; v < w; ++v) {
+        const size_t alpha = order_f / (fact(v) * fact(w - v - 1));
+        for (size_t u = 0; u < w; ++u, ++i)
+          k->positive_range += k->values[i] =
+              static_cast<double>(alpha * order_f / (fact(u) * fact(w - u - 1)));
+      }
+      k->minimum = 1.0;
+      k->maximum = k->values[k->x + k->y * static_cast<long>(w)];
+      k->negative_range = 0.0;
+      return k;
+    }
+    case MB200_DiamondKernel: {                                 // :1537
+      const size_t w = rho < 1.0 ? 3 : static_cast<size_t>(rho) * 2 + 1;
+      return shape_kernel(type, w, sigma_arg,
+          [](long u, long v, const mb200_kernel_info *k) { return std::labs(u) + std::labs(v) <= k->x; }, true);
+    }
+    case MB200_OctagonKernel: {                                 // :1601
+      const size_t w = rho < 1.0 ? 5 : static_cast<size_t>(rho) * 2 + 1;
+      return shape_kernel(type, w, sigma_arg,
+          [](long u, long v, const mb200_kernel_info *k) { return std::labs(u) + std::labs(v) <= k->x + k->x / 2; }, true);
+    }
+    case MB200_DiskKernel: {                                    // :1625
+      long limit = static_cast<long>(rho * rho);
+      size_t w;
+      if (rho < 0.4) { w = 9; limit = 18; } else w = static_cast<size_t>(std::fabs(rho)) * 2 + 1;
+      return shape_kernel(type, w, sigma_arg,
+          [limit](long u, long v, const mb200_kernel_info *) { return u * u + v * v <= limit; }, true);
+    }
+    case MB200_PlusKernel: case MB200_CrossKernel: {            // :1651, :1673
+      const size_t w = rho < 1.0 ? 5 : static_cast<size_t>(rho) * 2 + 1;
+      mb200_kernel_info *k = (type == MB200_PlusKernel)
+          ? shape_kernel(type, w, sigma_arg, [](long u, long v, const mb200_kernel_info *) { return u == 0 || v == 0; }, false)
+          : shape_kernel(type, w, sigma_arg, [](long u, long v, const mb200_kernel_info *) { return u == v || u == -v; }, false);
+      if (k) k->positive_range = sigma_arg * (k->width * 2.0 - 1.0);
+      return k;
+    }
+    case MB200_SquareKernel: case MB200_RectangleKernel: {      // :1560
+      size_t w, h; long ox, oy; double scale;
+      if (type == MB200_SquareKernel) {
+        w = h = rho < 1.0 ? 3 : static_cast<size_t>(2 * rho + 1);
+        ox = oy = static_cast<long>((w - 1) / 2);
+        scale = sigma_arg;
+      } else {
+        if (rho < 1.0 || sigma_arg < 1.0) return nullptr;
+        w = static_cast<size_t>(rho); h = static_cast<size_t>(sigma_arg);
+        if (xi < 0.0 || xi > static_cast<double>(w) || psi < 0.0 || psi > static_cast<double>(h)) return nullptr;
+        ox = static_cast<long>(xi); oy = static_cast<long>(psi);
+        scale = 1.0;
+      }
+      mb200_kernel_info *k = new_kernel(type, w, h);
+      if (!k) return nullptr;
+      k->x = ox; k->y = oy;
+      const long n = static_cast<long>(w * h);
+      for (long i = 0; i < n; ++i) k->values[i] = scale;
+      k->minimum = k->maximum = scale;
+      k->positive_range = scale * n;
+      return k;
+    }
+    default:
+      return nullptr;
+  }
+}
+
+mb200_kernel_info *mb200_acquire_kernel_info(const char *kernel_string) {   // :485
+  if (!kernel_string) return nullptr;
+  std::string all(kernel_string);
+  mb200_kernel_info *head = nullptr, *tail = nullptr;
+  size_t pos = 0;
+  while (pos <= all.size()) {
+    size_t semi = all.find(';', pos);
+    if (semi == std::string::npos) semi = all.size();
+    std::string def = all.substr(pos, semi - pos);
+    pos = semi + 1;
+    bool blank = true;
+    for (char c : def) if (!std::isspace(static_cast<unsigned char>(c))) blank = false;
+    if (blank) { if (semi == all.size()) break; else continue; }
+    size_t first = 0;
+    while (first < def.size() && std::isspace(static_cast<unsigned char>(def[first]))) ++first;
+    mb200_kernel_info *k = nullptr;
+    if (std::isalpha(static_cast<unsigned char>(def[first]))) {
+      bool named = false;
+      k = parse_named_kernel(def, &named);
+      if (!named) k = parse_user_kernel(def);   // e.g. "nan,1,nan,..."
+    } else {
+      k = parse_user_kernel(def);
+    }
+    if (!k) { mb200_destroy_kernel_info(head); return nullptr; }
+    if (!head) head = k; else tail->next = k;
+    tail = k;
+    while (tail->next) tail = tail->next;
+    if (semi == all.size()) break;
+  }
+  return head;
+}
+
+mb200_kernel_info *mb200_clone_kernel_info(const mb200_kernel_info *kernel) {
+  if (!kernel) return nullptr;
+  mb200_kernel_info *k = new_kernel(kernel->type, kernel->width, kernel->height);
+  if (!k) return nullptr;
+  double *vals = k->values;
+  *k = *kernel;
+  k->values = vals;
+  std::memcpy(k->values, kernel->values, kernel->width * kernel->height * sizeof(double));
+  k->next = nullptr;
+  if (kernel->next) {
+    k->next = mb200_clone_kernel_info(kernel->next);
+    if (!k->next) return mb200_destroy_kernel_info(k);
+  }
+  return k;
+}
+
+mb200_kernel_info *mb200_destroy_kernel_info(mb200_kernel_info *kernel) {
+  while (kernel) {
+    mb200_kernel_info *next = kernel->next;
+    std::free(kernel->values);
+    std::free(kernel);
+    kernel = next;
+  }
+  return nullptr;
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+// mb200_internal.h -- shared declarations inside libmagickb200 (not installed).
+#pragma once
+
+#include "../../include/magick_b200.h"
+
+#include <cstddef>
+#include <cstdint>
+
+namespace mb200 {
+
+// ---- error plumbing (runtime.cu) -------------------------------------------
+int fail(int code, const char *fmt, ...);       // records thread-local message, returns code
+int cuda_fail(int cuda_error, const char *what); // wraps a cudaError_t
+void count_launch(unsigned n = 1);
+
+// ---- per-device state (runtime.cu) -----------------------------------------
+struct DeviceState;
+int ensure_device();                     // lazily initialises the current device; 0 or error
+void *default_stream();                  // library-owned stream of the current device
+int scratch(void **ptr, size_t bytes, int slot);   // grow-only device scratch buffers
+int sm_count();
+
+// ---- kernel helpers (kernel_info.cpp) --------------------------------------
+void rotate_kernel_info(mb200_kernel_info *k, double angle);
+
+// ---- channel traits (pixel.c:6356-6381) ------------------------------------
+inline bool has_alpha(int channels) { return channels == 2 || channels == 4; }
+
+// ---- device launchers -------------------------------------------------------
+// All take device pointers and a cudaStream_t (as void*).  Return 0 / MB200_E*.
+
+// conv1d.cu: one 1-D convolution pass (width-1 or height-1 kernel) with the
+// reference's edge clamp, reflected taps and alpha blending.  taps[] is in window
+// order (tap t multiplies the source sample at offset t - origin_offset).
+// axis 0 = along x (row path, morphology.c:2815), axis 1 = along y (column path :2654).
+// d_changed: device counter (may be null) incremented per changed channel value.
+int launch_conv1d(const float *src, float *dst, size_t width, size_t height, int channels,
+                  int axis, const double *taps_window_order, int ntaps, int origin_offset,
+                  double bias, double gamma_scale, unsigned long long *d_changed, void *stream);
+
+// conv2d.cu: general 2-D convolution / erode / dilate (MorphologyPrimitive row path)
+int launch_morph2d(const float *src, float *dst, size_t width, size_t height, int channels,
+                   int method, const double *kernel_window_order, int kw, int kh, int ox, int oy,
+                   double bias, double gamma_scale, unsigned long long *d_changed, void *stream);
+
+// resize.cu: one axis of ResizeImage.  Contribution table lives in device memory.
+int launch_resize_axis(const float *src, size_t width, size_t height, int channels, float *dst,
+                       size_t out_n, int axis, const int *d_start, const int *d_count,
+                       const double *d_weights, int max_taps, int max_span, void *stream);
+
+// colorspace.cu
+int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to, void *stream);
+
+// pointwise.cu
+int launch_unsharp_combine(const float *src, float *blur_inout, size_t n, double gain,
+                           double quantum_threshold, void *stream);
+
+}  // namespace mb200

@@ -1,0 +1,195 @@
+// morph2d.cu -- the general neighbourhood loop: 2-D convolution (GaussianBlurImage,
+// ConvolveImage with arbitrary KernelInfo), ErodeMorphology and DilateMorphology.
+//
+// Semantics: MorphologyPrimitive's row loop, MagickCore/morphology.c:2811-3220
+//   Convolve :2897-2979 (reflected kernel, NaN cells skipped, alpha blending),
+//   Erode :2980-3006 (kernel as is, cells >= 0.5, min starting from the centre value),
+//   Dilate :3007-3036 (reflected, cells > 0.5, max starting from 0.0),
+//   result = ClampToQuantum(PerceptibleReciprocal(gamma)*pixel) :3197, changed :3199.
+// Erode/Dilate only select input values, so they are computed in float and are
+// bit-exact by construction.
+//
+// Mapping: a 32x8-pixel output tile per CTA, source tile + halo staged (edge-clamped)
+// in shared memory with coalesced loads; taps are read from a small global table
+// with warp-uniform (broadcast) loads; the active-cell list is compacted on the host so
+// NaN cells cost nothing.  Convolution accumulates in FP64.
+#include "mb200_internal.h"
+
+#include <cuda_runtime.h>
+
+namespace mb200 {
+namespace {
+
+constexpr double kQuantumScale = 1.0 / 65535.0;
+constexpr double kEpsilon = 1.0e-12;
+constexpr int kTileW = 32, kTileH = 8;
+
+struct Cell { short du, dv; float pad; double k; };   // window offset (u,v) and tap (window order)
+
+struct Morph2dArgs {
+  const float *src;
+  float *dst;
+  int width, height, channels;
+  int ox, oy;            // window top-left = (x - ox, y - oy)
+  int kw, kh;
+  int ncells;
+  const Cell *cells;     // device
+  double bias;
+  double gamma_scale;    // column-path kh/count factor (morphology.c:2775), else 1
+  int method;
+  unsigned long long *changed;
+};
+
+__device__ __forceinline__ double precise_reciprocal_gamma(double gamma) {
+  if (fabs(gamma) >= kEpsilon) return 1.0 / gamma;
+  return gamma < 0.0 ? -1.0 / kEpsilon : 1.0 / kEpsilon;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(kTileW *kTileH) morph2d_kernel(const Morph2dArgs a) {
+  extern __shared__ __align__(16) float tile[];
+  const int tw = kTileW + a.kw - 1, th = kTileH + a.kh - 1;
+  const int bx = blockIdx.x * kTileW, by = blockIdx.y * kTileH;
+  const int tid = threadIdx.y * kTileW + threadIdx.x;
+  const int wmax = a.width - 1, hmax = a.height - 1;
+  // stage (tw x th) pixels, clamped
+  const int n = tw * th * CH;
+  for (int idx = tid; idx < n; idx += kTileW * kTileH) {
+    const int p = idx / CH, c = idx - p * CH;
+    const int ty = p / tw, tx = p - ty * tw;
+    const int sx = min(max(bx - a.ox + tx, 0), wmax);
+    const int sy = min(max(by - a.oy + ty, 0), hmax);
+    tile[idx] = __ldg(a.src + (static_cast<size_t>(sy) * a.width + sx) * CH + c);
+  }
+  __syncthreads();
+  const int x = bx + threadIdx.x, y = by + threadIdx.y;
+  if (x >= a.width || y >= a.height) return;
+  const float *win = tile + (threadIdx.y * tw + threadIdx.x) * CH;   // window top-left
+  const float *centre = win + (a.oy * tw + a.ox) * CH;
+  float *out = a.dst + (static_cast<size_t>(y) * a.width + x) * CH;
+  constexpr bool kHasAlpha = (CH == 2 || CH == 4);
+  unsigned nchanged = 0;
+
+  if (a.method == MB200_ConvolveMorphology) {
+    double pix[CH];
+    double gamma = 0.0;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) pix[c] = 0.0;
+    for (int i = 0; i < a.ncells; ++i) {
+      const Cell cell = a.cells[i];
+      const float *p = win + (cell.dv * tw + cell.du) * CH;
+      if (kHasAlpha) {
+        // premultiplied form of :2962-2977: sum K*(A*p), gamma' = sum K*A (QS folded at the end)
+        const double al = static_cast<double>(p[CH - 1]);
+        const double ka = cell.k * al;
+        gamma += ka;
+#pragma unroll
+        for (int c = 0; c < CH - 1; ++c) pix[c] = fma(ka, static_cast<double>(p[c]), pix[c]);
+        pix[CH - 1] = fma(cell.k, al, pix[CH - 1]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) pix[c] = fma(cell.k, static_cast<double>(p[c]), pix[c]);
+      }
+    }
+    if (kHasAlpha) {
+      const double r = precise_reciprocal_gamma(kQuantumScale * gamma) * a.gamma_scale;
+#pragma unroll
+      for (int c = 0; c < CH - 1; ++c) {
+        const double pixel = fma(kQuantumScale, pix[c], a.bias);
+        out[c] = static_cast<float>(r * pixel);
+        nchanged += fabs(pixel - static_cast<double>(centre[c])) >= kEpsilon;
+      }
+      const double pixel = a.bias + pix[CH - 1];
+      out[CH - 1] = static_cast<float>(a.gamma_scale * pixel);
+      nchanged += fabs(pixel - static_cast<double>(centre[CH - 1])) >= kEpsilon;
+    } else {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const double pixel = a.bias + pix[c];
+        out[c] = static_cast<float>(a.gamma_scale * pixel);
+        nchanged += fabs(pixel - static_cast<double>(centre[c])) >= kEpsilon;
+      }
+    }
+  } else {
+    const bool dilate = a.method == MB200_DilateMorphology;
+    float pix[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) pix[c] = dilate ? 0.0f : centre[c];
+    for (int i = 0; i < a.ncells; ++i) {
+      const Cell cell = a.cells[i];
+      const float *p = win + (cell.dv * tw + cell.du) * CH;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const float v = p[c];
+        if (dilate) { if (v > pix[c]) pix[c] = v; }
+        else { if (v < pix[c]) pix[c] = v; }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      out[c] = pix[c];
+      nchanged += fabs(static_cast<double>(pix[c]) - static_cast<double>(centre[c])) >= kEpsilon;
+    }
+  }
+  if (a.changed != nullptr && nchanged != 0) atomicAdd(a.changed, static_cast<unsigned long long>(nchanged));
+}
+
+}  // namespace
+
+int launch_morph2d(const float *src, float *dst, size_t width, size_t height, int channels, int method,
+                   const double *kernel_window_order, int kw, int kh, int ox, int oy, double bias,
+                   double gamma_scale, unsigned long long *d_changed, void *stream) {
+  if (width == 0 || height == 0 || channels < 1 || channels > 4 || kw < 1 || kh < 1)
+    return fail(MB200_EINVAL, "morph2d: bad geometry");
+  if (width > 0x3fffffffull || height > 0x3fffffffull) return fail(MB200_EINVAL, "morph2d: image too large");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // compact the active cells (NaN = not in the neighbourhood; erode/dilate thresholds)
+  const int total = kw * kh;
+  Cell *host = static_cast<Cell *>(malloc(sizeof(Cell) * static_cast<size_t>(total)));
+  if (!host) return fail(MB200_ENOMEM, "morph2d: host alloc");
+  int n = 0;
+  for (int v = 0; v < kh; ++v)
+    for (int u = 0; u < kw; ++u) {
+      const double k = kernel_window_order[v * kw + u];
+      if (k != k) continue;
+      if (method == MB200_ErodeMorphology && !(k >= 0.5)) continue;
+      if (method == MB200_DilateMorphology && !(k > 0.5)) continue;
+      host[n].du = static_cast<short>(u); host[n].dv = static_cast<short>(v); host[n].pad = 0.f; host[n].k = k;
+      ++n;
+    }
+  void *d_cells = nullptr;
+  cudaError_t e = cudaMallocAsync(&d_cells, sizeof(Cell) * static_cast<size_t>(total), s);   // stream-ordered: re-entrant
+  if (e != cudaSuccess) { free(host); return cuda_fail(e, "morph2d: tap table alloc"); }
+  e = cudaMemcpyAsync(d_cells, host, sizeof(Cell) * static_cast<size_t>(n), cudaMemcpyHostToDevice, s);
+  free(host);   // pageable source: the copy has been staged when the call returns
+  if (e != cudaSuccess) { cudaFreeAsync(d_cells, s); return cuda_fail(e, "morph2d: tap upload"); }
+
+  Morph2dArgs a{};
+  a.src = src; a.dst = dst;
+  a.width = static_cast<int>(width); a.height = static_cast<int>(height); a.channels = channels;
+  a.ox = ox; a.oy = oy; a.kw = kw; a.kh = kh; a.ncells = n;
+  a.cells = static_cast<const Cell *>(d_cells);
+  a.bias = bias; a.gamma_scale = gamma_scale; a.method = method; a.changed = d_changed;
+  const size_t smem = static_cast<size_t>(kTileW + kw - 1) * (kTileH + kh - 1) * channels * sizeof(float);
+  if (smem > 200 * 1024) { cudaFreeAsync(d_cells, s); return fail(MB200_EUNSUPPORTED, "morph2d: %dx%d kernel needs %zu bytes of shared memory", kw, kh, smem); }
+  dim3 grid((a.width + kTileW - 1) / kTileW, (a.height + kTileH - 1) / kTileH), block(kTileW, kTileH);
+#define MB200_LAUNCH(CH)                                                                         \
+  do {                                                                                           \
+    cudaFuncSetAttribute(morph2d_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+    morph2d_kernel<CH><<<grid, block, smem, s>>>(a);                                             \
+  } while (0)
+  switch (channels) {
+    case 1: MB200_LAUNCH(1); break;
+    case 2: MB200_LAUNCH(2); break;
+    case 3: MB200_LAUNCH(3); break;
+    default: MB200_LAUNCH(4); break;
+  }
+#undef MB200_LAUNCH
+  count_launch();
+  e = cudaGetLastError();
+  cudaFreeAsync(d_cells, s);
+  if (e != cudaSuccess) return cuda_fail(e, "morph2d launch");
+  return MB200_OK;
+}
+
+}  // namespace mb200

@@ -1,0 +1,199 @@
+// resize.cu -- one axis of ResizeImage: the weighted gather of HorizontalFilter
+// (MagickCore/resize.c:3333-3547) and VerticalFilter (:3549-3759).
+//
+// Per output sample o the host (resize_filter.cpp) has already produced exactly the
+// reference's contribution list: first source index start[o], tap count count[o] and
+// the density-normalised double weights.  The device evaluates
+//     plain channel : out = (float) sum_j w_j * p_j                          (:3456-3468)
+//     blend channel : a_j = w_j*QS*A_j ; out = (float)(PerceptibleReciprocal(sum a_j) *
+//                                                     sum a_j*p_j)           (:3472-3484)
+// in FP64.  The alpha weighting is applied as one premultiply per tap per pixel
+// (t = w*A; acc_c += t*p_c); sum t is at the same time the alpha channel's own result
+// and (up to the constant QS, which cancels) gamma.
+//
+// Mapping: one thread per output pixel (all channels, float4 loads for RGBA).
+//  axis 1 (vertical): lanes span 32 consecutive pixels of a row => 512-byte coalesced
+//    row reads; a thread produces several consecutive output rows so the overlapping
+//    source rows are re-read from L1; weights are warp-uniform broadcast loads.
+//  axis 0 (horizontal): lanes span consecutive OUTPUT columns; weights are stored
+//    tap-major ([tap][o]) so their loads are coalesced; source reads of neighbouring
+//    lanes fall in the same / adjacent 128-byte lines.
+#include "mb200_internal.h"
+
+#include <cuda_runtime.h>
+
+namespace mb200 {
+namespace {
+
+constexpr double kQuantumScale = 1.0 / 65535.0;
+constexpr double kEpsilon = 1.0e-12;
+
+struct ResizeArgs {
+  const float *src;
+  float *dst;
+  int width, height;      // source
+  int out_w, out_h;       // destination
+  int out_n;              // outputs along the filtered axis
+  const int *start;
+  const int *count;
+  const double *weights;  // tap-major: weights[j*out_n + o]
+  int lines_per_thread;
+};
+
+template <int CH>
+struct Pixel { float v[CH]; };
+
+template <int CH>
+__device__ __forceinline__ Pixel<CH> load_pixel(const float *p) {
+  Pixel<CH> r;
+  if (CH == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[CH - 1] = t.w;
+  } else if (CH == 2) {
+    const float2 t = __ldg(reinterpret_cast<const float2 *>(p));
+    r.v[0] = t.x; r.v[CH - 1] = t.y;
+  } else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) r.v[c] = __ldg(p + c);
+  }
+  return r;
+}
+
+template <int CH>
+__device__ __forceinline__ void store_pixel(float *p, const float (&o)[CH]) {
+  if (CH == 4) *reinterpret_cast<float4 *>(p) = make_float4(o[0], o[1], o[2], o[CH - 1]);
+  else if (CH == 2) *reinterpret_cast<float2 *>(p) = make_float2(o[0], o[CH - 1]);
+  else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) p[c] = o[c];
+  }
+}
+
+template <int CH>
+__device__ __forceinline__ void accumulate(double (&acc)[CH], double w, const Pixel<CH> &px) {
+  constexpr bool kAlpha = (CH == 2 || CH == 4);
+  if (kAlpha) {
+    const double t = w * static_cast<double>(px.v[CH - 1]);
+#pragma unroll
+    for (int c = 0; c < CH - 1; ++c) acc[c] = fma(t, static_cast<double>(px.v[c]), acc[c]);
+    acc[CH - 1] += t;
+  } else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = fma(w, static_cast<double>(px.v[c]), acc[c]);
+  }
+}
+
+template <int CH>
+__device__ __forceinline__ void finish(const double (&acc)[CH], float (&out)[CH]) {
+  constexpr bool kAlpha = (CH == 2 || CH == 4);
+  if (kAlpha) {
+    const double gamma = kQuantumScale * acc[CH - 1];
+    if (fabs(gamma) >= kEpsilon) {
+      const double r = 1.0 / acc[CH - 1];
+#pragma unroll
+      for (int c = 0; c < CH - 1; ++c) out[c] = static_cast<float>(r * acc[c]);
+    } else {
+      const double r = gamma < 0.0 ? -1.0 / kEpsilon : 1.0 / kEpsilon;
+#pragma unroll
+      for (int c = 0; c < CH - 1; ++c) out[c] = static_cast<float>(r * (kQuantumScale * acc[c]));
+    }
+    out[CH - 1] = static_cast<float>(acc[CH - 1]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) out[c] = static_cast<float>(acc[c]);
+  }
+}
+
+// vertical: grid (ceil(width/128), ceil(out_h/lines_per_thread))
+template <int CH>
+__global__ void __launch_bounds__(128) resize_vertical_kernel(const ResizeArgs a) {
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  if (x >= a.width) return;
+  const int o0 = blockIdx.y * a.lines_per_thread;
+  const int o1 = min(o0 + a.lines_per_thread, a.out_h);
+  const float *col = a.src + static_cast<size_t>(x) * CH;
+  const size_t pitch = static_cast<size_t>(a.width) * CH;
+  for (int o = o0; o < o1; ++o) {
+    const int first = __ldg(a.start + o), n = __ldg(a.count + o);
+    if (n <= 0) continue;                               // resize.c:3440 leaves the row untouched
+    double acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = 0.0;
+    const float *p = col + static_cast<size_t>(first) * pitch;
+    for (int j = 0; j < n; ++j, p += pitch) {
+      const double w = __ldg(a.weights + static_cast<size_t>(j) * a.out_n + o);
+      accumulate<CH>(acc, w, load_pixel<CH>(p));
+    }
+    float out[CH];
+    finish<CH>(acc, out);
+    store_pixel<CH>(a.dst + (static_cast<size_t>(o) * a.out_w + x) * CH, out);
+  }
+}
+
+// horizontal: grid (ceil(out_w/128), ceil(height/lines_per_thread))
+template <int CH>
+__global__ void __launch_bounds__(128) resize_horizontal_kernel(const ResizeArgs a) {
+  const int o = blockIdx.x * 128 + threadIdx.x;
+  if (o >= a.out_w) return;
+  const int y0 = blockIdx.y * a.lines_per_thread;
+  const int y1 = min(y0 + a.lines_per_thread, a.height);
+  const int first = __ldg(a.start + o), n = __ldg(a.count + o);
+  if (n <= 0) return;
+  for (int y = y0; y < y1; ++y) {
+    double acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = 0.0;
+    const float *p = a.src + (static_cast<size_t>(y) * a.width + first) * CH;
+    for (int j = 0; j < n; ++j, p += CH) {
+      const double w = __ldg(a.weights + static_cast<size_t>(j) * a.out_n + o);
+      accumulate<CH>(acc, w, load_pixel<CH>(p));
+    }
+    float out[CH];
+    finish<CH>(acc, out);
+    store_pixel<CH>(a.dst + (static_cast<size_t>(y) * a.out_w + o) * CH, out);
+  }
+}
+
+}  // namespace
+
+int launch_resize_axis(const float *src, size_t width, size_t height, int channels, float *dst, size_t out_n,
+                       int axis, const int *d_start, const int *d_count, const double *d_weights,
+                       int /*max_taps*/, int /*max_span*/, void *stream) {
+  if (width == 0 || height == 0 || out_n == 0 || channels < 1 || channels > 4)
+    return fail(MB200_EINVAL, "resize: bad geometry");
+  if (width > 0x3fffffffull || height > 0x3fffffffull || out_n > 0x3fffffffull)
+    return fail(MB200_EINVAL, "resize: image too large");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ResizeArgs a{};
+  a.src = src; a.dst = dst;
+  a.width = static_cast<int>(width); a.height = static_cast<int>(height);
+  a.out_n = static_cast<int>(out_n);
+  a.start = d_start; a.count = d_count; a.weights = d_weights;
+  a.lines_per_thread = 8;
+  if (axis == 1) {
+    a.out_w = a.width; a.out_h = a.out_n;
+    dim3 grid((a.width + 127) / 128, (a.out_h + a.lines_per_thread - 1) / a.lines_per_thread);
+    switch (channels) {
+      case 1: resize_vertical_kernel<1><<<grid, 128, 0, s>>>(a); break;
+      case 2: resize_vertical_kernel<2><<<grid, 128, 0, s>>>(a); break;
+      case 3: resize_vertical_kernel<3><<<grid, 128, 0, s>>>(a); break;
+      default: resize_vertical_kernel<4><<<grid, 128, 0, s>>>(a); break;
+    }
+  } else {
+    a.out_w = a.out_n; a.out_h = a.height;
+    dim3 grid((a.out_w + 127) / 128, (a.height + a.lines_per_thread - 1) / a.lines_per_thread);
+    if (grid.y > 65535) return fail(MB200_EINVAL, "resize: too many rows");
+    switch (channels) {
+      case 1: resize_horizontal_kernel<1><<<grid, 128, 0, s>>>(a); break;
+      case 2: resize_horizontal_kernel<2><<<grid, 128, 0, s>>>(a); break;
+      case 3: resize_horizontal_kernel<3><<<grid, 128, 0, s>>>(a); break;
+      default: resize_horizontal_kernel<4><<<grid, 128, 0, s>>>(a); break;
+    }
+  }
+  count_launch();
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "resize launch");
+  return MB200_OK;
+}
+
+}  // namespace mb200

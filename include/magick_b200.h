@@ -1,0 +1,232 @@
+/*
+  magick_b200.h -- C-ABI of libmagickb200.so: ImageMagick's per-pixel hot path
+  (separable / 2-D convolution, erode/dilate morphology, filtered resize,
+  sRGB<->Lab/XYZ/linear colourspace) as hand-written sm_100a CUDA kernels.
+
+  Plain pointers and sizes only.  No torch / CUDA types in the signatures (a
+  CUDA stream is passed as void*).  Pixel buffers are the reference's own pixel
+  cache layout for its default Q16-HDRI build (MagickCore/cache.c:5142,
+  MagickCore/pixel.c:6158): tightly packed, row-major, channel-interleaved
+  float32 Quantum, values 0..65535, `channels` floats per pixel:
+
+      channels 1 = Gray, 2 = Gray+Alpha, 3 = RGB, 4 = RGBA (alpha last).
+
+  Images with alpha give their colour channels the Blend trait exactly like
+  MagickCore/pixel.c:6356-6381 (alpha-weighted convolution / resize).
+
+  Every entry point names the reference interface it replaces.  Return value:
+  0 (MB200_OK) on success, a negative MB200_E* code otherwise; the message is
+  available from mb200_last_error() (thread-local).  There is NO CPU fallback:
+  when no sm_100 device is usable the calls fail with MB200_ENODEVICE -- the
+  MagickCore shim (imagemagick_b200/shim) then returns NULL so that the caller's
+  stock CPU path runs, which is the accelerate hook contract of
+  MagickCore/effect.c:783-787 and MagickCore/resize.c:3818-3826.
+*/
+#ifndef MAGICK_B200_H
+#define MAGICK_B200_H
+
+#include <stddef.h>
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+# define MB200_API
+#else
+# define MB200_API __attribute__((visibility("default")))
+#endif
+
+enum {
+  MB200_OK = 0,
+  MB200_EINVAL = -1,        /* bad argument */
+  MB200_ENODEVICE = -2,     /* no usable CUDA device / wrong architecture */
+  MB200_ECUDA = -3,         /* CUDA runtime error (see mb200_last_error) */
+  MB200_ENOMEM = -4,
+  MB200_EUNSUPPORTED = -5   /* valid in the reference but not implemented here:
+                               the shim must fall back to the CPU path */
+};
+
+/* MagickCore/morphology.h:69-99 MorphologyMethod -- same numeric values */
+typedef enum {
+  MB200_UndefinedMorphology = 0,
+  MB200_ConvolveMorphology = 1,
+  MB200_CorrelateMorphology = 2,
+  MB200_ErodeMorphology = 3,
+  MB200_DilateMorphology = 4,
+  MB200_OpenMorphology = 8,
+  MB200_CloseMorphology = 9,
+  MB200_SmoothMorphology = 12,
+  MB200_EdgeInMorphology = 13,
+  MB200_EdgeOutMorphology = 14,
+  MB200_EdgeMorphology = 15,
+  MB200_TopHatMorphology = 16,
+  MB200_BottomHatMorphology = 17
+} mb200_morphology_method;
+
+/* MagickCore/resample.h:32-69 FilterType -- same numeric values */
+typedef enum {
+  MB200_UndefinedFilter = 0, MB200_PointFilter, MB200_BoxFilter, MB200_TriangleFilter,
+  MB200_HermiteFilter, MB200_HannFilter, MB200_HammingFilter, MB200_BlackmanFilter,
+  MB200_GaussianFilter, MB200_QuadraticFilter, MB200_CubicFilter, MB200_CatromFilter,
+  MB200_MitchellFilter, MB200_JincFilter, MB200_SincFilter, MB200_SincFastFilter,
+  MB200_KaiserFilter, MB200_WelchFilter, MB200_ParzenFilter, MB200_BohmanFilter,
+  MB200_BartlettFilter, MB200_LagrangeFilter, MB200_LanczosFilter, MB200_LanczosSharpFilter,
+  MB200_Lanczos2Filter, MB200_Lanczos2SharpFilter, MB200_RobidouxFilter,
+  MB200_RobidouxSharpFilter, MB200_CosineFilter, MB200_SplineFilter,
+  MB200_LanczosRadiusFilter, MB200_CubicSplineFilter, MB200_MagicKernelSharp2013Filter,
+  MB200_MagicKernelSharp2021Filter, MB200_SentinelFilter
+} mb200_filter_type;
+
+/* MagickCore/colorspace.h:27-67 ColorspaceType -- same numeric values */
+typedef enum {
+  MB200_LabColorspace = 11,
+  MB200_RGBColorspace = 21,      /* linear RGB */
+  MB200_sRGBColorspace = 23,
+  MB200_XYZColorspace = 26
+} mb200_colorspace;
+
+/* Mirror of KernelInfo (MagickCore/morphology.h:102-130): a singly linked list
+   of width x height double arrays, NaN == "not part of the neighbourhood",
+   (x,y) the origin.  `type` is an mb200_kernel_type (needed only because the
+   reference's 180-degree RotateKernelInfo is a no-op for some built-ins,
+   MagickCore/morphology.c:4281-4305). */
+typedef enum {
+  MB200_UserDefinedKernel = 0, MB200_BlurKernel, MB200_GaussianKernel, MB200_DiskKernel,
+  MB200_SquareKernel, MB200_DiamondKernel, MB200_OctagonKernel, MB200_PlusKernel,
+  MB200_CrossKernel, MB200_RectangleKernel, MB200_UnityKernel, MB200_DoGKernel,
+  MB200_LoGKernel, MB200_BinomialKernel
+} mb200_kernel_type;
+
+typedef struct mb200_kernel_info {
+  int type;
+  size_t width, height;
+  long x, y;
+  double *values;
+  double minimum, maximum, negative_range, positive_range, angle;
+  struct mb200_kernel_info *next;
+} mb200_kernel_info;
+
+/* ------------------------------------------------------------- runtime ---- */
+
+/* Number of usable sm_100 devices (0 when there is no GPU / driver). */
+MB200_API int mb200_device_count(void);
+/* Bind the calling thread (and the library's per-device state) to `device`.
+   One process per GPU is the intended deployment (imagemagick_b200.dist). */
+MB200_API int mb200_set_device(int device);
+MB200_API const char *mb200_last_error(void);
+MB200_API const char *mb200_version(void);
+/* Number of kernel launches issued by this library since process start
+   (bench.py's "gpu_launches"). */
+MB200_API unsigned long long mb200_launch_count(void);
+/* Block until all work queued by this library on `stream` (NULL = the library's
+   own stream for the current device) has finished. */
+MB200_API int mb200_synchronize(void *stream);
+
+/* Device pixel-cache staging (the CUDA analogue of AcquireMagickCLCacheInfo /
+   GetAuthenticOpenCLBuffer, MagickCore/opencl.c:528-553, MagickCore/cache.c:1259). */
+MB200_API int mb200_malloc(void **dev_ptr, size_t bytes);
+MB200_API int mb200_free(void *dev_ptr);
+MB200_API int mb200_malloc_host(void **host_ptr, size_t bytes);   /* pinned */
+MB200_API int mb200_free_host(void *host_ptr);
+MB200_API int mb200_upload(void *dev_dst, const void *host_src, size_t bytes, void *stream);
+MB200_API int mb200_download(void *host_dst, const void *dev_src, size_t bytes, void *stream);
+
+/* ------------------------------------------------------- kernel builders ---- */
+
+/* AcquireKernelInfo (MagickCore/morphology.c:485): parses the reference's kernel
+   strings -- "blur:RxS[+angle]", "gaussian:RxS", "dog:", "log:", "disk:R[,scale]",
+   "square:", "diamond:", "octagon:", "plus:", "cross:", "rectangle:WxH+X+Y",
+   "unity", "binomial:", user arrays "WxH+X+Y:v,v,..." and old-style "v,v,v,..." --
+   and ';'-separated lists.  Returns NULL on a parse error / unsupported name. */
+MB200_API mb200_kernel_info *mb200_acquire_kernel_info(const char *kernel_string);
+/* AcquireKernelBuiltIn (MagickCore/morphology.c:950) with GeometryInfo rho,sigma,xi,psi. */
+MB200_API mb200_kernel_info *mb200_acquire_kernel_builtin(int type, double rho, double sigma,
+                                                         double xi, double psi);
+MB200_API mb200_kernel_info *mb200_clone_kernel_info(const mb200_kernel_info *kernel);
+MB200_API mb200_kernel_info *mb200_destroy_kernel_info(mb200_kernel_info *kernel);
+/* ScaleKernelInfo (MagickCore/morphology.c:4571); flags: 1 = NormalizeValue,
+   2 = CorrelateNormalizeValue. */
+MB200_API void mb200_scale_kernel_info(mb200_kernel_info *kernel, double scaling_factor, int flags);
+/* GetOptimalKernelWidth1D/2D (MagickCore/gem.c:262, :302). */
+MB200_API size_t mb200_optimal_kernel_width_1d(double radius, double sigma);
+MB200_API size_t mb200_optimal_kernel_width_2d(double radius, double sigma);
+
+/* Resize contribution table of one axis: exactly the start/stop/weights that
+   HorizontalFilter / VerticalFilter (MagickCore/resize.c:3398-3443, :3614-3657)
+   compute per output column/row.  weights is out_n * max_taps doubles (row o at
+   weights[o*max_taps]); returns max_taps (>0) or a negative error.  Pass
+   start/count/weights == NULL to only query max_taps. */
+MB200_API long mb200_resize_contributions(int filter, size_t in_n, size_t out_n, double factor,
+                                         long *start, int *count, double *weights,
+                                         size_t max_taps);
+/* GetResizeFilterWeight / GetResizeFilterSupport (MagickCore/resize.c:1690, :1656). */
+MB200_API double mb200_resize_filter_weight(int filter, double x);
+MB200_API double mb200_resize_filter_support(int filter);
+
+/* --------------------------------------- device-resident operators (HBM) ---- */
+/* src/dst are DEVICE pointers (from mb200_malloc or any CUDA allocation, e.g. a
+   torch tensor's data_ptr()); they must not alias unless stated.  `stream` is a
+   cudaStream_t passed as void* (NULL = library stream).  Calls are asynchronous
+   with respect to the host unless a `changed` result is requested. */
+
+/* MorphologyPrimitive (MagickCore/morphology.c:2566-3227) for ONE kernel:
+   method in {Convolve, Erode, Dilate}.  *changed (host, may be NULL) receives the
+   reference's return value (pixels changed).  Width-1 Convolve kernels take the
+   reference's column path semantics (:2654-2807). */
+MB200_API int mb200_morphology_primitive_dev(const float *src, float *dst, size_t width,
+    size_t height, int channels, int method, const mb200_kernel_info *kernel, double bias,
+    long long *changed, void *stream);
+
+/* MorphologyImage / MorphologyApply (MagickCore/morphology.c:4129, :3634) with the
+   default compose (re-iterate kernel lists): iterations (<0 = until unchanged),
+   compound methods Open / Close / Smooth and Correlate (Edge, TopHat and
+   BottomHat variants need CompositeImage and return MB200_EUNSUPPORTED). */
+MB200_API int mb200_morphology_image_dev(const float *src, float *dst, size_t width,
+    size_t height, int channels, int method, long iterations,
+    const mb200_kernel_info *kernel, double bias, void *stream);
+
+/* ConvolveImage (MagickCore/effect.c:1170) */
+MB200_API int mb200_convolve_image_dev(const float *src, float *dst, size_t width, size_t height,
+    int channels, const mb200_kernel_info *kernel, void *stream);
+/* BlurImage (MagickCore/effect.c:765) == AccelerateBlurImage (accelerate-private.h:36) */
+MB200_API int mb200_blur_image_dev(const float *src, float *dst, size_t width, size_t height,
+    int channels, double radius, double sigma, void *stream);
+/* GaussianBlurImage (MagickCore/effect.c:1709) */
+MB200_API int mb200_gaussian_blur_image_dev(const float *src, float *dst, size_t width,
+    size_t height, int channels, double radius, double sigma, void *stream);
+/* UnsharpMaskImage (MagickCore/effect.c:4256) == AccelerateUnsharpMaskImage (:46) */
+MB200_API int mb200_unsharp_mask_image_dev(const float *src, float *dst, size_t width,
+    size_t height, int channels, double radius, double sigma, double gain, double threshold,
+    void *stream);
+/* ResizeImage (MagickCore/resize.c:3761) == AccelerateResizeImage (:43).  filter
+   UndefinedFilter applies the reference's own default choice (:3806-3816). */
+MB200_API int mb200_resize_image_dev(const float *src, size_t width, size_t height, int channels,
+    float *dst, size_t out_width, size_t out_height, int filter, void *stream);
+/* TransformImageColorspace (MagickCore/colorspace.c:1751), in place on `buf`. */
+MB200_API int mb200_transform_colorspace_dev(float *buf, size_t width, size_t height,
+    int channels, int from_colorspace, int to_colorspace, void *stream);
+
+/* ---------------------------------------------- host-buffer operators ---- */
+/* Same operators on HOST buffers: stage into HBM, run, copy back, synchronise.
+   These are what the MagickCore shim calls with the pixel-cache pointers
+   (GetVirtualPixels / GetAuthenticPixels, MagickCore/cache.c:3257, :1490). */
+MB200_API int mb200_blur_image(const float *src, float *dst, size_t width, size_t height,
+    int channels, double radius, double sigma);
+MB200_API int mb200_gaussian_blur_image(const float *src, float *dst, size_t width, size_t height,
+    int channels, double radius, double sigma);
+MB200_API int mb200_convolve_image(const float *src, float *dst, size_t width, size_t height,
+    int channels, const mb200_kernel_info *kernel);
+MB200_API int mb200_morphology_image(const float *src, float *dst, size_t width, size_t height,
+    int channels, int method, long iterations, const mb200_kernel_info *kernel, double bias);
+MB200_API int mb200_unsharp_mask_image(const float *src, float *dst, size_t width, size_t height,
+    int channels, double radius, double sigma, double gain, double threshold);
+MB200_API int mb200_resize_image(const float *src, size_t width, size_t height, int channels,
+    float *dst, size_t out_width, size_t out_height, int filter);
+MB200_API int mb200_transform_colorspace(float *buf, size_t width, size_t height, int channels,
+    int from_colorspace, int to_colorspace);
+
+#if defined(__cplusplus)
+}
+#endif
+#endif /* MAGICK_B200_H */

@@ -1,0 +1,222 @@
+"""Parity of the CUDA path (through the C-ABI) against the oracle on seeded inputs.
+
+Bar (BASELINE.json north_star): bit-exact for erode/dilate (selection ops), <= 1 ULP of
+the float Quantum for convolution / resize / colourspace.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import util
+from util import P, make_image, max_ulp, oracle
+
+pytestmark = pytest.mark.gpu
+
+im = pytest.importorskip("imagemagick_b200")
+
+
+def _dev(a: np.ndarray):
+    import torch
+    return im.Image(torch.from_numpy(a).cuda())
+
+
+def _host(img) -> np.ndarray:
+    return img.pixels.cpu().numpy() if img.on_device else img.pixels
+
+
+def orc(fn, src, *args):
+    h, w, ch = src.shape
+    dst = np.empty_like(src)
+    assert getattr(oracle(), fn)(P(src), P(dst), w, h, ch, *args) == 0
+    return dst
+
+
+SIZES = [(67, 45), (256, 131), (1, 1), (5, 300), (300, 3)]
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["noise", "alpha_blocks", "hdr"])
+@pytest.mark.parametrize("radius,sigma", [(0.0, 2.0), (0.0, 4.0), (0.0, 0.5), (3.0, 1.5), (0.0, 1.0), (0.0, 3.0)])
+def test_blur_host_path(ch, kind, radius, sigma):
+    for (w, h) in SIZES[:3]:
+        src = make_image(w, h, ch, seed=w * 7 + ch, kind=kind)
+        want = orc("orc_blur", src, radius, sigma)
+        got = im.BlurImage(im.Image(src), radius, sigma).pixels
+        assert max_ulp(got, want) <= 1, (w, h, ch, kind, radius, sigma)
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("sigma", [2.0, 4.0, 6.0, 8.0])
+def test_blur_device_path(ch, sigma):
+    for (w, h) in SIZES:
+        src = make_image(w, h, ch, seed=w + h + ch)
+        want = orc("orc_blur", src, 0.0, sigma)
+        got = _host(im.BlurImage(_dev(src), 0.0, sigma))
+        assert max_ulp(got, want) <= 1, (w, h, ch, sigma)
+
+
+def test_blur_config1_1024_rgba_sigma2():
+    """BASELINE.json configs[0]: 1024x1024 RGBA GaussianBlur sigma=2 (BlurImage(0,2))."""
+    src = make_image(1024, 1024, 4, seed=42)
+    want = orc("orc_blur", src, 0.0, 2.0)
+    got = _host(im.BlurImage(_dev(src), 0.0, 2.0))
+    d = util.ulp_distance(got, want)
+    assert d.max() <= 1
+    assert (d == 0).mean() > 0.999
+
+
+def test_blur_wide_kernel_falls_back_to_generic():
+    src = make_image(200, 90, 4, seed=3)
+    want = orc("orc_blur", src, 0.0, 12.0)       # 97 taps > templated sizes
+    got = _host(im.BlurImage(_dev(src), 0.0, 12.0))
+    assert max_ulp(got, want) <= 1
+
+
+@pytest.mark.parametrize("ch", [1, 3, 4])
+@pytest.mark.parametrize("sigma", [1.0, 2.0])
+def test_gaussian_blur_2d(ch, sigma):
+    src = make_image(97, 61, ch, seed=11, kind="alpha_blocks")
+    want = orc("orc_gaussian_blur", src, 0.0, sigma)
+    assert max_ulp(im.GaussianBlurImage(im.Image(src), 0.0, sigma).pixels, want) <= 1
+    assert max_ulp(_host(im.GaussianBlurImage(_dev(src), 0.0, sigma)), want) <= 1
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+def test_unsharp(ch):
+    src = make_image(120, 77, ch, seed=5)
+    want = orc("orc_unsharp", src, 0.0, 2.0, 1.5, 0.02)
+    got = _host(im.UnsharpMaskImage(_dev(src), 0.0, 2.0, 1.5, 0.02))
+    d = util.ulp_distance(got, want)
+    # where the blur differs by 1 ULP the amplified difference may round differently; the
+    # pass-through branch must be exact
+    assert d.max() <= 2
+    assert (d == 0).mean() > 0.99
+
+
+KERNELS = [("Disk:3", ("disk", 3, 1, 0, 0)), ("Disk:1.5", ("disk", 1.5, 1, 0, 0)), ("Square:2", ("square", 2, 1, 0, 0)),
+           ("Diamond:2", ("diamond", 2, 1, 0, 0)), ("Octagon:3", ("octagon", 3, 1, 0, 0)),
+           ("Plus:2", ("plus", 2, 1, 0, 0)), ("Cross:1", ("cross", 1, 1, 0, 0)),
+           ("Rectangle:5x3+1+2", ("rectangle", 5, 3, 1, 2))]
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("name,args", KERNELS)
+def test_erode_dilate_bit_exact(ch, name, args):
+    src = make_image(83, 59, ch, seed=17, kind="hdr" if ch == 3 else "noise")
+    k = util.orc_kernel(*args)
+    for method, its in ((im.ErodeMorphology, 1), (im.DilateMorphology, 1), (im.DilateMorphology, 3),
+                        (im.OpenMorphology, 1), (im.CloseMorphology, 1), (im.SmoothMorphology, 1)):
+        want = util.orc_morphology(src, method, its, [k])
+        got = _host(im.MorphologyImage(_dev(src), method, its, name))
+        assert max_ulp(got, want) == 0, (name, ch, method, its)
+        got_h = im.MorphologyImage(im.Image(src), method, its, name).pixels
+        assert max_ulp(got_h, want) == 0
+
+
+def test_dilate_until_convergence_and_changed_count():
+    src = make_image(64, 48, 1, seed=9, kind="binary")
+    k = util.orc_kernel("diamond", 1, 1, 0, 0)
+    want = util.orc_morphology(src, im.DilateMorphology, -1, [k])
+    got = _host(im.MorphologyImage(_dev(src), im.DilateMorphology, -1, "Diamond:1"))
+    assert max_ulp(got, want) == 0
+    dst = np.empty_like(src)
+    changed_ref = oracle().orc_morphology_primitive(P(src), P(dst), 64, 48, 1, im.ErodeMorphology, C.byref(k), 0.0)
+    out, changed = im.MorphologyPrimitive(_dev(src), im.ErodeMorphology, "Diamond:1")
+    assert changed == changed_ref
+    assert max_ulp(_host(out), dst) == 0
+
+
+@pytest.mark.parametrize("ch", [1, 4])
+def test_user_kernel_convolve_and_correlate(ch):
+    src = make_image(90, 70, ch, seed=23)
+    vals = np.array([[1.0, 2.0, 0.5], [0.0, -1.0, np.nan], [3.0, 0.25, -2.0]])
+    k = util.orc_kernel_from_array(vals, 0, 2)
+    ks = "3x3+0+2: 1,2,0.5 0,-1,nan 3,0.25,-2"
+    for method in (im.ConvolveMorphology, im.CorrelateMorphology):
+        want = util.orc_morphology(src, method, 1, [k])
+        got = _host(im.MorphologyImage(_dev(src), method, 1, ks))
+        assert max_ulp(got, want) <= 1, (ch, method)
+    want = util.orc_morphology(src, im.ConvolveMorphology, 1, [k], bias=100.0)
+    got = _host(im.MorphologyImage(_dev(src), im.ConvolveMorphology, 1, ks, bias=100.0))
+    assert max_ulp(got, want) <= 1
+
+
+FILTERS = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33]
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("filt", [22, 12, 0, 3, 11])
+def test_resize_shapes(ch, filt):
+    src = make_image(131, 77, ch, seed=31, kind="alpha_blocks")
+    for (ow, oh) in ((65, 38), (66, 39), (262, 154), (131, 40), (50, 77), (300, 20), (1, 1), (131, 77)):
+        want = np.empty((oh, ow, ch), np.float32)
+        assert oracle().orc_resize(P(src), 131, 77, ch, P(want), ow, oh, filt) == 0
+        got = _host(im.ResizeImage(_dev(src), ow, oh, filt))
+        assert max_ulp(got, want) <= 1, (ch, filt, ow, oh)
+
+
+@pytest.mark.parametrize("filt", FILTERS)
+def test_resize_all_filters(filt):
+    src = make_image(96, 64, 4, seed=37)
+    for (ow, oh) in ((48, 32), (144, 100)):
+        want = np.empty((oh, ow, 4), np.float32)
+        assert oracle().orc_resize(P(src), 96, 64, 4, P(want), ow, oh, filt) == 0
+        got = im.ResizeImage(im.Image(src), ow, oh, filt).pixels
+        assert max_ulp(got, want) <= 1, (filt, ow, oh)
+
+
+def test_resize_lanczos_2x_down_2048():
+    """configs[2] at 1/8 scale: Lanczos 2x downscale, 1-ULP check against the CPU result."""
+    src = make_image(2048, 2048, 4, seed=42)
+    want = np.empty((1024, 1024, 4), np.float32)
+    assert oracle().orc_resize(P(src), 2048, 2048, 4, P(want), 1024, 1024, 22) == 0
+    got = _host(im.ResizeImage(_dev(src), 1024, 1024, im.LanczosFilter))
+    d = util.ulp_distance(got, want)
+    assert d.max() <= 1
+    assert (d == 0).mean() > 0.999
+
+
+@pytest.mark.parametrize("ch", [3, 4])
+@pytest.mark.parametrize("frm,to", [(23, 11), (23, 26), (23, 21), (11, 23), (26, 23), (21, 23), (11, 26)])
+def test_colorspace(ch, frm, to):
+    src = make_image(128, 96, ch, seed=41)
+    src[0, :8, :3] = [0, 1, 2]                        # toe segment of the sRGB curve
+    src[1, :8, :3] = [65535, 2650, 2651]
+    want = src.copy()
+    assert oracle().orc_colorspace(P(want), 128, 96, ch, frm, to) == 0
+    a = im.Image(src.copy(), colorspace=frm)
+    assert im.TransformImageColorspace(a, to) is True and a.colorspace == to
+    assert max_ulp(a.pixels, want) <= 1, (ch, frm, to)
+    b = _dev(src.copy()); b.colorspace = frm
+    im.TransformImageColorspace(b, to)
+    assert max_ulp(_host(b), want) <= 1
+    if ch == 4:
+        assert np.array_equal(a.pixels[..., 3], src[..., 3])   # alpha untouched
+
+
+def test_config4_lab_then_dilate_512():
+    """configs[3] at reduced size: sRGB->Lab then 7x7 Disk dilate."""
+    src = make_image(512, 512, 4, seed=42)
+    want = src.copy()
+    assert oracle().orc_colorspace(P(want), 512, 512, 4, 23, 11) == 0
+    k = util.orc_kernel("disk", 3, 1, 0, 0)
+    want2 = util.orc_morphology(want, im.DilateMorphology, 1, [k])
+    a = _dev(src)
+    im.TransformImageColorspace(a, im.LabColorspace)
+    lab = _host(a)
+    assert max_ulp(lab, want) <= 1
+    got2 = _host(im.MorphologyImage(_dev(want), im.DilateMorphology, 1, "Disk:3"))
+    assert max_ulp(got2, want2) == 0
+
+
+def test_errors_are_loud():
+    src = make_image(16, 16, 4)
+    with pytest.raises(im.MagickB200Error):
+        im.MorphologyImage(_dev(src), im.EdgeMorphology, 1, "Disk:1")     # unsupported -> decline
+    with pytest.raises(im.MagickB200Error):
+        im.ResizeImage(_dev(src), 8, 8, im.JincFilter)
+    with pytest.raises(im.MagickB200Error):
+        im.AcquireKernelInfo("nosuchkernel:3")
+    with pytest.raises(im.MagickB200Error):
+        im.ResizeImage(_dev(src), 0, 8)

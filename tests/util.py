@@ -1,0 +1,160 @@
+"""Test helpers: ctypes access to the oracle (tests only!), ULP metrics, fixtures."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_SO = ROOT / "oracle" / "liboracle.so"
+REF_SO = ROOT / "oracle" / "_ref" / "libmagickref.so"
+
+_fp = C.POINTER(C.c_float)
+_sz, _d, _i, _l = C.c_size_t, C.c_double, C.c_int, C.c_long
+
+
+def P(a: np.ndarray):
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_fp)
+
+
+class OrcKernel(C.Structure):
+    _fields_ = [("width", _sz), ("height", _sz), ("x", _l), ("y", _l), ("values", C.POINTER(_d)),
+                ("minimum", _d), ("maximum", _d), ("negative_range", _d), ("positive_range", _d), ("type", _i)]
+
+    def array(self):
+        n = self.width * self.height
+        return np.array([self.values[i] for i in range(n)]).reshape(self.height, self.width)
+
+
+# oracle kernel type ids (oracle.h)
+ORC_K = dict(blur=0, gaussian=1, disk=2, square=3, diamond=4, octagon=5, plus=6, cross=7, rectangle=8)
+
+_oracle = None
+_ref = None
+
+
+def oracle() -> C.CDLL:
+    global _oracle
+    if _oracle is None:
+        o = C.CDLL(str(ORACLE_SO))
+        for f in (o.orc_blur, o.orc_gaussian_blur):
+            f.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d]
+        o.orc_unsharp.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d, _d, _d]
+        o.orc_resize.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz, _i]
+        o.orc_colorspace.argtypes = [_fp, _sz, _sz, _i, _i, _i]
+        o.orc_kernel_builtin.argtypes = [_i, _d, _d, _d, _d, C.POINTER(OrcKernel)]
+        o.orc_kernel_user.argtypes = [_sz, _sz, _l, _l, C.POINTER(_d), C.POINTER(OrcKernel)]
+        o.orc_kernel_free.argtypes = [C.POINTER(OrcKernel)]
+        o.orc_morphology_apply.argtypes = [_fp, _fp, _sz, _sz, _i, _i, _l, C.POINTER(OrcKernel), _i, _d]
+        o.orc_morphology_primitive.argtypes = [_fp, _fp, _sz, _sz, _i, _i, C.POINTER(OrcKernel), _d]
+        o.orc_morphology_primitive.restype = _l
+        o.orc_filter_weight.argtypes = [_i, _d]
+        o.orc_filter_weight.restype = _d
+        o.orc_filter_support.argtypes = [_i]
+        o.orc_filter_support.restype = _d
+        o.orc_optimal_kernel_width_1d.argtypes = [_d, _d]
+        o.orc_optimal_kernel_width_1d.restype = _sz
+        o.orc_optimal_kernel_width_2d.argtypes = [_d, _d]
+        o.orc_optimal_kernel_width_2d.restype = _sz
+        o.orc_set_threads.argtypes = [_i]
+        _oracle = o
+    return _oracle
+
+
+def have_ref() -> bool:
+    return REF_SO.exists()
+
+
+def ref() -> C.CDLL:
+    """The real reference (ImageMagick compiled from source); only exists where
+    oracle/_ref has been built (this container / shipped prebuilt to the GPU box)."""
+    global _ref
+    if _ref is None:
+        r = C.CDLL(str(REF_SO))
+        for f in (r.ref_blur, r.ref_gaussian_blur):
+            f.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d]
+        r.ref_unsharp.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d, _d, _d]
+        r.ref_convolve.argtypes = [_fp, _fp, _sz, _sz, _i, C.c_char_p]
+        r.ref_morphology.argtypes = [_fp, _fp, _sz, _sz, _i, _i, _l, C.c_char_p]
+        r.ref_resize.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz, _i]
+        r.ref_colorspace.argtypes = [_fp, _sz, _sz, _i, _i, _i]
+        r.ref_kernel.argtypes = [C.c_char_p, _i, C.POINTER(_d), _sz, C.POINTER(_sz), C.POINTER(_sz),
+                                 C.POINTER(_l), C.POINTER(_l)]
+        r.ref_version.restype = C.c_char_p
+        r.ref_set_threads.argtypes = [_i]
+        _ref = r
+    return _ref
+
+
+def ref_kernel(string: str, idx: int = 0):
+    vals = (_d * 65536)()
+    kw, kh, kx, ky = _sz(), _sz(), _l(), _l()
+    rc = ref().ref_kernel(string.encode(), idx, vals, 65536, C.byref(kw), C.byref(kh), C.byref(kx), C.byref(ky))
+    if rc:
+        return None
+    return np.array(vals[: kw.value * kh.value]).reshape(kh.value, kw.value), kx.value, ky.value
+
+
+def orc_kernel(kind: str, rho=0.0, sigma=0.0, xi=0.0, psi=0.0) -> OrcKernel:
+    k = OrcKernel()
+    rc = oracle().orc_kernel_builtin(ORC_K[kind], rho, sigma, xi, psi, C.byref(k))
+    assert rc == 0, (kind, rho, sigma, xi, psi)
+    return k
+
+
+def orc_kernel_from_array(values: np.ndarray, x: int, y: int) -> OrcKernel:
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    k = OrcKernel()
+    rc = oracle().orc_kernel_user(v.shape[1], v.shape[0], x, y, v.ctypes.data_as(C.POINTER(_d)), C.byref(k))
+    assert rc == 0
+    return k
+
+
+def orc_morphology(src: np.ndarray, method: int, iterations: int, kernels, bias=0.0) -> np.ndarray:
+    h, w, ch = src.shape
+    arr = (OrcKernel * len(kernels))(*kernels)
+    dst = np.empty_like(src)
+    rc = oracle().orc_morphology_apply(P(src), P(dst), w, h, ch, method, iterations, arr, len(kernels), bias)
+    assert rc == 0
+    return dst
+
+
+def ulp_distance(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Per-element distance in float32 ULPs (sign-magnitude ordered integers)."""
+    assert a.shape == b.shape and a.dtype == np.float32 and b.dtype == np.float32
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    ai = np.where(ai < 0, -(ai & 0x7FFFFFFF), ai)
+    bi = np.where(bi < 0, -(bi & 0x7FFFFFFF), bi)
+    return np.abs(ai - bi)
+
+
+def max_ulp(a, b) -> int:
+    return int(ulp_distance(np.ascontiguousarray(a), np.ascontiguousarray(b)).max())
+
+
+def frac_exact(a, b) -> float:
+    return float((ulp_distance(np.ascontiguousarray(a), np.ascontiguousarray(b)) == 0).mean())
+
+
+def make_image(w: int, h: int, ch: int, seed: int = 42, kind: str = "noise") -> np.ndarray:
+    """Seeded synthetic pixel cache (raw Quantum floats 0..65535).
+    kind: noise | alpha_blocks (fully transparent / opaque regions, exercises
+    PerceptibleReciprocal) | gradient | hdr (values outside 0..QuantumRange, negatives)."""
+    rng = np.random.default_rng(seed)
+    a = (rng.random((h, w, ch), dtype=np.float32) * np.float32(65535.0)).astype(np.float32)
+    if kind == "alpha_blocks" and ch in (2, 4):
+        a[: h // 2, : w // 2, ch - 1] = 0.0
+        a[h // 2:, w // 2:, ch - 1] = 65535.0
+        a[h // 3: h // 3 + 2, :, ch - 1] = 1.0
+    elif kind == "gradient":
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        for c in range(ch):
+            a[..., c] = ((xx * (c + 1) + yy * 3) % 256) * 257.0
+    elif kind == "hdr":
+        a = (a - 20000.0) * 1.7
+    elif kind == "binary":
+        a = np.where(a > 40000.0, np.float32(65535.0), np.float32(0.0)).astype(np.float32)
+    return np.ascontiguousarray(a)

@@ -1,0 +1,62 @@
+"""Developer micro-benchmark: device-resident timings of the hot-path operators (CUDA events).
+usage: python tools/devbench.py [blur|resize|lab|dilate|gauss|all] [size]"""
+import sys
+import torch
+import imagemagick_b200 as im
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+size = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+PEAK = 6576.1
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def report(name, ms, npix, bytes_per_px):
+    gbs = npix * bytes_per_px / ms / 1e6
+    print(f"{name:34s} {ms:9.3f} ms  {npix / ms / 1e3:10.1f} Mpix/s  {gbs:8.1f} GB/s  {gbs / PEAK * 100:5.1f}% of measured HBM peak", flush=True)
+
+
+torch.manual_seed(0)
+if which in ("blur", "all"):
+    x = im.Image(torch.rand(size, size, 4, device="cuda") * 65535)
+    for sigma in (4.0, 2.0):
+        ms = timeit(lambda: im.BlurImage(x, 0.0, sigma))
+        report(f"BlurImage {size}^2 RGBA sigma={sigma}", ms, size * size, 64)
+    k = im.AcquireKernelInfo("blur:0x4")
+    ms = timeit(lambda: im.ConvolveImage(x, k)); report("  row pass only (33 taps)", ms, size * size, 32)
+    k = im.AcquireKernelInfo("blur:0x4+90")
+    ms = timeit(lambda: im.ConvolveImage(x, k)); report("  column pass only (33 taps)", ms, size * size, 32)
+    del x
+if which in ("resize", "all"):
+    s2 = size * 2 if size <= 8192 else size
+    x = im.Image(torch.rand(s2, s2, 4, device="cuda") * 65535)
+    ms = timeit(lambda: im.ResizeImage(x, s2 // 2, s2 // 2, im.LanczosFilter))
+    report(f"ResizeImage {s2}^2->{s2 // 2}^2 Lanczos", ms, s2 * s2, 36)
+    del x
+if which in ("lab", "all"):
+    x = im.Image(torch.rand(size, size, 4, device="cuda") * 65535)
+    def f():
+        x.colorspace = im.sRGBColorspace
+        im.TransformImageColorspace(x, im.LabColorspace)
+    ms = timeit(f); report(f"sRGB->Lab {size}^2", ms, size * size, 32)
+    del x
+if which in ("dilate", "all"):
+    x = im.Image(torch.rand(size, size, 4, device="cuda") * 65535)
+    k = im.AcquireKernelInfo("Disk:3")
+    ms = timeit(lambda: im.MorphologyImage(x, im.DilateMorphology, 1, k)); report(f"Dilate Disk:3 {size}^2", ms, size * size, 32)
+    del x
+if which in ("gauss", "all"):
+    s = min(size, 4096)
+    x = im.Image(torch.rand(s, s, 4, device="cuda") * 65535)
+    ms = timeit(lambda: im.GaussianBlurImage(x, 0.0, 4.0), iters=3, warm=1); report(f"GaussianBlurImage 2-D 29x29 {s}^2", ms, s * s, 32)
