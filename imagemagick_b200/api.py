@@ -96,7 +96,10 @@ class Image:
 
 def _stream(image: Image):
     import torch
-    return C.c_void_p(torch.cuda.current_stream(image.pixels.device).cuda_stream)
+    handle = torch.cuda.current_stream(image.pixels.device).cuda_stream
+    # torch's default stream is the legacy NULL stream; NULL means "library stream" in the
+    # C-ABI, so name the legacy stream explicitly (cudaStreamLegacy == 0x1).
+    return C.c_void_p(handle if handle else 1)
 
 
 def _activate(image: Image) -> None:

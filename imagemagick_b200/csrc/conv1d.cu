@@ -50,14 +50,13 @@ struct Conv1dArgs {
   unsigned long long *changed;
 };
 
+// 1/g to ~2^-46: single-precision MUFU.RCP seed + one FP64 Newton step (2 FP64-pipe ops).
 __device__ __forceinline__ double fast_reciprocal(double g) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(g));
-  double e = fma(-g, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-g, r, 1.0);
-  r = fma(r, e, r);
-  return r;
+  float seed;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"(static_cast<float>(g)));
+  const double r0 = static_cast<double>(seed);
+  const double e = fma(-g, r0, 1.0);
+  return fma(r0, e, r0);
 }
 
 __device__ __forceinline__ double shfl_double(double v, int lane) {
@@ -67,36 +66,36 @@ __device__ __forceinline__ double shfl_double(double v, int lane) {
   return __hiloint2double(hi, lo);
 }
 
-// Turns the finished accumulator(s) into the output Quantum.
-//  plain : out = bias + sum
-//  blend : pixel = bias + QS*sum', gamma = QS*gsum'  (sum' = sum K*A*p, gsum' = sum K*A)
-//          out = PerceptibleReciprocal(gamma) * pixel          (morphology.c:3197)
-template <int MODE>
-__device__ __forceinline__ float finish(double sum, double gsum, bool is_alpha, double bias,
-                                        double *unnormalised) {
-  if (MODE == 0 || is_alpha) {
-    const double pixel = bias + sum;
-    *unnormalised = pixel;
-    return static_cast<float>(pixel);
-  }
-  const double pixel = fma(kQuantumScale, sum, bias);
-  const double gamma = kQuantumScale * gsum;
-  *unnormalised = pixel;
-  double r;
-  if (fabs(gamma) >= kEpsilon) r = fast_reciprocal(gamma);
-  else r = gamma < 0.0 ? -1.0 / kEpsilon : 1.0 / kEpsilon;
+// Per-thread constants of the output stage.  With sum' = sum K*(A*p) and gsum' = sum K*A the
+// reference's  PerceptibleReciprocal(QS*gsum') * (bias + QS*sum')  (morphology.c:3197) equals
+// (bias/QS + sum') / gsum'; alpha / plain lanes use a denominator of 1.
+struct Finish {
+  double bias_eff;   // bias (plain, alpha lane) or bias/QS (blend lane)
+  bool blend;
+};
+
+// branch-free: out = (bias_eff + sum) * 1/den, den = blend ? gsum : 1, with the reference's
+// |gamma| < MagickEpsilon clamp applied to QS*gsum.
+__device__ __forceinline__ float finish(const Finish &f, double sum, double gsum) {
+  const double pixel = f.bias_eff + sum;
+  const double den = f.blend ? gsum : 1.0;
+  double r = fast_reciprocal(den);
+  const double tiny = den < 0.0 ? -(kQuantumScale / kEpsilon) : (kQuantumScale / kEpsilon);
+  r = fabs(den) >= (kEpsilon / kQuantumScale) ? r : tiny;
   return static_cast<float>(r * pixel);
 }
 
-__device__ __forceinline__ void count_changed(bool changed, unsigned long long *counter) {
-  const unsigned mask = __ballot_sync(__activemask(), changed);
-  if (mask != 0 && (threadIdx.x & 31) == (__ffs(mask) - 1)) atomicAdd(counter, (unsigned long long) __popc(mask));
-}
+template <int NT> struct Ring { static constexpr int value = NT; };
+template <> struct Ring<33> { static constexpr int value = 11; };
+template <> struct Ring<65> { static constexpr int value = 13; };
 
 // ---------------------------------------------------------------- column pass
 // grid: (ceil(rc / THREADS), ceil(height / strip)); one thread per component column.
-template <int NT, int MODE, int THREADS>
-__global__ void __launch_bounds__(THREADS) conv_col_kernel(const Conv1dArgs a, const Taps<NT> taps) {
+// strip + NT - 1 is a whole number of NT-step rotations, so the unrolled body has no exits.
+template <int NT, int MODE, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) conv_col_kernel(const Conv1dArgs a, const Taps<NT> taps) {
+  constexpr int PF = Ring<NT>::value;          // source rows kept in flight per thread
+  static_assert(NT % PF == 0, "ring must divide the rotation");
   const int col_raw = blockIdx.x * THREADS + threadIdx.x;
   const bool active = col_raw < a.rc;
   const int col = active ? col_raw : a.rc - 1;
@@ -104,54 +103,55 @@ __global__ void __launch_bounds__(THREADS) conv_col_kernel(const Conv1dArgs a, c
   const int alane = MODE ? (lane | (MODE - 1)) : lane;
   const bool is_alpha = MODE ? ((col % MODE) == MODE - 1) : false;
   const int y0 = blockIdx.y * a.strip;
-  const int nout = min(a.strip, a.height - y0);
-  const int total = nout + NT - 1;
+  const int nout = active ? min(a.strip, a.height - y0) : 0;
+  const int total = a.strip + NT - 1;
   const int hmax = a.height - 1;
-  const size_t pitch = static_cast<size_t>(a.rc);
-  const float *base = a.src + col;
+  const unsigned pitch_bytes = static_cast<unsigned>(a.rc) * 4u;
+  const char *base = reinterpret_cast<const char *>(a.src + col);
+  char *outp = reinterpret_cast<char *>(a.dst + col) + static_cast<size_t>(y0) * pitch_bytes;
+  Finish fin;
+  fin.blend = MODE && !is_alpha;
+  fin.bias_eff = fin.blend ? a.bias * 65535.0 : a.bias;
 
   double acc[NT];
-  float pre[NT];
+  float pre[PF];
 #pragma unroll
   for (int q = 0; q < NT; ++q) acc[q] = 0.0;
+  int ysrc = y0 - a.off;                       // source row of step 0
 #pragma unroll
-  for (int s = 0; s < NT; ++s) {
-    const int yy = min(max(y0 + s - a.off, 0), hmax);
-    pre[s] = __ldg(base + static_cast<size_t>(yy) * pitch);
+  for (int s = 0; s < PF; ++s) {
+    const unsigned yy = static_cast<unsigned>(min(max(ysrc + s, 0), hmax));
+    pre[s] = __ldg(reinterpret_cast<const float *>(base + static_cast<size_t>(yy) * pitch_bytes));
   }
+  ysrc += PF;                                  // next row to fetch
 
+  int j = -(NT - 1);                           // output row (relative to y0) finished at this step
   for (int mb = 0; mb < total; mb += NT) {
 #pragma unroll
     for (int s = 0; s < NT; ++s) {
-      const int m = mb + s;
-      if (m >= total) break;
-      const float vf = pre[s];
-      {  // keep NT row loads in flight: refill this ring slot with the sample NT steps ahead
-        const int yy = min(max(y0 + m + NT - a.off, 0), hmax);
-        pre[s] = __ldg(base + static_cast<size_t>(yy) * pitch);
+      float vf = pre[s % PF];
+      {  // refill this ring slot with the row PF steps ahead (edge-clamped)
+        const unsigned yy = static_cast<unsigned>(min(max(ysrc, 0), hmax));
+        pre[s % PF] = __ldg(reinterpret_cast<const float *>(base + static_cast<size_t>(yy) * pitch_bytes));
+        ++ysrc;
       }
       double v = static_cast<double>(vf);
       if (MODE) {
-        const float af = __shfl_sync(0xffffffffu, vf, alane);
-        v *= is_alpha ? 1.0 : static_cast<double>(af);
+        float af = __shfl_sync(0xffffffffu, vf, alane);
+        af = is_alpha ? 1.0f : af;
+        v *= static_cast<double>(af);
       }
 #pragma unroll
       for (int q = 0; q < NT; ++q) acc[q] = fma(taps.k[(s - q + NT) % NT], v, acc[q]);
-      constexpr int kSlots = NT;
-      const int qf = (s + 1) % kSlots;
+      const int qf = (s + 1) % NT;
       const double sum = acc[qf];
       acc[qf] = 0.0;
-      double gsum = 0.0;
+      double gsum = 1.0;
       if (MODE) gsum = shfl_double(sum, alane);
-      const int j = m - (NT - 1);
-      if (j >= 0 && active) {
-        double unnorm;
-        const float out = finish<MODE>(sum, gsum, is_alpha, a.bias, &unnorm);
-        const size_t o = static_cast<size_t>(y0 + j) * pitch + col;
-        a.dst[o] = out;
-        if (a.changed != nullptr)
-          count_changed(fabs(unnorm - static_cast<double>(__ldg(a.src + o))) >= kEpsilon, a.changed);
-      }
+      const float out = finish(fin, sum, gsum);
+      if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<float *>(outp) = out;
+      if (j >= 0) outp += pitch_bytes;
+      ++j;
     }
   }
 }
@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(THREADS) conv_col_kernel(const Conv1dArgs a, c
 // ------------------------------------------------------------------- row pass
 // block: 128 threads = 4 warps; a warp covers RPW = 32/channels rows x channels lanes.
 // grid: (ceil(width / strip), ceil(height / rows_per_cta)).
-template <int NT, int MODE>
-__global__ void __launch_bounds__(128) conv_row_kernel(const Conv1dArgs a, const Taps<NT> taps) {
+template <int NT, int MODE, int MINB>
+__global__ void __launch_bounds__(128, MINB) conv_row_kernel(const Conv1dArgs a, const Taps<NT> taps) {
   extern __shared__ __align__(16) float tile[];
   const int ch = a.channels;
   const int rpw = 32 / ch;
@@ -168,8 +168,7 @@ __global__ void __launch_bounds__(128) conv_row_kernel(const Conv1dArgs a, const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x0 = blockIdx.x * a.strip;
   const int ybase = blockIdx.y * rows_per_cta;
-  const int nout = min(a.strip, a.width - x0);
-  const int total = nout + NT - 1;
+  const int total = a.strip + NT - 1;
   const int wmax = a.width - 1, hmax = a.height - 1;
 
   // ---- stage the tile: rows_per_cta x total source pixels, x edge-clamped
@@ -201,42 +200,42 @@ __global__ void __launch_bounds__(128) conv_row_kernel(const Conv1dArgs a, const
   const int r = warp * rpw + lr;
   const int y = ybase + r;
   const bool active = lane_ok && y < a.height;
+  const int nout = active ? min(a.strip, a.width - x0) : 0;
   const int alane = MODE ? (lane | (MODE - 1)) : lane;
   const bool is_alpha = MODE ? (c == MODE - 1) : false;
-  const float *trow = tile + static_cast<size_t>(r) * a.pitch * ch + c;
-  float *drow = a.dst + (static_cast<size_t>(min(y, hmax)) * a.width + x0) * ch + c;
-  const float *crow = a.src + (static_cast<size_t>(min(y, hmax)) * a.width + x0) * ch + c;
+  const float *tp = tile + static_cast<size_t>(r) * a.pitch * ch + c;
+  float *outp = a.dst + (static_cast<size_t>(min(y, hmax)) * a.width + x0) * ch + c;
+  Finish fin;
+  fin.blend = MODE && !is_alpha;
+  fin.bias_eff = fin.blend ? a.bias * 65535.0 : a.bias;
 
   double acc[NT];
 #pragma unroll
   for (int q = 0; q < NT; ++q) acc[q] = 0.0;
 
+  int j = -(NT - 1);
   for (int mb = 0; mb < total; mb += NT) {
 #pragma unroll
     for (int s = 0; s < NT; ++s) {
-      const int m = mb + s;
-      if (m >= total) break;
-      const float vf = trow[m * ch];
+      const float vf = *tp;
+      tp += ch;
       double v = static_cast<double>(vf);
       if (MODE) {
-        const float af = __shfl_sync(0xffffffffu, vf, alane);
-        v *= is_alpha ? 1.0 : static_cast<double>(af);
+        float af = __shfl_sync(0xffffffffu, vf, alane);
+        af = is_alpha ? 1.0f : af;
+        v *= static_cast<double>(af);
       }
 #pragma unroll
       for (int q = 0; q < NT; ++q) acc[q] = fma(taps.k[(s - q + NT) % NT], v, acc[q]);
       const int qf = (s + 1) % NT;
       const double sum = acc[qf];
       acc[qf] = 0.0;
-      double gsum = 0.0;
+      double gsum = 1.0;
       if (MODE) gsum = shfl_double(sum, alane);
-      const int j = m - (NT - 1);
-      if (j >= 0 && active) {
-        double unnorm;
-        const float out = finish<MODE>(sum, gsum, is_alpha, a.bias, &unnorm);
-        drow[j * ch] = out;
-        if (a.changed != nullptr)
-          count_changed(fabs(unnorm - static_cast<double>(__ldg(crow + j * ch))) >= kEpsilon, a.changed);
-      }
+      const float out = finish(fin, sum, gsum);
+      if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *outp = out;
+      if (j >= 0) outp += ch;
+      ++j;
     }
   }
 }
@@ -248,10 +247,12 @@ int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int nta
   Conv1dArgs a = base;
   if (axis == 1) {
     constexpr int kThreads = 128;
+    constexpr int kMinBlocks = NT <= 33 ? 4 : 2;
     a.strip = 8 * NT + 1;                       // strip + NT - 1 is a whole number of rotations
     dim3 grid((a.rc + kThreads - 1) / kThreads, (a.height + a.strip - 1) / a.strip);
-    conv_col_kernel<NT, MODE, kThreads><<<grid, kThreads, 0, stream>>>(a, taps);
+    conv_col_kernel<NT, MODE, kThreads, kMinBlocks><<<grid, kThreads, 0, stream>>>(a, taps);
   } else {
+    constexpr int kMinBlocks = NT <= 33 ? 4 : 2;
     // strip + NT - 1 is a whole number of rotations and the strip is at least ~64 outputs
     constexpr int kRot = (63 + NT - 1) / NT < 2 ? 2 : (63 + NT - 1) / NT;
     a.strip = kRot * NT + 1;
@@ -261,11 +262,11 @@ int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int nta
     const size_t smem = static_cast<size_t>(rows_per_cta) * a.pitch * a.channels * sizeof(float);
     static bool attr_set = false;   // per instantiation
     if (!attr_set) {
-      cudaFuncSetAttribute(conv_row_kernel<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(conv_row_kernel<NT, MODE, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attr_set = true;
     }
     dim3 grid((a.width + a.strip - 1) / a.strip, (a.height + rows_per_cta - 1) / rows_per_cta);
-    conv_row_kernel<NT, MODE><<<grid, 128, smem, stream>>>(a, taps);
+    conv_row_kernel<NT, MODE, kMinBlocks><<<grid, 128, smem, stream>>>(a, taps);
   }
   count_launch();
   const cudaError_t e = cudaGetLastError();
@@ -287,7 +288,8 @@ int launch_conv1d(const float *src, float *dst, size_t width, size_t height, int
                   unsigned long long *d_changed, void *stream) {
   if (width == 0 || height == 0 || channels < 1 || channels > 4 || ntaps < 1)
     return fail(MB200_EINVAL, "conv1d: bad geometry");
-  if (width * channels > 0x7fffffffull || height > 0x7fffffffull) return fail(MB200_EINVAL, "conv1d: image too large");
+  if (width * channels > 0x1fffffffull || height > 0x7fffffffull) return MB200_EUNSUPPORTED;   // 32-bit byte pitch
+  if (d_changed != nullptr) return MB200_EUNSUPPORTED;   // `changed` counting lives in the generic kernel
   Conv1dArgs a{};
   a.src = src; a.dst = dst;
   a.width = static_cast<int>(width); a.height = static_cast<int>(height); a.channels = channels;

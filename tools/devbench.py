@@ -1,6 +1,8 @@
 """Developer micro-benchmark: device-resident timings of the hot-path operators (CUDA events).
 usage: python tools/devbench.py [blur|resize|lab|dilate|gauss|all] [size]"""
 import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 import imagemagick_b200 as im
 
