@@ -1,0 +1,92 @@
+"""Pins the oracle (CPU restatement) to golden vectors produced by the REAL reference
+(tests/golden/make_golden.py ran ImageMagick 7.1.1-45 compiled from source).  Bit-exact."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import util
+from util import P, oracle
+
+G = np.load(Path(__file__).resolve().parent / "golden" / "hotpath_golden.npz")
+TAGS = sorted({k.split("/")[0] for k in G.files if k.startswith("c")})
+KERNEL_ARGS = {"Disk:3": ("disk", 3, 1, 0, 0), "Diamond:2": ("diamond", 2, 1, 0, 0),
+               "Rectangle:5x3+1+2": ("rectangle", 5, 3, 1, 2)}
+METHODS = {"erode": 3, "dilate": 4, "open": 8, "close": 9, "smooth": 12}
+FILTERS = {"lanczos": 22, "mitchell": 12, "undefined": 0, "triangle": 3, "point": 1}
+SPACES = {"srgb": 23, "lab": 11, "xyz": 26, "rgb": 21}
+
+
+def golden_cases(tag):
+    return [k for k in G.files if k.startswith(tag + "/") and not k.endswith("/src")]
+
+
+def run_oracle(src, name):
+    h, w, ch = src.shape
+    dst = np.empty_like(src)
+    o = oracle()
+    if name.startswith("blur_"):
+        r, s = name[5:].split("x")
+        assert o.orc_blur(P(src), P(dst), w, h, ch, float(r), float(s)) == 0
+    elif name.startswith("gaussian_"):
+        r, s = name[9:].split("x")
+        assert o.orc_gaussian_blur(P(src), P(dst), w, h, ch, float(r), float(s)) == 0
+    elif name.startswith("unsharp_"):
+        rs, gain, thr = name[8:].split("_")
+        r, s = rs.split("x")
+        assert o.orc_unsharp(P(src), P(dst), w, h, ch, float(r), float(s), float(gain), float(thr)) == 0
+    elif name.split("_")[0] in METHODS:
+        m, kname = name.split("_", 1)
+        k = util.orc_kernel(*KERNEL_ARGS[kname])
+        dst = util.orc_morphology(src, METHODS[m], 1, [k])
+    elif name == "convolve_user3x3":
+        vals = np.array([[1.0, 2.0, 0.5], [0.0, -1.0, np.nan], [3.0, 0.25, -2.0]])
+        dst = util.orc_morphology(src, 1, 1, [util.orc_kernel_from_array(vals, 1, 1)])
+    elif name.startswith("resize_"):
+        _, f, size = name.split("_")
+        ow, oh = map(int, size.split("x"))
+        dst = np.empty((oh, ow, ch), np.float32)
+        assert o.orc_resize(P(src), w, h, ch, P(dst), ow, oh, FILTERS[f]) == 0
+    elif name.startswith("colorspace_"):
+        _, a, b = name.split("_")
+        dst = src.copy()
+        assert o.orc_colorspace(P(dst), w, h, ch, SPACES[a], SPACES[b]) == 0
+    else:
+        raise AssertionError(name)
+    return dst
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_oracle_matches_reference_golden_bit_exact(tag):
+    src = np.ascontiguousarray(G[tag + "/src"])
+    cases = golden_cases(tag)
+    assert len(cases) > 20
+    for key in cases:
+        got = run_oracle(src, key.split("/", 1)[1])
+        want = G[key]
+        assert got.shape == want.shape, key
+        assert util.max_ulp(got, want) == 0, key
+
+
+def test_validate_c_known_answer_rgb_to_lab():
+    """tests/validate.c:244-259: sRGB (0.545877,0.966567,0.463759) -> L*a*b* 88.456154,-54.671483,51.662818
+    (the reference's own tolerance is 1% of QuantumRange, validate.c:67)."""
+    buf = np.ascontiguousarray(G["kat/srgb"]).copy()
+    assert oracle().orc_colorspace(P(buf), 1, 1, 3, 23, 11) == 0
+    assert util.max_ulp(buf, G["kat/lab"]) == 0
+    L = buf[0, 0, 0] / 65535.0 * 100.0
+    a = (buf[0, 0, 1] / 65535.0 - 0.5) * 255.0
+    b = (buf[0, 0, 2] / 65535.0 - 0.5) * 255.0
+    assert abs(L - 88.456154) < 5e-3 and abs(a + 54.671483) < 5e-3 and abs(b - 51.662818) < 5e-3
+
+
+def test_probed_kernel_sizes():
+    """SURVEY appendix B probes: -blur 0x2 -> 17 taps, 0x4 -> 33; gaussian 0x4 -> 29x29; Disk:3 -> 29 cells."""
+    o = oracle()
+    assert o.orc_optimal_kernel_width_1d(0.0, 2.0) == 17
+    assert o.orc_optimal_kernel_width_1d(0.0, 4.0) == 33
+    assert o.orc_optimal_kernel_width_2d(0.0, 4.0) == 29
+    k = util.orc_kernel("disk", 3, 1, 0, 0).array()
+    assert k.shape == (7, 7) and int(np.sum(~np.isnan(k))) == 29

@@ -1,0 +1,111 @@
+"""CPU-only checks of the product's host side (no GPU compute calls):
+ * libmagickb200.so loads and exports every symbol include/magick_b200.h declares,
+ * kernel builders / parser produce taps bit-identical to the reference's (golden + oracle),
+ * resize contribution tables equal the oracle's weights,
+ * the operators fail loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import util
+
+im = pytest.importorskip("imagemagick_b200")
+from imagemagick_b200 import _lib  # noqa: E402
+
+ROOT = Path(__file__).resolve().parent.parent
+G = np.load(ROOT / "tests" / "golden" / "hotpath_golden.npz")
+
+
+def test_every_declared_symbol_is_exported():
+    header = (ROOT / "include" / "magick_b200.h").read_text()
+    declared = set(re.findall(r"\b(mb200_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mb200_kernel_info", "mb200_kernel_type"}      # type names mentioned in comments
+    assert len(declared) >= 35
+    lib = C.CDLL(str(_lib.LIB_PATH))
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    assert b"sm_100a" in _lib.load().mb200_version()
+
+
+def same_kernel(a, b):
+    return a.shape == b.shape and np.array_equal(np.isnan(a), np.isnan(b)) and \
+        np.array_equal(a[~np.isnan(a)].view(np.int64), b[~np.isnan(b)].view(np.int64))
+
+
+@pytest.mark.parametrize("ks", [k.split("/", 1)[1] for k in G.files if k.startswith("kernel/")])
+def test_kernel_strings_match_reference_taps(ks):
+    vals, x, y = im.AcquireKernelInfo(ks).arrays()[0]
+    assert same_kernel(vals, G["kernel/" + ks]), ks
+    assert [x, y] == list(G["kernel_origin/" + ks]), ks
+
+
+def test_kernel_list_and_user_arrays():
+    ks = im.AcquireKernelInfo("blur:0x4;blur:0x4+90").arrays()
+    assert [k[0].shape for k in ks] == [(1, 33), (33, 1)]
+    assert same_kernel(ks[0][0].ravel(), ks[1][0].ravel())
+    (v, x, y), = im.AcquireKernelInfo("3x3+0+2: 1,2,0.5 0,-1,nan 3,0.25,-").arrays()
+    assert (x, y) == (0, 2) and np.isnan(v[1, 2]) and np.isnan(v[2, 2]) and v[2, 0] == 3
+    (v, x, y), = im.AcquireKernelInfo("1,1,1,1,4,1,1,1,1").arrays()
+    assert v.shape == (3, 3) and (x, y) == (1, 1) and v[1, 1] == 4
+    for bad in ("nosuch:3", "3x3: 1,2,3", "", "Disk:3>"):
+        with pytest.raises(im.MagickB200Error):
+            im.AcquireKernelInfo(bad)
+
+
+@pytest.mark.parametrize("r,s", [(0, 0.5), (0, 1), (0, 2), (0, 3.3), (0, 4), (0, 8), (2, 1), (7.5, 3)])
+def test_optimal_widths_and_blur_taps_match_oracle(r, s):
+    lib, o = _lib.load(), util.oracle()
+    assert lib.mb200_optimal_kernel_width_1d(r, s) == o.orc_optimal_kernel_width_1d(r, s)
+    assert lib.mb200_optimal_kernel_width_2d(r, s) == o.orc_optimal_kernel_width_2d(r, s)
+    mine = im.AcquireKernelBuiltIn(im.BlurKernel, r, s, 90.0).arrays()[0]
+    want = util.orc_kernel("blur", r, s, 90.0)
+    assert same_kernel(mine[0], want.array()) and (mine[1], mine[2]) == (want.x, want.y)
+    mine = im.AcquireKernelBuiltIn(im.GaussianKernel, r, s).arrays()[0]
+    assert same_kernel(mine[0], util.orc_kernel("gaussian", r, s).array())
+
+
+@pytest.mark.parametrize("filt", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 17, 18, 19, 20, 21, 22, 23, 24, 25,
+                                  26, 27, 28, 29, 30, 31, 32, 33])
+def test_filter_weights_match_oracle(filt):
+    lib, o = _lib.load(), util.oracle()
+    assert lib.mb200_resize_filter_support(filt) == o.orc_filter_support(filt)
+    for x in np.linspace(-5.0, 5.0, 401):
+        a, b = lib.mb200_resize_filter_weight(filt, float(x)), o.orc_filter_weight(filt, float(x))
+        assert a == b or (np.isnan(a) and np.isnan(b)), (filt, x)
+
+
+def test_resize_contributions_lanczos_2x():
+    lib = _lib.load()
+    n_in, n_out = 64, 32
+    taps = lib.mb200_resize_contributions(22, n_in, n_out, 0.5, None, None, None, 0)
+    assert taps == 15                                   # (size_t)(2*6+3), resize.c:3379
+    start = (C.c_long * n_out)()
+    count = (C.c_int * n_out)()
+    w = (C.c_double * (n_out * taps))()
+    assert lib.mb200_resize_contributions(22, n_in, n_out, 0.5, start, count, w, taps) == taps
+    w = np.array(w).reshape(n_out, taps)
+    assert max(count) == 12 and count[10] == 12 and start[10] == 2 * 10 - 5
+    assert np.allclose(w.sum(1), 1.0, atol=1e-14)
+    # an interior row reproduces the reference's weights: normalised Lanczos3 at half-pixel phase
+    o = util.oracle()
+    scale = 1.0 / (1.0 / 0.5 + 1e-12)                   # resize.c:3363, :3386
+    raw = np.array([o.orc_filter_weight(22, scale * ((start[10] + j) - ((10 + 0.5) / 0.5 + 1e-12) + 0.5)) for j in range(12)])
+    assert np.allclose(w[10, :12], raw * (1.0 / raw.sum()), rtol=0, atol=1e-16)
+    assert lib.mb200_resize_contributions(13, n_in, n_out, 0.5, None, None, None, 0) == _lib.EUNSUPPORTED  # Jinc
+
+
+def test_no_gpu_means_loud_failure_not_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    src = util.make_image(8, 8, 4)
+    with pytest.raises(im.MagickB200Error) as e:
+        im.BlurImage(im.Image(src), 0, 2)
+    assert e.value.code == _lib.ENODEVICE
+    with pytest.raises(im.MagickB200Error):
+        im.ResizeImage(im.Image(src), 4, 4, im.LanczosFilter)
+    assert _lib.load().mb200_device_count() == 0

@@ -1,0 +1,75 @@
+"""Oracle (our CPU restatement) against the real reference compiled from source
+(oracle/_ref/libmagickref.so).  Only runs where that library exists; the committed
+golden vectors (test_golden.py) cover the same ground everywhere else."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import util
+from util import P, make_image, max_ulp, oracle
+
+pytestmark = pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built (reference tree absent)")
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["noise", "alpha_blocks", "hdr"])
+def test_blur_family_bit_exact(ch, kind):
+    src = make_image(53, 37, ch, seed=ch * 11, kind=kind)
+    r, o = util.ref(), oracle()
+    for rf, of, args in ((r.ref_blur, o.orc_blur, (0.0, 2.0)), (r.ref_blur, o.orc_blur, (0.0, 5.0)),
+                         (r.ref_blur, o.orc_blur, (4.0, 1.2)), (r.ref_gaussian_blur, o.orc_gaussian_blur, (0.0, 1.3)),
+                         (r.ref_unsharp, o.orc_unsharp, (0.0, 1.5, 2.0, 0.01))):
+        a, b = np.empty_like(src), np.empty_like(src)
+        assert rf(P(src), P(a), 53, 37, ch, *args) == 0 and of(P(src), P(b), 53, 37, ch, *args) == 0
+        assert max_ulp(a, b) == 0
+
+
+@pytest.mark.parametrize("ch", [1, 4])
+def test_resize_all_filters_bit_exact(ch):
+    src = make_image(47, 33, ch, seed=5, kind="alpha_blocks")
+    for filt in [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33]:
+        for ow, oh in ((23, 16), (24, 17), (94, 66), (47, 10), (13, 33)):
+            a, b = np.empty((oh, ow, ch), np.float32), np.empty((oh, ow, ch), np.float32)
+            assert util.ref().ref_resize(P(src), 47, 33, ch, P(a), ow, oh, filt) == 0
+            assert oracle().orc_resize(P(src), 47, 33, ch, P(b), ow, oh, filt) == 0
+            assert max_ulp(a, b) == 0, (filt, ow, oh)
+
+
+@pytest.mark.parametrize("name,args", [("Disk:3", ("disk", 3, 1, 0, 0)), ("Octagon:2", ("octagon", 2, 1, 0, 0)),
+                                       ("Plus:2", ("plus", 2, 1, 0, 0)), ("Square:1", ("square", 1, 1, 0, 0)),
+                                       ("Rectangle:4x2+3+0", ("rectangle", 4, 2, 3, 0))])
+def test_morphology_bit_exact(name, args):
+    k = util.orc_kernel(*args)
+    ref_vals, x, y = util.ref_kernel(name)
+    assert (k.x, k.y) == (x, y)
+    mine = k.array()
+    assert np.array_equal(np.isnan(mine), np.isnan(ref_vals))
+    assert np.array_equal(mine[~np.isnan(mine)], ref_vals[~np.isnan(ref_vals)])
+    for ch in (1, 2, 4):
+        src = make_image(40, 29, ch, seed=3)
+        for method, its in ((3, 1), (4, 1), (4, 2), (8, 1), (9, 1), (12, 1), (3, -1)):
+            a = np.empty_like(src)
+            assert util.ref().ref_morphology(P(src), P(a), 40, 29, ch, method, its, name.encode()) == 0
+            assert max_ulp(a, util.orc_morphology(src, method, its, [k])) == 0, (name, ch, method, its)
+
+
+@pytest.mark.parametrize("frm,to", [(23, 11), (23, 26), (23, 21), (11, 23), (26, 23), (21, 23), (26, 11)])
+def test_colorspace_bit_exact(frm, to):
+    src = make_image(64, 48, 4, seed=8)
+    a, b = src.copy(), src.copy()
+    assert util.ref().ref_colorspace(P(a), 64, 48, 4, frm, to) == 0
+    assert oracle().orc_colorspace(P(b), 64, 48, 4, frm, to) == 0
+    assert max_ulp(a, b) == 0
+
+
+def test_thread_count_independence():
+    """results do not depend on the OpenMP thread count."""
+    src = make_image(128, 96, 4, seed=1)
+    outs = []
+    for n in (1, 4):
+        util.ref().ref_set_threads(n)
+        a = np.empty_like(src)
+        assert util.ref().ref_blur(P(src), P(a), 128, 96, 4, 0.0, 2.0) == 0
+        outs.append(a)
+    assert max_ulp(outs[0], outs[1]) == 0
