@@ -50,50 +50,66 @@ def measured_peak():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples nvidia-smi clocks / throttle reasons (one long-running `nvidia-smi -lms`) while the
+    timed regions run."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index = index
-        self.samples = []
-        self._stop = threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+    def __init__(self, index: int, period_ms: int = 20):
+        self.index, self.period_ms = index, period_ms
+        self.proc = None
+        self.lines = []
 
     def __enter__(self):
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                 "-lms", str(self.period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._drain, daemon=True)
+            self._t.start()
+            time.sleep(0.15)                      # let the first samples arrive before timing starts
+        except Exception:
+            self.proc = None
         return self
 
-    def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+    def _drain(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line))
 
-    def summary(self):
-        if not self.samples:
+    def mark(self):
+        return time.perf_counter()
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0=None, t1=None):
+        rows = []
+        for t, line in self.lines:
+            if t0 is not None and not (t0 <= t <= (t1 or t) + 0.05):
+                continue
+            parts = [p.strip() for p in line.strip().split(",")]
+            if len(parts) >= 7:
+                rows.append(parts)
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        num = lambda x: float(x) if x.replace(".", "", 1).isdigit() else None
+        sm = [num(r[0]) for r in rows if num(r[0]) is not None]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            for n, v in zip(names, s[3:7]):
+        for r in rows:
+            for n, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
-                "samples": len(self.samples), "reasons": sorted(reasons)}
+        pw = [num(r[2]) for r in rows if num(r[2]) is not None]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": num(rows[0][1]),
+                "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------ CPU arms
@@ -200,9 +216,12 @@ def run_gpu(args):
     mdist.barrier()
     launches0 = im.launch_count()
     blur_ms, resize_ms = [], []
-    with ClockSampler(local) as clocks:
+    clocks = ClockSampler(local)
+    clocks.__enter__()
+    if True:
         torch.cuda.synchronize()
         mdist.barrier()
+        clk_t0 = clocks.mark()
         t_start, t_end = ev(), ev()
         marks = []
         t_start.record()
@@ -247,6 +266,8 @@ def run_gpu(args):
         step_e2e()
     b_.record()
     torch.cuda.synchronize()
+    clk_t1 = clocks.mark()
+    clocks.__exit__()
     e2e_ms = mdist.max_over_ranks(a.elapsed_time(b_) / e2e_steps, device=dev)
     e2e_value = world * W * H / e2e_ms / 1e3
 
@@ -276,7 +297,7 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": "Mpixels/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": W * H * 16, "d2h_bytes_per_step": (W // 2) * (H // 2) * 16},
         "gpu_launches": int(launches),
-        "clocks": clocks.summary(),
+        "clocks": clocks.summary(clk_t0, clk_t1),
     }
     # traffic from the committed ncu capture, when present
     try:

@@ -28,6 +28,8 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 namespace mb200 {
 namespace {
 
@@ -240,6 +242,12 @@ __global__ void __launch_bounds__(128, MINB) conv_row_kernel(const Conv1dArgs a,
   }
 }
 
+// developer tuning knobs (environment, read on every launch; defaults are the tuned values)
+int tuning(const char *name, int fallback) {
+  const char *v = getenv(name);
+  return (v && *v) ? atoi(v) : fallback;
+}
+
 template <int NT, int MODE>
 int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int ntaps, cudaStream_t stream) {
   Taps<NT> taps;
@@ -248,14 +256,14 @@ int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int nta
   if (axis == 1) {
     constexpr int kThreads = 128;
     constexpr int kMinBlocks = NT <= 33 ? 4 : 2;
-    a.strip = 8 * NT + 1;                       // strip + NT - 1 is a whole number of rotations
+    a.strip = tuning("MB200_COL_ROT", 8) * NT + 1;   // strip + NT - 1 is a whole number of rotations
     dim3 grid((a.rc + kThreads - 1) / kThreads, (a.height + a.strip - 1) / a.strip);
     conv_col_kernel<NT, MODE, kThreads, kMinBlocks><<<grid, kThreads, 0, stream>>>(a, taps);
   } else {
     constexpr int kMinBlocks = NT <= 33 ? 4 : 2;
     // strip + NT - 1 is a whole number of rotations and the strip is at least ~64 outputs
     constexpr int kRot = (63 + NT - 1) / NT < 2 ? 2 : (63 + NT - 1) / NT;
-    a.strip = kRot * NT + 1;
+    a.strip = tuning("MB200_ROW_ROT", kRot) * NT + 1;
     a.seg_w = a.strip + NT - 1;
     a.pitch = a.seg_w | 1;
     const int rows_per_cta = 4 * (32 / a.channels);
