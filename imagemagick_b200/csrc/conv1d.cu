@@ -28,6 +28,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdint>
 #include <cstdlib>
 
 namespace mb200 {
@@ -88,7 +89,9 @@ __device__ __forceinline__ float finish(const Finish &f, double sum, double gsum
 }
 
 template <int NT> struct Ring { static constexpr int value = NT; };
+template <> struct Ring<25> { static constexpr int value = 5; };
 template <> struct Ring<33> { static constexpr int value = 11; };
+template <> struct Ring<49> { static constexpr int value = 7; };
 template <> struct Ring<65> { static constexpr int value = 13; };
 
 // ---------------------------------------------------------------- column pass
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(THREADS, MINB) conv_col_kernel(const Conv1dArg
   ysrc += PF;                                  // next row to fetch
 
   int j = -(NT - 1);                           // output row (relative to y0) finished at this step
+#pragma unroll 1
   for (int mb = 0; mb < total; mb += NT) {
 #pragma unroll
     for (int s = 0; s < NT; ++s) {
@@ -216,6 +220,7 @@ __global__ void __launch_bounds__(128, MINB) conv_row_kernel(const Conv1dArgs a,
   for (int q = 0; q < NT; ++q) acc[q] = 0.0;
 
   int j = -(NT - 1);
+#pragma unroll 1
   for (int mb = 0; mb < total; mb += NT) {
 #pragma unroll
     for (int s = 0; s < NT; ++s) {
@@ -242,6 +247,249 @@ __global__ void __launch_bounds__(128, MINB) conv_row_kernel(const Conv1dArgs a,
   }
 }
 
+// ======================================================================================
+// TMA (cp.async.bulk + mbarrier) staged variants for RGBA.  Every warp owns a private
+// shared-memory ring of source chunks filled by the bulk-copy engine: no thread spends
+// registers or issue slots on global loads, the prefetch depth is set by the ring (not by the
+// register file), and warps never synchronise with each other (no __syncthreads in the loop).
+// Edge clamping is done by the producer lanes: out-of-image rows / pixels are bulk-copied from
+// the clamped source address.  Other layouts use the register-ring kernels above.
+// ======================================================================================
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// Spin on the barrier phase.  The loop lives inside the asm block so that the compiler sees one
+// convergent instruction; a bounded poll count traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u32 cnt;\n\t"
+      "mov.u32 cnt, 0;\n\t"
+      "MB200_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra MB200_DONE;\n\t"
+      "add.u32 cnt, cnt, 1;\n\t"
+      "setp.gt.u32 p, cnt, 0x4000000;\n\t"
+      "@p trap;\n\t"
+      "bra MB200_WAIT;\n\t"
+      "MB200_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+constexpr int kTmaSlots = 4;      // ring depth (chunks in flight per warp)
+
+// blend-lane output stage without bias: out = sum / clamp(den), den = blend ? gsum : 1; the
+// reference's PerceptibleReciprocal clamp (|QS*gsum| < MagickEpsilon) is decided on the float copy.
+__device__ __forceinline__ float finish_rgba(bool blend, double sum, double gsum) {
+  const double den = blend ? gsum : 1.0;
+  const float denf = static_cast<float>(den);
+  float seed;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"(denf));
+  const double r0 = static_cast<double>(seed);
+  const double e = fma(-den, r0, 1.0);
+  double r = fma(r0, e, r0);
+  if (fabsf(denf) < static_cast<float>(kEpsilon / kQuantumScale))
+    r = denf < 0.0f ? -(kQuantumScale / kEpsilon) : (kQuantumScale / kEpsilon);
+  return static_cast<float>(r * sum);
+}
+
+// Producer step of the column pass (lanes 0..PF-1 of the warp): one edge-clamped 128-byte row
+// segment per lane into the warp's ring slot.
+template <int PF>
+__device__ __forceinline__ void col_issue(float *slot_base, unsigned long long *bar, const char *gbase, int y_first,
+                                       int hmax, unsigned pitch_bytes, unsigned row_bytes, int lane) {
+  __syncwarp();                                           // every lane has finished reading this slot
+  if (lane == 0) mbar_expect_tx(bar, row_bytes * PF);
+  __syncwarp();
+  if (lane < PF) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const unsigned yy = static_cast<unsigned>(min(max(y_first + lane, 0), hmax));
+    bulk_g2s(slot_base + lane * 32, gbase + static_cast<size_t>(yy) * pitch_bytes, row_bytes, bar);
+  }
+}
+
+// Producer step of the row pass (lanes 0..7 = the warp's 8 tile rows): PF pixels per row, the
+// out-of-image pixels replicated from the edge pixel with 16-byte copies.
+template <int PF>
+__device__ __forceinline__ void row_issue(float *slot_base, unsigned long long *bar, const float4 *src, int ybase,
+                                       int hmax, int xs, int width, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_expect_tx(bar, 8u * PF * 16u);
+  __syncwarp();
+  if (lane < 8) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const float4 *grow = src + static_cast<size_t>(min(ybase + lane, hmax)) * width;
+    float *dst = slot_base + lane * (PF * 4);
+    const int lo = max(xs, 0), hi = min(xs + PF, width);   // in-image part [lo, hi)
+    if (hi > lo) bulk_g2s(dst + (lo - xs) * 4, grow + lo, static_cast<unsigned>(hi - lo) * 16u, bar);
+#pragma unroll 1
+    for (int x = xs; x < min(xs + PF, 0); ++x) bulk_g2s(dst + (x - xs) * 4, grow, 16u, bar);
+#pragma unroll 1
+    for (int x = max(xs, width); x < xs + PF; ++x) bulk_g2s(dst + (x - xs) * 4, grow + (width - 1), 16u, bar);
+  }
+}
+
+// ---- column pass: CTA = 4 independent warps; a warp covers 32 consecutive components (8 RGBA
+//      pixels, 128 B per row); chunk = PF rows.  grid: (ceil(rc/128), ceil(height/strip)).
+template <int NT, int MINB>
+__global__ void __launch_bounds__(128, MINB) conv_col_tma_kernel(const Conv1dArgs a, const Taps<NT> taps) {
+  constexpr int PF = Ring<NT>::value;
+  __shared__ __align__(128) float ring[4][kTmaSlots][PF][32];
+  __shared__ __align__(8) unsigned long long full[4][kTmaSlots];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = blockIdx.x * 128 + warp * 32;
+  if (col0 >= a.rc) return;                              // whole warp out of the image (warps are independent)
+  const bool blend = (lane & 3) != 3;
+  const int alpha_lane = lane | 3;
+  const int y0 = blockIdx.y * a.strip;
+  const int nout = min(a.strip, a.height - y0);
+  const int total = a.strip + NT - 1;                 // multiple of NT, hence of PF
+  const int nchunks = total / PF;
+  const int hmax = a.height - 1;
+  const unsigned pitch_bytes = static_cast<unsigned>(a.rc) * 4u;
+  const char *gbase = reinterpret_cast<const char *>(a.src + col0);
+  char *outp = reinterpret_cast<char *>(a.dst + col0 + lane) + static_cast<size_t>(y0) * pitch_bytes;
+  unsigned long long *bars = &full[warp][0];
+  float *wring = &ring[warp][0][0][0];
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kTmaSlots; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int ysrc0 = y0 - a.off;
+  for (int c = 0; c < kTmaSlots - 1 && c < nchunks; ++c)
+    col_issue<PF>(wring + c * (PF * 32), &bars[c], gbase, ysrc0 + c * PF, hmax, pitch_bytes, 128u, lane);
+
+  double acc[NT];
+#pragma unroll
+  for (int q = 0; q < NT; ++q) acc[q] = 0.0;
+  int j = -(NT - 1);
+  int chunk = 0, slot = 0, nslot = kTmaSlots - 1;     // nslot = slot of chunk + kTmaSlots - 1
+  unsigned parity = 0;
+#pragma unroll 1
+  for (int mb = 0; mb < total; mb += NT) {
+#pragma unroll
+    for (int s = 0; s < NT; ++s) {
+      if (s % PF == 0) {
+        // the slot of chunk-1 is free now: refill it with chunk + kTmaSlots - 1, then wait for ours
+        const int nxt = chunk + kTmaSlots - 1;
+        if (nxt < nchunks)
+          col_issue<PF>(wring + nslot * (PF * 32), &bars[nslot], gbase, ysrc0 + nxt * PF, hmax, pitch_bytes, 128u, lane);
+        mbar_wait(&bars[slot], parity);
+      }
+      const float *rowp = wring + (slot * PF + (s % PF)) * 32;
+      const float vf = rowp[lane];
+      float af = rowp[alpha_lane];
+      af = blend ? af : 1.0f;
+      const double v = static_cast<double>(vf) * static_cast<double>(af);
+#pragma unroll
+      for (int q = 0; q < NT; ++q) acc[q] = fma(taps.k[(s - q + NT) % NT], v, acc[q]);
+      const int qf = (s + 1) % NT;
+      const double sum = acc[qf];
+      acc[qf] = 0.0;
+      const double gsum = shfl_double(sum, alpha_lane);
+      const float out = finish_rgba(blend, sum, gsum);
+      if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<float *>(outp) = out;
+      if (j >= 0) outp += pitch_bytes;
+      ++j;
+      if (s % PF == PF - 1) {
+        ++chunk;
+        nslot = slot;
+        if (++slot == kTmaSlots) { slot = 0; parity ^= 1u; }
+      }
+    }
+  }
+}
+
+// ---- row pass: CTA = 4 independent warps; a warp covers 8 rows x 4 channels; chunk = PF pixels of
+//      each row (pitch PF pixels, odd => conflict-free LDS).  grid: (ceil(width/strip), ceil(height/32)).
+template <int NT, int MINB>
+__global__ void __launch_bounds__(128, MINB) conv_row_tma_kernel(const Conv1dArgs a, const Taps<NT> taps) {
+  constexpr int PF = Ring<NT>::value;
+  static_assert(PF % 2 == 1, "odd chunk pitch keeps the LDS conflict-free");
+  __shared__ __align__(128) float ring[4][kTmaSlots][8][PF * 4];
+  __shared__ __align__(8) unsigned long long full[4][kTmaSlots];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ybase = blockIdx.y * 32 + warp * 8;
+  if (ybase >= a.height) return;
+  const int lr = lane >> 2, c = lane & 3;
+  const int x0 = blockIdx.x * a.strip;
+  const int y = ybase + lr;
+  const int hmax = a.height - 1;
+  const int nout = y < a.height ? min(a.strip, a.width - x0) : 0;
+  const int total = a.strip + NT - 1;
+  const int nchunks = total / PF;
+  const bool blend = c != 3;
+  const int alpha_lane = lane | 3;
+  float *outp = a.dst + (static_cast<size_t>(min(y, hmax)) * a.width + x0) * 4 + c;
+  unsigned long long *bars = &full[warp][0];
+  float *wring = &ring[warp][0][0][0];
+  const float4 *src4 = reinterpret_cast<const float4 *>(a.src);
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kTmaSlots; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int xsrc0 = x0 - a.off;
+  for (int ck = 0; ck < kTmaSlots - 1 && ck < nchunks; ++ck)
+    row_issue<PF>(wring + ck * (8 * PF * 4), &bars[ck], src4, ybase, hmax, xsrc0 + ck * PF, a.width, lane);
+
+  double acc[NT];
+#pragma unroll
+  for (int q = 0; q < NT; ++q) acc[q] = 0.0;
+  int j = -(NT - 1);
+  int chunk = 0, slot = 0, nslot = kTmaSlots - 1;
+  unsigned parity = 0;
+#pragma unroll 1
+  for (int mb = 0; mb < total; mb += NT) {
+#pragma unroll
+    for (int s = 0; s < NT; ++s) {
+      if (s % PF == 0) {
+        const int nxt = chunk + kTmaSlots - 1;
+        if (nxt < nchunks)
+          row_issue<PF>(wring + nslot * (8 * PF * 4), &bars[nslot], src4, ybase, hmax, xsrc0 + nxt * PF, a.width, lane);
+        mbar_wait(&bars[slot], parity);
+      }
+      const float *pp = wring + ((slot * 8 + lr) * PF + (s % PF)) * 4;
+      const float vf = pp[c];
+      float af = pp[3];
+      af = blend ? af : 1.0f;
+      const double v = static_cast<double>(vf) * static_cast<double>(af);
+#pragma unroll
+      for (int q = 0; q < NT; ++q) acc[q] = fma(taps.k[(s - q + NT) % NT], v, acc[q]);
+      const int qf = (s + 1) % NT;
+      const double sum = acc[qf];
+      acc[qf] = 0.0;
+      const double gsum = shfl_double(sum, alpha_lane);
+      const float out = finish_rgba(blend, sum, gsum);
+      if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *outp = out;
+      if (j >= 0) outp += 4;
+      ++j;
+      if (s % PF == PF - 1) {
+        ++chunk;
+        nslot = slot;
+        if (++slot == kTmaSlots) { slot = 0; parity ^= 1u; }
+      }
+    }
+  }
+}
+
 // developer tuning knobs (environment, read on every launch; defaults are the tuned values)
 int tuning(const char *name, int fallback) {
   const char *v = getenv(name);
@@ -253,7 +501,21 @@ int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int nta
   Taps<NT> taps;
   for (int i = 0; i < NT; ++i) taps.k[i] = i < ntaps ? taps_host[i] : 0.0;   // zero padding past the window
   Conv1dArgs a = base;
-  if (axis == 1) {
+  const bool tma_ok = MODE == 4 && a.bias == 0.0 && tuning("MB200_TMA", 0) != 0 && (a.rc % 32) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(a.src) | reinterpret_cast<uintptr_t>(a.dst)) & 15) == 0;
+  if (tma_ok && axis == 1) {
+    constexpr int kMinBlocks = NT <= 33 ? 4 : 2;
+    a.strip = tuning("MB200_COL_ROT", 8) * NT + 1;
+    dim3 grid((a.rc + 127) / 128, (a.height + a.strip - 1) / a.strip);
+    if (NT == 33 && tuning("MB200_MINB", 3) == 3) conv_col_tma_kernel<NT, 3><<<grid, 128, 0, stream>>>(a, taps);
+    else conv_col_tma_kernel<NT, kMinBlocks><<<grid, 128, 0, stream>>>(a, taps);
+  } else if (tma_ok && axis == 0) {
+    constexpr int kMinBlocks = NT <= 33 ? 4 : 2;
+    a.strip = tuning("MB200_ROW_TMA_ROT", 8) * NT + 1;
+    dim3 grid((a.width + a.strip - 1) / a.strip, (a.height + 31) / 32);
+    if (NT == 33 && tuning("MB200_MINB", 3) == 3) conv_row_tma_kernel<NT, 3><<<grid, 128, 0, stream>>>(a, taps);
+    else conv_row_tma_kernel<NT, kMinBlocks><<<grid, 128, 0, stream>>>(a, taps);
+  } else if (axis == 1) {
     constexpr int kThreads = 128;
     constexpr int kMinBlocks = NT <= 33 ? 4 : 2;
     a.strip = tuning("MB200_COL_ROT", 8) * NT + 1;   // strip + NT - 1 is a whole number of rotations
