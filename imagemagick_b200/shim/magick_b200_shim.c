@@ -1,0 +1,342 @@
+/*
+  magick_b200_shim.c -- the drop-in boundary: ImageMagick's own MagickCore entry points of
+  the hot path, backed by libmagickb200 (include/magick_b200.h).
+
+  Link an application / the MagickCore library with
+      -Wl,--wrap=BlurImage,--wrap=GaussianBlurImage,--wrap=ConvolveImage,--wrap=UnsharpMaskImage,\
+          --wrap=MorphologyImage,--wrap=ResizeImage,--wrap=TransformImageColorspace
+  and every caller of those exported functions (effect.c:765/1709/1170/4256, morphology.c:4129,
+  resize.c:3761, colorspace.c:1751) reaches __wrap_X below.  Each wrapper follows the accelerate
+  hook contract of effect.c:783-787 / resize.c:3818-3826: try the GPU; if the image is not
+  eligible or the GPU path declines (returns NULL / MagickFalse without raising), run the stock
+  CPU implementation (__real_X).  B200Accelerate*Image() are the same functions with the
+  accelerate-private.h:35-62 signatures, for a build that patches the #if OPENCL call sites.
+
+  Only public MagickCore API is used: GetVirtualPixels / GetAuthenticPixels return the pixel cache
+  itself for full-frame requests on memory caches (cache.c:5126-5156), which is exactly the
+  interleaved float Quantum layout the C-ABI takes.
+*/
+#include "MagickCore/studio.h"
+#include "MagickCore/MagickCore.h"
+#include "magick_b200.h"
+#include <string.h>
+
+#if !defined(MAGICKCORE_HDRI_SUPPORT) || (MAGICKCORE_QUANTUM_DEPTH != 16)
+# error "magick_b200_shim targets the reference's default Q16-HDRI build (Quantum == float)"
+#endif
+
+/* ---- eligibility: mirrors checkAccelerateCondition (accelerate.c:110-170) + SURVEY 8b --------- */
+static int b200_channels(const Image *image)
+{
+  const size_t n = GetPixelChannels(image);
+  const MagickBooleanType gray = (image->colorspace == GRAYColorspace) ||
+    (image->colorspace == LinearGRAYColorspace) ? MagickTrue : MagickFalse;
+  if (image->storage_class != DirectClass) return 0;
+  if ((image->channels & (ReadMaskChannel | WriteMaskChannel | CompositeMaskChannel)) != 0) return 0;
+  if (image->number_meta_channels != 0) return 0;
+  if ((GetImageVirtualPixelMethod(image) != UndefinedVirtualPixelMethod) &&
+      (GetImageVirtualPixelMethod(image) != EdgeVirtualPixelMethod)) return 0;
+  if (image->progress_monitor != (MagickProgressMonitor) NULL) return 0;
+  if (n < 1 || n > 4) return 0;
+  if (GetPixelChannelOffset(image, RedPixelChannel) != 0) return 0;
+  {
+    /* every channel must carry the default traits (no -channel restriction, pixel.c:6356-6381) */
+    ssize_t i;
+    for (i = 0; i < (ssize_t) n; i++) {
+      PixelChannel ch = GetPixelChannelChannel(image, i);
+      PixelTrait want = (ch == AlphaPixelChannel || image->alpha_trait == UndefinedPixelTrait)
+        ? UpdatePixelTrait : (PixelTrait) (UpdatePixelTrait | BlendPixelTrait);
+      if (GetPixelChannelTraits(image, ch) != want) return 0;
+    }
+  }
+  if (gray != MagickFalse) {
+    if (n == 1 && image->alpha_trait == UndefinedPixelTrait) return 1;
+    if (n == 2 && image->alpha_trait != UndefinedPixelTrait &&
+        GetPixelChannelOffset(image, AlphaPixelChannel) == 1) return 2;
+    return 0;
+  }
+  if (image->colorspace == CMYKColorspace) return 0;
+  if (GetPixelChannelOffset(image, GreenPixelChannel) != 1 ||
+      GetPixelChannelOffset(image, BluePixelChannel) != 2) return 0;
+  if (n == 3 && image->alpha_trait == UndefinedPixelTrait) return 3;
+  if (n == 4 && image->alpha_trait != UndefinedPixelTrait &&
+      GetPixelChannelOffset(image, AlphaPixelChannel) == 3) return 4;
+  return 0;
+}
+
+static MagickBooleanType has_artifact(const Image *image, const char *const *names)
+{
+  for (; *names != (const char *) NULL; names++)
+    if (GetImageArtifact(image, *names) != (const char *) NULL) return MagickTrue;
+  return MagickFalse;
+}
+
+static const char *const morphology_artifacts[] = { "convolve:bias", "convolve:scale",
+  "morphology:compose", "morphology:showKernel", "debug", (const char *) NULL };
+static const char *const filter_artifacts[] = { "filter:filter", "filter:window", "filter:sigma",
+  "filter:alpha", "filter:kaiser-beta", "filter:kaiser-alpha", "filter:lobes", "filter:blur",
+  "filter:support", "filter:win-support", "filter:b", "filter:c", "filter:verbose",
+  (const char *) NULL };
+
+/* Output image with the reference's conventions (morphology.c:3926-3933, resize.c:3827, :3872). */
+static Image *new_result(const Image *image, size_t columns, size_t rows, ExceptionInfo *exception)
+{
+  Image *out = CloneImage(image, columns, rows, MagickTrue, exception);
+  if (out == (Image *) NULL) return out;
+  if (SetImageStorageClass(out, DirectClass, exception) == MagickFalse) return DestroyImage(out);
+  if (GetPixelChannels(out) != GetPixelChannels(image)) return DestroyImage(out);
+  return out;
+}
+
+typedef int (*same_size_op)(const float *, float *, size_t, size_t, int, const void *);
+
+/* src pixels -> new image through `op`; NULL == declined (caller falls back to the CPU). */
+static Image *run_same_size(const Image *image, same_size_op op, const void *args,
+                            ExceptionInfo *exception)
+{
+  const int ch = b200_channels(image);
+  const Quantum *p;
+  Quantum *q;
+  Image *out;
+  if (ch == 0 || mb200_device_count() <= 0) return (Image *) NULL;
+  p = GetVirtualPixels(image, 0, 0, image->columns, image->rows, exception);
+  if (p == (const Quantum *) NULL) return (Image *) NULL;
+  out = new_result(image, image->columns, image->rows, exception);
+  if (out == (Image *) NULL) return out;
+  q = GetAuthenticPixels(out, 0, 0, out->columns, out->rows, exception);
+  if (q == (Quantum *) NULL || op((const float *) p, (float *) q, image->columns, image->rows, ch, args) != MB200_OK ||
+      SyncAuthenticPixels(out, exception) == MagickFalse)
+    return DestroyImage(out);
+  out->type = image->type;
+  return out;
+}
+
+/* ---- BlurImage / GaussianBlurImage / UnsharpMaskImage ------------------------------------------ */
+typedef struct { double radius, sigma, gain, threshold; } blur_args;
+static int op_blur(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
+{ const blur_args *b = (const blur_args *) a; return mb200_blur_image(s, d, w, h, ch, b->radius, b->sigma); }
+static int op_gaussian(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
+{ const blur_args *b = (const blur_args *) a; return mb200_gaussian_blur_image(s, d, w, h, ch, b->radius, b->sigma); }
+static int op_unsharp(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
+{ const blur_args *b = (const blur_args *) a;
+  return mb200_unsharp_mask_image(s, d, w, h, ch, b->radius, b->sigma, b->gain, b->threshold); }
+
+Image *B200AccelerateBlurImage(const Image *image, const double radius, const double sigma,
+                               ExceptionInfo *exception)
+{
+  blur_args a = { radius, sigma, 0.0, 0.0 };
+  if (has_artifact(image, morphology_artifacts) != MagickFalse) return (Image *) NULL;
+  return run_same_size(image, op_blur, &a, exception);
+}
+
+Image *B200AccelerateGaussianBlurImage(const Image *image, const double radius, const double sigma,
+                                       ExceptionInfo *exception)
+{
+  blur_args a = { radius, sigma, 0.0, 0.0 };
+  if (has_artifact(image, morphology_artifacts) != MagickFalse) return (Image *) NULL;
+  return run_same_size(image, op_gaussian, &a, exception);
+}
+
+Image *B200AccelerateUnsharpMaskImage(const Image *image, const double radius, const double sigma,
+                                      const double gain, const double threshold, ExceptionInfo *exception)
+{
+  blur_args a = { radius, sigma, gain, threshold };
+  if (has_artifact(image, morphology_artifacts) != MagickFalse) return (Image *) NULL;
+  return run_same_size(image, op_unsharp, &a, exception);
+}
+
+/* ---- MorphologyImage / ConvolveImage --------------------------------------------------------------- */
+static int map_kernel_type(KernelInfoType t)
+{
+  switch (t) {                       /* only what RotateKernelInfo distinguishes (morphology.c:4281-4305) */
+    case BlurKernel: return MB200_BlurKernel;
+    case GaussianKernel: case DoGKernel: case LoGKernel: case DiskKernel: case PeaksKernel:
+    case LaplacianKernel: case ChebyshevKernel: case ManhattanKernel: case EuclideanKernel:
+      return MB200_GaussianKernel;
+    case SquareKernel: case DiamondKernel: case PlusKernel: case CrossKernel: return MB200_SquareKernel;
+    default: return MB200_UserDefinedKernel;
+  }
+}
+
+typedef struct { int method; long iterations; const KernelInfo *kernel; } morph_args;
+static int op_morphology(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
+{
+  const morph_args *m = (const morph_args *) a;
+  mb200_kernel_info nodes[64];
+  const KernelInfo *k;
+  int n = 0, rc;
+  for (k = m->kernel; k != (const KernelInfo *) NULL; k = k->next) {
+    if (n == 64) return MB200_EUNSUPPORTED;
+    memset(&nodes[n], 0, sizeof(nodes[n]));
+    nodes[n].type = map_kernel_type(k->type);
+    nodes[n].width = k->width; nodes[n].height = k->height;
+    nodes[n].x = (long) k->x; nodes[n].y = (long) k->y;
+    nodes[n].values = (double *) k->values;      /* MagickRealType == double; read-only use */
+    nodes[n].minimum = k->minimum; nodes[n].maximum = k->maximum;
+    nodes[n].negative_range = k->negative_range; nodes[n].positive_range = k->positive_range;
+    nodes[n].angle = k->angle;
+    if (n > 0) nodes[n - 1].next = &nodes[n];
+    n++;
+  }
+  if (n == 0) return MB200_EINVAL;
+  rc = mb200_morphology_image(s, d, w, h, ch, m->method, m->iterations, &nodes[0], 0.0);
+  return rc;
+}
+
+Image *B200AccelerateMorphologyImage(const Image *image, const MorphologyMethod method,
+                                     const ssize_t iterations, const KernelInfo *kernel,
+                                     ExceptionInfo *exception)
+{
+  morph_args a;
+  if (kernel == (const KernelInfo *) NULL || iterations == 0) return (Image *) NULL;
+  if (has_artifact(image, morphology_artifacts) != MagickFalse) return (Image *) NULL;
+  switch (method) {
+    case ConvolveMorphology: case CorrelateMorphology: case ErodeMorphology: case DilateMorphology:
+    case OpenMorphology: case CloseMorphology: case SmoothMorphology: break;
+    default: return (Image *) NULL;          /* needs CompositeImage / sequential primitives: CPU */
+  }
+  a.method = (int) method; a.iterations = (long) iterations; a.kernel = kernel;
+  return run_same_size(image, op_morphology, &a, exception);
+}
+
+/* ---- ResizeImage -------------------------------------------------------------------------------------- */
+Image *B200AccelerateResizeImage(const Image *image, const size_t columns, const size_t rows,
+                                 const FilterType filter, ExceptionInfo *exception)
+{
+  const int ch = b200_channels(image);
+  const Quantum *p;
+  Quantum *q;
+  Image *out;
+  if (ch == 0 || columns == 0 || rows == 0 || mb200_device_count() <= 0) return (Image *) NULL;
+  if (has_artifact(image, filter_artifacts) != MagickFalse) return (Image *) NULL;
+  if (image->storage_class == PseudoClass) return (Image *) NULL;
+  p = GetVirtualPixels(image, 0, 0, image->columns, image->rows, exception);
+  if (p == (const Quantum *) NULL) return (Image *) NULL;
+  out = new_result(image, columns, rows, exception);
+  if (out == (Image *) NULL) return out;
+  q = GetAuthenticPixels(out, 0, 0, columns, rows, exception);
+  if (q == (Quantum *) NULL ||
+      mb200_resize_image((const float *) p, image->columns, image->rows, ch, (float *) q, columns, rows,
+                         (int) filter) != MB200_OK ||
+      SyncAuthenticPixels(out, exception) == MagickFalse)
+    return DestroyImage(out);
+  out->type = image->type;
+  return out;
+}
+
+/* ---- TransformImageColorspace (in place) ------------------------------------------------------------ */
+static int map_colorspace(ColorspaceType c)
+{
+  switch (c) {
+    case sRGBColorspace: return MB200_sRGBColorspace;
+    case RGBColorspace: return MB200_RGBColorspace;
+    case LabColorspace: return MB200_LabColorspace;
+    case XYZColorspace: return MB200_XYZColorspace;
+    default: return -1;
+  }
+}
+
+MagickBooleanType B200AccelerateTransformImageColorspace(Image *image, const ColorspaceType colorspace,
+                                                         ExceptionInfo *exception)
+{
+  const int from = map_colorspace(image->colorspace), to = map_colorspace(colorspace);
+  ColorspaceType saved = image->colorspace;
+  Quantum *q;
+  int ch;
+  if (from < 0 || to < 0 || from == to || mb200_device_count() <= 0) return MagickFalse;
+  if (GetImageArtifact(image, "color:illuminant") != (const char *) NULL) return MagickFalse;
+  if (GetImageProperty(image, "white-luminance", exception) != (const char *) NULL) return MagickFalse;
+  /* the channel layout test is colourspace-agnostic for 3/4-channel images */
+  image->colorspace = sRGBColorspace;
+  ch = b200_channels(image);
+  image->colorspace = saved;
+  if (ch != 3 && ch != 4) return MagickFalse;
+  q = GetAuthenticPixels(image, 0, 0, image->columns, image->rows, exception);
+  if (q == (Quantum *) NULL) return MagickFalse;
+  (void) DeleteImageProfile(image, "icc");                 /* colorspace.c:1763-1764 */
+  (void) DeleteImageProfile(image, "icm");
+  if (mb200_transform_colorspace((float *) q, image->columns, image->rows, ch, from, to) != MB200_OK)
+    return MagickFalse;
+  if (SyncAuthenticPixels(image, exception) == MagickFalse) return MagickFalse;
+  return SetImageColorspace(image, colorspace, exception);  /* colorspace.c:1051 */
+}
+
+/* ---- ld --wrap entry points ------------------------------------------------------------------------------ */
+extern Image *__real_BlurImage(const Image *, const double, const double, ExceptionInfo *);
+extern Image *__real_GaussianBlurImage(const Image *, const double, const double, ExceptionInfo *);
+extern Image *__real_ConvolveImage(const Image *, const KernelInfo *, ExceptionInfo *);
+extern Image *__real_UnsharpMaskImage(const Image *, const double, const double, const double, const double,
+                                      ExceptionInfo *);
+extern Image *__real_MorphologyImage(const Image *, const MorphologyMethod, const ssize_t, const KernelInfo *,
+                                     ExceptionInfo *);
+extern Image *__real_ResizeImage(const Image *, const size_t, const size_t, const FilterType, ExceptionInfo *);
+extern MagickBooleanType __real_TransformImageColorspace(Image *, const ColorspaceType, ExceptionInfo *);
+
+static long b200_hits = 0, b200_fallbacks = 0;
+static int b200_enabled = -1;       /* -1: not yet read from the environment */
+long B200ShimHits(void) { return b200_hits; }
+long B200ShimFallbacks(void) { return b200_fallbacks; }
+/* Runtime switch (also: environment MAGICK_B200_DISABLE=1), e.g. to A/B against the CPU path. */
+void B200ShimEnable(int on) { b200_enabled = on ? 1 : 0; }
+static int b200_on(void)
+{
+  if (b200_enabled < 0) {
+    const char *e = getenv("MAGICK_B200_DISABLE");
+    b200_enabled = (e != (const char *) NULL && *e != '\0' && *e != '0') ? 0 : 1;
+  }
+  return b200_enabled;
+}
+#define TRY(expr) do { if (b200_on()) { Image *r_ = (expr); if (r_ != (Image *) NULL) { b200_hits++; return r_; } b200_fallbacks++; } } while (0)
+
+Image *__wrap_BlurImage(const Image *image, const double radius, const double sigma, ExceptionInfo *exception)
+{
+  TRY(B200AccelerateBlurImage(image, radius, sigma, exception));
+  return __real_BlurImage(image, radius, sigma, exception);
+}
+
+Image *__wrap_GaussianBlurImage(const Image *image, const double radius, const double sigma,
+                                ExceptionInfo *exception)
+{
+  TRY(B200AccelerateGaussianBlurImage(image, radius, sigma, exception));
+  return __real_GaussianBlurImage(image, radius, sigma, exception);
+}
+
+Image *__wrap_ConvolveImage(const Image *image, const KernelInfo *kernel, ExceptionInfo *exception)
+{
+  TRY(B200AccelerateMorphologyImage(image, ConvolveMorphology, 1, kernel, exception));
+  return __real_ConvolveImage(image, kernel, exception);
+}
+
+Image *__wrap_UnsharpMaskImage(const Image *image, const double radius, const double sigma, const double gain,
+                               const double threshold, ExceptionInfo *exception)
+{
+  TRY(B200AccelerateUnsharpMaskImage(image, radius, sigma, gain, threshold, exception));
+  return __real_UnsharpMaskImage(image, radius, sigma, gain, threshold, exception);
+}
+
+Image *__wrap_MorphologyImage(const Image *image, const MorphologyMethod method, const ssize_t iterations,
+                              const KernelInfo *kernel, ExceptionInfo *exception)
+{
+  TRY(B200AccelerateMorphologyImage(image, method, iterations, kernel, exception));
+  return __real_MorphologyImage(image, method, iterations, kernel, exception);
+}
+
+Image *__wrap_ResizeImage(const Image *image, const size_t columns, const size_t rows, const FilterType filter,
+                          ExceptionInfo *exception)
+{
+  TRY(B200AccelerateResizeImage(image, columns, rows, filter, exception));
+  return __real_ResizeImage(image, columns, rows, filter, exception);
+}
+
+MagickBooleanType __wrap_TransformImageColorspace(Image *image, const ColorspaceType colorspace,
+                                                  ExceptionInfo *exception)
+{
+  if (b200_on()) {
+    if (B200AccelerateTransformImageColorspace(image, colorspace, exception) != MagickFalse) {
+      b200_hits++;
+      return MagickTrue;
+    }
+    b200_fallbacks++;
+  }
+  return __real_TransformImageColorspace(image, colorspace, exception);
+}

@@ -1,0 +1,111 @@
+/*
+  shim_harness.c -- end-to-end check of the drop-in boundary (test infrastructure).
+
+  Linked with the UNMODIFIED reference MagickCore (oracle/_ref/libMagickCoreRef.a), the shim and
+  libmagickb200 using ld --wrap: every call below enters through ImageMagick's own exported entry
+  point, is served by the GPU, and is compared against __real_X (the stock CPU path) on the same
+  Image.  Exit code 0 == all within the parity bar and every operator actually hit the GPU path.
+*/
+#include "MagickCore/studio.h"
+#include "MagickCore/MagickCore.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+extern Image *__real_BlurImage(const Image *, const double, const double, ExceptionInfo *);
+extern Image *__real_GaussianBlurImage(const Image *, const double, const double, ExceptionInfo *);
+extern Image *__real_UnsharpMaskImage(const Image *, const double, const double, const double, const double, ExceptionInfo *);
+extern Image *__real_MorphologyImage(const Image *, const MorphologyMethod, const ssize_t, const KernelInfo *, ExceptionInfo *);
+extern Image *__real_ResizeImage(const Image *, const size_t, const size_t, const FilterType, ExceptionInfo *);
+extern MagickBooleanType __real_TransformImageColorspace(Image *, const ColorspaceType, ExceptionInfo *);
+extern long B200ShimHits(void), B200ShimFallbacks(void);
+extern void B200ShimEnable(int);
+
+static long ulp(float a, float b)
+{
+  int ia, ib;
+  memcpy(&ia, &a, 4); memcpy(&ib, &b, 4);
+  if (ia < 0) ia = -(ia & 0x7fffffff);
+  if (ib < 0) ib = -(ib & 0x7fffffff);
+  return labs((long) ia - (long) ib);
+}
+
+static long compare(const Image *a, const Image *b, ExceptionInfo *ex)
+{
+  const Quantum *p, *q;
+  size_t i, n;
+  long worst = 0;
+  if (!a || !b || a->columns != b->columns || a->rows != b->rows) return 1L << 40;
+  n = a->columns * a->rows * GetPixelChannels(a);
+  p = GetVirtualPixels(a, 0, 0, a->columns, a->rows, ex);
+  q = GetVirtualPixels(b, 0, 0, b->columns, b->rows, ex);
+  for (i = 0; i < n; i++) { long d = ulp((float) p[i], (float) q[i]); if (d > worst) worst = d; }
+  return worst;
+}
+
+static Image *noise_image(size_t w, size_t h, MagickBooleanType alpha, ExceptionInfo *ex)
+{
+  ImageInfo *info = AcquireImageInfo();
+  Image *im = AcquireImage(info, ex);
+  Quantum *q;
+  size_t i, n;
+  unsigned long long s = 88172645463325252ULL;
+  info = DestroyImageInfo(info);
+  (void) SetImageExtent(im, w, h, ex);
+  if (alpha) im->alpha_trait = BlendPixelTrait;
+  (void) SetImageStorageClass(im, DirectClass, ex);
+  (void) SetImageColorspace(im, sRGBColorspace, ex);
+  q = GetAuthenticPixels(im, 0, 0, w, h, ex);
+  n = w * h * GetPixelChannels(im);
+  for (i = 0; i < n; i++) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; q[i] = (Quantum) ((s >> 40) * (65535.0 / 16777215.0)); }
+  (void) SyncAuthenticPixels(im, ex);
+  return im;
+}
+
+#define CPU(expr) (B200ShimEnable(0), cpu_tmp = (expr), B200ShimEnable(1), cpu_tmp)
+#define CHECK(name, bar, gpu, cpu) do { Image *g_ = (gpu); Image *c_ = (cpu); long d_ = compare(g_, c_, ex); \
+  printf("%-34s max ULP %ld (bar %d)%s\n", name, d_, bar, d_ <= bar ? "" : "  FAIL"); if (d_ > bar) failures++; \
+  if (g_) DestroyImage(g_); if (c_) DestroyImage(c_); } while (0)
+
+int main(void)
+{
+  ExceptionInfo *ex;
+  Image *rgba, *rgb, *a, *b, *cpu_tmp;
+  KernelInfo *k;
+  int failures = 0;
+  MagickCoreGenesis("shim_harness", MagickFalse);
+  ex = AcquireExceptionInfo();
+  rgba = noise_image(517, 389, MagickTrue, ex);
+  rgb = noise_image(300, 200, MagickFalse, ex);
+
+  CHECK("BlurImage(0,4) RGBA", 1, BlurImage(rgba, 0.0, 4.0, ex), CPU(__real_BlurImage(rgba, 0.0, 4.0, ex)));
+  CHECK("BlurImage(0,2) RGB", 1, BlurImage(rgb, 0.0, 2.0, ex), CPU(__real_BlurImage(rgb, 0.0, 2.0, ex)));
+  CHECK("GaussianBlurImage(0,1.5) RGBA", 1, GaussianBlurImage(rgba, 0.0, 1.5, ex), CPU(__real_GaussianBlurImage(rgba, 0.0, 1.5, ex)));
+  CHECK("UnsharpMaskImage RGBA", 2, UnsharpMaskImage(rgba, 0.0, 2.0, 1.5, 0.02, ex), CPU(__real_UnsharpMaskImage(rgba, 0.0, 2.0, 1.5, 0.02, ex)));
+  CHECK("ResizeImage Lanczos 2x down RGBA", 1, ResizeImage(rgba, 258, 194, LanczosFilter, ex), CPU(__real_ResizeImage(rgba, 258, 194, LanczosFilter, ex)));
+  CHECK("ResizeImage default up RGB", 1, ResizeImage(rgb, 450, 300, UndefinedFilter, ex), CPU(__real_ResizeImage(rgb, 450, 300, UndefinedFilter, ex)));
+  k = AcquireKernelInfo("Disk:3", ex);
+  CHECK("MorphologyImage Dilate Disk:3", 0, MorphologyImage(rgba, DilateMorphology, 1, k, ex), CPU(__real_MorphologyImage(rgba, DilateMorphology, 1, k, ex)));
+  CHECK("MorphologyImage Erode x2 Disk:3", 0, MorphologyImage(rgb, ErodeMorphology, 2, k, ex), CPU(__real_MorphologyImage(rgb, ErodeMorphology, 2, k, ex)));
+  k = DestroyKernelInfo(k);
+  a = CloneImage(rgba, 0, 0, MagickTrue, ex); b = CloneImage(rgba, 0, 0, MagickTrue, ex);
+  if (TransformImageColorspace(a, LabColorspace, ex) == MagickFalse || a->colorspace != LabColorspace) failures++;
+  B200ShimEnable(0); (void) __real_TransformImageColorspace(b, LabColorspace, ex); B200ShimEnable(1);
+  CHECK("TransformImageColorspace sRGB->Lab", 1, a, b);
+  {
+    /* a declined case must silently take the CPU path: tiled virtual pixels are not eligible */
+    long fb = B200ShimFallbacks();
+    Image *t = CloneImage(rgb, 0, 0, MagickTrue, ex);
+    (void) SetImageVirtualPixelMethod(t, TileVirtualPixelMethod, ex);
+    a = BlurImage(t, 0.0, 1.0, ex); b = CPU(__real_BlurImage(t, 0.0, 1.0, ex));
+    CHECK("fallback: tile virtual pixels", 0, a, b);
+    if (B200ShimFallbacks() <= fb) { printf("expected a fallback\n"); failures++; }
+    t = DestroyImage(t);
+  }
+  printf("gpu hits %ld, cpu fallbacks %ld\n", B200ShimHits(), B200ShimFallbacks());
+  if (B200ShimHits() < 9) { printf("FAIL: operators did not reach the GPU path\n"); failures++; }
+  rgba = DestroyImage(rgba); rgb = DestroyImage(rgb);
+  ex = DestroyExceptionInfo(ex);
+  MagickCoreTerminus();
+  return failures ? 1 : 0;
+}

@@ -220,3 +220,18 @@ def test_errors_are_loud():
         im.AcquireKernelInfo("nosuchkernel:3")
     with pytest.raises(im.MagickB200Error):
         im.ResizeImage(_dev(src), 0, 8)
+
+
+def test_magickcore_shim_end_to_end():
+    """The drop-in boundary: ImageMagick's own BlurImage/ResizeImage/MorphologyImage/... entry points
+    (unmodified reference library, ld --wrap) served by the GPU and compared with the stock CPU path.
+    The harness is built where the reference tree exists and travels prebuilt to the GPU box."""
+    import subprocess
+    from pathlib import Path
+    exe = Path(util.ROOT) / "imagemagick_b200" / "lib" / "shim_harness"
+    if not exe.exists():
+        pytest.skip("shim harness not built (needs the reference headers)")
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    print(p.stdout)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "gpu hits" in p.stdout and "FAIL" not in p.stdout
