@@ -53,11 +53,10 @@ struct Conv1dArgs {
   unsigned long long *changed;
 };
 
-// 1/g to ~2^-46: single-precision MUFU.RCP seed + one FP64 Newton step (2 FP64-pipe ops).
+// 1/g to ~2^-40: MUFU.RCP64H seed (one XU op, ~20 bits) + one FP64 Newton step.
 __device__ __forceinline__ double fast_reciprocal(double g) {
-  float seed;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"(static_cast<float>(g)));
-  const double r0 = static_cast<double>(seed);
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(g));
   const double e = fma(-g, r0, 1.0);
   return fma(r0, e, r0);
 }
@@ -78,14 +77,16 @@ struct Finish {
 };
 
 // branch-free: out = (bias_eff + sum) * 1/den, den = blend ? gsum : 1, with the reference's
-// |gamma| < MagickEpsilon clamp applied to QS*gsum.
+// |gamma| < MagickEpsilon clamp (PerceptibleReciprocal == 1/clamp(gamma)) applied to QS*gsum by
+// comparing the high word of |den| against the threshold (exact up to the low 32 mantissa bits).
 __device__ __forceinline__ float finish(const Finish &f, double sum, double gsum) {
   const double pixel = f.bias_eff + sum;
-  const double den = f.blend ? gsum : 1.0;
-  double r = fast_reciprocal(den);
-  const double tiny = den < 0.0 ? -(kQuantumScale / kEpsilon) : (kQuantumScale / kEpsilon);
-  r = fabs(den) >= (kEpsilon / kQuantumScale) ? r : tiny;
-  return static_cast<float>(r * pixel);
+  double den = f.blend ? gsum : 1.0;
+  constexpr double kTiny = kEpsilon / kQuantumScale;           // 6.5535e-8
+  const int hi = __double2hiint(den);
+  if ((hi & 0x7fffffff) < __double2hiint(kTiny))
+    den = __hiloint2double((hi & 0x80000000) | __double2hiint(kTiny), __double2loint(kTiny));
+  return static_cast<float>(fast_reciprocal(den) * pixel);
 }
 
 template <int NT> struct Ring { static constexpr int value = NT; };
@@ -518,13 +519,13 @@ int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int nta
   } else if (axis == 1) {
     constexpr int kThreads = 128;
     constexpr int kMinBlocks = NT <= 33 ? 4 : 2;
-    a.strip = tuning("MB200_COL_ROT", 8) * NT + 1;   // strip + NT - 1 is a whole number of rotations
+    a.strip = tuning("MB200_COL_ROT", 16) * NT + 1;   // strip + NT - 1 is a whole number of rotations
     dim3 grid((a.rc + kThreads - 1) / kThreads, (a.height + a.strip - 1) / a.strip);
     conv_col_kernel<NT, MODE, kThreads, kMinBlocks><<<grid, kThreads, 0, stream>>>(a, taps);
   } else {
     constexpr int kMinBlocks = NT <= 33 ? 4 : 2;
     // strip + NT - 1 is a whole number of rotations and the strip is at least ~64 outputs
-    constexpr int kRot = (63 + NT - 1) / NT < 2 ? 2 : (63 + NT - 1) / NT;
+    constexpr int kRot = (63 + NT - 1) / NT < 3 ? 3 : (63 + NT - 1) / NT;
     a.strip = tuning("MB200_ROW_ROT", kRot) * NT + 1;
     a.seg_w = a.strip + NT - 1;
     a.pitch = a.seg_w | 1;
