@@ -132,14 +132,17 @@ __global__ void __launch_bounds__(THREADS, MINB) conv_col_kernel(const Conv1dArg
   ysrc += PF;                                  // next row to fetch
 
   int j = -(NT - 1);                           // output row (relative to y0) finished at this step
+  // The rotation is unrolled PF steps at a time (not NT): after each block the accumulators are
+  // physically rotated by PF slots, so the static tap pattern repeats and the loop body stays
+  // small enough for the instruction cache (NT*NT FMAs would not).
 #pragma unroll 1
-  for (int mb = 0; mb < total; mb += NT) {
+  for (int mb = 0; mb < total; mb += PF) {
 #pragma unroll
-    for (int s = 0; s < NT; ++s) {
-      float vf = pre[s % PF];
+    for (int s = 0; s < PF; ++s) {
+      float vf = pre[s];
       {  // refill this ring slot with the row PF steps ahead (edge-clamped)
         const unsigned yy = static_cast<unsigned>(min(max(ysrc, 0), hmax));
-        pre[s % PF] = __ldg(reinterpret_cast<const float *>(base + static_cast<size_t>(yy) * pitch_bytes));
+        pre[s] = __ldg(reinterpret_cast<const float *>(base + static_cast<size_t>(yy) * pitch_bytes));
         ++ysrc;
       }
       double v = static_cast<double>(vf);
@@ -159,6 +162,15 @@ __global__ void __launch_bounds__(THREADS, MINB) conv_col_kernel(const Conv1dArg
       if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<float *>(outp) = out;
       if (j >= 0) outp += pitch_bytes;
       ++j;
+    }
+    if (PF != NT) {                              // rotate: new acc[q] = old acc[(q + PF) % NT]
+      double tmp[PF];
+#pragma unroll
+      for (int q = 0; q < PF; ++q) tmp[q] = acc[q];
+#pragma unroll
+      for (int q = 0; q < NT - PF; ++q) acc[q] = acc[q + PF];
+#pragma unroll
+      for (int q = 0; q < PF; ++q) acc[NT - PF + q] = tmp[q];
     }
   }
 }
@@ -221,10 +233,11 @@ __global__ void __launch_bounds__(128, MINB) conv_row_kernel(const Conv1dArgs a,
   for (int q = 0; q < NT; ++q) acc[q] = 0.0;
 
   int j = -(NT - 1);
+  constexpr int BLK = Ring<NT>::value;         // unrolled steps per block; accumulators rotate by BLK after it
 #pragma unroll 1
-  for (int mb = 0; mb < total; mb += NT) {
+  for (int mb = 0; mb < total; mb += BLK) {
 #pragma unroll
-    for (int s = 0; s < NT; ++s) {
+    for (int s = 0; s < BLK; ++s) {
       const float vf = *tp;
       tp += ch;
       double v = static_cast<double>(vf);
@@ -244,6 +257,15 @@ __global__ void __launch_bounds__(128, MINB) conv_row_kernel(const Conv1dArgs a,
       if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *outp = out;
       if (j >= 0) outp += ch;
       ++j;
+    }
+    if (BLK != NT) {                             // rotate: new acc[q] = old acc[(q + BLK) % NT]
+      double tmp[BLK];
+#pragma unroll
+      for (int q = 0; q < BLK; ++q) tmp[q] = acc[q];
+#pragma unroll
+      for (int q = 0; q < NT - BLK; ++q) acc[q] = acc[q + BLK];
+#pragma unroll
+      for (int q = 0; q < BLK; ++q) acc[NT - BLK + q] = tmp[q];
     }
   }
 }
@@ -491,6 +513,214 @@ __global__ void __launch_bounds__(128, MINB) conv_row_tma_kernel(const Conv1dArg
   }
 }
 
+// ======================================================================================
+// Two-components-per-thread kernels for RGBA ("pair" kernels, the default for 4 channels).
+// A thread owns two adjacent components of a pixel -- (R,G) on even lanes, (B,A) on odd lanes --
+// and therefore two independent rotations of NT accumulators.  Per pair of outputs this halves the
+// per-step overhead the single-component kernels pay (one 64-bit load/store, one alpha shuffle,
+// one reciprocal, three instead of four conversions), which matters because every half-rate
+// FP64 / quarter-rate conversion instruction costs issue time (tools/micro/mix.cu).
+// ======================================================================================
+
+// Output stage of a pair: r = 1/clamp(den) (PerceptibleReciprocal on QS*den, morphology.c:3197),
+// colour components are scaled by r, the alpha component (odd lane, .y) is stored unscaled.
+__device__ __forceinline__ float2 finish_pair(bool odd, double sum0, double sum1, double gsum) {
+  constexpr double kTiny = kEpsilon / kQuantumScale;
+  double den = gsum;
+  const int hi = __double2hiint(den);
+  if ((hi & 0x7fffffff) < __double2hiint(kTiny))
+    den = __hiloint2double((hi & 0x80000000) | __double2hiint(kTiny), __double2loint(kTiny));
+  const double r = fast_reciprocal(den);
+  const double m1 = odd ? 1.0 : r;
+  return make_float2(static_cast<float>(sum0 * r), static_cast<float>(sum1 * m1));
+}
+
+// ---- column pass: CTA = 128 threads = 256 consecutive components (64 RGBA pixels, 1 KB/row)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(128, MINB) conv_col_pair_kernel(const Conv1dArgs a, const Taps<NT> taps) {
+  constexpr int PF = Ring<NT>::value;
+  const int pair_raw = blockIdx.x * 128 + threadIdx.x;          // index of the float2 within the row
+  const int npairs = a.rc >> 1;
+  const bool active = pair_raw < npairs;
+  const int pair = active ? pair_raw : npairs - 1;
+  const int lane = threadIdx.x & 31;
+  const bool odd = (pair & 1) != 0;
+  const int alpha_lane = lane | 1;
+  const int y0 = blockIdx.y * a.strip;
+  const int nout = active ? min(a.strip, a.height - y0) : 0;
+  const int total = a.strip + NT - 1;
+  const int hmax = a.height - 1;
+  const unsigned pitch_bytes = static_cast<unsigned>(a.rc) * 4u;
+  const char *base = reinterpret_cast<const char *>(a.src) + static_cast<size_t>(pair) * 8;
+  char *outp = reinterpret_cast<char *>(a.dst) + static_cast<size_t>(pair) * 8 + static_cast<size_t>(y0) * pitch_bytes;
+
+  double acc0[NT], acc1[NT];
+  float2 pre[PF];
+#pragma unroll
+  for (int q = 0; q < NT; ++q) { acc0[q] = 0.0; acc1[q] = 0.0; }
+  int ysrc = y0 - a.off;
+#pragma unroll
+  for (int s = 0; s < PF; ++s) {
+    const unsigned yy = static_cast<unsigned>(min(max(ysrc + s, 0), hmax));
+    pre[s] = __ldg(reinterpret_cast<const float2 *>(base + static_cast<size_t>(yy) * pitch_bytes));
+  }
+  ysrc += PF;
+
+  int j = -(NT - 1);
+#pragma unroll 1
+  for (int mb = 0; mb < total; mb += PF) {       // PF unrolled steps, then rotate the accumulators by PF
+#pragma unroll
+    for (int s = 0; s < PF; ++s) {
+      const float2 vf = pre[s];
+      {
+        const unsigned yy = static_cast<unsigned>(min(max(ysrc, 0), hmax));
+        pre[s] = __ldg(reinterpret_cast<const float2 *>(base + static_cast<size_t>(yy) * pitch_bytes));
+        ++ysrc;
+      }
+      const float af = __shfl_sync(0xffffffffu, vf.y, alpha_lane);
+      const double da = static_cast<double>(af);
+      const double v0 = static_cast<double>(vf.x) * da;
+      const double v1 = static_cast<double>(vf.y) * (odd ? 1.0 : da);
+#pragma unroll
+      for (int q = 0; q < NT; ++q) {
+        const double k = taps.k[(s - q + NT) % NT];
+        acc0[q] = fma(k, v0, acc0[q]);
+        acc1[q] = fma(k, v1, acc1[q]);
+      }
+      const int qf = (s + 1) % NT;
+      const double sum0 = acc0[qf], sum1 = acc1[qf];
+      acc0[qf] = 0.0;
+      acc1[qf] = 0.0;
+      const double gsum = shfl_double(sum1, alpha_lane);
+      const float2 out = finish_pair(odd, sum0, sum1, gsum);
+      if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<float2 *>(outp) = out;
+      if (j >= 0) outp += pitch_bytes;
+      ++j;
+    }
+    if (PF != NT) {
+      double t0[PF], t1[PF];
+#pragma unroll
+      for (int q = 0; q < PF; ++q) { t0[q] = acc0[q]; t1[q] = acc1[q]; }
+#pragma unroll
+      for (int q = 0; q < NT - PF; ++q) { acc0[q] = acc0[q + PF]; acc1[q] = acc1[q + PF]; }
+#pragma unroll
+      for (int q = 0; q < PF; ++q) { acc0[NT - PF + q] = t0[q]; acc1[NT - PF + q] = t1[q]; }
+    }
+  }
+}
+
+// ---- row pass: CTA = 4 independent warps; a warp covers 16 rows x 2 component pairs; every warp
+//      streams its rows through a private cp.async.bulk ring (chunk = PF pixels per row, odd
+//      pixel pitch => conflict-free LDS.64), so strips can be long and no block barrier is needed.
+//      grid: (ceil(width/strip), ceil(height/64)).
+template <int PF>
+__device__ __forceinline__ void row_pair_issue(float *slot_base, unsigned long long *bar, const float4 *src, int ybase,
+                                               int hmax, int xs, int width, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_expect_tx(bar, 16u * PF * 16u);
+  __syncwarp();
+  if (lane < 16) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const float4 *grow = src + static_cast<size_t>(min(ybase + lane, hmax)) * width;
+    float *dst = slot_base + lane * (PF * 4);
+    const int lo = max(xs, 0), hi = min(xs + PF, width);
+    if (hi > lo) bulk_g2s(dst + (lo - xs) * 4, grow + lo, static_cast<unsigned>(hi - lo) * 16u, bar);
+#pragma unroll 1
+    for (int x = xs; x < min(xs + PF, 0); ++x) bulk_g2s(dst + (x - xs) * 4, grow, 16u, bar);
+#pragma unroll 1
+    for (int x = max(xs, width); x < xs + PF; ++x) bulk_g2s(dst + (x - xs) * 4, grow + (width - 1), 16u, bar);
+  }
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(128, MINB) conv_row_pair_kernel(const Conv1dArgs a, const Taps<NT> taps) {
+  constexpr int PF = Ring<NT>::value;
+  constexpr int kSlots = (PF > 11) ? 2 : 4;       // static shared memory stays below 48 KB
+  static_assert(PF % 2 == 1, "odd chunk pitch keeps the LDS conflict-free");
+  __shared__ __align__(128) float ring[4][kSlots][16][PF * 4];
+  __shared__ __align__(8) unsigned long long full[4][kSlots];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ybase = blockIdx.y * 64 + warp * 16;
+  if (ybase >= a.height) return;
+  const int lr = lane >> 1;
+  const bool odd = (lane & 1) != 0;
+  const int alpha_lane = lane | 1;
+  const int x0 = blockIdx.x * a.strip;
+  const int y = ybase + lr;
+  const int hmax = a.height - 1;
+  const int nout = y < a.height ? min(a.strip, a.width - x0) : 0;
+  const int total = a.strip + NT - 1;
+  const int nchunks = total / PF;
+  float *outp = a.dst + (static_cast<size_t>(min(y, hmax)) * a.width + x0) * 4 + (odd ? 2 : 0);
+  unsigned long long *bars = &full[warp][0];
+  float *wring = &ring[warp][0][0][0];
+  const float4 *src4 = reinterpret_cast<const float4 *>(a.src);
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int xsrc0 = x0 - a.off;
+  for (int ck = 0; ck < kSlots - 1 && ck < nchunks; ++ck)
+    row_pair_issue<PF>(wring + ck * (16 * PF * 4), &bars[ck], src4, ybase, hmax, xsrc0 + ck * PF, a.width, lane);
+
+  double acc0[NT], acc1[NT];
+#pragma unroll
+  for (int q = 0; q < NT; ++q) { acc0[q] = 0.0; acc1[q] = 0.0; }
+  int j = -(NT - 1);
+  int chunk = 0, slot = 0, nslot = kSlots - 1;
+  unsigned parity = 0;
+#pragma unroll 1
+  for (int mb = 0; mb < total; mb += PF) {       // one ring chunk == one unrolled block
+    {
+      const int nxt = chunk + kSlots - 1;
+      if (nxt < nchunks)
+        row_pair_issue<PF>(wring + nslot * (16 * PF * 4), &bars[nslot], src4, ybase, hmax, xsrc0 + nxt * PF, a.width,
+                           lane);
+      mbar_wait(&bars[slot], parity);
+    }
+    const float *cp = wring + ((slot * 16 + lr) * PF) * 4;
+#pragma unroll
+    for (int s = 0; s < PF; ++s) {
+      const float *pp = cp + s * 4;
+      const float2 vf = *reinterpret_cast<const float2 *>(pp + (odd ? 2 : 0));
+      const float af = pp[3];
+      const double da = static_cast<double>(af);
+      const double v0 = static_cast<double>(vf.x) * da;
+      const double v1 = static_cast<double>(vf.y) * (odd ? 1.0 : da);
+#pragma unroll
+      for (int q = 0; q < NT; ++q) {
+        const double k = taps.k[(s - q + NT) % NT];
+        acc0[q] = fma(k, v0, acc0[q]);
+        acc1[q] = fma(k, v1, acc1[q]);
+      }
+      const int qf = (s + 1) % NT;
+      const double sum0 = acc0[qf], sum1 = acc1[qf];
+      acc0[qf] = 0.0;
+      acc1[qf] = 0.0;
+      const double gsum = shfl_double(sum1, alpha_lane);
+      const float2 out = finish_pair(odd, sum0, sum1, gsum);
+      if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<float2 *>(outp) = out;
+      if (j >= 0) outp += 4;
+      ++j;
+    }
+    ++chunk;
+    nslot = slot;
+    if (++slot == kSlots) { slot = 0; parity ^= 1u; }
+    if (PF != NT) {
+      double t0[PF], t1[PF];
+#pragma unroll
+      for (int q = 0; q < PF; ++q) { t0[q] = acc0[q]; t1[q] = acc1[q]; }
+#pragma unroll
+      for (int q = 0; q < NT - PF; ++q) { acc0[q] = acc0[q + PF]; acc1[q] = acc1[q + PF]; }
+#pragma unroll
+      for (int q = 0; q < PF; ++q) { acc0[NT - PF + q] = t0[q]; acc1[NT - PF + q] = t1[q]; }
+    }
+  }
+}
+
 // developer tuning knobs (environment, read on every launch; defaults are the tuned values)
 int tuning(const char *name, int fallback) {
   const char *v = getenv(name);
@@ -504,7 +734,21 @@ int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int nta
   Conv1dArgs a = base;
   const bool tma_ok = MODE == 4 && a.bias == 0.0 && tuning("MB200_TMA", 0) != 0 && (a.rc % 32) == 0 &&
                       ((reinterpret_cast<uintptr_t>(a.src) | reinterpret_cast<uintptr_t>(a.dst)) & 15) == 0;
-  if (tma_ok && axis == 1) {
+  const bool pair_ok = MODE == 4 && a.bias == 0.0 && NT <= 33 && tuning("MB200_PAIR", 1) != 0 &&
+                       ((reinterpret_cast<uintptr_t>(a.src) | reinterpret_cast<uintptr_t>(a.dst)) & 15) == 0;
+  if (pair_ok && axis == 1) {
+    if constexpr (NT <= 33) {
+      a.strip = tuning("MB200_COL_ROT", 16) * NT + 1;
+      dim3 grid((a.rc / 2 + 127) / 128, (a.height + a.strip - 1) / a.strip);
+      conv_col_pair_kernel<NT, 2><<<grid, 128, 0, stream>>>(a, taps);
+    }
+  } else if (pair_ok && axis == 0) {
+    if constexpr (NT <= 33) {
+      a.strip = tuning("MB200_ROW_PAIR_ROT", 8) * NT + 1;
+      dim3 grid((a.width + a.strip - 1) / a.strip, (a.height + 63) / 64);
+      conv_row_pair_kernel<NT, 2><<<grid, 128, 0, stream>>>(a, taps);
+    }
+  } else if (tma_ok && axis == 1) {
     constexpr int kMinBlocks = NT <= 33 ? 4 : 2;
     a.strip = tuning("MB200_COL_ROT", 8) * NT + 1;
     dim3 grid((a.rc + 127) / 128, (a.height + a.strip - 1) / a.strip);

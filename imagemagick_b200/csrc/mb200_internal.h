@@ -46,7 +46,8 @@ int launch_morph2d(const float *src, float *dst, size_t width, size_t height, in
 // resize.cu: one axis of ResizeImage.  Contribution table lives in device memory.
 int launch_resize_axis(const float *src, size_t width, size_t height, int channels, float *dst,
                        size_t out_n, int axis, const int *d_start, const int *d_count,
-                       const double *d_weights, int max_taps, int max_span, void *stream);
+                       const double *d_weights, int max_taps, int max_span, int reg_stride, int reg_taps,
+                       const double *d_wreg, void *stream);
 
 // colorspace.cu
 int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to, void *stream);
