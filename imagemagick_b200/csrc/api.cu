@@ -102,6 +102,10 @@ int primitive(const float *src, float *dst, size_t w, size_t h, int ch, int meth
                                  bias, 1.0, d_counter, s);
     if (rc != MB200_EUNSUPPORTED) return rc;
   }
+  if (method == MB200_ErodeMorphology || method == MB200_DilateMorphology) {
+    const int rc = launch_morph_flat(src, dst, w, h, ch, method, win.data(), kw, kh, ox, oy, d_counter, s);
+    if (rc != MB200_EUNSUPPORTED) return rc;
+  }
   double gamma_scale = 1.0;
   if (method == MB200_ConvolveMorphology && kw == 1) {
     size_t count = 0;

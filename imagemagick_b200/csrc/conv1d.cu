@@ -535,36 +535,61 @@ __device__ __forceinline__ float2 finish_pair(bool odd, double sum0, double sum1
   return make_float2(static_cast<float>(sum0 * r), static_cast<float>(sum1 * m1));
 }
 
-// ---- column pass: CTA = 128 threads = 256 consecutive components (64 RGBA pixels, 1 KB/row)
-template <int NT, int MINB>
-__global__ void __launch_bounds__(128, MINB) conv_col_pair_kernel(const Conv1dArgs a, const Taps<NT> taps) {
+// ---- pair stream kernel, both axes.  A thread owns one component pair and walks along the
+//      filter axis with a register ring of PF samples in flight.
+//      AXIS 1 (column pass): CTA = 128 threads = 256 consecutive components of a row (1 KB, fully
+//        coalesced); step = one row.          grid (ceil(rc/256), ceil(height/strip))
+//      AXIS 0 (row pass):    CTA = 128 threads = 64 rows x 2 pairs; step = one pixel (16 B); a
+//        lane pair reads the 16 B of its pixel, consecutive steps of a lane fall in the same 128-B
+//        line (L1-resident), so no shared-memory staging or barrier is needed.
+//                                              grid (ceil(width/strip), ceil(height/64))
+template <int NT, int MINB, int AXIS>
+__global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a, const Taps<NT> taps) {
   constexpr int PF = Ring<NT>::value;
-  const int pair_raw = blockIdx.x * 128 + threadIdx.x;          // index of the float2 within the row
-  const int npairs = a.rc >> 1;
-  const bool active = pair_raw < npairs;
-  const int pair = active ? pair_raw : npairs - 1;
   const int lane = threadIdx.x & 31;
-  const bool odd = (pair & 1) != 0;
+  const bool odd = (threadIdx.x & 1) != 0;
   const int alpha_lane = lane | 1;
-  const int y0 = blockIdx.y * a.strip;
-  const int nout = active ? min(a.strip, a.height - y0) : 0;
-  const int total = a.strip + NT - 1;
-  const int hmax = a.height - 1;
   const unsigned pitch_bytes = static_cast<unsigned>(a.rc) * 4u;
-  const char *base = reinterpret_cast<const char *>(a.src) + static_cast<size_t>(pair) * 8;
-  char *outp = reinterpret_cast<char *>(a.dst) + static_cast<size_t>(pair) * 8 + static_cast<size_t>(y0) * pitch_bytes;
+  int first, nout, limit;                 // first output / number of outputs / clamp limit along the axis
+  const char *base;                       // address of sample 0 of this thread's line
+  char *outp;
+  unsigned step;                          // bytes between consecutive samples
+  if (AXIS == 1) {
+    const int npairs = a.rc >> 1;
+    const int pair_raw = blockIdx.x * 128 + threadIdx.x;
+    const bool active = pair_raw < npairs;
+    const int pair = active ? pair_raw : npairs - 1;
+    first = blockIdx.y * a.strip;
+    nout = active ? min(a.strip, a.height - first) : 0;
+    limit = a.height - 1;
+    step = pitch_bytes;
+    base = reinterpret_cast<const char *>(a.src) + static_cast<size_t>(pair) * 8;
+    outp = reinterpret_cast<char *>(a.dst) + static_cast<size_t>(pair) * 8 + static_cast<size_t>(first) * pitch_bytes;
+  } else {
+    const int row_raw = blockIdx.y * 64 + (threadIdx.x >> 1);
+    const bool active = row_raw < a.height;
+    const int row = active ? row_raw : a.height - 1;
+    first = blockIdx.x * a.strip;
+    nout = active ? min(a.strip, a.width - first) : 0;
+    limit = a.width - 1;
+    step = 16u;
+    base = reinterpret_cast<const char *>(a.src) + static_cast<size_t>(row) * pitch_bytes + (odd ? 8 : 0);
+    outp = reinterpret_cast<char *>(a.dst) + static_cast<size_t>(row) * pitch_bytes + (odd ? 8 : 0) +
+           static_cast<size_t>(first) * 16u;
+  }
+  const int total = a.strip + NT - 1;
 
   double acc0[NT], acc1[NT];
   float2 pre[PF];
 #pragma unroll
   for (int q = 0; q < NT; ++q) { acc0[q] = 0.0; acc1[q] = 0.0; }
-  int ysrc = y0 - a.off;
+  int isrc = first - a.off;                 // source index of step 0
 #pragma unroll
   for (int s = 0; s < PF; ++s) {
-    const unsigned yy = static_cast<unsigned>(min(max(ysrc + s, 0), hmax));
-    pre[s] = __ldg(reinterpret_cast<const float2 *>(base + static_cast<size_t>(yy) * pitch_bytes));
+    const unsigned ii = static_cast<unsigned>(min(max(isrc + s, 0), limit));
+    pre[s] = __ldg(reinterpret_cast<const float2 *>(base + static_cast<size_t>(ii) * step));
   }
-  ysrc += PF;
+  isrc += PF;
 
   int j = -(NT - 1);
 #pragma unroll 1
@@ -573,9 +598,9 @@ __global__ void __launch_bounds__(128, MINB) conv_col_pair_kernel(const Conv1dAr
     for (int s = 0; s < PF; ++s) {
       const float2 vf = pre[s];
       {
-        const unsigned yy = static_cast<unsigned>(min(max(ysrc, 0), hmax));
-        pre[s] = __ldg(reinterpret_cast<const float2 *>(base + static_cast<size_t>(yy) * pitch_bytes));
-        ++ysrc;
+        const unsigned ii = static_cast<unsigned>(min(max(isrc, 0), limit));
+        pre[s] = __ldg(reinterpret_cast<const float2 *>(base + static_cast<size_t>(ii) * step));
+        ++isrc;
       }
       const float af = __shfl_sync(0xffffffffu, vf.y, alpha_lane);
       const double da = static_cast<double>(af);
@@ -594,7 +619,7 @@ __global__ void __launch_bounds__(128, MINB) conv_col_pair_kernel(const Conv1dAr
       const double gsum = shfl_double(sum1, alpha_lane);
       const float2 out = finish_pair(odd, sum0, sum1, gsum);
       if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<float2 *>(outp) = out;
-      if (j >= 0) outp += pitch_bytes;
+      if (j >= 0) outp += step;
       ++j;
     }
     if (PF != NT) {
@@ -740,13 +765,14 @@ int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int nta
     if constexpr (NT <= 33) {
       a.strip = tuning("MB200_COL_ROT", 16) * NT + 1;
       dim3 grid((a.rc / 2 + 127) / 128, (a.height + a.strip - 1) / a.strip);
-      conv_col_pair_kernel<NT, 2><<<grid, 128, 0, stream>>>(a, taps);
+      conv_pair_kernel<NT, 2, 1><<<grid, 128, 0, stream>>>(a, taps);
     }
   } else if (pair_ok && axis == 0) {
     if constexpr (NT <= 33) {
-      a.strip = tuning("MB200_ROW_PAIR_ROT", 8) * NT + 1;
+      a.strip = tuning("MB200_ROW_PAIR_ROT", 16) * NT + 1;
       dim3 grid((a.width + a.strip - 1) / a.strip, (a.height + 63) / 64);
-      conv_row_pair_kernel<NT, 2><<<grid, 128, 0, stream>>>(a, taps);
+      if (tuning("MB200_ROW_PAIR_TMA", 0)) conv_row_pair_kernel<NT, 2><<<grid, 128, 0, stream>>>(a, taps);
+      else conv_pair_kernel<NT, 2, 0><<<grid, 128, 0, stream>>>(a, taps);
     }
   } else if (tma_ok && axis == 1) {
     constexpr int kMinBlocks = NT <= 33 ? 4 : 2;

@@ -43,6 +43,11 @@ int launch_morph2d(const float *src, float *dst, size_t width, size_t height, in
                    int method, const double *kernel_window_order, int kw, int kh, int ox, int oy,
                    double bias, double gamma_scale, unsigned long long *d_changed, void *stream);
 
+// morph_flat.cu: erode / dilate by run decomposition (MB200_EUNSUPPORTED => use launch_morph2d)
+int launch_morph_flat(const float *src, float *dst, size_t width, size_t height, int channels,
+                      int method, const double *kernel_window_order, int kw, int kh, int ox, int oy,
+                      unsigned long long *d_changed, void *stream);
+
 // resize.cu: one axis of ResizeImage.  Contribution table lives in device memory.
 int launch_resize_axis(const float *src, size_t width, size_t height, int channels, float *dst,
                        size_t out_n, int axis, const int *d_start, const int *d_count,
