@@ -102,7 +102,8 @@ int primitive(const float *src, float *dst, size_t w, size_t h, int ch, int meth
                                  bias, 1.0, d_counter, s);
     if (rc != MB200_EUNSUPPORTED) return rc;
   }
-  if (method == MB200_ErodeMorphology || method == MB200_DilateMorphology) {
+  if ((method == MB200_ErodeMorphology || method == MB200_DilateMorphology) &&
+      std::getenv("MB200_MORPH_FLAT") != nullptr) {          // run-decomposition variant: opt-in (r01: not faster yet)
     const int rc = launch_morph_flat(src, dst, w, h, ch, method, win.data(), kw, kh, ox, oy, d_counter, s);
     if (rc != MB200_EUNSUPPORTED) return rc;
   }

@@ -134,6 +134,107 @@ __global__ void __launch_bounds__(kTileW *kTileH) morph2d_kernel(const Morph2dAr
   if (a.changed != nullptr && nchanged != 0) atomicAdd(a.changed, static_cast<unsigned long long>(nchanged));
 }
 
+// Erode / dilate, tight version: CTA = 32x8 threads, each thread produces 4 output rows (y, y+8,
+// y+16, y+24) of one column, so every active-cell offset (one broadcast LDS) is amortised over four
+// LDS.128 + min/max groups.  fminf/fmaxf compile to FMNMX(3); a NaN sample never replaces the value.
+constexpr int kMmTile = 32, kMmRows = 4;
+constexpr int kMmPitch = 64;          // fixed shared-memory pitch in pixels (kernel width <= 33)
+
+template <int CH, bool DILATE>
+__global__ void __launch_bounds__(256, 4) minmax2d_kernel(const Morph2dArgs a) {
+  extern __shared__ __align__(16) float tile[];
+  __shared__ int s_off[1024];
+  const int tw = kMmTile + a.kw - 1, th = kMmTile + a.kh - 1;
+  const int bx = blockIdx.x * kMmTile, by = blockIdx.y * kMmTile;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int wmax = a.width - 1, hmax = a.height - 1;
+  const int ncells = min(a.ncells, 1024);
+  for (int i = tid; i < ncells; i += 256) s_off[i] = (a.cells[i].dv * kMmPitch + a.cells[i].du) * CH;
+  // stage th rows x tw pixels: 64 threads per row, 4 rows per pass
+  for (int ty = tid >> 6; ty < th; ty += 4) {
+    const int tx = tid & 63;
+    if (tx < tw) {
+      const int sx = min(max(bx - a.ox + tx, 0), wmax);
+      const int sy = min(max(by - a.oy + ty, 0), hmax);
+      const float *g = a.src + (static_cast<size_t>(sy) * a.width + sx) * CH;
+      float *d = tile + static_cast<size_t>(ty * kMmPitch + tx) * CH;
+      if (CH == 4) *reinterpret_cast<float4 *>(d) = __ldg(reinterpret_cast<const float4 *>(g));
+      else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) d[c] = __ldg(g + c);
+      }
+    }
+  }
+  __syncthreads();
+  const int x = bx + threadIdx.x;
+  const float *base = tile + (threadIdx.y * kMmPitch + threadIdx.x) * CH;   // window top-left of row 0
+  constexpr int kRowStride = 8 * kMmPitch * CH;                             // rows handled: ty, ty+8, ...
+  const int coff = (a.oy * kMmPitch + a.ox) * CH;
+  float acc[kMmRows][CH], ctr[kMmRows][CH];
+#pragma unroll
+  for (int r = 0; r < kMmRows; ++r)
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      ctr[r][c] = base[r * kRowStride + coff + c];
+      acc[r][c] = DILATE ? 0.0f : ctr[r][c];
+    }
+  auto fold = [&](const float *p) {
+#pragma unroll
+    for (int r = 0; r < kMmRows; ++r) {
+      float v[CH];
+      if (CH == 4) { const float4 t = *reinterpret_cast<const float4 *>(p + r * kRowStride); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[CH - 1] = t.w; }
+      else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) v[c] = p[r * kRowStride + c];
+      }
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[r][c] = DILATE ? fmaxf(acc[r][c], v[c]) : fminf(acc[r][c], v[c]);
+    }
+  };
+  int i = 0;
+  for (; i + 1 < ncells; i += 2) {          // two cells per trip: lets the compiler form 3-input min/max
+    const float *p0 = base + s_off[i], *p1 = base + s_off[i + 1];
+#pragma unroll
+    for (int r = 0; r < kMmRows; ++r) {
+      float v0[CH], v1[CH];
+      if (CH == 4) {
+        const float4 t0 = *reinterpret_cast<const float4 *>(p0 + r * kRowStride);
+        const float4 t1 = *reinterpret_cast<const float4 *>(p1 + r * kRowStride);
+        v0[0] = t0.x; v0[1] = t0.y; v0[2] = t0.z; v0[CH - 1] = t0.w;
+        v1[0] = t1.x; v1[1] = t1.y; v1[2] = t1.z; v1[CH - 1] = t1.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) { v0[c] = p0[r * kRowStride + c]; v1[c] = p1[r * kRowStride + c]; }
+      }
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        acc[r][c] = DILATE ? fmaxf(fmaxf(acc[r][c], v0[c]), v1[c]) : fminf(fminf(acc[r][c], v0[c]), v1[c]);
+    }
+  }
+  if (i < ncells) fold(base + s_off[i]);
+  unsigned nchanged = 0;
+  if (x < a.width) {
+#pragma unroll
+    for (int r = 0; r < kMmRows; ++r) {
+      const int y = by + threadIdx.y + 8 * r;
+      if (y < a.height) {
+        float *o = a.dst + (static_cast<size_t>(y) * a.width + x) * CH;
+        if (CH == 4) *reinterpret_cast<float4 *>(o) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][CH - 1]);
+        else {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) o[c] = acc[r][c];
+        }
+        if (a.changed != nullptr) {
+#pragma unroll
+          for (int c = 0; c < CH; ++c)
+            nchanged += fabs(static_cast<double>(acc[r][c]) - static_cast<double>(ctr[r][c])) >= kEpsilon;
+        }
+      }
+    }
+  }
+  if (a.changed != nullptr && nchanged != 0) atomicAdd(a.changed, static_cast<unsigned long long>(nchanged));
+}
+
 }  // namespace
 
 int launch_morph2d(const float *src, float *dst, size_t width, size_t height, int channels, int method,
@@ -170,6 +271,36 @@ int launch_morph2d(const float *src, float *dst, size_t width, size_t height, in
   a.ox = ox; a.oy = oy; a.kw = kw; a.kh = kh; a.ncells = n;
   a.cells = static_cast<const Cell *>(d_cells);
   a.bias = bias; a.gamma_scale = gamma_scale; a.method = method; a.changed = d_changed;
+  if (method != MB200_ConvolveMorphology && n <= 1024 && kw <= kMmPitch - kMmTile + 1) {
+    const int th = kMmTile + kh - 1;
+    const size_t msmem = static_cast<size_t>(kMmPitch) * th * channels * sizeof(float);
+    if (msmem <= 160 * 1024) {
+      dim3 mgrid((a.width + kMmTile - 1) / kMmTile, (a.height + kMmTile - 1) / kMmTile), mblock(32, 8);
+      const bool dil = method == MB200_DilateMorphology;
+#define MB200_MM(CH)                                                                                   \
+      do {                                                                                             \
+        if (dil) {                                                                                     \
+          cudaFuncSetAttribute(minmax2d_kernel<CH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);  \
+          minmax2d_kernel<CH, true><<<mgrid, mblock, msmem, s>>>(a);                            \
+        } else {                                                                                       \
+          cudaFuncSetAttribute(minmax2d_kernel<CH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+          minmax2d_kernel<CH, false><<<mgrid, mblock, msmem, s>>>(a);                           \
+        }                                                                                              \
+      } while (0)
+      switch (channels) {
+        case 1: MB200_MM(1); break;
+        case 2: MB200_MM(2); break;
+        case 3: MB200_MM(3); break;
+        default: MB200_MM(4); break;
+      }
+#undef MB200_MM
+      count_launch();
+      e = cudaGetLastError();
+      cudaFreeAsync(d_cells, s);
+      if (e != cudaSuccess) return cuda_fail(e, "minmax2d launch");
+      return MB200_OK;
+    }
+  }
   const size_t smem = static_cast<size_t>(kTileW + kw - 1) * (kTileH + kh - 1) * channels * sizeof(float);
   if (smem > 200 * 1024) { cudaFreeAsync(d_cells, s); return fail(MB200_EUNSUPPORTED, "morph2d: %dx%d kernel needs %zu bytes of shared memory", kw, kh, smem); }
   dim3 grid((a.width + kTileW - 1) / kTileW, (a.height + kTileH - 1) / kTileH), block(kTileW, kTileH);
