@@ -102,6 +102,41 @@ int primitive(const float *src, float *dst, size_t w, size_t h, int ch, int meth
                                  bias, 1.0, d_counter, s);
     if (rc != MB200_EUNSUPPORTED) return rc;
   }
+  if (method == MB200_ConvolveMorphology && !has_nan && kw > 1 && kh > 1 && kw <= 33 && kh <= 33 && ch == 4 &&
+      bias == 0.0 && d_counter == nullptr && std::getenv("MB200_NO_RANK1") == nullptr) {
+    // Rank-1 kernels with non-negative taps ("gaussian:RxS", "binomial", "square" ...): K[v][u] = a[v] * b[u]
+    // to 1e-14, so the kw*kh-tap sum is evaluated as a row pass that keeps RAW double sums and a column
+    // pass that normalises -- same double accumulation as MorphologyPrimitive's inner loop
+    // (morphology.c:2837-2871) without the float rounding a two-kernel list would add between passes.
+    size_t pivot = 0;
+    bool nonneg = true;
+    for (size_t i = 0; i < n; ++i) {
+      if (win[i] < 0.0) nonneg = false;
+      if (win[i] > win[pivot]) pivot = i;
+    }
+    if (nonneg && win[pivot] > 0.0) {
+      const int pv = static_cast<int>(pivot) / kw, pu = static_cast<int>(pivot) % kw;
+      std::vector<double> colf(kh), rowf(kw);
+      for (int v = 0; v < kh; ++v) colf[v] = win[static_cast<size_t>(v) * kw + pu];
+      for (int u = 0; u < kw; ++u) rowf[u] = win[static_cast<size_t>(pv) * kw + u] / win[pivot];
+      bool rank1 = true;
+      for (int v = 0; v < kh && rank1; ++v)
+        for (int u = 0; u < kw; ++u)
+          if (std::fabs(win[static_cast<size_t>(v) * kw + u] - colf[v] * rowf[u]) > 1.0e-14 * win[pivot]) { rank1 = false; break; }
+      if (rank1) {
+        StreamAlloc sums(s);
+        int rc = sums.alloc(w * h * 4 * sizeof(double));
+        if (rc == MB200_OK) {
+          rc = launch_conv1d(src, static_cast<float *>(sums.ptr), w, h, ch, 0, rowf.data(), kw, ox, 0.0, 1.0, nullptr, s, 1);
+          if (rc == MB200_OK)
+            rc = launch_conv1d(static_cast<const float *>(sums.ptr), dst, w, h, ch, 1, colf.data(), kh, oy, 0.0, 1.0,
+                               nullptr, s, 2);
+          if (rc != MB200_EUNSUPPORTED) return rc;
+        }
+        // allocation failure / unsupported geometry: fall through to the direct 2-D kernel
+      }
+    }
+  }
   if ((method == MB200_ErodeMorphology || method == MB200_DilateMorphology) &&
       std::getenv("MB200_MORPH_FLAT") != nullptr) {          // run-decomposition variant: opt-in (r01: not faster yet)
     const int rc = launch_morph_flat(src, dst, w, h, ch, method, win.data(), kw, kh, ox, oy, d_counter, s);

@@ -24,6 +24,21 @@ namespace {
 constexpr double QR = 65535.0;
 constexpr double QS = 1.0 / 65535.0;
 
+__constant__ double kDecodeCf[9] = {1.7917488588043277509, 0.82045614371976854984, 0.027694100686325412819,
+                                    -0.00094244335181762134018, 0.000064355540911469709545,
+                                    -5.7224404636060757485e-06, 5.8767669437311184313e-07,
+                                    -6.6139920053589721168e-08, 7.9323242696227458163e-09};
+__constant__ double kDecodeP2[5] = {1.0, 2.6390158215457883983, 6.9644045063689921093, 1.8379173679952558018e+01,
+                                    4.8502930128332728543e+01};
+__constant__ double kEncodeCf[9] = {1.1758200232996901923, 0.16665763094889061230, -0.0083154894939042125035,
+                                    0.00075187976780420279038, -0.000083240178519391795367,
+                                    0.000010229209410070008679, -1.3400466409860246e-06,
+                                    1.8333422241635376682e-07, -2.5878596761348859722e-08};
+__constant__ double kEncodeP2[12] = {1.0, 1.3348398541700343678, 1.7817974362806785482, 2.3784142300054420538,
+                                     3.1748021039363991669, 4.2378523774371812394, 5.6568542494923805819,
+                                     7.5509945014535482244, 1.0079368399158985525e1, 1.3454342644059433809e1,
+                                     1.7959392772949968275e1, 2.3972913230026907883e1};
+
 __device__ __forceinline__ double cheb9(const double *cf, double t1) {
   // term[i] = 2*t1*term[i-1] - term[i-2]; p = sum cf[i]*term[i] (left to right, pixel.c:299-309)
   double tm2 = 1.0, tm1 = t1;
@@ -37,34 +52,36 @@ __device__ __forceinline__ double cheb9(const double *cf, double t1) {
   return p;
 }
 
-__device__ double decode_gamma(double x) {            // pixel.c:260-316
-  const double cf[9] = {1.7917488588043277509, 0.82045614371976854984, 0.027694100686325412819,
-                        -0.00094244335181762134018, 0.000064355540911469709545, -5.7224404636060757485e-06,
-                        5.8767669437311184313e-07, -6.6139920053589721168e-08, 7.9323242696227458163e-09};
-  const double p2[5] = {1.0, 2.6390158215457883983, 6.9644045063689921093, 1.8379173679952558018e+01,
-                        4.8502930128332728543e+01};
-  int e;
-  const double mant = frexp(x, &e);
-  const double p = cheb9(cf, 4.0 * mant - 3.0);
-  int quot = (e - 1) / 5, rem = (e - 1) % 5;
-  if (rem < 0) { quot -= 1; rem += 5; }
-  return x * ldexp(p2[rem] * p, 7 * quot);
+// frexp / ldexp for positive normal doubles (the only arguments the gamma curves see above their
+// linear toe): pure exponent-field arithmetic on the high word.
+__device__ __forceinline__ double frexp_normal(double x, int *e) {
+  const int hi = __double2hiint(x);
+  *e = ((hi >> 20) & 0x7ff) - 1022;
+  return __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(x));
+}
+__device__ __forceinline__ double ldexp_normal(double x, int n) {
+  return __hiloint2double(__double2hiint(x) + (n << 20), __double2loint(x));
+}
+__device__ __forceinline__ void floor_divmod(int v, int d, int *quot, int *rem) {   // C div() + the reference's fix-up
+  int q = v / d, r = v - q * d;
+  if (r < 0) { q -= 1; r += d; }
+  *quot = q; *rem = r;
 }
 
-__device__ double encode_gamma(double x) {            // pixel.c:380-443
-  const double cf[9] = {1.1758200232996901923, 0.16665763094889061230, -0.0083154894939042125035,
-                        0.00075187976780420279038, -0.000083240178519391795367, 0.000010229209410070008679,
-                        -1.3400466409860246e-06, 1.8333422241635376682e-07, -2.5878596761348859722e-08};
-  const double p2[12] = {1.0, 1.3348398541700343678, 1.7817974362806785482, 2.3784142300054420538,
-                         3.1748021039363991669, 4.2378523774371812394, 5.6568542494923805819,
-                         7.5509945014535482244, 1.0079368399158985525e1, 1.3454342644059433809e1,
-                         1.7959392772949968275e1, 2.3972913230026907883e1};
-  int e;
-  const double mant = frexp(x, &e);
-  const double p = cheb9(cf, 4.0 * mant - 3.0);
-  int quot = (e - 1) / 12, rem = (e - 1) % 12;
-  if (rem < 0) { quot -= 1; rem += 12; }
-  return ldexp(p2[rem] * p, 5 * quot);
+__device__ __forceinline__ double decode_gamma(double x) {            // pixel.c:260-316
+  int e, quot, rem;
+  const double mant = frexp_normal(x, &e);
+  const double p = cheb9(kDecodeCf, 4.0 * mant - 3.0);
+  floor_divmod(e - 1, 5, &quot, &rem);
+  return x * ldexp_normal(kDecodeP2[rem] * p, 7 * quot);
+}
+
+__device__ __forceinline__ double encode_gamma(double x) {            // pixel.c:380-443
+  int e, quot, rem;
+  const double mant = frexp_normal(x, &e);
+  const double p = cheb9(kEncodeCf, 4.0 * mant - 3.0);
+  floor_divmod(e - 1, 12, &quot, &rem);
+  return ldexp_normal(kEncodeP2[rem] * p, 5 * quot);
 }
 
 __device__ __forceinline__ double decode_pixel_gamma(double pixel) {   // pixel.c:318

@@ -30,6 +30,7 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <type_traits>
 
 namespace mb200 {
 namespace {
@@ -543,17 +544,24 @@ __device__ __forceinline__ float2 finish_pair(bool odd, double sum0, double sum1
 //        lane pair reads the 16 B of its pixel, consecutive steps of a lane fall in the same 128-B
 //        line (L1-resident), so no shared-memory staging or barrier is needed.
 //                                              grid (ceil(width/strip), ceil(height/64))
-template <int NT, int MINB, int AXIS>
+// IO selects the element types: 0 = float Quantum in, float Quantum out (one full pass);
+// 1 = float in, RAW double sums out (first half of a rank-1 2-D kernel: no normalisation, no rounding);
+// 2 = raw double sums in, float Quantum out (second half).  With IO 1 + 2 a separable 2-D kernel
+// (e.g. "gaussian:RxS") is evaluated with kw + kh instead of kw * kh taps per sample while keeping the
+// intermediate in double, i.e. without the float rounding a two-kernel list would introduce.
+template <int NT, int MINB, int AXIS, int IO>
 __global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a, const Taps<NT> taps) {
   constexpr int PF = Ring<NT>::value;
+  constexpr unsigned kInB = (IO == 2) ? 8u : 4u, kOutB = (IO == 1) ? 8u : 4u;   // bytes per component
+  using InT = typename std::conditional<IO == 2, double2, float2>::type;
   const int lane = threadIdx.x & 31;
   const bool odd = (threadIdx.x & 1) != 0;
   const int alpha_lane = lane | 1;
-  const unsigned pitch_bytes = static_cast<unsigned>(a.rc) * 4u;
+  const unsigned in_pitch = static_cast<unsigned>(a.rc) * kInB, out_pitch = static_cast<unsigned>(a.rc) * kOutB;
   int first, nout, limit;                 // first output / number of outputs / clamp limit along the axis
   const char *base;                       // address of sample 0 of this thread's line
   char *outp;
-  unsigned step;                          // bytes between consecutive samples
+  unsigned step, ostep;                   // bytes between consecutive samples (input / output)
   if (AXIS == 1) {
     const int npairs = a.rc >> 1;
     const int pair_raw = blockIdx.x * 128 + threadIdx.x;
@@ -562,9 +570,10 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a
     first = blockIdx.y * a.strip;
     nout = active ? min(a.strip, a.height - first) : 0;
     limit = a.height - 1;
-    step = pitch_bytes;
-    base = reinterpret_cast<const char *>(a.src) + static_cast<size_t>(pair) * 8;
-    outp = reinterpret_cast<char *>(a.dst) + static_cast<size_t>(pair) * 8 + static_cast<size_t>(first) * pitch_bytes;
+    step = in_pitch;
+    ostep = out_pitch;
+    base = reinterpret_cast<const char *>(a.src) + static_cast<size_t>(pair) * (2 * kInB);
+    outp = reinterpret_cast<char *>(a.dst) + static_cast<size_t>(pair) * (2 * kOutB) + static_cast<size_t>(first) * out_pitch;
   } else {
     const int row_raw = blockIdx.y * 64 + (threadIdx.x >> 1);
     const bool active = row_raw < a.height;
@@ -572,22 +581,23 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a
     first = blockIdx.x * a.strip;
     nout = active ? min(a.strip, a.width - first) : 0;
     limit = a.width - 1;
-    step = 16u;
-    base = reinterpret_cast<const char *>(a.src) + static_cast<size_t>(row) * pitch_bytes + (odd ? 8 : 0);
-    outp = reinterpret_cast<char *>(a.dst) + static_cast<size_t>(row) * pitch_bytes + (odd ? 8 : 0) +
-           static_cast<size_t>(first) * 16u;
+    step = 4 * kInB;
+    ostep = 4 * kOutB;
+    base = reinterpret_cast<const char *>(a.src) + static_cast<size_t>(row) * in_pitch + (odd ? 2 * kInB : 0);
+    outp = reinterpret_cast<char *>(a.dst) + static_cast<size_t>(row) * out_pitch + (odd ? 2 * kOutB : 0) +
+           static_cast<size_t>(first) * ostep;
   }
   const int total = a.strip + NT - 1;
 
   double acc0[NT], acc1[NT];
-  float2 pre[PF];
+  InT pre[PF];
 #pragma unroll
   for (int q = 0; q < NT; ++q) { acc0[q] = 0.0; acc1[q] = 0.0; }
   int isrc = first - a.off;                 // source index of step 0
 #pragma unroll
   for (int s = 0; s < PF; ++s) {
     const unsigned ii = static_cast<unsigned>(min(max(isrc + s, 0), limit));
-    pre[s] = __ldg(reinterpret_cast<const float2 *>(base + static_cast<size_t>(ii) * step));
+    pre[s] = __ldg(reinterpret_cast<const InT *>(base + static_cast<size_t>(ii) * step));
   }
   isrc += PF;
 
@@ -596,16 +606,21 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a
   for (int mb = 0; mb < total; mb += PF) {       // PF unrolled steps, then rotate the accumulators by PF
 #pragma unroll
     for (int s = 0; s < PF; ++s) {
-      const float2 vf = pre[s];
+      const InT vf = pre[s];
       {
         const unsigned ii = static_cast<unsigned>(min(max(isrc, 0), limit));
-        pre[s] = __ldg(reinterpret_cast<const float2 *>(base + static_cast<size_t>(ii) * step));
+        pre[s] = __ldg(reinterpret_cast<const InT *>(base + static_cast<size_t>(ii) * step));
         ++isrc;
       }
-      const float af = __shfl_sync(0xffffffffu, vf.y, alpha_lane);
-      const double da = static_cast<double>(af);
-      const double v0 = static_cast<double>(vf.x) * da;
-      const double v1 = static_cast<double>(vf.y) * (odd ? 1.0 : da);
+      double v0, v1;
+      if (IO == 2) {
+        v0 = vf.x; v1 = vf.y;                       // already premultiplied sums
+      } else {
+        const float af = __shfl_sync(0xffffffffu, static_cast<float>(vf.y), alpha_lane);
+        const double da = static_cast<double>(af);
+        v0 = static_cast<double>(vf.x) * da;
+        v1 = static_cast<double>(vf.y) * (odd ? 1.0 : da);
+      }
 #pragma unroll
       for (int q = 0; q < NT; ++q) {
         const double k = taps.k[(s - q + NT) % NT];
@@ -616,10 +631,14 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a
       const double sum0 = acc0[qf], sum1 = acc1[qf];
       acc0[qf] = 0.0;
       acc1[qf] = 0.0;
-      const double gsum = shfl_double(sum1, alpha_lane);
-      const float2 out = finish_pair(odd, sum0, sum1, gsum);
-      if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<float2 *>(outp) = out;
-      if (j >= 0) outp += step;
+      if (IO == 1) {
+        if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<double2 *>(outp) = make_double2(sum0, sum1);
+      } else {
+        const double gsum = shfl_double(sum1, alpha_lane);
+        const float2 out = finish_pair(odd, sum0, sum1, gsum);
+        if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<float2 *>(outp) = out;
+      }
+      if (j >= 0) outp += ostep;
       ++j;
     }
     if (PF != NT) {
@@ -753,26 +772,32 @@ int tuning(const char *name, int fallback) {
 }
 
 template <int NT, int MODE>
-int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int ntaps, cudaStream_t stream) {
+int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int ntaps, int io, cudaStream_t stream) {
   Taps<NT> taps;
   for (int i = 0; i < NT; ++i) taps.k[i] = i < ntaps ? taps_host[i] : 0.0;   // zero padding past the window
   Conv1dArgs a = base;
   const bool tma_ok = MODE == 4 && a.bias == 0.0 && tuning("MB200_TMA", 0) != 0 && (a.rc % 32) == 0 &&
                       ((reinterpret_cast<uintptr_t>(a.src) | reinterpret_cast<uintptr_t>(a.dst)) & 15) == 0;
-  const bool pair_ok = MODE == 4 && a.bias == 0.0 && NT <= 33 && tuning("MB200_PAIR", 1) != 0 &&
+  if (io != 0 && !(MODE == 4 && NT <= 33)) return MB200_EUNSUPPORTED;
+  const bool pair_ok = MODE == 4 && a.bias == 0.0 && NT <= 33 && (io != 0 || tuning("MB200_PAIR", 1) != 0) &&
                        ((reinterpret_cast<uintptr_t>(a.src) | reinterpret_cast<uintptr_t>(a.dst)) & 15) == 0;
+  if (io != 0 && !pair_ok) return MB200_EUNSUPPORTED;
   if (pair_ok && axis == 1) {
     if constexpr (NT <= 33) {
       a.strip = tuning("MB200_COL_ROT", 16) * NT + 1;
       dim3 grid((a.rc / 2 + 127) / 128, (a.height + a.strip - 1) / a.strip);
-      conv_pair_kernel<NT, 2, 1><<<grid, 128, 0, stream>>>(a, taps);
+      if (io == 1) conv_pair_kernel<NT, 2, 1, 1><<<grid, 128, 0, stream>>>(a, taps);
+      else if (io == 2) conv_pair_kernel<NT, 2, 1, 2><<<grid, 128, 0, stream>>>(a, taps);
+      else conv_pair_kernel<NT, 2, 1, 0><<<grid, 128, 0, stream>>>(a, taps);
     }
   } else if (pair_ok && axis == 0) {
     if constexpr (NT <= 33) {
       a.strip = tuning("MB200_ROW_PAIR_ROT", 16) * NT + 1;
       dim3 grid((a.width + a.strip - 1) / a.strip, (a.height + 63) / 64);
-      if (tuning("MB200_ROW_PAIR_TMA", 0)) conv_row_pair_kernel<NT, 2><<<grid, 128, 0, stream>>>(a, taps);
-      else conv_pair_kernel<NT, 2, 0><<<grid, 128, 0, stream>>>(a, taps);
+      if (io == 1) conv_pair_kernel<NT, 2, 0, 1><<<grid, 128, 0, stream>>>(a, taps);
+      else if (io == 2) conv_pair_kernel<NT, 2, 0, 2><<<grid, 128, 0, stream>>>(a, taps);
+      else if (tuning("MB200_ROW_PAIR_TMA", 0)) conv_row_pair_kernel<NT, 2><<<grid, 128, 0, stream>>>(a, taps);
+      else conv_pair_kernel<NT, 2, 0, 0><<<grid, 128, 0, stream>>>(a, taps);
     }
   } else if (tma_ok && axis == 1) {
     constexpr int kMinBlocks = NT <= 33 ? 4 : 2;
@@ -816,17 +841,18 @@ int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int nta
 }
 
 template <int NT>
-int launch_mode(const Conv1dArgs &a, int axis, const double *taps, int ntaps, cudaStream_t s) {
-  if (a.channels == 4) return launch_nt<NT, 4>(a, axis, taps, ntaps, s);
-  if (a.channels == 2) return launch_nt<NT, 2>(a, axis, taps, ntaps, s);
-  return launch_nt<NT, 0>(a, axis, taps, ntaps, s);
+int launch_mode(const Conv1dArgs &a, int axis, const double *taps, int ntaps, int io, cudaStream_t s) {
+  if (a.channels == 4) return launch_nt<NT, 4>(a, axis, taps, ntaps, io, s);
+  if (io != 0) return MB200_EUNSUPPORTED;
+  if (a.channels == 2) return launch_nt<NT, 2>(a, axis, taps, ntaps, io, s);
+  return launch_nt<NT, 0>(a, axis, taps, ntaps, io, s);
 }
 
 }  // namespace
 
 int launch_conv1d(const float *src, float *dst, size_t width, size_t height, int channels, int axis,
                   const double *taps, int ntaps, int origin_offset, double bias, double /*gamma_scale*/,
-                  unsigned long long *d_changed, void *stream) {
+                  unsigned long long *d_changed, void *stream, int io) {
   if (width == 0 || height == 0 || channels < 1 || channels > 4 || ntaps < 1)
     return fail(MB200_EINVAL, "conv1d: bad geometry");
   if (width * channels > 0x1fffffffull || height > 0x7fffffffull) return MB200_EUNSUPPORTED;   // 32-bit byte pitch
@@ -839,12 +865,12 @@ int launch_conv1d(const float *src, float *dst, size_t width, size_t height, int
   a.bias = bias;
   a.changed = d_changed;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (ntaps <= 9) return launch_mode<9>(a, axis, taps, ntaps, s);
-  if (ntaps <= 17) return launch_mode<17>(a, axis, taps, ntaps, s);
-  if (ntaps <= 25) return launch_mode<25>(a, axis, taps, ntaps, s);
-  if (ntaps <= 33) return launch_mode<33>(a, axis, taps, ntaps, s);
-  if (ntaps <= 49) return launch_mode<49>(a, axis, taps, ntaps, s);
-  if (ntaps <= 65) return launch_mode<65>(a, axis, taps, ntaps, s);
+  if (ntaps <= 9) return launch_mode<9>(a, axis, taps, ntaps, io, s);
+  if (ntaps <= 17) return launch_mode<17>(a, axis, taps, ntaps, io, s);
+  if (ntaps <= 25) return launch_mode<25>(a, axis, taps, ntaps, io, s);
+  if (ntaps <= 33) return launch_mode<33>(a, axis, taps, ntaps, io, s);
+  if (ntaps <= 49) return launch_mode<49>(a, axis, taps, ntaps, io, s);
+  if (ntaps <= 65) return launch_mode<65>(a, axis, taps, ntaps, io, s);
   return MB200_EUNSUPPORTED;   // caller falls back to the generic 2-D kernel
 }
 

@@ -36,7 +36,8 @@ inline bool has_alpha(int channels) { return channels == 2 || channels == 4; }
 // d_changed: device counter (may be null) incremented per changed channel value.
 int launch_conv1d(const float *src, float *dst, size_t width, size_t height, int channels,
                   int axis, const double *taps_window_order, int ntaps, int origin_offset,
-                  double bias, double gamma_scale, unsigned long long *d_changed, void *stream);
+                  double bias, double gamma_scale, unsigned long long *d_changed, void *stream,
+                  int io = 0);   // io: 0 float->float, 1 float->raw double sums, 2 raw double sums->float (RGBA only)
 
 // conv2d.cu: general 2-D convolution / erode / dilate (MorphologyPrimitive row path)
 int launch_morph2d(const float *src, float *dst, size_t width, size_t height, int channels,

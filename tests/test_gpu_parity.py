@@ -82,6 +82,50 @@ def test_gaussian_blur_2d(ch, sigma):
     assert max_ulp(_host(im.GaussianBlurImage(_dev(src), 0.0, sigma)), want) <= 1
 
 
+@pytest.mark.parametrize("kind", ["noise", "alpha_blocks", "hdr"])
+@pytest.mark.parametrize("sigma", [0.5, 1.0, 2.0, 3.0, 4.0])
+def test_gaussian_blur_2d_rank1_path(kind, sigma, monkeypatch):
+    """RGBA rank-1 kernels run as row pass (raw double sums) + column pass; both that path and the
+    direct kw*kh kernel must agree with the oracle's 2-D MorphologyPrimitive."""
+    for (w, h) in ((97, 61), (300, 5), (3, 200), (1, 1), (640, 130)):
+        src = make_image(w, h, 4, seed=w + 3, kind=kind)
+        want = orc("orc_gaussian_blur", src, 0.0, sigma)
+        n0 = im.launch_count()
+        got = _host(im.GaussianBlurImage(_dev(src), 0.0, sigma))
+        launches = im.launch_count() - n0
+        assert max_ulp(got, want) <= 1, (w, h, kind, sigma)
+        monkeypatch.setenv("MB200_NO_RANK1", "1")
+        n0 = im.launch_count()
+        direct = _host(im.GaussianBlurImage(_dev(src), 0.0, sigma))
+        assert im.launch_count() - n0 == 1
+        monkeypatch.delenv("MB200_NO_RANK1")
+        assert max_ulp(direct, want) <= 1
+        assert launches == 2          # the separable path was taken
+
+
+def test_rank1_user_kernel_and_non_rank1_neighbour():
+    src = make_image(150, 90, 4, seed=77, kind="alpha_blocks")
+    col = np.array([1.0, 3.0, 2.0, 0.5, 0.25])
+    row = np.array([0.5, 2.0, 1.0])
+    vals = np.outer(col, row)
+    for (x, y) in ((1, 2), (0, 4), (2, 0)):
+        k = util.orc_kernel_from_array(vals, x, y)
+        ks = f"3x5+{x}+{y}: " + " ".join(",".join(repr(float(v)) for v in r) for r in vals)
+        want = util.orc_morphology(src, im.ConvolveMorphology, 1, [k])
+        n0 = im.launch_count()
+        got = _host(im.MorphologyImage(_dev(src), im.ConvolveMorphology, 1, ks))
+        assert im.launch_count() - n0 == 2
+        assert max_ulp(got, want) <= 1, (x, y)
+    vals2 = vals.copy()
+    vals2[2, 1] += 1e-9                      # no longer rank 1 -> direct kernel
+    k = util.orc_kernel_from_array(vals2, 1, 2)
+    ks = "3x5+1+2: " + " ".join(",".join(repr(float(v)) for v in r) for r in vals2)
+    n0 = im.launch_count()
+    got = _host(im.MorphologyImage(_dev(src), im.ConvolveMorphology, 1, ks))
+    assert im.launch_count() - n0 == 1
+    assert max_ulp(got, util.orc_morphology(src, im.ConvolveMorphology, 1, [k])) <= 1
+
+
 @pytest.mark.parametrize("ch", [1, 2, 3, 4])
 def test_unsharp(ch):
     src = make_image(120, 77, ch, seed=5)
