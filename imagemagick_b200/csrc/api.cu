@@ -137,6 +137,11 @@ int primitive(const float *src, float *dst, size_t w, size_t h, int ch, int meth
       }
     }
   }
+  if ((method == MB200_ErodeMorphology || method == MB200_DilateMorphology) && d_counter == nullptr &&
+      std::getenv("MB200_NO_MORPH_STREAM") == nullptr) {     // register-streaming kernel for the built-in shapes
+    const int rc = launch_morph_stream(src, dst, w, h, ch, method, win.data(), kw, kh, ox, oy, s);
+    if (rc != MB200_EUNSUPPORTED) return rc;
+  }
   if ((method == MB200_ErodeMorphology || method == MB200_DilateMorphology) &&
       std::getenv("MB200_MORPH_FLAT") != nullptr) {          // run-decomposition variant: opt-in (r01: not faster yet)
     const int rc = launch_morph_flat(src, dst, w, h, ch, method, win.data(), kw, kh, ox, oy, d_counter, s);

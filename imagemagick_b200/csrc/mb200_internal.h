@@ -49,6 +49,11 @@ int launch_morph_flat(const float *src, float *dst, size_t width, size_t height,
                       int method, const double *kernel_window_order, int kw, int kh, int ox, int oy,
                       unsigned long long *d_changed, void *stream);
 
+// morph_stream.cu: erode / dilate for the built-in structuring elements, register streaming
+// (MB200_EUNSUPPORTED => shape not in the table; use launch_morph2d)
+int launch_morph_stream(const float *src, float *dst, size_t width, size_t height, int channels, int method,
+                        const double *kernel_window_order, int kw, int kh, int ox, int oy, void *stream);
+
 // resize.cu: one axis of ResizeImage.  Contribution table lives in device memory.
 int launch_resize_axis(const float *src, size_t width, size_t height, int channels, float *dst,
                        size_t out_n, int axis, const int *d_start, const int *d_count,

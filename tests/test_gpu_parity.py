@@ -158,6 +158,36 @@ def test_erode_dilate_bit_exact(ch, name, args):
         assert max_ulp(got_h, want) == 0
 
 
+STREAM_SHAPES = [("Disk:1", ("disk", 1, 1, 0, 0)), ("Disk:2", ("disk", 2, 1, 0, 0)), ("Disk:2.5", ("disk", 2.5, 1, 0, 0)),
+                 ("Disk:3", ("disk", 3, 1, 0, 0)), ("Disk:3.5", ("disk", 3.5, 1, 0, 0)), ("Disk:4", ("disk", 4, 1, 0, 0)),
+                 ("Disk:4.5", ("disk", 4.5, 1, 0, 0)), ("Disk:5", ("disk", 5, 1, 0, 0)), ("Square:1", ("square", 1, 1, 0, 0)),
+                 ("Square:3", ("square", 3, 1, 0, 0)), ("Square:4", ("square", 4, 1, 0, 0)),
+                 ("Diamond:3", ("diamond", 3, 1, 0, 0)), ("Diamond:4", ("diamond", 4, 1, 0, 0)),
+                 ("Diamond:5", ("diamond", 5, 1, 0, 0)), ("Octagon:2", ("octagon", 2, 1, 0, 0)),
+                 ("Octagon:4", ("octagon", 4, 1, 0, 0)), ("Octagon:5", ("octagon", 5, 1, 0, 0)),
+                 ("Plus:3", ("plus", 3, 1, 0, 0)), ("Plus:4", ("plus", 4, 1, 0, 0))]
+
+
+@pytest.mark.parametrize("ch", [1, 4])
+@pytest.mark.parametrize("name,args", STREAM_SHAPES)
+def test_erode_dilate_streaming_kernel(ch, name, args, monkeypatch):
+    """Built-in structuring elements take the register-streaming kernel (morph_stream.cu): bit exact against
+    the oracle and against the generic kernel, on widths around the 32-2R lane groups and strips taller
+    than one CTA strip."""
+    k = util.orc_kernel(*args)
+    for (w, h) in ((83, 59), (1, 1), (3, 140), (22, 7), (23, 67), (300, 150)):
+        src = make_image(w, h, ch, seed=w + h, kind="hdr" if w == 23 else "noise")
+        for method in (im.ErodeMorphology, im.DilateMorphology):
+            want = util.orc_morphology(src, method, 1, [k])
+            got = _host(im.MorphologyImage(_dev(src), method, 1, name))
+            assert max_ulp(got, want) == 0, (name, ch, method, w, h)
+    src = make_image(131, 97, ch, seed=5)
+    got = _host(im.MorphologyImage(_dev(src), im.DilateMorphology, 1, name))
+    monkeypatch.setenv("MB200_NO_MORPH_STREAM", "1")
+    generic = _host(im.MorphologyImage(_dev(src), im.DilateMorphology, 1, name))
+    assert max_ulp(got, generic) == 0
+
+
 def test_dilate_until_convergence_and_changed_count():
     src = make_image(64, 48, 1, seed=9, kind="binary")
     k = util.orc_kernel("diamond", 1, 1, 0, 0)
