@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 using namespace mb200;
@@ -34,6 +35,12 @@ struct ResizeTables {
   int max_span = 0, reg_stride = 0, reg_taps = 0;
   int *d_start = nullptr, *d_count = nullptr;
   double *d_weights = nullptr, *d_wreg = nullptr;
+  // streaming kernels (resize_stream.cu): runs of outputs with bit-identical weights, and the
+  // complement (borders, short runs) that stays with the gather kernels
+  int nseg = 0, seg_o[MB200_RESIZE_MAX_SEGMENTS], seg_n[MB200_RESIZE_MAX_SEGMENTS], seg_src[MB200_RESIZE_MAX_SEGMENTS];
+  double *d_wsets = nullptr;
+  int nborder = 0;
+  int *d_border = nullptr;
 };
 std::mutex g_tables_mutex;
 std::vector<ResizeTables *> g_tables;      // entries are never freed before process exit (<= 64 kept)
@@ -383,7 +390,8 @@ int mb200_resize_image_dev(const float *src, size_t width, size_t height, int ch
     if (taps < 0) return static_cast<int>(taps);
     std::vector<long> start(out_n);
     std::vector<int> istart(out_n), count(out_n);
-    std::vector<double> w(out_n * static_cast<size_t>(taps)), wt(out_n * static_cast<size_t>(taps)), wreg;
+    std::vector<double> w(out_n * static_cast<size_t>(taps)), wt(out_n * static_cast<size_t>(taps)), wreg, wsets;
+    std::vector<int> border;
     const long r = mb200_resize_contributions(filter_type, in_n, out_n, factor, start.data(), count.data(), w.data(),
                                               static_cast<size_t>(taps));
     if (r < 0) return static_cast<int>(r);
@@ -410,6 +418,39 @@ int mb200_resize_image_dev(const float *src, size_t width, size_t height, int ch
         wreg.assign(out_n * static_cast<size_t>(n), 0.0);
         for (size_t o = 0; o < out_n; ++o)
           for (int j = 0; j < n && j < count[o]; ++j) wreg[o * n + j] = w[o * taps + j];
+        // longest run [lo, lo+len) with count == n and start advancing by st
+        // runs of outputs whose weights are bit-identical (same binade of bisect, resize.c:3398-3443)
+        struct Run { size_t lo, len; };
+        std::vector<Run> runs;
+        size_t lo = 0;
+        for (size_t o = 1; o <= out_n; ++o) {
+          const bool same = o < out_n && count[o] == n && count[lo] == n && start[o] - start[o - 1] == st &&
+                            std::memcmp(&w[o * taps], &w[lo * taps], static_cast<size_t>(n) * sizeof(double)) == 0;
+          if (!same) {
+            if (count[lo] == n && o - lo >= 8) runs.push_back({lo, o - lo});
+            lo = o;
+          }
+        }
+        std::sort(runs.begin(), runs.end(), [](const Run &a, const Run &b) { return a.len > b.len; });
+        if (runs.size() > MB200_RESIZE_MAX_SEGMENTS) runs.resize(MB200_RESIZE_MAX_SEGMENTS);
+        std::sort(runs.begin(), runs.end(), [](const Run &a, const Run &b) { return a.lo < b.lo; });
+        size_t covered = 0;
+        for (const Run &r : runs) covered += r.len;
+        if (!runs.empty() && covered * 10 >= out_n * 6) {
+          long next = 0;
+          for (const Run &r : runs) {
+            t->seg_o[t->nseg] = static_cast<int>(r.lo);
+            t->seg_n[t->nseg] = static_cast<int>(r.len);
+            t->seg_src[t->nseg] = static_cast<int>(start[r.lo]);
+            ++t->nseg;
+            wsets.insert(wsets.end(), &w[r.lo * taps], &w[r.lo * taps] + n);
+            for (long o = next; o < static_cast<long>(r.lo); ++o) border.push_back(static_cast<int>(o));
+            next = static_cast<long>(r.lo + r.len);
+          }
+          for (long o = next; o < static_cast<long>(out_n); ++o) border.push_back(static_cast<int>(o));
+          t->nborder = static_cast<int>(border.size());
+          if (border.empty()) border.push_back(0);      // keep the buffer non-null
+        }
       }
     }
     for (size_t o = 0; o < out_n; ++o) {          // tap-major transpose for coalesced weight loads
@@ -420,13 +461,19 @@ int mb200_resize_image_dev(const float *src, size_t width, size_t height, int ch
     if (e == cudaSuccess) e = cudaMalloc(&t->d_count, out_n * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&t->d_weights, wt.size() * sizeof(double));
     if (e == cudaSuccess && !wreg.empty()) e = cudaMalloc(&t->d_wreg, wreg.size() * sizeof(double));
+    if (e == cudaSuccess && !wsets.empty()) e = cudaMalloc(&t->d_wsets, wsets.size() * sizeof(double));
+    if (e == cudaSuccess && !wsets.empty())
+      e = cudaMemcpy(t->d_wsets, wsets.data(), wsets.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !border.empty()) e = cudaMalloc(&t->d_border, border.size() * sizeof(int));
+    if (e == cudaSuccess && !border.empty())
+      e = cudaMemcpy(t->d_border, border.data(), border.size() * sizeof(int), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(t->d_start, istart.data(), out_n * sizeof(int), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(t->d_count, count.data(), out_n * sizeof(int), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(t->d_weights, wt.data(), wt.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !wreg.empty())
       e = cudaMemcpy(t->d_wreg, wreg.data(), wreg.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
-      cudaFree(t->d_start); cudaFree(t->d_count); cudaFree(t->d_weights); cudaFree(t->d_wreg);
+      cudaFree(t->d_start); cudaFree(t->d_count); cudaFree(t->d_weights); cudaFree(t->d_wreg); cudaFree(t->d_wsets); cudaFree(t->d_border);
       delete t;
       return cuda_fail(e, "resize: table upload");
     }
@@ -443,7 +490,14 @@ int mb200_resize_image_dev(const float *src, size_t width, size_t height, int ch
   if (rc) return rc;
   StreamAlloc tmp(s);
   const bool reg_h = std::getenv("MB200_RESIZE_REGULAR_H") != nullptr;   // tiled regular H kernel: opt-in (r01: slower)
+  const bool no_stream = std::getenv("MB200_NO_RESIZE_STREAM") != nullptr;
   auto run_axis = [&](const float *in, size_t w, size_t h, float *out, int axis, const ResizeTables *t) -> int {
+    if (channels == 4 && t->d_wsets != nullptr && !no_stream) {        // streaming kernels (+ border gather CTAs)
+      const int rs = launch_resize_stream(in, w, h, out, t->out_n, axis, t->reg_stride, t->reg_taps, t->nseg, t->seg_o,
+                                          t->seg_n, t->seg_src, t->d_wsets, t->nborder, t->d_border, t->d_start,
+                                          t->d_count, t->d_weights, s);
+      if (rs != MB200_EUNSUPPORTED) return rs;
+    }
     const bool use_reg = t->d_wreg != nullptr && (axis == 1 || reg_h);
     return launch_resize_axis(in, w, h, channels, out, t->out_n, axis, t->d_start, t->d_count, t->d_weights,
                               static_cast<int>(t->taps), t->max_span, use_reg ? t->reg_stride : 0, t->reg_taps,

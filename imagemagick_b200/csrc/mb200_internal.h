@@ -58,7 +58,16 @@ int launch_morph_stream(const float *src, float *dst, size_t width, size_t heigh
 int launch_resize_axis(const float *src, size_t width, size_t height, int channels, float *dst,
                        size_t out_n, int axis, const int *d_start, const int *d_count,
                        const double *d_weights, int max_taps, int max_span, int reg_stride, int reg_taps,
-                       const double *d_wreg, void *stream);
+                       const double *d_wreg, void *stream, long o_begin = -1, long o_end = -1);
+
+// resize_stream.cu: streaming kernels for runs of outputs with bit-identical weights (integer-ratio
+// reductions, RGBA).  seg_*: first output / number of outputs / start[] of each run; d_wsets[nseg][taps];
+// d_border: the outputs outside the runs (gathered by extra CTAs of the same launch).
+#define MB200_RESIZE_MAX_SEGMENTS 8
+int launch_resize_stream(const float *src, size_t width, size_t height, float *dst, size_t out_n, int axis,
+                         int stride, int taps, int nseg, const int *seg_o, const int *seg_n, const int *seg_src,
+                         const double *d_wsets, int nborder, const int *d_border, const int *d_start,
+                         const int *d_count, const double *d_weights, void *stream);
 
 // colorspace.cu
 int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to, void *stream);

@@ -38,6 +38,7 @@ struct ResizeArgs {
   const int *count;
   const double *weights;  // tap-major: weights[j*out_n + o]
   int lines_per_thread;
+  int o_begin, o_end;     // generic kernels: output sub-range along the filtered axis
 };
 
 template <int CH>
@@ -109,8 +110,8 @@ template <int CH>
 __global__ void __launch_bounds__(128) resize_vertical_kernel(const ResizeArgs a) {
   const int x = blockIdx.x * 128 + threadIdx.x;
   if (x >= a.width) return;
-  const int o0 = blockIdx.y * a.lines_per_thread;
-  const int o1 = min(o0 + a.lines_per_thread, a.out_h);
+  const int o0 = a.o_begin + blockIdx.y * a.lines_per_thread;
+  const int o1 = min(o0 + a.lines_per_thread, a.o_end);
   const float *col = a.src + static_cast<size_t>(x) * CH;
   const size_t pitch = static_cast<size_t>(a.width) * CH;
   for (int o = o0; o < o1; ++o) {
@@ -133,8 +134,8 @@ __global__ void __launch_bounds__(128) resize_vertical_kernel(const ResizeArgs a
 // horizontal: grid (ceil(out_w/128), ceil(height/lines_per_thread))
 template <int CH>
 __global__ void __launch_bounds__(128) resize_horizontal_kernel(const ResizeArgs a) {
-  const int o = blockIdx.x * 128 + threadIdx.x;
-  if (o >= a.out_w) return;
+  const int o = a.o_begin + blockIdx.x * 128 + threadIdx.x;
+  if (o >= a.o_end) return;
   const int y0 = blockIdx.y * a.lines_per_thread;
   const int y1 = min(y0 + a.lines_per_thread, a.height);
   const int first = __ldg(a.start + o), n = __ldg(a.count + o);
@@ -365,7 +366,7 @@ int launch_regular_ch(const ResizeArgs &a, int axis, int stride, int ntaps, cons
 int launch_resize_axis(const float *src, size_t width, size_t height, int channels, float *dst, size_t out_n,
                        int axis, const int *d_start, const int *d_count, const double *d_weights,
                        int /*max_taps*/, int max_span, int reg_stride, int reg_taps, const double *d_wreg,
-                       void *stream) {
+                       void *stream, long o_begin, long o_end) {
   if (width == 0 || height == 0 || out_n == 0 || channels < 1 || channels > 4)
     return fail(MB200_EINVAL, "resize: bad geometry");
   if (width > 0x3fffffffull || height > 0x3fffffffull || out_n > 0x3fffffffull)
@@ -379,7 +380,11 @@ int launch_resize_axis(const float *src, size_t width, size_t height, int channe
   a.lines_per_thread = 8;
   if (axis == 1) { a.out_w = a.width; a.out_h = a.out_n; }
   else { a.out_w = a.out_n; a.out_h = a.height; }
-  if (reg_stride > 0 && d_wreg != nullptr) {
+  const bool whole = o_begin < 0;
+  a.o_begin = whole ? 0 : static_cast<int>(o_begin);
+  a.o_end = whole ? a.out_n : static_cast<int>(o_end);
+  if (a.o_begin >= a.o_end) return MB200_OK;
+  if (whole && reg_stride > 0 && d_wreg != nullptr) {
     int rc = MB200_EUNSUPPORTED;
     switch (channels) {
       case 1: rc = launch_regular_ch<1>(a, axis, reg_stride, reg_taps, d_wreg, max_span, s); break;
@@ -395,7 +400,7 @@ int launch_resize_axis(const float *src, size_t width, size_t height, int channe
     }
   }
   if (axis == 1) {
-    dim3 grid((a.width + 127) / 128, (a.out_h + a.lines_per_thread - 1) / a.lines_per_thread);
+    dim3 grid((a.width + 127) / 128, (a.o_end - a.o_begin + a.lines_per_thread - 1) / a.lines_per_thread);
     if (grid.y > 65535) return fail(MB200_EINVAL, "resize: too many rows");
     switch (channels) {
       case 1: resize_vertical_kernel<1><<<grid, 128, 0, s>>>(a); break;
@@ -404,7 +409,7 @@ int launch_resize_axis(const float *src, size_t width, size_t height, int channe
       default: resize_vertical_kernel<4><<<grid, 128, 0, s>>>(a); break;
     }
   } else {
-    dim3 grid((a.out_w + 127) / 128, (a.height + a.lines_per_thread - 1) / a.lines_per_thread);
+    dim3 grid((a.o_end - a.o_begin + 127) / 128, (a.height + a.lines_per_thread - 1) / a.lines_per_thread);
     if (grid.y > 65535) return fail(MB200_EINVAL, "resize: too many rows");
     switch (channels) {
       case 1: resize_horizontal_kernel<1><<<grid, 128, 0, s>>>(a); break;

@@ -1,0 +1,383 @@
+// resize_stream.cu -- streaming kernels for one axis of ResizeImage over UNIFORM SEGMENTS of the
+// contribution table (integer-ratio reductions).
+//
+// HorizontalFilter / VerticalFilter (MagickCore/resize.c:3333-3547, :3549-3759) evaluate the filter
+// weights per output from  bisect = (o + 0.5)/factor + MagickEpsilon  (:3398-3443).  For an integer
+// reduction ratio  start - bisect  is the same real number for every output, and in floating point it
+// is the same double for every output whose bisect lies in the same binade (the epsilon is absorbed
+// identically).  The reference's table therefore consists of a dozen runs of outputs with
+// BIT-IDENTICAL weights, the same tap count N and a window that advances by S samples per output
+// (8192 -> 4096 Lanczos3: runs of 96, 384 and 3581 outputs cover all but 35 of them).  The host
+// (api.cu) finds those runs by comparing the reference's own weights bit for bit; nothing is
+// approximated.
+//
+// Inside a run the operator is a strided 1-D convolution, so it is evaluated like conv1d.cu: a
+// thread walks ALONG the filtered axis over a strip of outputs and keeps the R = ceil(N/S) outputs
+// whose windows contain the current source sample as rotating FP64 accumulators in registers; the N
+// weights live in registers for the whole strip.  Every source sample is loaded, converted and
+// alpha-premultiplied exactly once and feeds <= R x 4 FMAs in the reference's tap order; one output
+// completes every S steps (double accumulation, one rounding to float, resize.c:3472-3484).
+//
+//  vertical (axis 1): lane = pixel column, 512-byte coalesced row reads, register prefetch ring.
+//  horizontal (axis 0): lane = image row.  Each warp stages 8-pixel (128-byte, line-aligned)
+//    chunks of its 32 rows into a private shared-memory ring with cp.async (LDGSTS) -- full-line
+//    global requests, no block barriers -- and reads its own row back with conflict-free LDS.128
+//    (row pitch 144 B).  Outputs are 16-byte stores; eight consecutive steps of a lane fill a line.
+//
+// Outputs outside the streamed runs (the image borders, where the window is clipped, and the very
+// short low-binade runs) are produced by the generic gather kernels of resize.cu.
+#include "mb200_internal.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+
+namespace mb200 {
+namespace {
+
+constexpr double kQuantumScale = 1.0 / 65535.0;
+constexpr double kEpsilon = 1.0e-12;
+constexpr int kMaxSegments = MB200_RESIZE_MAX_SEGMENTS;
+
+struct StreamArgs {
+  const float *src;
+  float *dst;
+  int width, height;      // source image
+  int out_w, out_h;       // destination image
+  int in_n;               // source extent along the filtered axis
+  int strip;              // outputs per strip
+  int nseg;
+  int seg_o[kMaxSegments];        // first output of the run
+  int seg_n[kMaxSegments];        // outputs in the run
+  int seg_src[kMaxSegments];      // start[] of its first output
+  int seg_strip0[kMaxSegments];   // index of its first strip
+  const double *wsets;            // [nseg][N] weights of each run
+  int nstrips;                    // CTAs beyond the strips produce the border outputs (gather)
+  int nborder, out_n;
+  const int *border;              // outputs outside the runs
+  const int *start, *count;       // the reference's contribution table (resize.cu layout)
+  const double *weights;          // tap-major [tap][out_n]
+};
+
+// 1/g to ~2^-40 relative: MUFU.RCP64H seed + one Newton step (same helper as conv1d.cu).
+__device__ __forceinline__ double fast_reciprocal(double g) {
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(g));
+  const double e = fma(-g, r0, 1.0);
+  return fma(r0, e, r0);
+}
+
+// resize.c:3472-3484 for RGBA with acc[3] = sum w*A (QuantumScale cancels), acc[c] = sum w*A*p_c:
+// out_c = PerceptibleReciprocal(QS*acc[3]) * QS*acc[c]; branch-free by clamping the denominator.
+__device__ __forceinline__ float4 finish_rgba(const double (&acc)[4]) {
+  constexpr double kTiny = kEpsilon / kQuantumScale;
+  const bool perceptible = fabs(kQuantumScale * acc[3]) >= kEpsilon;
+  const double den = perceptible ? acc[3] : (acc[3] < 0.0 ? -kTiny : kTiny);
+  const double r = fast_reciprocal(den);
+  return make_float4(static_cast<float>(r * acc[0]), static_cast<float>(r * acc[1]), static_cast<float>(r * acc[2]),
+                     static_cast<float>(acc[3]));
+}
+
+template <int S, int N>
+struct Rot {
+  static constexpr int R = (N + S - 1) / S;     // live outputs
+  static constexpr int P = R * S;               // rotation period in source steps
+  static constexpr int BODY = P < 8 ? 8 : P;    // unrolled steps per loop iteration (multiple of P)
+  static constexpr int PF = BODY % 12 == 0 ? 12 : BODY % 8 == 0 ? 8 : BODY % 7 == 0 ? 7 : BODY % 6 == 0 ? 6 : 4;
+  static_assert(BODY % P == 0 && BODY % PF == 0, "ring / period mismatch");
+};
+
+// one source sample into the live accumulators; m = step within the rotation period (static).
+// Slot q holds the output whose window started at step S*q of this (or the previous) period.
+template <int S, int N>
+__device__ __forceinline__ void feed(double (&acc)[Rot<S, N>::R][4], const double (&W)[N], const float4 v, int m) {
+  constexpr int R = Rot<S, N>::R, P = Rot<S, N>::P;
+  const double a = static_cast<double>(v.w);
+  const double q0 = static_cast<double>(v.x) * a, q1 = static_cast<double>(v.y) * a, q2 = static_cast<double>(v.z) * a;
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    const int j = (m - S * q + 2 * P) % P;        // tap index of this sample in slot q's window
+    if (j == 0) {
+      acc[q][0] = W[0] * q0; acc[q][1] = W[0] * q1; acc[q][2] = W[0] * q2; acc[q][3] = W[0] * a;
+    } else if (j < N) {
+      acc[q][0] = fma(W[j], q0, acc[q][0]);
+      acc[q][1] = fma(W[j], q1, acc[q][1]);
+      acc[q][2] = fma(W[j], q2, acc[q][2]);
+      acc[q][3] = fma(W[j], a, acc[q][3]);
+    }
+  }
+}
+// slot that receives its last tap at step m of the period, or -1
+template <int S, int N>
+__device__ __forceinline__ constexpr int done_slot(int m) {
+  constexpr int P = Rot<S, N>::P;
+  const int jd = (m - (N - 1) + 2 * P) % P;
+  return jd % S == 0 ? jd / S : -1;
+}
+
+// One border output (window clipped by the image edge, or a run too short to stream): plain gather
+// over the reference's contribution list.  axis 1: line = column x; axis 0: line = row y.
+template <int AXIS>
+__device__ __forceinline__ void border_output(const StreamArgs &a, int o, int line) {
+  const int first = __ldg(a.start + o), n = __ldg(a.count + o);
+  if (n <= 0) return;                                 // resize.c:3440 leaves the output untouched
+  const size_t step = AXIS == 1 ? static_cast<size_t>(a.width) * 4 : 4;
+  const float *p = AXIS == 1 ? a.src + (static_cast<size_t>(first) * a.width + line) * 4
+                             : a.src + (static_cast<size_t>(line) * a.width + first) * 4;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int j = 0; j < n; ++j, p += step) {
+    const double w = __ldg(a.weights + static_cast<size_t>(j) * a.out_n + o);
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    const double al = static_cast<double>(v.w);
+    acc[0] = fma(w, static_cast<double>(v.x) * al, acc[0]);
+    acc[1] = fma(w, static_cast<double>(v.y) * al, acc[1]);
+    acc[2] = fma(w, static_cast<double>(v.z) * al, acc[2]);
+    acc[3] = fma(w, al, acc[3]);
+  }
+  float *q = AXIS == 1 ? a.dst + (static_cast<size_t>(o) * a.out_w + line) * 4
+                       : a.dst + (static_cast<size_t>(line) * a.out_w + o) * 4;
+  *reinterpret_cast<float4 *>(q) = finish_rgba(acc);
+}
+
+struct Strip { int o0, nout, src0, set; };
+__device__ __forceinline__ Strip locate(const StreamArgs &a, int b, int stride) {
+  int k = 0;
+#pragma unroll
+  for (int t = 1; t < kMaxSegments; ++t)
+    if (t < a.nseg && b >= a.seg_strip0[t]) k = t;
+  const int rel = (b - a.seg_strip0[k]) * a.strip;
+  Strip s;
+  s.o0 = a.seg_o[k] + rel;
+  s.nout = min(a.strip, a.seg_n[k] - rel);
+  s.src0 = a.seg_src[k] + stride * rel;
+  s.set = k;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------- vertical
+// grid (ceil(width/128), total strips); thread = one RGBA pixel column.
+template <int S, int N>
+__global__ void __launch_bounds__(128, 3) resize_v_stream_kernel(const StreamArgs a) {
+  using T = Rot<S, N>;
+  constexpr int R = T::R, P = T::P, BODY = T::BODY, PF = T::PF;
+  const int x_raw = blockIdx.x * 128 + threadIdx.x;
+  const bool active = x_raw < a.width;
+  const int x = active ? x_raw : a.width - 1;
+  if (static_cast<int>(blockIdx.y) >= a.nstrips) {   // border rows: one output row per CTA row
+    if (active) border_output<1>(a, __ldg(a.border + (blockIdx.y - a.nstrips)), x);
+    return;
+  }
+  const Strip st = locate(a, blockIdx.y, S);
+  double W[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) W[j] = __ldg(a.wsets + st.set * N + j);
+  const int niter = (S * (st.nout - 1) + N + BODY - 1) / BODY;
+  const size_t pitch = static_cast<size_t>(a.width) * 4;
+  const float *col = a.src + static_cast<size_t>(x) * 4;
+  const int last = a.in_n - 1;
+  int row = st.src0;                                 // source row of the next ring load
+  float4 pre[PF];
+#pragma unroll
+  for (int s = 0; s < PF; ++s, ++row)
+    pre[s] = __ldg(reinterpret_cast<const float4 *>(col + static_cast<size_t>(min(row, last)) * pitch));
+  double acc[R][4];
+#pragma unroll
+  for (int q = 0; q < R; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0; }
+  int c = -R;                                        // R-1 slots complete once before output 0 does
+  const size_t opitch = static_cast<size_t>(a.out_w) * 4;
+  float *outp = a.dst + (static_cast<ptrdiff_t>(st.o0 - (R - 1)) * a.out_w + x) * 4;
+#pragma unroll 1
+  for (int t = 0; t < niter; ++t) {
+#pragma unroll
+    for (int b = 0; b < BODY; ++b) {
+      const int m = b % P;
+      const float4 v = pre[b % PF];
+      pre[b % PF] = __ldg(reinterpret_cast<const float4 *>(col + static_cast<size_t>(min(row, last)) * pitch));
+      ++row;
+      feed<S, N>(acc, W, v, m);
+      const int qd = done_slot<S, N>(m);
+      if (qd >= 0) {
+        ++c;
+        if (c >= 0 && c < st.nout && active) *reinterpret_cast<float4 *>(outp) = finish_rgba(acc[qd]);
+        outp += opitch;
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------- horizontal
+// grid (total strips, ceil(height/128)); warp = 32 rows (lane = row), private cp.async ring.
+constexpr int kChunkPx = 8;                         // pixels per row per ring slot (128 B)
+constexpr int kRowPitch = kChunkPx * 16 + 16;       // 144 B: (9*row + k) mod 8 distinct => conflict-free
+constexpr int kSlotBytes = 32 * kRowPitch;          // 4608 B
+
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void *gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int K>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
+
+template <int S, int N, int NSLOT>
+__global__ void __launch_bounds__(128, 3) resize_h_stream_kernel(const StreamArgs a) {
+  using T = Rot<S, N>;
+  constexpr int R = T::R, P = T::P, BODY = T::BODY;
+  extern __shared__ __align__(128) unsigned char ring_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned ring_s =
+      static_cast<unsigned>(__cvta_generic_to_shared(ring_all + static_cast<size_t>(warp) * NSLOT * kSlotBytes));
+  const int row0 = blockIdx.y * 128 + warp * 32;
+  if (row0 >= a.height) return;
+  if (static_cast<int>(blockIdx.x) >= a.nstrips) {   // border columns: thread = row, CTA = one output column
+    if (row0 + lane < a.height) border_output<0>(a, __ldg(a.border + (blockIdx.x - a.nstrips)), row0 + lane);
+    return;
+  }
+  const Strip st = locate(a, blockIdx.x, S);
+  double W[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) W[j] = __ldg(a.wsets + st.set * N + j);
+  const int niter = (S * (st.nout - 1) + N + BODY - 1) / BODY;
+  const int p0 = st.src0;                            // absolute source pixel of step 0
+  const int c0 = p0 / kChunkPx;                      // first chunk (line aligned)
+  const int nchunks = (p0 + niter * BODY + kChunkPx - 1) / kChunkPx - c0;
+  // loader role: instruction j copies pixel (lane & 7) of row 4j + (lane >> 3)
+  const int lrow = lane >> 3, lpx = lane & 7;
+  const size_t pitch_b = static_cast<size_t>(a.width) * 16;
+  const unsigned char *srcb = reinterpret_cast<const unsigned char *>(a.src);
+  const int last_px = a.in_n - 1;
+  auto issue = [&](int chunk_rel) {
+    if (chunk_rel < nchunks) {
+      const int px = min((c0 + chunk_rel) * kChunkPx + lpx, last_px);
+      const unsigned slot = ring_s + static_cast<unsigned>(chunk_rel % NSLOT) * kSlotBytes;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = 4 * j + lrow;
+        const int y = min(row0 + r, a.height - 1);
+        cp_async16(slot + r * kRowPitch + lpx * 16, srcb + static_cast<size_t>(y) * pitch_b + static_cast<size_t>(px) * 16);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int c = 0; c < NSLOT; ++c) issue(c);
+
+  const int y = row0 + lane;
+  const bool active = y < a.height;
+  double acc[R][4];
+#pragma unroll
+  for (int q = 0; q < R; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0; }
+  int c = -R;
+  float *outp = a.dst + (static_cast<ptrdiff_t>(active ? y : 0) * a.out_w + (st.o0 - (R - 1))) * 4;
+  int chunk = 0;                                    // chunk being consumed (relative)
+  int px_in = p0 - c0 * kChunkPx;                   // pixel within the chunk
+  cp_async_wait<NSLOT - 1>();
+  __syncwarp();
+  unsigned rd = ring_s + lane * kRowPitch + px_in * 16;   // this lane's next LDS address (slot 0)
+#pragma unroll 1
+  for (int t = 0; t < niter; ++t) {
+#pragma unroll
+    for (int b = 0; b < BODY; ++b) {
+      const int m = b % P;
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(rd));
+      feed<S, N>(acc, W, v, m);
+      const int qd = done_slot<S, N>(m);
+      if (qd >= 0) {
+        ++c;
+        if (c >= 0 && c < st.nout && active) *reinterpret_cast<float4 *>(outp) = finish_rgba(acc[qd]);
+        outp += 4;
+      }
+      rd += 16;
+      if (++px_in == kChunkPx) {                    // warp-uniform: chunk exhausted
+        px_in = 0;
+        __syncwarp();                               // every lane is done reading the slot
+        issue(chunk + NSLOT);                       // refill it (same slot: (chunk + NSLOT) % NSLOT)
+        ++chunk;
+        cp_async_wait<NSLOT - 1>();                 // chunk is complete; NSLOT-1 later ones stay in flight
+        __syncwarp();
+        rd = ring_s + static_cast<unsigned>(chunk % NSLOT) * kSlotBytes + lane * kRowPitch;
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+template <int S, int N>
+int launch_sn(StreamArgs a, int axis, cudaStream_t s) {
+  static int strip_env = -1, slots_env = -1;
+  if (strip_env < 0) {
+    const char *e = std::getenv("MB200_RESIZE_STRIP");
+    strip_env = e ? std::atoi(e) : 0;
+    const char *f = std::getenv("MB200_RESIZE_SLOTS");
+    slots_env = f ? std::atoi(f) : 0;
+  }
+  const int lanes_blocks = axis == 1 ? (a.width + 127) / 128 : (a.height + 127) / 128;
+  int total = 0;
+  for (int k = 0; k < a.nseg; ++k) total += a.seg_n[k];
+  // enough CTAs for ~8 waves of 148 SMs x 3 resident CTAs; strips no shorter than 24 outputs
+  // (runs shorter than that are single strips)
+  const int want = (8 * 148 * 3 + lanes_blocks - 1) / lanes_blocks;
+  int strip = (total + want - 1) / want;
+  if (strip < 24) strip = 24;
+  if (strip_env > 0) strip = strip_env;
+  a.strip = strip;
+  int nstrips = 0;
+  for (int k = 0; k < a.nseg; ++k) {
+    a.seg_strip0[k] = nstrips;
+    nstrips += (a.seg_n[k] + strip - 1) / strip;
+  }
+  a.nstrips = nstrips;
+  nstrips += a.nborder;
+  if (nstrips <= 0 || nstrips > 65535 || lanes_blocks > 65535) return MB200_EUNSUPPORTED;
+  if (axis == 1) {
+    resize_v_stream_kernel<S, N><<<dim3(lanes_blocks, nstrips), 128, 0, s>>>(a);
+  } else if (slots_env == 3) {
+    constexpr int smem = 4 * 3 * kSlotBytes;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    resize_h_stream_kernel<S, N, 3><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a);
+  } else {
+    constexpr int smem = 4 * 4 * kSlotBytes;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    resize_h_stream_kernel<S, N, 4><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a);
+  }
+  return MB200_OK;
+}
+
+}  // namespace
+
+// Streams the uniform runs of one axis (RGBA only) and gathers the `nborder` remaining outputs in the
+// same launch.  MB200_EUNSUPPORTED => the caller uses the kernels of resize.cu for the whole axis.
+int launch_resize_stream(const float *src, size_t width, size_t height, float *dst, size_t out_n, int axis,
+                         int stride, int taps, int nseg, const int *seg_o, const int *seg_n, const int *seg_src,
+                         const double *d_wsets, int nborder, const int *d_border, const int *d_start,
+                         const int *d_count, const double *d_weights, void *stream) {
+  if (d_wsets == nullptr || nseg <= 0 || nseg > kMaxSegments) return MB200_EUNSUPPORTED;
+  if (width > 0x3fffffffull || height > 0x3fffffffull || out_n > 0x3fffffffull) return MB200_EUNSUPPORTED;
+  StreamArgs a{};
+  a.src = src; a.dst = dst;
+  a.width = static_cast<int>(width); a.height = static_cast<int>(height);
+  if (axis == 1) { a.out_w = a.width; a.out_h = static_cast<int>(out_n); a.in_n = a.height; }
+  else { a.out_w = static_cast<int>(out_n); a.out_h = a.height; a.in_n = a.width; }
+  a.nseg = nseg;
+  for (int k = 0; k < nseg; ++k) { a.seg_o[k] = seg_o[k]; a.seg_n[k] = seg_n[k]; a.seg_src[k] = seg_src[k]; }
+  a.wsets = d_wsets;
+  a.nborder = nborder; a.border = d_border; a.out_n = static_cast<int>(out_n);
+  a.start = d_start; a.count = d_count; a.weights = d_weights;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = MB200_EUNSUPPORTED;
+  if (stride == 2 && taps == 12) rc = launch_sn<2, 12>(a, axis, s);        // 3-lobe filters, 2x
+  else if (stride == 2 && taps == 8) rc = launch_sn<2, 8>(a, axis, s);     // 2-lobe / cubic filters, 2x
+  else if (stride == 2 && taps == 4) rc = launch_sn<2, 4>(a, axis, s);     // triangle, 2x
+  else if (stride == 3 && taps == 19) rc = launch_sn<3, 19>(a, axis, s);   // 3-lobe, 3x
+  else if (stride == 4 && taps == 24) rc = launch_sn<4, 24>(a, axis, s);   // 3-lobe, 4x
+  else if (stride == 4 && taps == 16) rc = launch_sn<4, 16>(a, axis, s);   // 2-lobe / cubic, 4x
+  if (rc != MB200_OK) return rc;
+  count_launch();
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "resize stream launch");
+  return MB200_OK;
+}
+
+}  // namespace mb200

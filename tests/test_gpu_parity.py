@@ -251,6 +251,33 @@ def test_resize_lanczos_2x_down_2048():
     assert (d == 0).mean() > 0.999
 
 
+# streaming kernels of resize_stream.cu: integer-ratio reductions (S, N) = (2,12) Lanczos, (2,8) Lanczos2 /
+# Mitchell / Catrom, (2,4) Triangle, (3,19), (4,24), (4,16); ragged sizes (rows not a multiple of 32,
+# columns not a multiple of 8), several strips per axis, borders through the gather kernels.
+@pytest.mark.parametrize("kind", ["noise", "alpha_blocks", "hdr"])
+@pytest.mark.parametrize("filt,ratio", [(22, 2), (24, 2), (12, 2), (11, 2), (3, 2), (22, 3), (22, 4), (24, 4), (12, 4)])
+def test_resize_streaming_kernels(filt, ratio, kind, monkeypatch):
+    ow, oh = 173, 131
+    w, h = ow * ratio, oh * ratio
+    src = make_image(w, h, 4, seed=97 + filt + ratio, kind=kind)
+    want = np.empty((oh, ow, 4), np.float32)
+    assert oracle().orc_resize(P(src), w, h, 4, P(want), ow, oh, filt) == 0
+    d = _dev(src)
+    n0 = im.launch_count()
+    got = _host(im.ResizeImage(d, ow, oh, filt))
+    streamed = im.launch_count() - n0
+    assert max_ulp(got, want) <= 1, (filt, ratio, kind)
+    monkeypatch.setenv("MB200_NO_RESIZE_STREAM", "1")
+    ref = _host(im.ResizeImage(d, ow, oh, filt))
+    assert streamed == 2                          # one launch per axis (borders ride along as extra CTAs)
+    assert max_ulp(got, ref) <= 1
+    # only one axis reduced: the other axis is a 1:1 pass through the gather kernel
+    monkeypatch.delenv("MB200_NO_RESIZE_STREAM")
+    want = np.empty((h, ow, 4), np.float32)
+    assert oracle().orc_resize(P(src), w, h, 4, P(want), ow, h, filt) == 0
+    assert max_ulp(_host(im.ResizeImage(d, ow, h, filt)), want) <= 1
+
+
 @pytest.mark.parametrize("ch", [3, 4])
 @pytest.mark.parametrize("frm,to", [(23, 11), (23, 26), (23, 21), (11, 23), (26, 23), (21, 23), (11, 26)])
 def test_colorspace(ch, frm, to):
