@@ -610,6 +610,10 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a
       {
         const unsigned ii = static_cast<unsigned>(min(max(isrc, 0), limit));
         pre[s] = __ldg(reinterpret_cast<const InT *>(base + static_cast<size_t>(ii) * step));
+        if (a.seg_w > 0) {      // L2 prefetch far ahead: the ring's LDGs then complete at L2 latency
+          const unsigned ip = static_cast<unsigned>(min(isrc + a.seg_w, limit));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + static_cast<size_t>(ip) * step));
+        }
         ++isrc;
       }
       double v0, v1;
@@ -765,6 +769,170 @@ __global__ void __launch_bounds__(128, MINB) conv_row_pair_kernel(const Conv1dAr
   }
 }
 
+// ---- pair stream kernel with a shared-memory prefetch ring (cp.async / LDGSTS), both axes.
+// Same arithmetic and thread mapping as conv_pair_kernel; only the way source samples reach the
+// thread differs.  With the register ring every in-flight LDG needs one of the six hardware
+// scoreboards, which it has to share with the F2F / SHFL / MUFU results of the output stage: ncu
+// showed 13 % (column) / 30 % (row) of all stall samples on output STGs that were waiting, through
+// such a shared scoreboard, for an unrelated prefetch issued a few hundred cycles earlier.  cp.async
+// groups are counted separately (DEPBAR.LE), cost no registers, and the ring depth is no longer tied
+// to the rotation length.
+//   AXIS 1: per-warp ring of NS rows x 256 B; a lane copies and later reads its own 8 bytes (no
+//           cross-lane hazard, no barrier); LDS issued one step ahead.
+//   AXIS 0: per-warp ring of 8-pixel chunks of its 16 rows (full 128-B line requests, 144-B row pitch
+//           => conflict-free LDS.64); edge replication is applied by the loader.
+template <int NT, int MINB, int AXIS, int IO>
+__global__ void __launch_bounds__(128, MINB) conv_pair_async_kernel(const Conv1dArgs a, const Taps<NT> taps) {
+  static_assert(IO == 0 || IO == 1, "float input only");
+  // The asm statements below are volatile (ordered among themselves: copy -> commit -> wait -> LDS) but
+  // carry no "memory" clobber: the ring is touched by nothing else, and the output STGs must stay free
+  // to sink below the next step's copies (otherwise every step exposes the F2F -> STG latency).
+  constexpr int UN = Ring<NT>::value;
+  constexpr unsigned kOutB = (IO == 1) ? 8u : 4u;
+  constexpr int NS = 16;                              // AXIS 1: rows in the ring
+  constexpr int NC = 4, kPitch = 144, kSlot = 16 * kPitch;   // AXIS 0: chunk slots
+  constexpr int kWarpBytes = AXIS == 1 ? NS * 256 : NC * kSlot;
+  __shared__ __align__(128) unsigned char ring_all[4 * kWarpBytes];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool odd = (lane & 1) != 0;
+  const int alpha_lane = lane | 1;
+  const unsigned ring_s = static_cast<unsigned>(__cvta_generic_to_shared(ring_all + warp * kWarpBytes));
+  const unsigned in_pitch = static_cast<unsigned>(a.rc) * 4u, out_pitch = static_cast<unsigned>(a.rc) * kOutB;
+  int first, nout;
+  char *outp;
+  unsigned ostep;
+  const int total = a.strip + NT - 1;
+
+  // ---- loader state
+  const char *lbase;            // AXIS 1: this lane's column; AXIS 0: image base
+  int limit, isrc0;
+  unsigned rd;                  // shared-memory address of this lane's next sample
+  int chunk = 0, px_in = 0, c0 = 0, nchunks = 0, lrow0 = 0;
+  if (AXIS == 1) {
+    const int npairs = a.rc >> 1;
+    const int pair_raw = blockIdx.x * 128 + threadIdx.x;
+    const bool active = pair_raw < npairs;
+    const int pair = active ? pair_raw : npairs - 1;
+    first = blockIdx.y * a.strip;
+    nout = active ? min(a.strip, a.height - first) : 0;
+    limit = a.height - 1;
+    ostep = out_pitch;
+    lbase = reinterpret_cast<const char *>(a.src) + static_cast<size_t>(pair) * 8;
+    outp = reinterpret_cast<char *>(a.dst) + static_cast<size_t>(pair) * (2 * kOutB) + static_cast<size_t>(first) * out_pitch;
+    isrc0 = first - a.off;
+    rd = ring_s + lane * 8;
+  } else {
+    const int row_raw = blockIdx.y * 64 + (threadIdx.x >> 1);
+    const bool active = row_raw < a.height;
+    first = blockIdx.x * a.strip;
+    nout = active ? min(a.strip, a.width - first) : 0;
+    limit = a.width - 1;
+    ostep = 4 * kOutB;
+    lbase = reinterpret_cast<const char *>(a.src);
+    outp = reinterpret_cast<char *>(a.dst) + static_cast<size_t>(active ? row_raw : 0) * out_pitch + (odd ? 2 * kOutB : 0) +
+           static_cast<size_t>(first) * ostep;
+    isrc0 = first - a.off;
+    c0 = isrc0 >= 0 ? isrc0 / 8 : -((7 - isrc0) / 8);            // floor(isrc0 / 8)
+    px_in = isrc0 - 8 * c0;
+    nchunks = (px_in + ((total + UN - 1) / UN) * UN + 7) / 8;
+    lrow0 = blockIdx.y * 64 + warp * 16;
+    rd = ring_s + (lane >> 1) * kPitch + (odd ? 8 : 0) + px_in * 16;
+  }
+  // AXIS 1: one row (step k) per group; AXIS 0: one 8-pixel chunk of the warp's 16 rows per group
+  auto issue = [&](int k) {
+    if (AXIS == 1) {
+      const unsigned ii = static_cast<unsigned>(min(max(isrc0 + k, 0), limit));
+      const unsigned dst = ring_s + static_cast<unsigned>(k & (NS - 1)) * 256u + lane * 8;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(lbase + static_cast<size_t>(ii) * in_pitch));
+    } else if (k < nchunks) {
+      const int x = min(max((c0 + k) * 8 + (lane & 7), 0), limit);
+      const unsigned slot = ring_s + static_cast<unsigned>(k & (NC - 1)) * kSlot;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = 4 * i + (lane >> 3);
+        const int y = min(lrow0 + r, a.height - 1);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot + r * kPitch + (lane & 7) * 16),
+                     "l"(lbase + static_cast<size_t>(y) * in_pitch + static_cast<size_t>(x) * 16));
+      }
+    }
+    asm volatile("cp.async.commit_group;" );
+  };
+  constexpr int kAhead = AXIS == 1 ? NS - 1 : NC;    // groups issued before the loop
+#pragma unroll
+  for (int k = 0; k < kAhead; ++k) issue(k);
+
+  double acc0[NT], acc1[NT];
+#pragma unroll
+  for (int q = 0; q < NT; ++q) { acc0[q] = 0.0; acc1[q] = 0.0; }
+  float2 vnext;
+  if (AXIS == 1) asm volatile("cp.async.wait_group %0;" ::"n"(NS - 2));
+  else { asm volatile("cp.async.wait_group %0;" ::"n"(NC - 1)); __syncwarp(); }
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(vnext.x), "=f"(vnext.y) : "r"(rd));
+
+  int j = -(NT - 1);
+  int step = 0;
+#pragma unroll 1
+  for (int mb = 0; mb < total; mb += UN) {       // UN unrolled steps, then rotate the accumulators by UN
+#pragma unroll
+    for (int s = 0; s < UN; ++s) {
+      const float2 vf = vnext;
+      // fetch the next step's sample and keep the ring full
+      if (AXIS == 1) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(NS - 3));      // row step+1 has landed
+        rd = ring_s + static_cast<unsigned>((step + 1) & (NS - 1)) * 256u + lane * 8;
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(vnext.x), "=f"(vnext.y) : "r"(rd));
+        issue(step + NS - 1);                                                  // into the slot read at step-1
+      } else {
+        rd += 16;
+        if (++px_in == 8) {                        // warp-uniform: chunk exhausted
+          px_in = 0;
+          __syncwarp();
+          issue(chunk + NC);
+          ++chunk;
+          asm volatile("cp.async.wait_group %0;" ::"n"(NC - 1));
+          __syncwarp();
+          rd = ring_s + static_cast<unsigned>(chunk & (NC - 1)) * kSlot + (lane >> 1) * kPitch + (odd ? 8 : 0);
+        }
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(vnext.x), "=f"(vnext.y) : "r"(rd));
+      }
+      ++step;
+      const float af = __shfl_sync(0xffffffffu, vf.y, alpha_lane);
+      const double da = static_cast<double>(af);
+      const double v0 = static_cast<double>(vf.x) * da;
+      const double v1 = static_cast<double>(vf.y) * (odd ? 1.0 : da);
+#pragma unroll
+      for (int q = 0; q < NT; ++q) {
+        const double k = taps.k[(s - q + NT) % NT];
+        acc0[q] = fma(k, v0, acc0[q]);
+        acc1[q] = fma(k, v1, acc1[q]);
+      }
+      const int qf = (s + 1) % NT;
+      const double sum0 = acc0[qf], sum1 = acc1[qf];
+      acc0[qf] = 0.0;
+      acc1[qf] = 0.0;
+      if (IO == 1) {
+        if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<double2 *>(outp) = make_double2(sum0, sum1);
+      } else {
+        const double gsum = shfl_double(sum1, alpha_lane);
+        const float2 out = finish_pair(odd, sum0, sum1, gsum);
+        if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<float2 *>(outp) = out;
+      }
+      if (j >= 0) outp += ostep;
+      ++j;
+    }
+    if (UN != NT) {
+      double t0[UN], t1[UN];
+#pragma unroll
+      for (int q = 0; q < UN; ++q) { t0[q] = acc0[q]; t1[q] = acc1[q]; }
+#pragma unroll
+      for (int q = 0; q < NT - UN; ++q) { acc0[q] = acc0[q + UN]; acc1[q] = acc1[q + UN]; }
+#pragma unroll
+      for (int q = 0; q < UN; ++q) { acc0[NT - UN + q] = t0[q]; acc1[NT - UN + q] = t1[q]; }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" );
+}
+
 // developer tuning knobs (environment, read on every launch; defaults are the tuned values)
 int tuning(const char *name, int fallback) {
   const char *v = getenv(name);
@@ -785,17 +953,24 @@ int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int nta
   if (pair_ok && axis == 1) {
     if constexpr (NT <= 33) {
       a.strip = tuning("MB200_COL_ROT", 16) * NT + 1;
+      a.seg_w = tuning("MB200_COL_PREFETCH", 16);   // rows of L2 prefetch ahead of the register ring
       dim3 grid((a.rc / 2 + 127) / 128, (a.height + a.strip - 1) / a.strip);
-      if (io == 1) conv_pair_kernel<NT, 2, 1, 1><<<grid, 128, 0, stream>>>(a, taps);
+      const bool async = tuning("MB200_PAIR_ASYNC_COL", 0) != 0;
+      if (io == 1 && async) conv_pair_async_kernel<NT, 2, 1, 1><<<grid, 128, 0, stream>>>(a, taps);
+      else if (io == 1) conv_pair_kernel<NT, 2, 1, 1><<<grid, 128, 0, stream>>>(a, taps);
       else if (io == 2) conv_pair_kernel<NT, 2, 1, 2><<<grid, 128, 0, stream>>>(a, taps);
+      else if (async) conv_pair_async_kernel<NT, 2, 1, 0><<<grid, 128, 0, stream>>>(a, taps);
       else conv_pair_kernel<NT, 2, 1, 0><<<grid, 128, 0, stream>>>(a, taps);
     }
   } else if (pair_ok && axis == 0) {
     if constexpr (NT <= 33) {
       a.strip = tuning("MB200_ROW_PAIR_ROT", 16) * NT + 1;
       dim3 grid((a.width + a.strip - 1) / a.strip, (a.height + 63) / 64);
-      if (io == 1) conv_pair_kernel<NT, 2, 0, 1><<<grid, 128, 0, stream>>>(a, taps);
+      const bool async = tuning("MB200_PAIR_ASYNC", 1) != 0;
+      if (io == 1 && async) conv_pair_async_kernel<NT, 2, 0, 1><<<grid, 128, 0, stream>>>(a, taps);
+      else if (io == 1) conv_pair_kernel<NT, 2, 0, 1><<<grid, 128, 0, stream>>>(a, taps);
       else if (io == 2) conv_pair_kernel<NT, 2, 0, 2><<<grid, 128, 0, stream>>>(a, taps);
+      else if (async && !tuning("MB200_ROW_PAIR_TMA", 0)) conv_pair_async_kernel<NT, 2, 0, 0><<<grid, 128, 0, stream>>>(a, taps);
       else if (tuning("MB200_ROW_PAIR_TMA", 0)) conv_row_pair_kernel<NT, 2><<<grid, 128, 0, stream>>>(a, taps);
       else conv_pair_kernel<NT, 2, 0, 0><<<grid, 128, 0, stream>>>(a, taps);
     }

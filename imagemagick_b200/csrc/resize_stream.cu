@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(128, 3) resize_v_stream_kernel(const StreamArg
   const int niter = (S * (st.nout - 1) + N + BODY - 1) / BODY;
   const size_t pitch = static_cast<size_t>(a.width) * 4;
   const float *col = a.src + static_cast<size_t>(x) * 4;
-  const int last = a.in_n - 1;
+  // loads past the strip's last tap (ring over-run, rounded-up last iteration) re-read that row from L1
+  const int last = min(a.in_n - 1, st.src0 + S * (st.nout - 1) + N - 1);
   int row = st.src0;                                 // source row of the next ring load
   float4 pre[PF];
 #pragma unroll
@@ -212,14 +213,16 @@ constexpr int kRowPitch = kChunkPx * 16 + 16;       // 144 B: (9*row + k) mod 8 
 constexpr int kSlotBytes = 32 * kRowPitch;          // 4608 B
 
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void *gptr) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// volatile orders these among themselves and with the LDS below; no "memory" clobber so that the
+// output stores stay free to move across them.
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int K>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K)); }
 
-template <int S, int N, int NSLOT>
-__global__ void __launch_bounds__(128, 3) resize_h_stream_kernel(const StreamArgs a) {
+template <int S, int N, int NSLOT, int MINB>
+__global__ void __launch_bounds__(128, MINB) resize_h_stream_kernel(const StreamArgs a) {
   using T = Rot<S, N>;
   constexpr int R = T::R, P = T::P, BODY = T::BODY;
   extern __shared__ __align__(128) unsigned char ring_all[];
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(128, 3) resize_h_stream_kernel(const StreamArg
   const int niter = (S * (st.nout - 1) + N + BODY - 1) / BODY;
   const int p0 = st.src0;                            // absolute source pixel of step 0
   const int c0 = p0 / kChunkPx;                      // first chunk (line aligned)
-  const int nchunks = (p0 + niter * BODY + kChunkPx - 1) / kChunkPx - c0;
+  const int nchunks = (p0 + S * (st.nout - 1) + N + kChunkPx - 1) / kChunkPx - c0;   // steps past the last tap read stale slots
   // loader role: instruction j copies pixel (lane & 7) of row 4j + (lane >> 3)
   const int lrow = lane >> 3, lpx = lane & 7;
   const size_t pitch_b = static_cast<size_t>(a.width) * 16;
@@ -273,20 +276,14 @@ __global__ void __launch_bounds__(128, 3) resize_h_stream_kernel(const StreamArg
   cp_async_wait<NSLOT - 1>();
   __syncwarp();
   unsigned rd = ring_s + lane * kRowPitch + px_in * 16;   // this lane's next LDS address (slot 0)
+  float4 vnext;                                            // sample of the next step (LDS one step ahead)
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(vnext.x), "=f"(vnext.y), "=f"(vnext.z), "=f"(vnext.w) : "r"(rd));
 #pragma unroll 1
   for (int t = 0; t < niter; ++t) {
 #pragma unroll
     for (int b = 0; b < BODY; ++b) {
       const int m = b % P;
-      float4 v;
-      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(rd));
-      feed<S, N>(acc, W, v, m);
-      const int qd = done_slot<S, N>(m);
-      if (qd >= 0) {
-        ++c;
-        if (c >= 0 && c < st.nout && active) *reinterpret_cast<float4 *>(outp) = finish_rgba(acc[qd]);
-        outp += 4;
-      }
+      const float4 v = vnext;
       rd += 16;
       if (++px_in == kChunkPx) {                    // warp-uniform: chunk exhausted
         px_in = 0;
@@ -296,6 +293,14 @@ __global__ void __launch_bounds__(128, 3) resize_h_stream_kernel(const StreamArg
         cp_async_wait<NSLOT - 1>();                 // chunk is complete; NSLOT-1 later ones stay in flight
         __syncwarp();
         rd = ring_s + static_cast<unsigned>(chunk % NSLOT) * kSlotBytes + lane * kRowPitch;
+      }
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(vnext.x), "=f"(vnext.y), "=f"(vnext.z), "=f"(vnext.w) : "r"(rd));
+      feed<S, N>(acc, W, v, m);
+      const int qd = done_slot<S, N>(m);
+      if (qd >= 0) {
+        ++c;
+        if (c >= 0 && c < st.nout && active) *reinterpret_cast<float4 *>(outp) = finish_rgba(acc[qd]);
+        outp += 4;
       }
     }
   }
@@ -331,16 +336,16 @@ int launch_sn(StreamArgs a, int axis, cudaStream_t s) {
   if (nstrips <= 0 || nstrips > 65535 || lanes_blocks > 65535) return MB200_EUNSUPPORTED;
   if (axis == 1) {
     resize_v_stream_kernel<S, N><<<dim3(lanes_blocks, nstrips), 128, 0, s>>>(a);
-  } else if (slots_env == 3) {
+  } else if (slots_env == 3) {                     // 4 CTAs / SM, 3-slot rings (221 KB of shared memory per SM)
     constexpr int smem = 4 * 3 * kSlotBytes;
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    resize_h_stream_kernel<S, N, 3><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a);
+    if (!attr) { cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    resize_h_stream_kernel<S, N, 3, 4><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a);
   } else {
     constexpr int smem = 4 * 4 * kSlotBytes;
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    resize_h_stream_kernel<S, N, 4><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a);
+    if (!attr) { cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    resize_h_stream_kernel<S, N, 4, 3><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a);
   }
   return MB200_OK;
 }
