@@ -8,6 +8,7 @@ include/magick_b200.h:
     MorphologyImage, AcquireKernelInfo                              morphology.c:4129/485
     ResizeImage                                                     resize.c:3761
     TransformImageColorspace                                        colorspace.c:1751
+    BilevelImage, BlackThresholdImage, WhiteThresholdImage, ClampImage  threshold.c:805/927/2518/1087
 
 An `Image` wraps the pixel cache: an (rows, columns, channels) float32 array of raw
 Quantum values (0..65535), either a NumPy array (host; every call stages through
@@ -231,6 +232,41 @@ def TransformImageColorspace(image: Image, colorspace: int) -> bool:
                                              image.colorspace, colorspace))
     image.colorspace = colorspace
     return True
+
+
+def _in_place(image: Image, dev_fn: str, host_fn: str, *args) -> bool:
+    lib = _lib.load()
+    if image.on_device:
+        _activate(image)
+        check(getattr(lib, dev_fn)(image._ptr(), image.columns, image.rows, image.channels, *args, _stream(image)))
+    else:
+        check(getattr(lib, host_fn)(image._ptr(), image.columns, image.rows, image.channels, *args))
+    return True
+
+
+def BilevelImage(image: Image, threshold: float) -> bool:
+    """MagickCore/threshold.c:805 -- in place; a non-gray image is re-tagged sRGB (:827)."""
+    ok = _in_place(image, "mb200_bilevel_image_dev", "mb200_bilevel_image", float(threshold))
+    if image.channels >= 3:
+        image.colorspace = sRGBColorspace
+    return ok
+
+
+def BlackThresholdImage(image: Image, thresholds: str) -> bool:
+    """MagickCore/threshold.c:927 -- in place."""
+    return _in_place(image, "mb200_black_threshold_image_dev", "mb200_black_threshold_image", int(image.colorspace),
+                     thresholds.encode())
+
+
+def WhiteThresholdImage(image: Image, thresholds: str) -> bool:
+    """MagickCore/threshold.c:2518 -- in place."""
+    return _in_place(image, "mb200_white_threshold_image_dev", "mb200_white_threshold_image", int(image.colorspace),
+                     thresholds.encode())
+
+
+def ClampImage(image: Image) -> bool:
+    """MagickCore/threshold.c:1087 -- in place."""
+    return _in_place(image, "mb200_clamp_image_dev", "mb200_clamp_image")
 
 
 def MorphologyPrimitive(image: Image, method: int, kernel: Union[str, KernelInfo], bias: float = 0.0):

@@ -600,3 +600,125 @@ int mb200_transform_colorspace(float *buf, size_t w, size_t h, int ch, int from,
 }
 
 }  // extern "C"
+
+// ---- threshold.c point operators ---------------------------------------------------------
+namespace {
+// The ParseGeometry step of Black/WhiteThresholdImage (threshold.c:955-985) for "v[,v[,v[,v]]][%]".
+int parse_thresholds(const char *spec, double (&t)[4]) {
+  if (spec == nullptr) return fail(MB200_EINVAL, "thresholds == NULL (the reference returns MagickTrue untouched)");
+  double v[4] = {0, 0, 0, 0};
+  int n = 0;
+  bool percent = false;
+  const char *p = spec;
+  while (*p) {
+    while (*p == ' ') ++p;
+    if (*p == '\0') break;
+    if (n == 4) return fail(MB200_EUNSUPPORTED, "threshold geometry '%s' has more than four values", spec);
+    char *end = nullptr;
+    v[n] = std::strtod(p, &end);
+    if (end == p) return fail(MB200_EUNSUPPORTED, "threshold geometry '%s' is not of the form v[,v[,v[,v]]][%%]", spec);
+    ++n;
+    p = end;
+    while (*p == ' ') ++p;
+    if (*p == '%') { percent = true; ++p; }
+    while (*p == ' ') ++p;
+    if (*p == ',') ++p;
+    else if (*p != '\0') return fail(MB200_EUNSUPPORTED, "threshold geometry '%s' is not of the form v[,v[,v[,v]]][%%]", spec);
+  }
+  if (n == 0) return fail(MB200_EUNSUPPORTED, "empty threshold geometry");
+  t[0] = v[0];
+  t[1] = n > 1 ? v[1] : v[0];
+  t[2] = n > 2 ? v[2] : v[0];
+  t[3] = n > 3 ? v[3] : 100.0;
+  if (percent)
+    for (double &x : t) x *= (65535.0 / 100.0);
+  return MB200_OK;
+}
+
+int threshold_dev(float *buf, size_t width, size_t height, int channels, int op, const double *t, void *stream) {
+  if (!buf || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "threshold: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  return launch_threshold(buf, width * height, channels, op, t, s);
+}
+
+int black_white_dev(float *buf, size_t width, size_t height, int channels, int colorspace, const char *thresholds, int op,
+                    void *stream) {
+  if (!buf || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "threshold: bad arguments");
+  if (channels < 3)
+    return fail(MB200_EUNSUPPORTED, "Black/WhiteThresholdImage promote gray images to sRGB (threshold.c:949)");
+  if (colorspace == MB200_RGBColorspace)
+    return fail(MB200_EUNSUPPORTED, "linear RGB: the intensity needs EncodePixelGamma (pixel.c:2421)");
+  double t[4];
+  const int rc = parse_thresholds(thresholds, t);
+  if (rc) return rc;
+  return threshold_dev(buf, width, height, channels, op, t, stream);
+}
+
+template <typename Op>
+int in_place_host(float *buf, size_t bytes, Op op) {
+  cudaStream_t s;
+  int rc = prepare(nullptr, &s);
+  if (rc) return rc;
+  StreamAlloc d(s);
+  rc = d.alloc(bytes);
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpyAsync(d.ptr, buf, bytes, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cuda_fail(e, "H2D");
+  rc = op(static_cast<float *>(d.ptr), s);
+  if (rc) { cudaStreamSynchronize(s); return rc; }
+  e = cudaMemcpyAsync(buf, d.ptr, bytes, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  return e == cudaSuccess ? MB200_OK : cuda_fail(e, "D2H");
+}
+}  // namespace
+
+extern "C" {
+
+int mb200_bilevel_image_dev(float *buf, size_t width, size_t height, int channels, double threshold, void *stream) {
+  const double t[4] = {threshold, 0, 0, 0};
+  return threshold_dev(buf, width, height, channels, 0, t, stream);
+}
+int mb200_black_threshold_image_dev(float *buf, size_t width, size_t height, int channels, int colorspace,
+                                    const char *thresholds, void *stream) {
+  return black_white_dev(buf, width, height, channels, colorspace, thresholds, 1, stream);
+}
+int mb200_white_threshold_image_dev(float *buf, size_t width, size_t height, int channels, int colorspace,
+                                    const char *thresholds, void *stream) {
+  return black_white_dev(buf, width, height, channels, colorspace, thresholds, 2, stream);
+}
+int mb200_clamp_image_dev(float *buf, size_t width, size_t height, int channels, void *stream) {
+  return threshold_dev(buf, width, height, channels, 3, nullptr, stream);
+}
+
+int mb200_bilevel_image(float *buf, size_t w, size_t h, int ch, double threshold) {
+  if (!buf || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "bilevel: bad arguments");
+  return in_place_host(buf, w * h * ch * sizeof(float),
+                       [&](float *d, cudaStream_t st) { return mb200_bilevel_image_dev(d, w, h, ch, threshold, st); });
+}
+int mb200_black_threshold_image(float *buf, size_t w, size_t h, int ch, int colorspace, const char *thresholds) {
+  if (!buf || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "black threshold: bad arguments");
+  double t[4];
+  if (ch < 3 || colorspace == MB200_RGBColorspace || parse_thresholds(thresholds, t) != MB200_OK)
+    return black_white_dev(buf, w, h, ch, colorspace, thresholds, 1, nullptr);   // reports the decline before staging
+  return in_place_host(buf, w * h * ch * sizeof(float), [&](float *d, cudaStream_t st) {
+    return mb200_black_threshold_image_dev(d, w, h, ch, colorspace, thresholds, st);
+  });
+}
+int mb200_white_threshold_image(float *buf, size_t w, size_t h, int ch, int colorspace, const char *thresholds) {
+  if (!buf || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "white threshold: bad arguments");
+  double t[4];
+  if (ch < 3 || colorspace == MB200_RGBColorspace || parse_thresholds(thresholds, t) != MB200_OK)
+    return black_white_dev(buf, w, h, ch, colorspace, thresholds, 2, nullptr);
+  return in_place_host(buf, w * h * ch * sizeof(float), [&](float *d, cudaStream_t st) {
+    return mb200_white_threshold_image_dev(d, w, h, ch, colorspace, thresholds, st);
+  });
+}
+int mb200_clamp_image(float *buf, size_t w, size_t h, int ch) {
+  if (!buf || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "clamp: bad arguments");
+  return in_place_host(buf, w * h * ch * sizeof(float),
+                       [&](float *d, cudaStream_t st) { return mb200_clamp_image_dev(d, w, h, ch, st); });
+}
+
+}  // extern "C"

@@ -76,4 +76,7 @@ int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to
 int launch_unsharp_combine(const float *src, float *blur_inout, size_t n, double gain,
                            double quantum_threshold, void *stream);
 
+// threshold.c point operators in place; op: 0 bilevel (t[0]), 1 black, 2 white (t = r,g,b,a), 3 clamp
+int launch_threshold(float *buf, size_t npixels, int channels, int op, const double *thresholds, void *stream);
+
 }  // namespace mb200

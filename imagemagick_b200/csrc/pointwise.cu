@@ -3,6 +3,8 @@
 // unsharp combine: the point pass of UnsharpMaskImage (MagickCore/effect.c:4310-4384):
 //   d = p - blur;  out = (|2d| < QuantumRange*threshold) ? p : p + gain*d     (double -> float)
 // applied to every channel (all carry the Update trait on the accelerated path).
+//
+// threshold point operators of MagickCore/threshold.c (see threshold_kernel below).
 #include "mb200_internal.h"
 
 #include <cuda_runtime.h>
@@ -37,7 +39,87 @@ __global__ void __launch_bounds__(256) unsharp_tail_kernel(const float *__restri
   blur[i] = static_cast<float>(pixel);
 }
 
+// threshold.c point operators, in place (BilevelImage :805, BlackThresholdImage :927, WhiteThresholdImage
+// :2518, ClampImage :1087).  Every channel (alpha included) is compared through the pixel's intensity
+// (pixel.c:2356, Rec709Luma on an sRGB / gray image), evaluated exactly as the reference does: three
+// products summed left to right in double with no contraction, so the comparison -- and therefore the
+// result -- is bit-identical.  op: 0 bilevel, 1 black, 2 white, 3 clamp.
+struct ThresholdArgs {
+  double t[4];     // bilevel: t[0]; black / white: red, green, blue, alpha
+  int op;
+};
+
+template <int CH>
+__global__ void __launch_bounds__(256) threshold_kernel(float *__restrict__ buf, size_t npixels, const ThresholdArgs a) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= npixels) return;
+  float v[CH];
+  if (CH == 4) {
+    const float4 t = reinterpret_cast<const float4 *>(buf)[i];
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[CH - 1] = t.w;
+  } else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) v[c] = buf[i * CH + c];
+  }
+  constexpr double kQR = 65535.0;
+  if (a.op == 3) {                                     // ClampPixel (pixel-accessor.h:35-46, HDRI)
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const double p = static_cast<double>(v[c]);
+      if (p < 0.0) v[c] = 0.0f;
+      else if (p >= kQR) v[c] = 65535.0f;
+    }
+  } else {
+    const double red = static_cast<double>(v[0]);
+    double pixel = red;
+    if (CH > 1) {
+      const double green = CH >= 3 ? static_cast<double>(v[1]) : red;
+      const double blue = CH >= 3 ? static_cast<double>(v[CH >= 3 ? 2 : 0]) : red;
+      pixel = __dadd_rn(__dadd_rn(__dmul_rn(0.212656, red), __dmul_rn(0.715158, green)), __dmul_rn(0.072186, blue));
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const bool is_alpha = (CH == 2 || CH == 4) && c == CH - 1;
+      const double t = a.op == 0 ? a.t[0] : (is_alpha ? a.t[3] : a.t[c < 3 ? c : 0]);
+      if (a.op == 0) v[c] = pixel <= t ? 0.0f : 65535.0f;
+      else if (a.op == 1) { if (pixel < t) v[c] = 0.0f; }
+      else { if (pixel > t) v[c] = 65535.0f; }
+    }
+  }
+  if (CH == 4) reinterpret_cast<float4 *>(buf)[i] = make_float4(v[0], v[1], v[2], v[CH - 1]);
+  else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) buf[i * CH + c] = v[c];
+  }
+}
+
 }  // namespace
+
+int launch_threshold(float *buf, size_t npixels, int channels, int op, const double *thresholds, void *stream) {
+  if (npixels == 0) return MB200_OK;
+  ThresholdArgs a{};
+  for (int k = 0; k < 4; ++k) a.t[k] = thresholds ? thresholds[k] : 0.0;
+  a.op = op;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t blocks = (npixels + 255) / 256;
+  if (blocks > 0x7fffffffull) return fail(MB200_EINVAL, "threshold: image too large");
+  const unsigned grid = static_cast<unsigned>(blocks);
+  const bool aligned = (reinterpret_cast<uintptr_t>(buf) & 15) == 0;
+  switch (channels) {
+    case 1: threshold_kernel<1><<<grid, 256, 0, s>>>(buf, npixels, a); break;
+    case 2: threshold_kernel<2><<<grid, 256, 0, s>>>(buf, npixels, a); break;
+    case 3: threshold_kernel<3><<<grid, 256, 0, s>>>(buf, npixels, a); break;
+    case 4:
+      if (!aligned) return fail(MB200_EINVAL, "threshold: RGBA buffers must be 16-byte aligned");
+      threshold_kernel<4><<<grid, 256, 0, s>>>(buf, npixels, a);
+      break;
+    default: return fail(MB200_EINVAL, "threshold: 1..4 channels");
+  }
+  count_launch();
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "threshold launch");
+  return MB200_OK;
+}
 
 int launch_unsharp_combine(const float *src, float *blur_inout, size_t n, double gain, double quantum_threshold,
                            void *stream) {

@@ -207,6 +207,24 @@ MB200_API int mb200_resize_image_dev(const float *src, size_t width, size_t heig
 MB200_API int mb200_transform_colorspace_dev(float *buf, size_t width, size_t height,
     int channels, int from_colorspace, int to_colorspace, void *stream);
 
+/* Threshold point operators of MagickCore/threshold.c, in place on `buf`, bit exact.
+   BilevelImage (:805): every channel (alpha included) := intensity <= threshold ? 0 : QuantumRange,
+   intensity = GetPixelIntensity (pixel.c:2356, Rec709Luma; the gray sample for Gray / Gray+Alpha).
+   A non-gray image is re-tagged sRGB by the reference (:827); the caller owns that tag. */
+MB200_API int mb200_bilevel_image_dev(float *buf, size_t width, size_t height, int channels,
+    double threshold, void *stream);
+/* BlackThresholdImage (:927) / WhiteThresholdImage (:2518).  `thresholds` is the reference's
+   geometry string "v[,v[,v[,v]]][%]" = red[,green[,blue[,alpha]]] (missing green/blue default to
+   red, alpha to 100, '%' scales all by QuantumRange/100, :955-985).  Gray images (which the
+   reference first promotes to sRGB, :949), linear-RGB images (`colorspace` == MB200_RGBColorspace:
+   the intensity then needs EncodePixelGamma) and other geometry syntax return MB200_EUNSUPPORTED. */
+MB200_API int mb200_black_threshold_image_dev(float *buf, size_t width, size_t height, int channels,
+    int colorspace, const char *thresholds, void *stream);
+MB200_API int mb200_white_threshold_image_dev(float *buf, size_t width, size_t height, int channels,
+    int colorspace, const char *thresholds, void *stream);
+/* ClampImage (:1087): ClampPixel on every channel (HDRI: below 0 -> 0, >= QuantumRange -> QuantumRange). */
+MB200_API int mb200_clamp_image_dev(float *buf, size_t width, size_t height, int channels, void *stream);
+
 /* ---------------------------------------------- host-buffer operators ---- */
 /* Same operators on HOST buffers: stage into HBM, run, copy back, synchronise.
    These are what the MagickCore shim calls with the pixel-cache pointers
@@ -225,6 +243,12 @@ MB200_API int mb200_resize_image(const float *src, size_t width, size_t height, 
     float *dst, size_t out_width, size_t out_height, int filter);
 MB200_API int mb200_transform_colorspace(float *buf, size_t width, size_t height, int channels,
     int from_colorspace, int to_colorspace);
+MB200_API int mb200_bilevel_image(float *buf, size_t width, size_t height, int channels, double threshold);
+MB200_API int mb200_black_threshold_image(float *buf, size_t width, size_t height, int channels,
+    int colorspace, const char *thresholds);
+MB200_API int mb200_white_threshold_image(float *buf, size_t width, size_t height, int channels,
+    int colorspace, const char *thresholds);
+MB200_API int mb200_clamp_image(float *buf, size_t width, size_t height, int channels);
 
 #if defined(__cplusplus)
 }

@@ -972,3 +972,58 @@ int orc_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to)
   }
   return 0;
 }
+
+
+/* ------------------------------------------------------------------------------------------
+   threshold.c point operators (in place).
+   BilevelImage :805-897, BlackThresholdImage :927-1053, WhiteThresholdImage :2518-2644,
+   ClampImage :1087-1190; GetPixelIntensity pixel.c:2356-2451 with the default
+   (Rec709Luma) method on an sRGB / gray image: 0.212656*R+0.715158*G+0.072186*B evaluated
+   left to right in double (no contraction); one-channel images return the gray value itself
+   (:2366); for Gray+Alpha the green/blue accessors resolve to the gray sample (channel map
+   offsets default to 0), so the same expression is evaluated on (g,g,g).
+   image->channel_mask == AllChannels, so every channel (alpha included: it carries the Update
+   trait, pixel.c:6370) is compared through the pixel's INTENSITY, against its own threshold.
+   op: 0 bilevel (thr[0]); 1 black, 2 white (thr = red, green, blue, alpha as left by the
+   ParseGeometry step :955-985); 3 clamp (pixel-accessor.h:35-46, HDRI: no rounding).
+   ------------------------------------------------------------------------------------------ */
+static double pixel_intensity(const float *q, int ch)
+{
+  double red = (double) q[0], green, blue;
+  if (ch == 1) return red;
+  green = ch >= 3 ? (double) q[1] : red;
+  blue = ch >= 3 ? (double) q[2] : red;
+  return 0.212656 * red + 0.715158 * green + 0.072186 * blue;
+}
+
+int orc_threshold(float *buf, size_t w, size_t h, int ch, int op, const double *thr)
+{
+  long i, n = (long) (w * h);
+  if (ch < 1 || ch > 4 || op < 0 || op > 3) return -1;
+  if ((op == 1 || op == 2) && ch < 3) return -1;   /* gray images are promoted to sRGB there (:949) */
+#pragma omp parallel for schedule(static)
+  for (i = 0; i < n; i++) {
+    float *q = buf + (size_t) i * ch;
+    int c;
+    if (op == 3) {
+      for (c = 0; c < ch; c++) {
+        double pixel = (double) q[c];
+        if (pixel < 0.0) q[c] = 0.0f;
+        else if (pixel >= QR) q[c] = (float) QR;
+        else q[c] = (float) pixel;
+      }
+      continue;
+    }
+    {
+      const double pixel = pixel_intensity(q, ch);
+      for (c = 0; c < ch; c++) {
+        const int is_alpha = (ch == 2 || ch == 4) && c == ch - 1;
+        const double t = op == 0 ? thr[0] : (is_alpha ? thr[3] : thr[c]);
+        if (op == 0) q[c] = (float) (pixel <= t ? 0.0 : QR);
+        else if (op == 1) { if (pixel < t) q[c] = 0.0f; }
+        else { if (pixel > t) q[c] = (float) QR; }
+      }
+    }
+  }
+  return 0;
+}

@@ -165,6 +165,30 @@ int ref_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to)
   END
 }
 
+/* threshold.c point operators, in place.  op: 0 BilevelImage(threshold), 1 BlackThresholdImage(thresholds),
+   2 WhiteThresholdImage(thresholds), 3 ClampImage.  The channel count must survive the call (gray
+   images are promoted to sRGB by the black/white operators: rc = -2 then). */
+__attribute__((visibility("default")))
+int ref_threshold(float *buf, size_t w, size_t h, int ch, int op, double threshold, const char *thresholds)
+{
+  BEGIN
+  MagickBooleanType ok = MagickFalse;
+  im = make_image(buf, w, h, ch, -1, ex);
+  if (im)
+    {
+      switch (op)
+      {
+        case 0: ok = BilevelImage(im, threshold, ex); break;
+        case 1: ok = BlackThresholdImage(im, thresholds, ex); break;
+        case 2: ok = WhiteThresholdImage(im, thresholds, ex); break;
+        case 3: ok = ClampImage(im, ex); break;
+        default: break;
+      }
+      if (ok != MagickFalse) rc = export_image(im, buf, w, h, ch, ex);
+    }
+  END
+}
+
 /* Kernel generation probe: returns the idx-th kernel of the list the string
    parses to (after the same normalisation ConvolveImage's callers apply is NOT
    applied here -- this is AcquireKernelInfo's raw output). */

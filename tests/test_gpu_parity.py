@@ -311,6 +311,54 @@ def test_config4_lab_then_dilate_512():
     assert max_ulp(got2, want2) == 0
 
 
+THRESHOLD_CASES = [(0, 32768.0, ""), (0, 12345.678, ""), (3, 0.0, ""), (1, 0.0, "50%"), (2, 0.0, "50%"),
+                   (1, 0.0, "20000,30000,40000"), (2, 0.0, "20%,30%,40%,50%"), (1, 0.0, "30000, 20000 ,40000,35000"),
+                   (2, 0.0, "45000")]
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["noise", "hdr", "gradient"])
+def test_threshold_point_ops_bit_exact(ch, kind):
+    """threshold.c point operators: bit exact (north_star: integer morphology / threshold), device and
+    host-buffer entry points, samples exactly on the threshold, NaN through ClampImage."""
+    src = make_image(203, 77, ch, seed=15 + ch, kind=kind)
+    src[0, :10, :] = 32768.0
+    src[1, :10, :] = 32767.5
+    src[2, 3, 0] = np.nan
+    for op, thr, spec in THRESHOLD_CASES:
+        def run(img):
+            if op == 0:
+                return im.BilevelImage(img, thr)
+            if op == 3:
+                return im.ClampImage(img)
+            return (im.BlackThresholdImage if op == 1 else im.WhiteThresholdImage)(img, spec)
+        if op in (1, 2) and ch < 3:
+            with pytest.raises(im.MagickB200Error) as e:
+                run(_dev(src.copy()))
+            assert e.value.code == -5                 # decline: the shim leaves it to the CPU path
+            continue
+        want = util.orc_threshold(src, op, [thr] if op in (0, 3) else util.parse_thresholds(spec.replace(" ", "")))
+        d = _dev(src.copy())
+        assert run(d) is True
+        got = _host(d)
+        assert np.array_equal(got.view(np.int32), want.view(np.int32)), (op, thr, spec)
+        h = im.Image(src.copy())
+        assert run(h) is True
+        assert np.array_equal(h.pixels.view(np.int32), want.view(np.int32)), (op, thr, spec)
+
+
+def test_threshold_declines():
+    img = _dev(make_image(16, 16, 4, seed=1))
+    img.colorspace = im.RGBColorspace
+    for bad in ("50%x20", "a,b", "1,2,3,4,5", ""):
+        with pytest.raises(im.MagickB200Error) as e:
+            im.BlackThresholdImage(_dev(make_image(16, 16, 4, seed=1)), bad)
+        assert e.value.code == -5
+    with pytest.raises(im.MagickB200Error) as e:
+        im.WhiteThresholdImage(img, "50%")            # linear RGB needs EncodePixelGamma for the intensity
+    assert e.value.code == -5
+
+
 def test_errors_are_loud():
     src = make_image(16, 16, 4)
     with pytest.raises(im.MagickB200Error):

@@ -63,6 +63,30 @@ def test_colorspace_bit_exact(frm, to):
     assert max_ulp(a, b) == 0
 
 
+THRESHOLD_CASES = [(0, 32768.0, ""), (0, 12345.678, ""), (3, 0.0, ""), (1, 0.0, "50%"), (2, 0.0, "50%"),
+                   (1, 0.0, "20000,30000,40000"), (2, 0.0, "20%,30%,40%,50%"), (1, 0.0, "30000,20000,40000,35000"),
+                   (2, 0.0, "45000")]
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["noise", "hdr", "gradient"])
+def test_threshold_point_ops_bit_exact(ch, kind):
+    """threshold.c BilevelImage / BlackThresholdImage / WhiteThresholdImage / ClampImage, incl. samples
+    exactly on the threshold and the gray -> sRGB promotion the black/white operators apply."""
+    src = make_image(97, 61, ch, seed=5, kind=kind)
+    src[0, :10, :] = 32768.0
+    src[1, :10, :] = 32767.5
+    for op, thr, spec in THRESHOLD_CASES:
+        got = src.copy()
+        rc = util.ref().ref_threshold(P(got), 97, 61, ch, op, thr, spec.encode())
+        if op in (1, 2) and ch < 3:
+            assert rc == -2            # channel count changed: gray image promoted to sRGB (threshold.c:949)
+            continue
+        assert rc == 0
+        want = util.orc_threshold(src, op, [thr] if op in (0, 3) else util.parse_thresholds(spec))
+        assert max_ulp(got, want) == 0, (op, thr, spec)
+
+
 def test_thread_count_independence():
     """results do not depend on the OpenMP thread count."""
     src = make_image(128, 96, 4, seed=1)

@@ -58,6 +58,7 @@ def oracle() -> C.CDLL:
         o.orc_optimal_kernel_width_1d.restype = _sz
         o.orc_optimal_kernel_width_2d.argtypes = [_d, _d]
         o.orc_optimal_kernel_width_2d.restype = _sz
+        o.orc_threshold.argtypes = [_fp, _sz, _sz, _i, _i, C.POINTER(_d)]
         o.orc_set_threads.argtypes = [_i]
         _oracle = o
     return _oracle
@@ -82,6 +83,7 @@ def ref() -> C.CDLL:
         r.ref_colorspace.argtypes = [_fp, _sz, _sz, _i, _i, _i]
         r.ref_kernel.argtypes = [C.c_char_p, _i, C.POINTER(_d), _sz, C.POINTER(_sz), C.POINTER(_sz),
                                  C.POINTER(_l), C.POINTER(_l)]
+        r.ref_threshold.argtypes = [_fp, _sz, _sz, _i, _i, _d, C.c_char_p]
         r.ref_version.restype = C.c_char_p
         r.ref_set_threads.argtypes = [_i]
         _ref = r
@@ -158,3 +160,24 @@ def make_image(w: int, h: int, ch: int, seed: int = 42, kind: str = "noise") -> 
     elif kind == "binary":
         a = np.where(a > 40000.0, np.float32(65535.0), np.float32(0.0)).astype(np.float32)
     return np.ascontiguousarray(a)
+
+
+def parse_thresholds(spec: str):
+    """The ParseGeometry step of Black/WhiteThresholdImage (threshold.c:955-985) for the
+    'v[,v[,v[,v]]][%]' forms: returns [red, green, blue, alpha] in Quantum units."""
+    pct = "%" in spec
+    vals = [float(t) for t in spec.replace("%", "").split(",") if t.strip()]
+    rho = vals[0]
+    thr = [rho, vals[1] if len(vals) > 1 else rho, vals[2] if len(vals) > 2 else rho,
+           vals[3] if len(vals) > 3 else 100.0]
+    if pct:
+        thr = [t * (65535.0 / 100.0) for t in thr]
+    return thr
+
+
+def orc_threshold(src: np.ndarray, op: int, thr) -> np.ndarray:
+    h, w, ch = src.shape
+    out = src.copy()
+    arr = (_d * 4)(*([float(t) for t in thr] + [0.0] * (4 - len(thr))))
+    assert oracle().orc_threshold(P(out), w, h, ch, op, arr) == 0
+    return out
