@@ -4,9 +4,10 @@
 
   Link an application / the MagickCore library with
       -Wl,--wrap=BlurImage,--wrap=GaussianBlurImage,--wrap=ConvolveImage,--wrap=UnsharpMaskImage,\
-          --wrap=MorphologyImage,--wrap=ResizeImage,--wrap=TransformImageColorspace
+          --wrap=MorphologyImage,--wrap=ResizeImage,--wrap=TransformImageColorspace,\
+          --wrap=BilevelImage,--wrap=BlackThresholdImage,--wrap=WhiteThresholdImage,--wrap=ClampImage
   and every caller of those exported functions (effect.c:765/1709/1170/4256, morphology.c:4129,
-  resize.c:3761, colorspace.c:1751) reaches __wrap_X below.  Each wrapper follows the accelerate
+  resize.c:3761, colorspace.c:1751, threshold.c:805/927/2518/1087) reaches __wrap_X below.  Each wrapper follows the accelerate
   hook contract of effect.c:783-787 / resize.c:3818-3826: try the GPU; if the image is not
   eligible or the GPU path declines (returns NULL / MagickFalse without raising), run the stock
   CPU implementation (__real_X).  B200Accelerate*Image() are the same functions with the
@@ -261,6 +262,51 @@ MagickBooleanType B200AccelerateTransformImageColorspace(Image *image, const Col
   return SetImageColorspace(image, colorspace, exception);  /* colorspace.c:1051 */
 }
 
+/* ---- threshold.c point operators (in place, bit exact) ---------------------------------------------- */
+static MagickBooleanType default_intensity(const Image *image)
+{
+  return ((image->intensity == UndefinedPixelIntensityMethod) ||
+          (image->intensity == Rec709LumaPixelIntensityMethod)) ? MagickTrue : MagickFalse;
+}
+
+/* op: 0 BilevelImage, 1 BlackThresholdImage, 2 WhiteThresholdImage, 3 ClampImage */
+static MagickBooleanType run_threshold(Image *image, int op, double threshold, const char *thresholds,
+                                       ExceptionInfo *exception)
+{
+  Quantum *q;
+  int ch, rc, cs;
+  if (mb200_device_count() <= 0) return MagickFalse;
+  if (op != 3 && default_intensity(image) == MagickFalse) return MagickFalse;
+  if (image->colorspace == LinearGRAYColorspace) return MagickFalse;       /* intensity would need EncodePixelGamma */
+  if ((op == 1 || op == 2) && thresholds == (const char *) NULL) return MagickFalse;
+  ch = b200_channels(image);
+  if (ch == 0) return MagickFalse;
+  if ((op == 1 || op == 2) && (ch < 3 || image->colorspace == RGBColorspace)) return MagickFalse;  /* :949, pixel.c:2421 */
+  if (op == 0 && image->colorspace != GRAYColorspace && image->colorspace != LinearGRAYColorspace)
+    (void) SetImageColorspace(image, sRGBColorspace, exception);            /* threshold.c:827 */
+  if (GetPixelChannels(image) != (size_t) ch) return MagickFalse;
+  q = GetAuthenticPixels(image, 0, 0, image->columns, image->rows, exception);
+  if (q == (Quantum *) NULL) return MagickFalse;
+  cs = image->colorspace == RGBColorspace ? MB200_RGBColorspace : MB200_sRGBColorspace;
+  switch (op) {
+    case 0: rc = mb200_bilevel_image((float *) q, image->columns, image->rows, ch, threshold); break;
+    case 1: rc = mb200_black_threshold_image((float *) q, image->columns, image->rows, ch, cs, thresholds); break;
+    case 2: rc = mb200_white_threshold_image((float *) q, image->columns, image->rows, ch, cs, thresholds); break;
+    default: rc = mb200_clamp_image((float *) q, image->columns, image->rows, ch); break;
+  }
+  if (rc != MB200_OK) return MagickFalse;     /* nothing was written back: the CPU path starts from the same pixels */
+  return SyncAuthenticPixels(image, exception);
+}
+
+MagickBooleanType B200AccelerateBilevelImage(Image *image, const double threshold, ExceptionInfo *exception)
+{ return run_threshold(image, 0, threshold, (const char *) NULL, exception); }
+MagickBooleanType B200AccelerateBlackThresholdImage(Image *image, const char *thresholds, ExceptionInfo *exception)
+{ return run_threshold(image, 1, 0.0, thresholds, exception); }
+MagickBooleanType B200AccelerateWhiteThresholdImage(Image *image, const char *thresholds, ExceptionInfo *exception)
+{ return run_threshold(image, 2, 0.0, thresholds, exception); }
+MagickBooleanType B200AccelerateClampImage(Image *image, ExceptionInfo *exception)
+{ return run_threshold(image, 3, 0.0, (const char *) NULL, exception); }
+
 /* ---- ld --wrap entry points ------------------------------------------------------------------------------ */
 extern Image *__real_BlurImage(const Image *, const double, const double, ExceptionInfo *);
 extern Image *__real_GaussianBlurImage(const Image *, const double, const double, ExceptionInfo *);
@@ -271,6 +317,10 @@ extern Image *__real_MorphologyImage(const Image *, const MorphologyMethod, cons
                                      ExceptionInfo *);
 extern Image *__real_ResizeImage(const Image *, const size_t, const size_t, const FilterType, ExceptionInfo *);
 extern MagickBooleanType __real_TransformImageColorspace(Image *, const ColorspaceType, ExceptionInfo *);
+extern MagickBooleanType __real_BilevelImage(Image *, const double, ExceptionInfo *);
+extern MagickBooleanType __real_BlackThresholdImage(Image *, const char *, ExceptionInfo *);
+extern MagickBooleanType __real_WhiteThresholdImage(Image *, const char *, ExceptionInfo *);
+extern MagickBooleanType __real_ClampImage(Image *, ExceptionInfo *);
 
 static long b200_hits = 0, b200_fallbacks = 0;
 static int b200_enabled = -1;       /* -1: not yet read from the environment */
@@ -339,4 +389,30 @@ MagickBooleanType __wrap_TransformImageColorspace(Image *image, const Colorspace
     b200_fallbacks++;
   }
   return __real_TransformImageColorspace(image, colorspace, exception);
+}
+
+#define TRY_BOOL(expr) do { if (b200_on()) { if ((expr) != MagickFalse) { b200_hits++; return MagickTrue; } b200_fallbacks++; } } while (0)
+
+MagickBooleanType __wrap_BilevelImage(Image *image, const double threshold, ExceptionInfo *exception)
+{
+  TRY_BOOL(B200AccelerateBilevelImage(image, threshold, exception));
+  return __real_BilevelImage(image, threshold, exception);
+}
+
+MagickBooleanType __wrap_BlackThresholdImage(Image *image, const char *thresholds, ExceptionInfo *exception)
+{
+  TRY_BOOL(B200AccelerateBlackThresholdImage(image, thresholds, exception));
+  return __real_BlackThresholdImage(image, thresholds, exception);
+}
+
+MagickBooleanType __wrap_WhiteThresholdImage(Image *image, const char *thresholds, ExceptionInfo *exception)
+{
+  TRY_BOOL(B200AccelerateWhiteThresholdImage(image, thresholds, exception));
+  return __real_WhiteThresholdImage(image, thresholds, exception);
+}
+
+MagickBooleanType __wrap_ClampImage(Image *image, ExceptionInfo *exception)
+{
+  TRY_BOOL(B200AccelerateClampImage(image, exception));
+  return __real_ClampImage(image, exception);
 }

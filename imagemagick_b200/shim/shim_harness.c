@@ -18,6 +18,10 @@ extern Image *__real_UnsharpMaskImage(const Image *, const double, const double,
 extern Image *__real_MorphologyImage(const Image *, const MorphologyMethod, const ssize_t, const KernelInfo *, ExceptionInfo *);
 extern Image *__real_ResizeImage(const Image *, const size_t, const size_t, const FilterType, ExceptionInfo *);
 extern MagickBooleanType __real_TransformImageColorspace(Image *, const ColorspaceType, ExceptionInfo *);
+extern MagickBooleanType __real_BilevelImage(Image *, const double, ExceptionInfo *);
+extern MagickBooleanType __real_BlackThresholdImage(Image *, const char *, ExceptionInfo *);
+extern MagickBooleanType __real_WhiteThresholdImage(Image *, const char *, ExceptionInfo *);
+extern MagickBooleanType __real_ClampImage(Image *, ExceptionInfo *);
 extern long B200ShimHits(void), B200ShimFallbacks(void);
 extern void B200ShimEnable(int);
 
@@ -92,6 +96,23 @@ int main(void)
   if (TransformImageColorspace(a, LabColorspace, ex) == MagickFalse || a->colorspace != LabColorspace) failures++;
   B200ShimEnable(0); (void) __real_TransformImageColorspace(b, LabColorspace, ex); B200ShimEnable(1);
   CHECK("TransformImageColorspace sRGB->Lab", 1, a, b);
+  /* threshold.c point operators: in place, bit exact */
+  a = CloneImage(rgba, 0, 0, MagickTrue, ex); b = CloneImage(rgba, 0, 0, MagickTrue, ex);
+  if (BilevelImage(a, 30000.0, ex) == MagickFalse) failures++;
+  B200ShimEnable(0); (void) __real_BilevelImage(b, 30000.0, ex); B200ShimEnable(1);
+  CHECK("BilevelImage(30000) RGBA", 0, a, b);
+  a = CloneImage(rgba, 0, 0, MagickTrue, ex); b = CloneImage(rgba, 0, 0, MagickTrue, ex);
+  if (BlackThresholdImage(a, "40%,50%,60%", ex) == MagickFalse) failures++;
+  B200ShimEnable(0); (void) __real_BlackThresholdImage(b, "40%,50%,60%", ex); B200ShimEnable(1);
+  CHECK("BlackThresholdImage RGBA", 0, a, b);
+  a = CloneImage(rgb, 0, 0, MagickTrue, ex); b = CloneImage(rgb, 0, 0, MagickTrue, ex);
+  if (WhiteThresholdImage(a, "45000", ex) == MagickFalse) failures++;
+  B200ShimEnable(0); (void) __real_WhiteThresholdImage(b, "45000", ex); B200ShimEnable(1);
+  CHECK("WhiteThresholdImage RGB", 0, a, b);
+  a = CloneImage(rgba, 0, 0, MagickTrue, ex); b = CloneImage(rgba, 0, 0, MagickTrue, ex);
+  if (ClampImage(a, ex) == MagickFalse) failures++;
+  B200ShimEnable(0); (void) __real_ClampImage(b, ex); B200ShimEnable(1);
+  CHECK("ClampImage RGBA", 0, a, b);
   {
     /* a declined case must silently take the CPU path: tiled virtual pixels are not eligible */
     long fb = B200ShimFallbacks();
@@ -103,7 +124,7 @@ int main(void)
     t = DestroyImage(t);
   }
   printf("gpu hits %ld, cpu fallbacks %ld\n", B200ShimHits(), B200ShimFallbacks());
-  if (B200ShimHits() < 9) { printf("FAIL: operators did not reach the GPU path\n"); failures++; }
+  if (B200ShimHits() < 13) { printf("FAIL: operators did not reach the GPU path\n"); failures++; }
   rgba = DestroyImage(rgba); rgb = DestroyImage(rgb);
   ex = DestroyExceptionInfo(ex);
   MagickCoreTerminus();
