@@ -185,6 +185,29 @@ struct Stage { int primitive; const mb200_kernel_info *kernel; };
 
 int morphology_apply(const float *src, float *dst, size_t w, size_t h, int ch, int method, long iterations,
                      const mb200_kernel_info *kernel, double bias, cudaStream_t s) {
+  // Methods that end in "difference with the original" (staging :3813-3893, CompositeImage :3995-4012):
+  // the morphological part is one of the methods below, then one Difference composite.
+  if (method == MB200_EdgeInMorphology || method == MB200_EdgeOutMorphology || method == MB200_EdgeMorphology ||
+      method == MB200_TopHatMorphology || method == MB200_BottomHatMorphology) {
+    if (kernel->next != nullptr)
+      return fail(MB200_EUNSUPPORTED, "compound difference methods with a multi-kernel list stay on the CPU path");
+    const size_t npix = w * h;
+    if (method == MB200_EdgeMorphology) {          // dilate; erode the ORIGINAL; canvas = eroded, source = dilated
+      StreamAlloc dil(s);
+      int rc = dil.alloc(npix * static_cast<size_t>(ch) * sizeof(float));
+      if (rc) return rc;
+      rc = morphology_apply(src, static_cast<float *>(dil.ptr), w, h, ch, MB200_DilateMorphology, iterations, kernel, bias, s);
+      if (!rc) rc = morphology_apply(src, dst, w, h, ch, MB200_ErodeMorphology, iterations, kernel, bias, s);
+      if (!rc) rc = launch_composite_difference(dst, static_cast<const float *>(dil.ptr), npix, ch, s);
+      return rc;
+    }
+    const int base = method == MB200_EdgeInMorphology ? MB200_ErodeMorphology
+                     : method == MB200_EdgeOutMorphology ? MB200_DilateMorphology
+                     : method == MB200_TopHatMorphology ? MB200_OpenMorphology : MB200_CloseMorphology;
+    int rc = morphology_apply(src, dst, w, h, ch, base, iterations, kernel, bias, s);
+    if (!rc) rc = launch_composite_difference(dst, src, npix, ch, s);
+    return rc;
+  }
   if (iterations == 0) return fail(MB200_EINVAL, "iterations == 0 is a null operation (reference returns NULL)");
   size_t kernel_limit = iterations < 0 ? (w > h ? w : h) : static_cast<size_t>(iterations);
   int stage_limit = 1;
@@ -194,7 +217,7 @@ int morphology_apply(const float *src, float *dst, size_t w, size_t h, int ch, i
     case MB200_ConvolveMorphology: case MB200_CorrelateMorphology:
     case MB200_ErodeMorphology: case MB200_DilateMorphology: break;
     default:
-      return fail(MB200_EUNSUPPORTED, "morphology method %d needs CompositeImage or a sequential primitive; "
+      return fail(MB200_EUNSUPPORTED, "morphology method %d is a sequential / intensity primitive; "
                   "not on the GPU path", method);
   }
   mb200_kernel_info *reflected = nullptr;

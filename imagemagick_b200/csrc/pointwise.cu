@@ -93,7 +93,78 @@ __global__ void __launch_bounds__(256) threshold_kernel(float *__restrict__ buf,
   }
 }
 
+// CompositeImage(canvas, source, DifferenceCompositeOp, clip_to_self, 0, 0) as MorphologyApply calls it for
+// the Edge / TopHat / BottomHat methods (morphology.c:3995-4012; composite.c:2377-3562 with the default
+// compose:sync / compose:clamp): same-size images, default channel traits.  Evaluated in the reference's
+// operation order with unfused double arithmetic => bit exact.
+//   Sa, Da = QS*alpha (1 without alpha);  alpha = RoundToUnity(Sa+Da-Sa*Da);  gamma = PerceptibleReciprocal(alpha)
+//   colour: QR*gamma*(Sca+Dca-2*min(Sca*Da,Dca*Sa)), Sca = QS*Sa*Sc, Dca = QS*Da*Dc;  alpha: QR*|Sa-Da|;  ClampPixel.
+template <int CH>
+__global__ void __launch_bounds__(256) difference_kernel(float *__restrict__ canvas, const float *__restrict__ source,
+                                                         size_t npixels) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= npixels) return;
+  constexpr bool kAlpha = (CH == 2 || CH == 4);
+  constexpr double kQR = 65535.0, kQS = 1.0 / 65535.0, kEps = 1.0e-12;
+  float q[CH], p[CH];
+  if (CH == 4) {
+    const float4 a = reinterpret_cast<const float4 *>(canvas)[i], b = __ldg(reinterpret_cast<const float4 *>(source) + i);
+    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[CH - 1] = a.w;
+    p[0] = b.x; p[1] = b.y; p[2] = b.z; p[CH - 1] = b.w;
+  } else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { q[c] = canvas[i * CH + c]; p[c] = __ldg(source + i * CH + c); }
+  }
+  const double Sa = __dmul_rn(kQS, kAlpha ? static_cast<double>(p[CH - 1]) : 65535.0);
+  const double Da = __dmul_rn(kQS, kAlpha ? static_cast<double>(q[CH - 1]) : 65535.0);
+  double alpha = __dsub_rn(__dadd_rn(Sa, Da), __dmul_rn(Sa, Da));
+  alpha = alpha < 0.0 ? 0.0 : (alpha > 1.0 ? 1.0 : alpha);
+  const double sign = alpha < 0.0 ? -1.0 : 1.0;
+  const double gamma = __dmul_rn(sign, alpha) >= kEps ? __ddiv_rn(1.0, alpha) : __ddiv_rn(sign, kEps);
+  float out[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    double pixel;
+    if (kAlpha && c == CH - 1) pixel = __dmul_rn(kQR, fabs(__dsub_rn(Sa, Da)));
+    else {
+      const double Sca = __dmul_rn(__dmul_rn(kQS, Sa), static_cast<double>(p[c]));
+      const double Dca = __dmul_rn(__dmul_rn(kQS, Da), static_cast<double>(q[c]));
+      const double a = __dmul_rn(Sca, Da), b = __dmul_rn(Dca, Sa);
+      pixel = __dmul_rn(__dmul_rn(kQR, gamma), __dsub_rn(__dadd_rn(Sca, Dca), __dmul_rn(2.0, a < b ? a : b)));
+    }
+    out[c] = pixel < 0.0 ? 0.0f : (pixel >= kQR ? 65535.0f : static_cast<float>(pixel));
+  }
+  if (CH == 4) reinterpret_cast<float4 *>(canvas)[i] = make_float4(out[0], out[1], out[2], out[CH - 1]);
+  else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) canvas[i * CH + c] = out[c];
+  }
+}
+
 }  // namespace
+
+int launch_composite_difference(float *canvas, const float *source, size_t npixels, int channels, void *stream) {
+  if (npixels == 0) return MB200_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t blocks = (npixels + 255) / 256;
+  if (blocks > 0x7fffffffull) return fail(MB200_EINVAL, "composite: image too large");
+  const unsigned grid = static_cast<unsigned>(blocks);
+  switch (channels) {
+    case 1: difference_kernel<1><<<grid, 256, 0, s>>>(canvas, source, npixels); break;
+    case 2: difference_kernel<2><<<grid, 256, 0, s>>>(canvas, source, npixels); break;
+    case 3: difference_kernel<3><<<grid, 256, 0, s>>>(canvas, source, npixels); break;
+    case 4:
+      if (((reinterpret_cast<uintptr_t>(canvas) | reinterpret_cast<uintptr_t>(source)) & 15) != 0)
+        return fail(MB200_EINVAL, "composite: RGBA buffers must be 16-byte aligned");
+      difference_kernel<4><<<grid, 256, 0, s>>>(canvas, source, npixels);
+      break;
+    default: return fail(MB200_EINVAL, "composite: 1..4 channels");
+  }
+  count_launch();
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "composite launch");
+  return MB200_OK;
+}
 
 int launch_threshold(float *buf, size_t npixels, int channels, int op, const double *thresholds, void *stream) {
   if (npixels == 0) return MB200_OK;

@@ -74,6 +74,8 @@ static MagickBooleanType has_artifact(const Image *image, const char *const *nam
 
 static const char *const morphology_artifacts[] = { "convolve:bias", "convolve:scale",
   "morphology:compose", "morphology:showKernel", "debug", (const char *) NULL };
+static const char *const compose_artifacts[] = { "compose:clamp", "compose:sync", "compose:args",
+  "compose:outside-overlay", "compose:clip-to-self", (const char *) NULL };
 static const char *const filter_artifacts[] = { "filter:filter", "filter:window", "filter:sigma",
   "filter:alpha", "filter:kaiser-beta", "filter:kaiser-alpha", "filter:lobes", "filter:blur",
   "filter:support", "filter:win-support", "filter:b", "filter:c", "filter:verbose",
@@ -194,7 +196,12 @@ Image *B200AccelerateMorphologyImage(const Image *image, const MorphologyMethod 
   switch (method) {
     case ConvolveMorphology: case CorrelateMorphology: case ErodeMorphology: case DilateMorphology:
     case OpenMorphology: case CloseMorphology: case SmoothMorphology: break;
-    default: return (Image *) NULL;          /* needs CompositeImage / sequential primitives: CPU */
+    case EdgeInMorphology: case EdgeOutMorphology: case EdgeMorphology: case TopHatMorphology:
+    case BottomHatMorphology:                /* end in CompositeImage(Difference), morphology.c:3995-4012 */
+      if (kernel->next != (KernelInfo *) NULL) return (Image *) NULL;
+      if (has_artifact(image, compose_artifacts) != MagickFalse) return (Image *) NULL;
+      break;
+    default: return (Image *) NULL;          /* sequential / intensity primitives: CPU */
   }
   a.method = (int) method; a.iterations = (long) iterations; a.kernel = kernel;
   return run_same_size(image, op_morphology, &a, exception);

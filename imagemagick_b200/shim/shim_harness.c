@@ -91,6 +91,8 @@ int main(void)
   k = AcquireKernelInfo("Disk:3", ex);
   CHECK("MorphologyImage Dilate Disk:3", 0, MorphologyImage(rgba, DilateMorphology, 1, k, ex), CPU(__real_MorphologyImage(rgba, DilateMorphology, 1, k, ex)));
   CHECK("MorphologyImage Erode x2 Disk:3", 0, MorphologyImage(rgb, ErodeMorphology, 2, k, ex), CPU(__real_MorphologyImage(rgb, ErodeMorphology, 2, k, ex)));
+  CHECK("MorphologyImage Edge Disk:3 RGBA", 0, MorphologyImage(rgba, EdgeMorphology, 1, k, ex), CPU(__real_MorphologyImage(rgba, EdgeMorphology, 1, k, ex)));
+  CHECK("MorphologyImage TopHat Disk:3 RGB", 0, MorphologyImage(rgb, TopHatMorphology, 1, k, ex), CPU(__real_MorphologyImage(rgb, TopHatMorphology, 1, k, ex)));
   k = DestroyKernelInfo(k);
   a = CloneImage(rgba, 0, 0, MagickTrue, ex); b = CloneImage(rgba, 0, 0, MagickTrue, ex);
   if (TransformImageColorspace(a, LabColorspace, ex) == MagickFalse || a->colorspace != LabColorspace) failures++;
@@ -124,7 +126,7 @@ int main(void)
     t = DestroyImage(t);
   }
   printf("gpu hits %ld, cpu fallbacks %ld\n", B200ShimHits(), B200ShimFallbacks());
-  if (B200ShimHits() < 13) { printf("FAIL: operators did not reach the GPU path\n"); failures++; }
+  if (B200ShimHits() < 15) { printf("FAIL: operators did not reach the GPU path\n"); failures++; }
   rgba = DestroyImage(rgba); rgb = DestroyImage(rgb);
   ex = DestroyExceptionInfo(ex);
   MagickCoreTerminus();

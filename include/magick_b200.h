@@ -180,8 +180,11 @@ MB200_API int mb200_morphology_primitive_dev(const float *src, float *dst, size_
 
 /* MorphologyImage / MorphologyApply (MagickCore/morphology.c:4129, :3634) with the
    default compose (re-iterate kernel lists): iterations (<0 = until unchanged),
-   compound methods Open / Close / Smooth and Correlate (Edge, TopHat and
-   BottomHat variants need CompositeImage and return MB200_EUNSUPPORTED). */
+   compound methods Open / Close / Smooth, Correlate, and -- for single kernels -- the
+   "difference" methods EdgeIn / EdgeOut / Edge / TopHat / BottomHat, whose final
+   CompositeImage(..., DifferenceCompositeOp, ...) step (:3995-4012) runs as one point
+   kernel (bit exact).  HitAndMiss / Thinning / Thicken / Distance / Voronoi / the
+   *Intensity methods return MB200_EUNSUPPORTED. */
 MB200_API int mb200_morphology_image_dev(const float *src, float *dst, size_t width,
     size_t height, int channels, int method, long iterations,
     const mb200_kernel_info *kernel, double bias, void *stream);

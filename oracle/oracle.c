@@ -419,8 +419,90 @@ long orc_morphology_primitive(const float *src, float *dst, size_t w, size_t h, 
   return changed / update_channels(ch);
 }
 
-/* morphology.c:3634-4077 MorphologyApply, compose == None (re-iterate) */
+/* composite.c:1439 CompositeImage(canvas, source, DifferenceCompositeOp, clip_to_self = MagickTrue, 0, 0)
+   for two images of the same size and channel layout, default artifacts (compose:sync and
+   compose:clamp true, :1529-1536), every channel with its default traits -- the call MorphologyApply
+   makes for the Edge / TopHat / BottomHat methods (morphology.c:3995-4012).  Per pixel (:2377-3562):
+     Sa, Da = QuantumScale*alpha (1 for images without alpha)      alpha = RoundToUnity(Sa+Da-Sa*Da)
+     colour : Sca = QS*Sa*Sc, Dca = QS*Da*Dc, gamma = PerceptibleReciprocal(alpha)
+              pixel = QR*gamma*(Sca+Dca-2*min(Sca*Da,Dca*Sa))                        (:2922-2932)
+     alpha  : pixel = QR*|Sa-Da|                                                       (:2635-2639)
+     q = ClampPixel(pixel)                                                             (:2708, :3562) */
+static double perceptible_reciprocal(double x)
+{
+  const double sign = x < 0.0 ? -1.0 : 1.0;
+  if ((sign * x) >= EPS) return 1.0 / x;
+  return sign / EPS;
+}
+
+static float clamp_pixel(double pixel)
+{
+  if (pixel < 0.0) return 0.0f;
+  if (pixel >= QR) return (float) QR;
+  return (float) pixel;
+}
+
+static void composite_difference(float *canvas, const float *source, size_t w, size_t h, int ch)
+{
+  const long n = (long) (w * h);
+  const int has_alpha = (ch == 2 || ch == 4);
+  long i;
+#pragma omp parallel for schedule(static)
+  for (i = 0; i < n; i++) {
+    float *q = canvas + (size_t) i * ch;
+    const float *p = source + (size_t) i * ch;
+    const double Sa = QS * (has_alpha ? (double) p[ch - 1] : 65535.0);
+    const double Da = QS * (has_alpha ? (double) q[ch - 1] : 65535.0);
+    double alpha = Sa + Da - Sa * Da;
+    int c;
+    alpha = alpha < 0.0 ? 0.0 : (alpha > 1.0 ? 1.0 : alpha);
+    for (c = 0; c < ch; c++) {
+      double pixel;
+      if (has_alpha && c == ch - 1) pixel = QR * fabs(Sa - Da);
+      else {
+        const double Sc = (double) p[c], Dc = (double) q[c];
+        const double Sca = QS * Sa * Sc, Dca = QS * Da * Dc;
+        const double gamma = perceptible_reciprocal(alpha);
+        const double a = Sca * Da, b = Dca * Sa;
+        pixel = QR * gamma * (Sca + Dca - 2.0 * (a < b ? a : b));
+      }
+      q[c] = clamp_pixel(pixel);
+    }
+  }
+}
+
+static int morphology_apply_basic(const float *src, float *dst, size_t w, size_t h, int ch,
+                                  int method, long iterations, const orc_kernel *kernels, int nk,
+                                  double bias);
+
+/* morphology.c:3634-4077 MorphologyApply, compose == None (re-iterate).  The methods that end in
+   "difference with the original" (:3813-3893 staging, :3995-4012 composite) are single-kernel only. */
 int orc_morphology_apply(const float *src, float *dst, size_t w, size_t h, int ch,
+                         int method, long iterations, const orc_kernel *kernels, int nk,
+                         double bias)
+{
+  const size_t n = w * h * (size_t) ch;
+  int rc;
+  if (method < ORC_EDGE_IN || method > ORC_BOTTOMHAT)
+    return morphology_apply_basic(src, dst, w, h, ch, method, iterations, kernels, nk, bias);
+  if (nk != 1) return -1;
+  if (method == ORC_EDGE) {                /* dilate, keep; erode the ORIGINAL; canvas = eroded, source = dilated */
+    float *dil = (float *) malloc(n * sizeof(float));
+    if (!dil) return -1;
+    rc = morphology_apply_basic(src, dil, w, h, ch, ORC_DILATE, iterations, kernels, 1, bias);
+    if (rc == 0) rc = morphology_apply_basic(src, dst, w, h, ch, ORC_ERODE, iterations, kernels, 1, bias);
+    if (rc == 0) composite_difference(dst, dil, w, h, ch);
+    free(dil);
+    return rc;
+  }
+  rc = morphology_apply_basic(src, dst, w, h, ch,
+                              method == ORC_EDGE_IN ? ORC_ERODE : method == ORC_EDGE_OUT ? ORC_DILATE :
+                              method == ORC_TOPHAT ? ORC_OPEN : ORC_CLOSE, iterations, kernels, 1, bias);
+  if (rc == 0) composite_difference(dst, src, w, h, ch);
+  return rc;
+}
+
+static int morphology_apply_basic(const float *src, float *dst, size_t w, size_t h, int ch,
                          int method, long iterations, const orc_kernel *kernels, int nk,
                          double bias)
 {

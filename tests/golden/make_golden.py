@@ -41,6 +41,19 @@ def main():
                     dst = np.empty_like(src)
                     assert r.ref_morphology(P(src), P(dst), W, H, ch, method, 1, kname.encode()) == 0
                     out[f"{tag}/{mname}_{kname}"] = dst
+            for method, mname in ((13, "edgein"), (14, "edgeout"), (15, "edge"), (16, "tophat"), (17, "bottomhat")):
+                dst = np.empty_like(src)            # morphology.c:3995-4012: ends in CompositeImage(Difference)
+                assert r.ref_morphology(P(src), P(dst), W, H, ch, method, 1, b"Disk:3") == 0
+                out[f"{tag}/{mname}_Disk:3"] = dst
+            for op, thr, spec, tname in ((0, 30000.0, "", "bilevel_30000"), (3, 0.0, "", "clamp"),
+                                         (1, 0.0, "40%,50%,60%", "black_40%,50%,60%"), (2, 0.0, "45000", "white_45000")):
+                if op in (1, 2) and ch < 3:
+                    continue                        # gray images are promoted to sRGB (threshold.c:949)
+                buf = (src - 9000.0).astype(np.float32) if op == 3 else src.copy()
+                if op == 3:
+                    out[f"{tag}/clamp_src"] = buf.copy()
+                assert r.ref_threshold(P(buf), W, H, ch, op, thr, spec.encode()) == 0
+                out[f"{tag}/threshold_{tname}"] = buf
             dst = np.empty_like(src)
             assert r.ref_convolve(P(src), P(dst), W, H, ch, b"3x3: 1,2,0.5 0,-1,nan 3,0.25,-2") == 0
             out[f"{tag}/convolve_user3x3"] = dst

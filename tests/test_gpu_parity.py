@@ -311,6 +311,25 @@ def test_config4_lab_then_dilate_512():
     assert max_ulp(got2, want2) == 0
 
 
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["noise", "alpha_blocks", "hdr"])
+def test_difference_morphology_methods_bit_exact(ch, kind):
+    """EdgeIn / EdgeOut / Edge / TopHat / BottomHat: erode/dilate stages + the Difference composite of
+    morphology.c:3995-4012, bit exact (selection ops + unfused double point arithmetic)."""
+    src = make_image(150, 97, ch, seed=50 + ch, kind=kind)
+    for kname, kargs in (("Disk:3", ("disk", 3, 1, 0, 0)), ("Rectangle:4x2+3+0", ("rectangle", 4, 2, 3, 0))):
+        k = util.orc_kernel(*kargs)
+        for method, its in ((13, 1), (14, 1), (15, 1), (16, 1), (17, 1), (15, 2), (17, 2)):
+            want = util.orc_morphology(src, method, its, [k])
+            got = _host(im.MorphologyImage(_dev(src), method, its, kname))
+            assert max_ulp(got, want) == 0, (kname, method, its)
+    got = im.MorphologyImage(im.Image(src), im.EdgeMorphology, 1, "Disk:3").pixels     # host-buffer entry point
+    assert max_ulp(got, util.orc_morphology(src, 15, 1, [util.orc_kernel("disk", 3, 1, 0, 0)])) == 0
+    with pytest.raises(im.MagickB200Error) as e:                                        # multi-kernel list: decline
+        im.MorphologyImage(_dev(src), im.EdgeMorphology, 1, "Disk:3;Disk:2")
+    assert e.value.code == -5
+
+
 THRESHOLD_CASES = [(0, 32768.0, ""), (0, 12345.678, ""), (3, 0.0, ""), (1, 0.0, "50%"), (2, 0.0, "50%"),
                    (1, 0.0, "20000,30000,40000"), (2, 0.0, "20%,30%,40%,50%"), (1, 0.0, "30000, 20000 ,40000,35000"),
                    (2, 0.0, "45000")]

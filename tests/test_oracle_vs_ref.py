@@ -48,7 +48,8 @@ def test_morphology_bit_exact(name, args):
     assert np.array_equal(mine[~np.isnan(mine)], ref_vals[~np.isnan(ref_vals)])
     for ch in (1, 2, 4):
         src = make_image(40, 29, ch, seed=3)
-        for method, its in ((3, 1), (4, 1), (4, 2), (8, 1), (9, 1), (12, 1), (3, -1)):
+        for method, its in ((3, 1), (4, 1), (4, 2), (8, 1), (9, 1), (12, 1), (3, -1),
+                            (13, 1), (14, 1), (15, 1), (16, 1), (17, 1), (15, 2), (17, 3)):   # Edge*/TopHat/BottomHat
             a = np.empty_like(src)
             assert util.ref().ref_morphology(P(src), P(a), 40, 29, ch, method, its, name.encode()) == 0
             assert max_ulp(a, util.orc_morphology(src, method, its, [k])) == 0, (name, ch, method, its)
@@ -61,6 +62,19 @@ def test_colorspace_bit_exact(frm, to):
     assert util.ref().ref_colorspace(P(a), 64, 48, 4, frm, to) == 0
     assert oracle().orc_colorspace(P(b), 64, 48, 4, frm, to) == 0
     assert max_ulp(a, b) == 0
+
+
+@pytest.mark.parametrize("kind", ["alpha_blocks", "hdr"])
+def test_difference_methods_bit_exact_on_awkward_pixels(kind):
+    """EdgeIn/EdgeOut/Edge/TopHat/BottomHat end in CompositeImage(Difference) (morphology.c:3995-4012):
+    transparent regions (PerceptibleReciprocal), values outside 0..QuantumRange (ClampPixel)."""
+    k = util.orc_kernel("disk", 3, 1, 0, 0)
+    for ch in (2, 3, 4):
+        src = make_image(61, 43, ch, seed=21, kind=kind)
+        for method in (13, 14, 15, 16, 17):
+            a = np.empty_like(src)
+            assert util.ref().ref_morphology(P(src), P(a), 61, 43, ch, method, 1, b"Disk:3") == 0
+            assert max_ulp(a, util.orc_morphology(src, method, 1, [k])) == 0, (ch, method)
 
 
 THRESHOLD_CASES = [(0, 32768.0, ""), (0, 12345.678, ""), (3, 0.0, ""), (1, 0.0, "50%"), (2, 0.0, "50%"),
