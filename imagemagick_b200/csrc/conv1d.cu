@@ -549,7 +549,7 @@ __device__ __forceinline__ float2 finish_pair(bool odd, double sum0, double sum1
 // 2 = raw double sums in, float Quantum out (second half).  With IO 1 + 2 a separable 2-D kernel
 // (e.g. "gaussian:RxS") is evaluated with kw + kh instead of kw * kh taps per sample while keeping the
 // intermediate in double, i.e. without the float rounding a two-kernel list would introduce.
-template <int NT, int MINB, int AXIS, int IO>
+template <int NT, int MINB, int AXIS, int IO, bool L2PF = false>
 __global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a, const Taps<NT> taps) {
   constexpr int PF = Ring<NT>::value;
   constexpr unsigned kInB = (IO == 2) ? 8u : 4u, kOutB = (IO == 1) ? 8u : 4u;   // bytes per component
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a
       {
         const unsigned ii = static_cast<unsigned>(min(max(isrc, 0), limit));
         pre[s] = __ldg(reinterpret_cast<const InT *>(base + static_cast<size_t>(ii) * step));
-        if (a.seg_w > 0) {      // L2 prefetch far ahead: the ring's LDGs then complete at L2 latency
+        if (L2PF) {             // L2 prefetch far ahead: the ring's LDGs then complete at L2 latency
           const unsigned ip = static_cast<unsigned>(min(isrc + a.seg_w, limit));
           asm volatile("prefetch.global.L2 [%0];" ::"l"(base + static_cast<size_t>(ip) * step));
         }
@@ -953,14 +953,16 @@ int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int nta
   if (pair_ok && axis == 1) {
     if constexpr (NT <= 33) {
       a.strip = tuning("MB200_COL_ROT", 16) * NT + 1;
-      a.seg_w = tuning("MB200_COL_PREFETCH", 16);   // rows of L2 prefetch ahead of the register ring
+      a.seg_w = 16;                                  // rows of L2 prefetch ahead of the register ring (L2PF kernels)
       dim3 grid((a.rc / 2 + 127) / 128, (a.height + a.strip - 1) / a.strip);
-      const bool async = tuning("MB200_PAIR_ASYNC_COL", 0) != 0;
-      if (io == 1 && async) conv_pair_async_kernel<NT, 2, 1, 1><<<grid, 128, 0, stream>>>(a, taps);
-      else if (io == 1) conv_pair_kernel<NT, 2, 1, 1><<<grid, 128, 0, stream>>>(a, taps);
-      else if (io == 2) conv_pair_kernel<NT, 2, 1, 2><<<grid, 128, 0, stream>>>(a, taps);
+      // NT = 33 is FP64-bound: the register-ring kernel (+ L2 prefetch) wins; shorter windows are closer to
+      // the HBM roof and gain from the cp.async ring (sigma=2: 1.36 -> 1.22 ms for the whole blur).
+      const bool async = tuning("MB200_PAIR_ASYNC_COL", NT < 33 ? 1 : 0) != 0 && tuning("MB200_PAIR_ASYNC", 1) != 0;
+      if (io == 2) conv_pair_kernel<NT, 2, 1, 2><<<grid, 128, 0, stream>>>(a, taps);
+      else if (io == 1 && async) conv_pair_async_kernel<NT, 2, 1, 1><<<grid, 128, 0, stream>>>(a, taps);
+      else if (io == 1) conv_pair_kernel<NT, 2, 1, 1, NT == 33><<<grid, 128, 0, stream>>>(a, taps);
       else if (async) conv_pair_async_kernel<NT, 2, 1, 0><<<grid, 128, 0, stream>>>(a, taps);
-      else conv_pair_kernel<NT, 2, 1, 0><<<grid, 128, 0, stream>>>(a, taps);
+      else conv_pair_kernel<NT, 2, 1, 0, NT == 33><<<grid, 128, 0, stream>>>(a, taps);
     }
   } else if (pair_ok && axis == 0) {
     if constexpr (NT <= 33) {

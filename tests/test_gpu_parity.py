@@ -381,7 +381,7 @@ def test_threshold_declines():
 def test_errors_are_loud():
     src = make_image(16, 16, 4)
     with pytest.raises(im.MagickB200Error):
-        im.MorphologyImage(_dev(src), im.EdgeMorphology, 1, "Disk:1")     # unsupported -> decline
+        im.MorphologyImage(_dev(src), 18, 1, "Disk:1")                    # HitAndMiss: sequential primitive -> decline
     with pytest.raises(im.MagickB200Error):
         im.ResizeImage(_dev(src), 8, 8, im.JincFilter)
     with pytest.raises(im.MagickB200Error):
