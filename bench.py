@@ -8,8 +8,8 @@ A "step" is one pass of the hot path over one synthetic image per GPU:
 
 metric  = input Mpixels/s (8192*8192 pixels per image per step), whole job over all ranks.
 value   : inputs already resident in HBM when the timed region starts.
-e2e     : the same through the public API with HOST (pinned) buffers, H2D + D2H inside the
-          timed region.
+e2e     : the same through the C-ABI with HOST (pinned) buffers: mb200_upload, the _dev operators,
+          mb200_download -- H2D + D2H inside the timed region.
 roofline: the dominant kernels are the two 1-D convolution passes of BlurImage; algorithmic
           bytes per launch = 32 B/pixel (16 read + 16 written) x 8192^2 pixels.
 cpu_baseline / --impl reference: the reference's own CPU implementation (ImageMagick 7.1.1-45
@@ -45,7 +45,7 @@ SIZE = 8192
 SIGMA = 4.0
 LANCZOS = 22
 METRIC = "Mpixels/s on 8K RGBA Gaussian-blur σ=4 + Lanczos 2×; % HBM roofline"
-CPU_SAMPLE = 2048          # the CPU arms run the same pipeline on a CPU_SAMPLE^2 image per step
+CPU_SAMPLE = 4096          # the CPU arms run the same pipeline on a CPU_SAMPLE^2 image per step (~2 s each)
 
 
 def measured_peak():
@@ -252,31 +252,51 @@ def run_gpu(args):
     ms_per_step = total_ms / args.steps
     value = world * W * H / ms_per_step / 1e3           # Mpixels/s over all ranks
 
-    # ---- end to end through the public API with pinned host buffers.  Two streams alternate so that
-    # the H2D copy of image i+1 overlaps the kernels + D2H of image i (PCIe is full duplex); every
-    # step still uploads its own 1.07 GB input and reads its own result back.
-    host_in = [torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True) for _ in range(2)]
-    for hbuf in host_in:
-        hbuf.copy_(src.pixels)
-    host_out = [torch.empty((job.out_rows, job.out_columns, 4), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    # ---- end to end through the C-ABI with HOST buffers (include/magick_b200.h): pinned host memory from
+    # mb200_malloc_host, HBM from mb200_malloc, and per step  mb200_upload -> mb200_convolve_image_dev ->
+    # mb200_resize_image_dev -> mb200_download.  Two streams alternate so that the H2D copy of image i+1
+    # overlaps the kernels + D2H of image i (PCIe is full duplex); every step still uploads its own 1.07 GB
+    # input and reads its own 0.27 GB result back.
+    from imagemagick_b200 import _lib
+    lib = _lib.load()
+    in_bytes, out_bytes = W * H * 16, job.out_columns * job.out_rows * 16
+    vp = C.c_void_p
+
+    def c_alloc(fn, nbytes):
+        p = vp()
+        _lib.check(fn(C.byref(p), nbytes))
+        return p
+
+    host_in = [c_alloc(lib.mb200_malloc_host, in_bytes) for _ in range(2)]
+    host_out = [c_alloc(lib.mb200_malloc_host, out_bytes) for _ in range(2)]
+    d_in = [c_alloc(lib.mb200_malloc, in_bytes) for _ in range(2)]
+    d_blur = [c_alloc(lib.mb200_malloc, in_bytes) for _ in range(2)]
+    d_out = [c_alloc(lib.mb200_malloc, out_bytes) for _ in range(2)]
+    for hbuf in host_in:                                     # the step's input lives in host memory
+        _lib.check(lib.mb200_download(hbuf, vp(src.pixels.data_ptr()), in_bytes, None))
+    _lib.check(lib.mb200_synchronize(None))
     streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
 
     def step_e2e(i):
         k = i & 1
-        with torch.cuda.stream(streams[k]):
-            d = im.Image(host_in[k].to(dev, non_blocking=True))
-            b = im.ConvolveImage(d, blur_kernel)
-            r = im.ResizeImage(b, job.out_columns, job.out_rows, job.resize_filter)
-            host_out[k].copy_(r.pixels, non_blocking=True)
+        st = vp(streams[k].cuda_stream)
+        _lib.check(lib.mb200_upload(d_in[k], host_in[k], in_bytes, st))
+        _lib.check(lib.mb200_convolve_image_dev(d_in[k], d_blur[k], W, H, 4, blur_kernel._ptr, st))
+        _lib.check(lib.mb200_resize_image_dev(d_blur[k], W, H, 4, d_out[k], job.out_columns, job.out_rows,
+                                              job.resize_filter, st))
+        _lib.check(lib.mb200_download(host_out[k], d_out[k], out_bytes, st))
 
     e2e_steps = max(2, min(args.steps, 6))
     step_e2e(0)
     step_e2e(1)
     torch.cuda.synchronize()
     mdist.barrier()
-    t0 = time.perf_counter()
     a, b_ = ev(), ev()
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream())
     a.record()
+    for st in streams:
+        st.wait_event(a)
     for i in range(e2e_steps):
         step_e2e(i)
     for st in streams:
@@ -287,6 +307,19 @@ def run_gpu(args):
     clocks.__exit__()
     e2e_ms = mdist.max_over_ranks(a.elapsed_time(b_) / e2e_steps, device=dev)
     e2e_value = world * W * H / e2e_ms / 1e3
+    # the e2e result equals the device-resident result (same kernels, same bits)
+    chk = np.ctypeslib.as_array((C.c_float * 64).from_address(host_out[(e2e_steps - 1) & 1].value)).copy()
+    assert np.array_equal(chk, out.pixels.reshape(-1)[:64].cpu().numpy()), "e2e result differs from the device-resident one"
+    # what one reference-facing call per operator costs (the shim's path today: every operator stages its
+    # input up and its result down): mb200_convolve_image + mb200_resize_image on the same host buffers
+    t0 = time.perf_counter()
+    _lib.check(lib.mb200_convolve_image(host_in[0], host_in[1], W, H, 4, blur_kernel._ptr))
+    _lib.check(lib.mb200_resize_image(host_in[1], W, H, 4, host_out[0], job.out_columns, job.out_rows, job.resize_filter))
+    per_call_ms = (time.perf_counter() - t0) * 1e3
+    for pp in d_in + d_blur + d_out:
+        lib.mb200_free(pp)
+    for pp in host_in + host_out:
+        lib.mb200_free_host(pp)
 
     if rank != 0:
         try:
@@ -302,7 +335,7 @@ def run_gpu(args):
     alg_bytes = 32.0 * W * H
     achieved = alg_bytes / (blur_launch_ms * 1e-3) / 1e9
     resize_alg = 36.0 * W * H                                       # V: 16+8, H: 8+4 bytes per input px
-    cpu, _ = cpu_pipeline(steps=2, warmup=1)
+    cpu, _ = cpu_pipeline(steps=6, warmup=1)        # ~10-15 s of the reference on all host cores
     line = {
         "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -313,9 +346,13 @@ def run_gpu(args):
                    "sharding": "one image per rank, one NCCL broadcast of the filter taps, no pixel traffic",
                    "blur_ms": statistics.mean(blur_ms), "resize_ms": statistics.mean(resize_ms),
                    "blur_mpix_s": W * H / statistics.mean(blur_ms) / 1e3,
+                   "e2e_path": "C-ABI: mb200_upload -> mb200_convolve_image_dev -> mb200_resize_image_dev -> "
+                               "mb200_download on pinned host buffers, two streams",
+                   "e2e_one_host_call_per_operator_ms": per_call_ms,
                    "resize_hbm_frac": resize_alg / (statistics.mean(resize_ms) * 1e-3) / 1e9 / peak},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "conv_pair_kernel<33,2,0> (row pass) / conv_pair_kernel<33,2,1> (column pass) of BlurImage",
+                     "traffic": None, "kernel": "conv_pair_async_kernel<33,2,0,0> (row pass) / conv_pair_kernel<33,2,1,0,true> (column pass) "
+                               "of BlurImage; average of the two launches",
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "Mpixels/s", "ms_per_step": e2e_ms,
