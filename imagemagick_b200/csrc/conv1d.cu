@@ -616,6 +616,7 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a
         }
         ++isrc;
       }
+      // (premultiplying one step ahead, as the cp.async kernel does, costs this kernel 5 %: 220 registers)
       double v0, v1;
       if (IO == 2) {
         v0 = vf.x; v1 = vf.y;                       // already premultiplied sums
@@ -868,6 +869,13 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_async_kernel(const Conv1d
   if (AXIS == 1) asm volatile("cp.async.wait_group %0;" ::"n"(NS - 2));
   else { asm volatile("cp.async.wait_group %0;" ::"n"(NC - 1)); __syncwarp(); }
   asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(vnext.x), "=f"(vnext.y) : "r"(rd));
+  double nv0, nv1;                                 // premultiplied sample of the next step
+  {
+    const float af = __shfl_sync(0xffffffffu, vnext.y, alpha_lane);
+    const double da = static_cast<double>(af);
+    nv0 = static_cast<double>(vnext.x) * da;
+    nv1 = static_cast<double>(vnext.y) * (odd ? 1.0 : da);
+  }
 
   int j = -(NT - 1);
   int step = 0;
@@ -875,7 +883,7 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_async_kernel(const Conv1d
   for (int mb = 0; mb < total; mb += UN) {       // UN unrolled steps, then rotate the accumulators by UN
 #pragma unroll
     for (int s = 0; s < UN; ++s) {
-      const float2 vf = vnext;
+      const double v0 = nv0, v1 = nv1;
       // fetch the next step's sample and keep the ring full
       if (AXIS == 1) {
         asm volatile("cp.async.wait_group %0;" ::"n"(NS - 3));      // row step+1 has landed
@@ -896,10 +904,12 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_async_kernel(const Conv1d
         asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(vnext.x), "=f"(vnext.y) : "r"(rd));
       }
       ++step;
-      const float af = __shfl_sync(0xffffffffu, vf.y, alpha_lane);
-      const double da = static_cast<double>(af);
-      const double v0 = static_cast<double>(vf.x) * da;
-      const double v1 = static_cast<double>(vf.y) * (odd ? 1.0 : da);
+      {                                            // next step's SHFL -> F2F -> DMUL chain, under this step's FMAs
+        const float af = __shfl_sync(0xffffffffu, vnext.y, alpha_lane);
+        const double da = static_cast<double>(af);
+        nv0 = static_cast<double>(vnext.x) * da;
+        nv1 = static_cast<double>(vnext.y) * (odd ? 1.0 : da);
+      }
 #pragma unroll
       for (int q = 0; q < NT; ++q) {
         const double k = taps.k[(s - q + NT) % NT];
