@@ -82,6 +82,12 @@ PROTOTYPES = {
     "mb200_unsharp_mask_image": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d, _d, _d]),
     "mb200_resize_image": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i]),
     "mb200_transform_colorspace": (_i, [_vp, _sz, _sz, _i, _i, _i]),
+    "mb200_sharpen_kernel": (KernelPtr, [_d, _d]),
+    "mb200_edge_kernel": (KernelPtr, [_d]),
+    "mb200_sharpen_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d, _vp]),
+    "mb200_edge_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _d, _vp]),
+    "mb200_sharpen_image": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d]),
+    "mb200_edge_image": (_i, [_vp, _vp, _sz, _sz, _i, _d]),
     "mb200_bilevel_image_dev": (_i, [_vp, _sz, _sz, _i, _d, _vp]),
     "mb200_black_threshold_image_dev": (_i, [_vp, _sz, _sz, _i, _i, C.c_char_p, _vp]),
     "mb200_white_threshold_image_dev": (_i, [_vp, _sz, _sz, _i, _i, C.c_char_p, _vp]),

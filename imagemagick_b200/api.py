@@ -5,6 +5,7 @@ Same names, argument meaning and error behaviour as the reference operators
 include/magick_b200.h:
 
     BlurImage, GaussianBlurImage, ConvolveImage, UnsharpMaskImage   effect.c:765/1709/1170/4256
+    SharpenImage, EdgeImage                                         effect.c:3991/1520
     MorphologyImage, AcquireKernelInfo                              morphology.c:4129/485
     ResizeImage                                                     resize.c:3761
     TransformImageColorspace                                        colorspace.c:1751
@@ -200,6 +201,16 @@ def UnsharpMaskImage(image: Image, radius: float, sigma: float, gain: float, thr
     """MagickCore/effect.c:4256."""
     return _same_size_op(image, "mb200_unsharp_mask_image_dev", "mb200_unsharp_mask_image", float(radius),
                          float(sigma), float(gain), float(threshold))
+
+
+def SharpenImage(image: Image, radius: float, sigma: float) -> Image:
+    """MagickCore/effect.c:3991 -- ConvolveImage with the inline sharpening kernel."""
+    return _same_size_op(image, "mb200_sharpen_image_dev", "mb200_sharpen_image", float(radius), float(sigma))
+
+
+def EdgeImage(image: Image, radius: float) -> Image:
+    """MagickCore/effect.c:1520 -- ConvolveImage with the all -1 / centre n-1 kernel."""
+    return _same_size_op(image, "mb200_edge_image_dev", "mb200_edge_image", float(radius))
 
 
 def ResizeImage(image: Image, columns: int, rows: int, filter: int = UndefinedFilter) -> Image:

@@ -745,3 +745,43 @@ int mb200_clamp_image(float *buf, size_t w, size_t h, int ch) {
 }
 
 }  // extern "C"
+
+// ---- SharpenImage / EdgeImage: effect.c builds a kernel inline and calls ConvolveImage ------------------------
+extern "C" {
+
+int mb200_sharpen_image_dev(const float *src, float *dst, size_t width, size_t height, int channels, double radius,
+                            double sigma, void *stream) {
+  mb200_kernel_info *k = mb200_sharpen_kernel(radius, sigma);
+  if (!k) return fail(MB200_ENOMEM, "sharpen kernel");
+  const int rc = mb200_convolve_image_dev(src, dst, width, height, channels, k, stream);
+  mb200_destroy_kernel_info(k);
+  return rc;
+}
+
+int mb200_edge_image_dev(const float *src, float *dst, size_t width, size_t height, int channels, double radius,
+                         void *stream) {
+  mb200_kernel_info *k = mb200_edge_kernel(radius);
+  if (!k) return fail(MB200_ENOMEM, "edge kernel");
+  const int rc = mb200_convolve_image_dev(src, dst, width, height, channels, k, stream);
+  mb200_destroy_kernel_info(k);
+  return rc;
+}
+
+int mb200_sharpen_image(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma) {
+  if (!src || !dst || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "sharpen: bad arguments");
+  const size_t bytes = w * h * ch * sizeof(float);
+  return with_staging(src, bytes, dst, bytes, [&](const float *s, float *d, cudaStream_t st) {
+    return mb200_sharpen_image_dev(s, d, w, h, ch, radius, sigma, st);
+  });
+}
+
+int mb200_edge_image(const float *src, float *dst, size_t w, size_t h, int ch, double radius) {
+  if (!src || !dst || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "edge: bad arguments");
+  const size_t bytes = w * h * ch * sizeof(float);
+  return with_staging(src, bytes, dst, bytes, [&](const float *s, float *d, cudaStream_t st) {
+    return mb200_edge_image_dev(s, d, w, h, ch, radius, st);
+  });
+}
+
+}  // extern "C"
+

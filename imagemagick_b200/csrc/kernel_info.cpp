@@ -598,3 +598,45 @@ mb200_kernel_info *mb200_destroy_kernel_info(mb200_kernel_info *kernel) {
 }
 
 }  // extern "C"
+
+// ---- effect.c kernels that are built inline by SharpenImage (:3991-4063) and EdgeImage (:1520-1570) ----------
+extern "C" {
+
+// SharpenImage: -exp(-(u*u+v*v)/(2 s^2))/(2 pi s^2) everywhere, centre = -2 * sum, then normalised to sum 1.
+mb200_kernel_info *mb200_sharpen_kernel(double radius, double sigma) {
+  const size_t width = mb200_optimal_kernel_width_2d(radius, sigma);
+  mb200_kernel_info *k = new_kernel(MB200_UserDefinedKernel, width, width);
+  if (!k) return nullptr;
+  centre_origin(k);
+  const double s = std::fabs(sigma) < kEps ? kEps : sigma;            // MagickSigma (effect.c)
+  double normalize = 0.0;
+  const long j = static_cast<long>(width - 1) / 2;
+  size_t i = 0;
+  for (long v = -j; v <= j; ++v)
+    for (long u = -j; u <= j; ++u) {
+      k->values[i] = -std::exp(-(static_cast<double>(u * u) + static_cast<double>(v * v)) / (2.0 * s * s)) / (2.0 * kPi * s * s);
+      normalize += k->values[i];
+      ++i;
+    }
+  k->values[i / 2] = (-2.0) * normalize;
+  normalize = 0.0;
+  for (i = 0; i < width * width; ++i) normalize += k->values[i];
+  const double gamma = perceptible_reciprocal(normalize);
+  for (i = 0; i < width * width; ++i) k->values[i] *= gamma;
+  return k;
+}
+
+// EdgeImage: width = GetOptimalKernelWidth1D(radius, 0.5); all cells -1, centre = width*height - 1.
+mb200_kernel_info *mb200_edge_kernel(double radius) {
+  const size_t width = mb200_optimal_kernel_width_1d(radius, 0.5);
+  mb200_kernel_info *k = new_kernel(MB200_UserDefinedKernel, width, width);
+  if (!k) return nullptr;
+  centre_origin(k);
+  const size_t n = width * width;
+  for (size_t i = 0; i < n; ++i) k->values[i] = -1.0;
+  k->values[n / 2] = static_cast<double>(width) * static_cast<double>(width) - 1.0;
+  return k;
+}
+
+}  // extern "C"
+

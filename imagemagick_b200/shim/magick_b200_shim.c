@@ -5,7 +5,8 @@
   Link an application / the MagickCore library with
       -Wl,--wrap=BlurImage,--wrap=GaussianBlurImage,--wrap=ConvolveImage,--wrap=UnsharpMaskImage,\
           --wrap=MorphologyImage,--wrap=ResizeImage,--wrap=TransformImageColorspace,\
-          --wrap=BilevelImage,--wrap=BlackThresholdImage,--wrap=WhiteThresholdImage,--wrap=ClampImage
+          --wrap=BilevelImage,--wrap=BlackThresholdImage,--wrap=WhiteThresholdImage,--wrap=ClampImage,\
+          --wrap=SharpenImage,--wrap=EdgeImage
   and every caller of those exported functions (effect.c:765/1709/1170/4256, morphology.c:4129,
   resize.c:3761, colorspace.c:1751, threshold.c:805/927/2518/1087) reaches __wrap_X below.  Each wrapper follows the accelerate
   hook contract of effect.c:783-787 / resize.c:3818-3826: try the GPU; if the image is not
@@ -314,6 +315,28 @@ MagickBooleanType B200AccelerateWhiteThresholdImage(Image *image, const char *th
 MagickBooleanType B200AccelerateClampImage(Image *image, ExceptionInfo *exception)
 { return run_threshold(image, 3, 0.0, (const char *) NULL, exception); }
 
+/* ---- SharpenImage / EdgeImage (effect.c:3991, :1520): inline kernel + ConvolveImage -------------------------- */
+static int op_sharpen(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
+{ const blur_args *b = (const blur_args *) a; return mb200_sharpen_image(s, d, w, h, ch, b->radius, b->sigma); }
+static int op_edge(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
+{ const blur_args *b = (const blur_args *) a; return mb200_edge_image(s, d, w, h, ch, b->radius); }
+
+Image *B200AccelerateSharpenImage(const Image *image, const double radius, const double sigma, ExceptionInfo *exception)
+{
+  blur_args a;
+  if (has_artifact(image, morphology_artifacts) != MagickFalse) return (Image *) NULL;
+  a.radius = radius; a.sigma = sigma; a.gain = 0.0; a.threshold = 0.0;
+  return run_same_size(image, op_sharpen, &a, exception);
+}
+
+Image *B200AccelerateEdgeImage(const Image *image, const double radius, ExceptionInfo *exception)
+{
+  blur_args a;
+  if (has_artifact(image, morphology_artifacts) != MagickFalse) return (Image *) NULL;
+  a.radius = radius; a.sigma = 0.0; a.gain = 0.0; a.threshold = 0.0;
+  return run_same_size(image, op_edge, &a, exception);
+}
+
 /* ---- ld --wrap entry points ------------------------------------------------------------------------------ */
 extern Image *__real_BlurImage(const Image *, const double, const double, ExceptionInfo *);
 extern Image *__real_GaussianBlurImage(const Image *, const double, const double, ExceptionInfo *);
@@ -324,6 +347,8 @@ extern Image *__real_MorphologyImage(const Image *, const MorphologyMethod, cons
                                      ExceptionInfo *);
 extern Image *__real_ResizeImage(const Image *, const size_t, const size_t, const FilterType, ExceptionInfo *);
 extern MagickBooleanType __real_TransformImageColorspace(Image *, const ColorspaceType, ExceptionInfo *);
+extern Image *__real_SharpenImage(const Image *, const double, const double, ExceptionInfo *);
+extern Image *__real_EdgeImage(const Image *, const double, ExceptionInfo *);
 extern MagickBooleanType __real_BilevelImage(Image *, const double, ExceptionInfo *);
 extern MagickBooleanType __real_BlackThresholdImage(Image *, const char *, ExceptionInfo *);
 extern MagickBooleanType __real_WhiteThresholdImage(Image *, const char *, ExceptionInfo *);
@@ -422,4 +447,16 @@ MagickBooleanType __wrap_ClampImage(Image *image, ExceptionInfo *exception)
 {
   TRY_BOOL(B200AccelerateClampImage(image, exception));
   return __real_ClampImage(image, exception);
+}
+
+Image *__wrap_SharpenImage(const Image *image, const double radius, const double sigma, ExceptionInfo *exception)
+{
+  TRY(B200AccelerateSharpenImage(image, radius, sigma, exception));
+  return __real_SharpenImage(image, radius, sigma, exception);
+}
+
+Image *__wrap_EdgeImage(const Image *image, const double radius, ExceptionInfo *exception)
+{
+  TRY(B200AccelerateEdgeImage(image, radius, exception));
+  return __real_EdgeImage(image, radius, exception);
 }

@@ -152,6 +152,11 @@ MB200_API void mb200_scale_kernel_info(mb200_kernel_info *kernel, double scaling
 MB200_API size_t mb200_optimal_kernel_width_1d(double radius, double sigma);
 MB200_API size_t mb200_optimal_kernel_width_2d(double radius, double sigma);
 
+/* The kernels SharpenImage (MagickCore/effect.c:3991-4063) and EdgeImage (:1520-1570) build inline
+   before calling ConvolveImage. */
+MB200_API mb200_kernel_info *mb200_sharpen_kernel(double radius, double sigma);
+MB200_API mb200_kernel_info *mb200_edge_kernel(double radius);
+
 /* Resize contribution table of one axis: exactly the start/stop/weights that
    HorizontalFilter / VerticalFilter (MagickCore/resize.c:3398-3443, :3614-3657)
    compute per output column/row.  weights is out_n * max_taps doubles (row o at
@@ -202,6 +207,11 @@ MB200_API int mb200_gaussian_blur_image_dev(const float *src, float *dst, size_t
 MB200_API int mb200_unsharp_mask_image_dev(const float *src, float *dst, size_t width,
     size_t height, int channels, double radius, double sigma, double gain, double threshold,
     void *stream);
+/* SharpenImage (MagickCore/effect.c:3991) and EdgeImage (:1520): ConvolveImage with the kernel above */
+MB200_API int mb200_sharpen_image_dev(const float *src, float *dst, size_t width, size_t height,
+    int channels, double radius, double sigma, void *stream);
+MB200_API int mb200_edge_image_dev(const float *src, float *dst, size_t width, size_t height,
+    int channels, double radius, void *stream);
 /* ResizeImage (MagickCore/resize.c:3761) == AccelerateResizeImage (:43).  filter
    UndefinedFilter applies the reference's own default choice (:3806-3816). */
 MB200_API int mb200_resize_image_dev(const float *src, size_t width, size_t height, int channels,
@@ -242,6 +252,10 @@ MB200_API int mb200_morphology_image(const float *src, float *dst, size_t width,
     int channels, int method, long iterations, const mb200_kernel_info *kernel, double bias);
 MB200_API int mb200_unsharp_mask_image(const float *src, float *dst, size_t width, size_t height,
     int channels, double radius, double sigma, double gain, double threshold);
+MB200_API int mb200_sharpen_image(const float *src, float *dst, size_t width, size_t height, int channels,
+    double radius, double sigma);
+MB200_API int mb200_edge_image(const float *src, float *dst, size_t width, size_t height, int channels,
+    double radius);
 MB200_API int mb200_resize_image(const float *src, size_t width, size_t height, int channels,
     float *dst, size_t out_width, size_t out_height, int filter);
 MB200_API int mb200_transform_colorspace(float *buf, size_t width, size_t height, int channels,

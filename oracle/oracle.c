@@ -1109,3 +1109,53 @@ int orc_threshold(float *buf, size_t w, size_t h, int ch, int op, const double *
   }
   return 0;
 }
+
+
+/* effect.c:3991-4063 SharpenImage, :1520-1570 EdgeImage: inline kernel + ConvolveImage */
+int orc_sharpen(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma)
+{
+  const size_t width = orc_optimal_kernel_width_2d(radius, sigma);
+  const double s = fabs(sigma) < EPS ? EPS : sigma;                 /* MagickSigma */
+  double *vals = (double *) malloc(width * width * sizeof(double)), normalize = 0.0, gamma;
+  const long j = (long) (width - 1) / 2;
+  long u, v;
+  size_t i = 0;
+  orc_kernel k;
+  int rc;
+  if (!vals) return -1;
+  for (v = -j; v <= j; v++)
+    for (u = -j; u <= j; u++) {
+      vals[i] = -exp(-((double) u * u + v * v) / (2.0 * s * s)) / (2.0 * PI_ * s * s);
+      normalize += vals[i];
+      i++;
+    }
+  vals[i / 2] = (-2.0) * normalize;
+  normalize = 0.0;
+  for (i = 0; i < width * width; i++) normalize += vals[i];
+  gamma = perceptible_reciprocal(normalize);
+  for (i = 0; i < width * width; i++) vals[i] *= gamma;
+  rc = orc_kernel_user(width, width, j, j, vals, &k);
+  free(vals);
+  if (rc) return rc;
+  rc = orc_morphology_apply(src, dst, w, h, ch, ORC_CONVOLVE, 1, &k, 1, 0.0);
+  orc_kernel_free(&k);
+  return rc;
+}
+
+int orc_edge(const float *src, float *dst, size_t w, size_t h, int ch, double radius)
+{
+  const size_t width = orc_optimal_kernel_width_1d(radius, 0.5), n = width * width;
+  double *vals = (double *) malloc(n * sizeof(double));
+  orc_kernel k;
+  size_t i;
+  int rc;
+  if (!vals) return -1;
+  for (i = 0; i < n; i++) vals[i] = -1.0;
+  vals[n / 2] = (double) width * width - 1.0;
+  rc = orc_kernel_user(width, width, (long) (width - 1) / 2, (long) (width - 1) / 2, vals, &k);
+  free(vals);
+  if (rc) return rc;
+  rc = orc_morphology_apply(src, dst, w, h, ch, ORC_CONVOLVE, 1, &k, 1, 0.0);
+  orc_kernel_free(&k);
+  return rc;
+}

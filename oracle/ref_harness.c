@@ -116,6 +116,24 @@ int ref_unsharp(const float *src, float *dst, size_t w, size_t h, int ch,
 }
 
 __attribute__((visibility("default")))
+int ref_sharpen(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma)
+{
+  BEGIN
+  im = make_image(src, w, h, ch, -1, ex);
+  if (im) { out = SharpenImage(im, radius, sigma, ex); rc = export_image(out, dst, w, h, ch, ex); }
+  END
+}
+
+__attribute__((visibility("default")))
+int ref_edge(const float *src, float *dst, size_t w, size_t h, int ch, double radius)
+{
+  BEGIN
+  im = make_image(src, w, h, ch, -1, ex);
+  if (im) { out = EdgeImage(im, radius, ex); rc = export_image(out, dst, w, h, ch, ex); }
+  END
+}
+
+__attribute__((visibility("default")))
 int ref_convolve(const float *src, float *dst, size_t w, size_t h, int ch,
                  const char *kernel)
 {

@@ -32,7 +32,8 @@ def main():
             for name, fn, args in (("blur_0x2", r.ref_blur, (0.0, 2.0)), ("blur_0x4", r.ref_blur, (0.0, 4.0)),
                                    ("blur_2x1", r.ref_blur, (2.0, 1.0)),
                                    ("gaussian_0x1.5", r.ref_gaussian_blur, (0.0, 1.5)),
-                                   ("unsharp_0x2_1.5_0.02", r.ref_unsharp, (0.0, 2.0, 1.5, 0.02))):
+                                   ("unsharp_0x2_1.5_0.02", r.ref_unsharp, (0.0, 2.0, 1.5, 0.02)),
+                                   ("sharpen_0x1", r.ref_sharpen, (0.0, 1.0)), ("edge_1", r.ref_edge, (1.0,))):
                 dst = np.empty_like(src)
                 assert fn(P(src), P(dst), W, H, ch, *args) == 0
                 out[f"{tag}/{name}"] = dst

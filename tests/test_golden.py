@@ -38,6 +38,11 @@ def run_oracle(src, name, clamp_src=None):
         rs, gain, thr = name[8:].split("_")
         r, s = rs.split("x")
         assert o.orc_unsharp(P(src), P(dst), w, h, ch, float(r), float(s), float(gain), float(thr)) == 0
+    elif name.startswith("sharpen_"):
+        r, s = name[8:].split("x")
+        assert o.orc_sharpen(P(src), P(dst), w, h, ch, float(r), float(s)) == 0
+    elif name.startswith("edge_") and name[5:].replace(".", "").isdigit():
+        assert o.orc_edge(P(src), P(dst), w, h, ch, float(name[5:])) == 0
     elif name.split("_")[0] in METHODS:
         m, kname = name.split("_", 1)
         k = util.orc_kernel(*KERNEL_ARGS[kname])
@@ -116,6 +121,11 @@ def run_cuda(im, src, name, clamp_src):
         rs, gain, thr = name[8:].split("_")
         r, s = rs.split("x")
         return host(im.UnsharpMaskImage(dev(src), float(r), float(s), float(gain), float(thr))), 2
+    if name.startswith("sharpen_"):
+        r, s = name[8:].split("x")
+        return host(im.SharpenImage(dev(src), float(r), float(s))), 1
+    if name.startswith("edge_") and name[5:].replace(".", "").isdigit():
+        return host(im.EdgeImage(dev(src), float(name[5:]))), 1
     if name.split("_")[0] in METHODS:
         m, kname = name.split("_", 1)
         return host(im.MorphologyImage(dev(src), METHODS[m], 1, kname)), 0

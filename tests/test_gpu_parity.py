@@ -127,6 +127,20 @@ def test_rank1_user_kernel_and_non_rank1_neighbour():
 
 
 @pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["noise", "alpha_blocks"])
+def test_sharpen_and_edge(ch, kind):
+    """SharpenImage / EdgeImage: kernels with negative taps through the generic 2-D convolution."""
+    src = make_image(131, 77, ch, seed=61 + ch, kind=kind)
+    for rad, sig in ((0.0, 1.0), (2.0, 0.7)):
+        want = orc("orc_sharpen", src, rad, sig)
+        assert max_ulp(_host(im.SharpenImage(_dev(src), rad, sig)), want) <= 1, (rad, sig)
+    for rad in (0.0, 1.0):
+        want = orc("orc_edge", src, rad)
+        assert max_ulp(_host(im.EdgeImage(_dev(src), rad)), want) <= 1, rad
+    assert max_ulp(im.SharpenImage(im.Image(src), 0.0, 1.0).pixels, orc("orc_sharpen", src, 0.0, 1.0)) <= 1
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
 def test_unsharp(ch):
     src = make_image(120, 77, ch, seed=5)
     want = orc("orc_unsharp", src, 0.0, 2.0, 1.5, 0.02)

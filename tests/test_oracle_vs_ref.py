@@ -25,6 +25,22 @@ def test_blur_family_bit_exact(ch, kind):
         assert max_ulp(a, b) == 0
 
 
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["noise", "alpha_blocks", "hdr"])
+def test_sharpen_edge_bit_exact(ch, kind):
+    """effect.c:3991 SharpenImage / :1520 EdgeImage: inline kernels (negative taps) + ConvolveImage."""
+    src = make_image(53, 37, ch, seed=7, kind=kind)
+    r, o = util.ref(), oracle()
+    for rad, sig in ((0.0, 1.0), (0.0, 2.0), (2.0, 0.7), (0.0, 0.5)):
+        a, b = np.empty_like(src), np.empty_like(src)
+        assert r.ref_sharpen(P(src), P(a), 53, 37, ch, rad, sig) == 0 and o.orc_sharpen(P(src), P(b), 53, 37, ch, rad, sig) == 0
+        assert max_ulp(a, b) == 0
+    for rad in (0.0, 1.0, 2.0):
+        a, b = np.empty_like(src), np.empty_like(src)
+        assert r.ref_edge(P(src), P(a), 53, 37, ch, rad) == 0 and o.orc_edge(P(src), P(b), 53, 37, ch, rad) == 0
+        assert max_ulp(a, b) == 0
+
+
 @pytest.mark.parametrize("ch", [1, 4])
 def test_resize_all_filters_bit_exact(ch):
     src = make_image(47, 33, ch, seed=5, kind="alpha_blocks")

@@ -42,6 +42,8 @@ def oracle() -> C.CDLL:
         for f in (o.orc_blur, o.orc_gaussian_blur):
             f.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d]
         o.orc_unsharp.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d, _d, _d]
+        o.orc_sharpen.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d]
+        o.orc_edge.argtypes = [_fp, _fp, _sz, _sz, _i, _d]
         o.orc_resize.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz, _i]
         o.orc_colorspace.argtypes = [_fp, _sz, _sz, _i, _i, _i]
         o.orc_kernel_builtin.argtypes = [_i, _d, _d, _d, _d, C.POINTER(OrcKernel)]
@@ -77,6 +79,8 @@ def ref() -> C.CDLL:
         for f in (r.ref_blur, r.ref_gaussian_blur):
             f.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d]
         r.ref_unsharp.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d, _d, _d]
+        r.ref_sharpen.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d]
+        r.ref_edge.argtypes = [_fp, _fp, _sz, _sz, _i, _d]
         r.ref_convolve.argtypes = [_fp, _fp, _sz, _sz, _i, C.c_char_p]
         r.ref_morphology.argtypes = [_fp, _fp, _sz, _sz, _i, _i, _l, C.c_char_p]
         r.ref_resize.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz, _i]
