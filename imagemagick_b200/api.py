@@ -48,6 +48,8 @@ EdgeInMorphology, EdgeOutMorphology, EdgeMorphology, TopHatMorphology, BottomHat
 
 # MagickCore/colorspace.h:27-67
 LabColorspace, RGBColorspace, sRGBColorspace, XYZColorspace = 11, 21, 23, 26
+CMYColorspace, OHTAColorspace, Rec601YCbCrColorspace, Rec709YCbCrColorspace = 1, 18, 19, 20
+YCbCrColorspace, YDbDrColorspace, YIQColorspace, YPbPrColorspace, YUVColorspace = 27, 29, 30, 31, 32
 
 # kernel types of include/magick_b200.h
 (UserDefinedKernel, BlurKernel, GaussianKernel, DiskKernel, SquareKernel, DiamondKernel, OctagonKernel,

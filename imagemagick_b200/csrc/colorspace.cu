@@ -186,25 +186,164 @@ int launch_mode(float *buf, size_t npixels, int channels, cudaStream_t s) {
   return MB200_OK;
 }
 
+// ---- matrix colourspaces: CMY, YCbCr (= YPbPr), YDbDr, YIQ, YPbPr, YUV through the generic branch
+// (colorspace.c:958-1054 / :2296-2390, colorspace-private.h:793, :141, :1551-1593, :1637-1701) and the
+// LUT branch for OHTA, Rec601YCbCr, Rec709YCbCr (colorspace.c:1229-1494 / :2560-2830): samples quantised to a
+// 16-bit map index (ScaleQuantumToMap), three double table entries summed left to right, ScaleMapToQuantum.
+// The tables are linear in the index, so they are evaluated instead of stored: c*i (forward),
+// c*i and K*(2i - MaxMap) (inverse) -- each a single rounded product like the table entry itself.
+// All sums unfused in the reference's order => bit exact.
+struct MatrixLeg {
+  double m[3][3];     // generic: row coefficients; lut forward: c; lut inverse: column 0 = x, 1 = y (already *0.5), 2 = z
+  int kind;           // 0 generic forward, 1 generic inverse, 2 lut forward, 3 lut inverse, 4 cmy forward, 5 cmy inverse
+};
+
+__device__ __forceinline__ double quantum_to_map(float q) {       // quantum-private.h:504-514 (HDRI)
+  if (q >= 65535.0f) return 65535.0;
+  if (q != q || q <= 0.0f) return 0.0;
+  return static_cast<double>(static_cast<unsigned int>(__fadd_rn(q, 0.5f)));
+}
+__device__ __forceinline__ float map_to_quantum(double v) {
+  if (v <= 0.0) return 0.0f;
+  if (v >= 65535.0) return 65535.0f;
+  return static_cast<float>(v);
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) matrix_leg_kernel(float *buf, size_t npixels, const MatrixLeg a) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= npixels) return;
+  float *q = buf + i * CH;
+  float in[3], in3 = 0.f;
+  if (CH == 4) { const float4 t = *reinterpret_cast<const float4 *>(q); in[0] = t.x; in[1] = t.y; in[2] = t.z; in3 = t.w; }
+  else { in[0] = q[0]; in[1] = q[1]; in[2] = q[2]; }
+  float o[3];
+  if (a.kind == 2 || a.kind == 3) {
+    const double r = quantum_to_map(in[0]), g = quantum_to_map(in[1]), b = quantum_to_map(in[2]);
+    const double g2 = __dsub_rn(__dmul_rn(2.0, g), 65535.0), b2 = __dsub_rn(__dmul_rn(2.0, b), 65535.0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double v;
+      if (a.kind == 2) {
+        v = __dadd_rn(__dadd_rn(__dmul_rn(a.m[k][0], r), __dmul_rn(a.m[k][1], g)), __dmul_rn(a.m[k][2], b));
+        v = __dadd_rn(v, k == 0 ? 0.0 : 32768.0);
+      } else {
+        v = __dadd_rn(__dadd_rn(__dmul_rn(a.m[k][0], r), __dmul_rn(a.m[k][1], g2)), __dmul_rn(a.m[k][2], b2));
+      }
+      o[k] = map_to_quantum(v);
+    }
+  } else if (a.kind == 4 || a.kind == 5) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double p = static_cast<double>(in[k]);
+      o[k] = a.kind == 4 ? static_cast<float>(__dmul_rn(QR, __dmul_rn(QS, __dsub_rn(QR, p))))
+                         : static_cast<float>(__dmul_rn(QR, __dsub_rn(1.0, __dmul_rn(QS, p))));
+    }
+  } else if (a.kind == 0) {
+    const double R = in[0], G = in[1], B = in[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double X = __dmul_rn(QS, __dadd_rn(__dadd_rn(__dmul_rn(a.m[k][0], R), __dmul_rn(a.m[k][1], G)), __dmul_rn(a.m[k][2], B)));
+      if (k) X = __dadd_rn(X, 0.5);
+      o[k] = static_cast<float>(__dmul_rn(QR, X));
+    }
+  } else {
+    const double Y = __dmul_rn(QS, static_cast<double>(in[0]));
+    const double U = __dsub_rn(__dmul_rn(QS, static_cast<double>(in[1])), 0.5);
+    const double V = __dsub_rn(__dmul_rn(QS, static_cast<double>(in[2])), 0.5);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double t = __dmul_rn(a.m[k][0], Y);        // * 1.0 is exact where the reference writes plain Y
+      o[k] = static_cast<float>(__dmul_rn(QR, __dadd_rn(__dadd_rn(t, __dmul_rn(a.m[k][1], U)), __dmul_rn(a.m[k][2], V))));
+    }
+  }
+  if (CH == 4) *reinterpret_cast<float4 *>(q) = make_float4(o[0], o[1], o[2], in3);
+  else { q[0] = o[0]; q[1] = o[1]; q[2] = o[2]; }
+}
+
+bool matrix_leg(int cs, bool forward, MatrixLeg &leg) {
+  auto set = [&](int kind, const double (&m)[3][3]) {
+    leg.kind = kind;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) leg.m[r][c] = m[r][c];
+    return true;
+  };
+  static const double zero[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  // forward generic (colorspace-private.h:1551-1593)
+  static const double f_ydbdr[3][3] = {{0.298839, 0.586811, 0.114350}, {-0.450, -0.883, 1.333}, {-1.333, 1.116, 0.217}};
+  static const double f_yiq[3][3] = {{0.298839, 0.586811, 0.114350}, {0.595716, -0.274453, -0.321263}, {0.211456, -0.522591, 0.311135}};
+  static const double f_ypbpr[3][3] = {{0.298839, 0.586811, 0.114350}, {-0.1687367, -0.331264, 0.5}, {0.5, -0.418688, -0.081312}};
+  static const double f_yuv[3][3] = {{0.298839, 0.586811, 0.114350}, {-0.147, -0.289, 0.436}, {0.615, -0.515, -0.100}};
+  // inverse generic (colorspace-private.h:1637-1701)
+  static const double i_ydbdr[3][3] = {{1.0, 9.2303716147657e-05, -0.52591263066186533}, {1.0, -0.12913289889050927, 0.26789932820759876},
+                                       {1.0, 0.66467905997895482, -7.9202543533108e-05}};
+  static const double i_yiq[3][3] = {{1.0, 0.9562957197589482261, 0.6210244164652610754}, {1.0, -0.2721220993185104464, -0.6473805968256950427},
+                                     {1.0, -1.1069890167364901945, 1.7046149983646481374}};
+  static const double i_ypbpr[3][3] = {{0.99999999999914679361, -1.2188941887145875e-06, 1.4019995886561440468},
+                                       {0.99999975910502514331, -0.34413567816504303521, -0.71413649331646789076},
+                                       {1.00000124040004623180, 1.77200006607230409200, 2.1453384174593273e-06}};
+  static const double i_yuv[3][3] = {{1.0, -3.945707070708279e-05, 1.1398279671717170825}, {1.0, -0.3946101641414141437, -0.5805003156565656797},
+                                     {1.0, 2.0319996843434342537, -4.813762626262513e-04}};
+  // LUT forward (colorspace.c:1254-1345)
+  static const double l_ohta[3][3] = {{0.33333, 0.33334, 0.33333}, {0.50000, 0.00000, -0.50000}, {-0.25000, 0.50000, -0.25000}};
+  static const double l_601[3][3] = {{0.298839, 0.586811, 0.114350}, {-0.1687367, -0.331264, 0.500000}, {0.500000, -0.418688, -0.081312}};
+  static const double l_709[3][3] = {{0.212656, 0.715158, 0.072186}, {-0.114572, -0.385428, 0.500000}, {0.500000, -0.454153, -0.045847}};
+  // LUT inverse (colorspace.c:2591-2678): rows = R, G, B; columns = x (on i_r), 0.5*y (on 2 i_g - MaxMap), 0.5*z
+  static const double li_ohta[3][3] = {{1.0, 0.5 * 1.00000, -0.5 * 0.66668}, {1.0, 0.5 * 0.00000, 0.5 * 1.33333}, {1.0, -0.5 * 1.00000, -0.5 * 0.66668}};
+  static const double li_601[3][3] = {{0.99999999999914679361, 0.5 * (-1.2188941887145875e-06), 0.5 * 1.4019995886561440468},
+                                      {0.99999975910502514331, 0.5 * (-0.34413567816504303521), 0.5 * (-0.71413649331646789076)},
+                                      {1.00000124040004623180, 0.5 * 1.77200006607230409200, 0.5 * 2.1453384174593273e-06}};
+  static const double li_709[3][3] = {{1.0, 0.5 * 0.000000, 0.5 * 1.574800}, {1.0, 0.5 * (-0.187324), 0.5 * (-0.468124)},
+                                      {1.0, 0.5 * 1.855600, 0.5 * 0.000000}};
+  switch (cs) {
+    case MB200_CMYColorspace: return set(forward ? 4 : 5, zero);
+    case MB200_YDbDrColorspace: return set(forward ? 0 : 1, forward ? f_ydbdr : i_ydbdr);
+    case MB200_YIQColorspace: return set(forward ? 0 : 1, forward ? f_yiq : i_yiq);
+    case MB200_YCbCrColorspace: case MB200_YPbPrColorspace: return set(forward ? 0 : 1, forward ? f_ypbpr : i_ypbpr);
+    case MB200_YUVColorspace: return set(forward ? 0 : 1, forward ? f_yuv : i_yuv);
+    case MB200_OHTAColorspace: return set(forward ? 2 : 3, forward ? l_ohta : li_ohta);
+    case MB200_Rec601YCbCrColorspace: return set(forward ? 2 : 3, forward ? l_601 : li_601);
+    case MB200_Rec709YCbCrColorspace: return set(forward ? 2 : 3, forward ? l_709 : li_709);
+    default: return false;
+  }
+}
+
+int launch_matrix_leg(float *buf, size_t npixels, int channels, const MatrixLeg &leg, cudaStream_t s) {
+  const unsigned blocks = static_cast<unsigned>((npixels + 255) / 256);
+  if (channels == 4) matrix_leg_kernel<4><<<blocks, 256, 0, s>>>(buf, npixels, leg);
+  else matrix_leg_kernel<3><<<blocks, 256, 0, s>>>(buf, npixels, leg);
+  count_launch();
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "colorspace launch");
+  return MB200_OK;
+}
+
 }  // namespace
 
 int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to, void *stream) {
   if (channels != 3 && channels != 4) return fail(MB200_EUNSUPPORTED, "colorspace: %d channels", channels);
   if (npixels == 0) return MB200_OK;
   if (npixels > 0xffffffffull * 256) return fail(MB200_EINVAL, "colorspace: image too large");
+  if (channels == 4 && (reinterpret_cast<uintptr_t>(buf) & 15) != 0)
+    return fail(MB200_EINVAL, "colorspace: RGBA buffers must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  auto known = [](int cs) { return cs == MB200_sRGBColorspace || cs == MB200_LabColorspace ||
-                                   cs == MB200_XYZColorspace || cs == MB200_RGBColorspace; };
-  if (!known(from) || !known(to)) return fail(MB200_EUNSUPPORTED, "colorspace %d -> %d not implemented", from, to);
+  auto core = [](int cs) { return cs == MB200_sRGBColorspace || cs == MB200_LabColorspace ||
+                                  cs == MB200_XYZColorspace || cs == MB200_RGBColorspace; };
+  MatrixLeg from_leg{}, to_leg{};
+  const bool from_matrix = !core(from) && matrix_leg(from, false, from_leg);
+  const bool to_matrix = !core(to) && matrix_leg(to, true, to_leg);
+  if ((!core(from) && !from_matrix) || (!core(to) && !to_matrix))
+    return fail(MB200_EUNSUPPORTED, "colorspace %d -> %d not implemented", from, to);
   if (from == to) return MB200_OK;
   int rc = MB200_OK;
   if (from != MB200_sRGBColorspace) {          // colorspace.c:1773-1774: back to sRGB first
-    if (from == MB200_LabColorspace) rc = launch_mode<kFromLab>(buf, npixels, channels, s);
+    if (from_matrix) rc = launch_matrix_leg(buf, npixels, channels, from_leg, s);
+    else if (from == MB200_LabColorspace) rc = launch_mode<kFromLab>(buf, npixels, channels, s);
     else if (from == MB200_XYZColorspace) rc = launch_mode<kFromXyz>(buf, npixels, channels, s);
     else rc = launch_mode<kFromLinear>(buf, npixels, channels, s);
     if (rc) return rc;
   }
-  if (to == MB200_LabColorspace) rc = launch_mode<kToLab>(buf, npixels, channels, s);
+  if (to_matrix) rc = launch_matrix_leg(buf, npixels, channels, to_leg, s);
+  else if (to == MB200_LabColorspace) rc = launch_mode<kToLab>(buf, npixels, channels, s);
   else if (to == MB200_XYZColorspace) rc = launch_mode<kToXyz>(buf, npixels, channels, s);
   else if (to == MB200_RGBColorspace) rc = launch_mode<kToLinear>(buf, npixels, channels, s);
   return rc;

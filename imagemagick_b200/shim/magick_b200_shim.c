@@ -241,6 +241,15 @@ static int map_colorspace(ColorspaceType c)
     case RGBColorspace: return MB200_RGBColorspace;
     case LabColorspace: return MB200_LabColorspace;
     case XYZColorspace: return MB200_XYZColorspace;
+    case CMYColorspace: return MB200_CMYColorspace;
+    case OHTAColorspace: return MB200_OHTAColorspace;
+    case Rec601YCbCrColorspace: return MB200_Rec601YCbCrColorspace;
+    case Rec709YCbCrColorspace: return MB200_Rec709YCbCrColorspace;
+    case YCbCrColorspace: return MB200_YCbCrColorspace;
+    case YDbDrColorspace: return MB200_YDbDrColorspace;
+    case YIQColorspace: return MB200_YIQColorspace;
+    case YPbPrColorspace: return MB200_YPbPrColorspace;
+    case YUVColorspace: return MB200_YUVColorspace;
     default: return -1;
   }
 }

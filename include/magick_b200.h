@@ -80,10 +80,19 @@ typedef enum {
 
 /* MagickCore/colorspace.h:27-67 ColorspaceType -- same numeric values */
 typedef enum {
+  MB200_CMYColorspace = 1,
   MB200_LabColorspace = 11,
-  MB200_RGBColorspace = 21,      /* linear RGB */
+  MB200_OHTAColorspace = 18,          /* LUT branch, colorspace.c:1229-1494 */
+  MB200_Rec601YCbCrColorspace = 19,   /* LUT branch */
+  MB200_Rec709YCbCrColorspace = 20,   /* LUT branch */
+  MB200_RGBColorspace = 21,           /* linear RGB */
   MB200_sRGBColorspace = 23,
-  MB200_XYZColorspace = 26
+  MB200_XYZColorspace = 26,
+  MB200_YCbCrColorspace = 27,
+  MB200_YDbDrColorspace = 29,
+  MB200_YIQColorspace = 30,
+  MB200_YPbPrColorspace = 31,
+  MB200_YUVColorspace = 32
 } mb200_colorspace;
 
 /* Mirror of KernelInfo (MagickCore/morphology.h:102-130): a singly linked list

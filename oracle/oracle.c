@@ -1004,7 +1004,7 @@ static void lab_to_xyz(double L, double a, double b, double *X, double *Y, doubl
 
 /* colorspace.c:1751-1783; forward generic branch :958-1054, linear :1164-1225;
    inverse generic :2296-2390, linear RGB->sRGB :2494-2550 */
-int orc_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to)
+static int colorspace_core(float *buf, size_t w, size_t h, int ch, int from, int to)
 {
   const long n = (long) (w * h);
   long i;
@@ -1055,6 +1055,168 @@ int orc_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to)
   return 0;
 }
 
+
+
+/* ---- matrix colourspaces -------------------------------------------------------------------------
+   Generic branch (colorspace.c:958-1054 forward, :2296-2390 inverse) through
+   ConvertRGBToGeneric / ConvertGenericToRGB for CMY, YCbCr (= YPbPr), YDbDr, YIQ, YPbPr, YUV
+   (colorspace-private.h:793-798, :141-147, :1551-1593, :1637-1701): each component is
+   QS*(m0*R+m1*G+m2*B) [+0.5], stored as (float)(QR*X); inverse QR*(a0*Y+a1*(U-.5)+a2*(V-.5)).
+   LUT branch (forward :1229-1494, inverse :2560-2830) for OHTA, Rec601YCbCr, Rec709YCbCr: the
+   samples are first quantised to a 16-bit map index (ScaleQuantumToMap, quantum-private.h:504-514),
+   the tables hold c*i (forward) or c*i / K*(2i-MaxMap) (inverse) in double, three entries are
+   summed left to right (+ the primary offset), and ScaleMapToQuantum clamps to 0..QuantumRange. */
+typedef struct { double m[3][3]; double off[3]; } cs_matrix;
+
+static const cs_matrix *generic_forward(int cs)
+{
+  static const cs_matrix ydbdr = {{{0.298839, 0.586811, 0.114350}, {-0.450, -0.883, 1.333}, {-1.333, 1.116, 0.217}}, {0, 0.5, 0.5}};
+  static const cs_matrix yiq = {{{0.298839, 0.586811, 0.114350}, {0.595716, -0.274453, -0.321263}, {0.211456, -0.522591, 0.311135}}, {0, 0.5, 0.5}};
+  static const cs_matrix ypbpr = {{{0.298839, 0.586811, 0.114350}, {-0.1687367, -0.331264, 0.5}, {0.5, -0.418688, -0.081312}}, {0, 0.5, 0.5}};
+  static const cs_matrix yuv = {{{0.298839, 0.586811, 0.114350}, {-0.147, -0.289, 0.436}, {0.615, -0.515, -0.100}}, {0, 0.5, 0.5}};
+  switch (cs) {
+    case ORC_CS_YDBDR: return &ydbdr;
+    case ORC_CS_YIQ: return &yiq;
+    case ORC_CS_YCBCR: case ORC_CS_YPBPR: return &ypbpr;
+    case ORC_CS_YUV: return &yuv;
+    default: return NULL;
+  }
+}
+
+static const cs_matrix *generic_inverse(int cs)
+{
+  static const cs_matrix ydbdr = {{{1.0, 9.2303716147657e-05, -0.52591263066186533}, {1.0, -0.12913289889050927, 0.26789932820759876},
+                                   {1.0, 0.66467905997895482, -7.9202543533108e-05}}, {0, 0, 0}};
+  static const cs_matrix yiq = {{{1.0, 0.9562957197589482261, 0.6210244164652610754}, {1.0, -0.2721220993185104464, -0.6473805968256950427},
+                                 {1.0, -1.1069890167364901945, 1.7046149983646481374}}, {0, 0, 0}};
+  static const cs_matrix ypbpr = {{{0.99999999999914679361, -1.2188941887145875e-06, 1.4019995886561440468},
+                                   {0.99999975910502514331, -0.34413567816504303521, -0.71413649331646789076},
+                                   {1.00000124040004623180, 1.77200006607230409200, 2.1453384174593273e-06}}, {0, 0, 0}};
+  static const cs_matrix yuv = {{{1.0, -3.945707070708279e-05, 1.1398279671717170825}, {1.0, -0.3946101641414141437, -0.5805003156565656797},
+                                 {1.0, 2.0319996843434342537, -4.813762626262513e-04}}, {0, 0, 0}};
+  switch (cs) {
+    case ORC_CS_YDBDR: return &ydbdr;
+    case ORC_CS_YIQ: return &yiq;
+    case ORC_CS_YCBCR: case ORC_CS_YPBPR: return &ypbpr;
+    case ORC_CS_YUV: return &yuv;
+    default: return NULL;
+  }
+}
+
+static unsigned int scale_quantum_to_map(float q)      /* quantum-private.h:504-514 (HDRI) */
+{
+  if (q >= (float) 65535.0f) return 65535u;
+  if (q != q || q <= 0.0f) return 0u;
+  return (unsigned int) (q + 0.5f);
+}
+
+static float scale_map_to_quantum(double v)            /* quantum-private.h (HDRI): clamp, no rounding */
+{
+  if (v <= 0.0) return 0.0f;
+  if (v >= 65535.0) return 65535.0f;
+  return (float) v;
+}
+
+static int lut_forward_coeffs(int cs, double c[3][3])
+{
+  static const double ohta[3][3] = {{0.33333, 0.33334, 0.33333}, {0.50000, 0.00000, -0.50000}, {-0.25000, 0.50000, -0.25000}};
+  static const double r601[3][3] = {{0.298839, 0.586811, 0.114350}, {-0.1687367, -0.331264, 0.500000}, {0.500000, -0.418688, -0.081312}};
+  static const double r709[3][3] = {{0.212656, 0.715158, 0.072186}, {-0.114572, -0.385428, 0.500000}, {0.500000, -0.454153, -0.045847}};
+  const double (*t)[3] = cs == ORC_CS_OHTA ? ohta : cs == ORC_CS_REC601YCBCR ? r601 : cs == ORC_CS_REC709YCBCR ? r709 : NULL;
+  if (!t) return -1;
+  memcpy(c, t, sizeof(double) * 9);
+  return 0;
+}
+
+/* inverse tables: row k of the result = x[k]*i_r + (0.5*y[k])*(2 i_g - MaxMap) + (0.5*z[k])*(2 i_b - MaxMap) */
+static int lut_inverse_coeffs(int cs, double x[3], double y[3], double z[3])
+{
+  if (cs == ORC_CS_OHTA) {
+    x[0] = x[1] = x[2] = 1.0;
+    y[0] = 0.5 * 1.00000; y[1] = 0.5 * 0.00000; y[2] = -0.5 * 1.00000;
+    z[0] = -0.5 * 0.66668; z[1] = 0.5 * 1.33333; z[2] = -0.5 * 0.66668;
+  } else if (cs == ORC_CS_REC601YCBCR) {
+    x[0] = 0.99999999999914679361; x[1] = 0.99999975910502514331; x[2] = 1.00000124040004623180;
+    y[0] = 0.5 * (-1.2188941887145875e-06); y[1] = 0.5 * (-0.34413567816504303521); y[2] = 0.5 * 1.77200006607230409200;
+    z[0] = 0.5 * 1.4019995886561440468; z[1] = 0.5 * (-0.71413649331646789076); z[2] = 0.5 * 2.1453384174593273e-06;
+  } else if (cs == ORC_CS_REC709YCBCR) {
+    x[0] = x[1] = x[2] = 1.0;
+    y[0] = 0.5 * 0.000000; y[1] = 0.5 * (-0.187324); y[2] = 0.5 * 1.855600;
+    z[0] = 0.5 * 1.574800; z[1] = 0.5 * (-0.468124); z[2] = 0.5 * 0.000000;
+  } else return -1;
+  return 0;
+}
+
+static int is_core_space(int cs) { return cs == ORC_CS_SRGB || cs == ORC_CS_LAB || cs == ORC_CS_XYZ || cs == ORC_CS_RGB; }
+
+/* one leg: sRGB -> `to` (forward != 0) or `from` -> sRGB, for the matrix / LUT / CMY spaces */
+static int colorspace_matrix_leg(float *buf, long n, int ch, int cs, int forward)
+{
+  long i;
+  double c[3][3], ix[3], iy[3], iz[3];
+  const cs_matrix *gm = forward ? generic_forward(cs) : generic_inverse(cs);
+  const int lut = lut_forward_coeffs(cs, c) == 0;
+  if (lut && !forward) lut_inverse_coeffs(cs, ix, iy, iz);
+  if (!gm && !lut && cs != ORC_CS_CMY) return -1;
+#pragma omp parallel for schedule(static)
+  for (i = 0; i < n; i++) {
+    float *q = buf + (size_t) i * ch;
+    int k;
+    if (lut) {
+      const double r = (double) scale_quantum_to_map(q[0]), g = (double) scale_quantum_to_map(q[1]),
+                   b = (double) scale_quantum_to_map(q[2]);
+      float o[3];
+      for (k = 0; k < 3; k++) {
+        double v;
+        if (forward) v = ((c[k][0] * r + c[k][1] * g) + c[k][2] * b) + (k == 0 ? 0.0 : 32768.0);
+        else v = (ix[k] * r + iy[k] * (2.0 * g - 65535.0)) + iz[k] * (2.0 * b - 65535.0);
+        o[k] = scale_map_to_quantum(v);
+      }
+      q[0] = o[0]; q[1] = o[1]; q[2] = o[2];
+    } else if (cs == ORC_CS_CMY) {
+      for (k = 0; k < 3; k++) {
+        if (forward) q[k] = (float) (QR * (QS * (QR - (double) q[k])));
+        else q[k] = (float) (QR * (1.0 - QS * (double) q[k]));
+      }
+    } else if (forward) {
+      const double R = q[0], G = q[1], B = q[2];
+      float o[3];
+      for (k = 0; k < 3; k++) {
+        double X = QS * ((gm->m[k][0] * R + gm->m[k][1] * G) + gm->m[k][2] * B);
+        if (k) X += 0.5;
+        o[k] = (float) (QR * X);
+      }
+      q[0] = o[0]; q[1] = o[1]; q[2] = o[2];
+    } else {
+      const double Y = QS * q[0], U = QS * q[1] - 0.5, V = QS * q[2] - 0.5;
+      float o[3];
+      for (k = 0; k < 3; k++) {
+        const double t = gm->m[k][0] == 1.0 ? Y : gm->m[k][0] * Y;
+        o[k] = (float) (QR * ((t + gm->m[k][1] * U) + gm->m[k][2] * V));
+      }
+      q[0] = o[0]; q[1] = o[1]; q[2] = o[2];
+    }
+  }
+  return 0;
+}
+
+/* colorspace.c:1751-1783 TransformImageColorspace: anything that is not sRGB goes back to sRGB
+   first (TransformsRGBImage), then forward (sRGBTransformImage). */
+int orc_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to)
+{
+  const long n = (long) (w * h);
+  int rc;
+  if (ch < 3) return -1;
+  if (from == to) return 0;
+  if (is_core_space(from) && is_core_space(to)) return colorspace_core(buf, w, h, ch, from, to);
+  if (from != ORC_CS_SRGB) {
+    rc = is_core_space(from) ? colorspace_core(buf, w, h, ch, from, ORC_CS_SRGB)
+                             : colorspace_matrix_leg(buf, n, ch, from, 0);
+    if (rc) return rc;
+  }
+  if (to == ORC_CS_SRGB) return 0;
+  return is_core_space(to) ? colorspace_core(buf, w, h, ch, ORC_CS_SRGB, to) : colorspace_matrix_leg(buf, n, ch, to, 1);
+}
 
 /* ------------------------------------------------------------------------------------------
    threshold.c point operators (in place).

@@ -67,7 +67,9 @@ def main():
                     out[f"{tag}/resize_{fname}_{ow}x{oh}"] = dst
             if ch >= 3:
                 for frm, to, cname in ((23, 11, "srgb_lab"), (23, 26, "srgb_xyz"), (23, 21, "srgb_rgb"),
-                                       (11, 23, "lab_srgb"), (21, 23, "rgb_srgb")):
+                                       (11, 23, "lab_srgb"), (21, 23, "rgb_srgb"), (23, 18, "srgb_ohta"),
+                                       (23, 19, "srgb_rec601ycbcr"), (20, 23, "rec709ycbcr_srgb"), (23, 30, "srgb_yiq"),
+                                       (32, 23, "yuv_srgb"), (23, 1, "srgb_cmy"), (27, 23, "ycbcr_srgb")):
                     buf = src.copy()
                     assert r.ref_colorspace(P(buf), W, H, ch, frm, to) == 0
                     out[f"{tag}/colorspace_{cname}"] = buf

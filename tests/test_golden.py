@@ -17,7 +17,8 @@ KERNEL_ARGS = {"Disk:3": ("disk", 3, 1, 0, 0), "Diamond:2": ("diamond", 2, 1, 0,
 METHODS = {"erode": 3, "dilate": 4, "open": 8, "close": 9, "smooth": 12, "edgein": 13, "edgeout": 14, "edge": 15,
            "tophat": 16, "bottomhat": 17}
 FILTERS = {"lanczos": 22, "mitchell": 12, "undefined": 0, "triangle": 3, "point": 1}
-SPACES = {"srgb": 23, "lab": 11, "xyz": 26, "rgb": 21}
+SPACES = {"srgb": 23, "lab": 11, "xyz": 26, "rgb": 21, "ohta": 18, "rec601ycbcr": 19, "rec709ycbcr": 20, "yiq": 30,
+          "yuv": 32, "cmy": 1, "ycbcr": 27}
 
 
 def golden_cases(tag):

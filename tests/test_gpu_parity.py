@@ -310,6 +310,29 @@ def test_colorspace(ch, frm, to):
         assert np.array_equal(a.pixels[..., 3], src[..., 3])   # alpha untouched
 
 
+@pytest.mark.parametrize("cs", [1, 18, 19, 20, 27, 29, 30, 31, 32])
+@pytest.mark.parametrize("kind", ["noise", "hdr"])
+def test_matrix_and_lut_colorspaces(cs, kind):
+    """CMY / YCbCr / YDbDr / YIQ / YPbPr / YUV (generic branch) and OHTA / Rec601YCbCr / Rec709YCbCr (LUT branch):
+    unfused double arithmetic in the reference's order => bit exact on the matrix leg; <= 1 ULP when the chain
+    passes through Lab / linear RGB."""
+    for ch in (3, 4):
+        src = make_image(131, 67, ch, seed=70 + cs, kind=kind)
+        src[0, :4, :3] = [[0, 0, 0], [65535, 65535, 65535], [0.4, 0.5, 0.6], [65534.6, 70000, -3]]
+        for frm, to, bar in ((23, cs, 0), (cs, 23, 0), (cs, 11, 1), (21, cs, 1), (cs, 18 if cs != 18 else 30, 0)):
+            want = src.copy()
+            assert oracle().orc_colorspace(P(want), 131, 67, ch, frm, to) == 0
+            img = _dev(src.copy())
+            img.colorspace = frm
+            assert im.TransformImageColorspace(img, to) is True and img.colorspace == to
+            assert max_ulp(_host(img), want) <= bar, (ch, frm, to)
+    h = im.Image(make_image(33, 21, 4, seed=3))                      # host-buffer entry point
+    want = h.pixels.copy()
+    assert oracle().orc_colorspace(P(want), 33, 21, 4, 23, cs) == 0
+    im.TransformImageColorspace(h, cs)
+    assert max_ulp(h.pixels, want) == 0
+
+
 def test_config4_lab_then_dilate_512():
     """configs[3] at reduced size: sRGB->Lab then 7x7 Disk dilate."""
     src = make_image(512, 512, 4, seed=42)

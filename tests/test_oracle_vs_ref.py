@@ -117,6 +117,25 @@ def test_threshold_point_ops_bit_exact(ch, kind):
         assert max_ulp(got, want) == 0, (op, thr, spec)
 
 
+MATRIX_SPACES = [1, 18, 19, 20, 27, 29, 30, 31, 32]   # CMY, OHTA, Rec601YCbCr, Rec709YCbCr, YCbCr, YDbDr, YIQ, YPbPr, YUV
+
+
+@pytest.mark.parametrize("cs", MATRIX_SPACES)
+@pytest.mark.parametrize("kind", ["noise", "hdr"])
+def test_matrix_and_lut_colorspaces_bit_exact(cs, kind):
+    """Generic-branch matrix spaces and the LUT branch (colorspace.c:1229-1494, :2560-2830), both
+    directions and chained through sRGB (colorspace.c:1773), incl. out-of-range samples (HDRI) that the
+    16-bit map quantisation clamps."""
+    for ch in (3, 4):
+        src = make_image(64, 48, ch, seed=8, kind=kind)
+        src[0, :4, :3] = [[0, 0, 0], [65535, 65535, 65535], [0.4, 0.5, 0.6], [65534.6, 70000, -3]]
+        for frm, to in ((23, cs), (cs, 23), (cs, 11), (21, cs), (cs, 18 if cs != 18 else 30)):
+            a, b = src.copy(), src.copy()
+            assert util.ref().ref_colorspace(P(a), 64, 48, ch, frm, to) == 0
+            assert oracle().orc_colorspace(P(b), 64, 48, ch, frm, to) == 0
+            assert max_ulp(a, b) == 0, (ch, frm, to)
+
+
 def test_thread_count_independence():
     """results do not depend on the OpenMP thread count."""
     src = make_image(128, 96, 4, seed=1)
