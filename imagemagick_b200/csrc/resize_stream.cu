@@ -19,10 +19,10 @@
 // completes every S steps (double accumulation, one rounding to float, resize.c:3472-3484).
 //
 //  vertical (axis 1): lane = pixel column, 512-byte coalesced row reads, register prefetch ring.
-//  horizontal (axis 0): lane = image row.  Each warp stages 8-pixel (128-byte, line-aligned)
+//  horizontal (axis 0): lane = image row.  Each warp stages 16-pixel (256-byte, line-aligned)
 //    chunks of its 32 rows into a private shared-memory ring with cp.async (LDGSTS) -- full-line
 //    global requests, no block barriers -- and reads its own row back with conflict-free LDS.128
-//    (row pitch 144 B).  Outputs are 16-byte stores; eight consecutive steps of a lane fill a line.
+//    (row pitch 272 B).  Outputs are 16-byte stores; eight consecutive steps of a lane fill a line.
 //
 // Outputs outside the streamed runs (the image borders, where the window is clipped, and the very
 // short low-binade runs) are produced by the generic gather kernels of resize.cu.
@@ -208,9 +208,12 @@ __global__ void __launch_bounds__(128, 3) resize_v_stream_kernel(const StreamArg
 
 // -------------------------------------------------------------------------------- horizontal
 // grid (total strips, ceil(height/128)); warp = 32 rows (lane = row), private cp.async ring.
-constexpr int kChunkPx = 8;                         // pixels per row per ring slot (128 B)
-constexpr int kRowPitch = kChunkPx * 16 + 16;       // 144 B: (9*row + k) mod 8 distinct => conflict-free
-constexpr int kSlotBytes = 32 * kRowPitch;          // 4608 B
+// CHUNK = pixels per row per ring slot: 8 (128 B, one line) or 16 (256 B: better DRAM page locality, half the
+// resident warps).  Row pitch = CHUNK*16 + 16 bytes: an odd multiple of 16 => (pitch/16 * row + k) mod 8 distinct.
+template <int CHUNK> struct HRing {
+  static constexpr int kRowPitch = CHUNK * 16 + 16;
+  static constexpr int kSlotBytes = 32 * kRowPitch;
+};
 
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void *gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr));
@@ -221,9 +224,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int K>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K)); }
 
-template <int S, int N, int NSLOT, int MINB>
+template <int S, int N, int NSLOT, int MINB, int CHUNK>
 __global__ void __launch_bounds__(128, MINB) resize_h_stream_kernel(const StreamArgs a) {
   using T = Rot<S, N>;
+  constexpr int kChunkPx = CHUNK, kRowPitch = HRing<CHUNK>::kRowPitch, kSlotBytes = HRing<CHUNK>::kSlotBytes;
+  constexpr int kLanesPerRow = CHUNK, kRowsPerInstr = 32 / CHUNK, kInstr = 32 / kRowsPerInstr;
   constexpr int R = T::R, P = T::P, BODY = T::BODY;
   extern __shared__ __align__(128) unsigned char ring_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -243,8 +248,8 @@ __global__ void __launch_bounds__(128, MINB) resize_h_stream_kernel(const Stream
   const int p0 = st.src0;                            // absolute source pixel of step 0
   const int c0 = p0 / kChunkPx;                      // first chunk (line aligned)
   const int nchunks = (p0 + S * (st.nout - 1) + N + kChunkPx - 1) / kChunkPx - c0;   // steps past the last tap read stale slots
-  // loader role: instruction j copies pixel (lane & 7) of row 4j + (lane >> 3)
-  const int lrow = lane >> 3, lpx = lane & 7;
+  // loader role: instruction j copies pixel (lane % CHUNK) of row (32/CHUNK)*j + lane / CHUNK
+  const int lrow = lane / kLanesPerRow, lpx = lane % kLanesPerRow;
   const size_t pitch_b = static_cast<size_t>(a.width) * 16;
   const unsigned char *srcb = reinterpret_cast<const unsigned char *>(a.src);
   const int last_px = a.in_n - 1;
@@ -253,8 +258,8 @@ __global__ void __launch_bounds__(128, MINB) resize_h_stream_kernel(const Stream
       const int px = min((c0 + chunk_rel) * kChunkPx + lpx, last_px);
       const unsigned slot = ring_s + static_cast<unsigned>(chunk_rel % NSLOT) * kSlotBytes;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = 4 * j + lrow;
+      for (int j = 0; j < kInstr; ++j) {
+        const int r = kRowsPerInstr * j + lrow;
         const int y = min(row0 + r, a.height - 1);
         cp_async16(slot + r * kRowPitch + lpx * 16, srcb + static_cast<size_t>(y) * pitch_b + static_cast<size_t>(px) * 16);
       }
@@ -309,8 +314,10 @@ __global__ void __launch_bounds__(128, MINB) resize_h_stream_kernel(const Stream
 
 template <int S, int N>
 int launch_sn(StreamArgs a, int axis, cudaStream_t s) {
-  static int strip_env = -1, slots_env = -1;
+  static int strip_env = -1, slots_env = -1, chunk_env = 0;
   if (strip_env < 0) {
+    const char *g = std::getenv("MB200_RESIZE_CHUNK");
+    chunk_env = g ? std::atoi(g) : 16;      // 16384^2 -> 8192^2: 2.02 ms with 128-byte chunks, 1.83 ms with 256-byte chunks
     const char *e = std::getenv("MB200_RESIZE_STRIP");
     strip_env = e ? std::atoi(e) : 0;
     const char *f = std::getenv("MB200_RESIZE_SLOTS");
@@ -336,16 +343,21 @@ int launch_sn(StreamArgs a, int axis, cudaStream_t s) {
   if (nstrips <= 0 || nstrips > 65535 || lanes_blocks > 65535) return MB200_EUNSUPPORTED;
   if (axis == 1) {
     resize_v_stream_kernel<S, N><<<dim3(lanes_blocks, nstrips), 128, 0, s>>>(a);
+  } else if (chunk_env == 16) {                    // 256-byte chunks, 3-slot rings, 2 CTAs / SM
+    constexpr int smem = 4 * 3 * HRing<16>::kSlotBytes;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 3, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    resize_h_stream_kernel<S, N, 3, 2, 16><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a);
   } else if (slots_env == 3) {                     // 4 CTAs / SM, 3-slot rings (221 KB of shared memory per SM)
-    constexpr int smem = 4 * 3 * kSlotBytes;
+    constexpr int smem = 4 * 3 * HRing<8>::kSlotBytes;
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    resize_h_stream_kernel<S, N, 3, 4><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a);
+    if (!attr) { cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 3, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    resize_h_stream_kernel<S, N, 3, 4, 8><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a);
   } else {
-    constexpr int smem = 4 * 4 * kSlotBytes;
+    constexpr int smem = 4 * 4 * HRing<8>::kSlotBytes;
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    resize_h_stream_kernel<S, N, 4, 3><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a);
+    if (!attr) { cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 4, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    resize_h_stream_kernel<S, N, 4, 3, 8><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a);
   }
   return MB200_OK;
 }
