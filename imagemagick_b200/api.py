@@ -7,7 +7,7 @@ include/magick_b200.h:
     BlurImage, GaussianBlurImage, ConvolveImage, UnsharpMaskImage   effect.c:765/1709/1170/4256
     SharpenImage, EdgeImage                                         effect.c:3991/1520
     MorphologyImage, AcquireKernelInfo                              morphology.c:4129/485
-    ResizeImage                                                     resize.c:3761
+    ResizeImage, SampleImage                                        resize.c:3761/3907
     TransformImageColorspace                                        colorspace.c:1751
     BilevelImage, BlackThresholdImage, WhiteThresholdImage, ClampImage  threshold.c:805/927/2518/1087
 
@@ -228,6 +228,21 @@ def ResizeImage(image: Image, columns: int, rows: int, filter: int = UndefinedFi
     else:
         check(lib.mb200_resize_image(image._ptr(), image.columns, image.rows, image.channels, out._ptr(), columns,
                                      rows, int(filter)))
+    return out
+
+
+def SampleImage(image: Image, columns: int, rows: int) -> Image:
+    """MagickCore/resize.c:3907 -- nearest-sample gather."""
+    if columns <= 0 or rows <= 0:
+        raise MagickB200Error(_lib.EINVAL, "NegativeOrZeroImageSize")
+    lib = _lib.load()
+    out = image._new_like(rows=rows, columns=columns)
+    if image.on_device:
+        _activate(image)
+        check(lib.mb200_sample_image_dev(image._ptr(), image.columns, image.rows, image.channels, out._ptr(), columns,
+                                         rows, _stream(image)))
+    else:
+        check(lib.mb200_sample_image(image._ptr(), image.columns, image.rows, image.channels, out._ptr(), columns, rows))
     return out
 
 

@@ -785,3 +785,30 @@ int mb200_edge_image(const float *src, float *dst, size_t w, size_t h, int ch, d
 
 }  // extern "C"
 
+// ---- SampleImage (resize.c:3907) --------------------------------------------------------------------------------
+extern "C" {
+
+int mb200_sample_image_dev(const float *src, size_t width, size_t height, int channels, float *dst, size_t out_width,
+                           size_t out_height, void *stream) {
+  if (!src || !dst || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "sample: bad arguments");
+  if (out_width == 0 || out_height == 0) return fail(MB200_EINVAL, "NegativeOrZeroImageSize");   // :3946
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  if (out_width == width && out_height == height) {                                              // :3948: clone
+    cudaError_t e = cudaMemcpyAsync(dst, src, width * height * channels * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    return e == cudaSuccess ? MB200_OK : cuda_fail(e, "sample: clone");
+  }
+  return launch_sample(src, width, height, channels, dst, out_width, out_height, s);
+}
+
+int mb200_sample_image(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh) {
+  if (!src || !dst || !valid_image(w, h, ch) || ow == 0 || oh == 0) return fail(MB200_EINVAL, "sample: bad arguments");
+  return with_staging(src, w * h * ch * sizeof(float), dst, ow * oh * ch * sizeof(float),
+                      [&](const float *s, float *d, cudaStream_t st) {
+                        return mb200_sample_image_dev(s, w, h, ch, d, ow, oh, st);
+                      });
+}
+
+}  // extern "C"
+

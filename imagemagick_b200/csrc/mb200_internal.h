@@ -79,6 +79,9 @@ int launch_unsharp_combine(const float *src, float *blur_inout, size_t n, double
 // CompositeImage(canvas, source, DifferenceCompositeOp) for same-size images (Edge/TopHat/BottomHat), in place on canvas
 int launch_composite_difference(float *canvas, const float *source, size_t npixels, int channels, void *stream);
 
+// SampleImage (resize.c:3907): nearest-sample gather, bit exact
+int launch_sample(const float *src, size_t w, size_t h, int channels, float *dst, size_t ow, size_t oh, void *stream);
+
 // threshold.c point operators in place; op: 0 bilevel (t[0]), 1 black, 2 white (t = r,g,b,a), 3 clamp
 int launch_threshold(float *buf, size_t npixels, int channels, int op, const double *thresholds, void *stream);
 

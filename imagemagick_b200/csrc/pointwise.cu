@@ -141,7 +141,54 @@ __global__ void __launch_bounds__(256) difference_kernel(float *__restrict__ can
   }
 }
 
+// SampleImage (MagickCore/resize.c:3907-4090): nearest-sample gather.  The source column / row of an output is
+// (ssize_t) (((j + 0.5 - MagickEpsilon) * in_n) / out_n) in double (:3973, :3996) -- single IEEE operations, so the
+// device evaluates the identical expression instead of reading offset tables.  Bit exact.
+template <int CH>
+__global__ void __launch_bounds__(256) sample_kernel(const float *__restrict__ src, float *__restrict__ dst, int w, int h,
+                                                     int ow, int oh) {
+  const int x = blockIdx.x * 256 + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= ow) return;
+  constexpr double kOffset = 0.5 - 1.0e-12;
+  const long xo = static_cast<long>(__ddiv_rn(__dmul_rn(__dadd_rn(static_cast<double>(x), kOffset), static_cast<double>(w)),
+                                               static_cast<double>(ow)));
+  const long yo = static_cast<long>(__ddiv_rn(__dmul_rn(__dadd_rn(static_cast<double>(y), kOffset), static_cast<double>(h)),
+                                               static_cast<double>(oh)));
+  const float *p = src + (static_cast<size_t>(yo) * w + static_cast<size_t>(xo)) * CH;
+  float *q = dst + (static_cast<size_t>(y) * ow + x) * CH;
+  if (CH == 4) *reinterpret_cast<float4 *>(q) = __ldg(reinterpret_cast<const float4 *>(p));
+  else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) q[c] = __ldg(p + c);
+  }
+}
+
 }  // namespace
+
+int launch_sample(const float *src, size_t w, size_t h, int channels, float *dst, size_t ow, size_t oh, void *stream) {
+  if (w > 0x3fffffffull || h > 0x3fffffffull || ow > 0x3fffffffull || oh > 65535ull * 1ull * 65535ull)
+    return fail(MB200_EINVAL, "sample: image too large");
+  if (oh > 65535) return fail(MB200_EUNSUPPORTED, "sample: more than 65535 output rows");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 grid(static_cast<unsigned>((ow + 255) / 256), static_cast<unsigned>(oh));
+  const int W = static_cast<int>(w), H = static_cast<int>(h), OW = static_cast<int>(ow), OH = static_cast<int>(oh);
+  switch (channels) {
+    case 1: sample_kernel<1><<<grid, 256, 0, s>>>(src, dst, W, H, OW, OH); break;
+    case 2: sample_kernel<2><<<grid, 256, 0, s>>>(src, dst, W, H, OW, OH); break;
+    case 3: sample_kernel<3><<<grid, 256, 0, s>>>(src, dst, W, H, OW, OH); break;
+    case 4:
+      if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) != 0)
+        return fail(MB200_EINVAL, "sample: RGBA buffers must be 16-byte aligned");
+      sample_kernel<4><<<grid, 256, 0, s>>>(src, dst, W, H, OW, OH);
+      break;
+    default: return fail(MB200_EINVAL, "sample: 1..4 channels");
+  }
+  count_launch();
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "sample launch");
+  return MB200_OK;
+}
 
 int launch_composite_difference(float *canvas, const float *source, size_t npixels, int channels, void *stream) {
   if (npixels == 0) return MB200_OK;

@@ -6,7 +6,7 @@
       -Wl,--wrap=BlurImage,--wrap=GaussianBlurImage,--wrap=ConvolveImage,--wrap=UnsharpMaskImage,\
           --wrap=MorphologyImage,--wrap=ResizeImage,--wrap=TransformImageColorspace,\
           --wrap=BilevelImage,--wrap=BlackThresholdImage,--wrap=WhiteThresholdImage,--wrap=ClampImage,\
-          --wrap=SharpenImage,--wrap=EdgeImage
+          --wrap=SharpenImage,--wrap=EdgeImage,--wrap=SampleImage
   and every caller of those exported functions (effect.c:765/1709/1170/4256, morphology.c:4129,
   resize.c:3761, colorspace.c:1751, threshold.c:805/927/2518/1087) reaches __wrap_X below.  Each wrapper follows the accelerate
   hook contract of effect.c:783-787 / resize.c:3818-3826: try the GPU; if the image is not
@@ -233,6 +233,29 @@ Image *B200AccelerateResizeImage(const Image *image, const size_t columns, const
   return out;
 }
 
+/* ---- SampleImage (resize.c:3907) ------------------------------------------------------------------------------ */
+Image *B200AccelerateSampleImage(const Image *image, const size_t columns, const size_t rows, ExceptionInfo *exception)
+{
+  const int ch = b200_channels(image);
+  const Quantum *p;
+  Quantum *q;
+  Image *out;
+  if (ch == 0 || columns == 0 || rows == 0 || mb200_device_count() <= 0) return (Image *) NULL;
+  if ((columns == image->columns) && (rows == image->rows)) return (Image *) NULL;      /* plain clone: CPU */
+  if (GetImageArtifact(image, "sample:offset") != (const char *) NULL) return (Image *) NULL;
+  p = GetVirtualPixels(image, 0, 0, image->columns, image->rows, exception);
+  if (p == (const Quantum *) NULL) return (Image *) NULL;
+  out = new_result(image, columns, rows, exception);
+  if (out == (Image *) NULL) return out;
+  q = GetAuthenticPixels(out, 0, 0, columns, rows, exception);
+  if (q == (Quantum *) NULL ||
+      mb200_sample_image((const float *) p, image->columns, image->rows, ch, (float *) q, columns, rows) != MB200_OK ||
+      SyncAuthenticPixels(out, exception) == MagickFalse)
+    return DestroyImage(out);
+  out->type = image->type;
+  return out;
+}
+
 /* ---- TransformImageColorspace (in place) ------------------------------------------------------------ */
 static int map_colorspace(ColorspaceType c)
 {
@@ -356,6 +379,7 @@ extern Image *__real_MorphologyImage(const Image *, const MorphologyMethod, cons
                                      ExceptionInfo *);
 extern Image *__real_ResizeImage(const Image *, const size_t, const size_t, const FilterType, ExceptionInfo *);
 extern MagickBooleanType __real_TransformImageColorspace(Image *, const ColorspaceType, ExceptionInfo *);
+extern Image *__real_SampleImage(const Image *, const size_t, const size_t, ExceptionInfo *);
 extern Image *__real_SharpenImage(const Image *, const double, const double, ExceptionInfo *);
 extern Image *__real_EdgeImage(const Image *, const double, ExceptionInfo *);
 extern MagickBooleanType __real_BilevelImage(Image *, const double, ExceptionInfo *);
@@ -468,4 +492,10 @@ Image *__wrap_EdgeImage(const Image *image, const double radius, ExceptionInfo *
 {
   TRY(B200AccelerateEdgeImage(image, radius, exception));
   return __real_EdgeImage(image, radius, exception);
+}
+
+Image *__wrap_SampleImage(const Image *image, const size_t columns, const size_t rows, ExceptionInfo *exception)
+{
+  TRY(B200AccelerateSampleImage(image, columns, rows, exception));
+  return __real_SampleImage(image, columns, rows, exception);
 }

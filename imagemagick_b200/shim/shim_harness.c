@@ -18,6 +18,7 @@ extern Image *__real_UnsharpMaskImage(const Image *, const double, const double,
 extern Image *__real_MorphologyImage(const Image *, const MorphologyMethod, const ssize_t, const KernelInfo *, ExceptionInfo *);
 extern Image *__real_ResizeImage(const Image *, const size_t, const size_t, const FilterType, ExceptionInfo *);
 extern MagickBooleanType __real_TransformImageColorspace(Image *, const ColorspaceType, ExceptionInfo *);
+extern Image *__real_SampleImage(const Image *, const size_t, const size_t, ExceptionInfo *);
 extern Image *__real_SharpenImage(const Image *, const double, const double, ExceptionInfo *);
 extern Image *__real_EdgeImage(const Image *, const double, ExceptionInfo *);
 extern MagickBooleanType __real_BilevelImage(Image *, const double, ExceptionInfo *);
@@ -90,6 +91,7 @@ int main(void)
   CHECK("UnsharpMaskImage RGBA", 2, UnsharpMaskImage(rgba, 0.0, 2.0, 1.5, 0.02, ex), CPU(__real_UnsharpMaskImage(rgba, 0.0, 2.0, 1.5, 0.02, ex)));
   CHECK("ResizeImage Lanczos 2x down RGBA", 1, ResizeImage(rgba, 258, 194, LanczosFilter, ex), CPU(__real_ResizeImage(rgba, 258, 194, LanczosFilter, ex)));
   CHECK("ResizeImage default up RGB", 1, ResizeImage(rgb, 450, 300, UndefinedFilter, ex), CPU(__real_ResizeImage(rgb, 450, 300, UndefinedFilter, ex)));
+  CHECK("SampleImage 517x389 -> 100x77 RGBA", 0, SampleImage(rgba, 100, 77, ex), CPU(__real_SampleImage(rgba, 100, 77, ex)));
   CHECK("SharpenImage(0,1) RGBA", 1, SharpenImage(rgba, 0.0, 1.0, ex), CPU(__real_SharpenImage(rgba, 0.0, 1.0, ex)));
   CHECK("EdgeImage(1) RGB", 1, EdgeImage(rgb, 1.0, ex), CPU(__real_EdgeImage(rgb, 1.0, ex)));
   k = AcquireKernelInfo("Disk:3", ex);
@@ -130,7 +132,7 @@ int main(void)
     t = DestroyImage(t);
   }
   printf("gpu hits %ld, cpu fallbacks %ld\n", B200ShimHits(), B200ShimFallbacks());
-  if (B200ShimHits() < 17) { printf("FAIL: operators did not reach the GPU path\n"); failures++; }
+  if (B200ShimHits() < 18) { printf("FAIL: operators did not reach the GPU path\n"); failures++; }
   rgba = DestroyImage(rgba); rgb = DestroyImage(rgb);
   ex = DestroyExceptionInfo(ex);
   MagickCoreTerminus();

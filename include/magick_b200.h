@@ -225,6 +225,10 @@ MB200_API int mb200_edge_image_dev(const float *src, float *dst, size_t width, s
    UndefinedFilter applies the reference's own default choice (:3806-3816). */
 MB200_API int mb200_resize_image_dev(const float *src, size_t width, size_t height, int channels,
     float *dst, size_t out_width, size_t out_height, int filter, void *stream);
+/* SampleImage (MagickCore/resize.c:3907): nearest-sample gather with the default sampling offset
+   (0.5 - MagickEpsilon; the "sample:offset" artifact is the shim's decline), bit exact. */
+MB200_API int mb200_sample_image_dev(const float *src, size_t width, size_t height, int channels,
+    float *dst, size_t out_width, size_t out_height, void *stream);
 /* TransformImageColorspace (MagickCore/colorspace.c:1751), in place on `buf`. */
 MB200_API int mb200_transform_colorspace_dev(float *buf, size_t width, size_t height,
     int channels, int from_colorspace, int to_colorspace, void *stream);
@@ -267,6 +271,8 @@ MB200_API int mb200_edge_image(const float *src, float *dst, size_t width, size_
     double radius);
 MB200_API int mb200_resize_image(const float *src, size_t width, size_t height, int channels,
     float *dst, size_t out_width, size_t out_height, int filter);
+MB200_API int mb200_sample_image(const float *src, size_t width, size_t height, int channels,
+    float *dst, size_t out_width, size_t out_height);
 MB200_API int mb200_transform_colorspace(float *buf, size_t width, size_t height, int channels,
     int from_colorspace, int to_colorspace);
 MB200_API int mb200_bilevel_image(float *buf, size_t width, size_t height, int channels, double threshold);

@@ -1321,3 +1321,22 @@ int orc_edge(const float *src, float *dst, size_t w, size_t h, int ch, double ra
   orc_kernel_free(&k);
   return rc;
 }
+
+
+/* resize.c:3907-4090 SampleImage (default sample:offset = 0.5 - MagickEpsilon) */
+int orc_sample(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh)
+{
+  const double off = 0.5 - EPS;
+  long y;
+  if (ow == 0 || oh == 0 || ch < 1 || ch > 4) return -1;
+#pragma omp parallel for schedule(static)
+  for (y = 0; y < (long) oh; y++) {
+    const long yo = (long) ((((double) y + off) * (double) h) / (double) oh);
+    size_t x;
+    for (x = 0; x < ow; x++) {
+      const long xo = (long) ((((double) x + off) * (double) w) / (double) ow);
+      memcpy(dst + ((size_t) y * ow + x) * ch, src + ((size_t) yo * w + (size_t) xo) * ch, (size_t) ch * sizeof(float));
+    }
+  }
+  return 0;
+}

@@ -65,6 +65,10 @@ def main():
                     dst = np.empty((oh, ow, ch), np.float32)
                     assert r.ref_resize(P(src), W, H, ch, P(dst), ow, oh, filt) == 0
                     out[f"{tag}/resize_{fname}_{ow}x{oh}"] = dst
+            for (ow, oh) in ((20, 15), (97, 50)):
+                dst = np.empty((oh, ow, ch), np.float32)
+                assert r.ref_sample(P(src), W, H, ch, P(dst), ow, oh) == 0
+                out[f"{tag}/sample_{ow}x{oh}"] = dst
             if ch >= 3:
                 for frm, to, cname in ((23, 11, "srgb_lab"), (23, 26, "srgb_xyz"), (23, 21, "srgb_rgb"),
                                        (11, 23, "lab_srgb"), (21, 23, "rgb_srgb"), (23, 18, "srgb_ohta"),

@@ -56,6 +56,10 @@ def run_oracle(src, name, clamp_src=None):
         ow, oh = map(int, size.split("x"))
         dst = np.empty((oh, ow, ch), np.float32)
         assert o.orc_resize(P(src), w, h, ch, P(dst), ow, oh, FILTERS[f]) == 0
+    elif name.startswith("sample_"):
+        ow, oh = map(int, name[7:].split("x"))
+        dst = np.empty((oh, ow, ch), np.float32)
+        assert o.orc_sample(P(src), w, h, ch, P(dst), ow, oh) == 0
     elif name.startswith("threshold_"):
         _, op, *rest = name.split("_")
         if op == "bilevel":
@@ -136,6 +140,9 @@ def run_cuda(im, src, name, clamp_src):
         _, f, size = name.split("_")
         ow, oh = map(int, size.split("x"))
         return host(im.ResizeImage(dev(src), ow, oh, FILTERS[f])), 1
+    if name.startswith("sample_"):
+        ow, oh = map(int, name[7:].split("x"))
+        return host(im.SampleImage(dev(src), ow, oh)), 0
     if name.startswith("threshold_"):
         _, op, *rest = name.split("_")
         img = dev(clamp_src if op == "clamp" else src)

@@ -230,6 +230,25 @@ def test_user_kernel_convolve_and_correlate(ch):
     assert max_ulp(got, want) <= 1
 
 
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+def test_sample_image_bit_exact(ch):
+    src = make_image(131, 77, ch, seed=9)
+    for ow, oh in ((65, 38), (66, 39), (262, 154), (131, 40), (50, 77), (300, 20), (1, 1), (131, 77), (7, 5), (1000, 3)):
+        want = np.empty((oh, ow, ch), np.float32)
+        assert oracle().orc_sample(P(src), 131, 77, ch, P(want), ow, oh) == 0
+        got = _host(im.SampleImage(_dev(src), ow, oh))
+        assert np.array_equal(got.view(np.int32), want.view(np.int32)), (ow, oh)
+    got = im.SampleImage(im.Image(src), 40, 30).pixels
+    want = np.empty((30, 40, ch), np.float32)
+    assert oracle().orc_sample(P(src), 131, 77, ch, P(want), 40, 30) == 0
+    assert np.array_equal(got.view(np.int32), want.view(np.int32))
+    # the offsets are exact at awkward ratios and large sizes: (j + 0.5 - eps) * in / out evaluated in IEEE double
+    big = make_image(4099, 3, ch, seed=2)
+    want = np.empty((2, 3001, ch), np.float32)
+    assert oracle().orc_sample(P(big), 4099, 3, ch, P(want), 3001, 2) == 0
+    assert np.array_equal(_host(im.SampleImage(_dev(big), 3001, 2)).view(np.int32), want.view(np.int32))
+
+
 FILTERS = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33]
 
 

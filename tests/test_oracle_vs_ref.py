@@ -41,6 +41,17 @@ def test_sharpen_edge_bit_exact(ch, kind):
         assert max_ulp(a, b) == 0
 
 
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+def test_sample_bit_exact(ch):
+    """resize.c:3907 SampleImage: the double offset arithmetic picks identical source samples."""
+    src = make_image(131, 77, ch, seed=9)
+    for ow, oh in ((65, 38), (66, 39), (262, 154), (131, 40), (50, 77), (300, 20), (1, 1), (7, 5), (1000, 3)):
+        a, b = np.empty((oh, ow, ch), np.float32), np.empty((oh, ow, ch), np.float32)
+        assert util.ref().ref_sample(P(src), 131, 77, ch, P(a), ow, oh) == 0
+        assert oracle().orc_sample(P(src), 131, 77, ch, P(b), ow, oh) == 0
+        assert np.array_equal(a.view(np.int32), b.view(np.int32)), (ow, oh)
+
+
 @pytest.mark.parametrize("ch", [1, 4])
 def test_resize_all_filters_bit_exact(ch):
     src = make_image(47, 33, ch, seed=5, kind="alpha_blocks")
