@@ -90,6 +90,8 @@ PROTOTYPES = {
     "mb200_edge_image": (_i, [_vp, _vp, _sz, _sz, _i, _d]),
     "mb200_sample_image_dev": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _vp]),
     "mb200_sample_image": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz]),
+    "mb200_thumbnail_image_dev": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i, _vp]),
+    "mb200_thumbnail_image": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i]),
     "mb200_bilevel_image_dev": (_i, [_vp, _sz, _sz, _i, _d, _vp]),
     "mb200_black_threshold_image_dev": (_i, [_vp, _sz, _sz, _i, _i, C.c_char_p, _vp]),
     "mb200_white_threshold_image_dev": (_i, [_vp, _sz, _sz, _i, _i, C.c_char_p, _vp]),

@@ -7,7 +7,7 @@ include/magick_b200.h:
     BlurImage, GaussianBlurImage, ConvolveImage, UnsharpMaskImage   effect.c:765/1709/1170/4256
     SharpenImage, EdgeImage                                         effect.c:3991/1520
     MorphologyImage, AcquireKernelInfo                              morphology.c:4129/485
-    ResizeImage, SampleImage                                        resize.c:3761/3907
+    ResizeImage, SampleImage, ThumbnailImage (pixel path)           resize.c:3761/3907/4591
     TransformImageColorspace                                        colorspace.c:1751
     BilevelImage, BlackThresholdImage, WhiteThresholdImage, ClampImage  threshold.c:805/927/2518/1087
 
@@ -243,6 +243,22 @@ def SampleImage(image: Image, columns: int, rows: int) -> Image:
                                          rows, _stream(image)))
     else:
         check(lib.mb200_sample_image(image._ptr(), image.columns, image.rows, image.channels, out._ptr(), columns, rows))
+    return out
+
+
+def ThumbnailImage(image: Image, columns: int, rows: int, filter: int = UndefinedFilter) -> Image:
+    """MagickCore/resize.c:4591 -- pixel path (sample / box / LanczosSharp cascade); `filter` is image->filter."""
+    if columns <= 0 or rows <= 0:
+        raise MagickB200Error(_lib.EINVAL, "NegativeOrZeroImageSize")
+    lib = _lib.load()
+    out = image._new_like(rows=rows, columns=columns)
+    if image.on_device:
+        _activate(image)
+        check(lib.mb200_thumbnail_image_dev(image._ptr(), image.columns, image.rows, image.channels, out._ptr(), columns,
+                                            rows, int(filter), _stream(image)))
+    else:
+        check(lib.mb200_thumbnail_image(image._ptr(), image.columns, image.rows, image.channels, out._ptr(), columns,
+                                        rows, int(filter)))
     return out
 
 

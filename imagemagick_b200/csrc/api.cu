@@ -812,3 +812,54 @@ int mb200_sample_image(const float *src, size_t w, size_t h, int ch, float *dst,
 
 }  // extern "C"
 
+// ---- ThumbnailImage (resize.c:4591-4650), pixel path: SampleImage to 4x the target when both integer reduction
+// factors exceed 4, ResizeImage(Box) to 2x when they exceed 2, then ResizeImage(filter; the reference passes
+// image->filter, LanczosSharp when undefined).  The metadata the reference attaches afterwards (profile stripping,
+// Thumb::* properties) is control plane and stays with the caller.
+extern "C" {
+
+int mb200_thumbnail_image_dev(const float *src, size_t width, size_t height, int channels, float *dst, size_t columns,
+                              size_t rows, int filter, void *stream) {
+  if (!src || !dst || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "thumbnail: bad arguments");
+  if (columns == 0 || rows == 0) return fail(MB200_EINVAL, "NegativeOrZeroImageSize");
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  const size_t px = static_cast<size_t>(channels) * sizeof(float);
+  if (columns == width && rows == height) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, width * height * px, cudaMemcpyDeviceToDevice, s);
+    return e == cudaSuccess ? MB200_OK : cuda_fail(e, "thumbnail: clone");
+  }
+  const long x_factor = static_cast<long>(width) / static_cast<long>(columns);
+  const long y_factor = static_cast<long>(height) / static_cast<long>(rows);
+  const float *cur = src;
+  size_t cw = width, chh = height;
+  StreamAlloc a(s), b(s);
+  if (x_factor > 4 && y_factor > 4) {
+    rc = a.alloc(4 * columns * 4 * rows * px);
+    if (rc) return rc;
+    rc = mb200_sample_image_dev(cur, cw, chh, channels, static_cast<float *>(a.ptr), 4 * columns, 4 * rows, s);
+    if (rc) return rc;
+    cur = static_cast<const float *>(a.ptr); cw = 4 * columns; chh = 4 * rows;
+  }
+  if (x_factor > 2 && y_factor > 2) {
+    rc = b.alloc(2 * columns * 2 * rows * px);
+    if (rc) return rc;
+    rc = mb200_resize_image_dev(cur, cw, chh, channels, static_cast<float *>(b.ptr), 2 * columns, 2 * rows, MB200_BoxFilter, s);
+    if (rc) return rc;
+    cur = static_cast<const float *>(b.ptr); cw = 2 * columns; chh = 2 * rows;
+  }
+  return mb200_resize_image_dev(cur, cw, chh, channels, dst, columns, rows,
+                                filter == MB200_UndefinedFilter ? MB200_LanczosSharpFilter : filter, s);
+}
+
+int mb200_thumbnail_image(const float *src, size_t w, size_t h, int ch, float *dst, size_t columns, size_t rows, int filter) {
+  if (!src || !dst || !valid_image(w, h, ch) || columns == 0 || rows == 0) return fail(MB200_EINVAL, "thumbnail: bad arguments");
+  return with_staging(src, w * h * ch * sizeof(float), dst, columns * rows * ch * sizeof(float),
+                      [&](const float *s, float *d, cudaStream_t st) {
+                        return mb200_thumbnail_image_dev(s, w, h, ch, d, columns, rows, filter, st);
+                      });
+}
+
+}  // extern "C"
+

@@ -229,6 +229,12 @@ MB200_API int mb200_resize_image_dev(const float *src, size_t width, size_t heig
    (0.5 - MagickEpsilon; the "sample:offset" artifact is the shim's decline), bit exact. */
 MB200_API int mb200_sample_image_dev(const float *src, size_t width, size_t height, int channels,
     float *dst, size_t out_width, size_t out_height, void *stream);
+/* ThumbnailImage (MagickCore/resize.c:4591-4650), pixel path only: SampleImage to 4x the target when both
+   integer reduction factors exceed 4, ResizeImage(BoxFilter) to 2x when they exceed 2, then
+   ResizeImage(`filter` = image->filter; UndefinedFilter selects LanczosSharp like the reference).  The
+   profile stripping and Thumb::* properties the reference adds afterwards are left to the caller. */
+MB200_API int mb200_thumbnail_image_dev(const float *src, size_t width, size_t height, int channels,
+    float *dst, size_t columns, size_t rows, int filter, void *stream);
 /* TransformImageColorspace (MagickCore/colorspace.c:1751), in place on `buf`. */
 MB200_API int mb200_transform_colorspace_dev(float *buf, size_t width, size_t height,
     int channels, int from_colorspace, int to_colorspace, void *stream);
@@ -273,6 +279,8 @@ MB200_API int mb200_resize_image(const float *src, size_t width, size_t height, 
     float *dst, size_t out_width, size_t out_height, int filter);
 MB200_API int mb200_sample_image(const float *src, size_t width, size_t height, int channels,
     float *dst, size_t out_width, size_t out_height);
+MB200_API int mb200_thumbnail_image(const float *src, size_t width, size_t height, int channels,
+    float *dst, size_t columns, size_t rows, int filter);
 MB200_API int mb200_transform_colorspace(float *buf, size_t width, size_t height, int channels,
     int from_colorspace, int to_colorspace);
 MB200_API int mb200_bilevel_image(float *buf, size_t width, size_t height, int channels, double threshold);

@@ -1340,3 +1340,30 @@ int orc_sample(const float *src, size_t w, size_t h, int ch, float *dst, size_t 
   }
   return 0;
 }
+
+
+/* resize.c:4591-4650 ThumbnailImage, pixel path (image->filter undefined => LanczosSharp) */
+int orc_thumbnail(const float *src, size_t w, size_t h, int ch, float *dst, size_t columns, size_t rows)
+{
+  const long xf = (long) w / (long) columns, yf = (long) h / (long) rows;
+  const float *cur = src;
+  float *a = NULL, *b = NULL;
+  size_t cw = w, chh = h;
+  int rc = 0;
+  if (columns == w && rows == h) { memcpy(dst, src, w * h * (size_t) ch * sizeof(float)); return 0; }
+  if (xf > 4 && yf > 4) {
+    a = (float *) malloc(16 * columns * rows * (size_t) ch * sizeof(float));
+    if (!a) return -1;
+    rc = orc_sample(cur, cw, chh, ch, a, 4 * columns, 4 * rows);
+    cur = a; cw = 4 * columns; chh = 4 * rows;
+  }
+  if (rc == 0 && xf > 2 && yf > 2) {
+    b = (float *) malloc(4 * columns * rows * (size_t) ch * sizeof(float));
+    if (!b) { free(a); return -1; }
+    rc = orc_resize(cur, cw, chh, ch, b, 2 * columns, 2 * rows, ORC_F_BOX);
+    cur = b; cw = 2 * columns; chh = 2 * rows;
+  }
+  if (rc == 0) rc = orc_resize(cur, cw, chh, ch, dst, columns, rows, ORC_F_LANCZOS_SHARP);
+  free(a); free(b);
+  return rc;
+}

@@ -181,6 +181,15 @@ int ref_sample(const float *src, size_t w, size_t h, int ch, float *dst, size_t 
   END
 }
 
+__attribute__((visibility("default")))
+int ref_thumbnail(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh)
+{
+  BEGIN
+  im = make_image(src, w, h, ch, -1, ex);
+  if (im) { out = ThumbnailImage(im, ow, oh, ex); rc = export_image(out, dst, ow, oh, ch, ex); }
+  END
+}
+
 /* in place; from/to: ColorspaceType enum values (colorspace.h:27-67) */
 __attribute__((visibility("default")))
 int ref_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to)

@@ -249,6 +249,33 @@ def test_sample_image_bit_exact(ch):
     assert np.array_equal(_host(im.SampleImage(_dev(big), 3001, 2)).view(np.int32), want.view(np.int32))
 
 
+@pytest.mark.parametrize("ch", [1, 4])
+def test_thumbnail_pixel_path(ch):
+    """ThumbnailImage's cascade: the sample stage is exact; each of the (up to two) resize stages is a <= 1 ULP
+    operator fed by the previous stage, so the cascade is pinned stage by stage on the product's own intermediates
+    and end to end with the corresponding budget."""
+    src = make_image(640, 480, ch, seed=9, kind="alpha_blocks" if ch == 4 else "noise")
+    for ow, oh in ((64, 48), (100, 75), (200, 150), (320, 240), (400, 300), (640, 480), (31, 23)):
+        got = _host(im.ThumbnailImage(_dev(src), ow, oh))
+        want = np.empty((oh, ow, ch), np.float32)
+        assert oracle().orc_thumbnail(P(src), 640, 480, ch, P(want), ow, oh) == 0
+        stages = 1 + (640 // ow > 2 and 480 // oh > 2)
+        err = np.abs(got.astype(np.float64) - want.astype(np.float64)).max()
+        assert err <= stages * 1.5 * 0.00390625, (ow, oh, err)          # float ULPs at the top of the Quantum range
+        # stage-wise: reproduce the cascade from the product's own intermediates, each stage within 1 ULP
+        cur = _dev(src)
+        if 640 // ow > 4 and 480 // oh > 4:
+            cur = im.SampleImage(cur, 4 * ow, 4 * oh)
+        if 640 // ow > 2 and 480 // oh > 2:
+            cur = im.ResizeImage(cur, 2 * ow, 2 * oh, im.BoxFilter)
+        if (ow, oh) != (640, 480):
+            mid = np.ascontiguousarray(_host(cur))
+            last = np.empty((oh, ow, ch), np.float32)
+            assert oracle().orc_resize(P(mid), mid.shape[1], mid.shape[0], ch, P(last), ow, oh, 23) == 0
+            assert max_ulp(got, last) <= 1, (ow, oh)
+    assert max_ulp(im.ThumbnailImage(im.Image(src), 100, 75).pixels, _host(im.ThumbnailImage(_dev(src), 100, 75))) == 0
+
+
 FILTERS = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33]
 
 

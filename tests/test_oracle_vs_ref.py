@@ -53,6 +53,17 @@ def test_sample_bit_exact(ch):
 
 
 @pytest.mark.parametrize("ch", [1, 4])
+def test_thumbnail_pixel_path_bit_exact(ch):
+    """resize.c:4591 ThumbnailImage: sample (factors > 4) / box (factors > 2) / LanczosSharp cascade."""
+    src = make_image(640, 480, ch, seed=9, kind="alpha_blocks" if ch == 4 else "noise")
+    for ow, oh in ((64, 48), (100, 75), (200, 150), (320, 240), (400, 300), (640, 480), (31, 23)):
+        a, b = np.empty((oh, ow, ch), np.float32), np.empty((oh, ow, ch), np.float32)
+        assert util.ref().ref_thumbnail(P(src), 640, 480, ch, P(a), ow, oh) == 0
+        assert oracle().orc_thumbnail(P(src), 640, 480, ch, P(b), ow, oh) == 0
+        assert max_ulp(a, b) == 0, (ow, oh)
+
+
+@pytest.mark.parametrize("ch", [1, 4])
 def test_resize_all_filters_bit_exact(ch):
     src = make_image(47, 33, ch, seed=5, kind="alpha_blocks")
     for filt in [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33]:
