@@ -1018,11 +1018,8 @@ int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int nta
     a.pitch = a.seg_w | 1;
     const int rows_per_cta = 4 * (32 / a.channels);
     const size_t smem = static_cast<size_t>(rows_per_cta) * a.pitch * a.channels * sizeof(float);
-    static bool attr_set = false;   // per instantiation
-    if (!attr_set) {
+    if (smem > 48 * 1024)            // per device attribute: set on every launch that needs it (a few microseconds)
       cudaFuncSetAttribute(conv_row_kernel<NT, MODE, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_set = true;
-    }
     dim3 grid((a.width + a.strip - 1) / a.strip, (a.height + rows_per_cta - 1) / rows_per_cta);
     conv_row_kernel<NT, MODE, kMinBlocks><<<grid, 128, smem, stream>>>(a, taps);
   }

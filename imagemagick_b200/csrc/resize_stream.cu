@@ -347,18 +347,15 @@ int launch_sn(StreamArgs a, int axis, cudaStream_t s) {
     resize_v_stream_kernel<S, N><<<dim3(lanes_blocks, nstrips), 128, 0, s>>>(a);
   } else if (chunk_env == 16) {                    // 256-byte chunks, 3-slot rings, 2 CTAs / SM
     constexpr int smem = 4 * 3 * HRing<16>::kSlotBytes;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 3, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 3, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device; cheap
     resize_h_stream_kernel<S, N, 3, 2, 16><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a);
   } else if (slots_env == 3) {                     // 4 CTAs / SM, 3-slot rings (221 KB of shared memory per SM)
     constexpr int smem = 4 * 3 * HRing<8>::kSlotBytes;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 3, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 3, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     resize_h_stream_kernel<S, N, 3, 4, 8><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a);
   } else {
     constexpr int smem = 4 * 4 * HRing<8>::kSlotBytes;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 4, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 4, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     resize_h_stream_kernel<S, N, 4, 3, 8><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a);
   }
   return MB200_OK;
