@@ -109,3 +109,23 @@ def test_no_gpu_means_loud_failure_not_cpu_fallback():
     with pytest.raises(im.MagickB200Error):
         im.ResizeImage(im.Image(src), 4, 4, im.LanczosFilter)
     assert _lib.load().mb200_device_count() == 0
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm): one JSON line with the
+    contract's keys; it times the real reference (oracle/_ref) when that library exists, else the oracle port."""
+    import json
+    import subprocess
+    import sys
+    env = dict(**__import__("os").environ, OMP_NUM_THREADS="")
+    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0, p.stderr[-500:]
+    line = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "Mpixels/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
