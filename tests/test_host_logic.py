@@ -129,3 +129,39 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+def test_sharpen_and_edge_kernels_match_the_reference_taps():
+    """effect.c:3991 / :1520 build their kernels inline; convolving a one-pixel impulse with the real
+    SharpenImage / EdgeImage returns those taps (reflected), which must equal the product's host-built kernels."""
+    lib = _lib.load()
+    for name, build, ref_call in (
+            ("sharpen", lambda: lib.mb200_sharpen_kernel(0.0, 1.0), lambda s, d, n: util.ref().ref_sharpen(util.P(s), util.P(d), n, n, 1, 0.0, 1.0)),
+            ("sharpen r2", lambda: lib.mb200_sharpen_kernel(2.0, 0.7), lambda s, d, n: util.ref().ref_sharpen(util.P(s), util.P(d), n, n, 1, 2.0, 0.7)),
+            ("edge", lambda: lib.mb200_edge_kernel(1.0), lambda s, d, n: util.ref().ref_edge(util.P(s), util.P(d), n, n, 1, 1.0))):
+        k = im.KernelInfo(build())
+        vals, kx, ky = k.arrays()[0]
+        w = vals.shape[0]
+        n = w + 8
+        src = np.zeros((n, n, 1), np.float32)
+        src[n // 2, n // 2, 0] = 1.0
+        dst = np.empty_like(src)
+        assert ref_call(src, dst, n) == 0
+        got = dst[n // 2 - ky: n // 2 - ky + w, n // 2 - kx: n // 2 - kx + w, 0]
+        want = vals[::-1, ::-1].astype(np.float32)          # convolution reflects the kernel
+        assert np.array_equal(got, want), name
+
+
+def test_threshold_geometry_is_parsed_before_the_device_is_touched():
+    """Black/WhiteThreshold: syntax the host parser does not take and images the reference first promotes
+    (gray) or gamma-encodes (linear RGB) are declined (EUNSUPPORTED) -- decided on the host, GPU or not."""
+    lib = _lib.load()
+    buf = np.zeros((4, 4, 4), np.float32)
+    for bad in (b"50%x20", b"a,b", b"1,2,3,4,5", b""):
+        assert lib.mb200_black_threshold_image_dev(buf.ctypes.data, 4, 4, 4, 23, bad, None) == _lib.EUNSUPPORTED
+    assert lib.mb200_white_threshold_image_dev(buf.ctypes.data, 4, 4, 2, 23, b"50%", None) == _lib.EUNSUPPORTED   # gray+alpha
+    assert lib.mb200_white_threshold_image_dev(buf.ctypes.data, 4, 4, 4, 21, b"50%", None) == _lib.EUNSUPPORTED   # linear RGB
+    if lib.mb200_device_count() == 0:                            # (never hand a host pointer to a real device)
+        rc = lib.mb200_black_threshold_image_dev(buf.ctypes.data, 4, 4, 4, 23, b"10%,20%,30%", None)
+        assert rc in (_lib.ENODEVICE, _lib.ECUDA)                # well-formed: only the missing device stops it
