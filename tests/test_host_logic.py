@@ -165,3 +165,22 @@ def test_threshold_geometry_is_parsed_before_the_device_is_touched():
     if lib.mb200_device_count() == 0:                            # (never hand a host pointer to a real device)
         rc = lib.mb200_black_threshold_image_dev(buf.ctypes.data, 4, 4, 4, 23, b"10%,20%,30%", None)
         assert rc in (_lib.ENODEVICE, _lib.ECUDA)                # well-formed: only the missing device stops it
+
+
+def test_header_is_plain_c99_and_links(tmp_path):
+    """The boundary is a C ABI: include/magick_b200.h compiles as strict C99 (no C++-isms, no CUDA types) and
+    examples/blur_resize.c links against the shared library and runs (it stops after printing the version when
+    there is no device)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    exe = tmp_path / "blur_resize"
+    libdir = _lib.LIB_PATH.parent
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT / 'include'}",
+                    str(ROOT / "examples" / "blur_resize.c"), f"-L{libdir}", "-lmagickb200", f"-Wl,-rpath,{libdir}",
+                    "-o", str(exe)], check=True, capture_output=True)
+    if _lib.load().mb200_device_count() == 0:
+        p = subprocess.run([str(exe), "64", "64"], capture_output=True, text=True, timeout=120)
+        assert p.returncode == 0 and "sm_100a" in p.stdout
