@@ -184,3 +184,20 @@ def test_header_is_plain_c99_and_links(tmp_path):
     if _lib.load().mb200_device_count() == 0:
         p = subprocess.run([str(exe), "64", "64"], capture_output=True, text=True, timeout=120)
         assert p.returncode == 0 and "sm_100a" in p.stdout
+
+
+def test_process_filter_module_on_the_cpu_path():
+    """imagemagick_b200/shim/b200_filter.c (`magick ... -process "b200 blur 0x2 resize 50% ..."`): driven like
+    InvokeDynamicImageFilter on a two-image list.  Without a device every accelerate call declines, so the filter
+    must reproduce the stock operators bit for bit, keep the list intact and reject unknown operators."""
+    import os
+    import subprocess
+    exe = ROOT / "imagemagick_b200" / "lib" / "filter_harness"
+    if not exe.exists():
+        pytest.skip("filter_harness not built (needs the reference tree: python __graft_entry__.py)")
+    env = dict(os.environ)
+    if _lib.load().mb200_device_count() == 0:
+        env["B200_FILTER_EXPECT_EXACT"] = "1"
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300, env=env)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "ok" in p.stdout
