@@ -6,7 +6,7 @@
       -Wl,--wrap=BlurImage,--wrap=GaussianBlurImage,--wrap=ConvolveImage,--wrap=UnsharpMaskImage,\
           --wrap=MorphologyImage,--wrap=ResizeImage,--wrap=TransformImageColorspace,\
           --wrap=BilevelImage,--wrap=BlackThresholdImage,--wrap=WhiteThresholdImage,--wrap=ClampImage,\
-          --wrap=SharpenImage,--wrap=EdgeImage,--wrap=SampleImage
+          --wrap=SharpenImage,--wrap=EdgeImage,--wrap=SampleImage,--wrap=ThumbnailImage
   and every caller of those exported functions (effect.c:765/1709/1170/4256, morphology.c:4129,
   resize.c:3761, colorspace.c:1751, threshold.c:805/927/2518/1087) reaches __wrap_X below.  Each wrapper follows the accelerate
   hook contract of effect.c:783-787 / resize.c:3818-3826: try the GPU; if the image is not
@@ -498,4 +498,45 @@ Image *__wrap_SampleImage(const Image *image, const size_t columns, const size_t
 {
   TRY(B200AccelerateSampleImage(image, columns, rows, exception));
   return __real_SampleImage(image, columns, rows, exception);
+}
+
+/* ---- ThumbnailImage (resize.c:4591) ------------------------------------------------------------------------------
+   Its SampleImage / ResizeImage calls are made from inside resize.o, which --wrap does not redirect, so the pixel
+   cascade (:4617-4645) is re-issued here through the wrapped entry points (each stage takes the GPU or declines
+   to the CPU on its own).  The metadata half of the reference (page geometry, depth, profile stripping, the
+   Thumb::* properties) is NOT restated: the real ThumbnailImage is called on the finished thumbnail with its
+   own size -- a same-size call skips the resize block and only applies the metadata, which it derives from
+   fields the cascade's CloneImage-based results inherit from the source (filenames, magick_columns/rows, blob,
+   properties).  Only the page count refers to the source's image list and is set afterwards. */
+extern Image *__real_ThumbnailImage(const Image *, const size_t, const size_t, ExceptionInfo *);
+
+Image *__wrap_ThumbnailImage(const Image *image, const size_t columns, const size_t rows, ExceptionInfo *exception)
+{
+  Image *clone_image, *stage, *result;
+  ssize_t x_factor, y_factor;
+  if (!b200_on() || columns == 0 || rows == 0 || ((columns == image->columns) && (rows == image->rows)))
+    return __real_ThumbnailImage(image, columns, rows, exception);
+  x_factor = (ssize_t) image->columns / (ssize_t) columns;
+  y_factor = (ssize_t) image->rows / (ssize_t) rows;
+  clone_image = (Image *) NULL;                       /* result of the previous stage (NULL: still the source) */
+  if ((x_factor > 4) && (y_factor > 4)) {
+    stage = SampleImage(image, 4 * columns, 4 * rows, exception);
+    if (stage != (Image *) NULL) clone_image = stage;
+  }
+  if ((x_factor > 2) && (y_factor > 2)) {
+    stage = ResizeImage(clone_image != (Image *) NULL ? clone_image : image, 2 * columns, 2 * rows, BoxFilter, exception);
+    if (stage != (Image *) NULL) {
+      if (clone_image != (Image *) NULL) clone_image = DestroyImage(clone_image);
+      clone_image = stage;
+    }
+  }
+  stage = ResizeImage(clone_image != (Image *) NULL ? clone_image : image, columns, rows,
+                      image->filter == UndefinedFilter ? LanczosSharpFilter : image->filter, exception);
+  if (clone_image != (Image *) NULL) clone_image = DestroyImage(clone_image);
+  if (stage == (Image *) NULL) return (Image *) NULL;
+  result = __real_ThumbnailImage(stage, columns, rows, exception);     /* same size: metadata only */
+  stage = DestroyImage(stage);
+  if (result != (Image *) NULL)
+    (void) FormatImageProperty(result, "Thumb::Document::Pages", "%.20g", (double) GetImageListLength(image));
+  return result;
 }

@@ -201,3 +201,19 @@ def test_process_filter_module_on_the_cpu_path():
     p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300, env=env)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "ok" in p.stdout
+
+
+def test_wrapped_entry_points_fall_back_on_the_cpu():
+    """shim_harness (ld --wrap build of the unmodified reference) without a device: every wrapped entry point
+    declines silently and returns exactly what the stock function returns -- including __wrap_ThumbnailImage,
+    whose cascade is re-issued by the shim and whose Thumb::* metadata comes from the real function."""
+    import subprocess
+    exe = ROOT / "imagemagick_b200" / "lib" / "shim_harness"
+    if not exe.exists():
+        pytest.skip("shim_harness not built (needs the reference tree: python __graft_entry__.py)")
+    if _lib.load().mb200_device_count() != 0:
+        pytest.skip("device present: the GPU variant of this check is tests/test_gpu_parity.py::test_magickcore_shim_end_to_end")
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-500:]
+    assert "FAIL" not in p.stdout and "gpu hits 0" in p.stdout
+    assert p.stdout.count("ThumbnailImage RGBA") == 3
