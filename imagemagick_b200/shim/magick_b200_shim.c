@@ -6,7 +6,7 @@
       -Wl,--wrap=BlurImage,--wrap=GaussianBlurImage,--wrap=ConvolveImage,--wrap=UnsharpMaskImage,\
           --wrap=MorphologyImage,--wrap=ResizeImage,--wrap=TransformImageColorspace,\
           --wrap=BilevelImage,--wrap=BlackThresholdImage,--wrap=WhiteThresholdImage,--wrap=ClampImage,\
-          --wrap=SharpenImage,--wrap=EdgeImage,--wrap=SampleImage,--wrap=ThumbnailImage
+          --wrap=SharpenImage,--wrap=EdgeImage,--wrap=SampleImage,--wrap=ThumbnailImage,--wrap=MinifyImage,--wrap=ResampleImage
   and every caller of those exported functions (effect.c:765/1709/1170/4256, morphology.c:4129,
   resize.c:3761, colorspace.c:1751, threshold.c:805/927/2518/1087) reaches __wrap_X below.  Each wrapper follows the accelerate
   hook contract of effect.c:783-787 / resize.c:3818-3826: try the GPU; if the image is not
@@ -539,4 +539,28 @@ Image *__wrap_ThumbnailImage(const Image *image, const size_t columns, const siz
   if (result != (Image *) NULL)
     (void) FormatImageProperty(result, "Thumb::Document::Pages", "%.20g", (double) GetImageListLength(image));
   return result;
+}
+
+/* ---- MinifyImage (resize.c:3158) and ResampleImage (:3209): one-line callers of ResizeImage from inside resize.o,
+   which --wrap does not redirect; re-issued here through the wrapped ResizeImage. */
+extern Image *__real_MinifyImage(const Image *, ExceptionInfo *);
+extern Image *__real_ResampleImage(const Image *, const double, const double, const FilterType, ExceptionInfo *);
+
+Image *__wrap_MinifyImage(const Image *image, ExceptionInfo *exception)
+{
+  if (!b200_on() || image->columns < 2 || image->rows < 2) return __real_MinifyImage(image, exception);
+  return ResizeImage(image, image->columns / 2, image->rows / 2, SplineFilter, exception);          /* :3170 */
+}
+
+Image *__wrap_ResampleImage(const Image *image, const double x_resolution, const double y_resolution,
+                            const FilterType filter, ExceptionInfo *exception)
+{
+  Image *out;
+  size_t width, height;
+  if (!b200_on()) return __real_ResampleImage(image, x_resolution, y_resolution, filter, exception);
+  width = (size_t) (x_resolution * image->columns / (image->resolution.x == 0.0 ? 72.0 : image->resolution.x) + 0.5);   /* :3230 */
+  height = (size_t) (y_resolution * image->rows / (image->resolution.y == 0.0 ? 72.0 : image->resolution.y) + 0.5);
+  out = ResizeImage(image, width, height, filter, exception);
+  if (out != (Image *) NULL) { out->resolution.x = x_resolution; out->resolution.y = y_resolution; }
+  return out;
 }
