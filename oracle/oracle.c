@@ -1367,3 +1367,64 @@ int orc_thumbnail(const float *src, size_t w, size_t h, int ch, float *dst, size
   free(a); free(b);
   return rc;
 }
+
+
+/* ------------------------------------------------------------------------------------------
+   effect.c:2316-2345 GetMotionBlurKernel + :2347-2560 MotionBlurImage (groundwork for the next
+   hot-path row): a one-sided Gaussian of `width` taps walked along `angle` from the
+   output pixel, integer offsets ceil(w*cos - 0.5) / ceil(w*sin - 0.5), edge-replicated source
+   (cache.c:2663), alpha-weighted blend for the colour channels of images with alpha.
+   ------------------------------------------------------------------------------------------ */
+int orc_motion_blur(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma,
+                    double angle)
+{
+  const size_t width = orc_optimal_kernel_width_1d(radius, sigma);
+  const double s = fabs(sigma) < EPS ? EPS : sigma;                 /* MagickSigma */
+  double *kernel = (double *) malloc(width * sizeof(double)), normalize = 0.0;
+  long *ox = (long *) malloc(width * sizeof(long)), *oy = (long *) malloc(width * sizeof(long));
+  const int has_alpha = (ch == 2 || ch == 4);
+  double px, py;
+  size_t i;
+  long y;
+  if (!kernel || !ox || !oy) { free(kernel); free(ox); free(oy); return -1; }
+  for (i = 0; i < width; i++) {
+    kernel[i] = exp((-((double) i * i) / (double) (2.0 * s * s))) / (SQ2PI_ * s);
+    normalize += kernel[i];
+  }
+  for (i = 0; i < width; i++) kernel[i] /= normalize;
+  px = (double) width * sin((double) (PI_ * angle / 180.0));
+  py = (double) width * cos((double) (PI_ * angle / 180.0));
+  for (i = 0; i < width; i++) {
+    ox[i] = (long) ceil((double) ((double) i * py) / hypot(px, py) - 0.5);     /* CastDoubleToLong of a small value */
+    oy[i] = (long) ceil((double) ((double) i * px) / hypot(px, py) - 0.5);
+  }
+#pragma omp parallel for schedule(static)
+  for (y = 0; y < (long) h; y++) {
+    size_t x;
+    for (x = 0; x < w; x++) {
+      int c;
+      for (c = 0; c < ch; c++) {
+        double pixel = 0.0, gamma = 0.0;
+        size_t j;
+        const int blend = has_alpha && c != ch - 1;
+        for (j = 0; j < width; j++) {
+          long xx = (long) x + ox[j], yy = y + oy[j];
+          const float *r;
+          xx = xx < 0 ? 0 : (xx >= (long) w ? (long) w - 1 : xx);
+          yy = yy < 0 ? 0 : (yy >= (long) h ? (long) h - 1 : yy);
+          r = src + ((size_t) yy * w + (size_t) xx) * ch;
+          if (!blend) pixel += kernel[j] * (double) r[c];
+          else {
+            const double alpha = QS * (double) r[ch - 1];
+            pixel += kernel[j] * alpha * (double) r[c];
+            gamma += kernel[j] * alpha;
+          }
+        }
+        if (blend) pixel = perceptible_reciprocal(gamma) * pixel;
+        dst[((size_t) y * w + x) * ch + c] = (float) pixel;
+      }
+    }
+  }
+  free(kernel); free(ox); free(oy);
+  return 0;
+}

@@ -52,6 +52,18 @@ def test_sample_bit_exact(ch):
         assert np.array_equal(a.view(np.int32), b.view(np.int32)), (ow, oh)
 
 
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["noise", "alpha_blocks", "hdr"])
+def test_motion_blur_oracle_bit_exact(ch, kind):
+    """effect.c:2347 MotionBlurImage -- oracle groundwork for the next hot-path row."""
+    src = make_image(61, 47, ch, seed=13, kind=kind)
+    for rad, sig, ang in ((0, 2, 0), (0, 2, 45), (0, 3, 90), (0, 1.5, -30), (0, 4, 180), (5, 2, 270), (0, 2, 123.4)):
+        a, b = np.empty_like(src), np.empty_like(src)
+        assert util.ref().ref_motion_blur(P(src), P(a), 61, 47, ch, rad, sig, ang) == 0
+        assert oracle().orc_motion_blur(P(src), P(b), 61, 47, ch, rad, sig, ang) == 0
+        assert max_ulp(a, b) == 0, (rad, sig, ang)
+
+
 @pytest.mark.parametrize("ch", [1, 4])
 def test_thumbnail_pixel_path_bit_exact(ch):
     """resize.c:4591 ThumbnailImage: sample (factors > 4) / box (factors > 2) / LanczosSharp cascade."""
