@@ -92,6 +92,9 @@ PROTOTYPES = {
     "mb200_sample_image": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz]),
     "mb200_thumbnail_image_dev": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i, _vp]),
     "mb200_thumbnail_image": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i]),
+    "mb200_motion_blur_kernel": (_l, [_d, _d, _d, C.POINTER(_d), C.POINTER(_l), C.POINTER(_l), _sz]),
+    "mb200_motion_blur_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d, _d, _vp]),
+    "mb200_motion_blur_image": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d, _d]),
     "mb200_bilevel_image_dev": (_i, [_vp, _sz, _sz, _i, _d, _vp]),
     "mb200_black_threshold_image_dev": (_i, [_vp, _sz, _sz, _i, _i, C.c_char_p, _vp]),
     "mb200_white_threshold_image_dev": (_i, [_vp, _sz, _sz, _i, _i, C.c_char_p, _vp]),

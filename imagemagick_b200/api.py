@@ -5,7 +5,7 @@ Same names, argument meaning and error behaviour as the reference operators
 include/magick_b200.h:
 
     BlurImage, GaussianBlurImage, ConvolveImage, UnsharpMaskImage   effect.c:765/1709/1170/4256
-    SharpenImage, EdgeImage                                         effect.c:3991/1520
+    SharpenImage, EdgeImage, MotionBlurImage                        effect.c:3991/1520/2347
     MorphologyImage, AcquireKernelInfo                              morphology.c:4129/485
     ResizeImage, SampleImage, ThumbnailImage (pixel path)           resize.c:3761/3907/4591
     TransformImageColorspace                                        colorspace.c:1751
@@ -213,6 +213,12 @@ def SharpenImage(image: Image, radius: float, sigma: float) -> Image:
 def EdgeImage(image: Image, radius: float) -> Image:
     """MagickCore/effect.c:1520 -- ConvolveImage with the all -1 / centre n-1 kernel."""
     return _same_size_op(image, "mb200_edge_image_dev", "mb200_edge_image", float(radius))
+
+
+def MotionBlurImage(image: Image, radius: float, sigma: float, angle: float) -> Image:
+    """MagickCore/effect.c:2347."""
+    return _same_size_op(image, "mb200_motion_blur_image_dev", "mb200_motion_blur_image", float(radius), float(sigma),
+                         float(angle))
 
 
 def ResizeImage(image: Image, columns: int, rows: int, filter: int = UndefinedFilter) -> Image:

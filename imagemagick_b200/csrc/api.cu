@@ -863,3 +863,30 @@ int mb200_thumbnail_image(const float *src, size_t w, size_t h, int ch, float *d
 
 }  // extern "C"
 
+// ---- MotionBlurImage (effect.c:2347) ------------------------------------------------------------------------------
+extern "C" {
+
+int mb200_motion_blur_image_dev(const float *src, float *dst, size_t width, size_t height, int channels, double radius,
+                                double sigma, double angle, void *stream) {
+  if (!src || !dst || src == dst || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "motion blur: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  double taps[129];
+  long ox[129], oy[129];
+  const long n = mb200_motion_blur_kernel(radius, sigma, angle, taps, ox, oy, 129);
+  if (n < 0) return fail(MB200_EUNSUPPORTED, "motion blur: more than 129 taps");
+  return launch_motion_blur(src, dst, width, height, channels, taps, ox, oy, static_cast<int>(n), s);
+}
+
+int mb200_motion_blur_image(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma,
+                            double angle) {
+  if (!src || !dst || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "motion blur: bad arguments");
+  const size_t bytes = w * h * ch * sizeof(float);
+  return with_staging(src, bytes, dst, bytes, [&](const float *s, float *d, cudaStream_t st) {
+    return mb200_motion_blur_image_dev(s, d, w, h, ch, radius, sigma, angle, st);
+  });
+}
+
+}  // extern "C"
+

@@ -638,5 +638,27 @@ mb200_kernel_info *mb200_edge_kernel(double radius) {
   return k;
 }
 
-}  // extern "C"
+// MotionBlurImage's taps (GetMotionBlurKernel, effect.c:2316-2345) and offsets (:2390-2398).  Returns the tap count
+// (GetOptimalKernelWidth1D) or a negative error; arrays hold `max` entries.
+long mb200_motion_blur_kernel(double radius, double sigma, double angle, double *taps, long *offset_x, long *offset_y,
+                              size_t max) {
+  const size_t width = mb200_optimal_kernel_width_1d(radius, sigma);
+  if (taps == nullptr || offset_x == nullptr || offset_y == nullptr) return static_cast<long>(width);
+  if (width > max) return MB200_EINVAL;
+  const double s = std::fabs(sigma) < kEps ? kEps : sigma;            // MagickSigma
+  double normalize = 0.0;
+  for (size_t i = 0; i < width; ++i) {
+    taps[i] = std::exp((-(static_cast<double>(i) * static_cast<double>(i)) / (2.0 * s * s))) / (kSq2Pi * s);
+    normalize += taps[i];
+  }
+  for (size_t i = 0; i < width; ++i) taps[i] /= normalize;
+  const double px = static_cast<double>(width) * std::sin(kPi * angle / 180.0);
+  const double py = static_cast<double>(width) * std::cos(kPi * angle / 180.0);
+  for (size_t i = 0; i < width; ++i) {
+    offset_x[i] = static_cast<long>(std::ceil((static_cast<double>(i) * py) / std::hypot(px, py) - 0.5));
+    offset_y[i] = static_cast<long>(std::ceil((static_cast<double>(i) * px) / std::hypot(px, py) - 0.5));
+  }
+  return static_cast<long>(width);
+}
 
+}  // extern "C"

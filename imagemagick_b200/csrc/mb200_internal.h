@@ -79,6 +79,10 @@ int launch_unsharp_combine(const float *src, float *blur_inout, size_t n, double
 // CompositeImage(canvas, source, DifferenceCompositeOp) for same-size images (Edge/TopHat/BottomHat), in place on canvas
 int launch_composite_difference(float *canvas, const float *source, size_t npixels, int channels, void *stream);
 
+// MotionBlurImage (effect.c:2347): taps + integer offsets from the host, gather along the blur direction
+int launch_motion_blur(const float *src, float *dst, size_t w, size_t h, int channels, const double *taps, const long *ox,
+                       const long *oy, int width, void *stream);
+
 // SampleImage (resize.c:3907): nearest-sample gather, bit exact
 int launch_sample(const float *src, size_t w, size_t h, int channels, float *dst, size_t ow, size_t oh, void *stream);
 

@@ -6,7 +6,7 @@
       -Wl,--wrap=BlurImage,--wrap=GaussianBlurImage,--wrap=ConvolveImage,--wrap=UnsharpMaskImage,\
           --wrap=MorphologyImage,--wrap=ResizeImage,--wrap=TransformImageColorspace,\
           --wrap=BilevelImage,--wrap=BlackThresholdImage,--wrap=WhiteThresholdImage,--wrap=ClampImage,\
-          --wrap=SharpenImage,--wrap=EdgeImage,--wrap=SampleImage,--wrap=ThumbnailImage,--wrap=MinifyImage,--wrap=ResampleImage
+          --wrap=SharpenImage,--wrap=EdgeImage,--wrap=SampleImage,--wrap=ThumbnailImage,--wrap=MinifyImage,--wrap=ResampleImage,--wrap=MotionBlurImage
   and every caller of those exported functions (effect.c:765/1709/1170/4256, morphology.c:4129,
   resize.c:3761, colorspace.c:1751, threshold.c:805/927/2518/1087) reaches __wrap_X below.  Each wrapper follows the accelerate
   hook contract of effect.c:783-787 / resize.c:3818-3826: try the GPU; if the image is not
@@ -563,4 +563,25 @@ Image *__wrap_ResampleImage(const Image *image, const double x_resolution, const
   out = ResizeImage(image, width, height, filter, exception);
   if (out != (Image *) NULL) { out->resolution.x = x_resolution; out->resolution.y = y_resolution; }
   return out;
+}
+
+/* ---- MotionBlurImage (effect.c:2347; the reference's own hook is AccelerateMotionBlurImage, :2401) ------------------ */
+typedef struct { double radius, sigma, angle; } motion_args;
+static int op_motion(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
+{ const motion_args *m = (const motion_args *) a; return mb200_motion_blur_image(s, d, w, h, ch, m->radius, m->sigma, m->angle); }
+
+Image *B200AccelerateMotionBlurImage(const Image *image, const double radius, const double sigma, const double angle,
+                                     ExceptionInfo *exception)
+{
+  motion_args a;
+  a.radius = radius; a.sigma = sigma; a.angle = angle;
+  return run_same_size(image, op_motion, &a, exception);
+}
+
+extern Image *__real_MotionBlurImage(const Image *, const double, const double, const double, ExceptionInfo *);
+Image *__wrap_MotionBlurImage(const Image *image, const double radius, const double sigma, const double angle,
+                              ExceptionInfo *exception)
+{
+  TRY(B200AccelerateMotionBlurImage(image, radius, sigma, angle, exception));
+  return __real_MotionBlurImage(image, radius, sigma, angle, exception);
 }

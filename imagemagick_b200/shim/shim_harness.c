@@ -22,6 +22,7 @@ extern MagickBooleanType __real_TransformImageColorspace(Image *, const Colorspa
 extern Image *__real_SampleImage(const Image *, const size_t, const size_t, ExceptionInfo *);
 extern Image *__real_ThumbnailImage(const Image *, const size_t, const size_t, ExceptionInfo *);
 extern Image *__real_MinifyImage(const Image *, ExceptionInfo *);
+extern Image *__real_MotionBlurImage(const Image *, const double, const double, const double, ExceptionInfo *);
 extern Image *__real_ResampleImage(const Image *, const double, const double, const FilterType, ExceptionInfo *);
 extern int mb200_device_count(void);
 extern Image *__real_SharpenImage(const Image *, const double, const double, ExceptionInfo *);
@@ -96,6 +97,7 @@ int main(void)
   CHECK("UnsharpMaskImage RGBA", 2, UnsharpMaskImage(rgba, 0.0, 2.0, 1.5, 0.02, ex), CPU(__real_UnsharpMaskImage(rgba, 0.0, 2.0, 1.5, 0.02, ex)));
   CHECK("ResizeImage Lanczos 2x down RGBA", 1, ResizeImage(rgba, 258, 194, LanczosFilter, ex), CPU(__real_ResizeImage(rgba, 258, 194, LanczosFilter, ex)));
   CHECK("ResizeImage default up RGB", 1, ResizeImage(rgb, 450, 300, UndefinedFilter, ex), CPU(__real_ResizeImage(rgb, 450, 300, UndefinedFilter, ex)));
+  CHECK("MotionBlurImage(0,3,30) RGBA", 1, MotionBlurImage(rgba, 0.0, 3.0, 30.0, ex), CPU(__real_MotionBlurImage(rgba, 0.0, 3.0, 30.0, ex)));
   CHECK("MinifyImage RGBA (Spline 2x)", 1, MinifyImage(rgba, ex), CPU(__real_MinifyImage(rgba, ex)));
   CHECK("ResampleImage 36 dpi RGB (Lanczos)", 1, ResampleImage(rgb, 36.0, 36.0, LanczosFilter, ex), CPU(__real_ResampleImage(rgb, 36.0, 36.0, LanczosFilter, ex)));
   CHECK("SampleImage 517x389 -> 100x77 RGBA", 0, SampleImage(rgba, 100, 77, ex), CPU(__real_SampleImage(rgba, 100, 77, ex)));

@@ -166,6 +166,11 @@ MB200_API size_t mb200_optimal_kernel_width_2d(double radius, double sigma);
 MB200_API mb200_kernel_info *mb200_sharpen_kernel(double radius, double sigma);
 MB200_API mb200_kernel_info *mb200_edge_kernel(double radius);
 
+/* MotionBlurImage's taps (GetMotionBlurKernel, MagickCore/effect.c:2316-2345) and integer offsets along
+   `angle` (:2390-2398).  Returns the tap count; pass NULL arrays to query it. */
+MB200_API long mb200_motion_blur_kernel(double radius, double sigma, double angle, double *taps,
+    long *offset_x, long *offset_y, size_t max_taps);
+
 /* Resize contribution table of one axis: exactly the start/stop/weights that
    HorizontalFilter / VerticalFilter (MagickCore/resize.c:3398-3443, :3614-3657)
    compute per output column/row.  weights is out_n * max_taps doubles (row o at
@@ -221,6 +226,9 @@ MB200_API int mb200_sharpen_image_dev(const float *src, float *dst, size_t width
     int channels, double radius, double sigma, void *stream);
 MB200_API int mb200_edge_image_dev(const float *src, float *dst, size_t width, size_t height,
     int channels, double radius, void *stream);
+/* MotionBlurImage (MagickCore/effect.c:2347) == AccelerateMotionBlurImage (accelerate-private.h). */
+MB200_API int mb200_motion_blur_image_dev(const float *src, float *dst, size_t width, size_t height,
+    int channels, double radius, double sigma, double angle, void *stream);
 /* ResizeImage (MagickCore/resize.c:3761) == AccelerateResizeImage (:43).  filter
    UndefinedFilter applies the reference's own default choice (:3806-3816). */
 MB200_API int mb200_resize_image_dev(const float *src, size_t width, size_t height, int channels,
@@ -275,6 +283,8 @@ MB200_API int mb200_sharpen_image(const float *src, float *dst, size_t width, si
     double radius, double sigma);
 MB200_API int mb200_edge_image(const float *src, float *dst, size_t width, size_t height, int channels,
     double radius);
+MB200_API int mb200_motion_blur_image(const float *src, float *dst, size_t width, size_t height, int channels,
+    double radius, double sigma, double angle);
 MB200_API int mb200_resize_image(const float *src, size_t width, size_t height, int channels,
     float *dst, size_t out_width, size_t out_height, int filter);
 MB200_API int mb200_sample_image(const float *src, size_t width, size_t height, int channels,

@@ -141,6 +141,19 @@ def test_sharpen_and_edge(ch, kind):
 
 
 @pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["noise", "alpha_blocks", "hdr"])
+def test_motion_blur(ch, kind):
+    """MotionBlurImage (effect.c:2347): reference-ordered unfused double accumulation => expected bit exact; bar 1 ULP."""
+    src = make_image(131, 77, ch, seed=81 + ch, kind=kind)
+    for rad, sig, ang in ((0, 2, 0), (0, 2, 45), (0, 3, 90), (0, 1.5, -30), (0, 4, 180), (5, 2, 270), (0, 2, 123.4)):
+        want = orc("orc_motion_blur", src, float(rad), float(sig), float(ang))
+        got = _host(im.MotionBlurImage(_dev(src), rad, sig, ang))
+        assert max_ulp(got, want) <= 1, (rad, sig, ang, max_ulp(got, want))
+    got = im.MotionBlurImage(im.Image(src), 0, 2, 30).pixels
+    assert max_ulp(got, orc("orc_motion_blur", src, 0.0, 2.0, 30.0)) <= 1
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
 def test_unsharp(ch):
     src = make_image(120, 77, ch, seed=5)
     want = orc("orc_unsharp", src, 0.0, 2.0, 1.5, 0.02)

@@ -217,3 +217,24 @@ def test_wrapped_entry_points_fall_back_on_the_cpu():
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-500:]
     assert "FAIL" not in p.stdout and "gpu hits 0" in p.stdout
     assert p.stdout.count("ThumbnailImage RGBA") == 3
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("rad,sig,ang", [(0, 2, 0), (0, 2, 45), (0, 3, 90), (0, 1.5, -30), (0, 4, 180), (5, 2, 270), (0, 2, 123.4)])
+def test_motion_blur_taps_and_offsets_match_the_reference(rad, sig, ang):
+    """The product builds MotionBlurImage's taps / offsets on the host (effect.c:2316-2345, :2390-2398); the real
+    MotionBlurImage applied to a one-pixel impulse scatters exactly those taps to -offset."""
+    lib = _lib.load()
+    n = lib.mb200_motion_blur_kernel(rad, sig, ang, None, None, None, 0)
+    t, ox, oy = (C.c_double * n)(), (C.c_long * n)(), (C.c_long * n)()
+    assert lib.mb200_motion_blur_kernel(rad, sig, ang, t, ox, oy, n) == n
+    size = 2 * n + 5
+    c = size // 2
+    src = np.zeros((size, size, 1), np.float32)
+    src[c, c, 0] = 1.0
+    dst = np.empty_like(src)
+    assert util.ref().ref_motion_blur(util.P(src), util.P(dst), size, size, 1, rad, sig, ang) == 0
+    want = np.zeros((size, size), np.float64)
+    for j in range(n):                      # out[y][x] = sum_j k_j * src[y + oy_j][x + ox_j], accumulated in tap order
+        want[c - oy[j], c - ox[j]] += t[j]
+    assert np.array_equal(dst[..., 0], want.astype(np.float32))
