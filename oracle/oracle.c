@@ -1428,3 +1428,89 @@ int orc_motion_blur(const float *src, float *dst, size_t w, size_t h, int ch, do
   free(kernel); free(ox); free(oy);
   return 0;
 }
+
+
+/* ------------------------------------------------------------------------------------------
+   effect.c:821-1165 BilateralBlurImage (groundwork).  Odd window sizes only: for even
+   sizes the reference's reflected window index (2*mid - v) steps outside the window it fetched.
+   Tonal weight = gaussian of the 8-bit intensity difference (ScaleQuantumToChar of the FLOAT-converted
+   GetPixelIntensity, quantum.h:113-124), spatial weight = gaussian of the distance; colour channels of
+   images with alpha accumulate w*r but normalise by sum w*alpha(p)*alpha(r) (:1108-1125), as written.
+   The reference never initialises intensity_gaussian[510] (difference == +255, :935); the oracle uses
+   BlurGaussian(255) there -- inputs with a full-range 8-bit jump inside one window are outside the pin.
+   ------------------------------------------------------------------------------------------ */
+static double blur_gaussian(double x, double sigma)
+{
+  return exp(-((double) x * x) * perceptible_reciprocal(2.0 * sigma * sigma)) *
+         perceptible_reciprocal(TWOPI_ * sigma * sigma);
+}
+
+static unsigned char scale_quantum_to_char(float quantum)
+{
+  if (quantum != quantum || quantum <= 0.0f) return 0;
+  if ((quantum / 257.0f) >= 255.0f) return 255;
+  return (unsigned char) (quantum / 257.0f + 0.5f);
+}
+
+int orc_bilateral_blur(const float *src, float *dst, size_t w, size_t h, int ch, size_t width, size_t height,
+                       double intensity_sigma, double spatial_sigma)
+{
+  const long W = (long) (width > 1 ? width : 1), Hh = (long) (height > 1 ? height : 1);
+  const long midx = W / 2, midy = Hh / 2;
+  const int has_alpha = (ch == 2 || ch == 4);
+  double ig[512], *sg;
+  long y, u, v, n = 0;
+  if ((W % 2) == 0 || (Hh % 2) == 0) return -1;
+  sg = (double *) malloc((size_t) (W * Hh) * sizeof(double));
+  if (!sg) return -1;
+  for (v = -255; v <= 255; v++) ig[v + 255] = blur_gaussian((double) v, intensity_sigma);
+  for (v = 0; v < Hh; v++)
+    for (u = 0; u < W; u++) {
+      const double dx = (double) 0 - (double) (u - midx), dy = (double) 0 - (double) (v - midy);
+      sg[n++] = blur_gaussian(sqrt(dx * dx + dy * dy), spatial_sigma);
+    }
+#pragma omp parallel for schedule(static) private(u, v)
+  for (y = 0; y < (long) h; y++) {
+    double *wt = (double *) malloc((size_t) (W * Hh) * sizeof(double));
+    long x;
+    for (x = 0; x < (long) w; x++) {
+      const float *p = src + ((size_t) y * w + (size_t) x) * ch;
+      const double ip = (double) scale_quantum_to_char((float) pixel_intensity(p, ch));
+      long k = 0;
+      int c;
+      for (v = 0; v < Hh; v++)
+        for (u = 0; u < W; u++) {
+          long xx = x + midx - u, yy = y + midy - v;
+          const float *r;
+          double d;
+          xx = xx < 0 ? 0 : (xx >= (long) w ? (long) w - 1 : xx);
+          yy = yy < 0 ? 0 : (yy >= (long) h ? (long) h - 1 : yy);
+          r = src + ((size_t) yy * w + (size_t) xx) * ch;
+          d = (double) scale_quantum_to_char((float) pixel_intensity(r, ch)) - ip;
+          wt[k] = ig[(long) d + 255] * sg[k];
+          k++;
+        }
+      for (c = 0; c < ch; c++) {
+        double pixel = 0.0, gamma = 0.0;
+        const int blend = has_alpha && c != ch - 1;
+        k = 0;
+        for (v = 0; v < Hh; v++)
+          for (u = 0; u < W; u++) {
+            long xx = x + midx - u, yy = y + midy - v;
+            const float *r;
+            xx = xx < 0 ? 0 : (xx >= (long) w ? (long) w - 1 : xx);
+            yy = yy < 0 ? 0 : (yy >= (long) h ? (long) h - 1 : yy);
+            r = src + ((size_t) yy * w + (size_t) xx) * ch;
+            pixel += wt[k] * (double) r[c];
+            if (!blend) gamma += wt[k];
+            else gamma += wt[k] * (double) (QS * (double) p[ch - 1]) * (double) (QS * (double) r[ch - 1]);
+            k++;
+          }
+        dst[((size_t) y * w + (size_t) x) * ch + c] = (float) (perceptible_reciprocal(gamma) * pixel);
+      }
+    }
+    free(wt);
+  }
+  free(sg);
+  return 0;
+}

@@ -143,6 +143,16 @@ int ref_motion_blur(const float *src, float *dst, size_t w, size_t h, int ch, do
 }
 
 __attribute__((visibility("default")))
+int ref_bilateral_blur(const float *src, float *dst, size_t w, size_t h, int ch, size_t width, size_t height,
+                       double intensity_sigma, double spatial_sigma)
+{
+  BEGIN
+  im = make_image(src, w, h, ch, -1, ex);
+  if (im) { out = BilateralBlurImage(im, width, height, intensity_sigma, spatial_sigma, ex); rc = export_image(out, dst, w, h, ch, ex); }
+  END
+}
+
+__attribute__((visibility("default")))
 int ref_convolve(const float *src, float *dst, size_t w, size_t h, int ch,
                  const char *kernel)
 {

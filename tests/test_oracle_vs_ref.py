@@ -64,6 +64,18 @@ def test_motion_blur_oracle_bit_exact(ch, kind):
         assert max_ulp(a, b) == 0, (rad, sig, ang)
 
 
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["noise", "alpha_blocks", "gradient"])
+def test_bilateral_blur_oracle_bit_exact(ch, kind):
+    """effect.c:871 BilateralBlurImage (odd windows) -- oracle groundwork for SURVEY 8f rank 4."""
+    src = make_image(47, 33, ch, seed=17, kind=kind)
+    for W, H, isig, ssig in ((3, 3, 10.0, 1.0), (5, 5, 20.0, 2.0), (7, 3, 8.0, 1.5), (1, 1, 5.0, 1.0), (5, 9, 30.0, 3.0)):
+        a, b = np.empty_like(src), np.empty_like(src)
+        assert util.ref().ref_bilateral_blur(P(src), P(a), 47, 33, ch, W, H, isig, ssig) == 0
+        assert oracle().orc_bilateral_blur(P(src), P(b), 47, 33, ch, W, H, isig, ssig) == 0
+        assert max_ulp(a, b) == 0, (W, H, isig, ssig)
+
+
 @pytest.mark.parametrize("ch", [1, 4])
 def test_thumbnail_pixel_path_bit_exact(ch):
     """resize.c:4591 ThumbnailImage: sample (factors > 4) / box (factors > 2) / LanczosSharp cascade."""
