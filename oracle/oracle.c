@@ -1514,3 +1514,69 @@ int orc_bilateral_blur(const float *src, float *dst, size_t w, size_t h, int ch,
   free(sg);
   return 0;
 }
+
+
+/* ------------------------------------------------------------------------------------------
+   effect.c:3129-3400 RotationalBlurImage (groundwork): n samples on the arc through the
+   pixel about the image centre (cos/sin tables of theta*w - offset), every `step`-th one taken
+   (step = blur_radius / radius, clamped to [1, n-1]); sample coordinates are (ssize_t)(value + 0.5)
+   (truncation toward zero) with edge replication; plain average without alpha / for the alpha
+   channel, alpha-weighted average for the colour channels of images with alpha.
+   ------------------------------------------------------------------------------------------ */
+int orc_rotational_blur(const float *src, float *dst, size_t w, size_t h, int ch, double angle)
+{
+  const double cx = (double) (w - 1) / 2.0, cy = (double) (h - 1) / 2.0;
+  const double blur_radius = hypot(cx, cy);
+  const double rad = (double) (PI_ * angle / 180.0);
+  const size_t n = (size_t) fabs(4.0 * rad * sqrt((double) blur_radius) + 2UL);
+  const double theta = rad / (double) (n - 1), offset = theta * (double) (n - 1) / 2.0;
+  const int has_alpha = (ch == 2 || ch == 4);
+  double *ct, *st;
+  long y;
+  size_t k;
+  if (n < 2) return -1;
+  ct = (double *) malloc(n * sizeof(double));
+  st = (double *) malloc(n * sizeof(double));
+  if (!ct || !st) { free(ct); free(st); return -1; }
+  for (k = 0; k < n; k++) {
+    ct[k] = cos((double) (theta * (double) (long) k - offset));
+    st[k] = sin((double) (theta * (double) (long) k - offset));
+  }
+#pragma omp parallel for schedule(static)
+  for (y = 0; y < (long) h; y++) {
+    long x;
+    for (x = 0; x < (long) w; x++) {
+      const double dx = (double) x - cx, dy = (double) y - cy;
+      const double radius = hypot(dx, dy);
+      size_t step = 1;
+      int c;
+      if (radius != 0) {
+        step = (size_t) (blur_radius / radius);
+        if (step == 0) step = 1;
+        else if (step >= n) step = n - 1;
+      }
+      for (c = 0; c < ch; c++) {
+        double gamma = 0.0, pixel = 0.0;
+        const int blend = has_alpha && c != ch - 1;
+        size_t j;
+        for (j = 0; j < n; j += step) {
+          long xx = (long) (cx + dx * ct[j] - dy * st[j] + 0.5);
+          long yy = (long) (cy + dx * st[j] + dy * ct[j] + 0.5);
+          const float *r;
+          xx = xx < 0 ? 0 : (xx >= (long) w ? (long) w - 1 : xx);
+          yy = yy < 0 ? 0 : (yy >= (long) h ? (long) h - 1 : yy);
+          r = src + ((size_t) yy * w + (size_t) xx) * ch;
+          if (!blend) { pixel += (double) r[c]; gamma++; }
+          else {
+            const double alpha = QS * (double) r[ch - 1];
+            pixel += alpha * (double) r[c];
+            gamma += alpha;
+          }
+        }
+        dst[((size_t) y * w + (size_t) x) * ch + c] = (float) (perceptible_reciprocal(gamma) * pixel);
+      }
+    }
+  }
+  free(ct); free(st);
+  return 0;
+}

@@ -153,6 +153,15 @@ int ref_bilateral_blur(const float *src, float *dst, size_t w, size_t h, int ch,
 }
 
 __attribute__((visibility("default")))
+int ref_rotational_blur(const float *src, float *dst, size_t w, size_t h, int ch, double angle)
+{
+  BEGIN
+  im = make_image(src, w, h, ch, -1, ex);
+  if (im) { out = RotationalBlurImage(im, angle, ex); rc = export_image(out, dst, w, h, ch, ex); }
+  END
+}
+
+__attribute__((visibility("default")))
 int ref_convolve(const float *src, float *dst, size_t w, size_t h, int ch,
                  const char *kernel)
 {

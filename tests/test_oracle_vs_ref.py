@@ -76,6 +76,18 @@ def test_bilateral_blur_oracle_bit_exact(ch, kind):
         assert max_ulp(a, b) == 0, (W, H, isig, ssig)
 
 
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["noise", "alpha_blocks", "hdr"])
+def test_rotational_blur_oracle_bit_exact(ch, kind):
+    """effect.c:3129 RotationalBlurImage -- oracle groundwork for SURVEY 8f rank 4."""
+    src = make_image(61, 47, ch, seed=19, kind=kind)
+    for ang in (5.0, 20.0, 45.0, -10.0, 90.0, 1.0):
+        a, b = np.empty_like(src), np.empty_like(src)
+        assert util.ref().ref_rotational_blur(P(src), P(a), 61, 47, ch, ang) == 0
+        assert oracle().orc_rotational_blur(P(src), P(b), 61, 47, ch, ang) == 0
+        assert max_ulp(a, b) == 0, ang
+
+
 @pytest.mark.parametrize("ch", [1, 4])
 def test_thumbnail_pixel_path_bit_exact(ch):
     """resize.c:4591 ThumbnailImage: sample (factors > 4) / box (factors > 2) / LanczosSharp cascade."""
