@@ -1580,3 +1580,76 @@ int orc_rotational_blur(const float *src, float *dst, size_t w, size_t h, int ch
   free(ct); free(st);
   return 0;
 }
+
+
+/* ------------------------------------------------------------------------------------------
+   statistic.c:2918-3160 StatisticImage (groundwork): per channel (alpha included, every
+   channel carries the Update trait) over the max(width,1) x max(height,1) window whose top-left corner is
+   (x - width/2, y - height/2), edge-replicated.  Gradient / Maximum / Mean / Minimum / RootMeanSquare /
+   StandardDeviation / Contrast accumulate in double in row-major window order; Median goes through the
+   reference's 16-bit skip list (InsertPixelList :2878 -> ScaleQuantumToShort; GetMedianPixelList :2784
+   returns the element at sorted index length/2), so its result is an integer Quantum.  Mode / Nonpeak
+   are not restated.  type: statistic.h:141-151 numeric values.
+   ------------------------------------------------------------------------------------------ */
+static unsigned short scale_quantum_to_short(float q)
+{
+  if (q != q || q <= 0.0f) return 0;
+  if (q >= 65535.0f) return 65535;
+  return (unsigned short) (q + 0.5f);
+}
+
+static int cmp_ushort(const void *a, const void *b)
+{
+  const unsigned short x = *(const unsigned short *) a, y = *(const unsigned short *) b;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+int orc_statistic(const float *src, float *dst, size_t w, size_t h, int ch, int type, size_t width, size_t height)
+{
+  const long W = (long) (width > 1 ? width : 1), Hh = (long) (height > 1 ? height : 1);
+  long y;
+  if (type < 1 || type > 10 || type == 6 || type == 7) return -1;
+#pragma omp parallel for schedule(static)
+  for (y = 0; y < (long) h; y++) {
+    unsigned short *list = (unsigned short *) malloc((size_t) (W * Hh) * sizeof(unsigned short));
+    long x;
+    for (x = 0; x < (long) w; x++) {
+      int c;
+      for (c = 0; c < ch; c++) {
+        double area = 0.0, minimum = 0.0, maximum = 0.0, sum = 0.0, sum_squared = 0.0, pixel;
+        long u, v, n = 0;
+        for (v = 0; v < Hh; v++)
+          for (u = 0; u < W; u++) {
+            long xx = x - W / 2 + u, yy = y - Hh / 2 + v;
+            double value;
+            xx = xx < 0 ? 0 : (xx >= (long) w ? (long) w - 1 : xx);
+            yy = yy < 0 ? 0 : (yy >= (long) h ? (long) h - 1 : yy);
+            value = (double) src[((size_t) yy * w + (size_t) xx) * ch + c];
+            if (n == 0) { minimum = value; maximum = value; }
+            list[n++] = scale_quantum_to_short((float) value);
+            area++;
+            if (value < minimum) minimum = value;
+            if (value > maximum) maximum = value;
+            sum += value;
+            sum_squared += value * value;
+          }
+        switch (type) {
+          case 1: pixel = fabs(maximum - minimum); break;                                          /* Gradient */
+          case 2: pixel = maximum; break;
+          case 4:
+            qsort(list, (size_t) n, sizeof(unsigned short), cmp_ushort);
+            pixel = (double) list[n >> 1];
+            break;
+          case 5: pixel = minimum; break;
+          case 8: pixel = sqrt(sum_squared / area); break;
+          case 9: pixel = sqrt(sum_squared / area - (sum / area * sum / area)); break;
+          case 10: pixel = fabs((maximum - minimum) * perceptible_reciprocal(maximum + minimum)); break;
+          default: pixel = sum / area; break;                                                      /* Mean */
+        }
+        dst[((size_t) y * w + (size_t) x) * ch + c] = (float) pixel;
+      }
+    }
+    free(list);
+  }
+  return 0;
+}

@@ -162,6 +162,15 @@ int ref_rotational_blur(const float *src, float *dst, size_t w, size_t h, int ch
 }
 
 __attribute__((visibility("default")))
+int ref_statistic(const float *src, float *dst, size_t w, size_t h, int ch, int type, size_t width, size_t height)
+{
+  BEGIN
+  im = make_image(src, w, h, ch, -1, ex);
+  if (im) { out = StatisticImage(im, (StatisticType) type, width, height, ex); rc = export_image(out, dst, w, h, ch, ex); }
+  END
+}
+
+__attribute__((visibility("default")))
 int ref_convolve(const float *src, float *dst, size_t w, size_t h, int ch,
                  const char *kernel)
 {

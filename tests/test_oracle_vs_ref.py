@@ -88,6 +88,20 @@ def test_rotational_blur_oracle_bit_exact(ch, kind):
         assert max_ulp(a, b) == 0, ang
 
 
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["noise", "hdr", "gradient"])
+def test_statistic_oracle_bit_exact(ch, kind):
+    """statistic.c:2918 StatisticImage (Gradient, Maximum, Mean, Median via the 16-bit skip list, Minimum,
+    RootMeanSquare, StandardDeviation, Contrast; odd, even and 1-wide windows) -- groundwork for SURVEY 8f rank 4."""
+    src = make_image(47, 33, ch, seed=23, kind=kind)
+    for typ in (1, 2, 3, 4, 5, 8, 9, 10):
+        for W, H in ((3, 3), (5, 5), (4, 2), (1, 7), (1, 1)):
+            a, b = np.empty_like(src), np.empty_like(src)
+            assert util.ref().ref_statistic(P(src), P(a), 47, 33, ch, typ, W, H) == 0
+            assert oracle().orc_statistic(P(src), P(b), 47, 33, ch, typ, W, H) == 0
+            assert max_ulp(a, b) == 0, (typ, W, H)
+
+
 @pytest.mark.parametrize("ch", [1, 4])
 def test_thumbnail_pixel_path_bit_exact(ch):
     """resize.c:4591 ThumbnailImage: sample (factors > 4) / box (factors > 2) / LanczosSharp cascade."""

@@ -46,6 +46,7 @@ def oracle() -> C.CDLL:
         o.orc_motion_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d, _d]
         o.orc_bilateral_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _sz, _sz, _d, _d]
         o.orc_rotational_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _d]
+        o.orc_statistic.argtypes = [_fp, _fp, _sz, _sz, _i, _i, _sz, _sz]
         o.orc_edge.argtypes = [_fp, _fp, _sz, _sz, _i, _d]
         o.orc_resize.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz, _i]
         o.orc_colorspace.argtypes = [_fp, _sz, _sz, _i, _i, _i]
@@ -88,6 +89,7 @@ def ref() -> C.CDLL:
         r.ref_motion_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d, _d]
         r.ref_bilateral_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _sz, _sz, _d, _d]
         r.ref_rotational_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _d]
+        r.ref_statistic.argtypes = [_fp, _fp, _sz, _sz, _i, _i, _sz, _sz]
         r.ref_edge.argtypes = [_fp, _fp, _sz, _sz, _i, _d]
         r.ref_convolve.argtypes = [_fp, _fp, _sz, _sz, _i, C.c_char_p]
         r.ref_morphology.argtypes = [_fp, _fp, _sz, _sz, _i, _i, _l, C.c_char_p]
