@@ -57,6 +57,17 @@ PROTOTYPES = {
     "mb200_free_host": (_i, [_vp]),
     "mb200_upload": (_i, [_vp, _vp, _sz, _vp]),
     "mb200_download": (_i, [_vp, _vp, _sz, _vp]),
+    "mb200_trim": (_i, [_sz]),
+    "mb200_probe_fp64_fma_rate": (_i, [C.POINTER(_d)]),
+    "mb200_set_option": (_i, [C.c_char_p, _i]),
+    "mb200_cache_attach": (_i, [_vp, _sz, _i]),
+    "mb200_cache_detach": (_i, [_vp]),
+    "mb200_cache_sync": (_i, [_vp]),
+    "mb200_cache_host_written": (_i, [_vp]),
+    "mb200_cache_resident": (_i, [_vp]),
+    "mb200_cache_set_lazy": (_i, [_i]),
+    "mb200_cache_stats": (None, [C.POINTER(C.c_ulonglong)]),
+    "mb200_copy_threads": (_i, []),
     "mb200_acquire_kernel_info": (KernelPtr, [C.c_char_p]),
     "mb200_acquire_kernel_builtin": (KernelPtr, [_i, _d, _d, _d, _d]),
     "mb200_clone_kernel_info": (KernelPtr, [KernelPtr]),

@@ -26,7 +26,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off",
               "-Xptxas", "-v"]
 
-SOURCES = ["runtime.cu", "kernel_info.cpp", "resize_filter.cpp", "conv1d.cu", "morph2d.cu", "morph_flat.cu", "morph_stream.cu",
+SOURCES = ["runtime.cu", "kernel_info.cpp", "resize_filter.cpp", "conv1d.cu", "morph2d.cu", "morph_stream.cu", "cache.cu",
            "resize.cu", "resize_stream.cu", "colorspace.cu", "pointwise.cu", "api.cu"]
 
 

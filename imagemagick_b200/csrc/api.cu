@@ -18,7 +18,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -41,9 +43,22 @@ struct ResizeTables {
   double *d_wsets = nullptr;
   int nborder = 0;
   int *d_border = nullptr;
+  ResizeTables() = default;
+  ResizeTables(const ResizeTables &) = delete;
+  ResizeTables &operator=(const ResizeTables &) = delete;
+  ~ResizeTables() {            // cudaFree waits for launches that still read the buffers
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (device >= 0 && cur != device) cudaSetDevice(device);
+    cudaFree(d_start); cudaFree(d_count); cudaFree(d_weights); cudaFree(d_wreg); cudaFree(d_wsets); cudaFree(d_border);
+    if (device >= 0 && cur != device) cudaSetDevice(cur);
+  }
 };
+// Bounded LRU of shared entries: a call holds a reference while its launches are being queued, eviction drops the
+// cache's reference and the last owner frees the device buffers.  Tables are built outside the lock.
 std::mutex g_tables_mutex;
-std::vector<ResizeTables *> g_tables;      // entries are never freed before process exit (<= 64 kept)
+std::vector<std::shared_ptr<ResizeTables>> g_tables;
+constexpr size_t kMaxCachedTables = 64;
 
 
 struct StreamAlloc {           // stream-ordered temporary; freed (stream-ordered) on scope exit
@@ -51,7 +66,7 @@ struct StreamAlloc {           // stream-ordered temporary; freed (stream-ordere
   cudaStream_t s;
   explicit StreamAlloc(cudaStream_t stream) : s(stream) {}
   int alloc(size_t bytes) {
-    cudaError_t e = cudaMallocAsync(&ptr, bytes ? bytes : 1, s);
+    cudaError_t e = cudaMallocAsync(&ptr, bytes ? bytes : 1, temp_pool(), s);      // the library's private pool
     if (e != cudaSuccess) { ptr = nullptr; return cuda_fail(e, "cudaMallocAsync"); }
     return MB200_OK;
   }
@@ -63,26 +78,34 @@ struct StreamAlloc {           // stream-ordered temporary; freed (stream-ordere
 int prepare(void *stream, cudaStream_t *out) {
   int rc = ensure_device();
   if (rc) return rc;
-  static thread_local int pool_configured_for = -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (pool_configured_for != dev) {   // keep freed temporaries cached in the pool across calls
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long threshold = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
-    }
-    pool_configured_for = dev;
-  }
   *out = stream ? static_cast<cudaStream_t>(stream) : static_cast<cudaStream_t>(default_stream());
   return MB200_OK;
 }
 
 bool valid_image(size_t w, size_t h, int ch) { return w > 0 && h > 0 && ch >= 1 && ch <= 4; }
 
+// Developer switches (environment, read once per process): force the generic kernels so that tests can compare them
+// with the specialised ones.
+struct Knobs {
+  bool no_rank1, no_morph_stream, no_resize_stream, resize_regular_h, no_fused_unsharp;
+  Knobs() {
+    auto on = [](const char *name) { const char *v = std::getenv(name); return v != nullptr && *v != '\0' && *v != '0'; };
+    no_rank1 = on("MB200_NO_RANK1");
+    no_morph_stream = on("MB200_NO_MORPH_STREAM");
+    no_resize_stream = on("MB200_NO_RESIZE_STREAM");
+    resize_regular_h = on("MB200_RESIZE_REGULAR_H");
+    no_fused_unsharp = on("MB200_NO_FUSED_UNSHARP");
+  }
+};
+Knobs &knobs() {
+  static Knobs k;
+  return k;
+}
+
 // One MorphologyPrimitive launch.  d_counter may be null.
 int primitive(const float *src, float *dst, size_t w, size_t h, int ch, int method,
-              const mb200_kernel_info *k, double bias, unsigned long long *d_counter, cudaStream_t s) {
+              const mb200_kernel_info *k, double bias, unsigned long long *d_counter, cudaStream_t s,
+              const UnsharpEpilogue *epilogue = nullptr, bool *epilogue_fused = nullptr) {
   const int kw = static_cast<int>(k->width), kh = static_cast<int>(k->height);
   const size_t n = k->width * k->height;
   std::vector<double> win(n);
@@ -106,11 +129,11 @@ int primitive(const float *src, float *dst, size_t w, size_t h, int ch, int meth
     // gamma*(height/count) factor is exactly 1.
     const int axis = (kw == 1) ? 1 : 0;
     const int rc = launch_conv1d(src, dst, w, h, ch, axis, win.data(), axis == 1 ? kh : kw, axis == 1 ? oy : ox,
-                                 bias, 1.0, d_counter, s);
+                                 bias, 1.0, d_counter, s, 0, epilogue, epilogue_fused);
     if (rc != MB200_EUNSUPPORTED) return rc;
   }
   if (method == MB200_ConvolveMorphology && !has_nan && kw > 1 && kh > 1 && kw <= 33 && kh <= 33 && ch == 4 &&
-      bias == 0.0 && d_counter == nullptr && std::getenv("MB200_NO_RANK1") == nullptr) {
+      bias == 0.0 && d_counter == nullptr && !knobs().no_rank1) {
     // Rank-1 kernels with non-negative taps ("gaussian:RxS", "binomial", "square" ...): K[v][u] = a[v] * b[u]
     // to 1e-14, so the kw*kh-tap sum is evaluated as a row pass that keeps RAW double sums and a column
     // pass that normalises -- same double accumulation as MorphologyPrimitive's inner loop
@@ -145,13 +168,8 @@ int primitive(const float *src, float *dst, size_t w, size_t h, int ch, int meth
     }
   }
   if ((method == MB200_ErodeMorphology || method == MB200_DilateMorphology) && d_counter == nullptr &&
-      std::getenv("MB200_NO_MORPH_STREAM") == nullptr) {     // register-streaming kernel for the built-in shapes
+      !knobs().no_morph_stream) {                            // register-streaming kernel for the built-in shapes
     const int rc = launch_morph_stream(src, dst, w, h, ch, method, win.data(), kw, kh, ox, oy, s);
-    if (rc != MB200_EUNSUPPORTED) return rc;
-  }
-  if ((method == MB200_ErodeMorphology || method == MB200_DilateMorphology) &&
-      std::getenv("MB200_MORPH_FLAT") != nullptr) {          // run-decomposition variant: opt-in (r01: not faster yet)
-    const int rc = launch_morph_flat(src, dst, w, h, ch, method, win.data(), kw, kh, ox, oy, d_counter, s);
     if (rc != MB200_EUNSUPPORTED) return rc;
   }
   double gamma_scale = 1.0;
@@ -184,7 +202,8 @@ mb200_kernel_info *reflected_clone(const mb200_kernel_info *kernel) {
 struct Stage { int primitive; const mb200_kernel_info *kernel; };
 
 int morphology_apply(const float *src, float *dst, size_t w, size_t h, int ch, int method, long iterations,
-                     const mb200_kernel_info *kernel, double bias, cudaStream_t s) {
+                     const mb200_kernel_info *kernel, double bias, cudaStream_t s,
+                     const UnsharpEpilogue *epilogue = nullptr, bool *epilogue_fused = nullptr) {
   // Methods that end in "difference with the original" (staging :3813-3893, CompositeImage :3995-4012):
   // the morphological part is one of the methods below, then one Difference composite.
   if (method == MB200_EdgeInMorphology || method == MB200_EdgeOutMorphology || method == MB200_EdgeMorphology ||
@@ -256,7 +275,9 @@ int morphology_apply(const float *src, float *dst, size_t w, size_t h, int ch, i
     const float *cur = src;
     for (size_t i = 0; i < total && rc == MB200_OK; ++i) {
       float *out = ((total - 1 - i) % 2 == 0) ? dst : static_cast<float *>(tmp.ptr);
-      rc = primitive(cur, out, w, h, ch, stages[i].primitive, stages[i].kernel, bias, nullptr, s);
+      const bool last = i + 1 == total;
+      rc = primitive(cur, out, w, h, ch, stages[i].primitive, stages[i].kernel, bias, nullptr, s,
+                     last ? epilogue : nullptr, last ? epilogue_fused : nullptr);
       cur = out;
     }
   } else {
@@ -291,29 +312,59 @@ int morphology_apply(const float *src, float *dst, size_t w, size_t h, int ch, i
   return rc;
 }
 
-// Runs `op(d_src, d_dst, stream)` on staged copies of host buffers.
+// Runs `op(d_src, d_dst, stream)` on the HBM copies of host buffers (cache.cu): an attached pixel cache keeps its HBM
+// copy between calls (and, in lazy mode, its result stays there until mb200_cache_sync); anything else is staged
+// through stream-ordered temporaries.  Pageable memory travels through the threaded pinned bounce ring.
 template <typename Op>
 int with_staging(const float *src, size_t src_bytes, float *dst, size_t dst_bytes, Op op) {
   cudaStream_t s;
   int rc = prepare(nullptr, &s);
   if (rc) return rc;
-  StreamAlloc d_src(s), d_dst(s);
-  rc = d_src.alloc(src_bytes);
-  if (!rc) rc = d_dst.alloc(dst_bytes);
+  StageRef in, out;
+  rc = stage_input(src, src_bytes, s, &in);
+  if (!rc) rc = stage_output(dst, dst_bytes, s, &out);
+  if (!rc) rc = op(static_cast<const float *>(in.dev), static_cast<float *>(out.dev), s);
+  if (rc) cudaStreamSynchronize(s);
+  else rc = finish_output(&out, s);
+  release_stage(&in, s);
+  release_stage(&out, s);
+  return rc;
+}
+
+// In-place operators on a host buffer.
+template <typename Op>
+int in_place_host(float *buf, size_t bytes, Op op) {
+  cudaStream_t s;
+  int rc = prepare(nullptr, &s);
   if (rc) return rc;
-  cudaError_t e = cudaMemcpyAsync(d_src.ptr, src, src_bytes, cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) return cuda_fail(e, "H2D");
-  rc = op(static_cast<const float *>(d_src.ptr), static_cast<float *>(d_dst.ptr), s);
-  if (rc) { cudaStreamSynchronize(s); return rc; }
-  e = cudaMemcpyAsync(dst, d_dst.ptr, dst_bytes, cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  if (e != cudaSuccess) return cuda_fail(e, "D2H");
-  return MB200_OK;
+  StageRef io;
+  rc = stage_input(buf, bytes, s, &io);
+  if (!rc) rc = op(static_cast<float *>(io.dev), s);
+  if (rc) cudaStreamSynchronize(s);
+  else rc = finish_output(&io, s);
+  release_stage(&io, s);
+  return rc;
 }
 
 }  // namespace
 
 extern "C" {
+
+// Test / developer hook: the switches above (initialised from the MB200_* environment variables of the same upper-case
+// names) can be flipped at run time, e.g. to compare a specialised kernel with the generic one in one process.
+int mb200_set_option(const char *name, int value) {
+  if (!name) return fail(MB200_EINVAL, "set_option: null name");
+  Knobs &k = knobs();
+  const bool v = value != 0;
+  const std::string n(name);
+  if (n == "no_rank1") k.no_rank1 = v;
+  else if (n == "no_morph_stream") k.no_morph_stream = v;
+  else if (n == "no_resize_stream") k.no_resize_stream = v;
+  else if (n == "resize_regular_h") k.resize_regular_h = v;
+  else if (n == "no_fused_unsharp") k.no_fused_unsharp = v;
+  else return fail(MB200_EINVAL, "set_option: unknown option '%s'", name);
+  return MB200_OK;
+}
 
 int mb200_morphology_primitive_dev(const float *src, float *dst, size_t width, size_t height, int channels,
                                    int method, const mb200_kernel_info *kernel, double bias, long long *changed,
@@ -374,11 +425,25 @@ int mb200_gaussian_blur_image_dev(const float *src, float *dst, size_t width, si
 
 int mb200_unsharp_mask_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
                                  double radius, double sigma, double gain, double threshold, void *stream) {
-  int rc = mb200_blur_image_dev(src, dst, width, height, channels, radius, sigma, stream);
-  if (rc) return rc;
+  if (!src || !dst || src == dst || !valid_image(width, height, channels))
+    return fail(MB200_EINVAL, "unsharp: bad arguments");
   cudaStream_t s;
-  rc = prepare(stream, &s);
+  int rc = prepare(stream, &s);
   if (rc) return rc;
+  // BlurImage (effect.c:4295) + the point pass (:4310-4384).  With the RGBA pair kernels the point pass is the
+  // epilogue of the blur's column pass: it is applied to the float-ROUNDED blur value, exactly what the reference
+  // reads back from its blurred image, so the fused and the two-launch forms produce the same bits while the fused one
+  // saves the 48 B/pixel of the separate pass.
+  mb200_kernel_info *k = mb200_acquire_kernel_builtin(MB200_BlurKernel, radius, sigma, 0.0, 0.0);
+  if (!k) return fail(MB200_ENOMEM, "blur kernel");
+  k->next = mb200_acquire_kernel_builtin(MB200_BlurKernel, radius, sigma, 90.0, 0.0);
+  if (!k->next) { mb200_destroy_kernel_info(k); return fail(MB200_ENOMEM, "blur kernel"); }
+  const UnsharpEpilogue epi{src, gain, 65535.0 * threshold};
+  bool fused = false;
+  rc = morphology_apply(src, dst, width, height, channels, MB200_ConvolveMorphology, 1, k, 0.0, s,
+                        knobs().no_fused_unsharp ? nullptr : &epi, &fused);
+  mb200_destroy_kernel_info(k);
+  if (rc || fused) return rc;
   return launch_unsharp_combine(src, dst, width * height * static_cast<size_t>(channels), gain,
                                 65535.0 * threshold, s);
 }
@@ -403,12 +468,24 @@ int mb200_resize_image_dev(const float *src, size_t width, size_t height, int ch
   else if (x_factor == 1.0 && y_factor == 1.0) filter_type = MB200_PointFilter;
   else if (has_alpha(channels) || (x_factor * y_factor) > 1.0) filter_type = MB200_MitchellFilter;
 
-  auto get_tables = [&](size_t in_n, size_t out_n, double factor, const ResizeTables **out) -> int {
+  auto get_tables = [&](size_t in_n, size_t out_n, double factor, std::shared_ptr<ResizeTables> *out) -> int {
     int dev = 0;
     cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lock(g_tables_mutex);
-    for (ResizeTables *t : g_tables)
-      if (t->device == dev && t->filter == filter_type && t->in_n == in_n && t->out_n == out_n) { *out = t; return MB200_OK; }
+    auto find = [&]() -> std::shared_ptr<ResizeTables> {
+      for (size_t i = 0; i < g_tables.size(); ++i) {
+        const std::shared_ptr<ResizeTables> &t = g_tables[i];
+        if (t->device == dev && t->filter == filter_type && t->in_n == in_n && t->out_n == out_n) {
+          std::shared_ptr<ResizeTables> hit = t;
+          if (i + 1 != g_tables.size()) { g_tables.erase(g_tables.begin() + i); g_tables.push_back(hit); }   // most recent last
+          return hit;
+        }
+      }
+      return nullptr;
+    };
+    {
+      std::lock_guard<std::mutex> lock(g_tables_mutex);
+      if ((*out = find())) return MB200_OK;
+    }
     const long taps = mb200_resize_contributions(filter_type, in_n, out_n, factor, nullptr, nullptr, nullptr, 0);
     if (taps < 0) return static_cast<int>(taps);
     std::vector<long> start(out_n);
@@ -418,7 +495,7 @@ int mb200_resize_image_dev(const float *src, size_t width, size_t height, int ch
     const long r = mb200_resize_contributions(filter_type, in_n, out_n, factor, start.data(), count.data(), w.data(),
                                               static_cast<size_t>(taps));
     if (r < 0) return static_cast<int>(r);
-    ResizeTables *t = new ResizeTables();
+    std::shared_ptr<ResizeTables> t = std::make_shared<ResizeTables>();
     t->device = dev; t->filter = filter_type; t->in_n = in_n; t->out_n = out_n; t->taps = taps;
     // widest source span of any aligned block of 32 outputs (tile width of the tiled horizontal kernel)
     for (size_t o = 0; o < out_n; o += 32) {
@@ -495,25 +572,22 @@ int mb200_resize_image_dev(const float *src, size_t width, size_t height, int ch
     if (e == cudaSuccess) e = cudaMemcpy(t->d_weights, wt.data(), wt.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !wreg.empty())
       e = cudaMemcpy(t->d_wreg, wreg.data(), wreg.size() * sizeof(double), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-      cudaFree(t->d_start); cudaFree(t->d_count); cudaFree(t->d_weights); cudaFree(t->d_wreg); cudaFree(t->d_wsets); cudaFree(t->d_border);
-      delete t;
-      return cuda_fail(e, "resize: table upload");
-    }
-    if (g_tables.size() >= 64) {                   // bounded: drop the oldest entry (its buffers stay valid
-      g_tables.erase(g_tables.begin());            // for launches already queued; small leak by design)
-    }
+    if (e != cudaSuccess) return cuda_fail(e, "resize: table upload");     // ~ResizeTables frees what was allocated
+    std::lock_guard<std::mutex> lock(g_tables_mutex);
+    if ((*out = find())) return MB200_OK;          // another thread built the same table meanwhile: keep theirs
+    if (g_tables.size() >= kMaxCachedTables) g_tables.erase(g_tables.begin());     // least recently used
     g_tables.push_back(t);
     *out = t;
     return MB200_OK;
   };
-  const ResizeTables *tx = nullptr, *ty = nullptr;
-  rc = get_tables(width, out_width, x_factor, &tx);
-  if (!rc) rc = get_tables(height, out_height, y_factor, &ty);
+  std::shared_ptr<ResizeTables> tx_owner, ty_owner;
+  rc = get_tables(width, out_width, x_factor, &tx_owner);
+  if (!rc) rc = get_tables(height, out_height, y_factor, &ty_owner);
   if (rc) return rc;
+  const ResizeTables *tx = tx_owner.get(), *ty = ty_owner.get();
   StreamAlloc tmp(s);
-  const bool reg_h = std::getenv("MB200_RESIZE_REGULAR_H") != nullptr;   // tiled regular H kernel: opt-in (r01: slower)
-  const bool no_stream = std::getenv("MB200_NO_RESIZE_STREAM") != nullptr;
+  const bool reg_h = knobs().resize_regular_h;         // tiled regular H kernel: opt-in (r01: slower)
+  const bool no_stream = knobs().no_resize_stream;
   auto run_axis = [&](const float *in, size_t w, size_t h, float *out, int axis, const ResizeTables *t) -> int {
     if (channels == 4 && t->d_wsets != nullptr && !no_stream) {        // streaming kernels (+ border gather CTAs)
       const int rs = launch_resize_stream(in, w, h, out, t->out_n, axis, t->reg_stride, t->reg_taps, t->nseg, t->seg_o,
@@ -606,20 +680,8 @@ int mb200_resize_image(const float *src, size_t w, size_t h, int ch, float *dst,
 
 int mb200_transform_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to) {
   if (!buf || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "colorspace: bad arguments");
-  cudaStream_t s;
-  int rc = prepare(nullptr, &s);
-  if (rc) return rc;
-  const size_t bytes = w * h * ch * sizeof(float);
-  StreamAlloc d(s);
-  rc = d.alloc(bytes);
-  if (rc) return rc;
-  cudaError_t e = cudaMemcpyAsync(d.ptr, buf, bytes, cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) return cuda_fail(e, "H2D");
-  rc = launch_colorspace(static_cast<float *>(d.ptr), w * h, ch, from, to, s);
-  if (rc) { cudaStreamSynchronize(s); return rc; }
-  e = cudaMemcpyAsync(buf, d.ptr, bytes, cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  return e == cudaSuccess ? MB200_OK : cuda_fail(e, "D2H");
+  return in_place_host(buf, w * h * ch * sizeof(float),
+                       [&](float *d, cudaStream_t st) { return launch_colorspace(d, w * h, ch, from, to, st); });
 }
 
 }  // extern "C"
@@ -679,22 +741,6 @@ int black_white_dev(float *buf, size_t width, size_t height, int channels, int c
   return threshold_dev(buf, width, height, channels, op, t, stream);
 }
 
-template <typename Op>
-int in_place_host(float *buf, size_t bytes, Op op) {
-  cudaStream_t s;
-  int rc = prepare(nullptr, &s);
-  if (rc) return rc;
-  StreamAlloc d(s);
-  rc = d.alloc(bytes);
-  if (rc) return rc;
-  cudaError_t e = cudaMemcpyAsync(d.ptr, buf, bytes, cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) return cuda_fail(e, "H2D");
-  rc = op(static_cast<float *>(d.ptr), s);
-  if (rc) { cudaStreamSynchronize(s); return rc; }
-  e = cudaMemcpyAsync(buf, d.ptr, bytes, cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  return e == cudaSuccess ? MB200_OK : cuda_fail(e, "D2H");
-}
 }  // namespace
 
 extern "C" {

@@ -50,9 +50,43 @@ struct Conv1dArgs {
   int strip;     // outputs per thread along the filter axis
   int seg_w;     // row pass: source pixels staged per tile row (strip + NT - 1)
   int pitch;     // row pass: shared-memory tile pitch in pixels (odd)
+  int ntaps;     // taps of the real window; the kernel template carries NT >= ntaps slots (taps[ntaps..NT) are zero)
   double bias;
   unsigned long long *changed;
+  // fused UnsharpMaskImage epilogue (column pass of the pair kernels, EPI = 1): the source image of the operator,
+  // gain and QuantumRange * threshold (effect.c:4299, :4358-4363)
+  const float *aux;
+  double gain, qthreshold;
 };
+
+// A zero-padded tap multiplies a sample OUTSIDE the reference's window; 0 * (+-inf | NaN) = NaN would poison outputs
+// the reference computes from finite samples only (HDRI pixels may be non-finite).  Padded launches therefore test
+// every sample (exponent field all ones) and take a predicated slow path for the few steps that carry one.
+__device__ __forceinline__ bool nonfinite_bits(float v) { return (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u; }
+__device__ __forceinline__ bool nonfinite_bits(double v) {
+  return (static_cast<unsigned>(__double2hiint(v)) & 0x7ff00000u) == 0x7ff00000u;
+}
+
+// |den| < MagickEpsilon / QuantumScale, decided exactly on the 64-bit pattern (positive doubles order like their
+// bits) with integer instructions: the FP64 pipe is the bottleneck of these kernels, a DSETP would cost issue time.
+// This is PerceptibleReciprocal's test (pixel-accessor.h:242-254) applied to gamma = QS * den.
+__device__ __forceinline__ double clamp_denominator(double den) {
+  constexpr double kTiny = kEpsilon / kQuantumScale;           // 6.5535e-8
+  const unsigned hi = static_cast<unsigned>(__double2hiint(den)), lo = static_cast<unsigned>(__double2loint(den));
+  const unsigned habs = hi & 0x7fffffffu;
+  const unsigned th = static_cast<unsigned>(__double2hiint(kTiny)), tl = static_cast<unsigned>(__double2loint(kTiny));
+  if (habs < th || (habs == th && lo < tl))
+    den = __hiloint2double(static_cast<int>((hi & 0x80000000u) | th), static_cast<int>(tl));
+  return den;
+}
+
+// UnsharpMaskImage's point pass (effect.c:4358-4364) on the float-rounded blur value, in the reference's operation
+// order with unfused double arithmetic: bit-identical to running it as a separate pass.
+__device__ __forceinline__ float unsharp_point(float p, float blurred, double gain, double qthreshold) {
+  const double d = __dsub_rn(static_cast<double>(p), static_cast<double>(blurred));
+  if (fabs(__dmul_rn(2.0, d)) < qthreshold) return p;
+  return static_cast<float>(__dadd_rn(static_cast<double>(p), __dmul_rn(gain, d)));
+}
 
 // 1/g to ~1 ulp: MUFU.RCP64H seed (one XU op, ~20 bits) + two FP64 Newton steps.
 __device__ __forceinline__ double fast_reciprocal(double g) {
@@ -79,16 +113,11 @@ struct Finish {
   bool blend;
 };
 
-// branch-free: out = (bias_eff + sum) * 1/den, den = blend ? gsum : 1, with the reference's
-// |gamma| < MagickEpsilon clamp (PerceptibleReciprocal == 1/clamp(gamma)) applied to QS*gsum by
-// comparing the high word of |den| against the threshold (exact up to the low 32 mantissa bits).
+// out = (bias_eff + sum) * 1/den, den = blend ? gsum : 1, with the reference's |gamma| < MagickEpsilon clamp
+// (PerceptibleReciprocal == 1/clamp(gamma)).
 __device__ __forceinline__ float finish(const Finish &f, double sum, double gsum) {
   const double pixel = f.bias_eff + sum;
-  double den = f.blend ? gsum : 1.0;
-  constexpr double kTiny = kEpsilon / kQuantumScale;           // 6.5535e-8
-  const int hi = __double2hiint(den);
-  if ((hi & 0x7fffffff) < __double2hiint(kTiny))
-    den = __hiloint2double((hi & 0x80000000) | __double2hiint(kTiny), __double2loint(kTiny));
+  const double den = clamp_denominator(f.blend ? gsum : 1.0);
   return static_cast<float>(fast_reciprocal(den) * pixel);
 }
 
@@ -154,8 +183,14 @@ __global__ void __launch_bounds__(THREADS, MINB) conv_col_kernel(const Conv1dArg
         af = is_alpha ? 1.0f : af;
         v *= static_cast<double>(af);
       }
+      if (a.ntaps != NT && __any_sync(0xffffffffu, nonfinite_bits(vf))) {     // padded taps must not touch it
 #pragma unroll
-      for (int q = 0; q < NT; ++q) acc[q] = fma(taps.k[(s - q + NT) % NT], v, acc[q]);
+        for (int q = 0; q < NT; ++q)
+          if ((s - q + NT) % NT < a.ntaps) acc[q] = fma(taps.k[(s - q + NT) % NT], v, acc[q]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < NT; ++q) acc[q] = fma(taps.k[(s - q + NT) % NT], v, acc[q]);
+      }
       const int qf = (s + 1) % NT;
       const double sum = acc[qf];
       acc[qf] = 0.0;
@@ -249,8 +284,14 @@ __global__ void __launch_bounds__(128, MINB) conv_row_kernel(const Conv1dArgs a,
         af = is_alpha ? 1.0f : af;
         v *= static_cast<double>(af);
       }
+      if (a.ntaps != NT && __any_sync(0xffffffffu, nonfinite_bits(vf))) {     // padded taps must not touch it
 #pragma unroll
-      for (int q = 0; q < NT; ++q) acc[q] = fma(taps.k[(s - q + NT) % NT], v, acc[q]);
+        for (int q = 0; q < NT; ++q)
+          if ((s - q + NT) % NT < a.ntaps) acc[q] = fma(taps.k[(s - q + NT) % NT], v, acc[q]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < NT; ++q) acc[q] = fma(taps.k[(s - q + NT) % NT], v, acc[q]);
+      }
       const int qf = (s + 1) % NT;
       const double sum = acc[qf];
       acc[qf] = 0.0;
@@ -274,249 +315,6 @@ __global__ void __launch_bounds__(128, MINB) conv_row_kernel(const Conv1dArgs a,
 }
 
 // ======================================================================================
-// TMA (cp.async.bulk + mbarrier) staged variants for RGBA.  Every warp owns a private
-// shared-memory ring of source chunks filled by the bulk-copy engine: no thread spends
-// registers or issue slots on global loads, the prefetch depth is set by the ring (not by the
-// register file), and warps never synchronise with each other (no __syncthreads in the loop).
-// Edge clamping is done by the producer lanes: out-of-image rows / pixels are bulk-copied from
-// the clamped source address.  Other layouts use the register-ring kernels above.
-// ======================================================================================
-
-__device__ __forceinline__ unsigned smem_u32(const void *p) {
-  return static_cast<unsigned>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// Spin on the barrier phase.  The loop lives inside the asm block so that the compiler sees one
-// convergent instruction; a bounded poll count traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .u32 cnt;\n\t"
-      "mov.u32 cnt, 0;\n\t"
-      "MB200_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra MB200_DONE;\n\t"
-      "add.u32 cnt, cnt, 1;\n\t"
-      "setp.gt.u32 p, cnt, 0x4000000;\n\t"
-      "@p trap;\n\t"
-      "bra MB200_WAIT;\n\t"
-      "MB200_DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-constexpr int kTmaSlots = 4;      // ring depth (chunks in flight per warp)
-
-// blend-lane output stage without bias: out = sum / clamp(den), den = blend ? gsum : 1; the
-// reference's PerceptibleReciprocal clamp (|QS*gsum| < MagickEpsilon) is decided on the float copy.
-__device__ __forceinline__ float finish_rgba(bool blend, double sum, double gsum) {
-  const double den = blend ? gsum : 1.0;
-  const float denf = static_cast<float>(den);
-  float seed;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"(denf));
-  const double r0 = static_cast<double>(seed);
-  const double e = fma(-den, r0, 1.0);
-  double r = fma(r0, e, r0);
-  if (fabsf(denf) < static_cast<float>(kEpsilon / kQuantumScale))
-    r = denf < 0.0f ? -(kQuantumScale / kEpsilon) : (kQuantumScale / kEpsilon);
-  return static_cast<float>(r * sum);
-}
-
-// Producer step of the column pass (lanes 0..PF-1 of the warp): one edge-clamped 128-byte row
-// segment per lane into the warp's ring slot.
-template <int PF>
-__device__ __forceinline__ void col_issue(float *slot_base, unsigned long long *bar, const char *gbase, int y_first,
-                                       int hmax, unsigned pitch_bytes, unsigned row_bytes, int lane) {
-  __syncwarp();                                           // every lane has finished reading this slot
-  if (lane == 0) mbar_expect_tx(bar, row_bytes * PF);
-  __syncwarp();
-  if (lane < PF) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const unsigned yy = static_cast<unsigned>(min(max(y_first + lane, 0), hmax));
-    bulk_g2s(slot_base + lane * 32, gbase + static_cast<size_t>(yy) * pitch_bytes, row_bytes, bar);
-  }
-}
-
-// Producer step of the row pass (lanes 0..7 = the warp's 8 tile rows): PF pixels per row, the
-// out-of-image pixels replicated from the edge pixel with 16-byte copies.
-template <int PF>
-__device__ __forceinline__ void row_issue(float *slot_base, unsigned long long *bar, const float4 *src, int ybase,
-                                       int hmax, int xs, int width, int lane) {
-  __syncwarp();
-  if (lane == 0) mbar_expect_tx(bar, 8u * PF * 16u);
-  __syncwarp();
-  if (lane < 8) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const float4 *grow = src + static_cast<size_t>(min(ybase + lane, hmax)) * width;
-    float *dst = slot_base + lane * (PF * 4);
-    const int lo = max(xs, 0), hi = min(xs + PF, width);   // in-image part [lo, hi)
-    if (hi > lo) bulk_g2s(dst + (lo - xs) * 4, grow + lo, static_cast<unsigned>(hi - lo) * 16u, bar);
-#pragma unroll 1
-    for (int x = xs; x < min(xs + PF, 0); ++x) bulk_g2s(dst + (x - xs) * 4, grow, 16u, bar);
-#pragma unroll 1
-    for (int x = max(xs, width); x < xs + PF; ++x) bulk_g2s(dst + (x - xs) * 4, grow + (width - 1), 16u, bar);
-  }
-}
-
-// ---- column pass: CTA = 4 independent warps; a warp covers 32 consecutive components (8 RGBA
-//      pixels, 128 B per row); chunk = PF rows.  grid: (ceil(rc/128), ceil(height/strip)).
-template <int NT, int MINB>
-__global__ void __launch_bounds__(128, MINB) conv_col_tma_kernel(const Conv1dArgs a, const Taps<NT> taps) {
-  constexpr int PF = Ring<NT>::value;
-  __shared__ __align__(128) float ring[4][kTmaSlots][PF][32];
-  __shared__ __align__(8) unsigned long long full[4][kTmaSlots];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col0 = blockIdx.x * 128 + warp * 32;
-  if (col0 >= a.rc) return;                              // whole warp out of the image (warps are independent)
-  const bool blend = (lane & 3) != 3;
-  const int alpha_lane = lane | 3;
-  const int y0 = blockIdx.y * a.strip;
-  const int nout = min(a.strip, a.height - y0);
-  const int total = a.strip + NT - 1;                 // multiple of NT, hence of PF
-  const int nchunks = total / PF;
-  const int hmax = a.height - 1;
-  const unsigned pitch_bytes = static_cast<unsigned>(a.rc) * 4u;
-  const char *gbase = reinterpret_cast<const char *>(a.src + col0);
-  char *outp = reinterpret_cast<char *>(a.dst + col0 + lane) + static_cast<size_t>(y0) * pitch_bytes;
-  unsigned long long *bars = &full[warp][0];
-  float *wring = &ring[warp][0][0][0];
-
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < kTmaSlots; ++s) mbar_init(&bars[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  const int ysrc0 = y0 - a.off;
-  for (int c = 0; c < kTmaSlots - 1 && c < nchunks; ++c)
-    col_issue<PF>(wring + c * (PF * 32), &bars[c], gbase, ysrc0 + c * PF, hmax, pitch_bytes, 128u, lane);
-
-  double acc[NT];
-#pragma unroll
-  for (int q = 0; q < NT; ++q) acc[q] = 0.0;
-  int j = -(NT - 1);
-  int chunk = 0, slot = 0, nslot = kTmaSlots - 1;     // nslot = slot of chunk + kTmaSlots - 1
-  unsigned parity = 0;
-#pragma unroll 1
-  for (int mb = 0; mb < total; mb += NT) {
-#pragma unroll
-    for (int s = 0; s < NT; ++s) {
-      if (s % PF == 0) {
-        // the slot of chunk-1 is free now: refill it with chunk + kTmaSlots - 1, then wait for ours
-        const int nxt = chunk + kTmaSlots - 1;
-        if (nxt < nchunks)
-          col_issue<PF>(wring + nslot * (PF * 32), &bars[nslot], gbase, ysrc0 + nxt * PF, hmax, pitch_bytes, 128u, lane);
-        mbar_wait(&bars[slot], parity);
-      }
-      const float *rowp = wring + (slot * PF + (s % PF)) * 32;
-      const float vf = rowp[lane];
-      float af = rowp[alpha_lane];
-      af = blend ? af : 1.0f;
-      const double v = static_cast<double>(vf) * static_cast<double>(af);
-#pragma unroll
-      for (int q = 0; q < NT; ++q) acc[q] = fma(taps.k[(s - q + NT) % NT], v, acc[q]);
-      const int qf = (s + 1) % NT;
-      const double sum = acc[qf];
-      acc[qf] = 0.0;
-      const double gsum = shfl_double(sum, alpha_lane);
-      const float out = finish_rgba(blend, sum, gsum);
-      if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<float *>(outp) = out;
-      if (j >= 0) outp += pitch_bytes;
-      ++j;
-      if (s % PF == PF - 1) {
-        ++chunk;
-        nslot = slot;
-        if (++slot == kTmaSlots) { slot = 0; parity ^= 1u; }
-      }
-    }
-  }
-}
-
-// ---- row pass: CTA = 4 independent warps; a warp covers 8 rows x 4 channels; chunk = PF pixels of
-//      each row (pitch PF pixels, odd => conflict-free LDS).  grid: (ceil(width/strip), ceil(height/32)).
-template <int NT, int MINB>
-__global__ void __launch_bounds__(128, MINB) conv_row_tma_kernel(const Conv1dArgs a, const Taps<NT> taps) {
-  constexpr int PF = Ring<NT>::value;
-  static_assert(PF % 2 == 1, "odd chunk pitch keeps the LDS conflict-free");
-  __shared__ __align__(128) float ring[4][kTmaSlots][8][PF * 4];
-  __shared__ __align__(8) unsigned long long full[4][kTmaSlots];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ybase = blockIdx.y * 32 + warp * 8;
-  if (ybase >= a.height) return;
-  const int lr = lane >> 2, c = lane & 3;
-  const int x0 = blockIdx.x * a.strip;
-  const int y = ybase + lr;
-  const int hmax = a.height - 1;
-  const int nout = y < a.height ? min(a.strip, a.width - x0) : 0;
-  const int total = a.strip + NT - 1;
-  const int nchunks = total / PF;
-  const bool blend = c != 3;
-  const int alpha_lane = lane | 3;
-  float *outp = a.dst + (static_cast<size_t>(min(y, hmax)) * a.width + x0) * 4 + c;
-  unsigned long long *bars = &full[warp][0];
-  float *wring = &ring[warp][0][0][0];
-  const float4 *src4 = reinterpret_cast<const float4 *>(a.src);
-
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < kTmaSlots; ++s) mbar_init(&bars[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  const int xsrc0 = x0 - a.off;
-  for (int ck = 0; ck < kTmaSlots - 1 && ck < nchunks; ++ck)
-    row_issue<PF>(wring + ck * (8 * PF * 4), &bars[ck], src4, ybase, hmax, xsrc0 + ck * PF, a.width, lane);
-
-  double acc[NT];
-#pragma unroll
-  for (int q = 0; q < NT; ++q) acc[q] = 0.0;
-  int j = -(NT - 1);
-  int chunk = 0, slot = 0, nslot = kTmaSlots - 1;
-  unsigned parity = 0;
-#pragma unroll 1
-  for (int mb = 0; mb < total; mb += NT) {
-#pragma unroll
-    for (int s = 0; s < NT; ++s) {
-      if (s % PF == 0) {
-        const int nxt = chunk + kTmaSlots - 1;
-        if (nxt < nchunks)
-          row_issue<PF>(wring + nslot * (8 * PF * 4), &bars[nslot], src4, ybase, hmax, xsrc0 + nxt * PF, a.width, lane);
-        mbar_wait(&bars[slot], parity);
-      }
-      const float *pp = wring + ((slot * 8 + lr) * PF + (s % PF)) * 4;
-      const float vf = pp[c];
-      float af = pp[3];
-      af = blend ? af : 1.0f;
-      const double v = static_cast<double>(vf) * static_cast<double>(af);
-#pragma unroll
-      for (int q = 0; q < NT; ++q) acc[q] = fma(taps.k[(s - q + NT) % NT], v, acc[q]);
-      const int qf = (s + 1) % NT;
-      const double sum = acc[qf];
-      acc[qf] = 0.0;
-      const double gsum = shfl_double(sum, alpha_lane);
-      const float out = finish_rgba(blend, sum, gsum);
-      if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *outp = out;
-      if (j >= 0) outp += 4;
-      ++j;
-      if (s % PF == PF - 1) {
-        ++chunk;
-        nslot = slot;
-        if (++slot == kTmaSlots) { slot = 0; parity ^= 1u; }
-      }
-    }
-  }
-}
-
-// ======================================================================================
 // Two-components-per-thread kernels for RGBA ("pair" kernels, the default for 4 channels).
 // A thread owns two adjacent components of a pixel -- (R,G) on even lanes, (B,A) on odd lanes --
 // and therefore two independent rotations of NT accumulators.  Per pair of outputs this halves the
@@ -528,12 +326,7 @@ __global__ void __launch_bounds__(128, MINB) conv_row_tma_kernel(const Conv1dArg
 // Output stage of a pair: r = 1/clamp(den) (PerceptibleReciprocal on QS*den, morphology.c:3197),
 // colour components are scaled by r, the alpha component (odd lane, .y) is stored unscaled.
 __device__ __forceinline__ float2 finish_pair(bool odd, double sum0, double sum1, double gsum) {
-  constexpr double kTiny = kEpsilon / kQuantumScale;
-  double den = gsum;
-  const int hi = __double2hiint(den);
-  if ((hi & 0x7fffffff) < __double2hiint(kTiny))
-    den = __hiloint2double((hi & 0x80000000) | __double2hiint(kTiny), __double2loint(kTiny));
-  const double r = fast_reciprocal(den);
+  const double r = fast_reciprocal(clamp_denominator(gsum));
   const double m1 = odd ? 1.0 : r;
   return make_float2(static_cast<float>(sum0 * r), static_cast<float>(sum1 * m1));
 }
@@ -551,8 +344,11 @@ __device__ __forceinline__ float2 finish_pair(bool odd, double sum0, double sum1
 // 2 = raw double sums in, float Quantum out (second half).  With IO 1 + 2 a separable 2-D kernel
 // (e.g. "gaussian:RxS") is evaluated with kw + kh instead of kw * kh taps per sample while keeping the
 // intermediate in double, i.e. without the float rounding a two-kernel list would introduce.
-template <int NT, int MINB, int AXIS, int IO, bool L2PF = false>
+// PADDED: the launch carries fewer real taps than NT slots (see nonfinite_bits above).  EPI = 1: UnsharpMaskImage's
+// point pass fused into the output stage (AXIS 1, IO 0 only).
+template <int NT, int MINB, int AXIS, int IO, bool L2PF = false, bool PADDED = false, int EPI = 0>
 __global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a, const Taps<NT> taps) {
+  static_assert(EPI == 0 || (AXIS == 1 && IO == 0), "the fused epilogue belongs to the final column pass");
   constexpr int PF = Ring<NT>::value;
   constexpr unsigned kInB = (IO == 2) ? 8u : 4u, kOutB = (IO == 1) ? 8u : 4u;   // bytes per component
   using InT = typename std::conditional<IO == 2, double2, float2>::type;
@@ -628,11 +424,22 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a
         v0 = static_cast<double>(vf.x) * da;
         v1 = static_cast<double>(vf.y) * (odd ? 1.0 : da);
       }
+      if (PADDED && __any_sync(0xffffffffu, nonfinite_bits(vf.x) || nonfinite_bits(vf.y))) {
 #pragma unroll
-      for (int q = 0; q < NT; ++q) {
-        const double k = taps.k[(s - q + NT) % NT];
-        acc0[q] = fma(k, v0, acc0[q]);
-        acc1[q] = fma(k, v1, acc1[q]);
+        for (int q = 0; q < NT; ++q) {
+          if ((s - q + NT) % NT < a.ntaps) {
+            const double k = taps.k[(s - q + NT) % NT];
+            acc0[q] = fma(k, v0, acc0[q]);
+            acc1[q] = fma(k, v1, acc1[q]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < NT; ++q) {
+          const double k = taps.k[(s - q + NT) % NT];
+          acc0[q] = fma(k, v0, acc0[q]);
+          acc1[q] = fma(k, v1, acc1[q]);
+        }
       }
       const int qf = (s + 1) % NT;
       const double sum0 = acc0[qf], sum1 = acc1[qf];
@@ -642,124 +449,20 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a
         if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<double2 *>(outp) = make_double2(sum0, sum1);
       } else {
         const double gsum = shfl_double(sum1, alpha_lane);
-        const float2 out = finish_pair(odd, sum0, sum1, gsum);
-        if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<float2 *>(outp) = out;
+        float2 out = finish_pair(odd, sum0, sum1, gsum);
+        if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) {
+          if (EPI == 1) {          // same element of the operator's source image (outp - dst == its byte offset)
+            const float2 p = __ldg(reinterpret_cast<const float2 *>(
+                reinterpret_cast<const char *>(a.aux) + (outp - reinterpret_cast<char *>(a.dst))));
+            out.x = unsharp_point(p.x, out.x, a.gain, a.qthreshold);
+            out.y = unsharp_point(p.y, out.y, a.gain, a.qthreshold);
+          }
+          *reinterpret_cast<float2 *>(outp) = out;
+        }
       }
       if (j >= 0) outp += ostep;
       ++j;
     }
-    if (PF != NT) {
-      double t0[PF], t1[PF];
-#pragma unroll
-      for (int q = 0; q < PF; ++q) { t0[q] = acc0[q]; t1[q] = acc1[q]; }
-#pragma unroll
-      for (int q = 0; q < NT - PF; ++q) { acc0[q] = acc0[q + PF]; acc1[q] = acc1[q + PF]; }
-#pragma unroll
-      for (int q = 0; q < PF; ++q) { acc0[NT - PF + q] = t0[q]; acc1[NT - PF + q] = t1[q]; }
-    }
-  }
-}
-
-// ---- row pass: CTA = 4 independent warps; a warp covers 16 rows x 2 component pairs; every warp
-//      streams its rows through a private cp.async.bulk ring (chunk = PF pixels per row, odd
-//      pixel pitch => conflict-free LDS.64), so strips can be long and no block barrier is needed.
-//      grid: (ceil(width/strip), ceil(height/64)).
-template <int PF>
-__device__ __forceinline__ void row_pair_issue(float *slot_base, unsigned long long *bar, const float4 *src, int ybase,
-                                               int hmax, int xs, int width, int lane) {
-  __syncwarp();
-  if (lane == 0) mbar_expect_tx(bar, 16u * PF * 16u);
-  __syncwarp();
-  if (lane < 16) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const float4 *grow = src + static_cast<size_t>(min(ybase + lane, hmax)) * width;
-    float *dst = slot_base + lane * (PF * 4);
-    const int lo = max(xs, 0), hi = min(xs + PF, width);
-    if (hi > lo) bulk_g2s(dst + (lo - xs) * 4, grow + lo, static_cast<unsigned>(hi - lo) * 16u, bar);
-#pragma unroll 1
-    for (int x = xs; x < min(xs + PF, 0); ++x) bulk_g2s(dst + (x - xs) * 4, grow, 16u, bar);
-#pragma unroll 1
-    for (int x = max(xs, width); x < xs + PF; ++x) bulk_g2s(dst + (x - xs) * 4, grow + (width - 1), 16u, bar);
-  }
-}
-
-template <int NT, int MINB>
-__global__ void __launch_bounds__(128, MINB) conv_row_pair_kernel(const Conv1dArgs a, const Taps<NT> taps) {
-  constexpr int PF = Ring<NT>::value;
-  constexpr int kSlots = (PF > 11) ? 2 : 4;       // static shared memory stays below 48 KB
-  static_assert(PF % 2 == 1, "odd chunk pitch keeps the LDS conflict-free");
-  __shared__ __align__(128) float ring[4][kSlots][16][PF * 4];
-  __shared__ __align__(8) unsigned long long full[4][kSlots];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ybase = blockIdx.y * 64 + warp * 16;
-  if (ybase >= a.height) return;
-  const int lr = lane >> 1;
-  const bool odd = (lane & 1) != 0;
-  const int alpha_lane = lane | 1;
-  const int x0 = blockIdx.x * a.strip;
-  const int y = ybase + lr;
-  const int hmax = a.height - 1;
-  const int nout = y < a.height ? min(a.strip, a.width - x0) : 0;
-  const int total = a.strip + NT - 1;
-  const int nchunks = total / PF;
-  float *outp = a.dst + (static_cast<size_t>(min(y, hmax)) * a.width + x0) * 4 + (odd ? 2 : 0);
-  unsigned long long *bars = &full[warp][0];
-  float *wring = &ring[warp][0][0][0];
-  const float4 *src4 = reinterpret_cast<const float4 *>(a.src);
-
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) mbar_init(&bars[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  const int xsrc0 = x0 - a.off;
-  for (int ck = 0; ck < kSlots - 1 && ck < nchunks; ++ck)
-    row_pair_issue<PF>(wring + ck * (16 * PF * 4), &bars[ck], src4, ybase, hmax, xsrc0 + ck * PF, a.width, lane);
-
-  double acc0[NT], acc1[NT];
-#pragma unroll
-  for (int q = 0; q < NT; ++q) { acc0[q] = 0.0; acc1[q] = 0.0; }
-  int j = -(NT - 1);
-  int chunk = 0, slot = 0, nslot = kSlots - 1;
-  unsigned parity = 0;
-#pragma unroll 1
-  for (int mb = 0; mb < total; mb += PF) {       // one ring chunk == one unrolled block
-    {
-      const int nxt = chunk + kSlots - 1;
-      if (nxt < nchunks)
-        row_pair_issue<PF>(wring + nslot * (16 * PF * 4), &bars[nslot], src4, ybase, hmax, xsrc0 + nxt * PF, a.width,
-                           lane);
-      mbar_wait(&bars[slot], parity);
-    }
-    const float *cp = wring + ((slot * 16 + lr) * PF) * 4;
-#pragma unroll
-    for (int s = 0; s < PF; ++s) {
-      const float *pp = cp + s * 4;
-      const float2 vf = *reinterpret_cast<const float2 *>(pp + (odd ? 2 : 0));
-      const float af = pp[3];
-      const double da = static_cast<double>(af);
-      const double v0 = static_cast<double>(vf.x) * da;
-      const double v1 = static_cast<double>(vf.y) * (odd ? 1.0 : da);
-#pragma unroll
-      for (int q = 0; q < NT; ++q) {
-        const double k = taps.k[(s - q + NT) % NT];
-        acc0[q] = fma(k, v0, acc0[q]);
-        acc1[q] = fma(k, v1, acc1[q]);
-      }
-      const int qf = (s + 1) % NT;
-      const double sum0 = acc0[qf], sum1 = acc1[qf];
-      acc0[qf] = 0.0;
-      acc1[qf] = 0.0;
-      const double gsum = shfl_double(sum1, alpha_lane);
-      const float2 out = finish_pair(odd, sum0, sum1, gsum);
-      if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<float2 *>(outp) = out;
-      if (j >= 0) outp += 4;
-      ++j;
-    }
-    ++chunk;
-    nslot = slot;
-    if (++slot == kSlots) { slot = 0; parity ^= 1u; }
     if (PF != NT) {
       double t0[PF], t1[PF];
 #pragma unroll
@@ -784,9 +487,10 @@ __global__ void __launch_bounds__(128, MINB) conv_row_pair_kernel(const Conv1dAr
 //           cross-lane hazard, no barrier); LDS issued one step ahead.
 //   AXIS 0: per-warp ring of 8-pixel chunks of its 16 rows (full 128-B line requests, 144-B row pitch
 //           => conflict-free LDS.64); edge replication is applied by the loader.
-template <int NT, int MINB, int AXIS, int IO>
+template <int NT, int MINB, int AXIS, int IO, bool PADDED = false, int EPI = 0>
 __global__ void __launch_bounds__(128, MINB) conv_pair_async_kernel(const Conv1dArgs a, const Taps<NT> taps) {
   static_assert(IO == 0 || IO == 1, "float input only");
+  static_assert(EPI == 0 || (AXIS == 1 && IO == 0), "the fused epilogue belongs to the final column pass");
   // The asm statements below are volatile (ordered among themselves: copy -> commit -> wait -> LDS) but
   // carry no "memory" clobber: the ring is touched by nothing else, and the output STGs must stay free
   // to sink below the next step's copies (otherwise every step exposes the F2F -> STG latency).
@@ -872,11 +576,13 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_async_kernel(const Conv1d
   else { asm volatile("cp.async.wait_group %0;" ::"n"(NC - 1)); __syncwarp(); }
   asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(vnext.x), "=f"(vnext.y) : "r"(rd));
   double nv0, nv1;                                 // premultiplied sample of the next step
+  bool nbad = false;                               // ... and whether any lane's sample of that step is non-finite
   {
     const float af = __shfl_sync(0xffffffffu, vnext.y, alpha_lane);
     const double da = static_cast<double>(af);
     nv0 = static_cast<double>(vnext.x) * da;
     nv1 = static_cast<double>(vnext.y) * (odd ? 1.0 : da);
+    if (PADDED) nbad = __any_sync(0xffffffffu, nonfinite_bits(vnext.x) || nonfinite_bits(vnext.y));
   }
 
   int j = -(NT - 1);
@@ -886,6 +592,7 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_async_kernel(const Conv1d
 #pragma unroll
     for (int s = 0; s < UN; ++s) {
       const double v0 = nv0, v1 = nv1;
+      const bool bad = nbad;
       // fetch the next step's sample and keep the ring full
       if (AXIS == 1) {
         asm volatile("cp.async.wait_group %0;" ::"n"(NS - 3));      // row step+1 has landed
@@ -911,12 +618,24 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_async_kernel(const Conv1d
         const double da = static_cast<double>(af);
         nv0 = static_cast<double>(vnext.x) * da;
         nv1 = static_cast<double>(vnext.y) * (odd ? 1.0 : da);
+        if (PADDED) nbad = __any_sync(0xffffffffu, nonfinite_bits(vnext.x) || nonfinite_bits(vnext.y));
       }
+      if (PADDED && bad) {
 #pragma unroll
-      for (int q = 0; q < NT; ++q) {
-        const double k = taps.k[(s - q + NT) % NT];
-        acc0[q] = fma(k, v0, acc0[q]);
-        acc1[q] = fma(k, v1, acc1[q]);
+        for (int q = 0; q < NT; ++q) {
+          if ((s - q + NT) % NT < a.ntaps) {
+            const double k = taps.k[(s - q + NT) % NT];
+            acc0[q] = fma(k, v0, acc0[q]);
+            acc1[q] = fma(k, v1, acc1[q]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < NT; ++q) {
+          const double k = taps.k[(s - q + NT) % NT];
+          acc0[q] = fma(k, v0, acc0[q]);
+          acc1[q] = fma(k, v1, acc1[q]);
+        }
       }
       const int qf = (s + 1) % NT;
       const double sum0 = acc0[qf], sum1 = acc1[qf];
@@ -926,8 +645,16 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_async_kernel(const Conv1d
         if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<double2 *>(outp) = make_double2(sum0, sum1);
       } else {
         const double gsum = shfl_double(sum1, alpha_lane);
-        const float2 out = finish_pair(odd, sum0, sum1, gsum);
-        if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<float2 *>(outp) = out;
+        float2 out = finish_pair(odd, sum0, sum1, gsum);
+        if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) {
+          if (EPI == 1) {
+            const float2 p = __ldg(reinterpret_cast<const float2 *>(
+                reinterpret_cast<const char *>(a.aux) + (outp - reinterpret_cast<char *>(a.dst))));
+            out.x = unsharp_point(p.x, out.x, a.gain, a.qthreshold);
+            out.y = unsharp_point(p.y, out.y, a.gain, a.qthreshold);
+          }
+          *reinterpret_cast<float2 *>(outp) = out;
+        }
       }
       if (j >= 0) outp += ostep;
       ++j;
@@ -945,75 +672,92 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_async_kernel(const Conv1d
   asm volatile("cp.async.wait_group 0;" );
 }
 
-// developer tuning knobs (environment, read on every launch; defaults are the tuned values)
-int tuning(const char *name, int fallback) {
-  const char *v = getenv(name);
-  return (v && *v) ? atoi(v) : fallback;
+// Developer tuning knobs: environment variables read ONCE per process (defaults are the measured best).
+struct Tuning {
+  int pair, pair_async, pair_async_col, col_rot, row_pair_rot, row_rot, minb3;
+  Tuning() {
+    auto get = [](const char *name, int fallback) {
+      const char *v = getenv(name);
+      return (v && *v) ? atoi(v) : fallback;
+    };
+    pair = get("MB200_PAIR", 1);
+    pair_async = get("MB200_PAIR_ASYNC", 1);
+    pair_async_col = get("MB200_PAIR_ASYNC_COL", -1);     // -1: cp.async ring for windows shorter than 33 taps
+    col_rot = get("MB200_COL_ROT", 16);
+    row_pair_rot = get("MB200_ROW_PAIR_ROT", 16);
+    row_rot = get("MB200_ROW_ROT", 0);
+    minb3 = get("MB200_MINB3", 0);                         // experiment: 3 CTAs per SM (168 registers, small spills)
+  }
+};
+const Tuning &tuning() {
+  static const Tuning t;
+  return t;
+}
+
+// The RGBA pair kernels of one pass.  PADDED / EPI select the instantiation; everything else is the r01 choice.
+template <int NT, bool PADDED>
+void launch_pair(const Conv1dArgs &a, const Taps<NT> &taps, int axis, int io, bool fuse_unsharp, cudaStream_t stream) {
+  const Tuning &t = tuning();
+  if (axis == 1) {
+    dim3 grid((a.rc / 2 + 127) / 128, (a.height + a.strip - 1) / a.strip);
+    // NT = 33 is FP64-bound: the register-ring kernel (+ L2 prefetch) wins; shorter windows are closer to
+    // the HBM roof and gain from the cp.async ring (sigma=2: 1.36 -> 1.22 ms for the whole blur).
+    const bool async = (t.pair_async_col < 0 ? NT < 33 : t.pair_async_col != 0) && t.pair_async != 0;
+    if (io == 2) conv_pair_kernel<NT, 2, 1, 2, false, PADDED><<<grid, 128, 0, stream>>>(a, taps);
+    else if (io == 1 && async) conv_pair_async_kernel<NT, 2, 1, 1, PADDED><<<grid, 128, 0, stream>>>(a, taps);
+    else if (io == 1) conv_pair_kernel<NT, 2, 1, 1, NT == 33, PADDED><<<grid, 128, 0, stream>>>(a, taps);
+    else if (fuse_unsharp && async) conv_pair_async_kernel<NT, 2, 1, 0, PADDED, 1><<<grid, 128, 0, stream>>>(a, taps);
+    else if (fuse_unsharp) conv_pair_kernel<NT, 2, 1, 0, NT == 33, PADDED, 1><<<grid, 128, 0, stream>>>(a, taps);
+    else if (NT == 33 && !PADDED && t.minb3 == 1) conv_pair_async_kernel<NT, 3, 1, 0, false><<<grid, 128, 0, stream>>>(a, taps);
+    else if (async) conv_pair_async_kernel<NT, 2, 1, 0, PADDED><<<grid, 128, 0, stream>>>(a, taps);
+    else conv_pair_kernel<NT, 2, 1, 0, NT == 33, PADDED><<<grid, 128, 0, stream>>>(a, taps);
+  } else {
+    dim3 grid((a.width + a.strip - 1) / a.strip, (a.height + 63) / 64);
+    const bool async = t.pair_async != 0;
+    if (io == 1 && async) conv_pair_async_kernel<NT, 2, 0, 1, PADDED><<<grid, 128, 0, stream>>>(a, taps);
+    else if (io == 1) conv_pair_kernel<NT, 2, 0, 1, false, PADDED><<<grid, 128, 0, stream>>>(a, taps);
+    else if (io == 2) conv_pair_kernel<NT, 2, 0, 2, false, PADDED><<<grid, 128, 0, stream>>>(a, taps);
+    else if (NT == 33 && !PADDED && t.minb3 == 1) conv_pair_async_kernel<NT, 3, 0, 0, false><<<grid, 128, 0, stream>>>(a, taps);
+    else if (async) conv_pair_async_kernel<NT, 2, 0, 0, PADDED><<<grid, 128, 0, stream>>>(a, taps);
+    else conv_pair_kernel<NT, 2, 0, 0, false, PADDED><<<grid, 128, 0, stream>>>(a, taps);
+  }
 }
 
 template <int NT, int MODE>
-int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int ntaps, int io, cudaStream_t stream) {
+int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int ntaps, int io, bool *fused,
+              cudaStream_t stream) {
   Taps<NT> taps;
   for (int i = 0; i < NT; ++i) taps.k[i] = i < ntaps ? taps_host[i] : 0.0;   // zero padding past the window
   Conv1dArgs a = base;
-  const bool tma_ok = MODE == 4 && a.bias == 0.0 && tuning("MB200_TMA", 0) != 0 && (a.rc % 32) == 0 &&
-                      ((reinterpret_cast<uintptr_t>(a.src) | reinterpret_cast<uintptr_t>(a.dst)) & 15) == 0;
+  a.ntaps = ntaps;
+  const Tuning &t = tuning();
   if (io != 0 && !(MODE == 4 && NT <= 33)) return MB200_EUNSUPPORTED;
-  const bool pair_ok = MODE == 4 && a.bias == 0.0 && NT <= 33 && (io != 0 || tuning("MB200_PAIR", 1) != 0) &&
+  const bool pair_ok = MODE == 4 && a.bias == 0.0 && NT <= 33 && (io != 0 || t.pair != 0) &&
                        ((reinterpret_cast<uintptr_t>(a.src) | reinterpret_cast<uintptr_t>(a.dst)) & 15) == 0;
   if (io != 0 && !pair_ok) return MB200_EUNSUPPORTED;
-  if (pair_ok && axis == 1) {
-    if constexpr (NT <= 33) {
+  if (pair_ok) {
+    if constexpr (MODE == 4 && NT <= 33) {
       // strip = 16 rotations.  (A list-scheduling model of the launch -- equal-cost CTAs on 2 slots per SM -- preferred
       // 27 rotations for 8192 rows, 6 % fewer modelled steps; measured it is 5 % SLOWER, 0.822 vs 0.778 ms: CTAs that
       // run alone on an SM in the last wave get the whole FP64 pipe, so the tail balances itself.)
-      a.strip = tuning("MB200_COL_ROT", 16) * NT + 1;
+      a.strip = (axis == 1 ? t.col_rot : t.row_pair_rot) * NT + 1;
       a.seg_w = 16;                                  // rows of L2 prefetch ahead of the register ring (L2PF kernels)
-      dim3 grid((a.rc / 2 + 127) / 128, (a.height + a.strip - 1) / a.strip);
-      // NT = 33 is FP64-bound: the register-ring kernel (+ L2 prefetch) wins; shorter windows are closer to
-      // the HBM roof and gain from the cp.async ring (sigma=2: 1.36 -> 1.22 ms for the whole blur).
-      const bool async = tuning("MB200_PAIR_ASYNC_COL", NT < 33 ? 1 : 0) != 0 && tuning("MB200_PAIR_ASYNC", 1) != 0;
-      if (io == 2) conv_pair_kernel<NT, 2, 1, 2><<<grid, 128, 0, stream>>>(a, taps);
-      else if (io == 1 && async) conv_pair_async_kernel<NT, 2, 1, 1><<<grid, 128, 0, stream>>>(a, taps);
-      else if (io == 1) conv_pair_kernel<NT, 2, 1, 1, NT == 33><<<grid, 128, 0, stream>>>(a, taps);
-      else if (async) conv_pair_async_kernel<NT, 2, 1, 0><<<grid, 128, 0, stream>>>(a, taps);
-      else conv_pair_kernel<NT, 2, 1, 0, NT == 33><<<grid, 128, 0, stream>>>(a, taps);
+      const bool fuse = axis == 1 && io == 0 && a.aux != nullptr && (reinterpret_cast<uintptr_t>(a.aux) & 15) == 0;
+      if (ntaps != NT) launch_pair<NT, true>(a, taps, axis, io, fuse, stream);
+      else launch_pair<NT, false>(a, taps, axis, io, fuse, stream);
+      if (fused) *fused = fuse;
     }
-  } else if (pair_ok && axis == 0) {
-    if constexpr (NT <= 33) {
-      a.strip = tuning("MB200_ROW_PAIR_ROT", 16) * NT + 1;
-      dim3 grid((a.width + a.strip - 1) / a.strip, (a.height + 63) / 64);
-      const bool async = tuning("MB200_PAIR_ASYNC", 1) != 0;
-      if (io == 1 && async) conv_pair_async_kernel<NT, 2, 0, 1><<<grid, 128, 0, stream>>>(a, taps);
-      else if (io == 1) conv_pair_kernel<NT, 2, 0, 1><<<grid, 128, 0, stream>>>(a, taps);
-      else if (io == 2) conv_pair_kernel<NT, 2, 0, 2><<<grid, 128, 0, stream>>>(a, taps);
-      else if (async && !tuning("MB200_ROW_PAIR_TMA", 0)) conv_pair_async_kernel<NT, 2, 0, 0><<<grid, 128, 0, stream>>>(a, taps);
-      else if (tuning("MB200_ROW_PAIR_TMA", 0)) conv_row_pair_kernel<NT, 2><<<grid, 128, 0, stream>>>(a, taps);
-      else conv_pair_kernel<NT, 2, 0, 0><<<grid, 128, 0, stream>>>(a, taps);
-    }
-  } else if (tma_ok && axis == 1) {
-    constexpr int kMinBlocks = NT <= 33 ? 4 : 2;
-    a.strip = tuning("MB200_COL_ROT", 8) * NT + 1;
-    dim3 grid((a.rc + 127) / 128, (a.height + a.strip - 1) / a.strip);
-    if (NT == 33 && tuning("MB200_MINB", 3) == 3) conv_col_tma_kernel<NT, 3><<<grid, 128, 0, stream>>>(a, taps);
-    else conv_col_tma_kernel<NT, kMinBlocks><<<grid, 128, 0, stream>>>(a, taps);
-  } else if (tma_ok && axis == 0) {
-    constexpr int kMinBlocks = NT <= 33 ? 4 : 2;
-    a.strip = tuning("MB200_ROW_TMA_ROT", 8) * NT + 1;
-    dim3 grid((a.width + a.strip - 1) / a.strip, (a.height + 31) / 32);
-    if (NT == 33 && tuning("MB200_MINB", 3) == 3) conv_row_tma_kernel<NT, 3><<<grid, 128, 0, stream>>>(a, taps);
-    else conv_row_tma_kernel<NT, kMinBlocks><<<grid, 128, 0, stream>>>(a, taps);
   } else if (axis == 1) {
     constexpr int kThreads = 128;
     constexpr int kMinBlocks = NT <= 33 ? 4 : 2;
-    a.strip = tuning("MB200_COL_ROT", 16) * NT + 1;   // strip + NT - 1 is a whole number of rotations
+    a.strip = t.col_rot * NT + 1;   // strip + NT - 1 is a whole number of rotations
     dim3 grid((a.rc + kThreads - 1) / kThreads, (a.height + a.strip - 1) / a.strip);
     conv_col_kernel<NT, MODE, kThreads, kMinBlocks><<<grid, kThreads, 0, stream>>>(a, taps);
   } else {
     constexpr int kMinBlocks = NT <= 33 ? 4 : 2;
     // strip + NT - 1 is a whole number of rotations and the strip is at least ~64 outputs
     constexpr int kRot = (63 + NT - 1) / NT < 3 ? 3 : (63 + NT - 1) / NT;
-    a.strip = tuning("MB200_ROW_ROT", kRot) * NT + 1;
+    a.strip = (t.row_rot > 0 ? t.row_rot : kRot) * NT + 1;
     a.seg_w = a.strip + NT - 1;
     a.pitch = a.seg_w | 1;
     const int rows_per_cta = 4 * (32 / a.channels);
@@ -1030,18 +774,20 @@ int launch_nt(const Conv1dArgs &base, int axis, const double *taps_host, int nta
 }
 
 template <int NT>
-int launch_mode(const Conv1dArgs &a, int axis, const double *taps, int ntaps, int io, cudaStream_t s) {
-  if (a.channels == 4) return launch_nt<NT, 4>(a, axis, taps, ntaps, io, s);
+int launch_mode(const Conv1dArgs &a, int axis, const double *taps, int ntaps, int io, bool *fused, cudaStream_t s) {
+  if (a.channels == 4) return launch_nt<NT, 4>(a, axis, taps, ntaps, io, fused, s);
   if (io != 0) return MB200_EUNSUPPORTED;
-  if (a.channels == 2) return launch_nt<NT, 2>(a, axis, taps, ntaps, io, s);
-  return launch_nt<NT, 0>(a, axis, taps, ntaps, io, s);
+  if (a.channels == 2) return launch_nt<NT, 2>(a, axis, taps, ntaps, io, fused, s);
+  return launch_nt<NT, 0>(a, axis, taps, ntaps, io, fused, s);
 }
 
 }  // namespace
 
 int launch_conv1d(const float *src, float *dst, size_t width, size_t height, int channels, int axis,
                   const double *taps, int ntaps, int origin_offset, double bias, double /*gamma_scale*/,
-                  unsigned long long *d_changed, void *stream, int io) {
+                  unsigned long long *d_changed, void *stream, int io, const UnsharpEpilogue *epilogue,
+                  bool *epilogue_fused) {
+  if (epilogue_fused) *epilogue_fused = false;
   if (width == 0 || height == 0 || channels < 1 || channels > 4 || ntaps < 1)
     return fail(MB200_EINVAL, "conv1d: bad geometry");
   if (width * channels > 0x1fffffffull || height > 0x7fffffffull) return MB200_EUNSUPPORTED;   // 32-bit byte pitch
@@ -1053,13 +799,14 @@ int launch_conv1d(const float *src, float *dst, size_t width, size_t height, int
   a.off = origin_offset;
   a.bias = bias;
   a.changed = d_changed;
+  if (epilogue && epilogue->source) { a.aux = epilogue->source; a.gain = epilogue->gain; a.qthreshold = epilogue->quantum_threshold; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (ntaps <= 9) return launch_mode<9>(a, axis, taps, ntaps, io, s);
-  if (ntaps <= 17) return launch_mode<17>(a, axis, taps, ntaps, io, s);
-  if (ntaps <= 25) return launch_mode<25>(a, axis, taps, ntaps, io, s);
-  if (ntaps <= 33) return launch_mode<33>(a, axis, taps, ntaps, io, s);
-  if (ntaps <= 49) return launch_mode<49>(a, axis, taps, ntaps, io, s);
-  if (ntaps <= 65) return launch_mode<65>(a, axis, taps, ntaps, io, s);
+  if (ntaps <= 9) return launch_mode<9>(a, axis, taps, ntaps, io, epilogue_fused, s);
+  if (ntaps <= 17) return launch_mode<17>(a, axis, taps, ntaps, io, epilogue_fused, s);
+  if (ntaps <= 25) return launch_mode<25>(a, axis, taps, ntaps, io, epilogue_fused, s);
+  if (ntaps <= 33) return launch_mode<33>(a, axis, taps, ntaps, io, epilogue_fused, s);
+  if (ntaps <= 49) return launch_mode<49>(a, axis, taps, ntaps, io, epilogue_fused, s);
+  if (ntaps <= 65) return launch_mode<65>(a, axis, taps, ntaps, io, epilogue_fused, s);
   return MB200_EUNSUPPORTED;   // caller falls back to the generic 2-D kernel
 }
 

@@ -6,6 +6,8 @@
 #include <cstddef>
 #include <cstdint>
 
+struct CUmemPoolHandle_st;      // cudaMemPool_t == CUmemPoolHandle_st * (driver_types.h)
+
 namespace mb200 {
 
 // ---- error plumbing (runtime.cu) -------------------------------------------
@@ -19,6 +21,27 @@ int ensure_device();                     // lazily initialises the current devic
 void *default_stream();                  // library-owned stream of the current device
 int scratch(void **ptr, size_t bytes, int slot);   // grow-only device scratch buffers
 int sm_count();
+// The library's PRIVATE stream-ordered memory pool of the current device (temporaries of the operators).  The host
+// application's default pool is left alone; mb200_trim() gives the cached memory back.
+::CUmemPoolHandle_st *temp_pool();
+
+// ---- pixel-cache staging (cache.cu) ------------------------------------------
+// copy_h2d returns once the host buffer has been consumed (the copy itself may still be in flight on `stream`);
+// copy_d2h returns when the host buffer holds the data.  Pinned / registered / managed host memory is copied
+// directly, pageable memory through the threaded pinned bounce ring.
+int copy_h2d(void *dev, const void *host, size_t bytes, void *stream);
+int copy_d2h(void *host, const void *dev, size_t bytes, void *stream);
+struct StageRef {
+  void *entry = nullptr;     // residency-registry entry when the host buffer is an attached pixel cache
+  void *dev = nullptr;       // HBM copy to run the operator on
+  void *host = nullptr;
+  size_t bytes = 0;
+  bool temporary = false;    // dev is a stream-ordered temporary (unattached host buffer)
+};
+int stage_input(const void *host, size_t bytes, void *stream, StageRef *out);
+int stage_output(void *host, size_t bytes, void *stream, StageRef *out);
+int finish_output(StageRef *ref, void *stream);
+void release_stage(StageRef *ref, void *stream);
 
 // ---- kernel helpers (kernel_info.cpp) --------------------------------------
 void rotate_kernel_info(mb200_kernel_info *k, double angle);
@@ -34,20 +57,19 @@ inline bool has_alpha(int channels) { return channels == 2 || channels == 4; }
 // order (tap t multiplies the source sample at offset t - origin_offset).
 // axis 0 = along x (row path, morphology.c:2815), axis 1 = along y (column path :2654).
 // d_changed: device counter (may be null) incremented per changed channel value.
+// epilogue: UnsharpMaskImage's point pass (effect.c:4358-4364) fused into the output stage when the RGBA pair kernels
+// run the pass (*epilogue_fused tells; otherwise the caller runs launch_unsharp_combine afterwards).
+struct UnsharpEpilogue { const float *source; double gain, quantum_threshold; };
 int launch_conv1d(const float *src, float *dst, size_t width, size_t height, int channels,
                   int axis, const double *taps_window_order, int ntaps, int origin_offset,
                   double bias, double gamma_scale, unsigned long long *d_changed, void *stream,
-                  int io = 0);   // io: 0 float->float, 1 float->raw double sums, 2 raw double sums->float (RGBA only)
+                  int io = 0,    // io: 0 float->float, 1 float->raw double sums, 2 raw double sums->float (RGBA only)
+                  const UnsharpEpilogue *epilogue = nullptr, bool *epilogue_fused = nullptr);
 
 // conv2d.cu: general 2-D convolution / erode / dilate (MorphologyPrimitive row path)
 int launch_morph2d(const float *src, float *dst, size_t width, size_t height, int channels,
                    int method, const double *kernel_window_order, int kw, int kh, int ox, int oy,
                    double bias, double gamma_scale, unsigned long long *d_changed, void *stream);
-
-// morph_flat.cu: erode / dilate by run decomposition (MB200_EUNSUPPORTED => use launch_morph2d)
-int launch_morph_flat(const float *src, float *dst, size_t width, size_t height, int channels,
-                      int method, const double *kernel_window_order, int kw, int kh, int ox, int oy,
-                      unsigned long long *d_changed, void *stream);
 
 // morph_stream.cu: erode / dilate for the built-in structuring elements, register streaming
 // (MB200_EUNSUPPORTED => shape not in the table; use launch_morph2d)

@@ -25,6 +25,7 @@ constexpr int kScratchSlots = 8;
 struct DeviceStateImpl {
   bool ready = false;
   cudaStream_t stream = nullptr;
+  cudaMemPool_t pool = nullptr;      // private pool of the operators' temporaries
   int sms = 0;
   void *scratch[kScratchSlots] = {nullptr};
   size_t scratch_bytes[kScratchSlots] = {0};
@@ -68,6 +69,20 @@ int ensure_device() {
   d.sms = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+  {
+    // Temporaries come from a pool of our own: freed blocks stay cached for the next call (an 8192^2 blur needs a
+    // 1 GiB intermediate per call; re-creating it costs ~130 ms, reusing it 3 us -- tools/micro/staging.cu) without
+    // touching the release threshold of the host application's default pool.  mb200_trim() returns the memory.
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    e = cudaMemPoolCreate(&d.pool, &props);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemPoolCreate");
+    unsigned long long threshold = ~0ull;
+    cudaMemPoolSetAttribute(d.pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
   d.ready = true;
   return MB200_OK;
 }
@@ -81,6 +96,11 @@ static DeviceStateImpl *current() {
 void *default_stream() {
   DeviceStateImpl *d = current();
   return d ? d->stream : nullptr;
+}
+
+::CUmemPoolHandle_st *temp_pool() {
+  DeviceStateImpl *d = current();
+  return d ? d->pool : nullptr;
 }
 
 int sm_count() {
@@ -107,6 +127,22 @@ int scratch(void **ptr, size_t bytes, int slot) {
   return MB200_OK;
 }
 
+// FP64 FMA issue-rate probe (the co-limit of the convolution kernels): 16 independent DFMA chains per
+// thread, 1024 threads per SM.
+__global__ void __launch_bounds__(1024) fp64_probe_kernel(double *out, double a, double b, int iters) {
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 123.456) out[0] = s;
+}
+
 }  // namespace mb200
 
 using namespace mb200;
@@ -114,14 +150,27 @@ using namespace mb200;
 extern "C" {
 
 int mb200_device_count(void) {
-  int n = 0;
-  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
-  int usable = 0;
-  for (int i = 0; i < n; ++i) {
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++usable;
-  }
+  // probed once per process: cudaGetDeviceProperties costs milliseconds per device on a multi-GPU host
+  static std::once_flag once;
+  static int usable = 0;
+  std::call_once(once, [] {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return; }
+    for (int i = 0; i < n; ++i) {
+      int major = 0;
+      if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++usable;
+    }
+  });
   return usable;
+}
+
+int mb200_trim(size_t keep_bytes) {
+  int rc = ensure_device();
+  if (rc) return rc;
+  cudaStreamSynchronize(static_cast<cudaStream_t>(default_stream()));
+  cudaError_t e = cudaMemPoolTrimTo(temp_pool(), keep_bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemPoolTrimTo");
+  return MB200_OK;
 }
 
 int mb200_set_device(int device) {
@@ -140,6 +189,35 @@ int mb200_synchronize(void *stream) {
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : static_cast<cudaStream_t>(default_stream());
   cudaError_t e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+  return MB200_OK;
+}
+
+int mb200_probe_fp64_fma_rate(double *fma_per_second) {
+  if (!fma_per_second) return fail(MB200_EINVAL, "probe: null result");
+  int rc = ensure_device();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(default_stream());
+  void *buf = nullptr;
+  rc = scratch(&buf, 64, 7);
+  if (rc) return rc;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  const int iters = 8192, blocks = sm_count() * 2;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(a, s);
+    fp64_probe_kernel<<<blocks, 1024, 0, s>>>(static_cast<double *>(buf), 1.0000001, 1e-9, iters);
+    cudaEventRecord(b, s);
+    cudaError_t e = cudaEventSynchronize(b);
+    if (e != cudaSuccess) { cudaEventDestroy(a); cudaEventDestroy(b); return cuda_fail(e, "fp64 probe"); }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    const double rate = static_cast<double>(blocks) * 1024.0 * 16.0 * iters / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  count_launch(4);
+  *fma_per_second = best;
   return MB200_OK;
 }
 
@@ -175,18 +253,21 @@ int mb200_upload(void *dev_dst, const void *host_src, size_t bytes, void *stream
   int rc = ensure_device();
   if (rc) return rc;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : static_cast<cudaStream_t>(default_stream());
-  cudaError_t e = cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(H2D)");
-  return MB200_OK;
+  return copy_h2d(dev_dst, host_src, bytes, s);
 }
 
 int mb200_download(void *host_dst, const void *dev_src, size_t bytes, void *stream) {
   int rc = ensure_device();
   if (rc) return rc;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : static_cast<cudaStream_t>(default_stream());
-  cudaError_t e = cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, s);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(D2H)");
-  return MB200_OK;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, host_dst) == cudaSuccess &&
+      (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged)) {       // pinned: stays asynchronous
+    cudaError_t e = cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, s);
+    return e == cudaSuccess ? MB200_OK : cuda_fail(e, "cudaMemcpyAsync(D2H)");
+  }
+  cudaGetLastError();
+  return copy_d2h(host_dst, dev_src, bytes, s);
 }
 
 }  // extern "C"

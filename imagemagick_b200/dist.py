@@ -98,6 +98,29 @@ def blur_kernel_from_taps(taps: Sequence[float]):
     return api.AcquireKernelInfo(f"{n}x1:{vals};1x{n}:{vals}")
 
 
+def run_pipeline(images, blur_kernel, job: FilterJob):
+    """The configs[4] pipeline on this rank's shard: {index: Image} -> {index: Image}.  BlurImage (as ConvolveImage with
+    the broadcast taps) then ResizeImage; device-resident Images stay in HBM, no pixel leaves the GPU."""
+    from . import api
+    out = {}
+    for idx, image in images.items():
+        blurred = api.ConvolveImage(image, blur_kernel)
+        out[idx] = api.ResizeImage(blurred, job.out_columns, job.out_rows, job.resize_filter)
+    return out
+
+
+def gather_over_ranks(values, device=None):
+    """All ranks' float lists (equal length) as a [world][n] nested list on every rank."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [list(values)]
+    t = torch.tensor(list(values), dtype=torch.float64, device=device if device is not None else "cpu")
+    outs = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, t)
+    return [o.cpu().tolist() for o in outs]
+
+
 def max_over_ranks(value: float, device=None) -> float:
     import torch
     import torch.distributed as dist

@@ -92,6 +92,28 @@ static Image *new_result(const Image *image, size_t columns, size_t rows, Except
   return out;
 }
 
+/* The pixel cache itself, for images whose cache is heap memory (cache.c:1273: the OpenCL path makes the same
+   MemoryCache test; disk, map and distributed caches decline).  GetPixelCachePixels (cache.c:2310) hands out
+   cache_info->pixels without passing one of the cache's sync sites -- what GetAuthenticOpenCLBuffer (cache.c:1259)
+   is to the OpenCL path: in hook mode a result that still lives in HBM must not be pulled back just because the
+   next operator asks where the pixels are. */
+static float *b200_cache_pixels(const Image *image, int channels, ExceptionInfo *exception)
+{
+  MagickSizeType length = 0;
+  void *pixels;
+  if (GetImagePixelCacheType(image) != MemoryCache) return (float *) NULL;
+  pixels = GetPixelCachePixels((Image *) image, &length, exception);
+  if (pixels == (void *) NULL ||
+      length != (MagickSizeType) image->columns * image->rows * (size_t) channels * sizeof(Quantum))
+    return (float *) NULL;
+  return (float *) pixels;
+}
+
+/* A GPU attempt reports into an ExceptionInfo of its own: when it declines, the CPU path must start with the
+   caller's exception untouched (the "declined without raising" contract of effect.c:783-787). */
+#define B200_ATTEMPT_BEGIN ExceptionInfo *attempt = AcquireExceptionInfo()
+#define B200_ATTEMPT_END   attempt = DestroyExceptionInfo(attempt)
+
 typedef int (*same_size_op)(const float *, float *, size_t, size_t, int, const void *);
 
 /* src pixels -> new image through `op`; NULL == declined (caller falls back to the CPU). */
@@ -99,19 +121,26 @@ static Image *run_same_size(const Image *image, same_size_op op, const void *arg
                             ExceptionInfo *exception)
 {
   const int ch = b200_channels(image);
-  const Quantum *p;
+  const float *p;
   Quantum *q;
   Image *out;
+  (void) exception;
   if (ch == 0 || mb200_device_count() <= 0) return (Image *) NULL;
-  p = GetVirtualPixels(image, 0, 0, image->columns, image->rows, exception);
-  if (p == (const Quantum *) NULL) return (Image *) NULL;
-  out = new_result(image, image->columns, image->rows, exception);
-  if (out == (Image *) NULL) return out;
-  q = GetAuthenticPixels(out, 0, 0, out->columns, out->rows, exception);
-  if (q == (Quantum *) NULL || op((const float *) p, (float *) q, image->columns, image->rows, ch, args) != MB200_OK ||
-      SyncAuthenticPixels(out, exception) == MagickFalse)
-    return DestroyImage(out);
-  out->type = image->type;
+  {
+    B200_ATTEMPT_BEGIN;
+    out = (Image *) NULL;
+    p = b200_cache_pixels(image, ch, attempt);
+    if (p != (const float *) NULL) out = new_result(image, image->columns, image->rows, attempt);
+    if (out != (Image *) NULL) {
+      q = GetAuthenticPixels(out, 0, 0, out->columns, out->rows, attempt);
+      if (q == (Quantum *) NULL || b200_cache_pixels(out, ch, attempt) != (float *) q ||
+          op(p, (float *) q, image->columns, image->rows, ch, args) != MB200_OK ||
+          SyncAuthenticPixels(out, attempt) == MagickFalse)
+        out = DestroyImage(out);
+    }
+    B200_ATTEMPT_END;
+  }
+  if (out != (Image *) NULL) out->type = image->type;
   return out;
 }
 
@@ -213,23 +242,28 @@ Image *B200AccelerateResizeImage(const Image *image, const size_t columns, const
                                  const FilterType filter, ExceptionInfo *exception)
 {
   const int ch = b200_channels(image);
-  const Quantum *p;
+  const float *p;
   Quantum *q;
   Image *out;
+  (void) exception;
   if (ch == 0 || columns == 0 || rows == 0 || mb200_device_count() <= 0) return (Image *) NULL;
   if (has_artifact(image, filter_artifacts) != MagickFalse) return (Image *) NULL;
   if (image->storage_class == PseudoClass) return (Image *) NULL;
-  p = GetVirtualPixels(image, 0, 0, image->columns, image->rows, exception);
-  if (p == (const Quantum *) NULL) return (Image *) NULL;
-  out = new_result(image, columns, rows, exception);
-  if (out == (Image *) NULL) return out;
-  q = GetAuthenticPixels(out, 0, 0, columns, rows, exception);
-  if (q == (Quantum *) NULL ||
-      mb200_resize_image((const float *) p, image->columns, image->rows, ch, (float *) q, columns, rows,
-                         (int) filter) != MB200_OK ||
-      SyncAuthenticPixels(out, exception) == MagickFalse)
-    return DestroyImage(out);
-  out->type = image->type;
+  {
+    B200_ATTEMPT_BEGIN;
+    out = (Image *) NULL;
+    p = b200_cache_pixels(image, ch, attempt);
+    if (p != (const float *) NULL) out = new_result(image, columns, rows, attempt);
+    if (out != (Image *) NULL) {
+      q = GetAuthenticPixels(out, 0, 0, columns, rows, attempt);
+      if (q == (Quantum *) NULL || b200_cache_pixels(out, ch, attempt) != (float *) q ||
+          mb200_resize_image(p, image->columns, image->rows, ch, (float *) q, columns, rows, (int) filter) != MB200_OK ||
+          SyncAuthenticPixels(out, attempt) == MagickFalse)
+        out = DestroyImage(out);
+    }
+    B200_ATTEMPT_END;
+  }
+  if (out != (Image *) NULL) out->type = image->type;
   return out;
 }
 
@@ -237,22 +271,28 @@ Image *B200AccelerateResizeImage(const Image *image, const size_t columns, const
 Image *B200AccelerateSampleImage(const Image *image, const size_t columns, const size_t rows, ExceptionInfo *exception)
 {
   const int ch = b200_channels(image);
-  const Quantum *p;
+  const float *p;
   Quantum *q;
   Image *out;
+  (void) exception;
   if (ch == 0 || columns == 0 || rows == 0 || mb200_device_count() <= 0) return (Image *) NULL;
   if ((columns == image->columns) && (rows == image->rows)) return (Image *) NULL;      /* plain clone: CPU */
   if (GetImageArtifact(image, "sample:offset") != (const char *) NULL) return (Image *) NULL;
-  p = GetVirtualPixels(image, 0, 0, image->columns, image->rows, exception);
-  if (p == (const Quantum *) NULL) return (Image *) NULL;
-  out = new_result(image, columns, rows, exception);
-  if (out == (Image *) NULL) return out;
-  q = GetAuthenticPixels(out, 0, 0, columns, rows, exception);
-  if (q == (Quantum *) NULL ||
-      mb200_sample_image((const float *) p, image->columns, image->rows, ch, (float *) q, columns, rows) != MB200_OK ||
-      SyncAuthenticPixels(out, exception) == MagickFalse)
-    return DestroyImage(out);
-  out->type = image->type;
+  {
+    B200_ATTEMPT_BEGIN;
+    out = (Image *) NULL;
+    p = b200_cache_pixels(image, ch, attempt);
+    if (p != (const float *) NULL) out = new_result(image, columns, rows, attempt);
+    if (out != (Image *) NULL) {
+      q = GetAuthenticPixels(out, 0, 0, columns, rows, attempt);
+      if (q == (Quantum *) NULL || b200_cache_pixels(out, ch, attempt) != (float *) q ||
+          mb200_sample_image(p, image->columns, image->rows, ch, (float *) q, columns, rows) != MB200_OK ||
+          SyncAuthenticPixels(out, attempt) == MagickFalse)
+        out = DestroyImage(out);
+    }
+    B200_ATTEMPT_END;
+  }
+  if (out != (Image *) NULL) out->type = image->type;
   return out;
 }
 
@@ -292,13 +332,20 @@ MagickBooleanType B200AccelerateTransformImageColorspace(Image *image, const Col
   ch = b200_channels(image);
   image->colorspace = saved;
   if (ch != 3 && ch != 4) return MagickFalse;
-  q = GetAuthenticPixels(image, 0, 0, image->columns, image->rows, exception);
-  if (q == (Quantum *) NULL) return MagickFalse;
+  {
+    MagickBooleanType ok = MagickFalse;
+    B200_ATTEMPT_BEGIN;
+    /* GetAuthenticPixels un-shares a copy-on-write cache (GetImagePixelCache, cache.c:1715) before it is written */
+    q = GetAuthenticPixels(image, 0, 0, image->columns, image->rows, attempt);
+    if (q != (Quantum *) NULL && b200_cache_pixels(image, ch, attempt) == (float *) q &&
+        mb200_transform_colorspace((float *) q, image->columns, image->rows, ch, from, to) == MB200_OK &&
+        SyncAuthenticPixels(image, attempt) != MagickFalse)
+      ok = MagickTrue;
+    B200_ATTEMPT_END;
+    if (ok == MagickFalse) return MagickFalse;    /* nothing was written back: the CPU path starts from the same pixels */
+  }
   (void) DeleteImageProfile(image, "icc");                 /* colorspace.c:1763-1764 */
   (void) DeleteImageProfile(image, "icm");
-  if (mb200_transform_colorspace((float *) q, image->columns, image->rows, ch, from, to) != MB200_OK)
-    return MagickFalse;
-  if (SyncAuthenticPixels(image, exception) == MagickFalse) return MagickFalse;
   return SetImageColorspace(image, colorspace, exception);  /* colorspace.c:1051 */
 }
 
@@ -316,6 +363,10 @@ static MagickBooleanType run_threshold(Image *image, int op, double threshold, c
   Quantum *q;
   int ch, rc, cs;
   if (mb200_device_count() <= 0) return MagickFalse;
+  /* With a channel mask the reference thresholds every selected channel on ITS OWN value (threshold.c:871, :1032,
+     :2623); the kernel implements the default, intensity-driven form only.  `-channel RGB` on an opaque RGB image
+     leaves every trait at its default, so the trait test of b200_channels() cannot see the mask. */
+  if (op != 3 && image->channel_mask != AllChannels) return MagickFalse;
   if (op != 3 && default_intensity(image) == MagickFalse) return MagickFalse;
   if (image->colorspace == LinearGRAYColorspace) return MagickFalse;       /* intensity would need EncodePixelGamma */
   if ((op == 1 || op == 2) && thresholds == (const char *) NULL) return MagickFalse;
@@ -325,17 +376,24 @@ static MagickBooleanType run_threshold(Image *image, int op, double threshold, c
   if (op == 0 && image->colorspace != GRAYColorspace && image->colorspace != LinearGRAYColorspace)
     (void) SetImageColorspace(image, sRGBColorspace, exception);            /* threshold.c:827 */
   if (GetPixelChannels(image) != (size_t) ch) return MagickFalse;
-  q = GetAuthenticPixels(image, 0, 0, image->columns, image->rows, exception);
-  if (q == (Quantum *) NULL) return MagickFalse;
   cs = image->colorspace == RGBColorspace ? MB200_RGBColorspace : MB200_sRGBColorspace;
-  switch (op) {
-    case 0: rc = mb200_bilevel_image((float *) q, image->columns, image->rows, ch, threshold); break;
-    case 1: rc = mb200_black_threshold_image((float *) q, image->columns, image->rows, ch, cs, thresholds); break;
-    case 2: rc = mb200_white_threshold_image((float *) q, image->columns, image->rows, ch, cs, thresholds); break;
-    default: rc = mb200_clamp_image((float *) q, image->columns, image->rows, ch); break;
+  {
+    MagickBooleanType ok = MagickFalse;
+    B200_ATTEMPT_BEGIN;
+    q = GetAuthenticPixels(image, 0, 0, image->columns, image->rows, attempt);
+    rc = MB200_EINVAL;
+    if (q != (Quantum *) NULL && b200_cache_pixels(image, ch, attempt) == (float *) q)
+      switch (op) {
+        case 0: rc = mb200_bilevel_image((float *) q, image->columns, image->rows, ch, threshold); break;
+        case 1: rc = mb200_black_threshold_image((float *) q, image->columns, image->rows, ch, cs, thresholds); break;
+        case 2: rc = mb200_white_threshold_image((float *) q, image->columns, image->rows, ch, cs, thresholds); break;
+        default: rc = mb200_clamp_image((float *) q, image->columns, image->rows, ch); break;
+      }
+    /* on failure nothing was written back: the CPU path starts from the same pixels */
+    if (rc == MB200_OK && SyncAuthenticPixels(image, attempt) != MagickFalse) ok = MagickTrue;
+    B200_ATTEMPT_END;
+    return ok;
   }
-  if (rc != MB200_OK) return MagickFalse;     /* nothing was written back: the CPU path starts from the same pixels */
-  return SyncAuthenticPixels(image, exception);
 }
 
 MagickBooleanType B200AccelerateBilevelImage(Image *image, const double threshold, ExceptionInfo *exception)
@@ -387,10 +445,11 @@ extern MagickBooleanType __real_BlackThresholdImage(Image *, const char *, Excep
 extern MagickBooleanType __real_WhiteThresholdImage(Image *, const char *, ExceptionInfo *);
 extern MagickBooleanType __real_ClampImage(Image *, ExceptionInfo *);
 
-static long b200_hits = 0, b200_fallbacks = 0;
+static long b200_hits = 0, b200_fallbacks = 0;          /* updated with atomic adds: the entry points are re-entrant */
 static int b200_enabled = -1;       /* -1: not yet read from the environment */
-long B200ShimHits(void) { return b200_hits; }
-long B200ShimFallbacks(void) { return b200_fallbacks; }
+#define B200_COUNT(var) ((void) __atomic_fetch_add(&(var), 1L, __ATOMIC_RELAXED))
+long B200ShimHits(void) { return __atomic_load_n(&b200_hits, __ATOMIC_RELAXED); }
+long B200ShimFallbacks(void) { return __atomic_load_n(&b200_fallbacks, __ATOMIC_RELAXED); }
 /* Runtime switch (also: environment MAGICK_B200_DISABLE=1), e.g. to A/B against the CPU path. */
 void B200ShimEnable(int on) { b200_enabled = on ? 1 : 0; }
 static int b200_on(void)
@@ -401,7 +460,7 @@ static int b200_on(void)
   }
   return b200_enabled;
 }
-#define TRY(expr) do { if (b200_on()) { Image *r_ = (expr); if (r_ != (Image *) NULL) { b200_hits++; return r_; } b200_fallbacks++; } } while (0)
+#define TRY(expr) do { if (b200_on()) { Image *r_ = (expr); if (r_ != (Image *) NULL) { B200_COUNT(b200_hits); return r_; } B200_COUNT(b200_fallbacks); } } while (0)
 
 Image *__wrap_BlurImage(const Image *image, const double radius, const double sigma, ExceptionInfo *exception)
 {
@@ -448,15 +507,15 @@ MagickBooleanType __wrap_TransformImageColorspace(Image *image, const Colorspace
 {
   if (b200_on()) {
     if (B200AccelerateTransformImageColorspace(image, colorspace, exception) != MagickFalse) {
-      b200_hits++;
+      B200_COUNT(b200_hits);
       return MagickTrue;
     }
-    b200_fallbacks++;
+    B200_COUNT(b200_fallbacks);
   }
   return __real_TransformImageColorspace(image, colorspace, exception);
 }
 
-#define TRY_BOOL(expr) do { if (b200_on()) { if ((expr) != MagickFalse) { b200_hits++; return MagickTrue; } b200_fallbacks++; } } while (0)
+#define TRY_BOOL(expr) do { if (b200_on()) { if ((expr) != MagickFalse) { B200_COUNT(b200_hits); return MagickTrue; } B200_COUNT(b200_fallbacks); } } while (0)
 
 MagickBooleanType __wrap_BilevelImage(Image *image, const double threshold, ExceptionInfo *exception)
 {
@@ -584,4 +643,111 @@ Image *__wrap_MotionBlurImage(const Image *image, const double radius, const dou
 {
   TRY(B200AccelerateMotionBlurImage(image, radius, sigma, angle, exception));
   return __real_MotionBlurImage(image, radius, sigma, angle, exception);
+}
+
+/* ---- pixel caches in pinned host memory --------------------------------------------------------------------------------
+   OpenPixelCache takes a memory cache's pixels from AcquireAlignedMemory (cache.c:3757), and that function honours the
+   public SetMagickAlignedMemoryMethods hook (memory.c:376, :1541).  B200ShimInstallPixelCachePool() installs an allocator
+   that serves large blocks (pixel caches) from a recycling pool of CUDA-pinned host memory and attaches each block to
+   libmagickb200's residency registry: the operators then move pixels at PCIe speed (55 GB/s instead of the 9 / 19 GB/s of
+   pageable cudaMemcpy, tools/micro/staging.cu) straight from / to the cache, and every pixel cache keeps one HBM copy for
+   its lifetime.  Pinning costs ~300 ms per GiB, which is why freed blocks are recycled instead of being unpinned.  Small
+   blocks and everything allocated before the installation stay with posix_memalign / free.
+   Enabled by calling the function, or by MAGICK_B200_PINNED_CACHE=1 in the environment (checked when the shim is loaded). */
+#include <pthread.h>
+
+#define B200_POOL_MIN_BYTES ((size_t) 1 << 20)
+#define B200_POOL_MAX_BLOCKS 256
+static struct { void *ptr; size_t capacity; int in_use; } b200_pool[B200_POOL_MAX_BLOCKS];
+static size_t b200_pool_idle_bytes = 0, b200_pool_idle_limit = (size_t) 8 << 30;
+static pthread_mutex_t b200_pool_mutex = PTHREAD_MUTEX_INITIALIZER;
+static long b200_pool_reused = 0, b200_pool_pinned = 0;
+
+static void *b200_acquire_aligned(const size_t size, const size_t alignment)
+{
+  void *memory = (void *) NULL;
+  if (size >= B200_POOL_MIN_BYTES && mb200_device_count() > 0) {
+    int i, best = -1, slot = -1;
+    pthread_mutex_lock(&b200_pool_mutex);
+    for (i = 0; i < B200_POOL_MAX_BLOCKS; i++) {
+      if (b200_pool[i].ptr == (void *) NULL) { if (slot < 0) slot = i; continue; }
+      if (b200_pool[i].in_use == 0 && b200_pool[i].capacity >= size && b200_pool[i].capacity <= size + size / 4 &&
+          (best < 0 || b200_pool[i].capacity < b200_pool[best].capacity)) best = i;
+    }
+    if (best >= 0) {
+      b200_pool[best].in_use = 1;
+      b200_pool_idle_bytes -= b200_pool[best].capacity;
+      b200_pool_reused++;
+      memory = b200_pool[best].ptr;
+    } else if (slot >= 0) {
+      const size_t capacity = (size + ((size_t) 1 << 21) - 1) & ~(((size_t) 1 << 21) - 1);
+      b200_pool[slot].in_use = 1;                 /* reserve the slot while the (slow) pinning runs unlocked */
+      b200_pool[slot].ptr = (void *) &b200_pool;  /* placeholder: not a block anybody can hold */
+      pthread_mutex_unlock(&b200_pool_mutex);
+      if (mb200_malloc_host(&memory, capacity) != MB200_OK) memory = (void *) NULL;
+      pthread_mutex_lock(&b200_pool_mutex);
+      if (memory != (void *) NULL) { b200_pool[slot].ptr = memory; b200_pool[slot].capacity = capacity; b200_pool_pinned++; }
+      else { b200_pool[slot].ptr = (void *) NULL; b200_pool[slot].in_use = 0; }
+    }
+    pthread_mutex_unlock(&b200_pool_mutex);
+    if (memory != (void *) NULL) {
+      (void) mb200_cache_attach(memory, size, 0);
+      return memory;
+    }
+  }
+  if (posix_memalign(&memory, alignment < sizeof(void *) ? sizeof(void *) : alignment, size) != 0) return (void *) NULL;
+  return memory;
+}
+
+static void b200_relinquish_aligned(void *memory)
+{
+  int i, ours = 0;
+  void *release = (void *) NULL;
+  if (memory == (void *) NULL) return;
+  pthread_mutex_lock(&b200_pool_mutex);
+  for (i = 0; i < B200_POOL_MAX_BLOCKS; i++)
+    if (b200_pool[i].ptr == memory && b200_pool[i].in_use != 0) {
+      ours = 1;
+      b200_pool[i].in_use = 0;
+      if (b200_pool_idle_bytes + b200_pool[i].capacity > b200_pool_idle_limit) { release = memory; b200_pool[i].ptr = (void *) NULL; }
+      else b200_pool_idle_bytes += b200_pool[i].capacity;
+      break;
+    }
+  pthread_mutex_unlock(&b200_pool_mutex);
+  if (ours == 0) { free(memory); return; }
+  (void) mb200_cache_detach(memory);              /* the image is gone: drop its HBM copy */
+  if (release != (void *) NULL) (void) mb200_free_host(release);
+}
+
+void B200ShimInstallPixelCachePool(void)
+{
+  SetMagickAlignedMemoryMethods(b200_acquire_aligned, b200_relinquish_aligned);
+}
+void B200ShimPixelCachePoolStats(long *pinned_blocks, long *reused_blocks)
+{
+  if (pinned_blocks) *pinned_blocks = b200_pool_pinned;
+  if (reused_blocks) *reused_blocks = b200_pool_reused;
+}
+
+/* ---- lazy synchronisation (hook mode) -----------------------------------------------------------------------------------
+   The reference keeps an OpenCL result in its cl_mem until somebody looks at the pixels: CopyOpenCLBuffer() is called at
+   three places of cache.c -- GetImagePixelCache (:1710, before the host writes), GetVirtualPixelCacheNexus (:2771, before the
+   host reads) and PersistPixelCache (:4079).  A build that adds B200PixelCacheHook(cache_info->pixels, for_write) at the
+   same three places (INTEGRATION.md has the patch; oracle/Makefile generates such a cache.c for the hooked harness) gets the
+   same behaviour here: call B200ShimSetLazySync(1) once and chained operators (-blur ... -resize ...) upload once and
+   download once.  Without the hooks lazy mode must stay off: nothing would bring a result back to the host. */
+void B200PixelCacheHook(void *pixels, int for_write)
+{
+  if (pixels == (void *) NULL) return;
+  (void) mb200_cache_sync(pixels);
+  if (for_write != 0) (void) mb200_cache_host_written(pixels);
+}
+void B200ShimSetLazySync(int on) { (void) mb200_cache_set_lazy(on); }
+
+__attribute__((constructor)) static void b200_shim_init(void)
+{
+  const char *e = getenv("MAGICK_B200_PINNED_CACHE");
+  if (e != (const char *) NULL && *e != '\0' && *e != '0') B200ShimInstallPixelCachePool();
+  e = getenv("MAGICK_B200_LAZY_SYNC");          /* only for builds that carry the cache.c hooks */
+  if (e != (const char *) NULL && *e != '\0' && *e != '0') B200ShimSetLazySync(1);
 }

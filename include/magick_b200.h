@@ -138,8 +138,49 @@ MB200_API int mb200_malloc(void **dev_ptr, size_t bytes);
 MB200_API int mb200_free(void *dev_ptr);
 MB200_API int mb200_malloc_host(void **host_ptr, size_t bytes);   /* pinned */
 MB200_API int mb200_free_host(void *host_ptr);
+/* Asynchronous on `stream` when the host memory is pinned; pageable memory is moved through the bounce ring
+   (mb200_upload returns once the host buffer has been consumed, mb200_download when it holds the data). */
 MB200_API int mb200_upload(void *dev_dst, const void *host_src, size_t bytes, void *stream);
 MB200_API int mb200_download(void *host_dst, const void *dev_src, size_t bytes, void *stream);
+
+/* Gives the memory cached in the library's private stream-ordered pool (operator temporaries of the
+   current device) back to the driver, keeping at most `keep_bytes`.  The host application's default pool is
+   never touched. */
+MB200_API int mb200_trim(size_t keep_bytes);
+/* Measures the FP64 FMA issue rate of the current device (FMA/s; 16 independent DFMA chains per thread):
+   the co-limit of the FP64-accumulating convolution kernels (bench.py's second roofline entry). */
+MB200_API int mb200_probe_fp64_fma_rate(double *fma_per_second);
+/* Test / developer hook: force the generic kernels ("no_rank1", "no_morph_stream", "no_resize_stream",
+   "resize_regular_h", "no_fused_unsharp"; initialised from the MB200_<NAME> environment variables). */
+MB200_API int mb200_set_option(const char *name, int value);
+
+/* ------------------------------------------ pixel cache staged into HBM ---- */
+/* Residency of HOST pixel caches in HBM -- the CUDA analogue of the reference's OpenCL cache plumbing:
+     mb200_cache_attach        AcquireMagickCLCacheInfo      MagickCore/opencl.c:528-553
+     (operators below)         GetAuthenticOpenCLBuffer      MagickCore/cache.c:1259-1292
+     mb200_cache_sync          CopyOpenCLBuffer              MagickCore/cache.c:5341-5364 (sites :1710, :2771, :4079)
+     mb200_cache_detach        RelinquishMagickCLCacheInfo   MagickCore/cache.c:978-984
+   An attached buffer keeps one HBM copy for its lifetime.  The host-buffer operators find it by the buffer's
+   base address: inputs whose HBM copy is current are not uploaded again, results are written to the HBM copy.
+   EAGER mode (default): a result is copied to its host buffer before the operator returns, and an input's HBM
+   copy is trusted only while it is the sole current copy -- always safe, no cooperation needed.
+   LAZY mode (mb200_cache_set_lazy(1)): results stay in HBM until mb200_cache_sync(host) and resident inputs
+   are not re-uploaded; the caller must call mb200_cache_sync before the host READS a buffer and
+   mb200_cache_host_written after the host WRITES one (the three CopyOpenCLBuffer sites of cache.c are exactly
+   those places; INTEGRATION.md shows the patch).  Unattached buffers are staged per call in either mode.
+   Host memory that is pinned (mb200_malloc_host, cudaHostRegister, MB200_CACHE_REGISTER) moves at PCIe speed
+   (55 GB/s); pageable memory goes through a threaded pinned bounce ring (49 / 44 GB/s up / down instead of
+   cudaMemcpy's 9 / 19 GB/s). */
+enum { MB200_CACHE_REGISTER = 1 };   /* pin the buffer with cudaHostRegister (67-450 ms per GiB, once) */
+MB200_API int mb200_cache_attach(void *host_pixels, size_t bytes, int flags);
+MB200_API int mb200_cache_detach(void *host_pixels);            /* drops the HBM copy WITHOUT syncing */
+MB200_API int mb200_cache_sync(void *host_pixels);              /* HBM -> host if the HBM copy is newer */
+MB200_API int mb200_cache_host_written(void *host_pixels);      /* the HBM copy is stale */
+MB200_API int mb200_cache_resident(const void *host_pixels);    /* -1 unknown; bit 0: HBM copy current, bit 1: host copy current */
+MB200_API int mb200_cache_set_lazy(int on);                     /* returns the previous mode */
+/* uploads, upload bytes, downloads, download bytes, resident-input hits, bytes moved through the bounce ring */
+MB200_API void mb200_cache_stats(unsigned long long out[6]);
+MB200_API int mb200_copy_threads(void);
 
 /* ------------------------------------------------------- kernel builders ---- */
 

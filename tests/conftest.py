@@ -25,3 +25,10 @@ def _build_oracle_port():
         subprocess.run(["make", "-C", str(ROOT / "oracle"), "port"], check=True, env=env,
                        stdout=subprocess.DEVNULL)
     yield
+
+
+@pytest.fixture(autouse=True)
+def _restore_library_options():
+    yield
+    import util
+    util.reset_options()

@@ -125,7 +125,7 @@ def run_cuda(im, src, name, clamp_src):
     if name.startswith("unsharp_"):
         rs, gain, thr = name[8:].split("_")
         r, s = rs.split("x")
-        return host(im.UnsharpMaskImage(dev(src), float(r), float(s), float(gain), float(thr))), 2
+        return host(im.UnsharpMaskImage(dev(src), float(r), float(s), float(gain), float(thr))), 1
     if name.startswith("sharpen_"):
         r, s = name[8:].split("x")
         return host(im.SharpenImage(dev(src), float(r), float(s))), 1

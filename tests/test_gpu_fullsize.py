@@ -80,9 +80,9 @@ def test_config3_resize_16384_to_8192_lanczos(monkeypatch):
     got = out[:n, :n].cpu().numpy()
     assert max_ulp(got, want[:n, :n]) <= 1
     # (b) the streaming kernels against the independent gather kernels on the whole image
-    monkeypatch.setenv("MB200_NO_RESIZE_STREAM", "1")
+    util.set_option("no_resize_stream", 1)
     ref = im.ResizeImage(im.Image(src), W // 2, H // 2, im.LanczosFilter).pixels
-    monkeypatch.delenv("MB200_NO_RESIZE_STREAM")
+    util.set_option("no_resize_stream", 0)
     a = out.view(torch.int32).to(torch.int64)
     b = ref.view(torch.int32).to(torch.int64)
     a = torch.where(a < 0, -(a & 0x7FFFFFFF), a)

@@ -94,11 +94,11 @@ def test_gaussian_blur_2d_rank1_path(kind, sigma, monkeypatch):
         got = _host(im.GaussianBlurImage(_dev(src), 0.0, sigma))
         launches = im.launch_count() - n0
         assert max_ulp(got, want) <= 1, (w, h, kind, sigma)
-        monkeypatch.setenv("MB200_NO_RANK1", "1")
+        util.set_option("no_rank1", 1)
         n0 = im.launch_count()
         direct = _host(im.GaussianBlurImage(_dev(src), 0.0, sigma))
         assert im.launch_count() - n0 == 1
-        monkeypatch.delenv("MB200_NO_RANK1")
+        util.set_option("no_rank1", 0)
         assert max_ulp(direct, want) <= 1
         assert launches == 2          # the separable path was taken
 
@@ -159,10 +159,17 @@ def test_unsharp(ch):
     want = orc("orc_unsharp", src, 0.0, 2.0, 1.5, 0.02)
     got = _host(im.UnsharpMaskImage(_dev(src), 0.0, 2.0, 1.5, 0.02))
     d = util.ulp_distance(got, want)
-    # where the blur differs by 1 ULP the amplified difference may round differently; the
-    # pass-through branch must be exact
-    assert d.max() <= 2
-    assert (d == 0).mean() > 0.99
+    assert d.max() <= 1                      # <= 1 ULP ...
+    assert (d == 0).mean() > 0.9999
+    passthrough = want == src                # ... and the |2d| < QR*threshold branch returns the input itself: 0 ULP
+    assert passthrough.mean() > 0.005        # the branch is exercised
+    assert np.array_equal(got[passthrough], src[passthrough])
+    # the fused epilogue of the column pass and the separate point pass are the same arithmetic on the same
+    # float-rounded blur: identical bits
+    util.set_option("no_fused_unsharp", 1)
+    unfused = _host(im.UnsharpMaskImage(_dev(src), 0.0, 2.0, 1.5, 0.02))
+    util.set_option("no_fused_unsharp", 0)
+    assert np.array_equal(got, unfused)
 
 
 KERNELS = [("Disk:3", ("disk", 3, 1, 0, 0)), ("Disk:1.5", ("disk", 1.5, 1, 0, 0)), ("Square:2", ("square", 2, 1, 0, 0)),
@@ -210,7 +217,7 @@ def test_erode_dilate_streaming_kernel(ch, name, args, monkeypatch):
             assert max_ulp(got, want) == 0, (name, ch, method, w, h)
     src = make_image(131, 97, ch, seed=5)
     got = _host(im.MorphologyImage(_dev(src), im.DilateMorphology, 1, name))
-    monkeypatch.setenv("MB200_NO_MORPH_STREAM", "1")
+    util.set_option("no_morph_stream", 1)
     generic = _host(im.MorphologyImage(_dev(src), im.DilateMorphology, 1, name))
     assert max_ulp(got, generic) == 0
 
@@ -340,12 +347,12 @@ def test_resize_streaming_kernels(filt, ratio, kind, monkeypatch):
     got = _host(im.ResizeImage(d, ow, oh, filt))
     streamed = im.launch_count() - n0
     assert max_ulp(got, want) <= 1, (filt, ratio, kind)
-    monkeypatch.setenv("MB200_NO_RESIZE_STREAM", "1")
+    util.set_option("no_resize_stream", 1)
     ref = _host(im.ResizeImage(d, ow, oh, filt))
     assert streamed == 2                          # one launch per axis (borders ride along as extra CTAs)
     assert max_ulp(got, ref) <= 1
     # only one axis reduced: the other axis is a 1:1 pass through the gather kernel
-    monkeypatch.delenv("MB200_NO_RESIZE_STREAM")
+    util.set_option("no_resize_stream", 0)
     want = np.empty((h, ow, 4), np.float32)
     assert oracle().orc_resize(P(src), w, h, 4, P(want), ow, h, filt) == 0
     assert max_ulp(_host(im.ResizeImage(d, ow, h, filt)), want) <= 1

@@ -197,3 +197,22 @@ def orc_threshold(src: np.ndarray, op: int, thr) -> np.ndarray:
     arr = (_d * 4)(*([float(t) for t in thr] + [0.0] * (4 - len(thr))))
     assert oracle().orc_threshold(P(out), w, h, ch, op, arr) == 0
     return out
+
+
+# ---- run-time switches of the product library (mb200_set_option): restored after every test by conftest.py
+_touched_options = set()
+
+
+def set_option(name: str, value: int) -> None:
+    from imagemagick_b200 import _lib
+    _lib.check(_lib.load().mb200_set_option(name.encode(), int(value)))
+    _touched_options.add(name)
+
+
+def reset_options() -> None:
+    if not _touched_options:
+        return
+    from imagemagick_b200 import _lib
+    for name in list(_touched_options):
+        _lib.load().mb200_set_option(name.encode(), 0)
+    _touched_options.clear()
