@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_async_kernel(const Conv1d
 
 // Developer tuning knobs: environment variables read ONCE per process (defaults are the measured best).
 struct Tuning {
-  int pair, pair_async, pair_async_col, col_rot, row_pair_rot, row_rot, minb3;
+  int pair, pair_async, pair_async_col, col_rot, row_pair_rot, row_rot;
   Tuning() {
     auto get = [](const char *name, int fallback) {
       const char *v = getenv(name);
@@ -686,7 +686,9 @@ struct Tuning {
     col_rot = get("MB200_COL_ROT", 16);
     row_pair_rot = get("MB200_ROW_PAIR_ROT", 16);
     row_rot = get("MB200_ROW_ROT", 0);
-    minb3 = get("MB200_MINB3", 0);                         // experiment: 3 CTAs per SM (168 registers, small spills)
+    // (r02 experiment: 3 CTAs per SM for the NT = 33 cp.async kernels -- __launch_bounds__(128, 3), 168 registers, 48-160
+    //  bytes of spills -- measured 0.903 ms column / 1.215 ms row against 0.780 / 0.789 ms with 2 CTAs: the third warp per
+    //  scheduler does not pay for the spilled accumulators.  profiles/r02_minb3.log)
   }
 };
 const Tuning &tuning() {
@@ -708,7 +710,6 @@ void launch_pair(const Conv1dArgs &a, const Taps<NT> &taps, int axis, int io, bo
     else if (io == 1) conv_pair_kernel<NT, 2, 1, 1, NT == 33, PADDED><<<grid, 128, 0, stream>>>(a, taps);
     else if (fuse_unsharp && async) conv_pair_async_kernel<NT, 2, 1, 0, PADDED, 1><<<grid, 128, 0, stream>>>(a, taps);
     else if (fuse_unsharp) conv_pair_kernel<NT, 2, 1, 0, NT == 33, PADDED, 1><<<grid, 128, 0, stream>>>(a, taps);
-    else if (NT == 33 && !PADDED && t.minb3 == 1) conv_pair_async_kernel<NT, 3, 1, 0, false><<<grid, 128, 0, stream>>>(a, taps);
     else if (async) conv_pair_async_kernel<NT, 2, 1, 0, PADDED><<<grid, 128, 0, stream>>>(a, taps);
     else conv_pair_kernel<NT, 2, 1, 0, NT == 33, PADDED><<<grid, 128, 0, stream>>>(a, taps);
   } else {
@@ -717,7 +718,6 @@ void launch_pair(const Conv1dArgs &a, const Taps<NT> &taps, int axis, int io, bo
     if (io == 1 && async) conv_pair_async_kernel<NT, 2, 0, 1, PADDED><<<grid, 128, 0, stream>>>(a, taps);
     else if (io == 1) conv_pair_kernel<NT, 2, 0, 1, false, PADDED><<<grid, 128, 0, stream>>>(a, taps);
     else if (io == 2) conv_pair_kernel<NT, 2, 0, 2, false, PADDED><<<grid, 128, 0, stream>>>(a, taps);
-    else if (NT == 33 && !PADDED && t.minb3 == 1) conv_pair_async_kernel<NT, 3, 0, 0, false><<<grid, 128, 0, stream>>>(a, taps);
     else if (async) conv_pair_async_kernel<NT, 2, 0, 0, PADDED><<<grid, 128, 0, stream>>>(a, taps);
     else conv_pair_kernel<NT, 2, 0, 0, false, PADDED><<<grid, 128, 0, stream>>>(a, taps);
   }

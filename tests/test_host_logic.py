@@ -117,7 +117,7 @@ def test_bench_reference_arm_contract():
     import json
     import subprocess
     import sys
-    env = dict(**__import__("os").environ, OMP_NUM_THREADS="")
+    env = dict(**__import__("os").environ, OMP_NUM_THREADS="", MB200_BENCH_CPU_SIZE="1024")
     p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=600, env=env)
     assert p.returncode == 0, p.stderr[-500:]
@@ -128,7 +128,8 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["unit"] == "Mpixels/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in line["config"]
+    assert "workload" in line["config"] and "8192x8192" in line["config"]["workload"]
+    assert "1024x1024" in line["cpu_baseline"]["sample"]          # this test shrinks the sample; the driver runs 8192^2
 
 
 @pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
