@@ -405,12 +405,13 @@ def run_gpu(args):
     in_bytes, out_bytes = W * H * 16, job.out_columns * job.out_rows * 16
     affinity, affinity_spec = gpu_cpu_affinity(local)
 
-    def make_host_buffers():
-        src = [np.empty((H, W, 4), np.float32) for _ in range(2)]
-        for k, a in enumerate(src):                          # the step's inputs live in ordinary host memory
-            _lib.check(lib.mb200_download(vp(a), C.c_void_p(batch[k].pixels.data_ptr()), in_bytes, None))
+    E2E_THREADS = 2          # application threads calling the plugin path (each gets its own library stream)
+
+    def make_host_buffers(k):
+        src = np.empty((H, W, 4), np.float32)                 # the step's inputs live in ordinary host memory
+        _lib.check(lib.mb200_download(vp(src), C.c_void_p(batch[k].pixels.data_ptr()), in_bytes, None))
         _lib.check(lib.mb200_synchronize(None))
-        return src, np.empty((H, W, 4), np.float32), [np.empty((job.out_rows, job.out_columns, 4), np.float32) for _ in range(2)]
+        return src, np.empty((H, W, 4), np.float32), np.empty((job.out_rows, job.out_columns, 4), np.float32)
 
     def e2e_image(src, mid, out):
         _lib.check(lib.mb200_cache_host_written(vp(src)))                       # new pixels arrived in the host cache
@@ -418,49 +419,72 @@ def run_gpu(args):
         _lib.check(lib.mb200_resize_image(vp(mid), W, H, 4, vp(out), job.out_columns, job.out_rows, job.resize_filter))
         _lib.check(lib.mb200_cache_sync(vp(out)))                               # the caller reads the result
 
-    def e2e_run(images, attach):
-        src, mid, out = make_host_buffers()
+    def e2e_run(images, attach, nthreads):
+        """`images` images through the two host-buffer calls, split over `nthreads` application threads (ctypes releases
+        the GIL; every thread owns its source / intermediate / result buffers and gets its own library stream, so one
+        thread's upload overlaps the other's kernels and download).  Returns ms per image (wall clock)."""
+        sets = [make_host_buffers(k) for k in range(nthreads)]
+        flat = [a for st in sets for a in st]
         if attach:
-            for a in src + [mid] + out:
+            for a in flat:
                 _lib.check(lib.mb200_cache_attach(vp(a), a.nbytes, 1))
             lib.mb200_cache_set_lazy(1)
+        errors = []
+
+        def worker(k, n):
+            try:
+                _lib.check(lib.mb200_set_device(local))           # the current device is a per-thread setting
+                for _ in range(n):
+                    e2e_image(*sets[k])
+                _lib.check(lib.mb200_synchronize(None))
+            except Exception as exc:                              # surfaced after the join
+                errors.append(exc)
+
+        def run(n_each):
+            ts = [threading.Thread(target=worker, args=(k, n_each)) for k in range(nthreads)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            if errors:
+                raise errors[0]
+
         try:
-            e2e_image(src[0], mid, out[0])
-            e2e_image(src[1], mid, out[1])
+            run(2)                                                # warm-up: pins, pools, tables
             mdist.barrier()
             t0 = time.perf_counter()
-            for i in range(images):
-                e2e_image(src[i & 1], mid, out[i & 1])
-            _lib.check(lib.mb200_synchronize(None))
-            ms = (time.perf_counter() - t0) * 1e3 / images
-            ok = np.array_equal(out[0].reshape(-1)[:64], one_image(batch[0]).pixels.reshape(-1)[:64].cpu().numpy())
+            run(images // nthreads)
+            ms = (time.perf_counter() - t0) * 1e3 / (images // nthreads * nthreads)
+            ok = np.array_equal(sets[0][2].reshape(-1)[:64], one_image(batch[0]).pixels.reshape(-1)[:64].cpu().numpy())
         finally:
             if attach:
                 lib.mb200_cache_set_lazy(0)
-                for a in src + [mid] + out:
+                for a in flat:
                     lib.mb200_cache_detach(vp(a))
         assert ok, "e2e result differs from the device-resident one"
         return ms
 
     e2e_steps = max(1, min(args.steps, 2))
     e2e_images = IMAGES * e2e_steps
-    e2e_unbound = mdist.max_over_ranks(e2e_run(e2e_images, True), device=dev)
+    e2e_single = mdist.max_over_ranks(e2e_run(8, True, 1), device=dev)
+    e2e_unbound = mdist.max_over_ranks(e2e_run(e2e_images, True, E2E_THREADS), device=dev)
     e2e_bound = None
     if affinity:
         original_affinity = os.sched_getaffinity(0)
         try:                                                  # experiment: run on the cores of the GPU's NUMA node and
             os.sched_setaffinity(0, affinity)                 # first-touch / pin the host buffers there
-            e2e_bound = mdist.max_over_ranks(e2e_run(e2e_images, True), device=dev)
+            e2e_bound = mdist.max_over_ranks(e2e_run(e2e_images, True, E2E_THREADS), device=dev)
         except Exception:
             e2e_bound = None
         finally:
             os.sched_setaffinity(0, original_affinity)        # the CPU baseline below uses every core
     e2e_ms = min(e2e_unbound, e2e_bound) if e2e_bound else e2e_unbound
     e2e_value = world * W * H / e2e_ms / 1e3
-    e2e_modes = {"lazy_attached_ms_per_image": e2e_unbound, "lazy_attached_numa_bound_ms_per_image": e2e_bound,
-                 "numa_cpu_affinity": affinity_spec}
+    e2e_modes = {"application_threads": E2E_THREADS, "lazy_attached_ms_per_image": e2e_unbound,
+                 "lazy_attached_numa_bound_ms_per_image": e2e_bound, "numa_cpu_affinity": affinity_spec,
+                 "lazy_attached_single_thread_ms_per_image": e2e_single}
     # the same two calls on UNATTACHED pageable buffers: every operator stages in and out through the bounce ring
-    pageable_ms = e2e_run(4, False) if world == 1 else None
+    pageable_ms = e2e_run(4, False, 1) if world == 1 else None
     if rank == 0:
         e2e_modes["eager_pageable_ms_per_image"] = pageable_ms
         harness = ROOT / "imagemagick_b200" / "lib" / "chain_harness"
@@ -538,7 +562,8 @@ def run_gpu(args):
                    "config5": config5,
                    "e2e_path": "plugin path: mb200_convolve_image + mb200_resize_image on ordinary host buffers (numpy / malloc) "
                                "attached to the pixel-cache registry (cudaHostRegister once), lazy mode: per image one 1.07 GB "
-                               "upload, the blurred intermediate stays in HBM, one 0.27 GB download (mb200_cache_sync)",
+                               "upload, the blurred intermediate stays in HBM, one 0.27 GB download (mb200_cache_sync); "
+                               f"{E2E_THREADS} application threads, each on its own library stream",
                    "e2e_modes": e2e_modes, "copy_threads": int(lib.mb200_copy_threads())},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None,

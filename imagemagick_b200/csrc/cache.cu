@@ -143,6 +143,7 @@ struct Entry {
   bool host_valid = true;       // the host buffer holds the current pixels
   bool dev_valid = false;       // the HBM copy holds the current pixels
   bool registered = false;      // pinned by us with cudaHostRegister
+  cudaEvent_t ready = nullptr;  // last use of the HBM copy (any stream): the next user's stream waits for it
 };
 std::mutex g_cache_mutex;
 std::unordered_map<const void *, Entry *> g_entries;
@@ -170,7 +171,13 @@ int ensure_device_copy(Entry *e) {
   if (e->dev) return MB200_OK;
   cudaError_t err = cudaMalloc(&e->dev, e->bytes ? e->bytes : 1);
   if (err != cudaSuccess) { e->dev = nullptr; return cuda_fail(err, "pixel cache: cudaMalloc"); }
+  if (!e->ready) cudaEventCreateWithFlags(&e->ready, cudaEventDisableTiming);
   return MB200_OK;
+}
+
+// Calls come in on per-thread streams: order this stream behind the last use of the entry's HBM copy.
+void order_after_last_use(Entry *e, void *stream) {
+  if (e->ready) cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), e->ready, 0);
 }
 
 }  // namespace
@@ -254,6 +261,7 @@ int stage_input(const void *host, size_t bytes, void *stream, StageRef *out) {
     if (rc) return rc;
     out->entry = e;
     out->dev = e->dev;
+    order_after_last_use(e, stream);
     // The HBM copy may be used without a fresh upload when it is the only current copy, or when the caller vouches
     // for host writes (lazy / hook mode: every host access goes through mb200_cache_sync / _host_written).
     if (e->dev_valid && (!e->host_valid || g_lazy.load(std::memory_order_relaxed))) {
@@ -279,6 +287,7 @@ int stage_output(void *host, size_t bytes, void *stream, StageRef *out) {
     if (rc) return rc;
     out->entry = e;
     out->dev = e->dev;
+    order_after_last_use(e, stream);
     return MB200_OK;
   }
   cudaError_t err = cudaMallocAsync(&out->dev, bytes ? bytes : 1, temp_pool(), static_cast<cudaStream_t>(stream));
@@ -302,6 +311,8 @@ int finish_output(StageRef *ref, void *stream) {
 }
 
 void release_stage(StageRef *ref, void *stream) {
+  Entry *e = static_cast<Entry *>(ref->entry);
+  if (e && e->ready) cudaEventRecord(e->ready, static_cast<cudaStream_t>(stream));
   if (ref->temporary && ref->dev) cudaFreeAsync(ref->dev, static_cast<cudaStream_t>(stream));
   ref->dev = nullptr;
   ref->temporary = false;
@@ -336,6 +347,7 @@ int mb200_cache_attach(void *host_pixels, size_t bytes, int flags) {
     set_state(old, true, false);
     if (old->registered && !e->registered) cudaHostUnregister(old->host);
     if (old->dev) cudaFree(old->dev);
+    if (old->ready) cudaEventDestroy(old->ready);
     delete old;
   }
   return MB200_OK;
@@ -359,6 +371,7 @@ int mb200_cache_detach(void *host_pixels) {
     if (cur != e->device) cudaSetDevice(cur);
   }
   if (e->registered) cudaHostUnregister(e->host);
+  if (e->ready) cudaEventDestroy(e->ready);
   delete e;
   return MB200_OK;
 }
@@ -377,7 +390,10 @@ int mb200_cache_sync(void *host_pixels) {
   cudaGetDevice(&cur);
   if (cur != e->device) cudaSetDevice(e->device);
   int rc = ensure_device();
-  if (rc == MB200_OK) rc = copy_d2h(e->host, e->dev, e->bytes, default_stream());
+  if (rc == MB200_OK) {
+    order_after_last_use(e, default_stream());
+    rc = copy_d2h(e->host, e->dev, e->bytes, default_stream());
+  }
   if (cur != e->device) cudaSetDevice(cur);
   if (rc == MB200_OK) set_state(e, true, e->dev_valid);
   return rc;

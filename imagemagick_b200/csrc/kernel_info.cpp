@@ -10,8 +10,8 @@
 //
 // Taps are generated on the host in double with the host libm `exp`, i.e. with the
 // very same arithmetic the reference uses, so they are bit-identical to the
-// reference's KernelInfo (tests/test_kernel_info.py checks this against the
-// compiled reference).  Nothing here touches the GPU.
+// reference's KernelInfo (tests/test_host_logic.py::test_kernel_strings_match_reference_taps and
+// tests/test_golden.py check this against the compiled reference).  Nothing here touches the GPU.
 #include "mb200_internal.h"
 
 #include <cctype>
@@ -261,53 +261,48 @@ mb200_kernel_info *parse_named_kernel(const std::string &def, bool *was_named) {
   return mb200_acquire_kernel_builtin(type, g.rho, g.sigma, g.xi, g.psi);
 }
 
-// morphology.c:4258 RotateKernelInfo, restricted to what a single kernel needs:
-// +-90 transposes of 1-D kernels / 90-degree turns of squares, and 180 reflection.
+// RotateKernelInfo (morphology.c:4258) as what it amounts to for the angles the hot path uses: a rotation by q quarter
+// turns, written as ONE index permutation.  With i = column and j = row, a quarter turn maps
+//     new(i, j) = old(j, W_new - 1 - i),      origin (x, y) -> (W_new - 1 - y, x),      W_new = H_old,
+// which reproduces the reference's three separate mechanisms: the transpose of 1-D kernels (row -> column keeps the tap
+// order, column -> row reverses it), the cyclic four-way swap of square kernels and, for q = 2, the plain reversal.
+// Like the reference, cylindrical / symmetric built-ins are left alone, a Blur kernel only ever turns by +-90 (a half
+// turn of a symmetric 1-D kernel is the identity), a non-square 2-D kernel can only be reflected, and 45-degree steps
+// (3x3 only in the reference) are not produced by anything on this path.
 void rotate_kernel(mb200_kernel_info *k, double angle) {
   angle = std::fmod(angle, 360.0);
   if (angle < 0) angle += 360.0;
-  if (337.5 < angle || angle <= 22.5) return;
+  int q = angle > 45.0 && angle <= 135.0 ? 1 : angle > 135.0 && angle <= 225.0 ? 2 : angle > 225.0 && angle <= 315.0 ? 3 : 0;
   switch (k->type) {
     case MB200_GaussianKernel: case MB200_DoGKernel: case MB200_LoGKernel: case MB200_DiskKernel:
     case MB200_SquareKernel: case MB200_DiamondKernel: case MB200_PlusKernel: case MB200_CrossKernel:
       return;
     case MB200_BlurKernel:
-      if (135.0 < angle && angle <= 225.0) return;
-      if (225.0 < angle && angle <= 315.0) angle -= 180;
+      if (q == 2) return;
+      if (q == 3) q = 1;
       break;
     default: break;
   }
-  if (45.0 < std::fmod(angle, 180.0) && std::fmod(angle, 180.0) <= 135.0) {
-    if (k->width == 1 || k->height == 1) {
-      std::swap(k->width, k->height);
-      std::swap(k->x, k->y);
-      if (k->width == 1) { angle = std::fmod(angle + 270.0, 360.0); k->angle = std::fmod(k->angle + 90.0, 360.0); }
-      else { angle = std::fmod(angle + 90.0, 360.0); k->angle = std::fmod(k->angle + 270.0, 360.0); }
-    } else if (k->width == k->height) {
-      const long W = static_cast<long>(k->width), H = static_cast<long>(k->height);
-      double *v = k->values;
-      for (long i = 0, x = W - 1; i <= x; ++i, --x)
-        for (long j = 0, y = H - 1; j < y; ++j, --y) {
-          const double t = v[i + j * W];
-          v[i + j * W] = v[j + x * W];
-          v[j + x * W] = v[x + y * W];
-          v[x + y * W] = v[y + i * W];
-          v[y + i * W] = t;
-        }
-      const long x = k->x * 2 - W + 1, y = k->y * 2 - H + 1;
-      k->x = (-y + W - 1) / 2;
-      k->y = (+x + H - 1) / 2;
-      angle = std::fmod(angle + 270.0, 360.0);
-      k->angle = std::fmod(k->angle + 90.0, 360.0);
+  const long W = static_cast<long>(k->width), H = static_cast<long>(k->height);
+  if ((q & 1) && W != H && W != 1 && H != 1) return;        // the reference cannot turn such a kernel either
+  if (q == 0) return;
+  const std::vector<double> old(k->values, k->values + W * H);
+  const long Wn = (q & 1) ? H : W, Hn = (q & 1) ? W : H;
+  for (long j = 0; j < Hn; ++j)
+    for (long i = 0; i < Wn; ++i) {
+      long si, sj;                                           // source column / row of new(i, j)
+      if (q == 1) { si = j; sj = Wn - 1 - i; }
+      else if (q == 2) { si = W - 1 - i; sj = H - 1 - j; }
+      else { si = Hn - 1 - j; sj = i; }                      // three quarter turns == one backwards
+      k->values[i + j * Wn] = old[si + sj * W];
     }
-  }
-  if (135.0 < angle && angle <= 225.0) {
-    const size_t n = k->width * k->height;
-    for (size_t i = 0, j = n - 1; i < j; ++i, --j) std::swap(k->values[i], k->values[j]);
-    k->x = static_cast<long>(k->width) - k->x - 1;
-    k->y = static_cast<long>(k->height) - k->y - 1;
-    k->angle = std::fmod(k->angle + 180.0, 360.0);
-  }
+  const long x = k->x, y = k->y;
+  if (q == 1) { k->x = Wn - 1 - y; k->y = x; }
+  else if (q == 2) { k->x = W - 1 - x; k->y = H - 1 - y; }
+  else { k->x = y; k->y = Hn - 1 - x; }
+  k->width = static_cast<size_t>(Wn);
+  k->height = static_cast<size_t>(Hn);
+  k->angle = std::fmod(k->angle + 90.0 * q, 360.0);
 }
 
 }  // namespace

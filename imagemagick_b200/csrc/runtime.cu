@@ -93,9 +93,18 @@ static DeviceStateImpl *current() {
   return &g_dev[dev];
 }
 
+// The library stream of the CALLING THREAD on the current device: host-buffer calls made from different application
+// threads (MagickWand users, `-concurrent`) run on different streams and overlap -- one thread's upload with another's
+// kernels and download -- while the calls of one thread stay ordered.  (SURVEY 8b "Threading": re-entrant, per-call stream.)
 void *default_stream() {
-  DeviceStateImpl *d = current();
-  return d ? d->stream : nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  thread_local cudaStream_t streams[kMaxDevices] = {nullptr};
+  if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    return g_dev[dev].stream;            // the per-device stream created by ensure_device()
+  }
+  return streams[dev];
 }
 
 ::CUmemPoolHandle_st *temp_pool() {
@@ -114,7 +123,7 @@ int scratch(void **ptr, size_t bytes, int slot) {
   std::lock_guard<std::mutex> lock(g_mutex);
   if (d->scratch_bytes[slot] < bytes) {
     if (d->scratch[slot]) {
-      cudaStreamSynchronize(d->stream);
+      cudaDeviceSynchronize();
       cudaFree(d->scratch[slot]);
       d->scratch[slot] = nullptr;
       d->scratch_bytes[slot] = 0;
@@ -167,7 +176,7 @@ int mb200_device_count(void) {
 int mb200_trim(size_t keep_bytes) {
   int rc = ensure_device();
   if (rc) return rc;
-  cudaStreamSynchronize(static_cast<cudaStream_t>(default_stream()));
+  cudaDeviceSynchronize();
   cudaError_t e = cudaMemPoolTrimTo(temp_pool(), keep_bytes);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemPoolTrimTo");
   return MB200_OK;

@@ -240,3 +240,58 @@ def test_fp64_probe_reports_a_sane_rate():
     rate = C.c_double(0)
     _lib.check(_lib.load().mb200_probe_fp64_fma_rate(C.byref(rate)))
     assert 5e12 < rate.value < 4e13
+
+
+def test_host_buffer_calls_from_two_application_threads():
+    """Every application thread gets its own library stream (runtime.cu default_stream): concurrent callers overlap and
+    still produce the single-threaded bits; an attached buffer written by one thread and read by another is ordered by
+    the entry's event."""
+    import threading
+    from imagemagick_b200 import _lib
+    lib = _lib.load()
+    imgs = [make_image(700, 500, 4, seed=40 + k) for k in range(4)]
+    want = [_host(im.ResizeImage(im.BlurImage(_dev(a), 0.0, 2.0), 350, 250, im.LanczosFilter)) for a in imgs]
+    got = [None] * 4
+    errors = []
+    dev = torch.cuda.current_device()
+
+    def worker(k):
+        try:
+            _lib.check(lib.mb200_set_device(dev))
+            for _ in range(3):
+                b = im.BlurImage(im.Image(imgs[k]), 0.0, 2.0)
+                got[k] = im.ResizeImage(b, 350, 250, im.LanczosFilter).pixels
+        except Exception as exc:
+            errors.append(exc)
+
+    ts = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors
+    for k in range(4):
+        assert np.array_equal(got[k], want[k])
+    # producer / consumer across threads on an attached, lazily synchronised buffer
+    src, mid = imgs[0], np.empty_like(imgs[0])
+    out = np.empty((250, 350, 4), np.float32)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    for a in (src, mid, out):
+        _lib.check(lib.mb200_cache_attach(vp(a), a.nbytes, 0))
+    lib.mb200_cache_set_lazy(1)
+    try:
+        def producer():
+            lib.mb200_set_device(dev)
+            _lib.check(lib.mb200_blur_image(vp(src), vp(mid), 700, 500, 4, 0.0, 2.0))
+
+        def consumer():
+            lib.mb200_set_device(dev)
+            _lib.check(lib.mb200_resize_image(vp(mid), 700, 500, 4, vp(out), 350, 250, im.LanczosFilter))
+            _lib.check(lib.mb200_cache_sync(vp(out)))
+        for fn in (producer, consumer):
+            t = threading.Thread(target=fn)
+            t.start()
+            t.join()
+        assert np.array_equal(out, want[0])
+    finally:
+        lib.mb200_cache_set_lazy(0)
+        for a in (src, mid, out):
+            lib.mb200_cache_detach(vp(a))
