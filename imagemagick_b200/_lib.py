@@ -95,6 +95,17 @@ PROTOTYPES = {
     "mb200_transform_colorspace": (_i, [_vp, _sz, _sz, _i, _i, _i]),
     "mb200_sharpen_kernel": (KernelPtr, [_d, _d]),
     "mb200_edge_kernel": (KernelPtr, [_d]),
+    "mb200_statistic_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _i, _sz, _sz, _vp]),
+    "mb200_rotational_blur_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _d, _vp]),
+    "mb200_bilateral_blur_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _sz, _sz, _d, _d, _vp]),
+    "mb200_statistic_image": (_i, [_vp, _vp, _sz, _sz, _i, _i, _sz, _sz]),
+    "mb200_rotational_blur_image": (_i, [_vp, _vp, _sz, _sz, _i, _d]),
+    "mb200_bilateral_blur_image": (_i, [_vp, _vp, _sz, _sz, _i, _sz, _sz, _d, _d]),
+    "mb200_emboss_kernel": (KernelPtr, [_d, _d]),
+    "mb200_equalize_image_dev": (_i, [_vp, _sz, _sz, _i, _i, _vp]),
+    "mb200_emboss_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d, _vp]),
+    "mb200_equalize_image": (_i, [_vp, _sz, _sz, _i, _i]),
+    "mb200_emboss_image": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d]),
     "mb200_sharpen_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d, _vp]),
     "mb200_edge_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _d, _vp]),
     "mb200_sharpen_image": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d]),

@@ -5,7 +5,10 @@ Same names, argument meaning and error behaviour as the reference operators
 include/magick_b200.h:
 
     BlurImage, GaussianBlurImage, ConvolveImage, UnsharpMaskImage   effect.c:765/1709/1170/4256
-    SharpenImage, EdgeImage, MotionBlurImage                        effect.c:3991/1520/2347
+    SharpenImage, EdgeImage, EmbossImage, MotionBlurImage           effect.c:3991/1520/1600/2347
+    EqualizeImage                                                   enhance.c:2040
+    BilateralBlurImage, RotationalBlurImage                         effect.c:821/3129
+    StatisticImage                                                  statistic.c:2918
     MorphologyImage, AcquireKernelInfo                              morphology.c:4129/485
     ResizeImage, SampleImage, ThumbnailImage (pixel path)           resize.c:3761/3907/4591
     TransformImageColorspace                                        colorspace.c:1751
@@ -213,6 +216,38 @@ def SharpenImage(image: Image, radius: float, sigma: float) -> Image:
 def EdgeImage(image: Image, radius: float) -> Image:
     """MagickCore/effect.c:1520 -- ConvolveImage with the all -1 / centre n-1 kernel."""
     return _same_size_op(image, "mb200_edge_image_dev", "mb200_edge_image", float(radius))
+
+
+def EmbossImage(image: Image, radius: float, sigma: float) -> Image:
+    """MagickCore/effect.c:1600 -- ConvolveImage with the anti-diagonal emboss kernel, then EqualizeImage."""
+    return _same_size_op(image, "mb200_emboss_image_dev", "mb200_emboss_image", float(radius), float(sigma))
+
+
+def EqualizeImage(image: Image, sync_channels: bool = True) -> bool:
+    """MagickCore/enhance.c:2040 -- in place.  sync_channels: the channel mask carries SyncChannels (the default)."""
+    return _in_place(image, "mb200_equalize_image_dev", "mb200_equalize_image", int(bool(sync_channels)))
+
+
+# MagickCore/statistic.h:141-151
+(UndefinedStatistic, GradientStatistic, MaximumStatistic, MeanStatistic, MedianStatistic, MinimumStatistic, ModeStatistic,
+ NonpeakStatistic, RootMeanSquareStatistic, StandardDeviationStatistic, ContrastStatistic) = range(11)
+
+
+def StatisticImage(image: Image, statistic_type: int, width: int, height: int) -> Image:
+    """MagickCore/statistic.c:2918."""
+    return _same_size_op(image, "mb200_statistic_image_dev", "mb200_statistic_image", int(statistic_type), int(width),
+                         int(height))
+
+
+def RotationalBlurImage(image: Image, angle: float) -> Image:
+    """MagickCore/effect.c:3129."""
+    return _same_size_op(image, "mb200_rotational_blur_image_dev", "mb200_rotational_blur_image", float(angle))
+
+
+def BilateralBlurImage(image: Image, width: int, height: int, intensity_sigma: float, spatial_sigma: float) -> Image:
+    """MagickCore/effect.c:821."""
+    return _same_size_op(image, "mb200_bilateral_blur_image_dev", "mb200_bilateral_blur_image", int(width), int(height),
+                         float(intensity_sigma), float(spatial_sigma))
 
 
 def MotionBlurImage(image: Image, radius: float, sigma: float, angle: float) -> Image:

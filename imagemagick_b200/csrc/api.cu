@@ -831,6 +831,101 @@ int mb200_edge_image(const float *src, float *dst, size_t w, size_t h, int ch, d
 
 }  // extern "C"
 
+// ---- EqualizeImage (enhance.c:2040) and EmbossImage (effect.c:1600: inline kernel + ConvolveImage + EqualizeImage) -----------
+extern "C" {
+
+int mb200_equalize_image_dev(float *buf, size_t width, size_t height, int channels, int sync_channels, void *stream) {
+  if (!buf || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "equalize: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  return launch_equalize(buf, width * height, channels, sync_channels, s);
+}
+
+int mb200_emboss_image_dev(const float *src, float *dst, size_t width, size_t height, int channels, double radius,
+                           double sigma, void *stream) {
+  mb200_kernel_info *k = mb200_emboss_kernel(radius, sigma);
+  if (!k) return fail(MB200_ENOMEM, "emboss kernel");
+  int rc = mb200_convolve_image_dev(src, dst, width, height, channels, k, stream);
+  mb200_destroy_kernel_info(k);
+  if (rc) return rc;
+  return mb200_equalize_image_dev(dst, width, height, channels, 1, stream);      // effect.c:1679, default channel mask
+}
+
+int mb200_equalize_image(float *buf, size_t w, size_t h, int ch, int sync_channels) {
+  if (!buf || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "equalize: bad arguments");
+  return in_place_host(buf, w * h * ch * sizeof(float),
+                       [&](float *d, cudaStream_t st) { return mb200_equalize_image_dev(d, w, h, ch, sync_channels, st); });
+}
+
+int mb200_emboss_image(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma) {
+  if (!src || !dst || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "emboss: bad arguments");
+  const size_t bytes = w * h * ch * sizeof(float);
+  return with_staging(src, bytes, dst, bytes, [&](const float *s, float *d, cudaStream_t st) {
+    return mb200_emboss_image_dev(s, d, w, h, ch, radius, sigma, st);
+  });
+}
+
+}  // extern "C"
+
+// ---- StatisticImage (statistic.c:2918), RotationalBlurImage (effect.c:3129), BilateralBlurImage (effect.c:821) ----------
+extern "C" {
+
+int mb200_statistic_image_dev(const float *src, float *dst, size_t width, size_t height, int channels, int type,
+                              size_t window_width, size_t window_height, void *stream) {
+  if (!src || !dst || src == dst || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "statistic: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  return launch_statistic(src, dst, width, height, channels, type, window_width, window_height, s);
+}
+
+int mb200_rotational_blur_image_dev(const float *src, float *dst, size_t width, size_t height, int channels, double angle,
+                                    void *stream) {
+  if (!src || !dst || src == dst || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "rotational blur: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  return launch_rotational_blur(src, dst, width, height, channels, angle, s);
+}
+
+int mb200_bilateral_blur_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
+                                   size_t window_width, size_t window_height, double intensity_sigma, double spatial_sigma,
+                                   void *stream) {
+  if (!src || !dst || src == dst || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "bilateral blur: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  return launch_bilateral_blur(src, dst, width, height, channels, window_width, window_height, intensity_sigma, spatial_sigma, s);
+}
+
+int mb200_statistic_image(const float *src, float *dst, size_t w, size_t h, int ch, int type, size_t ww, size_t wh) {
+  if (!src || !dst || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "statistic: bad arguments");
+  const size_t bytes = w * h * ch * sizeof(float);
+  return with_staging(src, bytes, dst, bytes, [&](const float *s, float *d, cudaStream_t st) {
+    return mb200_statistic_image_dev(s, d, w, h, ch, type, ww, wh, st);
+  });
+}
+
+int mb200_rotational_blur_image(const float *src, float *dst, size_t w, size_t h, int ch, double angle) {
+  if (!src || !dst || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "rotational blur: bad arguments");
+  const size_t bytes = w * h * ch * sizeof(float);
+  return with_staging(src, bytes, dst, bytes, [&](const float *s, float *d, cudaStream_t st) {
+    return mb200_rotational_blur_image_dev(s, d, w, h, ch, angle, st);
+  });
+}
+
+int mb200_bilateral_blur_image(const float *src, float *dst, size_t w, size_t h, int ch, size_t ww, size_t wh,
+                               double intensity_sigma, double spatial_sigma) {
+  if (!src || !dst || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "bilateral blur: bad arguments");
+  const size_t bytes = w * h * ch * sizeof(float);
+  return with_staging(src, bytes, dst, bytes, [&](const float *s, float *d, cudaStream_t st) {
+    return mb200_bilateral_blur_image_dev(s, d, w, h, ch, ww, wh, intensity_sigma, spatial_sigma, st);
+  });
+}
+
+}  // extern "C"
+
 // ---- SampleImage (resize.c:3907) --------------------------------------------------------------------------------
 extern "C" {
 

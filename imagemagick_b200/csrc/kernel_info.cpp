@@ -621,6 +621,34 @@ mb200_kernel_info *mb200_sharpen_kernel(double radius, double sigma) {
   return k;
 }
 
+// EmbossImage (effect.c:1632-1665): width = GetOptimalKernelWidth1D(radius, sigma); only the anti-diagonal is non-zero:
+// +-8 * exp(-(u*u+v*v)/(2 s^2))/(2 pi s^2), negative where u < 0 or v < 0; normalised to sum 1 (PerceptibleReciprocal).
+mb200_kernel_info *mb200_emboss_kernel(double radius, double sigma) {
+  const size_t width = mb200_optimal_kernel_width_1d(radius, sigma);
+  mb200_kernel_info *k = new_kernel(MB200_UserDefinedKernel, width, width);
+  if (!k) return nullptr;
+  centre_origin(k);
+  const double s = std::fabs(sigma) < kEps ? kEps : sigma;            // MagickSigma
+  const long j = static_cast<long>(width - 1) / 2;
+  long diag = j;
+  size_t i = 0;
+  for (long v = -j; v <= j; ++v) {
+    for (long u = -j; u <= j; ++u) {
+      k->values[i] = ((u < 0 || v < 0) ? -8.0 : 8.0) *
+                     std::exp(-(static_cast<double>(u) * static_cast<double>(u) + static_cast<double>(v * v)) / (2.0 * s * s)) /
+                     (2.0 * kPi * s * s);
+      if (u != diag) k->values[i] = 0.0;
+      ++i;
+    }
+    --diag;
+  }
+  double normalize = 0.0;
+  for (i = 0; i < width * width; ++i) normalize += k->values[i];
+  const double gamma = perceptible_reciprocal(normalize);
+  for (i = 0; i < width * width; ++i) k->values[i] *= gamma;
+  return k;
+}
+
 // EdgeImage: width = GetOptimalKernelWidth1D(radius, 0.5); all cells -1, centre = width*height - 1.
 mb200_kernel_info *mb200_edge_kernel(double radius) {
   const size_t width = mb200_optimal_kernel_width_1d(radius, 0.5);

@@ -105,8 +105,19 @@ int launch_composite_difference(float *canvas, const float *source, size_t npixe
 int launch_motion_blur(const float *src, float *dst, size_t w, size_t h, int channels, const double *taps, const long *ox,
                        const long *oy, int width, void *stream);
 
+// stencils.cu: StatisticImage (statistic.c:2918), RotationalBlurImage (effect.c:3129), BilateralBlurImage (effect.c:821)
+int launch_statistic(const float *src, float *dst, size_t w, size_t h, int channels, int type, size_t width, size_t height,
+                     void *stream);
+int launch_rotational_blur(const float *src, float *dst, size_t w, size_t h, int channels, double angle, void *stream);
+int launch_bilateral_blur(const float *src, float *dst, size_t w, size_t h, int channels, size_t width, size_t height,
+                          double intensity_sigma, double spatial_sigma, void *stream);
+
 // SampleImage (resize.c:3907): nearest-sample gather, bit exact
 int launch_sample(const float *src, size_t w, size_t h, int channels, float *dst, size_t ow, size_t oh, void *stream);
+
+// equalize.cu: EqualizeImage (enhance.c:2040) in place; sync_channels = the channel mask carries SyncChannels (the
+// default): one intensity-driven histogram for all channels.  Synchronises the stream (host step between the kernels).
+int launch_equalize(float *buf, size_t npixels, int channels, int sync_channels, void *stream);
 
 // threshold.c point operators in place; op: 0 bilevel (t[0]), 1 black, 2 white (t = r,g,b,a), 3 clamp
 int launch_threshold(float *buf, size_t npixels, int channels, int op, const double *thresholds, void *stream);

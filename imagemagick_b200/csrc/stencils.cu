@@ -1,0 +1,392 @@
+// stencils.cu -- the neighbourhood operators next to the convolution path:
+//   StatisticImage       MagickCore/statistic.c:2918-3160   (Gradient, Maximum, Mean, Median, Minimum, RootMeanSquare,
+//                                                             StandardDeviation, Contrast)
+//   RotationalBlurImage  MagickCore/effect.c:3129-3400
+//   BilateralBlurImage   MagickCore/effect.c:821-1165
+// One thread per output pixel, all channels of the pixel in one pass over the window (the per-channel accumulation
+// order of the reference -- window order, sequential double adds -- is kept, and every operation is an UNFUSED IEEE double
+// operation, so the results are bit-identical to the reference's).  Neighbours are fetched through the read-only path
+// (float4 for RGBA); the windows of adjacent threads overlap almost completely, so L1 / L2 serve the re-reads.  These
+// are first, untuned versions (correctness first; DESIGN.md lists their measured throughput).
+#include "mb200_internal.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <vector>
+
+namespace mb200 {
+namespace {
+
+constexpr double kQS = 1.0 / 65535.0, kEps = 1.0e-12;
+
+template <int CH>
+__device__ __forceinline__ void load_pixel(const float *__restrict__ src, size_t index, float (&v)[CH]) {
+  const float *r = src + index * CH;
+  if (CH == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4 *>(r));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[CH - 1] = t.w;
+  } else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) v[c] = __ldg(r + c);
+  }
+}
+
+template <int CH>
+__device__ __forceinline__ void store_pixel(float *__restrict__ dst, size_t index, const float (&o)[CH]) {
+  float *q = dst + index * CH;
+  if (CH == 4) *reinterpret_cast<float4 *>(q) = make_float4(o[0], o[1], o[2], o[CH - 1]);
+  else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) q[c] = o[c];
+  }
+}
+
+// PerceptibleReciprocal (pixel-accessor.h:242-254) with IEEE division
+__device__ __forceinline__ double perceptible_reciprocal(double x) {
+  const double sign = x < 0.0 ? -1.0 : 1.0;
+  return __dmul_rn(sign, x) >= kEps ? __ddiv_rn(1.0, x) : __ddiv_rn(sign, kEps);
+}
+
+// GetPixelIntensity, Rec709Luma on an sRGB / gray image (pixel.c:2356): see threshold_kernel (pointwise.cu)
+template <int CH>
+__device__ __forceinline__ double pixel_intensity(const float (&v)[CH]) {
+  const double red = static_cast<double>(v[0]);
+  if (CH == 1) return red;
+  const double green = CH >= 3 ? static_cast<double>(v[CH >= 3 ? 1 : 0]) : red;
+  const double blue = CH >= 3 ? static_cast<double>(v[CH >= 3 ? 2 : 0]) : red;
+  return __dadd_rn(__dadd_rn(__dmul_rn(0.212656, red), __dmul_rn(0.715158, green)), __dmul_rn(0.072186, blue));
+}
+
+// ------------------------------------------------------------------------------------------------ StatisticImage
+__device__ __forceinline__ unsigned scale_quantum_to_short(float q) {      // quantum-private.h (HDRI)
+  if (!(q > 0.0f)) return 0u;
+  if (q >= 65535.0f) return 65535u;
+  return static_cast<unsigned>(q + 0.5f);
+}
+
+// type: statistic.h:141-151 (1 Gradient, 2 Maximum, 3 Mean, 4 Median, 5 Minimum, 8 RootMeanSquare, 9 StandardDeviation,
+// 10 Contrast).  The window's top-left corner is (x - W/2, y - H/2), edge replicated (:3012-3020).
+template <int CH>
+__global__ void __launch_bounds__(128) statistic_kernel(const float *__restrict__ src, float *__restrict__ dst, int w, int h,
+                                                        int type, int W, int H) {
+  const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const int x0 = x - W / 2, y0 = y - H / 2;
+  float o[CH];
+  if (type == 4) {
+    // Median: the reference inserts ScaleQuantumToShort(value) into a skip list and returns the element at sorted index
+    // length/2 (:2784, :2878) -- a 16-bit radix select over the window gives the same element without storing it.
+    const unsigned n = static_cast<unsigned>(W) * static_cast<unsigned>(H);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      unsigned prefix = 0, k = n >> 1;
+      for (int bit = 15; bit >= 0; --bit) {
+        const unsigned himask = bit == 15 ? 0u : (0xffffu << (bit + 1)) & 0xffffu;
+        unsigned zeros = 0;
+        for (int v = 0; v < H; ++v) {
+          const size_t row = static_cast<size_t>(min(max(y0 + v, 0), h - 1)) * w;
+          for (int u = 0; u < W; ++u) {
+            const unsigned s = scale_quantum_to_short(__ldg(src + (row + min(max(x0 + u, 0), w - 1)) * CH + c));
+            zeros += ((s & himask) == prefix && !(s >> bit & 1u)) ? 1u : 0u;
+          }
+        }
+        if (k >= zeros) { k -= zeros; prefix |= 1u << bit; }
+      }
+      o[c] = static_cast<float>(static_cast<double>(prefix));
+    }
+    store_pixel<CH>(dst, static_cast<size_t>(y) * w + x, o);
+    return;
+  }
+  double minimum[CH], maximum[CH], sum[CH], sum_squared[CH];
+  double area = 0.0;
+  bool first = true;
+  for (int v = 0; v < H; ++v) {
+    const size_t row = static_cast<size_t>(min(max(y0 + v, 0), h - 1)) * w;
+    for (int u = 0; u < W; ++u) {
+      float p[CH];
+      load_pixel<CH>(src, row + min(max(x0 + u, 0), w - 1), p);
+      area = __dadd_rn(area, 1.0);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const double value = static_cast<double>(p[c]);
+        if (first) { minimum[c] = value; maximum[c] = value; sum[c] = 0.0; sum_squared[c] = 0.0; }
+        if (value < minimum[c]) minimum[c] = value;
+        if (value > maximum[c]) maximum[c] = value;
+        sum[c] = __dadd_rn(sum[c], value);
+        sum_squared[c] = __dadd_rn(sum_squared[c], __dmul_rn(value, value));
+      }
+      first = false;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    double pixel;
+    switch (type) {
+      case 1: pixel = fabs(__dsub_rn(maximum[c], minimum[c])); break;
+      case 2: pixel = maximum[c]; break;
+      case 5: pixel = minimum[c]; break;
+      case 8: pixel = __dsqrt_rn(__ddiv_rn(sum_squared[c], area)); break;
+      case 9: {                                              // sqrt(ss/area - (sum/area*sum/area)), left to right
+        const double m = __ddiv_rn(__dmul_rn(__ddiv_rn(sum[c], area), sum[c]), area);
+        pixel = __dsqrt_rn(__dsub_rn(__ddiv_rn(sum_squared[c], area), m));
+        break;
+      }
+      case 10: pixel = fabs(__dmul_rn(__dsub_rn(maximum[c], minimum[c]), perceptible_reciprocal(__dadd_rn(maximum[c], minimum[c])))); break;
+      default: pixel = __ddiv_rn(sum[c], area); break;
+    }
+    o[c] = static_cast<float>(pixel);
+  }
+  store_pixel<CH>(dst, static_cast<size_t>(y) * w + x, o);
+}
+
+// ------------------------------------------------------------------------------------------- RotationalBlurImage
+// n samples on the arc through the pixel about the image centre; cos / sin tables from the host (libm, like the
+// reference); every `step`-th sample, step = blur_radius / radius clamped to [1, n-1] (:3246-3262).
+template <int CH>
+__global__ void __launch_bounds__(128) rotational_blur_kernel(const float *__restrict__ src, float *__restrict__ dst, int w,
+                                                              int h, const double *__restrict__ cos_theta,
+                                                              const double *__restrict__ sin_theta, int n, double cx, double cy,
+                                                              double blur_radius) {
+  const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  constexpr bool kAlpha = (CH == 2 || CH == 4);
+  const double dx = __dsub_rn(static_cast<double>(x), cx), dy = __dsub_rn(static_cast<double>(y), cy);
+  // hypot(dx, dy): dx, dy are multiples of 0.5 of moderate size, dx*dx + dy*dy is exact, so the correctly rounded square
+  // root IS the correctly rounded hypot glibc returns
+  const double radius = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+  int step = 1;
+  if (radius != 0.0) {
+    const double ratio = __ddiv_rn(blur_radius, radius);
+    step = ratio >= static_cast<double>(n) ? n - 1 : static_cast<int>(ratio);
+    if (step == 0) step = 1;
+    else if (step >= n) step = n - 1;
+  }
+  double pixel[CH], gamma = 0.0, count = 0.0;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) pixel[c] = 0.0;
+  for (int j = 0; j < n; j += step) {
+    const double ct = __ldg(cos_theta + j), st = __ldg(sin_theta + j);
+    // (ssize_t) (cx + dx*cos - dy*sin + 0.5): truncation toward zero, then edge replication
+    const double fx = __dadd_rn(__dsub_rn(__dadd_rn(cx, __dmul_rn(dx, ct)), __dmul_rn(dy, st)), 0.5);
+    const double fy = __dadd_rn(__dadd_rn(__dadd_rn(cy, __dmul_rn(dx, st)), __dmul_rn(dy, ct)), 0.5);
+    const int xx = min(max(static_cast<int>(fx), 0), w - 1), yy = min(max(static_cast<int>(fy), 0), h - 1);
+    float r[CH];
+    load_pixel<CH>(src, static_cast<size_t>(yy) * w + xx, r);
+    count = __dadd_rn(count, 1.0);
+    if (kAlpha) {
+      const double alpha = __dmul_rn(kQS, static_cast<double>(r[CH - 1]));
+#pragma unroll
+      for (int c = 0; c < CH - 1; ++c) pixel[c] = __dadd_rn(pixel[c], __dmul_rn(alpha, static_cast<double>(r[c])));
+      gamma = __dadd_rn(gamma, alpha);
+      pixel[CH - 1] = __dadd_rn(pixel[CH - 1], static_cast<double>(r[CH - 1]));
+    } else {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) pixel[c] = __dadd_rn(pixel[c], static_cast<double>(r[c]));
+    }
+  }
+  float o[CH];
+  const double plain = perceptible_reciprocal(count);
+  if (kAlpha) {
+    const double g = perceptible_reciprocal(gamma);
+#pragma unroll
+    for (int c = 0; c < CH - 1; ++c) o[c] = static_cast<float>(__dmul_rn(g, pixel[c]));
+    o[CH - 1] = static_cast<float>(__dmul_rn(plain, pixel[CH - 1]));
+  } else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) o[c] = static_cast<float>(__dmul_rn(plain, pixel[c]));
+  }
+  store_pixel<CH>(dst, static_cast<size_t>(y) * w + x, o);
+}
+
+// -------------------------------------------------------------------------------------------- BilateralBlurImage
+// 8-bit intensity plane (ScaleQuantumToChar of the float-converted intensity, :1017-1030): one pre-pass instead of an
+// intensity evaluation per tap.
+__device__ __forceinline__ unsigned scale_quantum_to_char(float q) {       // quantum.h:113-124 (HDRI)
+  if (!(q > 0.0f)) return 0u;
+  const float s = q / 257.0f;
+  if (s >= 255.0f) return 255u;
+  return static_cast<unsigned>(s + 0.5f);
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) intensity8_kernel(const float *__restrict__ src, unsigned char *__restrict__ out, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  float v[CH];
+  load_pixel<CH>(src, i, v);
+  out[i] = static_cast<unsigned char>(scale_quantum_to_char(static_cast<float>(pixel_intensity<CH>(v))));
+}
+
+// weight(k) = intensity_gaussian[I(r_k) - I(p) + 255] * spatial_gaussian[k]; r_k = (x + mid_x - u, y + mid_y - v), the
+// reference's reflected window index (:1060-1070); colour channels of images with alpha normalise by
+// sum w * (QS*alpha(p)) * (QS*alpha(r)) while accumulating w * r unweighted (:1108-1125), as written there.
+template <int CH>
+__global__ void __launch_bounds__(128) bilateral_kernel(const float *__restrict__ src, const unsigned char *__restrict__ i8,
+                                                        float *__restrict__ dst, int w, int h, int W, int H,
+                                                        const double *__restrict__ intensity_gaussian,
+                                                        const double *__restrict__ spatial_gaussian) {
+  const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  constexpr bool kAlpha = (CH == 2 || CH == 4);
+  const int midx = W / 2, midy = H / 2;
+  const size_t centre = static_cast<size_t>(y) * w + x;
+  const int ip = i8[centre];
+  double palpha = 1.0;
+  if (kAlpha) palpha = __dmul_rn(kQS, static_cast<double>(__ldg(src + centre * CH + CH - 1)));
+  double pixel[CH], gamma_plain = 0.0, gamma_blend = 0.0;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) pixel[c] = 0.0;
+  int k = 0;
+  for (int v = 0; v < H; ++v) {
+    const size_t row = static_cast<size_t>(min(max(y + midy - v, 0), h - 1)) * w;
+    for (int u = 0; u < W; ++u, ++k) {
+      const size_t idx = row + min(max(x + midx - u, 0), w - 1);
+      const int d = static_cast<int>(__ldg(i8 + idx)) - ip;
+      const double wt = __dmul_rn(__ldg(intensity_gaussian + d + 255), __ldg(spatial_gaussian + k));
+      float r[CH];
+      load_pixel<CH>(src, idx, r);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) pixel[c] = __dadd_rn(pixel[c], __dmul_rn(wt, static_cast<double>(r[c])));
+      gamma_plain = __dadd_rn(gamma_plain, wt);
+      if (kAlpha)
+        gamma_blend = __dadd_rn(gamma_blend, __dmul_rn(__dmul_rn(wt, palpha), __dmul_rn(kQS, static_cast<double>(r[CH - 1]))));
+    }
+  }
+  float o[CH];
+  const double gp = perceptible_reciprocal(gamma_plain);
+  const double gb = kAlpha ? perceptible_reciprocal(gamma_blend) : gp;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) o[c] = static_cast<float>(__dmul_rn((kAlpha && c != CH - 1) ? gb : gp, pixel[c]));
+  store_pixel<CH>(dst, centre, o);
+}
+
+int check_image(const float *src, float *dst, size_t w, size_t h, int channels, const char *what) {
+  if (!src || !dst || w == 0 || h == 0 || w > 0x3fffffffull || h > 65535ull * 32768ull) return fail(MB200_EINVAL, "%s: bad geometry", what);
+  if (h > 65535) return fail(MB200_EUNSUPPORTED, "%s: more than 65535 rows", what);
+  if (channels < 1 || channels > 4) return fail(MB200_EINVAL, "%s: 1..4 channels", what);
+  if (channels == 4 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) != 0)
+    return fail(MB200_EINVAL, "%s: RGBA buffers must be 16-byte aligned", what);
+  return MB200_OK;
+}
+
+int upload_table(const std::vector<double> &host, double **dev, cudaStream_t s) {
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(dev), host.size() * sizeof(double), temp_pool(), s);
+  if (e != cudaSuccess) { *dev = nullptr; return cuda_fail(e, "table allocation"); }
+  // pageable source: the runtime stages it before returning, so `host` may die right after the call
+  e = cudaMemcpyAsync(*dev, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) { cudaFreeAsync(*dev, s); *dev = nullptr; return cuda_fail(e, "table upload"); }
+  return MB200_OK;
+}
+
+}  // namespace
+
+int launch_statistic(const float *src, float *dst, size_t w, size_t h, int channels, int type, size_t width, size_t height,
+                     void *stream) {
+  int rc = check_image(src, dst, w, h, channels, "statistic");
+  if (rc) return rc;
+  if (type < 1 || type > 10 || type == 6 || type == 7)
+    return fail(MB200_EUNSUPPORTED, "statistic type %d (Mode / Nonpeak walk the reference's skip list) stays on the CPU path", type);
+  const size_t W = width > 1 ? width : 1, H = height > 1 ? height : 1;
+  if (W > 255 || H > 255) return fail(MB200_EUNSUPPORTED, "statistic: window larger than 255");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 grid(static_cast<unsigned>((w + 127) / 128), static_cast<unsigned>(h));
+  const int iw = static_cast<int>(w), ih = static_cast<int>(h), iW = static_cast<int>(W), iH = static_cast<int>(H);
+  switch (channels) {
+    case 1: statistic_kernel<1><<<grid, 128, 0, s>>>(src, dst, iw, ih, type, iW, iH); break;
+    case 2: statistic_kernel<2><<<grid, 128, 0, s>>>(src, dst, iw, ih, type, iW, iH); break;
+    case 3: statistic_kernel<3><<<grid, 128, 0, s>>>(src, dst, iw, ih, type, iW, iH); break;
+    default: statistic_kernel<4><<<grid, 128, 0, s>>>(src, dst, iw, ih, type, iW, iH); break;
+  }
+  count_launch();
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MB200_OK : cuda_fail(e, "statistic launch");
+}
+
+int launch_rotational_blur(const float *src, float *dst, size_t w, size_t h, int channels, double angle, void *stream) {
+  int rc = check_image(src, dst, w, h, channels, "rotational blur");
+  if (rc) return rc;
+  // effect.c:3177-3203: centre, blur radius, sample count and the cos / sin tables
+  const double kPi = 3.14159265358979323846264338327950288419716939937510;
+  const double cx = static_cast<double>(w - 1) / 2.0, cy = static_cast<double>(h - 1) / 2.0;
+  const double blur_radius = std::hypot(cx, cy);
+  const double rad = kPi * angle / 180.0;
+  const size_t n = static_cast<size_t>(std::fabs(4.0 * rad * std::sqrt(blur_radius) + 2UL));
+  if (n < 2 || n > (1u << 20)) return fail(MB200_EUNSUPPORTED, "rotational blur: %zu samples per pixel", n);
+  const double theta = rad / static_cast<double>(n - 1), offset = theta * static_cast<double>(n - 1) / 2.0;
+  std::vector<double> tables(2 * n);
+  for (size_t k = 0; k < n; ++k) {
+    tables[k] = std::cos(theta * static_cast<double>(static_cast<long>(k)) - offset);
+    tables[n + k] = std::sin(theta * static_cast<double>(static_cast<long>(k)) - offset);
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  double *d_tables = nullptr;
+  rc = upload_table(tables, &d_tables, s);
+  if (rc) return rc;
+  dim3 grid(static_cast<unsigned>((w + 127) / 128), static_cast<unsigned>(h));
+  const int iw = static_cast<int>(w), ih = static_cast<int>(h), in = static_cast<int>(n);
+  switch (channels) {
+    case 1: rotational_blur_kernel<1><<<grid, 128, 0, s>>>(src, dst, iw, ih, d_tables, d_tables + n, in, cx, cy, blur_radius); break;
+    case 2: rotational_blur_kernel<2><<<grid, 128, 0, s>>>(src, dst, iw, ih, d_tables, d_tables + n, in, cx, cy, blur_radius); break;
+    case 3: rotational_blur_kernel<3><<<grid, 128, 0, s>>>(src, dst, iw, ih, d_tables, d_tables + n, in, cx, cy, blur_radius); break;
+    default: rotational_blur_kernel<4><<<grid, 128, 0, s>>>(src, dst, iw, ih, d_tables, d_tables + n, in, cx, cy, blur_radius); break;
+  }
+  count_launch();
+  const cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(d_tables, s);
+  return e == cudaSuccess ? MB200_OK : cuda_fail(e, "rotational blur launch");
+}
+
+int launch_bilateral_blur(const float *src, float *dst, size_t w, size_t h, int channels, size_t width, size_t height,
+                          double intensity_sigma, double spatial_sigma, void *stream) {
+  int rc = check_image(src, dst, w, h, channels, "bilateral blur");
+  if (rc) return rc;
+  const size_t W = width > 1 ? width : 1, H = height > 1 ? height : 1;
+  if ((W % 2) == 0 || (H % 2) == 0)
+    return fail(MB200_EUNSUPPORTED, "bilateral blur: even window sizes (the reference's reflected index leaves the window it fetched)");
+  if (W > 255 || H > 255) return fail(MB200_EUNSUPPORTED, "bilateral blur: window larger than 255");
+  // BlurGaussian (effect.c:808-819) tables: 511 intensity differences, W*H distances from the window centre
+  auto reciprocal = [](double x) { const double sign = x < 0.0 ? -1.0 : 1.0; return sign * x >= kEps ? 1.0 / x : sign / kEps; };
+  const double k2Pi = 6.28318530717958647692528676655900576839433879875020;
+  auto blur_gaussian = [&](double x, double sigma) {
+    return std::exp(-(x * x) * reciprocal(2.0 * sigma * sigma)) * reciprocal(k2Pi * sigma * sigma);
+  };
+  std::vector<double> tables(512 + W * H);
+  for (int v = -255; v <= 255; ++v) tables[v + 255] = blur_gaussian(static_cast<double>(v), intensity_sigma);
+  tables[511] = 0.0;
+  size_t n = 512;
+  const long midx = static_cast<long>(W) / 2, midy = static_cast<long>(H) / 2;
+  for (long v = 0; v < static_cast<long>(H); ++v)
+    for (long u = 0; u < static_cast<long>(W); ++u) {
+      const double dx = 0.0 - static_cast<double>(u - midx), dy = 0.0 - static_cast<double>(v - midy);
+      tables[n++] = blur_gaussian(std::sqrt(dx * dx + dy * dy), spatial_sigma);
+    }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  double *d_tables = nullptr;
+  unsigned char *d_i8 = nullptr;
+  rc = upload_table(tables, &d_tables, s);
+  if (rc) return rc;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&d_i8), w * h, temp_pool(), s);
+  if (e != cudaSuccess) { cudaFreeAsync(d_tables, s); return cuda_fail(e, "bilateral blur: intensity plane"); }
+  const size_t npix = w * h;
+  const unsigned pgrid = static_cast<unsigned>((npix + 255) / 256);
+  dim3 grid(static_cast<unsigned>((w + 127) / 128), static_cast<unsigned>(h));
+  const int iw = static_cast<int>(w), ih = static_cast<int>(h), iW = static_cast<int>(W), iH = static_cast<int>(H);
+  switch (channels) {
+    case 1: intensity8_kernel<1><<<pgrid, 256, 0, s>>>(src, d_i8, npix);
+            bilateral_kernel<1><<<grid, 128, 0, s>>>(src, d_i8, dst, iw, ih, iW, iH, d_tables, d_tables + 512); break;
+    case 2: intensity8_kernel<2><<<pgrid, 256, 0, s>>>(src, d_i8, npix);
+            bilateral_kernel<2><<<grid, 128, 0, s>>>(src, d_i8, dst, iw, ih, iW, iH, d_tables, d_tables + 512); break;
+    case 3: intensity8_kernel<3><<<pgrid, 256, 0, s>>>(src, d_i8, npix);
+            bilateral_kernel<3><<<grid, 128, 0, s>>>(src, d_i8, dst, iw, ih, iW, iH, d_tables, d_tables + 512); break;
+    default: intensity8_kernel<4><<<pgrid, 256, 0, s>>>(src, d_i8, npix);
+             bilateral_kernel<4><<<grid, 128, 0, s>>>(src, d_i8, dst, iw, ih, iW, iH, d_tables, d_tables + 512); break;
+  }
+  count_launch(2);
+  e = cudaGetLastError();
+  cudaFreeAsync(d_i8, s);
+  cudaFreeAsync(d_tables, s);
+  return e == cudaSuccess ? MB200_OK : cuda_fail(e, "bilateral blur launch");
+}
+
+}  // namespace mb200

@@ -6,7 +6,8 @@
       -Wl,--wrap=BlurImage,--wrap=GaussianBlurImage,--wrap=ConvolveImage,--wrap=UnsharpMaskImage,\
           --wrap=MorphologyImage,--wrap=ResizeImage,--wrap=TransformImageColorspace,\
           --wrap=BilevelImage,--wrap=BlackThresholdImage,--wrap=WhiteThresholdImage,--wrap=ClampImage,\
-          --wrap=SharpenImage,--wrap=EdgeImage,--wrap=SampleImage,--wrap=ThumbnailImage,--wrap=MinifyImage,--wrap=ResampleImage,--wrap=MotionBlurImage
+          --wrap=SharpenImage,--wrap=EdgeImage,--wrap=SampleImage,--wrap=ThumbnailImage,--wrap=MinifyImage,--wrap=ResampleImage,--wrap=MotionBlurImage,\
+          --wrap=EmbossImage,--wrap=EqualizeImage
   and every caller of those exported functions (effect.c:765/1709/1170/4256, morphology.c:4129,
   resize.c:3761, colorspace.c:1751, threshold.c:805/927/2518/1087) reaches __wrap_X below.  Each wrapper follows the accelerate
   hook contract of effect.c:783-787 / resize.c:3818-3826: try the GPU; if the image is not
@@ -427,6 +428,48 @@ Image *B200AccelerateEdgeImage(const Image *image, const double radius, Exceptio
   return run_same_size(image, op_edge, &a, exception);
 }
 
+/* ---- EqualizeImage (enhance.c:2040; the reference's hook is AccelerateEqualizeImage) and EmbossImage (effect.c:1600) ----- */
+static MagickBooleanType equalize_eligible(const Image *image)
+{
+  /* the histogram is indexed by GetPixelIntensity (pixel.c:2356): only its default method on non-linear images is
+     restated; linear RGB / gray would go through EncodePixelGamma */
+  if (default_intensity(image) == MagickFalse) return MagickFalse;
+  if (image->colorspace == RGBColorspace || image->colorspace == LinearGRAYColorspace) return MagickFalse;
+  return MagickTrue;
+}
+
+MagickBooleanType B200AccelerateEqualizeImage(Image *image, ExceptionInfo *exception)
+{
+  const int ch = b200_channels(image);
+  const int sync = (image->channel_mask & SyncChannels) != 0 ? 1 : 0;
+  MagickBooleanType ok = MagickFalse;
+  Quantum *q;
+  (void) exception;
+  if (ch == 0 || mb200_device_count() <= 0 || equalize_eligible(image) == MagickFalse) return MagickFalse;
+  {
+    B200_ATTEMPT_BEGIN;
+    q = GetAuthenticPixels(image, 0, 0, image->columns, image->rows, attempt);
+    if (q != (Quantum *) NULL && b200_cache_pixels(image, ch, attempt) == (float *) q &&
+        mb200_equalize_image((float *) q, image->columns, image->rows, ch, sync) == MB200_OK &&
+        SyncAuthenticPixels(image, attempt) != MagickFalse)
+      ok = MagickTrue;
+    B200_ATTEMPT_END;
+  }
+  return ok;
+}
+
+static int op_emboss(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
+{ const blur_args *b = (const blur_args *) a; return mb200_emboss_image(s, d, w, h, ch, b->radius, b->sigma); }
+
+Image *B200AccelerateEmbossImage(const Image *image, const double radius, const double sigma, ExceptionInfo *exception)
+{
+  blur_args a;
+  if (has_artifact(image, morphology_artifacts) != MagickFalse) return (Image *) NULL;
+  if (equalize_eligible(image) == MagickFalse || (image->channel_mask & SyncChannels) == 0) return (Image *) NULL;
+  a.radius = radius; a.sigma = sigma; a.gain = 0.0; a.threshold = 0.0;
+  return run_same_size(image, op_emboss, &a, exception);
+}
+
 /* ---- ld --wrap entry points ------------------------------------------------------------------------------ */
 extern Image *__real_BlurImage(const Image *, const double, const double, ExceptionInfo *);
 extern Image *__real_GaussianBlurImage(const Image *, const double, const double, ExceptionInfo *);
@@ -551,6 +594,21 @@ Image *__wrap_EdgeImage(const Image *image, const double radius, ExceptionInfo *
 {
   TRY(B200AccelerateEdgeImage(image, radius, exception));
   return __real_EdgeImage(image, radius, exception);
+}
+
+extern Image *__real_EmbossImage(const Image *, const double, const double, ExceptionInfo *);
+extern MagickBooleanType __real_EqualizeImage(Image *, ExceptionInfo *);
+
+Image *__wrap_EmbossImage(const Image *image, const double radius, const double sigma, ExceptionInfo *exception)
+{
+  TRY(B200AccelerateEmbossImage(image, radius, sigma, exception));
+  return __real_EmbossImage(image, radius, sigma, exception);
+}
+
+MagickBooleanType __wrap_EqualizeImage(Image *image, ExceptionInfo *exception)
+{
+  TRY_BOOL(B200AccelerateEqualizeImage(image, exception));
+  return __real_EqualizeImage(image, exception);
 }
 
 Image *__wrap_SampleImage(const Image *image, const size_t columns, const size_t rows, ExceptionInfo *exception)

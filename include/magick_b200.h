@@ -206,6 +206,8 @@ MB200_API size_t mb200_optimal_kernel_width_2d(double radius, double sigma);
    before calling ConvolveImage. */
 MB200_API mb200_kernel_info *mb200_sharpen_kernel(double radius, double sigma);
 MB200_API mb200_kernel_info *mb200_edge_kernel(double radius);
+/* The anti-diagonal kernel EmbossImage (MagickCore/effect.c:1600-1665) builds inline. */
+MB200_API mb200_kernel_info *mb200_emboss_kernel(double radius, double sigma);
 
 /* MotionBlurImage's taps (GetMotionBlurKernel, MagickCore/effect.c:2316-2345) and integer offsets along
    `angle` (:2390-2398).  Returns the tap count; pass NULL arrays to query it. */
@@ -267,6 +269,26 @@ MB200_API int mb200_sharpen_image_dev(const float *src, float *dst, size_t width
     int channels, double radius, double sigma, void *stream);
 MB200_API int mb200_edge_image_dev(const float *src, float *dst, size_t width, size_t height,
     int channels, double radius, void *stream);
+/* EqualizeImage (MagickCore/enhance.c:2040; the reference's hook is AccelerateEqualizeImage, accelerate-private.h), in place:
+   histogram on the device, the 65 536-entry map on the host in the reference's order, table lookup on the device --
+   bit exact.  sync_channels != 0: the channel mask carries SyncChannels (the default mask does): one histogram of the
+   pixel intensity for all channels; 0: one histogram per channel.  Synchronises `stream`. */
+MB200_API int mb200_equalize_image_dev(float *buf, size_t width, size_t height, int channels, int sync_channels,
+    void *stream);
+/* EmbossImage (MagickCore/effect.c:1600): ConvolveImage with mb200_emboss_kernel, then EqualizeImage. */
+MB200_API int mb200_emboss_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
+    double radius, double sigma, void *stream);
+/* StatisticImage (MagickCore/statistic.c:2918): `type` is a StatisticType (statistic.h:141-151: 1 Gradient, 2 Maximum,
+   3 Mean, 4 Median, 5 Minimum, 8 RootMeanSquare, 9 StandardDeviation, 10 Contrast; Mode 6 / Nonpeak 7 return
+   MB200_EUNSUPPORTED) over a window_width x window_height neighbourhood, bit exact. */
+MB200_API int mb200_statistic_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
+    int type, size_t window_width, size_t window_height, void *stream);
+/* RotationalBlurImage (MagickCore/effect.c:3129) == AccelerateRotationalBlurImage (accelerate-private.h), bit exact. */
+MB200_API int mb200_rotational_blur_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
+    double angle, void *stream);
+/* BilateralBlurImage (MagickCore/effect.c:821), odd window sizes (even ones return MB200_EUNSUPPORTED), bit exact. */
+MB200_API int mb200_bilateral_blur_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
+    size_t window_width, size_t window_height, double intensity_sigma, double spatial_sigma, void *stream);
 /* MotionBlurImage (MagickCore/effect.c:2347) == AccelerateMotionBlurImage (accelerate-private.h). */
 MB200_API int mb200_motion_blur_image_dev(const float *src, float *dst, size_t width, size_t height,
     int channels, double radius, double sigma, double angle, void *stream);
@@ -326,6 +348,15 @@ MB200_API int mb200_edge_image(const float *src, float *dst, size_t width, size_
     double radius);
 MB200_API int mb200_motion_blur_image(const float *src, float *dst, size_t width, size_t height, int channels,
     double radius, double sigma, double angle);
+MB200_API int mb200_statistic_image(const float *src, float *dst, size_t width, size_t height, int channels, int type,
+    size_t window_width, size_t window_height);
+MB200_API int mb200_rotational_blur_image(const float *src, float *dst, size_t width, size_t height, int channels,
+    double angle);
+MB200_API int mb200_bilateral_blur_image(const float *src, float *dst, size_t width, size_t height, int channels,
+    size_t window_width, size_t window_height, double intensity_sigma, double spatial_sigma);
+MB200_API int mb200_equalize_image(float *buf, size_t width, size_t height, int channels, int sync_channels);
+MB200_API int mb200_emboss_image(const float *src, float *dst, size_t width, size_t height, int channels,
+    double radius, double sigma);
 MB200_API int mb200_resize_image(const float *src, size_t width, size_t height, int channels,
     float *dst, size_t out_width, size_t out_height, int filter);
 MB200_API int mb200_sample_image(const float *src, size_t width, size_t height, int channels,

@@ -1322,6 +1322,93 @@ int orc_edge(const float *src, float *dst, size_t w, size_t h, int ch, double ra
   return rc;
 }
 
+/* enhance.c:2040-2290 EqualizeImage, Q16-HDRI (MaxMap 65535), default traits.  sync != 0: the channel mask carries
+   SyncChannels (AllChannels, the default mask, does: pixel.h:62,74): every channel's histogram is indexed by the pixel
+   INTENSITY (:2125-2129); 0: by the channel's own value.  ScaleQuantumToMap / ScaleMapToQuantum: quantum-private.h:504, :464. */
+int orc_equalize(float *buf, size_t w, size_t h, int ch, int sync)
+{
+  const size_t n = w * h, bins = 65536;
+  double *histogram, *map, *equalize_map, black[4], white[4];
+  size_t i, j;
+  int c;
+  if (ch < 1 || ch > 4) return -1;
+  histogram = (double *) calloc(bins * (size_t) ch, sizeof(double));
+  map = (double *) malloc(bins * (size_t) ch * sizeof(double));
+  equalize_map = (double *) calloc(bins * (size_t) ch, sizeof(double));
+  if (!histogram || !map || !equalize_map) { free(histogram); free(map); free(equalize_map); return -1; }
+  for (i = 0; i < n; i++) {
+    const float *p = buf + i * (size_t) ch;
+    for (c = 0; c < ch; c++) {
+      double intensity = (double) p[c];
+      if (sync) intensity = pixel_intensity(p, ch);
+      histogram[(size_t) ch * scale_quantum_to_map((float) intensity) + (size_t) c]++;     /* ClampToQuantum: the float cast */
+    }
+  }
+  for (c = 0; c < ch; c++) {
+    double intensity = 0.0;
+    for (j = 0; j < bins; j++) {
+      intensity += histogram[(size_t) ch * j + (size_t) c];
+      map[(size_t) ch * j + (size_t) c] = intensity;
+    }
+  }
+  for (c = 0; c < ch; c++) {
+    black[c] = map[c];
+    white[c] = map[(size_t) ch * (bins - 1) + (size_t) c];
+    if (black[c] != white[c])
+      for (j = 0; j < bins; j++) {
+        const double value = (65535.0 * (map[(size_t) ch * j + (size_t) c] - black[c])) / (white[c] - black[c]);
+        equalize_map[(size_t) ch * j + (size_t) c] =
+            (double) (value <= 0.0 ? 0.0f : value >= 65535.0 ? 65535.0f : (float) value);      /* ScaleMapToQuantum */
+      }
+  }
+  for (i = 0; i < n; i++) {
+    float *q = buf + i * (size_t) ch;
+    for (c = 0; c < ch; c++) {
+      if (black[c] == white[c]) continue;
+      q[c] = (float) equalize_map[(size_t) ch * scale_quantum_to_map(q[c]) + (size_t) c];
+    }
+  }
+  free(histogram); free(map); free(equalize_map);
+  return 0;
+}
+
+/* effect.c:1600-1681 EmbossImage: anti-diagonal kernel (:1649-1665) + ConvolveImage + EqualizeImage */
+int orc_emboss_kernel(double radius, double sigma, orc_kernel *out)
+{
+  const size_t width = orc_optimal_kernel_width_1d(radius, sigma);
+  const double s = fabs(sigma) < EPS ? EPS : sigma;                 /* MagickSigma */
+  double *vals = (double *) malloc(width * width * sizeof(double)), normalize = 0.0, gamma;
+  const long j = (long) (width - 1) / 2;
+  long u, v, k = j;
+  size_t i = 0;
+  int rc;
+  if (!vals) return -1;
+  for (v = -j; v <= j; v++) {
+    for (u = -j; u <= j; u++) {
+      vals[i] = ((u < 0) || (v < 0) ? -8.0 : 8.0) * exp(-((double) u * u + v * v) / (2.0 * s * s)) / (2.0 * PI_ * s * s);
+      if (u != k) vals[i] = 0.0;
+      i++;
+    }
+    k--;
+  }
+  for (i = 0; i < width * width; i++) normalize += vals[i];
+  gamma = perceptible_reciprocal(normalize);
+  for (i = 0; i < width * width; i++) vals[i] *= gamma;
+  rc = orc_kernel_user(width, width, j, j, vals, out);
+  free(vals);
+  return rc;
+}
+
+int orc_emboss(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma)
+{
+  orc_kernel k;
+  int rc = orc_emboss_kernel(radius, sigma, &k);
+  if (rc) return rc;
+  rc = orc_morphology_apply(src, dst, w, h, ch, ORC_CONVOLVE, 1, &k, 1, 0.0);
+  orc_kernel_free(&k);
+  if (rc) return rc;
+  return orc_equalize(dst, w, h, ch, 1);
+}
 
 /* resize.c:3907-4090 SampleImage (default sample:offset = 0.5 - MagickEpsilon) */
 int orc_sample(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh)

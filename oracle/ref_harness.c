@@ -134,6 +134,29 @@ int ref_edge(const float *src, float *dst, size_t w, size_t h, int ch, double ra
 }
 
 __attribute__((visibility("default")))
+int ref_emboss(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma)
+{
+  BEGIN
+  im = make_image(src, w, h, ch, -1, ex);
+  if (im) { out = EmbossImage(im, radius, sigma, ex); rc = export_image(out, dst, w, h, ch, ex); }
+  END
+}
+
+/* EqualizeImage in place; sync == 0 clears SyncChannels from the channel mask (per-channel histograms) */
+__attribute__((visibility("default")))
+int ref_equalize(float *buf, size_t w, size_t h, int ch, int sync)
+{
+  BEGIN
+  im = make_image(buf, w, h, ch, -1, ex);
+  if (im)
+    {
+      if (!sync) (void) SetPixelChannelMask(im, (ChannelType) (AllChannels & ~SyncChannels));
+      if (EqualizeImage(im, ex) != MagickFalse) rc = export_image(im, buf, w, h, ch, ex);
+    }
+  END
+}
+
+__attribute__((visibility("default")))
 int ref_motion_blur(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma, double angle)
 {
   BEGIN

@@ -295,3 +295,78 @@ def test_host_buffer_calls_from_two_application_threads():
         lib.mb200_cache_set_lazy(0)
         for a in (src, mid, out):
             lib.mb200_cache_detach(vp(a))
+
+
+# ---- EqualizeImage / EmbossImage (enhance.c:2040, effect.c:1600) --------------------------------------------------------
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["noise", "gradient", "hdr"])
+@pytest.mark.parametrize("sync", [True, False])
+def test_equalize_bit_exact(ch, kind, sync):
+    src = make_image(301, 157, ch, seed=51, kind=kind)
+    want = src.copy()
+    assert oracle().orc_equalize(P(want), 301, 157, ch, int(sync)) == 0
+    d = _dev(src)
+    assert im.EqualizeImage(d, sync)
+    assert np.array_equal(_host(d), want)
+    h = im.Image(src.copy())
+    assert im.EqualizeImage(h, sync)
+    assert np.array_equal(h.pixels, want)
+
+
+@pytest.mark.parametrize("ch", [1, 3, 4])
+@pytest.mark.parametrize("radius,sigma", [(0.0, 1.0), (0.0, 2.0), (2.0, 0.7)])
+def test_emboss(ch, radius, sigma):
+    """Kernel taps bit-identical to the oracle's (pinned to the reference); the convolution within 1 ULP; the
+    equalisation -- a discontinuous function of the convolved values: one sample crossing a histogram bin moves the whole
+    map -- bit exact ON THE SAME convolved image, and the end-to-end result identical to the reference's wherever the
+    convolution was (which is nearly everywhere)."""
+    k = util.OrcKernel()
+    assert oracle().orc_emboss_kernel(radius, sigma, C.byref(k)) == 0
+    from imagemagick_b200 import _lib
+    mine = im.KernelInfo(_lib.load().mb200_emboss_kernel(radius, sigma)).arrays()[0][0]
+    assert np.array_equal(mine, k.array())
+    src = make_image(211, 133, ch, seed=52, kind="alpha_blocks" if ch == 4 else "noise")
+    conv_want = util.orc_morphology(src, im.ConvolveMorphology, 1, [k])
+    conv_got = _host(im.ConvolveImage(_dev(src), im.KernelInfo(_lib.load().mb200_emboss_kernel(radius, sigma))))
+    assert max_ulp(conv_got, conv_want) <= 1
+    got = _host(im.EmbossImage(_dev(src), radius, sigma))
+    eq = conv_got.copy()
+    assert oracle().orc_equalize(P(eq), 211, 133, ch, 1) == 0
+    assert np.array_equal(got, eq)
+    want = orc("orc_emboss", src, radius, sigma)
+    if np.array_equal(conv_got, conv_want):
+        assert np.array_equal(got, want)
+    assert util.frac_exact(got, want) > 0.99
+
+
+# ---- rank-4 stencils: StatisticImage, RotationalBlurImage, BilateralBlurImage (oracles pinned to the reference) ----------
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("stat", [1, 2, 3, 4, 5, 8, 9, 10])
+@pytest.mark.parametrize("win", [(3, 3), (5, 3), (1, 7), (4, 4)])
+def test_statistic_image_bit_exact(ch, stat, win):
+    src = make_image(97, 61, ch, seed=61, kind="hdr" if stat in (1, 10) else "noise")
+    want = orc("orc_statistic", src, stat, win[0], win[1])
+    got = _host(im.StatisticImage(_dev(src), stat, win[0], win[1]))
+    assert_same_specials_and_ulp(got, want, bar=0)
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("size,angle", [((120, 80), 10.0), ((64, 64), 45.0), ((201, 33), 3.0), ((50, 90), -20.0)])
+def test_rotational_blur_bit_exact(ch, size, angle):
+    w, h = size
+    src = make_image(w, h, ch, seed=62, kind="alpha_blocks" if ch in (2, 4) else "noise")
+    want = orc("orc_rotational_blur", src, angle)
+    got = _host(im.RotationalBlurImage(_dev(src), angle))
+    assert max_ulp(got, want) == 0
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("win,isig,ssig", [((5, 5), 0.75, 2.0), ((7, 3), 12.0, 1.5), ((3, 9), 40.0, 4.0)])
+def test_bilateral_blur_bit_exact(ch, win, isig, ssig):
+    src = make_image(90, 70, ch, seed=63, kind="alpha_blocks" if ch in (2, 4) else "gradient")
+    want = orc("orc_bilateral_blur", src, win[0], win[1], isig, ssig)
+    got = _host(im.BilateralBlurImage(_dev(src), win[0], win[1], isig, ssig))
+    assert max_ulp(got, want) == 0
+    with pytest.raises(im.MagickB200Error) as e:
+        im.BilateralBlurImage(_dev(src), 4, 4, isig, ssig)
+    assert e.value.code == -5

@@ -218,3 +218,28 @@ def test_thread_count_independence():
         assert util.ref().ref_blur(P(src), P(a), 128, 96, 4, 0.0, 2.0) == 0
         outs.append(a)
     assert max_ulp(outs[0], outs[1]) == 0
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["noise", "gradient", "hdr"])
+@pytest.mark.parametrize("sync", [1, 0])
+def test_equalize_bit_exact(ch, kind, sync):
+    """EqualizeImage (enhance.c:2040): histogram / running sums / table lookup restated; integer counts and one division
+    per table entry, so the restatement must reproduce the reference bit for bit."""
+    src = util.make_image(97, 61, ch, seed=31, kind=kind)
+    a, b = src.copy(), src.copy()
+    assert util.oracle().orc_equalize(util.P(a), 97, 61, ch, sync) == 0
+    assert util.ref().ref_equalize(util.P(b), 97, 61, ch, sync) == 0
+    assert np.array_equal(a, b)
+    assert not np.array_equal(a, src)
+
+
+@pytest.mark.parametrize("ch", [1, 3, 4])
+@pytest.mark.parametrize("radius,sigma", [(0.0, 1.0), (0.0, 2.0), (2.0, 0.7)])
+def test_emboss_bit_exact(ch, radius, sigma):
+    """EmbossImage (effect.c:1600): inline anti-diagonal kernel + ConvolveImage + EqualizeImage."""
+    src = util.make_image(83, 59, ch, seed=32, kind="alpha_blocks" if ch == 4 else "noise")
+    a, b = np.empty_like(src), np.empty_like(src)
+    assert util.oracle().orc_emboss(util.P(src), util.P(a), 83, 59, ch, radius, sigma) == 0
+    assert util.ref().ref_emboss(util.P(src), util.P(b), 83, 59, ch, radius, sigma) == 0
+    assert np.array_equal(a, b)

@@ -48,6 +48,9 @@ def oracle() -> C.CDLL:
         o.orc_rotational_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _d]
         o.orc_statistic.argtypes = [_fp, _fp, _sz, _sz, _i, _i, _sz, _sz]
         o.orc_edge.argtypes = [_fp, _fp, _sz, _sz, _i, _d]
+        o.orc_emboss.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d]
+        o.orc_emboss_kernel.argtypes = [_d, _d, C.POINTER(OrcKernel)]
+        o.orc_equalize.argtypes = [_fp, _sz, _sz, _i, _i]
         o.orc_resize.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz, _i]
         o.orc_colorspace.argtypes = [_fp, _sz, _sz, _i, _i, _i]
         o.orc_sample.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
@@ -91,6 +94,8 @@ def ref() -> C.CDLL:
         r.ref_rotational_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _d]
         r.ref_statistic.argtypes = [_fp, _fp, _sz, _sz, _i, _i, _sz, _sz]
         r.ref_edge.argtypes = [_fp, _fp, _sz, _sz, _i, _d]
+        r.ref_emboss.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d]
+        r.ref_equalize.argtypes = [_fp, _sz, _sz, _i, _i]
         r.ref_convolve.argtypes = [_fp, _fp, _sz, _sz, _i, C.c_char_p]
         r.ref_morphology.argtypes = [_fp, _fp, _sz, _sz, _i, _i, _l, C.c_char_p]
         r.ref_resize.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz, _i]
