@@ -72,12 +72,21 @@ __device__ __forceinline__ bool nonfinite_bits(double v) {
 // This is PerceptibleReciprocal's test (pixel-accessor.h:242-254) applied to gamma = QS * den.
 __device__ __forceinline__ double clamp_denominator(double den) {
   constexpr double kTiny = kEpsilon / kQuantumScale;           // 6.5535e-8
-  const unsigned hi = static_cast<unsigned>(__double2hiint(den)), lo = static_cast<unsigned>(__double2loint(den));
+  const unsigned hi = static_cast<unsigned>(__double2hiint(den));
   const unsigned habs = hi & 0x7fffffffu;
   const unsigned th = static_cast<unsigned>(__double2hiint(kTiny)), tl = static_cast<unsigned>(__double2loint(kTiny));
-  if (habs < th || (habs == th && lo < tl))
-    den = __hiloint2double(static_cast<int>((hi & 0x80000000u) | th), static_cast<int>(tl));
+  if (__builtin_expect(habs <= th, 0)) {                       // rare: (almost) fully transparent neighbourhood
+    const unsigned lo = static_cast<unsigned>(__double2loint(den));
+    if (habs < th || lo < tl) den = __hiloint2double(static_cast<int>((hi & 0x80000000u) | th), static_cast<int>(tl));
+  }
   return den;
+}
+
+// v * m on lanes where `cond` holds, v elsewhere, as ONE predicated DMUL (the compiler's own lowering of the conditional
+// is a DMUL plus two 32-bit selects; the loop-invariant predicate is hoisted by ptxas).
+__device__ __forceinline__ double mul_if(double v, double m, int cond) {
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p mul.f64 %0, %0, %1;\n\t}" : "+d"(v) : "d"(m), "r"(cond));
+  return v;
 }
 
 // UnsharpMaskImage's point pass (effect.c:4358-4364) on the float-rounded blur value, in the reference's operation
@@ -327,8 +336,8 @@ __global__ void __launch_bounds__(128, MINB) conv_row_kernel(const Conv1dArgs a,
 // colour components are scaled by r, the alpha component (odd lane, .y) is stored unscaled.
 __device__ __forceinline__ float2 finish_pair(bool odd, double sum0, double sum1, double gsum) {
   const double r = fast_reciprocal(clamp_denominator(gsum));
-  const double m1 = odd ? 1.0 : r;
-  return make_float2(static_cast<float>(sum0 * r), static_cast<float>(sum1 * m1));
+  const double o1 = mul_if(sum1, r, !odd);      // the alpha component (odd lane, .y) is stored unscaled
+  return make_float2(static_cast<float>(sum0 * r), static_cast<float>(o1));
 }
 
 // ---- pair stream kernel, both axes.  A thread owns one component pair and walks along the
@@ -391,15 +400,13 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a
   InT pre[PF];
 #pragma unroll
   for (int q = 0; q < NT; ++q) { acc0[q] = 0.0; acc1[q] = 0.0; }
-  int isrc = first - a.off;                 // source index of step 0
+  const int isrc0 = first - a.off;          // source index of step 0
 #pragma unroll
   for (int s = 0; s < PF; ++s) {
-    const unsigned ii = static_cast<unsigned>(min(max(isrc + s, 0), limit));
+    const unsigned ii = static_cast<unsigned>(min(max(isrc0 + s, 0), limit));
     pre[s] = __ldg(reinterpret_cast<const InT *>(base + static_cast<size_t>(ii) * step));
   }
-  isrc += PF;
 
-  int j = -(NT - 1);
   // EPI: the operator's source pixel of every output, fetched PF steps ahead of the step that needs it (a load issued
   // in the output stage itself would expose a DRAM round trip per step: measured 2x on the whole operator).
   float2 epi[EPI ? PF : 1];
@@ -409,82 +416,101 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a
                static_cast<size_t>(first) * ostep;       // element (row 0) of this thread's column pair
 #pragma unroll
     for (int s = 0; s < PF; ++s) {
-      const unsigned r = static_cast<unsigned>(min(max(first + j + s, 0), limit));
+      const unsigned r = static_cast<unsigned>(min(max(first - (NT - 1) + s, 0), limit));
       epi[s] = __ldg(reinterpret_cast<const float2 *>(epi_base + static_cast<size_t>(r) * ostep));
     }
   }
+  // Issue slots, not the FP64 pipe alone, bound this loop: a step is 70 DFMA + 4 DMUL (2 issue cycles each on the half-rate
+  // pipe = 148 cycles per warp) and two warps per scheduler leave room for ~70 other instructions per step before the
+  // scheduler itself saturates; r01 issued ~50.  Hence:
+  //  * strips whose samples all lie inside the image (every strip but the first and the last of a line) run a loop
+  //    without index clamping: the load, L2-prefetch and store addresses advance by one 64-bit add each;
+  //  * an accumulator is (re)started by its first tap as a plain product instead of being zeroed and FMA-ed;
+  //  * the odd lanes' "multiply by one" is a predicated multiply instead of a 64-bit select.
+  outp -= static_cast<size_t>(NT - 1) * ostep;           // where output j = -(NT-1) would be; never dereferenced for j < 0
+  const bool inside = isrc0 >= 0 && isrc0 + total + PF + (L2PF ? a.seg_w : 0) <= limit;   // uniform over the CTA
+  auto run = [&](auto clamp_tag) {
+    constexpr bool CLAMP = decltype(clamp_tag)::value;
+    int isrc = isrc0 + PF;
+    const char *lp = base + static_cast<size_t>(CLAMP ? 0 : isrc) * step;          // next sample to fetch (CLAMP: unused)
+    const size_t pf_bytes = static_cast<size_t>(a.seg_w) * step;
+    int jb = -(NT - 1);                      // output index of step 0 of the current block
 #pragma unroll 1
-  for (int mb = 0; mb < total; mb += PF) {       // PF unrolled steps, then rotate the accumulators by PF
+    for (int mb = 0; mb < total; mb += PF, jb += PF) {       // PF unrolled steps, then rotate the accumulators by PF
 #pragma unroll
-    for (int s = 0; s < PF; ++s) {
-      const InT vf = pre[s];
-      {
-        const unsigned ii = static_cast<unsigned>(min(max(isrc, 0), limit));
-        pre[s] = __ldg(reinterpret_cast<const InT *>(base + static_cast<size_t>(ii) * step));
-        if (L2PF) {             // L2 prefetch far ahead: the ring's LDGs then complete at L2 latency
-          const unsigned ip = static_cast<unsigned>(min(isrc + a.seg_w, limit));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + static_cast<size_t>(ip) * step));
+      for (int s = 0; s < PF; ++s) {
+        const InT vf = pre[s];
+        if (CLAMP) {
+          const unsigned ii = static_cast<unsigned>(min(max(isrc, 0), limit));
+          pre[s] = __ldg(reinterpret_cast<const InT *>(base + static_cast<size_t>(ii) * step));
+          if (L2PF) {             // L2 prefetch far ahead: the ring's LDGs then complete at L2 latency
+            const unsigned ip = static_cast<unsigned>(min(isrc + a.seg_w, limit));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + static_cast<size_t>(ip) * step));
+          }
+          ++isrc;
+        } else {
+          pre[s] = __ldg(reinterpret_cast<const InT *>(lp));
+          if (L2PF) asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + pf_bytes));
+          lp += step;
         }
-        ++isrc;
-      }
-      // (premultiplying one step ahead, as the cp.async kernel does, costs this kernel 5 %: 220 registers)
-      double v0, v1;
-      if (IO == 2) {
-        v0 = vf.x; v1 = vf.y;                       // already premultiplied sums
-      } else {
-        const float af = __shfl_sync(0xffffffffu, static_cast<float>(vf.y), alpha_lane);
-        const double da = static_cast<double>(af);
-        v0 = static_cast<double>(vf.x) * da;
-        v1 = static_cast<double>(vf.y) * (odd ? 1.0 : da);
-      }
-      if (PADDED && __any_sync(0xffffffffu, nonfinite_bits(vf.x) || nonfinite_bits(vf.y))) {
+        // (premultiplying one step ahead, as the cp.async kernel does, costs this kernel 5 %: 220 registers)
+        double v0, v1;
+        if (IO == 2) {
+          v0 = vf.x; v1 = vf.y;                       // already premultiplied sums
+        } else {
+          const float af = __shfl_sync(0xffffffffu, static_cast<float>(vf.y), alpha_lane);
+          const double da = static_cast<double>(af);
+          v0 = static_cast<double>(vf.x) * da;
+          v1 = mul_if(static_cast<double>(vf.y), da, !odd);      // the alpha component itself is not premultiplied
+        }
+        if (PADDED && __any_sync(0xffffffffu, nonfinite_bits(vf.x) || nonfinite_bits(vf.y))) {
 #pragma unroll
-        for (int q = 0; q < NT; ++q) {
-          if ((s - q + NT) % NT < a.ntaps) {
-            const double k = taps.k[(s - q + NT) % NT];
-            acc0[q] = fma(k, v0, acc0[q]);
-            acc1[q] = fma(k, v1, acc1[q]);
+          for (int q = 0; q < NT; ++q) {
+            const int t = (s - q + NT) % NT;
+            if (t == 0) { acc0[q] = taps.k[0] * v0; acc1[q] = taps.k[0] * v1; }
+            else if (t < a.ntaps) { acc0[q] = fma(taps.k[t], v0, acc0[q]); acc1[q] = fma(taps.k[t], v1, acc1[q]); }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < NT; ++q) {
+            const int t = (s - q + NT) % NT;
+            const double k = taps.k[t];
+            if (t == 0) { acc0[q] = k * v0; acc1[q] = k * v1; }        // first tap of a new output: no zeroing needed
+            else { acc0[q] = fma(k, v0, acc0[q]); acc1[q] = fma(k, v1, acc1[q]); }
           }
         }
-      } else {
-#pragma unroll
-        for (int q = 0; q < NT; ++q) {
-          const double k = taps.k[(s - q + NT) % NT];
-          acc0[q] = fma(k, v0, acc0[q]);
-          acc1[q] = fma(k, v1, acc1[q]);
+        const int qf = (s + 1) % NT;                 // this slot has just received its last tap
+        const double sum0 = acc0[qf], sum1 = acc1[qf];
+        const bool store = static_cast<unsigned>(jb + s) < static_cast<unsigned>(nout);
+        if (IO == 1) {
+          if (store) *reinterpret_cast<double2 *>(outp) = make_double2(sum0, sum1);
+        } else {
+          const double gsum = shfl_double(sum1, alpha_lane);
+          float2 out = finish_pair(odd, sum0, sum1, gsum);
+          if (EPI == 1) {            // source pixel of output j (prefetched), then refill the slot for output j + PF
+            const float2 p = epi[s];
+            const unsigned r = static_cast<unsigned>(min(max(first + jb + s + PF, 0), limit));
+            epi[s] = __ldg(reinterpret_cast<const float2 *>(epi_base + static_cast<size_t>(r) * ostep));
+            out.x = unsharp_point(p.x, out.x, a.gain, a.qthreshold);
+            out.y = unsharp_point(p.y, out.y, a.gain, a.qthreshold);
+          }
+          if (store) *reinterpret_cast<float2 *>(outp) = out;
         }
+        outp += ostep;
       }
-      const int qf = (s + 1) % NT;
-      const double sum0 = acc0[qf], sum1 = acc1[qf];
-      acc0[qf] = 0.0;
-      acc1[qf] = 0.0;
-      if (IO == 1) {
-        if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<double2 *>(outp) = make_double2(sum0, sum1);
-      } else {
-        const double gsum = shfl_double(sum1, alpha_lane);
-        float2 out = finish_pair(odd, sum0, sum1, gsum);
-        if (EPI == 1) {            // source pixel of output j (prefetched), then refill the slot for output j + PF
-          const float2 p = epi[s];
-          const unsigned r = static_cast<unsigned>(min(max(first + j + PF, 0), limit));
-          epi[s] = __ldg(reinterpret_cast<const float2 *>(epi_base + static_cast<size_t>(r) * ostep));
-          out.x = unsharp_point(p.x, out.x, a.gain, a.qthreshold);
-          out.y = unsharp_point(p.y, out.y, a.gain, a.qthreshold);
-        }
-        if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<float2 *>(outp) = out;
+      if (PF != NT) {
+        double t0[PF], t1[PF];
+#pragma unroll
+        for (int q = 0; q < PF; ++q) { t0[q] = acc0[q]; t1[q] = acc1[q]; }
+#pragma unroll
+        for (int q = 0; q < NT - PF; ++q) { acc0[q] = acc0[q + PF]; acc1[q] = acc1[q + PF]; }
+#pragma unroll
+        for (int q = 0; q < PF; ++q) { acc0[NT - PF + q] = t0[q]; acc1[NT - PF + q] = t1[q]; }
       }
-      if (j >= 0) outp += ostep;
-      ++j;
     }
-    if (PF != NT) {
-      double t0[PF], t1[PF];
-#pragma unroll
-      for (int q = 0; q < PF; ++q) { t0[q] = acc0[q]; t1[q] = acc1[q]; }
-#pragma unroll
-      for (int q = 0; q < NT - PF; ++q) { acc0[q] = acc0[q + PF]; acc1[q] = acc1[q + PF]; }
-#pragma unroll
-      for (int q = 0; q < PF; ++q) { acc0[NT - PF + q] = t0[q]; acc1[NT - PF + q] = t1[q]; }
-    }
-  }
+  };
+  if (inside) run(std::false_type{});
+  else run(std::true_type{});
 }
 
 // ---- pair stream kernel with a shared-memory prefetch ring (cp.async / LDGSTS), both axes.
@@ -640,30 +666,27 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_async_kernel(const Conv1d
         const float af = __shfl_sync(0xffffffffu, vnext.y, alpha_lane);
         const double da = static_cast<double>(af);
         nv0 = static_cast<double>(vnext.x) * da;
-        nv1 = static_cast<double>(vnext.y) * (odd ? 1.0 : da);
+        nv1 = mul_if(static_cast<double>(vnext.y), da, !odd);
         if (PADDED) nbad = __any_sync(0xffffffffu, nonfinite_bits(vnext.x) || nonfinite_bits(vnext.y));
       }
       if (PADDED && bad) {
 #pragma unroll
         for (int q = 0; q < NT; ++q) {
-          if ((s - q + NT) % NT < a.ntaps) {
-            const double k = taps.k[(s - q + NT) % NT];
-            acc0[q] = fma(k, v0, acc0[q]);
-            acc1[q] = fma(k, v1, acc1[q]);
-          }
+          const int t = (s - q + NT) % NT;
+          if (t == 0) { acc0[q] = taps.k[0] * v0; acc1[q] = taps.k[0] * v1; }
+          else if (t < a.ntaps) { acc0[q] = fma(taps.k[t], v0, acc0[q]); acc1[q] = fma(taps.k[t], v1, acc1[q]); }
         }
       } else {
 #pragma unroll
         for (int q = 0; q < NT; ++q) {
-          const double k = taps.k[(s - q + NT) % NT];
-          acc0[q] = fma(k, v0, acc0[q]);
-          acc1[q] = fma(k, v1, acc1[q]);
+          const int t = (s - q + NT) % NT;
+          const double k = taps.k[t];
+          if (t == 0) { acc0[q] = k * v0; acc1[q] = k * v1; }          // first tap of a new output: no zeroing needed
+          else { acc0[q] = fma(k, v0, acc0[q]); acc1[q] = fma(k, v1, acc1[q]); }
         }
       }
-      const int qf = (s + 1) % NT;
+      const int qf = (s + 1) % NT;                 // this slot has just received its last tap
       const double sum0 = acc0[qf], sum1 = acc1[qf];
-      acc0[qf] = 0.0;
-      acc1[qf] = 0.0;
       if (IO == 1) {
         if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<double2 *>(outp) = make_double2(sum0, sum1);
       } else {

@@ -7,7 +7,7 @@
           --wrap=MorphologyImage,--wrap=ResizeImage,--wrap=TransformImageColorspace,\
           --wrap=BilevelImage,--wrap=BlackThresholdImage,--wrap=WhiteThresholdImage,--wrap=ClampImage,\
           --wrap=SharpenImage,--wrap=EdgeImage,--wrap=SampleImage,--wrap=ThumbnailImage,--wrap=MinifyImage,--wrap=ResampleImage,--wrap=MotionBlurImage,\
-          --wrap=EmbossImage,--wrap=EqualizeImage
+          --wrap=EmbossImage,--wrap=EqualizeImage,--wrap=StatisticImage,--wrap=RotationalBlurImage,--wrap=BilateralBlurImage
   and every caller of those exported functions (effect.c:765/1709/1170/4256, morphology.c:4129,
   resize.c:3761, colorspace.c:1751, threshold.c:805/927/2518/1087) reaches __wrap_X below.  Each wrapper follows the accelerate
   hook contract of effect.c:783-787 / resize.c:3818-3826: try the GPU; if the image is not
@@ -470,6 +470,44 @@ Image *B200AccelerateEmbossImage(const Image *image, const double radius, const 
   return run_same_size(image, op_emboss, &a, exception);
 }
 
+/* ---- StatisticImage (statistic.c:2918), RotationalBlurImage (effect.c:3129), BilateralBlurImage (effect.c:821) -------------- */
+typedef struct { int type; size_t width, height; double a, b; } stencil_args;
+static int op_statistic(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
+{ const stencil_args *t = (const stencil_args *) a; return mb200_statistic_image(s, d, w, h, ch, t->type, t->width, t->height); }
+static int op_rotational(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
+{ const stencil_args *t = (const stencil_args *) a; return mb200_rotational_blur_image(s, d, w, h, ch, t->a); }
+static int op_bilateral(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
+{ const stencil_args *t = (const stencil_args *) a; return mb200_bilateral_blur_image(s, d, w, h, ch, t->width, t->height, t->a, t->b); }
+
+Image *B200AccelerateStatisticImage(const Image *image, const StatisticType type, const size_t width, const size_t height,
+                                    ExceptionInfo *exception)
+{
+  stencil_args a;
+  switch (type) {
+    case GradientStatistic: case MaximumStatistic: case MeanStatistic: case MedianStatistic: case MinimumStatistic:
+    case RootMeanSquareStatistic: case StandardDeviationStatistic: case ContrastStatistic: break;
+    default: return (Image *) NULL;               /* Mode / Nonpeak walk the reference's skip list: CPU */
+  }
+  a.type = (int) type; a.width = width; a.height = height; a.a = a.b = 0.0;
+  return run_same_size(image, op_statistic, &a, exception);
+}
+
+Image *B200AccelerateRotationalBlurImage(const Image *image, const double angle, ExceptionInfo *exception)
+{
+  stencil_args a;
+  a.type = 0; a.width = a.height = 0; a.a = angle; a.b = 0.0;
+  return run_same_size(image, op_rotational, &a, exception);
+}
+
+Image *B200AccelerateBilateralBlurImage(const Image *image, const size_t width, const size_t height,
+                                        const double intensity_sigma, const double spatial_sigma, ExceptionInfo *exception)
+{
+  stencil_args a;
+  if (equalize_eligible(image) == MagickFalse) return (Image *) NULL;        /* tonal weights use GetPixelIntensity */
+  a.type = 0; a.width = width; a.height = height; a.a = intensity_sigma; a.b = spatial_sigma;
+  return run_same_size(image, op_bilateral, &a, exception);
+}
+
 /* ---- ld --wrap entry points ------------------------------------------------------------------------------ */
 extern Image *__real_BlurImage(const Image *, const double, const double, ExceptionInfo *);
 extern Image *__real_GaussianBlurImage(const Image *, const double, const double, ExceptionInfo *);
@@ -594,6 +632,30 @@ Image *__wrap_EdgeImage(const Image *image, const double radius, ExceptionInfo *
 {
   TRY(B200AccelerateEdgeImage(image, radius, exception));
   return __real_EdgeImage(image, radius, exception);
+}
+
+extern Image *__real_StatisticImage(const Image *, const StatisticType, const size_t, const size_t, ExceptionInfo *);
+extern Image *__real_RotationalBlurImage(const Image *, const double, ExceptionInfo *);
+extern Image *__real_BilateralBlurImage(const Image *, const size_t, const size_t, const double, const double, ExceptionInfo *);
+
+Image *__wrap_StatisticImage(const Image *image, const StatisticType type, const size_t width, const size_t height,
+                             ExceptionInfo *exception)
+{
+  TRY(B200AccelerateStatisticImage(image, type, width, height, exception));
+  return __real_StatisticImage(image, type, width, height, exception);
+}
+
+Image *__wrap_RotationalBlurImage(const Image *image, const double angle, ExceptionInfo *exception)
+{
+  TRY(B200AccelerateRotationalBlurImage(image, angle, exception));
+  return __real_RotationalBlurImage(image, angle, exception);
+}
+
+Image *__wrap_BilateralBlurImage(const Image *image, const size_t width, const size_t height, const double intensity_sigma,
+                                 const double spatial_sigma, ExceptionInfo *exception)
+{
+  TRY(B200AccelerateBilateralBlurImage(image, width, height, intensity_sigma, spatial_sigma, exception));
+  return __real_BilateralBlurImage(image, width, height, intensity_sigma, spatial_sigma, exception);
 }
 
 extern Image *__real_EmbossImage(const Image *, const double, const double, ExceptionInfo *);

@@ -27,6 +27,9 @@ extern Image *__real_ResampleImage(const Image *, const double, const double, co
 extern int mb200_device_count(void);
 extern Image *__real_SharpenImage(const Image *, const double, const double, ExceptionInfo *);
 extern Image *__real_EmbossImage(const Image *, const double, const double, ExceptionInfo *);
+extern Image *__real_StatisticImage(const Image *, const StatisticType, const size_t, const size_t, ExceptionInfo *);
+extern Image *__real_RotationalBlurImage(const Image *, const double, ExceptionInfo *);
+extern Image *__real_BilateralBlurImage(const Image *, const size_t, const size_t, const double, const double, ExceptionInfo *);
 extern MagickBooleanType __real_EqualizeImage(Image *, ExceptionInfo *);
 extern Image *__real_EdgeImage(const Image *, const double, ExceptionInfo *);
 extern MagickBooleanType __real_BilevelImage(Image *, const double, ExceptionInfo *);
@@ -105,6 +108,10 @@ int main(void)
   CHECK("SampleImage 517x389 -> 100x77 RGBA", 0, SampleImage(rgba, 100, 77, ex), CPU(__real_SampleImage(rgba, 100, 77, ex)));
   CHECK("SharpenImage(0,1) RGBA", 1, SharpenImage(rgba, 0.0, 1.0, ex), CPU(__real_SharpenImage(rgba, 0.0, 1.0, ex)));
   CHECK("EdgeImage(1) RGB", 1, EdgeImage(rgb, 1.0, ex), CPU(__real_EdgeImage(rgb, 1.0, ex)));
+  CHECK("StatisticImage Median 3x3 RGBA", 0, StatisticImage(rgba, MedianStatistic, 3, 3, ex), CPU(__real_StatisticImage(rgba, MedianStatistic, 3, 3, ex)));
+  CHECK("StatisticImage StdDev 5x3 RGB", 0, StatisticImage(rgb, StandardDeviationStatistic, 5, 3, ex), CPU(__real_StatisticImage(rgb, StandardDeviationStatistic, 5, 3, ex)));
+  CHECK("RotationalBlurImage(7) RGBA", 0, RotationalBlurImage(rgba, 7.0, ex), CPU(__real_RotationalBlurImage(rgba, 7.0, ex)));
+  CHECK("BilateralBlurImage 5x5 RGB", 0, BilateralBlurImage(rgb, 5, 5, 20.0, 2.0, ex), CPU(__real_BilateralBlurImage(rgb, 5, 5, 20.0, 2.0, ex)));
   k = AcquireKernelInfo("Disk:3", ex);
   CHECK("MorphologyImage Dilate Disk:3", 0, MorphologyImage(rgba, DilateMorphology, 1, k, ex), CPU(__real_MorphologyImage(rgba, DilateMorphology, 1, k, ex)));
   CHECK("MorphologyImage Erode x2 Disk:3", 0, MorphologyImage(rgb, ErodeMorphology, 2, k, ex), CPU(__real_MorphologyImage(rgb, ErodeMorphology, 2, k, ex)));
@@ -192,7 +199,7 @@ int main(void)
     t = DestroyImage(t);
   }
   printf("gpu hits %ld, cpu fallbacks %ld\n", B200ShimHits(), B200ShimFallbacks());
-  if (mb200_device_count() > 0 && B200ShimHits() < 20) { printf("FAIL: operators did not reach the GPU path\n"); failures++; }
+  if (mb200_device_count() > 0 && B200ShimHits() < 24) { printf("FAIL: operators did not reach the GPU path\n"); failures++; }
   rgba = DestroyImage(rgba); rgb = DestroyImage(rgb);
   ex = DestroyExceptionInfo(ex);
   MagickCoreTerminus();
