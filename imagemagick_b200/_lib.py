@@ -95,6 +95,10 @@ PROTOTYPES = {
     "mb200_transform_colorspace": (_i, [_vp, _sz, _sz, _i, _i, _i]),
     "mb200_sharpen_kernel": (KernelPtr, [_d, _d]),
     "mb200_edge_kernel": (KernelPtr, [_d]),
+    "mb200_restore_channels_dev": (_i, [_vp, _vp, _sz, _sz, _i, C.c_uint, _vp]),
+    "mb200_resize_copy_channels_dev": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i, C.c_uint, _vp]),
+    "mb200_restore_channels": (_i, [_vp, _vp, _sz, _sz, _i, C.c_uint]),
+    "mb200_resize_copy_channels": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i, C.c_uint]),
     "mb200_statistic_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _i, _sz, _sz, _vp]),
     "mb200_rotational_blur_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _d, _vp]),
     "mb200_bilateral_blur_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _sz, _sz, _d, _d, _vp]),

@@ -831,6 +831,90 @@ int mb200_edge_image(const float *src, float *dst, size_t w, size_t h, int ch, d
 
 }  // extern "C"
 
+// ---- Copy-trait channels of a `-channel` selection ------------------------------------------------------------------------
+extern "C" int mb200_resize_nearest(int filter, size_t in_n, size_t out_n, double factor, long *nearest);
+
+extern "C" {
+
+int mb200_restore_channels_dev(float *dst, const float *src, size_t width, size_t height, int channels, unsigned update_mask,
+                               void *stream) {
+  if (!dst || !src || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "restore channels: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  if ((update_mask & ((1u << channels) - 1u)) == ((1u << channels) - 1u)) return MB200_OK;      // nothing to restore
+  return launch_restore_channels(dst, src, width * height, channels, update_mask, s);
+}
+
+int mb200_resize_copy_channels_dev(const float *src, size_t width, size_t height, int channels, float *dst, size_t out_width,
+                                   size_t out_height, int filter, unsigned update_mask, void *stream) {
+  if (!dst || !src || !valid_image(width, height, channels) || out_width == 0 || out_height == 0)
+    return fail(MB200_EINVAL, "resize copy channels: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  if ((update_mask & ((1u << channels) - 1u)) == ((1u << channels) - 1u)) return MB200_OK;
+  auto reciprocal = [](double x) { return std::fabs(x) >= 1.0e-12 ? 1.0 / x : (x < 0 ? -1.0e12 : 1.0e12); };
+  const double x_factor = static_cast<double>(out_width) * reciprocal(static_cast<double>(width));
+  const double y_factor = static_cast<double>(out_height) * reciprocal(static_cast<double>(height));
+  int filter_type = MB200_LanczosFilter;                                                           // resize.c:3806-3816
+  if (filter != MB200_UndefinedFilter) filter_type = filter;
+  else if (x_factor == 1.0 && y_factor == 1.0) filter_type = MB200_PointFilter;
+  else if (has_alpha(channels) || (x_factor * y_factor) > 1.0) filter_type = MB200_MitchellFilter;
+  std::vector<long> nx(out_width), ny(out_height);
+  rc = mb200_resize_nearest(filter_type, width, out_width, x_factor, nx.data());
+  if (!rc) rc = mb200_resize_nearest(filter_type, height, out_height, y_factor, ny.data());
+  if (rc) return rc;
+  std::vector<int> table(out_width + out_height);
+  for (size_t i = 0; i < out_width; ++i) table[i] = static_cast<int>(nx[i]);
+  for (size_t i = 0; i < out_height; ++i) table[out_width + i] = static_cast<int>(ny[i]);
+  StreamAlloc d_table(s);
+  rc = d_table.alloc(table.size() * sizeof(int));
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpyAsync(d_table.ptr, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cuda_fail(e, "resize copy channels: table upload");
+  const int *d = static_cast<const int *>(d_table.ptr);
+  return launch_resize_copy_channels(dst, src, width, out_width, out_height, channels, d, d + out_width, update_mask, s);
+}
+
+// host buffers: dst already holds the operator's result (resident when attached), src is the operator's source
+int mb200_restore_channels(float *dst, const float *src, size_t w, size_t h, int ch, unsigned update_mask) {
+  if (!dst || !src || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "restore channels: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(nullptr, &s);
+  if (rc) return rc;
+  const size_t bytes = w * h * ch * sizeof(float);
+  StageRef io, in;
+  rc = stage_input(dst, bytes, s, &io);
+  if (!rc) rc = stage_input(src, bytes, s, &in);
+  if (!rc) rc = mb200_restore_channels_dev(static_cast<float *>(io.dev), static_cast<const float *>(in.dev), w, h, ch, update_mask, s);
+  if (rc) cudaStreamSynchronize(s);
+  else rc = finish_output(&io, s);
+  release_stage(&in, s);
+  release_stage(&io, s);
+  return rc;
+}
+
+int mb200_resize_copy_channels(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh, int filter,
+                               unsigned update_mask) {
+  if (!dst || !src || !valid_image(w, h, ch) || ow == 0 || oh == 0) return fail(MB200_EINVAL, "resize copy channels: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(nullptr, &s);
+  if (rc) return rc;
+  StageRef io, in;
+  rc = stage_input(dst, ow * oh * ch * sizeof(float), s, &io);
+  if (!rc) rc = stage_input(src, w * h * ch * sizeof(float), s, &in);
+  if (!rc) rc = mb200_resize_copy_channels_dev(static_cast<const float *>(in.dev), w, h, ch, static_cast<float *>(io.dev), ow, oh, filter,
+                                               update_mask, s);
+  if (rc) cudaStreamSynchronize(s);
+  else rc = finish_output(&io, s);
+  release_stage(&in, s);
+  release_stage(&io, s);
+  return rc;
+}
+
+}  // extern "C"
+
 // ---- EqualizeImage (enhance.c:2040) and EmbossImage (effect.c:1600: inline kernel + ConvolveImage + EqualizeImage) -----------
 extern "C" {
 

@@ -82,13 +82,6 @@ __device__ __forceinline__ double clamp_denominator(double den) {
   return den;
 }
 
-// v * m on lanes where `cond` holds, v elsewhere, as ONE predicated DMUL (the compiler's own lowering of the conditional
-// is a DMUL plus two 32-bit selects; the loop-invariant predicate is hoisted by ptxas).
-__device__ __forceinline__ double mul_if(double v, double m, int cond) {
-  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p mul.f64 %0, %0, %1;\n\t}" : "+d"(v) : "d"(m), "r"(cond));
-  return v;
-}
-
 // UnsharpMaskImage's point pass (effect.c:4358-4364) on the float-rounded blur value, in the reference's operation
 // order with unfused double arithmetic: bit-identical to running it as a separate pass.
 __device__ __forceinline__ float unsharp_point(float p, float blurred, double gain, double qthreshold) {
@@ -336,8 +329,8 @@ __global__ void __launch_bounds__(128, MINB) conv_row_kernel(const Conv1dArgs a,
 // colour components are scaled by r, the alpha component (odd lane, .y) is stored unscaled.
 __device__ __forceinline__ float2 finish_pair(bool odd, double sum0, double sum1, double gsum) {
   const double r = fast_reciprocal(clamp_denominator(gsum));
-  const double o1 = mul_if(sum1, r, !odd);      // the alpha component (odd lane, .y) is stored unscaled
-  return make_float2(static_cast<float>(sum0 * r), static_cast<float>(o1));
+  const double m1 = odd ? 1.0 : r;              // the alpha component (odd lane, .y) is stored unscaled
+  return make_float2(static_cast<float>(sum0 * r), static_cast<float>(sum1 * m1));
 }
 
 // ---- pair stream kernel, both axes.  A thread owns one component pair and walks along the
@@ -420,97 +413,88 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_kernel(const Conv1dArgs a
       epi[s] = __ldg(reinterpret_cast<const float2 *>(epi_base + static_cast<size_t>(r) * ostep));
     }
   }
-  // Issue slots, not the FP64 pipe alone, bound this loop: a step is 70 DFMA + 4 DMUL (2 issue cycles each on the half-rate
-  // pipe = 148 cycles per warp) and two warps per scheduler leave room for ~70 other instructions per step before the
-  // scheduler itself saturates; r01 issued ~50.  Hence:
-  //  * strips whose samples all lie inside the image (every strip but the first and the last of a line) run a loop
-  //    without index clamping: the load, L2-prefetch and store addresses advance by one 64-bit add each;
-  //  * an accumulator is (re)started by its first tap as a plain product instead of being zeroed and FMA-ed;
-  //  * the odd lanes' "multiply by one" is a predicated multiply instead of a 64-bit select.
-  outp -= static_cast<size_t>(NT - 1) * ostep;           // where output j = -(NT-1) would be; never dereferenced for j < 0
-  const bool inside = isrc0 >= 0 && isrc0 + total + PF + (L2PF ? a.seg_w : 0) <= limit;   // uniform over the CTA
-  auto run = [&](auto clamp_tag) {
-    constexpr bool CLAMP = decltype(clamp_tag)::value;
-    int isrc = isrc0 + PF;
-    const char *lp = base + static_cast<size_t>(CLAMP ? 0 : isrc) * step;          // next sample to fetch (CLAMP: unused)
-    const size_t pf_bytes = static_cast<size_t>(a.seg_w) * step;
-    int jb = -(NT - 1);                      // output index of step 0 of the current block
+  // r02 experiment (profiles/r02_devbench_blur_restructured.log): the SASS of this loop issues ~50 non-FP64 instructions
+  // per step next to 70 DFMA + 4 DMUL (2 issue cycles each on the half-rate pipe), i.e. with two warps per scheduler the
+  // ISSUE slots are ~85 % taken -- that, not the FP64 pipe alone, is what holds it at 78 % pipe utilisation.  A variant with
+  // an unclamped interior loop (pointer increments instead of clamp + 64-bit multiply per address), the first tap as a
+  // product instead of zero + FMA, and predicated instead of selected multiplies removed ~6 instructions per step but
+  // needed 255 registers (two loop bodies) and ran 0.852 ms against 0.780 ms; it was dropped.  (An FP64 mma.sync
+  // formulation would cut the issue count 8x, but the band structure wastes 17.5 % of every 8x4 Toeplitz tile and DMMA
+  // shares the DFMA pipe at the same FMA rate: at best +5 %.)
+  int isrc = isrc0 + PF;
+  int j = -(NT - 1);
 #pragma unroll 1
-    for (int mb = 0; mb < total; mb += PF, jb += PF) {       // PF unrolled steps, then rotate the accumulators by PF
+  for (int mb = 0; mb < total; mb += PF) {       // PF unrolled steps, then rotate the accumulators by PF
 #pragma unroll
-      for (int s = 0; s < PF; ++s) {
-        const InT vf = pre[s];
-        if (CLAMP) {
-          const unsigned ii = static_cast<unsigned>(min(max(isrc, 0), limit));
-          pre[s] = __ldg(reinterpret_cast<const InT *>(base + static_cast<size_t>(ii) * step));
-          if (L2PF) {             // L2 prefetch far ahead: the ring's LDGs then complete at L2 latency
-            const unsigned ip = static_cast<unsigned>(min(isrc + a.seg_w, limit));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + static_cast<size_t>(ip) * step));
-          }
-          ++isrc;
-        } else {
-          pre[s] = __ldg(reinterpret_cast<const InT *>(lp));
-          if (L2PF) asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + pf_bytes));
-          lp += step;
+    for (int s = 0; s < PF; ++s) {
+      const InT vf = pre[s];
+      {
+        const unsigned ii = static_cast<unsigned>(min(max(isrc, 0), limit));
+        pre[s] = __ldg(reinterpret_cast<const InT *>(base + static_cast<size_t>(ii) * step));
+        if (L2PF) {             // L2 prefetch far ahead: the ring's LDGs then complete at L2 latency
+          const unsigned ip = static_cast<unsigned>(min(isrc + a.seg_w, limit));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + static_cast<size_t>(ip) * step));
         }
-        // (premultiplying one step ahead, as the cp.async kernel does, costs this kernel 5 %: 220 registers)
-        double v0, v1;
-        if (IO == 2) {
-          v0 = vf.x; v1 = vf.y;                       // already premultiplied sums
-        } else {
-          const float af = __shfl_sync(0xffffffffu, static_cast<float>(vf.y), alpha_lane);
-          const double da = static_cast<double>(af);
-          v0 = static_cast<double>(vf.x) * da;
-          v1 = mul_if(static_cast<double>(vf.y), da, !odd);      // the alpha component itself is not premultiplied
-        }
-        if (PADDED && __any_sync(0xffffffffu, nonfinite_bits(vf.x) || nonfinite_bits(vf.y))) {
-#pragma unroll
-          for (int q = 0; q < NT; ++q) {
-            const int t = (s - q + NT) % NT;
-            if (t == 0) { acc0[q] = taps.k[0] * v0; acc1[q] = taps.k[0] * v1; }
-            else if (t < a.ntaps) { acc0[q] = fma(taps.k[t], v0, acc0[q]); acc1[q] = fma(taps.k[t], v1, acc1[q]); }
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < NT; ++q) {
-            const int t = (s - q + NT) % NT;
-            const double k = taps.k[t];
-            if (t == 0) { acc0[q] = k * v0; acc1[q] = k * v1; }        // first tap of a new output: no zeroing needed
-            else { acc0[q] = fma(k, v0, acc0[q]); acc1[q] = fma(k, v1, acc1[q]); }
-          }
-        }
-        const int qf = (s + 1) % NT;                 // this slot has just received its last tap
-        const double sum0 = acc0[qf], sum1 = acc1[qf];
-        const bool store = static_cast<unsigned>(jb + s) < static_cast<unsigned>(nout);
-        if (IO == 1) {
-          if (store) *reinterpret_cast<double2 *>(outp) = make_double2(sum0, sum1);
-        } else {
-          const double gsum = shfl_double(sum1, alpha_lane);
-          float2 out = finish_pair(odd, sum0, sum1, gsum);
-          if (EPI == 1) {            // source pixel of output j (prefetched), then refill the slot for output j + PF
-            const float2 p = epi[s];
-            const unsigned r = static_cast<unsigned>(min(max(first + jb + s + PF, 0), limit));
-            epi[s] = __ldg(reinterpret_cast<const float2 *>(epi_base + static_cast<size_t>(r) * ostep));
-            out.x = unsharp_point(p.x, out.x, a.gain, a.qthreshold);
-            out.y = unsharp_point(p.y, out.y, a.gain, a.qthreshold);
-          }
-          if (store) *reinterpret_cast<float2 *>(outp) = out;
-        }
-        outp += ostep;
+        ++isrc;
       }
-      if (PF != NT) {
-        double t0[PF], t1[PF];
-#pragma unroll
-        for (int q = 0; q < PF; ++q) { t0[q] = acc0[q]; t1[q] = acc1[q]; }
-#pragma unroll
-        for (int q = 0; q < NT - PF; ++q) { acc0[q] = acc0[q + PF]; acc1[q] = acc1[q + PF]; }
-#pragma unroll
-        for (int q = 0; q < PF; ++q) { acc0[NT - PF + q] = t0[q]; acc1[NT - PF + q] = t1[q]; }
+      // (premultiplying one step ahead, as the cp.async kernel does, costs this kernel 5 %: 220 registers)
+      double v0, v1;
+      if (IO == 2) {
+        v0 = vf.x; v1 = vf.y;                       // already premultiplied sums
+      } else {
+        const float af = __shfl_sync(0xffffffffu, static_cast<float>(vf.y), alpha_lane);
+        const double da = static_cast<double>(af);
+        v0 = static_cast<double>(vf.x) * da;
+        v1 = static_cast<double>(vf.y) * (odd ? 1.0 : da);
       }
+      if (PADDED && __any_sync(0xffffffffu, nonfinite_bits(vf.x) || nonfinite_bits(vf.y))) {
+#pragma unroll
+        for (int q = 0; q < NT; ++q) {
+          if ((s - q + NT) % NT < a.ntaps) {
+            const double k = taps.k[(s - q + NT) % NT];
+            acc0[q] = fma(k, v0, acc0[q]);
+            acc1[q] = fma(k, v1, acc1[q]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < NT; ++q) {
+          const double k = taps.k[(s - q + NT) % NT];
+          acc0[q] = fma(k, v0, acc0[q]);
+          acc1[q] = fma(k, v1, acc1[q]);
+        }
+      }
+      const int qf = (s + 1) % NT;
+      const double sum0 = acc0[qf], sum1 = acc1[qf];
+      acc0[qf] = 0.0;
+      acc1[qf] = 0.0;
+      if (IO == 1) {
+        if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<double2 *>(outp) = make_double2(sum0, sum1);
+      } else {
+        const double gsum = shfl_double(sum1, alpha_lane);
+        float2 out = finish_pair(odd, sum0, sum1, gsum);
+        if (EPI == 1) {            // source pixel of output j (prefetched), then refill the slot for output j + PF
+          const float2 p = epi[s];
+          const unsigned r = static_cast<unsigned>(min(max(first + j + PF, 0), limit));
+          epi[s] = __ldg(reinterpret_cast<const float2 *>(epi_base + static_cast<size_t>(r) * ostep));
+          out.x = unsharp_point(p.x, out.x, a.gain, a.qthreshold);
+          out.y = unsharp_point(p.y, out.y, a.gain, a.qthreshold);
+        }
+        if (static_cast<unsigned>(j) < static_cast<unsigned>(nout)) *reinterpret_cast<float2 *>(outp) = out;
+      }
+      if (j >= 0) outp += ostep;
+      ++j;
     }
-  };
-  if (inside) run(std::false_type{});
-  else run(std::true_type{});
+    if (PF != NT) {
+      double t0[PF], t1[PF];
+#pragma unroll
+      for (int q = 0; q < PF; ++q) { t0[q] = acc0[q]; t1[q] = acc1[q]; }
+#pragma unroll
+      for (int q = 0; q < NT - PF; ++q) { acc0[q] = acc0[q + PF]; acc1[q] = acc1[q + PF]; }
+#pragma unroll
+      for (int q = 0; q < PF; ++q) { acc0[NT - PF + q] = t0[q]; acc1[NT - PF + q] = t1[q]; }
+    }
+  }
 }
 
 // ---- pair stream kernel with a shared-memory prefetch ring (cp.async / LDGSTS), both axes.
@@ -666,7 +650,7 @@ __global__ void __launch_bounds__(128, MINB) conv_pair_async_kernel(const Conv1d
         const float af = __shfl_sync(0xffffffffu, vnext.y, alpha_lane);
         const double da = static_cast<double>(af);
         nv0 = static_cast<double>(vnext.x) * da;
-        nv1 = mul_if(static_cast<double>(vnext.y), da, !odd);
+        nv1 = static_cast<double>(vnext.y) * (odd ? 1.0 : da);
         if (PADDED) nbad = __any_sync(0xffffffffu, nonfinite_bits(vnext.x) || nonfinite_bits(vnext.y));
       }
       if (PADDED && bad) {

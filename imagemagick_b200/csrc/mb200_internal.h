@@ -98,6 +98,12 @@ int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to
 int launch_unsharp_combine(const float *src, float *blur_inout, size_t n, double gain,
                            double quantum_threshold, void *stream);
 
+// Copy-trait channels (a `-channel` selection): dst[c] = src[c] for the channels NOT in update_mask; the resize form takes
+// the nearest source sample of each axis (resize.c:3697-3707)
+int launch_restore_channels(float *dst, const float *src, size_t npixels, int channels, unsigned update_mask, void *stream);
+int launch_resize_copy_channels(float *dst, const float *src, size_t w, size_t ow, size_t oh, int channels, const int *d_nearest_x,
+                                const int *d_nearest_y, unsigned update_mask, void *stream);
+
 // CompositeImage(canvas, source, DifferenceCompositeOp) for same-size images (Edge/TopHat/BottomHat), in place on canvas
 int launch_composite_difference(float *canvas, const float *source, size_t npixels, int channels, void *stream);
 

@@ -235,6 +235,130 @@ __global__ void __launch_bounds__(256, 4) minmax2d_kernel(const Morph2dArgs a) {
   if (a.changed != nullptr && nchanged != 0) atomicAdd(a.changed, static_cast<unsigned long long>(nchanged));
 }
 
+// ---- dense 2-D convolution, register tiled (SharpenImage 11x11, EdgeImage, EmbossImage, DoG / LoG, user kernels) -------------
+// The generic kernel above spends, per kernel cell and output pixel, one tap load, one LDS.128 and four F2F conversions
+// for four FMAs: it sits on the conversion (XU) and shared-memory pipes, not on FP64.  Here
+//  * the source tile is converted to double and alpha-premultiplied ONCE while it is staged (v_c = A*p_c, v_alpha = A;
+//    plain p_c without alpha), so the inner loop has no conversions;
+//  * a thread owns R vertically adjacent outputs of one column: walking down a source column it loads each staged sample
+//    once (2 x LDS.128, lanes = consecutive pixels: conflict free) and feeds up to R x CH FMAs, the taps K[v][u] coming
+//    from shared memory as broadcast loads;
+//  * accumulation in FP64 (column-major over the window instead of the reference's row-major order: the usual <= 1 ULP
+//    argument of DESIGN.md section 4 applies), output stage as in morph2d_kernel (morphology.c:2962-2977, :3197).
+// Cells must all be finite (NaN = "not in the neighbourhood" kernels keep the compacted-cell kernel).
+// CTA = 32 x 8 threads, output tile 32 x (8*R); dynamic shared memory: taps + (8R+kh-1) x (32+kw-1) x CH doubles.
+template <int CH, int R>
+__global__ void __launch_bounds__(256) conv2d_dense_kernel(const Morph2dArgs a, const double *__restrict__ taps_window_order) {
+  extern __shared__ __align__(16) double dsm[];
+  constexpr bool kHasAlpha = (CH == 2 || CH == 4);
+  const int tw = 32 + a.kw - 1, th = 8 * R + a.kh - 1;
+  double *taps = dsm;                                        // kw*kh, window order
+  double *tile = dsm + ((a.kw * a.kh + 1) & ~1);             // 16-byte aligned
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * (8 * R);
+  const int wmax = a.width - 1, hmax = a.height - 1;
+  for (int i = tid; i < a.kw * a.kh; i += 256) taps[i] = taps_window_order[i];
+  for (int p = tid; p < tw * th; p += 256) {
+    const int ty = p / tw, tx = p - ty * tw;
+    const int sx = min(max(bx - a.ox + tx, 0), wmax), sy = min(max(by - a.oy + ty, 0), hmax);
+    const float *g = a.src + (static_cast<size_t>(sy) * a.width + sx) * CH;
+    double v[CH];
+    if (CH == 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4 *>(g));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[CH - 1] = t.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) v[c] = __ldg(g + c);
+    }
+    if (kHasAlpha) {
+#pragma unroll
+      for (int c = 0; c < CH - 1; ++c) v[c] *= v[CH - 1];
+    }
+    double *d = tile + static_cast<size_t>(p) * CH;
+    if (CH == 4) {
+      *reinterpret_cast<double2 *>(d) = make_double2(v[0], v[1]);
+      *reinterpret_cast<double2 *>(d + 2) = make_double2(v[2], v[CH - 1]);
+    } else if (CH == 2) {
+      *reinterpret_cast<double2 *>(d) = make_double2(v[0], v[CH - 1]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) d[c] = v[c];
+    }
+  }
+  __syncthreads();
+  double acc[R][CH];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[r][c] = 0.0;
+  const int y0 = threadIdx.y * R;                              // first of this thread's R output rows (tile coordinates)
+  const int span = R + a.kh - 1;                               // source rows that touch them
+  for (int u = 0; u < a.kw; ++u) {
+    const double *col = tile + (static_cast<size_t>(y0) * tw + threadIdx.x + u) * CH;
+    const double *kcol = taps + u;
+    for (int yy = 0; yy < span; ++yy) {
+      double v[CH];
+      const double *sp = col + static_cast<size_t>(yy) * tw * CH;
+      if (CH == 4) {
+        const double2 lo = *reinterpret_cast<const double2 *>(sp), hi = *reinterpret_cast<const double2 *>(sp + 2);
+        v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[CH - 1] = hi.y;
+      } else if (CH == 2) {
+        const double2 lo = *reinterpret_cast<const double2 *>(sp);
+        v[0] = lo.x; v[CH - 1] = lo.y;
+      } else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) v[c] = sp[c];
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int vv = yy - r;                                 // kernel row this sample has for output r
+        if (vv >= 0 && vv < a.kh) {
+          const double k = kcol[vv * a.kw];
+#pragma unroll
+          for (int c = 0; c < CH; ++c) acc[r][c] = fma(k, v[c], acc[r][c]);
+        }
+      }
+    }
+  }
+  const int x = bx + threadIdx.x;
+  unsigned nchanged = 0;
+  if (x < a.width) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int y = by + y0 + r;
+      if (y >= a.height) break;
+      float *out = a.dst + (static_cast<size_t>(y) * a.width + x) * CH;
+      const float *centre = a.src + (static_cast<size_t>(y) * a.width + x) * CH;
+      float o[CH];
+      if (kHasAlpha) {
+        const double g = precise_reciprocal_gamma(kQuantumScale * acc[r][CH - 1]) * a.gamma_scale;
+#pragma unroll
+        for (int c = 0; c < CH - 1; ++c) {
+          const double pixel = fma(kQuantumScale, acc[r][c], a.bias);
+          o[c] = static_cast<float>(g * pixel);
+          if (a.changed != nullptr) nchanged += fabs(pixel - static_cast<double>(__ldg(centre + c))) >= kEpsilon;
+        }
+        const double pixel = a.bias + acc[r][CH - 1];
+        o[CH - 1] = static_cast<float>(a.gamma_scale * pixel);
+        if (a.changed != nullptr) nchanged += fabs(pixel - static_cast<double>(__ldg(centre + CH - 1))) >= kEpsilon;
+      } else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const double pixel = a.bias + acc[r][c];
+          o[c] = static_cast<float>(a.gamma_scale * pixel);
+          if (a.changed != nullptr) nchanged += fabs(pixel - static_cast<double>(__ldg(centre + c))) >= kEpsilon;
+        }
+      }
+      if (CH == 4) *reinterpret_cast<float4 *>(out) = make_float4(o[0], o[1], o[2], o[CH - 1]);
+      else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) out[c] = o[c];
+      }
+    }
+  }
+  if (a.changed != nullptr && nchanged != 0) atomicAdd(a.changed, static_cast<unsigned long long>(nchanged));
+}
+
 }  // namespace
 
 int launch_morph2d(const float *src, float *dst, size_t width, size_t height, int channels, int method,
@@ -258,8 +382,62 @@ int launch_morph2d(const float *src, float *dst, size_t width, size_t height, in
       host[n].du = static_cast<short>(u); host[n].dv = static_cast<short>(v); host[n].pad = 0.f; host[n].k = k;
       ++n;
     }
+  if (method == MB200_ConvolveMorphology && n == total &&
+      ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    // every cell is part of the neighbourhood: register-tiled dense kernel (R = 4 output rows per thread, or 2 when the
+    // staged tile of doubles would not fit)
+    free(host);
+    auto tile_bytes = [&](int R) {
+      return (static_cast<size_t>((total + 1) & ~1) + static_cast<size_t>(32 + kw - 1) * (8 * R + kh - 1) * channels) * sizeof(double);
+    };
+    const int R = tile_bytes(4) <= 100 * 1024 ? 4 : (tile_bytes(2) <= 200 * 1024 ? 2 : 0);
+    if (R != 0) {
+      double *d_taps = nullptr;
+      cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&d_taps), sizeof(double) * static_cast<size_t>(total), temp_pool(), s);
+      if (e != cudaSuccess) return cuda_fail(e, "conv2d: tap table alloc");
+      e = cudaMemcpyAsync(d_taps, kernel_window_order, sizeof(double) * static_cast<size_t>(total), cudaMemcpyHostToDevice, s);
+      if (e != cudaSuccess) { cudaFreeAsync(d_taps, s); return cuda_fail(e, "conv2d: tap upload"); }
+      Morph2dArgs a{};
+      a.src = src; a.dst = dst;
+      a.width = static_cast<int>(width); a.height = static_cast<int>(height); a.channels = channels;
+      a.ox = ox; a.oy = oy; a.kw = kw; a.kh = kh; a.ncells = n;
+      a.bias = bias; a.gamma_scale = gamma_scale; a.method = method; a.changed = d_changed;
+      const size_t smem = tile_bytes(R);
+      dim3 grid((a.width + 31) / 32, (a.height + 8 * R - 1) / (8 * R)), block(32, 8);
+#define MB200_DENSE(CH, RR)                                                                                         \
+      do {                                                                                                          \
+        cudaFuncSetAttribute(conv2d_dense_kernel<CH, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+        conv2d_dense_kernel<CH, RR><<<grid, block, smem, s>>>(a, d_taps);                                           \
+      } while (0)
+      switch (channels * 10 + R) {
+        case 14: MB200_DENSE(1, 4); break;
+        case 12: MB200_DENSE(1, 2); break;
+        case 24: MB200_DENSE(2, 4); break;
+        case 22: MB200_DENSE(2, 2); break;
+        case 34: MB200_DENSE(3, 4); break;
+        case 32: MB200_DENSE(3, 2); break;
+        case 44: MB200_DENSE(4, 4); break;
+        default: MB200_DENSE(4, 2); break;
+      }
+#undef MB200_DENSE
+      count_launch();
+      e = cudaGetLastError();
+      cudaFreeAsync(d_taps, s);
+      if (e != cudaSuccess) return cuda_fail(e, "conv2d launch");
+      return MB200_OK;
+    }
+    host = static_cast<Cell *>(malloc(sizeof(Cell) * static_cast<size_t>(total)));      // too large: the compacted-cell kernel
+    if (!host) return fail(MB200_ENOMEM, "morph2d: host alloc");
+    n = 0;
+    for (int v = 0; v < kh; ++v)
+      for (int u = 0; u < kw; ++u) {
+        host[n].du = static_cast<short>(u); host[n].dv = static_cast<short>(v); host[n].pad = 0.f;
+        host[n].k = kernel_window_order[v * kw + u];
+        ++n;
+      }
+  }
   void *d_cells = nullptr;
-  cudaError_t e = cudaMallocAsync(&d_cells, sizeof(Cell) * static_cast<size_t>(total), s);   // stream-ordered: re-entrant
+  cudaError_t e = cudaMallocAsync(&d_cells, sizeof(Cell) * static_cast<size_t>(total), temp_pool(), s);   // stream-ordered: re-entrant
   if (e != cudaSuccess) { free(host); return cuda_fail(e, "morph2d: tap table alloc"); }
   e = cudaMemcpyAsync(d_cells, host, sizeof(Cell) * static_cast<size_t>(n), cudaMemcpyHostToDevice, s);
   free(host);   // pageable source: the copy has been staged when the call returns

@@ -332,6 +332,69 @@ int launch_threshold(float *buf, size_t npixels, int channels, int op, const dou
   return MB200_OK;
 }
 
+// Channels outside a `-channel` selection carry the Copy trait: every operator of the path hands them through from its
+// source (morphology.c:2733-2737, effect.c:4346-4350; resize.c:3697-3707 takes the NEAREST source sample of each pass).
+// The kernels compute all channels; these point passes put the Copy channels back.  update_mask bit c = channel c is updated.
+namespace {
+template <int CH>
+__global__ void __launch_bounds__(256) restore_channels_kernel(float *__restrict__ dst, const float *__restrict__ src, size_t npixels,
+                                                               unsigned update_mask) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= npixels) return;
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+    if (!(update_mask >> c & 1u)) dst[i * CH + c] = __ldg(src + i * CH + c);
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) resize_copy_channels_kernel(float *__restrict__ dst, const float *__restrict__ src, int w, int ow,
+                                                                   int oh, const int *__restrict__ nearest_x,
+                                                                   const int *__restrict__ nearest_y, unsigned update_mask) {
+  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+  if (x >= ow || y >= oh) return;
+  const size_t s = (static_cast<size_t>(__ldg(nearest_y + y)) * w + __ldg(nearest_x + x)) * CH;
+  const size_t d = (static_cast<size_t>(y) * ow + x) * CH;
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+    if (!(update_mask >> c & 1u)) dst[d + c] = __ldg(src + s + c);
+}
+}  // namespace
+
+int launch_restore_channels(float *dst, const float *src, size_t npixels, int channels, unsigned update_mask, void *stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t blocks = (npixels + 255) / 256;
+  if (blocks == 0 || blocks > 0x7fffffffull) return fail(MB200_EINVAL, "restore channels: bad image size");
+  const unsigned grid = static_cast<unsigned>(blocks);
+  switch (channels) {
+    case 1: restore_channels_kernel<1><<<grid, 256, 0, s>>>(dst, src, npixels, update_mask); break;
+    case 2: restore_channels_kernel<2><<<grid, 256, 0, s>>>(dst, src, npixels, update_mask); break;
+    case 3: restore_channels_kernel<3><<<grid, 256, 0, s>>>(dst, src, npixels, update_mask); break;
+    case 4: restore_channels_kernel<4><<<grid, 256, 0, s>>>(dst, src, npixels, update_mask); break;
+    default: return fail(MB200_EINVAL, "restore channels: 1..4 channels");
+  }
+  count_launch();
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MB200_OK : cuda_fail(e, "restore channels launch");
+}
+
+int launch_resize_copy_channels(float *dst, const float *src, size_t w, size_t ow, size_t oh, int channels, const int *d_nearest_x,
+                                const int *d_nearest_y, unsigned update_mask, void *stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (oh > 65535) return fail(MB200_EUNSUPPORTED, "resize copy channels: more than 65535 output rows");
+  dim3 grid(static_cast<unsigned>((ow + 255) / 256), static_cast<unsigned>(oh));
+  const int W = static_cast<int>(w), OW = static_cast<int>(ow), OH = static_cast<int>(oh);
+  switch (channels) {
+    case 1: resize_copy_channels_kernel<1><<<grid, 256, 0, s>>>(dst, src, W, OW, OH, d_nearest_x, d_nearest_y, update_mask); break;
+    case 2: resize_copy_channels_kernel<2><<<grid, 256, 0, s>>>(dst, src, W, OW, OH, d_nearest_x, d_nearest_y, update_mask); break;
+    case 3: resize_copy_channels_kernel<3><<<grid, 256, 0, s>>>(dst, src, W, OW, OH, d_nearest_x, d_nearest_y, update_mask); break;
+    case 4: resize_copy_channels_kernel<4><<<grid, 256, 0, s>>>(dst, src, W, OW, OH, d_nearest_x, d_nearest_y, update_mask); break;
+    default: return fail(MB200_EINVAL, "resize copy channels: 1..4 channels");
+  }
+  count_launch();
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MB200_OK : cuda_fail(e, "resize copy channels launch");
+}
+
 int launch_unsharp_combine(const float *src, float *blur_inout, size_t n, double gain, double quantum_threshold,
                            void *stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -267,4 +267,22 @@ long mb200_resize_contributions(int filter, size_t in_n, size_t out_n, double fa
   return need;
 }
 
+// The source sample a Copy-trait channel takes for every output of one axis (resize.c:3697-3707):
+// j = (ssize_t) (min(max(bisect, start), stop - 1) + 0.5), with bisect / start / stop as in the contribution list.
+int mb200_resize_nearest(int filter, size_t in_n, size_t out_n, double factor, long *nearest) {
+  ResizeFilter rf(filter);
+  if (!rf.valid) return mb200::fail(MB200_EUNSUPPORTED, "resize filter %d is not supported on the 1-D GPU path", filter);
+  if (in_n == 0 || out_n == 0 || !(factor > 0.0) || !nearest) return mb200::fail(MB200_EINVAL, "bad resize geometry");
+  double scale = std::fmax(1.0 / factor + kEps, 1.0);
+  double support = scale * rf.practical_support();
+  if (support < 0.5) support = 0.5;
+  for (size_t o = 0; o < out_n; ++o) {
+    const double bisect = static_cast<double>(o + 0.5) / factor + kEps;
+    const long first = static_cast<long>(std::fmax(bisect - support + 0.5, 0.0));
+    const long last = static_cast<long>(std::fmin(bisect + support + 0.5, static_cast<double>(in_n)));
+    nearest[o] = static_cast<long>(std::fmin(std::fmax(bisect, static_cast<double>(first)), static_cast<double>(last) - 1.0) + 0.5);
+  }
+  return MB200_OK;
+}
+
 }  // extern "C"

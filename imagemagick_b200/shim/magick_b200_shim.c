@@ -21,6 +21,7 @@
 */
 #include "MagickCore/studio.h"
 #include "MagickCore/MagickCore.h"
+#include "MagickCore/string-private.h"          /* StringToDoubleInterval (convolve:bias, morphology.c:4163) */
 #include "magick_b200.h"
 #include <string.h>
 
@@ -29,7 +30,9 @@
 #endif
 
 /* ---- eligibility: mirrors checkAccelerateCondition (accelerate.c:110-170) + SURVEY 8b --------- */
-static int b200_channels(const Image *image)
+/* update_mask == NULL: every channel must carry its default traits (no `-channel` selection).  Otherwise unselected
+   channels (Copy trait, pixel.c:6338-6393 SetPixelChannelMask) are accepted and reported: bit c set = channel c is updated. */
+static int b200_channels_masked(const Image *image, unsigned *update_mask)
 {
   const size_t n = GetPixelChannels(image);
   const MagickBooleanType gray = (image->colorspace == GRAYColorspace) ||
@@ -43,14 +46,19 @@ static int b200_channels(const Image *image)
   if (n < 1 || n > 4) return 0;
   if (GetPixelChannelOffset(image, RedPixelChannel) != 0) return 0;
   {
-    /* every channel must carry the default traits (no -channel restriction, pixel.c:6356-6381) */
+    /* default traits (pixel.c:6356-6381), or Copy for the channels a -channel selection leaves out */
     ssize_t i;
+    unsigned mask = 0;
     for (i = 0; i < (ssize_t) n; i++) {
       PixelChannel ch = GetPixelChannelChannel(image, i);
       PixelTrait want = (ch == AlphaPixelChannel || image->alpha_trait == UndefinedPixelTrait)
         ? UpdatePixelTrait : (PixelTrait) (UpdatePixelTrait | BlendPixelTrait);
-      if (GetPixelChannelTraits(image, ch) != want) return 0;
+      const PixelTrait have = GetPixelChannelTraits(image, ch);
+      if (have == want) mask |= 1u << i;
+      else if (have != CopyPixelTrait || update_mask == (unsigned *) NULL) return 0;
     }
+    if (update_mask != (unsigned *) NULL) *update_mask = mask;
+    if (mask == 0) return 0;                       /* nothing to compute: let the CPU path clone */
   }
   if (gray != MagickFalse) {
     if (n == 1 && image->alpha_trait == UndefinedPixelTrait) return 1;
@@ -67,6 +75,8 @@ static int b200_channels(const Image *image)
   return 0;
 }
 
+static int b200_channels(const Image *image) { return b200_channels_masked(image, (unsigned *) NULL); }
+
 static MagickBooleanType has_artifact(const Image *image, const char *const *names)
 {
   for (; *names != (const char *) NULL; names++)
@@ -76,6 +86,10 @@ static MagickBooleanType has_artifact(const Image *image, const char *const *nam
 
 static const char *const morphology_artifacts[] = { "convolve:bias", "convolve:scale",
   "morphology:compose", "morphology:showKernel", "debug", (const char *) NULL };
+/* MorphologyImage itself restates convolve:bias / convolve:scale (B200AccelerateMorphologyImage); the others change the
+   control flow (kernel-list merging, stderr output) */
+static const char *const morphology_control_artifacts[] = { "morphology:compose", "morphology:showKernel", "debug",
+  (const char *) NULL };
 static const char *const compose_artifacts[] = { "compose:clamp", "compose:sync", "compose:args",
   "compose:outside-overlay", "compose:clip-to-self", (const char *) NULL };
 static const char *const filter_artifacts[] = { "filter:filter", "filter:window", "filter:sigma",
@@ -117,11 +131,13 @@ static float *b200_cache_pixels(const Image *image, int channels, ExceptionInfo 
 
 typedef int (*same_size_op)(const float *, float *, size_t, size_t, int, const void *);
 
-/* src pixels -> new image through `op`; NULL == declined (caller falls back to the CPU). */
-static Image *run_same_size(const Image *image, same_size_op op, const void *args,
-                            ExceptionInfo *exception)
+/* src pixels -> new image through `op`; NULL == declined (caller falls back to the CPU).  allow_mask: the operator hands
+   Copy-trait channels through from its source, so a -channel selection is served by one extra point pass. */
+static Image *run_same_size_masked(const Image *image, same_size_op op, const void *args, int allow_mask,
+                                   ExceptionInfo *exception)
 {
-  const int ch = b200_channels(image);
+  unsigned update_mask = 0xfu;
+  const int ch = allow_mask ? b200_channels_masked(image, &update_mask) : b200_channels(image);
   const float *p;
   Quantum *q;
   Image *out;
@@ -136,6 +152,8 @@ static Image *run_same_size(const Image *image, same_size_op op, const void *arg
       q = GetAuthenticPixels(out, 0, 0, out->columns, out->rows, attempt);
       if (q == (Quantum *) NULL || b200_cache_pixels(out, ch, attempt) != (float *) q ||
           op(p, (float *) q, image->columns, image->rows, ch, args) != MB200_OK ||
+          ((update_mask & ((1u << ch) - 1u)) != ((1u << ch) - 1u) &&
+           mb200_restore_channels((float *) q, p, image->columns, image->rows, ch, update_mask) != MB200_OK) ||
           SyncAuthenticPixels(out, attempt) == MagickFalse)
         out = DestroyImage(out);
     }
@@ -144,6 +162,9 @@ static Image *run_same_size(const Image *image, same_size_op op, const void *arg
   if (out != (Image *) NULL) out->type = image->type;
   return out;
 }
+
+static Image *run_same_size(const Image *image, same_size_op op, const void *args, ExceptionInfo *exception)
+{ return run_same_size_masked(image, op, args, 0, exception); }
 
 /* ---- BlurImage / GaussianBlurImage / UnsharpMaskImage ------------------------------------------ */
 typedef struct { double radius, sigma, gain, threshold; } blur_args;
@@ -160,7 +181,7 @@ Image *B200AccelerateBlurImage(const Image *image, const double radius, const do
 {
   blur_args a = { radius, sigma, 0.0, 0.0 };
   if (has_artifact(image, morphology_artifacts) != MagickFalse) return (Image *) NULL;
-  return run_same_size(image, op_blur, &a, exception);
+  return run_same_size_masked(image, op_blur, &a, 1, exception);
 }
 
 Image *B200AccelerateGaussianBlurImage(const Image *image, const double radius, const double sigma,
@@ -168,7 +189,7 @@ Image *B200AccelerateGaussianBlurImage(const Image *image, const double radius, 
 {
   blur_args a = { radius, sigma, 0.0, 0.0 };
   if (has_artifact(image, morphology_artifacts) != MagickFalse) return (Image *) NULL;
-  return run_same_size(image, op_gaussian, &a, exception);
+  return run_same_size_masked(image, op_gaussian, &a, 1, exception);
 }
 
 Image *B200AccelerateUnsharpMaskImage(const Image *image, const double radius, const double sigma,
@@ -176,7 +197,7 @@ Image *B200AccelerateUnsharpMaskImage(const Image *image, const double radius, c
 {
   blur_args a = { radius, sigma, gain, threshold };
   if (has_artifact(image, morphology_artifacts) != MagickFalse) return (Image *) NULL;
-  return run_same_size(image, op_unsharp, &a, exception);
+  return run_same_size_masked(image, op_unsharp, &a, 1, exception);
 }
 
 /* ---- MorphologyImage / ConvolveImage --------------------------------------------------------------- */
@@ -192,7 +213,7 @@ static int map_kernel_type(KernelInfoType t)
   }
 }
 
-typedef struct { int method; long iterations; const KernelInfo *kernel; } morph_args;
+typedef struct { int method; long iterations; const KernelInfo *kernel; double bias; } morph_args;
 static int op_morphology(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
 {
   const morph_args *m = (const morph_args *) a;
@@ -213,7 +234,7 @@ static int op_morphology(const float *s, float *d, size_t w, size_t h, int ch, c
     n++;
   }
   if (n == 0) return MB200_EINVAL;
-  rc = mb200_morphology_image(s, d, w, h, ch, m->method, m->iterations, &nodes[0], 0.0);
+  rc = mb200_morphology_image(s, d, w, h, ch, m->method, m->iterations, &nodes[0], m->bias);
   return rc;
 }
 
@@ -222,27 +243,50 @@ Image *B200AccelerateMorphologyImage(const Image *image, const MorphologyMethod 
                                      ExceptionInfo *exception)
 {
   morph_args a;
+  KernelInfo *scaled = (KernelInfo *) NULL;
+  Image *out;
+  int allow_mask = 1;
+  const char *artifact;
   if (kernel == (const KernelInfo *) NULL || iterations == 0) return (Image *) NULL;
-  if (has_artifact(image, morphology_artifacts) != MagickFalse) return (Image *) NULL;
+  if (has_artifact(image, morphology_control_artifacts) != MagickFalse) return (Image *) NULL;
+  a.bias = 0.0;
   switch (method) {
-    case ConvolveMorphology: case CorrelateMorphology: case ErodeMorphology: case DilateMorphology:
-    case OpenMorphology: case CloseMorphology: case SmoothMorphology: break;
+    case ConvolveMorphology: case CorrelateMorphology:
+      /* convolve:bias / convolve:scale apply to these two methods only (morphology.c:4156-4183) */
+      artifact = GetImageArtifact(image, "convolve:bias");
+      if (artifact != (const char *) NULL) {
+        if (IsGeometry(artifact) == MagickFalse) return (Image *) NULL;      /* the reference warns: let it */
+        a.bias = StringToDoubleInterval(artifact, (double) QuantumRange + 1.0);
+      }
+      artifact = GetImageArtifact(image, "convolve:scale");
+      if (artifact != (const char *) NULL) {
+        if (IsGeometry(artifact) == MagickFalse) return (Image *) NULL;
+        scaled = CloneKernelInfo(kernel);
+        if (scaled == (KernelInfo *) NULL) return (Image *) NULL;
+        ScaleGeometryKernelInfo(scaled, artifact);
+      }
+      break;
+    case ErodeMorphology: case DilateMorphology: case OpenMorphology: case CloseMorphology: case SmoothMorphology: break;
     case EdgeInMorphology: case EdgeOutMorphology: case EdgeMorphology: case TopHatMorphology:
     case BottomHatMorphology:                /* end in CompositeImage(Difference), morphology.c:3995-4012 */
       if (kernel->next != (KernelInfo *) NULL) return (Image *) NULL;
       if (has_artifact(image, compose_artifacts) != MagickFalse) return (Image *) NULL;
+      allow_mask = 0;                        /* the composite step treats a channel selection on its own terms */
       break;
     default: return (Image *) NULL;          /* sequential / intensity primitives: CPU */
   }
-  a.method = (int) method; a.iterations = (long) iterations; a.kernel = kernel;
-  return run_same_size(image, op_morphology, &a, exception);
+  a.method = (int) method; a.iterations = (long) iterations; a.kernel = scaled != (KernelInfo *) NULL ? scaled : kernel;
+  out = run_same_size_masked(image, op_morphology, &a, allow_mask, exception);
+  if (scaled != (KernelInfo *) NULL) scaled = DestroyKernelInfo(scaled);
+  return out;
 }
 
 /* ---- ResizeImage -------------------------------------------------------------------------------------- */
 Image *B200AccelerateResizeImage(const Image *image, const size_t columns, const size_t rows,
                                  const FilterType filter, ExceptionInfo *exception)
 {
-  const int ch = b200_channels(image);
+  unsigned update_mask = 0xfu;
+  const int ch = b200_channels_masked(image, &update_mask);
   const float *p;
   Quantum *q;
   Image *out;
@@ -259,6 +303,9 @@ Image *B200AccelerateResizeImage(const Image *image, const size_t columns, const
       q = GetAuthenticPixels(out, 0, 0, columns, rows, attempt);
       if (q == (Quantum *) NULL || b200_cache_pixels(out, ch, attempt) != (float *) q ||
           mb200_resize_image(p, image->columns, image->rows, ch, (float *) q, columns, rows, (int) filter) != MB200_OK ||
+          ((update_mask & ((1u << ch) - 1u)) != ((1u << ch) - 1u) &&
+           mb200_resize_copy_channels(p, image->columns, image->rows, ch, (float *) q, columns, rows, (int) filter,
+                                      update_mask) != MB200_OK) ||
           SyncAuthenticPixels(out, attempt) == MagickFalse)
         out = DestroyImage(out);
     }
@@ -417,7 +464,7 @@ Image *B200AccelerateSharpenImage(const Image *image, const double radius, const
   blur_args a;
   if (has_artifact(image, morphology_artifacts) != MagickFalse) return (Image *) NULL;
   a.radius = radius; a.sigma = sigma; a.gain = 0.0; a.threshold = 0.0;
-  return run_same_size(image, op_sharpen, &a, exception);
+  return run_same_size_masked(image, op_sharpen, &a, 1, exception);
 }
 
 Image *B200AccelerateEdgeImage(const Image *image, const double radius, ExceptionInfo *exception)
@@ -425,7 +472,7 @@ Image *B200AccelerateEdgeImage(const Image *image, const double radius, Exceptio
   blur_args a;
   if (has_artifact(image, morphology_artifacts) != MagickFalse) return (Image *) NULL;
   a.radius = radius; a.sigma = 0.0; a.gain = 0.0; a.threshold = 0.0;
-  return run_same_size(image, op_edge, &a, exception);
+  return run_same_size_masked(image, op_edge, &a, 1, exception);
 }
 
 /* ---- EqualizeImage (enhance.c:2040; the reference's hook is AccelerateEqualizeImage) and EmbossImage (effect.c:1600) ----- */

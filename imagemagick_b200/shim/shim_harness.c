@@ -23,6 +23,7 @@ extern Image *__real_SampleImage(const Image *, const size_t, const size_t, Exce
 extern Image *__real_ThumbnailImage(const Image *, const size_t, const size_t, ExceptionInfo *);
 extern Image *__real_MinifyImage(const Image *, ExceptionInfo *);
 extern Image *__real_MotionBlurImage(const Image *, const double, const double, const double, ExceptionInfo *);
+extern Image *__real_ConvolveImage(const Image *, const KernelInfo *, ExceptionInfo *);
 extern Image *__real_ResampleImage(const Image *, const double, const double, const FilterType, ExceptionInfo *);
 extern int mb200_device_count(void);
 extern Image *__real_SharpenImage(const Image *, const double, const double, ExceptionInfo *);
@@ -189,6 +190,42 @@ int main(void)
     }
   }
   {
+    /* -channel selections: unselected channels carry the Copy trait and are handed through (nearest sample for resize) */
+    const long hits0 = B200ShimHits();
+    KernelInfo *uk = AcquireKernelInfo("3x3: 1,2,1, 2,4,2, 1,2,1", ex);
+    (void) SetPixelChannelMask(rgba, (ChannelType) (RedChannel | BlueChannel));
+    CHECK("BlurImage(0,2) -channel RB RGBA", 1, BlurImage(rgba, 0.0, 2.0, ex), CPU(__real_BlurImage(rgba, 0.0, 2.0, ex)));
+    CHECK("ResizeImage Lanczos -channel RB RGBA", 1, ResizeImage(rgba, 258, 194, LanczosFilter, ex), CPU(__real_ResizeImage(rgba, 258, 194, LanczosFilter, ex)));
+    CHECK("UnsharpMaskImage -channel RB RGBA", 1, UnsharpMaskImage(rgba, 0.0, 2.0, 1.5, 0.02, ex), CPU(__real_UnsharpMaskImage(rgba, 0.0, 2.0, 1.5, 0.02, ex)));
+    (void) SetPixelChannelMask(rgba, (ChannelType) (AlphaChannel | GreenChannel));
+    CHECK("MorphologyImage Dilate -channel GA", 0, MorphologyImage(rgba, DilateMorphology, 1, uk, ex), CPU(__real_MorphologyImage(rgba, DilateMorphology, 1, uk, ex)));
+    CHECK("ResizeImage up -channel GA RGBA", 1, ResizeImage(rgba, 700, 500, MitchellFilter, ex), CPU(__real_ResizeImage(rgba, 700, 500, MitchellFilter, ex)));
+    (void) SetPixelChannelMask(rgba, DefaultChannels);
+    if (mb200_device_count() > 0 && B200ShimHits() - hits0 < 5) { printf("FAIL: channel selections did not reach the GPU path\n"); failures++; }
+    /* convolve:bias / convolve:scale (morphology.c:4156-4183) are restated by the wrapper */
+    (void) SetImageArtifact(rgb, "convolve:bias", "10%");
+    (void) SetImageArtifact(rgb, "convolve:scale", "0.05,20%");
+    CHECK("ConvolveImage bias 10% scale 0.05,20% RGB", 1, ConvolveImage(rgb, uk, ex), CPU(__real_ConvolveImage(rgb, uk, ex)));
+    (void) DeleteImageArtifact(rgb, "convolve:bias");
+    (void) DeleteImageArtifact(rgb, "convolve:scale");
+    if (mb200_device_count() > 0 && B200ShimHits() - hits0 < 6) { printf("FAIL: convolve artifacts did not reach the GPU path\n"); failures++; }
+    uk = DestroyKernelInfo(uk);
+  }
+  {
+    /* `-channel RGB -threshold` on an opaque RGB image leaves every trait at its default, but the reference
+       then thresholds each channel on its own value -- the intensity-driven kernel must decline */
+    const long fb = B200ShimFallbacks();
+    (void) SetPixelChannelMask(rgb, (ChannelType) (RedChannel | GreenChannel | BlueChannel));
+    a = CloneImage(rgb, 0, 0, MagickTrue, ex); b = CloneImage(rgb, 0, 0, MagickTrue, ex);
+    (void) SetPixelChannelMask(a, (ChannelType) (RedChannel | GreenChannel | BlueChannel));
+    (void) SetPixelChannelMask(b, (ChannelType) (RedChannel | GreenChannel | BlueChannel));
+    if (BilevelImage(a, 30000.0, ex) == MagickFalse) failures++;
+    B200ShimEnable(0); (void) __real_BilevelImage(b, 30000.0, ex); B200ShimEnable(1);
+    CHECK("BilevelImage -channel RGB (declines)", 0, a, b);
+    if (mb200_device_count() > 0 && B200ShimFallbacks() <= fb) { printf("FAIL: per-channel threshold was not declined\n"); failures++; }
+    (void) SetPixelChannelMask(rgb, DefaultChannels);
+  }
+  {
     /* a declined case must silently take the CPU path: tiled virtual pixels are not eligible */
     long fb = B200ShimFallbacks();
     Image *t = CloneImage(rgb, 0, 0, MagickTrue, ex);
@@ -199,7 +236,7 @@ int main(void)
     t = DestroyImage(t);
   }
   printf("gpu hits %ld, cpu fallbacks %ld\n", B200ShimHits(), B200ShimFallbacks());
-  if (mb200_device_count() > 0 && B200ShimHits() < 24) { printf("FAIL: operators did not reach the GPU path\n"); failures++; }
+  if (mb200_device_count() > 0 && B200ShimHits() < 30) { printf("FAIL: operators did not reach the GPU path\n"); failures++; }
   rgba = DestroyImage(rgba); rgb = DestroyImage(rgb);
   ex = DestroyExceptionInfo(ex);
   MagickCoreTerminus();

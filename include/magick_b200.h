@@ -328,6 +328,17 @@ MB200_API int mb200_white_threshold_image_dev(float *buf, size_t width, size_t h
 /* ClampImage (:1087): ClampPixel on every channel (HDRI: below 0 -> 0, >= QuantumRange -> QuantumRange). */
 MB200_API int mb200_clamp_image_dev(float *buf, size_t width, size_t height, int channels, void *stream);
 
+/* Copy-trait channels.  With a `-channel` selection the reference hands the unselected channels through from the
+   operator's source (MagickCore/morphology.c:2733-2737, effect.c:4346-4350); ResizeImage takes the nearest source sample
+   of each pass (resize.c:3697-3707).  The operators above compute every channel; these point passes put the Copy channels
+   back into `dst` (bit c of update_mask set = channel c is updated by the operator).  Valid for the operators whose
+   selected channels do not depend on the selection: Blur, GaussianBlur, Convolve, the non-difference morphology methods,
+   UnsharpMask, Sharpen, Edge and Resize. */
+MB200_API int mb200_restore_channels_dev(float *dst, const float *src, size_t width, size_t height, int channels,
+    unsigned update_mask, void *stream);
+MB200_API int mb200_resize_copy_channels_dev(const float *src, size_t width, size_t height, int channels, float *dst,
+    size_t out_width, size_t out_height, int filter, unsigned update_mask, void *stream);
+
 /* ---------------------------------------------- host-buffer operators ---- */
 /* Same operators on HOST buffers: stage into HBM, run, copy back, synchronise.
    These are what the MagickCore shim calls with the pixel-cache pointers
@@ -348,6 +359,10 @@ MB200_API int mb200_edge_image(const float *src, float *dst, size_t width, size_
     double radius);
 MB200_API int mb200_motion_blur_image(const float *src, float *dst, size_t width, size_t height, int channels,
     double radius, double sigma, double angle);
+MB200_API int mb200_restore_channels(float *dst, const float *src, size_t width, size_t height, int channels,
+    unsigned update_mask);
+MB200_API int mb200_resize_copy_channels(const float *src, size_t width, size_t height, int channels, float *dst,
+    size_t out_width, size_t out_height, int filter, unsigned update_mask);
 MB200_API int mb200_statistic_image(const float *src, float *dst, size_t width, size_t height, int channels, int type,
     size_t window_width, size_t window_height);
 MB200_API int mb200_rotational_blur_image(const float *src, float *dst, size_t width, size_t height, int channels,
