@@ -67,18 +67,17 @@ __device__ __forceinline__ bool nonfinite_bits(double v) {
   return (static_cast<unsigned>(__double2hiint(v)) & 0x7ff00000u) == 0x7ff00000u;
 }
 
-// |den| < MagickEpsilon / QuantumScale, decided exactly on the 64-bit pattern (positive doubles order like their
-// bits) with integer instructions: the FP64 pipe is the bottleneck of these kernels, a DSETP would cost issue time.
-// This is PerceptibleReciprocal's test (pixel-accessor.h:242-254) applied to gamma = QS * den.
+// PerceptibleReciprocal's clamp (pixel-accessor.h:242-254: 1/x if |x| >= MagickEpsilon else sign/MagickEpsilon) applied
+// to gamma = QS * den, i.e. |den| is raised to MagickEpsilon / QuantumScale, exactly.
 __device__ __forceinline__ double clamp_denominator(double den) {
+  // |den| < eps/QS decided exactly as ONE 64-bit unsigned comparison of the magnitude bits (positive doubles order like
+  // their bit patterns): ISETP + ISETP.EX, then two selects -- one instruction more than r01's high-word-only test.
   constexpr double kTiny = kEpsilon / kQuantumScale;           // 6.5535e-8
   const unsigned hi = static_cast<unsigned>(__double2hiint(den));
-  const unsigned habs = hi & 0x7fffffffu;
-  const unsigned th = static_cast<unsigned>(__double2hiint(kTiny)), tl = static_cast<unsigned>(__double2loint(kTiny));
-  if (__builtin_expect(habs <= th, 0)) {                       // rare: (almost) fully transparent neighbourhood
-    const unsigned lo = static_cast<unsigned>(__double2loint(den));
-    if (habs < th || lo < tl) den = __hiloint2double(static_cast<int>((hi & 0x80000000u) | th), static_cast<int>(tl));
-  }
+  const unsigned long long mag = (static_cast<unsigned long long>(hi & 0x7fffffffu) << 32) | static_cast<unsigned>(__double2loint(den));
+  const unsigned long long tiny = static_cast<unsigned long long>(__double_as_longlong(kTiny));
+  if (mag < tiny)
+    den = __hiloint2double(static_cast<int>((hi & 0x80000000u) | static_cast<unsigned>(tiny >> 32)), static_cast<int>(tiny & 0xffffffffu));
   return den;
 }
 

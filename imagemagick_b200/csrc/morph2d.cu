@@ -252,13 +252,18 @@ __global__ void __launch_bounds__(256) conv2d_dense_kernel(const Morph2dArgs a, 
   extern __shared__ __align__(16) double dsm[];
   constexpr bool kHasAlpha = (CH == 2 || CH == 4);
   const int tw = 32 + a.kw - 1, th = 8 * R + a.kh - 1;
+  const int npix = tw * th;
   double *taps = dsm;                                        // kw*kh, window order
   double *tile = dsm + ((a.kw * a.kh + 1) & ~1);             // 16-byte aligned
+  // RGBA: two planes of double2 -- (c0, c1) and (c2, alpha) -- so that consecutive lanes (= consecutive pixels) read
+  // consecutive 16-byte words: conflict-free LDS.128 (one 32-byte pixel record per lane is a 2-way conflict: ncu showed
+  // 41 % of the wavefronts conflicting and 6 short-scoreboard stalls per instruction).  Other layouts: pixel-interleaved.
+  double *plane1 = tile + static_cast<size_t>(npix) * 2;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int bx = blockIdx.x * 32, by = blockIdx.y * (8 * R);
   const int wmax = a.width - 1, hmax = a.height - 1;
   for (int i = tid; i < a.kw * a.kh; i += 256) taps[i] = taps_window_order[i];
-  for (int p = tid; p < tw * th; p += 256) {
+  for (int p = tid; p < npix; p += 256) {
     const int ty = p / tw, tx = p - ty * tw;
     const int sx = min(max(bx - a.ox + tx, 0), wmax), sy = min(max(by - a.oy + ty, 0), hmax);
     const float *g = a.src + (static_cast<size_t>(sy) * a.width + sx) * CH;
@@ -274,15 +279,14 @@ __global__ void __launch_bounds__(256) conv2d_dense_kernel(const Morph2dArgs a, 
 #pragma unroll
       for (int c = 0; c < CH - 1; ++c) v[c] *= v[CH - 1];
     }
-    double *d = tile + static_cast<size_t>(p) * CH;
     if (CH == 4) {
-      *reinterpret_cast<double2 *>(d) = make_double2(v[0], v[1]);
-      *reinterpret_cast<double2 *>(d + 2) = make_double2(v[2], v[CH - 1]);
+      reinterpret_cast<double2 *>(tile)[p] = make_double2(v[0], v[1]);
+      reinterpret_cast<double2 *>(plane1)[p] = make_double2(v[2], v[CH - 1]);
     } else if (CH == 2) {
-      *reinterpret_cast<double2 *>(d) = make_double2(v[0], v[CH - 1]);
+      reinterpret_cast<double2 *>(tile)[p] = make_double2(v[0], v[CH - 1]);
     } else {
 #pragma unroll
-      for (int c = 0; c < CH; ++c) d[c] = v[c];
+      for (int c = 0; c < CH; ++c) tile[static_cast<size_t>(p) * CH + c] = v[c];
     }
   }
   __syncthreads();
@@ -294,28 +298,34 @@ __global__ void __launch_bounds__(256) conv2d_dense_kernel(const Morph2dArgs a, 
   const int y0 = threadIdx.y * R;                              // first of this thread's R output rows (tile coordinates)
   const int span = R + a.kh - 1;                               // source rows that touch them
   for (int u = 0; u < a.kw; ++u) {
-    const double *col = tile + (static_cast<size_t>(y0) * tw + threadIdx.x + u) * CH;
+    const int p0 = y0 * tw + threadIdx.x + u;                  // first sample of this source column
     const double *kcol = taps + u;
+    // k[r] = K[yy - r][u]: the tap the sample of source row yy has for output r; one new tap per row, the rest shifts
+    double k[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) k[r] = 0.0;
     for (int yy = 0; yy < span; ++yy) {
+#pragma unroll
+      for (int r = R - 1; r > 0; --r) k[r] = k[r - 1];
+      k[0] = yy < a.kh ? kcol[yy * a.kw] : 0.0;
+      const int p = p0 + yy * tw;
       double v[CH];
-      const double *sp = col + static_cast<size_t>(yy) * tw * CH;
       if (CH == 4) {
-        const double2 lo = *reinterpret_cast<const double2 *>(sp), hi = *reinterpret_cast<const double2 *>(sp + 2);
+        const double2 lo = reinterpret_cast<const double2 *>(tile)[p], hi = reinterpret_cast<const double2 *>(plane1)[p];
         v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[CH - 1] = hi.y;
       } else if (CH == 2) {
-        const double2 lo = *reinterpret_cast<const double2 *>(sp);
+        const double2 lo = reinterpret_cast<const double2 *>(tile)[p];
         v[0] = lo.x; v[CH - 1] = lo.y;
       } else {
 #pragma unroll
-        for (int c = 0; c < CH; ++c) v[c] = sp[c];
+        for (int c = 0; c < CH; ++c) v[c] = tile[static_cast<size_t>(p) * CH + c];
       }
+      // rows outside an output's window carry k = 0 but must not contribute 0 * (inf | NaN): predicate on the row range
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int vv = yy - r;                                 // kernel row this sample has for output r
-        if (vv >= 0 && vv < a.kh) {
-          const double k = kcol[vv * a.kw];
+        if (yy >= r && yy - r < a.kh) {
 #pragma unroll
-          for (int c = 0; c < CH; ++c) acc[r][c] = fma(k, v[c], acc[r][c]);
+          for (int c = 0; c < CH; ++c) acc[r][c] = fma(k[r], v[c], acc[r][c]);
         }
       }
     }
@@ -390,7 +400,7 @@ int launch_morph2d(const float *src, float *dst, size_t width, size_t height, in
     auto tile_bytes = [&](int R) {
       return (static_cast<size_t>((total + 1) & ~1) + static_cast<size_t>(32 + kw - 1) * (8 * R + kh - 1) * channels) * sizeof(double);
     };
-    const int R = tile_bytes(4) <= 100 * 1024 ? 4 : (tile_bytes(2) <= 200 * 1024 ? 2 : 0);
+    const int R = tile_bytes(8) <= 110 * 1024 ? 8 : tile_bytes(4) <= 110 * 1024 ? 4 : (tile_bytes(2) <= 200 * 1024 ? 2 : 0);
     if (R != 0) {
       double *d_taps = nullptr;
       cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&d_taps), sizeof(double) * static_cast<size_t>(total), temp_pool(), s);
@@ -410,12 +420,16 @@ int launch_morph2d(const float *src, float *dst, size_t width, size_t height, in
         conv2d_dense_kernel<CH, RR><<<grid, block, smem, s>>>(a, d_taps);                                           \
       } while (0)
       switch (channels * 10 + R) {
+        case 18: MB200_DENSE(1, 8); break;
         case 14: MB200_DENSE(1, 4); break;
         case 12: MB200_DENSE(1, 2); break;
+        case 28: MB200_DENSE(2, 8); break;
         case 24: MB200_DENSE(2, 4); break;
         case 22: MB200_DENSE(2, 2); break;
+        case 38: MB200_DENSE(3, 8); break;
         case 34: MB200_DENSE(3, 4); break;
         case 32: MB200_DENSE(3, 2); break;
+        case 48: MB200_DENSE(4, 8); break;
         case 44: MB200_DENSE(4, 4); break;
         default: MB200_DENSE(4, 2); break;
       }

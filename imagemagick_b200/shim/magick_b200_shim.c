@@ -59,6 +59,11 @@ static int b200_channels_masked(const Image *image, unsigned *update_mask)
     }
     if (update_mask != (unsigned *) NULL) *update_mask = mask;
     if (mask == 0) return 0;                       /* nothing to compute: let the CPU path clone */
+    /* An UNSELECTED alpha channel is copied by every stage of a multi-stage operator (row pass -> column pass, the two
+       resize passes), so the later stages weight the colour channels with the ORIGINAL alpha instead of the filtered
+       one: the selected channels then depend on the selection and a final restore pass cannot reproduce them.  Such
+       selections stay on the CPU path; with alpha selected (or no alpha) the unselected channels feed nothing. */
+    if (image->alpha_trait != UndefinedPixelTrait && mask != ((1u << n) - 1u) && (mask >> (n - 1) & 1u) == 0) return 0;
   }
   if (gray != MagickFalse) {
     if (n == 1 && image->alpha_trait == UndefinedPixelTrait) return 1;

@@ -193,10 +193,20 @@ int main(void)
     /* -channel selections: unselected channels carry the Copy trait and are handed through (nearest sample for resize) */
     const long hits0 = B200ShimHits();
     KernelInfo *uk = AcquireKernelInfo("3x3: 1,2,1, 2,4,2, 1,2,1", ex);
-    (void) SetPixelChannelMask(rgba, (ChannelType) (RedChannel | BlueChannel));
-    CHECK("BlurImage(0,2) -channel RB RGBA", 1, BlurImage(rgba, 0.0, 2.0, ex), CPU(__real_BlurImage(rgba, 0.0, 2.0, ex)));
-    CHECK("ResizeImage Lanczos -channel RB RGBA", 1, ResizeImage(rgba, 258, 194, LanczosFilter, ex), CPU(__real_ResizeImage(rgba, 258, 194, LanczosFilter, ex)));
-    CHECK("UnsharpMaskImage -channel RB RGBA", 1, UnsharpMaskImage(rgba, 0.0, 2.0, 1.5, 0.02, ex), CPU(__real_UnsharpMaskImage(rgba, 0.0, 2.0, 1.5, 0.02, ex)));
+    (void) SetPixelChannelMask(rgba, (ChannelType) (RedChannel | BlueChannel | AlphaChannel));
+    CHECK("BlurImage(0,2) -channel RBA RGBA", 1, BlurImage(rgba, 0.0, 2.0, ex), CPU(__real_BlurImage(rgba, 0.0, 2.0, ex)));
+    CHECK("ResizeImage Lanczos -channel RBA RGBA", 1, ResizeImage(rgba, 258, 194, LanczosFilter, ex), CPU(__real_ResizeImage(rgba, 258, 194, LanczosFilter, ex)));
+    CHECK("UnsharpMaskImage -channel RBA RGBA", 1, UnsharpMaskImage(rgba, 0.0, 2.0, 1.5, 0.02, ex), CPU(__real_UnsharpMaskImage(rgba, 0.0, 2.0, 1.5, 0.02, ex)));
+    {
+      /* alpha unselected: the second pass weights with the unfiltered alpha -- must decline, and still be right */
+      const long fb0 = B200ShimFallbacks();
+      (void) SetPixelChannelMask(rgba, (ChannelType) (RedChannel | BlueChannel));
+      CHECK("BlurImage(0,2) -channel RB (declines)", 0, BlurImage(rgba, 0.0, 2.0, ex), CPU(__real_BlurImage(rgba, 0.0, 2.0, ex)));
+      if (mb200_device_count() > 0 && B200ShimFallbacks() <= fb0) { printf("FAIL: alpha-less selection was not declined\n"); failures++; }
+    }
+    (void) SetPixelChannelMask(rgb, (ChannelType) (RedChannel | BlueChannel));
+    CHECK("BlurImage(0,2) -channel RB RGB (no alpha)", 1, BlurImage(rgb, 0.0, 2.0, ex), CPU(__real_BlurImage(rgb, 0.0, 2.0, ex)));
+    (void) SetPixelChannelMask(rgb, DefaultChannels);
     (void) SetPixelChannelMask(rgba, (ChannelType) (AlphaChannel | GreenChannel));
     CHECK("MorphologyImage Dilate -channel GA", 0, MorphologyImage(rgba, DilateMorphology, 1, uk, ex), CPU(__real_MorphologyImage(rgba, DilateMorphology, 1, uk, ex)));
     CHECK("ResizeImage up -channel GA RGBA", 1, ResizeImage(rgba, 700, 500, MitchellFilter, ex), CPU(__real_ResizeImage(rgba, 700, 500, MitchellFilter, ex)));

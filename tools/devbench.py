@@ -1,5 +1,5 @@
 """Developer micro-benchmark: device-resident timings of the hot-path operators (CUDA events).
-usage: python tools/devbench.py [blur|resize|lab|dilate|gauss|all] [size]"""
+usage: python tools/devbench.py [blur|resize|lab|dilate|gauss|conv2d|stencils|all] [size]"""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -62,3 +62,22 @@ if which in ("gauss", "all"):
     s = min(size, 4096)
     x = im.Image(torch.rand(s, s, 4, device="cuda") * 65535)
     ms = timeit(lambda: im.GaussianBlurImage(x, 0.0, 4.0), iters=3, warm=1); report(f"GaussianBlurImage 2-D 29x29 {s}^2", ms, s * s, 32)
+
+if which in ("conv2d", "all"):
+    hd = im.Image(torch.rand(1080, 1920, 4, device="cuda") * 65535)
+    ms = timeit(lambda: im.SharpenImage(hd, 5.0, 2.0), iters=9); report("SharpenImage 5x2 (11x11) 1920x1080", ms, 1920 * 1080, 32)
+    x = im.Image(torch.rand(size, size, 4, device="cuda") * 65535)
+    ms = timeit(lambda: im.SharpenImage(x, 5.0, 2.0)); report(f"SharpenImage 5x2 (11x11) {size}^2", ms, size * size, 32)
+    ms = timeit(lambda: im.EdgeImage(x, 1.0)); report(f"EdgeImage(1) (3x3) {size}^2", ms, size * size, 32)
+    ms = timeit(lambda: im.EmbossImage(x, 0.0, 1.0), iters=3); report(f"EmbossImage(0,1) {size}^2 (conv + equalize)", ms, size * size, 64)
+    ms = timeit(lambda: im.ConvolveImage(x, "LoG:0x2")); report(f"ConvolveImage LoG:0x2 {size}^2", ms, size * size, 32)
+    del x, hd
+if which in ("stencils", "all"):
+    s = min(size, 4096)
+    x = im.Image(torch.rand(s, s, 4, device="cuda") * 65535)
+    ms = timeit(lambda: im.StatisticImage(x, im.MedianStatistic, 3, 3), iters=3); report(f"StatisticImage Median 3x3 {s}^2", ms, s * s, 32)
+    ms = timeit(lambda: im.StatisticImage(x, im.MeanStatistic, 5, 5), iters=3); report(f"StatisticImage Mean 5x5 {s}^2", ms, s * s, 32)
+    ms = timeit(lambda: im.BilateralBlurImage(x, 7, 7, 20.0, 2.0), iters=3); report(f"BilateralBlurImage 7x7 {s}^2", ms, s * s, 32)
+    ms = timeit(lambda: im.RotationalBlurImage(x, 5.0), iters=3); report(f"RotationalBlurImage(5) {s}^2", ms, s * s, 32)
+    ms = timeit(lambda: im.MotionBlurImage(x, 0.0, 4.0, 30.0), iters=3); report(f"MotionBlurImage(0,4,30) {s}^2", ms, s * s, 32)
+    ms = timeit(lambda: im.EqualizeImage(x), iters=3); report(f"EqualizeImage {s}^2", ms, s * s, 32)
