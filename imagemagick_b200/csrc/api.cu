@@ -43,6 +43,10 @@ struct ResizeTables {
   double *d_wsets = nullptr;
   int nborder = 0;
   int *d_border = nullptr;
+  // fused V+H kernel (resize_stream.cu): the runs cut into tiles of tile_w (this axis used as x) / tile_h (as y) outputs
+  int *d_tiles_x = nullptr, *d_tiles_y = nullptr;
+  int ntiles_x = 0, ntiles_y = 0;
+  unsigned char *d_is_border = nullptr;       // [out_n]: output lies outside the runs
   ResizeTables() = default;
   ResizeTables(const ResizeTables &) = delete;
   ResizeTables &operator=(const ResizeTables &) = delete;
@@ -51,6 +55,7 @@ struct ResizeTables {
     cudaGetDevice(&cur);
     if (device >= 0 && cur != device) cudaSetDevice(device);
     cudaFree(d_start); cudaFree(d_count); cudaFree(d_weights); cudaFree(d_wreg); cudaFree(d_wsets); cudaFree(d_border);
+    cudaFree(d_tiles_x); cudaFree(d_tiles_y); cudaFree(d_is_border);
     if (device >= 0 && cur != device) cudaSetDevice(cur);
   }
 };
@@ -87,7 +92,7 @@ bool valid_image(size_t w, size_t h, int ch) { return w > 0 && h > 0 && ch >= 1 
 // Developer switches (environment, read once per process): force the generic kernels so that tests can compare them
 // with the specialised ones.
 struct Knobs {
-  bool no_rank1, no_morph_stream, no_resize_stream, resize_regular_h, no_fused_unsharp;
+  bool no_rank1, no_morph_stream, no_resize_stream, resize_regular_h, no_fused_unsharp, no_resize_fused;
   Knobs() {
     auto on = [](const char *name) { const char *v = std::getenv(name); return v != nullptr && *v != '\0' && *v != '0'; };
     no_rank1 = on("MB200_NO_RANK1");
@@ -95,6 +100,7 @@ struct Knobs {
     no_resize_stream = on("MB200_NO_RESIZE_STREAM");
     resize_regular_h = on("MB200_RESIZE_REGULAR_H");
     no_fused_unsharp = on("MB200_NO_FUSED_UNSHARP");
+    no_resize_fused = on("MB200_NO_RESIZE_FUSED");
   }
 };
 Knobs &knobs() {
@@ -362,6 +368,7 @@ int mb200_set_option(const char *name, int value) {
   else if (n == "no_resize_stream") k.no_resize_stream = v;
   else if (n == "resize_regular_h") k.resize_regular_h = v;
   else if (n == "no_fused_unsharp") k.no_fused_unsharp = v;
+  else if (n == "no_resize_fused") k.no_resize_fused = v;
   else return fail(MB200_EINVAL, "set_option: unknown option '%s'", name);
   return MB200_OK;
 }
@@ -553,6 +560,29 @@ int mb200_resize_image_dev(const float *src, size_t width, size_t height, int ch
         }
       }
     }
+    std::vector<int> tiles_x, tiles_y;
+    std::vector<unsigned char> is_border;
+    if (t->nseg > 0) {
+      int tw = 0, th = 0;
+      resize_fused_tile(t->reg_stride, t->reg_taps, &tw, &th);
+      if (tw > 0) {
+        auto cut = [&](int tile, std::vector<int> &out) {
+          for (int k = 0; k < t->nseg; ++k)
+            for (int rel = 0; rel < t->seg_n[k]; rel += tile) {
+              out.push_back(t->seg_o[k] + rel);
+              out.push_back(std::min(tile, t->seg_n[k] - rel));
+              out.push_back(t->seg_src[k] + t->reg_stride * rel);
+              out.push_back(k);
+            }
+        };
+        cut(tw, tiles_x);
+        cut(th, tiles_y);
+        t->ntiles_x = static_cast<int>(tiles_x.size() / 4);
+        t->ntiles_y = static_cast<int>(tiles_y.size() / 4);
+        is_border.assign(out_n, 0);
+        for (int k = 0; k < t->nborder; ++k) is_border[static_cast<size_t>(border[k])] = 1;
+      }
+    }
     for (size_t o = 0; o < out_n; ++o) {          // tap-major transpose for coalesced weight loads
       istart[o] = static_cast<int>(start[o]);
       for (long j = 0; j < taps; ++j) wt[static_cast<size_t>(j) * out_n + o] = w[o * taps + j];
@@ -572,6 +602,13 @@ int mb200_resize_image_dev(const float *src, size_t width, size_t height, int ch
     if (e == cudaSuccess) e = cudaMemcpy(t->d_weights, wt.data(), wt.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !wreg.empty())
       e = cudaMemcpy(t->d_wreg, wreg.data(), wreg.size() * sizeof(double), cudaMemcpyHostToDevice);
+    auto upload = [&](const void *host, size_t bytes, void **dev) {
+      if (e == cudaSuccess && bytes) e = cudaMalloc(dev, bytes);
+      if (e == cudaSuccess && bytes) e = cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice);
+    };
+    upload(tiles_x.data(), tiles_x.size() * sizeof(int), reinterpret_cast<void **>(&t->d_tiles_x));
+    upload(tiles_y.data(), tiles_y.size() * sizeof(int), reinterpret_cast<void **>(&t->d_tiles_y));
+    upload(is_border.data(), is_border.size(), reinterpret_cast<void **>(&t->d_is_border));
     if (e != cudaSuccess) return cuda_fail(e, "resize: table upload");     // ~ResizeTables frees what was allocated
     std::lock_guard<std::mutex> lock(g_tables_mutex);
     if ((*out = find())) return MB200_OK;          // another thread built the same table meanwhile: keep theirs
@@ -600,6 +637,16 @@ int mb200_resize_image_dev(const float *src, size_t width, size_t height, int ch
                               static_cast<int>(t->taps), t->max_span, use_reg ? t->reg_stride : 0, t->reg_taps,
                               use_reg ? t->d_wreg : nullptr, s);
   };
+  // Equal integer reduction on both axes (the reference filters vertically first when x_factor <= y_factor, :3854-3861):
+  // one fused launch keeps the vertically filtered intermediate of every output tile in shared memory.
+  if (channels == 4 && x_factor == y_factor && !no_stream && !knobs().no_resize_fused && tx->ntiles_x > 0 && ty->ntiles_y > 0 &&
+      tx->reg_stride == ty->reg_stride && tx->reg_taps == ty->reg_taps) {
+    rc = launch_resize_fused(src, width, height, dst, out_width, out_height, tx->reg_stride, tx->reg_taps, tx->d_tiles_x,
+                             tx->ntiles_x, ty->d_tiles_y, ty->ntiles_y, tx->d_wsets, ty->d_wsets, tx->d_start, tx->d_count,
+                             tx->d_weights, ty->d_start, ty->d_count, ty->d_weights, tx->d_border, tx->nborder, ty->d_border,
+                             ty->nborder, ty->d_is_border, s);
+    if (rc != MB200_EUNSUPPORTED) return rc;
+  }
   if (x_factor > y_factor) {                                                                       // :3846-3853
     rc = tmp.alloc(out_width * height * px);
     if (rc) return rc;

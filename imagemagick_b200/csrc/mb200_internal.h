@@ -91,6 +91,15 @@ int launch_resize_stream(const float *src, size_t width, size_t height, float *d
                          const double *d_wsets, int nborder, const int *d_border, const int *d_start,
                          const int *d_count, const double *d_weights, void *stream);
 
+// Fused vertical + horizontal pass for equal integer reductions on both axes (RGBA): tile lists of both axes' runs,
+// the two-pass path's contribution / border lists for the outputs outside the runs.
+void resize_fused_tile(int stride, int taps, int *tile_w, int *tile_h);
+int launch_resize_fused(const float *src, size_t width, size_t height, float *dst, size_t out_w, size_t out_h, int stride,
+                        int taps, const int *d_xtiles, int nxt, const int *d_ytiles, int nyt, const double *d_wx,
+                        const double *d_wy, const int *d_xstart, const int *d_xcount, const double *d_xweights,
+                        const int *d_ystart, const int *d_ycount, const double *d_yweights, const int *d_xborder, int nxborder,
+                        const int *d_yborder, int nyborder, const unsigned char *d_row_is_border, void *stream);
+
 // colorspace.cu
 int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to, void *stream);
 

@@ -30,6 +30,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace mb200 {
@@ -313,6 +314,234 @@ __global__ void __launch_bounds__(128, MINB) resize_h_stream_kernel(const Stream
   }
   cp_async_wait<0>();
 }
+
+// ------------------------------------------------------------------------------------------ fused V + H
+// ResizeImage with the SAME integer reduction on both axes (x_factor == y_factor: the reference filters vertically
+// first, resize.c:3854-3861).  The two-pass form moves 36 B per input pixel through HBM (16 + 8 for the vertical pass,
+// 8 + 4 for the horizontal one); here the vertically filtered intermediate of one output tile lives in shared memory --
+// as float, i.e. with the reference's rounding between the passes -- and HBM sees the source once (plus tile halos,
+// which the L2 absorbs) and the result: 20 B per input pixel.
+//   CTA = 128 threads, output tile TW x TH = (4*NW) x 31, both inside ONE run of bit-identical weights per axis.
+//   phase A: thread = source column of the tile (S*(TW-1)+N <= 128 columns), the vertical kernel's streaming loop over
+//            S*(TH-1)+N source rows (72 = 6 rotation periods for S=2, N=12): register prefetch ring, rotating FP64
+//            accumulators, weights in registers; finished rows go to the shared tile [TH][128] float4 (row pitch
+//            128*16+16 B: rows are read lane-wise in phase B, the odd pitch keeps LDS.128 conflict free);
+//   phase B: lane = output row, warp w = output columns [NW*w, NW*w + NW): the horizontal kernel's streaming loop along
+//            the shared tile (S*(NW-1)+N = 36 samples = 3 periods for NW = 13), 16-byte stores.
+// Outputs outside the runs (clipped windows at the image border, very short low-binade runs) are produced by
+// resize_border2d_kernel below from the reference's contribution lists.
+struct Tile { int o0, nout, src0, set; };
+struct FusedArgs {
+  const float *src;
+  float *dst;
+  int width, height, out_w, out_h;
+  const Tile *xt, *yt;          // tiles of the x / y runs (device)
+  const double *wx, *wy;        // [run][N] weights
+};
+
+template <int S, int N> struct FusedGeom {
+  static constexpr int P = Rot<S, N>::P;
+  static constexpr int TH = 31;                                  // S*(TH-1)+N = 72 = 6*P for S=2, N=12
+  static constexpr int NW = (128 - N) / S / 4 >= 13 ? 13 : (128 - N) / S / 4;   // S*(4*NW-1)+N <= 128
+  static constexpr int TW = 4 * NW;
+  static constexpr int kPitch = 128 * 16 + 16;                   // bytes per tile row
+  static constexpr int kSmem = 32 * kPitch;
+};
+
+template <int S, int N>
+__global__ void __launch_bounds__(128, 3) resize_fused_kernel(const FusedArgs a) {
+  using T = Rot<S, N>;
+  using G = FusedGeom<S, N>;
+  constexpr int R = T::R, P = T::P, BODY = T::BODY, PF = T::PF;
+  extern __shared__ __align__(16) unsigned char inter[];        // [TH][kPitch]
+  const Tile xt = a.xt[blockIdx.x], yt = a.yt[blockIdx.y];
+  double acc[R][4];
+  {
+    // ---- phase A: vertical filter of column xt.src0 + threadIdx.x over the tile's rows
+    double W[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) W[j] = __ldg(a.wy + yt.set * N + j);
+    const int x = min(xt.src0 + static_cast<int>(threadIdx.x), a.width - 1);
+    const int niter = (S * (yt.nout - 1) + N + BODY - 1) / BODY;
+    const size_t pitch = static_cast<size_t>(a.width) * 4;
+    const float *col = a.src + static_cast<size_t>(x) * 4;
+    const int last = min(a.height - 1, yt.src0 + S * (yt.nout - 1) + N - 1);
+    int row = yt.src0;
+    float4 pre[PF];
+#pragma unroll
+    for (int s = 0; s < PF; ++s, ++row)
+      pre[s] = __ldg(reinterpret_cast<const float4 *>(col + static_cast<size_t>(min(row, last)) * pitch));
+#pragma unroll
+    for (int q = 0; q < R; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0; }
+    int c = -R;
+    unsigned char *outp = inter + static_cast<ptrdiff_t>(-(R - 1)) * G::kPitch + threadIdx.x * 16;
+#pragma unroll 1
+    for (int t = 0; t < niter; ++t) {
+#pragma unroll
+      for (int b = 0; b < BODY; ++b) {
+        const int m = b % P;
+        const float4 v = pre[b % PF];
+        pre[b % PF] = __ldg(reinterpret_cast<const float4 *>(col + static_cast<size_t>(min(row, last)) * pitch));
+        ++row;
+        feed<S, N>(acc, W, v, m);
+        const int qd = done_slot<S, N>(m);
+        if (qd >= 0) {
+          ++c;
+          if (c >= 0 && c < yt.nout) *reinterpret_cast<float4 *>(outp) = finish_rgba(acc[qd]);
+          outp += G::kPitch;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  {
+    // ---- phase B: horizontal filter along the shared tile; lane = output row, warp = NW output columns
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o_first = warp * G::NW;                          // first output column of this warp within the tile
+    const int nout = min(G::NW, xt.nout - o_first);
+    if (nout <= 0 || lane >= yt.nout) return;
+    double W[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) W[j] = __ldg(a.wx + xt.set * N + j);
+    const int niter = (S * (nout - 1) + N + BODY - 1) / BODY;
+    // the last warp reads S*3*NW + niter*BODY + 1 <= 128 samples of its row: never past the tile
+    static_assert(S * 3 * G::NW + ((S * (G::NW - 1) + N + BODY - 1) / BODY) * BODY + 1 <= 128, "phase B would leave the tile row");
+    const unsigned char *rd = inter + static_cast<size_t>(lane) * G::kPitch + static_cast<size_t>(S * o_first) * 16;
+#pragma unroll
+    for (int q = 0; q < R; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0; }
+    int c = -R;
+    float *outp = a.dst + (static_cast<size_t>(yt.o0 + lane) * a.out_w + (xt.o0 + o_first - (R - 1))) * 4;
+    float4 vnext = *reinterpret_cast<const float4 *>(rd);
+#pragma unroll 1
+    for (int t = 0; t < niter; ++t) {
+#pragma unroll
+      for (int b = 0; b < BODY; ++b) {
+        const int m = b % P;
+        const float4 v = vnext;
+        rd += 16;
+        vnext = *reinterpret_cast<const float4 *>(rd);
+        feed<S, N>(acc, W, v, m);
+        const int qd = done_slot<S, N>(m);
+        if (qd >= 0) {
+          ++c;
+          if (c >= 0 && c < nout) *reinterpret_cast<float4 *>(outp) = finish_rgba(acc[qd]);
+          outp += 4;
+        }
+      }
+    }
+  }
+}
+
+// Outputs whose row or column lies outside the streamed runs: thread = one output pixel, the reference's two passes on
+// its own neighbourhood -- vertical contribution list per source column (rounded to float like the intermediate image,
+// resize.c:3854), then the horizontal list over those values.
+struct Border2dArgs {
+  const float *src;
+  float *dst;
+  int width, height, out_w, out_h;
+  const int *xstart, *xcount, *ystart, *ycount;
+  const double *xweights, *yweights;     // tap-major [tap][out_n]
+  const int *xborder, *yborder;          // output columns / rows outside the runs
+  int nxborder, nyborder;
+};
+
+__device__ __forceinline__ float4 border2d_pixel(const Border2dArgs &a, int ox, int oy) {
+  const int x0 = __ldg(a.xstart + ox), nx = __ldg(a.xcount + ox), y0 = __ldg(a.ystart + oy), ny = __ldg(a.ycount + oy);
+  double hacc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = 0; i < nx; ++i) {
+    double vacc[4] = {0.0, 0.0, 0.0, 0.0};
+    const float *p = a.src + (static_cast<size_t>(y0) * a.width + (x0 + i)) * 4;
+    for (int j = 0; j < ny; ++j, p += static_cast<size_t>(a.width) * 4) {
+      const double w = __ldg(a.yweights + static_cast<size_t>(j) * a.out_h + oy);
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+      const double al = static_cast<double>(v.w);
+      vacc[0] = fma(w, static_cast<double>(v.x) * al, vacc[0]);
+      vacc[1] = fma(w, static_cast<double>(v.y) * al, vacc[1]);
+      vacc[2] = fma(w, static_cast<double>(v.z) * al, vacc[2]);
+      vacc[3] = fma(w, al, vacc[3]);
+    }
+    const float4 m = finish_rgba(vacc);                        // the intermediate image's float Quantum
+    const double w = __ldg(a.xweights + static_cast<size_t>(i) * a.out_w + ox);
+    const double al = static_cast<double>(m.w);
+    hacc[0] = fma(w, static_cast<double>(m.x) * al, hacc[0]);
+    hacc[1] = fma(w, static_cast<double>(m.y) * al, hacc[1]);
+    hacc[2] = fma(w, static_cast<double>(m.z) * al, hacc[2]);
+    hacc[3] = fma(w, al, hacc[3]);
+  }
+  return finish_rgba(hacc);
+}
+
+// grid.y = 0: border rows x all columns; grid.y = 1: border columns x the rows that are NOT border rows (no double work)
+__global__ void __launch_bounds__(128) resize_border2d_kernel(const Border2dArgs a, const unsigned char *__restrict__ row_is_border) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * 128 + threadIdx.x;
+  int ox, oy;
+  if (blockIdx.y == 0) {
+    if (i >= static_cast<size_t>(a.nyborder) * a.out_w) return;
+    oy = __ldg(a.yborder + i / a.out_w);
+    ox = static_cast<int>(i % a.out_w);
+  } else {
+    if (i >= static_cast<size_t>(a.nxborder) * a.out_h) return;
+    ox = __ldg(a.xborder + i / a.out_h);
+    oy = static_cast<int>(i % a.out_h);
+    if (row_is_border[oy]) return;
+  }
+  if (__ldg(a.xcount + ox) <= 0 || __ldg(a.ycount + oy) <= 0) return;
+  *reinterpret_cast<float4 *>(a.dst + (static_cast<size_t>(oy) * a.out_w + ox) * 4) = border2d_pixel(a, ox, oy);
+}
+
+template <int S, int N>
+int launch_fused_sn(const FusedArgs &a, int nxt, int nyt, cudaStream_t s) {
+  using G = FusedGeom<S, N>;
+  cudaFuncSetAttribute(resize_fused_kernel<S, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmem);
+  resize_fused_kernel<S, N><<<dim3(nxt, nyt), 128, G::kSmem, s>>>(a);
+  return MB200_OK;
+}
+
+}  // namespace
+
+// Tile geometry of the fused kernel for (stride, taps): outputs per tile along x / y; 0 = no fused kernel for this pair.
+void resize_fused_tile(int stride, int taps, int *tw, int *th) {
+  *tw = *th = 0;
+  if (stride == 2 && taps == 12) { *tw = FusedGeom<2, 12>::TW; *th = FusedGeom<2, 12>::TH; }
+  else if (stride == 2 && taps == 8) { *tw = FusedGeom<2, 8>::TW; *th = FusedGeom<2, 8>::TH; }
+}
+
+// Fused vertical + horizontal pass.  d_xtiles / d_ytiles: {o0, nout, src0, set} of every tile (4 ints each); the
+// contribution lists and border lists are the ones of the two-pass path.  MB200_EUNSUPPORTED => use two passes.
+int launch_resize_fused(const float *src, size_t width, size_t height, float *dst, size_t out_w, size_t out_h, int stride,
+                        int taps, const int *d_xtiles, int nxt, const int *d_ytiles, int nyt, const double *d_wx,
+                        const double *d_wy, const int *d_xstart, const int *d_xcount, const double *d_xweights,
+                        const int *d_ystart, const int *d_ycount, const double *d_yweights, const int *d_xborder, int nxborder,
+                        const int *d_yborder, int nyborder, const unsigned char *d_row_is_border, void *stream) {
+  if (width > 0x3fffffffull || height > 0x3fffffffull || nxt <= 0 || nyt <= 0 || nyt > 65535) return MB200_EUNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FusedArgs a{};
+  a.src = src; a.dst = dst;
+  a.width = static_cast<int>(width); a.height = static_cast<int>(height);
+  a.out_w = static_cast<int>(out_w); a.out_h = static_cast<int>(out_h);
+  a.xt = reinterpret_cast<const Tile *>(d_xtiles); a.yt = reinterpret_cast<const Tile *>(d_ytiles);
+  a.wx = d_wx; a.wy = d_wy;
+  int rc = MB200_EUNSUPPORTED;
+  if (stride == 2 && taps == 12) rc = launch_fused_sn<2, 12>(a, nxt, nyt, s);
+  else if (stride == 2 && taps == 8) rc = launch_fused_sn<2, 8>(a, nxt, nyt, s);
+  if (rc != MB200_OK) return rc;
+  count_launch();
+  if (nxborder > 0 || nyborder > 0) {
+    Border2dArgs b{};
+    b.src = src; b.dst = dst; b.width = a.width; b.height = a.height; b.out_w = a.out_w; b.out_h = a.out_h;
+    b.xstart = d_xstart; b.xcount = d_xcount; b.ystart = d_ystart; b.ycount = d_ycount;
+    b.xweights = d_xweights; b.yweights = d_yweights;
+    b.xborder = d_xborder; b.yborder = d_yborder; b.nxborder = nxborder; b.nyborder = nyborder;
+    const size_t work = std::max(static_cast<size_t>(nyborder) * out_w, static_cast<size_t>(nxborder) * out_h);
+    resize_border2d_kernel<<<dim3(static_cast<unsigned>((work + 127) / 128), 2), 128, 0, s>>>(b, d_row_is_border);
+    count_launch();
+  }
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "fused resize launch");
+  return MB200_OK;
+}
+
+namespace {
 
 template <int S, int N>
 int launch_sn(StreamArgs a, int axis, cudaStream_t s) {

@@ -370,3 +370,27 @@ def test_bilateral_blur_bit_exact(ch, win, isig, ssig):
     with pytest.raises(im.MagickB200Error) as e:
         im.BilateralBlurImage(_dev(src), 4, 4, isig, ssig)
     assert e.value.code == -5
+
+
+# ---- fused vertical + horizontal ResizeImage (equal integer reduction on both axes) ------------------------------------
+@pytest.mark.parametrize("filt", [22, 12, 11])            # Lanczos (12 taps at 2x), Mitchell, Catrom (8 taps)
+@pytest.mark.parametrize("size", [(2048, 1536), (2222, 1554), (4096, 130), (140, 4100)])
+@pytest.mark.parametrize("kind", ["noise", "alpha_blocks"])
+def test_fused_resize_matches_the_oracle_and_the_two_pass_kernels(filt, size, kind):
+    w, h = size
+    src = make_image(w, h, 4, seed=71, kind=kind)
+    d = _dev(src)
+    n0 = im.launch_count()
+    got = _host(im.ResizeImage(d, w // 2, h // 2, filt))
+    launches = im.launch_count() - n0
+    util.set_option("no_resize_fused", 1)
+    two_pass = _host(im.ResizeImage(d, w // 2, h // 2, filt))
+    util.set_option("no_resize_fused", 0)
+    assert launches == 2                                  # the fused kernel + the border outputs
+    # same arithmetic in the same order, same float rounding between the passes: identical bits
+    assert np.array_equal(got, two_pass)
+    want = np.empty((h // 2, w // 2, 4), np.float32)
+    assert oracle().orc_resize(P(src), w, h, 4, P(want), w // 2, h // 2, filt) == 0
+    d_ = util.ulp_distance(got, want)
+    assert d_.max() <= 1
+    assert (d_ == 0).mean() > 0.9999
