@@ -116,6 +116,9 @@ PROTOTYPES = {
     "mb200_edge_image": (_i, [_vp, _vp, _sz, _sz, _i, _d]),
     "mb200_sample_image_dev": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _vp]),
     "mb200_sample_image": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz]),
+    "mb200_scale_image_dev": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _vp]),
+    "mb200_scale_image": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz]),
+    "mb200_scale_contributions": (_l, [_i, _sz, _sz, C.POINTER(_l), C.POINTER(_i), C.POINTER(_d), _sz]),
     "mb200_thumbnail_image_dev": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i, _vp]),
     "mb200_thumbnail_image": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i]),
     "mb200_motion_blur_kernel": (_l, [_d, _d, _d, C.POINTER(_d), C.POINTER(_l), C.POINTER(_l), _sz]),

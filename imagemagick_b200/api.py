@@ -10,7 +10,7 @@ include/magick_b200.h:
     BilateralBlurImage, RotationalBlurImage                         effect.c:821/3129
     StatisticImage                                                  statistic.c:2918
     MorphologyImage, AcquireKernelInfo                              morphology.c:4129/485
-    ResizeImage, SampleImage, ThumbnailImage (pixel path)           resize.c:3761/3907/4591
+    ResizeImage, SampleImage, ScaleImage, ThumbnailImage (pixel)    resize.c:3761/3907/4106/4591
     TransformImageColorspace                                        colorspace.c:1751
     BilevelImage, BlackThresholdImage, WhiteThresholdImage, ClampImage  threshold.c:805/927/2518/1087
 
@@ -284,6 +284,21 @@ def SampleImage(image: Image, columns: int, rows: int) -> Image:
                                          rows, _stream(image)))
     else:
         check(lib.mb200_sample_image(image._ptr(), image.columns, image.rows, image.channels, out._ptr(), columns, rows))
+    return out
+
+
+def ScaleImage(image: Image, columns: int, rows: int) -> Image:
+    """MagickCore/resize.c:4106 -- box scaling."""
+    if columns <= 0 or rows <= 0:
+        raise MagickB200Error(_lib.EINVAL, "NegativeOrZeroImageSize")
+    lib = _lib.load()
+    out = image._new_like(rows=rows, columns=columns)
+    if image.on_device:
+        _activate(image)
+        check(lib.mb200_scale_image_dev(image._ptr(), image.columns, image.rows, image.channels, out._ptr(), columns, rows,
+                                        _stream(image)))
+    else:
+        check(lib.mb200_scale_image(image._ptr(), image.columns, image.rows, image.channels, out._ptr(), columns, rows))
     return out
 
 

@@ -92,7 +92,7 @@ bool valid_image(size_t w, size_t h, int ch) { return w > 0 && h > 0 && ch >= 1 
 // Developer switches (environment, read once per process): force the generic kernels so that tests can compare them
 // with the specialised ones.
 struct Knobs {
-  bool no_rank1, no_morph_stream, no_resize_stream, resize_regular_h, no_fused_unsharp, no_resize_fused;
+  bool no_rank1, no_morph_stream, no_resize_stream, resize_regular_h, no_fused_unsharp, resize_fused;
   Knobs() {
     auto on = [](const char *name) { const char *v = std::getenv(name); return v != nullptr && *v != '\0' && *v != '0'; };
     no_rank1 = on("MB200_NO_RANK1");
@@ -100,7 +100,7 @@ struct Knobs {
     no_resize_stream = on("MB200_NO_RESIZE_STREAM");
     resize_regular_h = on("MB200_RESIZE_REGULAR_H");
     no_fused_unsharp = on("MB200_NO_FUSED_UNSHARP");
-    no_resize_fused = on("MB200_NO_RESIZE_FUSED");
+    resize_fused = on("MB200_RESIZE_FUSED");          // opt-in: measured slower than the two passes (profiles/r02_resize_fused.md)
   }
 };
 Knobs &knobs() {
@@ -368,7 +368,7 @@ int mb200_set_option(const char *name, int value) {
   else if (n == "no_resize_stream") k.no_resize_stream = v;
   else if (n == "resize_regular_h") k.resize_regular_h = v;
   else if (n == "no_fused_unsharp") k.no_fused_unsharp = v;
-  else if (n == "no_resize_fused") k.no_resize_fused = v;
+  else if (n == "resize_fused") k.resize_fused = v;
   else return fail(MB200_EINVAL, "set_option: unknown option '%s'", name);
   return MB200_OK;
 }
@@ -638,8 +638,11 @@ int mb200_resize_image_dev(const float *src, size_t width, size_t height, int ch
                               use_reg ? t->d_wreg : nullptr, s);
   };
   // Equal integer reduction on both axes (the reference filters vertically first when x_factor <= y_factor, :3854-3861):
-  // one fused launch keeps the vertically filtered intermediate of every output tile in shared memory.
-  if (channels == 4 && x_factor == y_factor && !no_stream && !knobs().no_resize_fused && tx->ntiles_x > 0 && ty->ntiles_y > 0 &&
+  // one fused launch keeps the vertically filtered intermediate of every output tile in shared memory.  Parity-green and
+  // bit-identical to the two passes, DRAM traffic 1.32 GB instead of 2.45 GB for 8192^2 -> 4096^2 -- but 0.565 ms against
+  // 0.489 ms: the passes are bound by the FP64 and conversion (XU) pipes, not by HBM, and the fused kernel adds 17 % of
+  // halo work.  Opt-in (MB200_RESIZE_FUSED=1 / mb200_set_option("resize_fused", 1)); A/B in profiles/r02_resize_fused.md.
+  if (channels == 4 && x_factor == y_factor && !no_stream && knobs().resize_fused && tx->ntiles_x > 0 && ty->ntiles_y > 0 &&
       tx->reg_stride == ty->reg_stride && tx->reg_taps == ty->reg_taps) {
     rc = launch_resize_fused(src, width, height, dst, out_width, out_height, tx->reg_stride, tx->reg_taps, tx->d_tiles_x,
                              tx->ntiles_x, ty->d_tiles_y, ty->ntiles_y, tx->d_wsets, ty->d_wsets, tx->d_start, tx->d_count,
@@ -1053,6 +1056,57 @@ int mb200_bilateral_blur_image(const float *src, float *dst, size_t w, size_t h,
   return with_staging(src, bytes, dst, bytes, [&](const float *s, float *d, cudaStream_t st) {
     return mb200_bilateral_blur_image_dev(s, d, w, h, ch, ww, wh, intensity_sigma, spatial_sigma, st);
   });
+}
+
+}  // extern "C"
+
+// ---- ScaleImage (resize.c:4106) ---------------------------------------------------------------------------------------------
+extern "C" long mb200_scale_contributions(int axis, size_t in_n, size_t out_n, long *offsets, int *index, double *weight,
+                                          size_t max_terms);
+extern "C" {
+
+int mb200_scale_image_dev(const float *src, size_t width, size_t height, int channels, float *dst, size_t out_width,
+                          size_t out_height, void *stream) {
+  if (!src || !dst || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "scale: bad arguments");
+  if (out_width == 0 || out_height == 0) return fail(MB200_EINVAL, "NegativeOrZeroImageSize");      // :4153
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  if (out_width == width && out_height == height) {                                                  // :4155: clone
+    cudaError_t e = cudaMemcpyAsync(dst, src, width * height * channels * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    return e == cudaSuccess ? MB200_OK : cuda_fail(e, "scale: clone");
+  }
+  // contribution lists of both axes (host, the reference's state machines), packed into one upload:
+  // [xoff (ow+1) | yoff (oh+1) | xidx | yidx] ints, then [xwt | ywt] doubles
+  std::vector<long> xoff(out_width + 1), yoff(out_height + 1);
+  const long nx = mb200_scale_contributions(0, width, out_width, xoff.data(), nullptr, nullptr, 0);
+  const long ny = mb200_scale_contributions(1, height, out_height, yoff.data(), nullptr, nullptr, 0);
+  if (nx < 0 || ny < 0) return static_cast<int>(nx < 0 ? nx : ny);
+  std::vector<int> ints(out_width + 1 + out_height + 1 + static_cast<size_t>(nx + ny));
+  std::vector<double> wts(static_cast<size_t>(nx + ny));
+  int *xo = ints.data(), *yo = xo + out_width + 1, *xi = yo + out_height + 1, *yi = xi + nx;
+  if (mb200_scale_contributions(0, width, out_width, xoff.data(), xi, wts.data(), static_cast<size_t>(nx)) < 0 ||
+      mb200_scale_contributions(1, height, out_height, yoff.data(), yi, wts.data() + nx, static_cast<size_t>(ny)) < 0)
+    return MB200_EINVAL;
+  for (size_t i = 0; i <= out_width; ++i) xo[i] = static_cast<int>(xoff[i]);
+  for (size_t i = 0; i <= out_height; ++i) yo[i] = static_cast<int>(yoff[i]);
+  StreamAlloc d_ints(s), d_wts(s);
+  rc = d_ints.alloc(ints.size() * sizeof(int));
+  if (!rc) rc = d_wts.alloc(wts.size() * sizeof(double));
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpyAsync(d_ints.ptr, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_wts.ptr, wts.data(), wts.size() * sizeof(double), cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cuda_fail(e, "scale: table upload");
+  const int *di = static_cast<const int *>(d_ints.ptr);
+  const double *dw = static_cast<const double *>(d_wts.ptr);
+  return launch_scale(src, width, height, channels, dst, out_width, out_height, di, di + out_width + 1 + out_height + 1, dw,
+                      di + out_width + 1, di + out_width + 1 + out_height + 1 + nx, dw + nx, s);
+}
+
+int mb200_scale_image(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh) {
+  if (!src || !dst || !valid_image(w, h, ch) || ow == 0 || oh == 0) return fail(MB200_EINVAL, "scale: bad arguments");
+  return with_staging(src, w * h * ch * sizeof(float), dst, ow * oh * ch * sizeof(float),
+                      [&](const float *s, float *d, cudaStream_t st) { return mb200_scale_image_dev(s, w, h, ch, d, ow, oh, st); });
 }
 
 }  // extern "C"

@@ -18,11 +18,29 @@
 
 #include <cuda_runtime.h>
 
+#include <cmath>
+#include <mutex>
+
 namespace mb200 {
 namespace {
 
 constexpr double QR = 65535.0;
 constexpr double QS = 1.0 / 65535.0;
+
+// Double constants of the sRGB -> XYZ -> Lab path as a __constant__ block: a literal double costs two MOV-immediates
+// every time the compiler rematerialises it (ncu r02: 147 of the kernel's 576 SASS instructions were moves and the
+// kernel issued 331 instructions per pixel at 87 % issue utilisation); a constant-bank operand costs nothing.
+struct LabConstants {
+  double third, qs, qr, toe_limit, inv_12_92, c055, inv_1055, four, three;
+  double m[3][3];
+  double inv_ill_x, inv_ill_z, cie_eps, c116, c16, inv100, c500, c200, inv255, half;
+};
+__constant__ LabConstants kk = {
+    1.0 / 3.0, 1.0 / 65535.0, 65535.0, 0.0404482362771076 * 65535.0, 1.0 / 12.92, 0.055, 1.0 / 1.055, 4.0, 3.0,
+    {{0.4123955889674142161, 0.3575834307637148171, 0.1804926473817015735},
+     {0.2125862307855955516, 0.7151703037034108499, 0.07220049864333622685},
+     {0.01929721549174694484, 0.1191838645808485318, 0.9504971251315797660}},
+    1.0 / 0.95047, 1.0 / 1.08883, 216.0 / 24389.0, 116.0, 16.0, 1.0 / 100.0, 500.0, 200.0, 1.0 / 255.0, 0.5};
 
 __constant__ double kDecodeCf[9] = {1.7917488588043277509, 0.82045614371976854984, 0.027694100686325412819,
                                     -0.00094244335181762134018, 0.000064355540911469709545,
@@ -77,9 +95,32 @@ __device__ __forceinline__ void floor_divmod(int v, int d, int *quot, int *rem) 
 __device__ __forceinline__ double decode_gamma(double x) {            // pixel.c:260-316
   int e, quot, rem;
   const double mant = frexp_normal(x, &e);
-  const double p = cheb9(kDecodeMono, 4.0 * mant - 3.0);
+  const double p = cheb9(kDecodeMono, fma(kk.four, mant, -kk.three));
   floor_divmod(e - 1, 5, &quot, &rem);
   return x * ldexp_normal(kDecodeP2[rem] * p, 7 * quot);
+}
+
+// kDecodeScale[e + 64] = kDecodeP2[(e-1) mod 5] * 2^(7 * floor((e-1)/5)) for the binary exponents e in [-64, 64): the
+// reference's power table and ldexp folded into one exact factor (a power of two times a table entry), filled on the
+// host once per device and copied to shared memory by every CTA -- the lanes of a warp index it with different
+// exponents, which a constant-bank read would serialise, and the integer floor-division by 5 plus the exponent
+// arithmetic (15 instructions per channel) disappears from a kernel that ncu shows to be issue-bound.
+__constant__ double kDecodeScale[128];
+
+__device__ __noinline__ double decode_gamma_far(double x) { return decode_gamma(x); }
+
+__device__ __forceinline__ double decode_gamma_tab(double x, const double *s_scale) {
+  const int hi = __double2hiint(x);
+  const int idx = ((hi >> 20) & 0x7ff) - (1022 - 64);
+  if (static_cast<unsigned>(idx) >= 128u) return decode_gamma_far(x);  // HDRI values far outside 0..QuantumRange
+  const double mant = __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(x));
+  const double p = cheb9(kDecodeMono, fma(kk.four, mant, -kk.three));
+  return x * (s_scale[idx] * p);
+}
+
+__device__ __forceinline__ double decode_pixel_gamma_tab(double pixel, const double *s_scale) {   // pixel.c:318
+  if (pixel <= kk.toe_limit) return pixel * kk.inv_12_92;
+  return kk.qr * decode_gamma_tab(fma(kk.qs, pixel, kk.c055) * kk.inv_1055, s_scale);
 }
 
 __device__ __forceinline__ double encode_gamma(double x) {            // pixel.c:380-443
@@ -91,8 +132,8 @@ __device__ __forceinline__ double encode_gamma(double x) {            // pixel.c
 }
 
 __device__ __forceinline__ double decode_pixel_gamma(double pixel) {   // pixel.c:318
-  if (pixel <= (0.0404482362771076 * QR)) return pixel * (1.0 / 12.92);
-  return QR * decode_gamma((QS * pixel + 0.055) * (1.0 / 1.055));
+  if (pixel <= kk.toe_limit) return pixel * kk.inv_12_92;
+  return kk.qr * decode_gamma(fma(kk.qs, pixel, kk.c055) * kk.inv_1055);
 }
 
 __device__ __forceinline__ double encode_pixel_gamma(double pixel) {   // pixel.c:445
@@ -105,12 +146,17 @@ constexpr double kCieEps = 216.0 / 24389.0, kCieK = 24389.0 / 27.0;
 
 // t^(1/3) for t in (216/24389, ~1.3]: z0 = 2^(-log2(t)/3) in fp32 (MUFU, ~2^-21), one Newton step
 // on z = t^(-1/3) (z1 = z0 + z0*(1 - t*z0^3)/3, error ~2^-41), result t*z1^2.
+// (lg2 / ex2 as the bare MUFU instructions: t is in (0.0088, ~1.4], so neither needs the range handling of log2f / exp2f,
+// which costs two divergent-branch regions per call.)
 __device__ __forceinline__ double cube_root(double t) {
   const float tf = static_cast<float>(t);
-  const double z0 = static_cast<double>(exp2f(__log2f(tf) * (-1.0f / 3.0f)));
+  float l, zf;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(tf));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(zf) : "f"(l * (-1.0f / 3.0f)));
+  const double z0 = static_cast<double>(zf);
   const double z2 = z0 * z0;
   const double e = fma(-t, z2 * z0, 1.0);
-  const double z1 = fma(z0 * (1.0 / 3.0), e, z0);
+  const double z1 = fma(z0 * kk.third, e, z0);
   return t * z1 * z1;
 }
 
@@ -118,15 +164,16 @@ __device__ __forceinline__ double cube_root(double t) {
 // it -- (CIEK*v/white + 16)/116 with IEEE divisions -- because L = 116*f(Y) - 16 cancels there: a black pixel
 // must give exactly 0, not -1e-13 (a huge ULP distance for a very common value).
 __device__ __forceinline__ double lab_f(double t, double v, double white) {
-  if (t > kCieEps) return cube_root(t);
+  if (t > kk.cie_eps) return cube_root(t);
   return (kCieK * v / white + 16.0) / 116.0;
 }
 
-__device__ __forceinline__ void rgb_to_xyz(double R, double G, double B, double &X, double &Y, double &Z) {
-  const double r = QS * decode_pixel_gamma(R), g = QS * decode_pixel_gamma(G), b = QS * decode_pixel_gamma(B);
-  X = (0.4123955889674142161 * r) + (0.3575834307637148171 * g) + (0.1804926473817015735 * b);
-  Y = (0.2125862307855955516 * r) + (0.7151703037034108499 * g) + (0.07220049864333622685 * b);
-  Z = (0.01929721549174694484 * r) + (0.1191838645808485318 * g) + (0.9504971251315797660 * b);
+__device__ __forceinline__ void rgb_to_xyz(double R, double G, double B, double &X, double &Y, double &Z, const double *s_scale) {
+  const double r = kk.qs * decode_pixel_gamma_tab(R, s_scale), g = kk.qs * decode_pixel_gamma_tab(G, s_scale),
+               b = kk.qs * decode_pixel_gamma_tab(B, s_scale);
+  X = fma(kk.m[0][2], b, fma(kk.m[0][1], g, kk.m[0][0] * r));
+  Y = fma(kk.m[1][2], b, fma(kk.m[1][1], g, kk.m[1][0] * r));
+  Z = fma(kk.m[2][2], b, fma(kk.m[2][1], g, kk.m[2][0] * r));
 }
 
 __device__ __forceinline__ void xyz_to_rgb(double X, double Y, double Z, double &R, double &G, double &B) {
@@ -145,6 +192,11 @@ enum Mode { kToLab, kToXyz, kToLinear, kFromLab, kFromXyz, kFromLinear };
 
 template <int CH, int MODE>
 __global__ void __launch_bounds__(256) colorspace_kernel(float *buf, size_t npixels) {
+  __shared__ double s_scale[128];
+  if (MODE == kToLinear || MODE == kToLab || MODE == kToXyz) {
+    if (threadIdx.x < 128) s_scale[threadIdx.x] = kDecodeScale[threadIdx.x];
+    __syncthreads();
+  }
   const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= npixels) return;
   float *q = buf + i * CH;
@@ -153,19 +205,19 @@ __global__ void __launch_bounds__(256) colorspace_kernel(float *buf, size_t npix
   else { in0 = q[0]; in1 = q[1]; in2 = q[2]; }
   double o0, o1, o2;
   if (MODE == kToLinear) {
-    o0 = decode_pixel_gamma(in0); o1 = decode_pixel_gamma(in1); o2 = decode_pixel_gamma(in2);
+    o0 = decode_pixel_gamma_tab(in0, s_scale); o1 = decode_pixel_gamma_tab(in1, s_scale); o2 = decode_pixel_gamma_tab(in2, s_scale);
   } else if (MODE == kFromLinear) {
     o0 = encode_pixel_gamma(in0); o1 = encode_pixel_gamma(in1); o2 = encode_pixel_gamma(in2);
   } else if (MODE == kToLab || MODE == kToXyz) {
     double X, Y, Z;
-    rgb_to_xyz(in0, in1, in2, X, Y, Z);
+    rgb_to_xyz(in0, in1, in2, X, Y, Z, s_scale);
     if (MODE == kToLab) {
-      const double x = lab_f(X * (1.0 / kIllX), X, kIllX), y = lab_f(Y, Y, 1.0), z = lab_f(Z * (1.0 / kIllZ), Z, kIllZ);
-      X = __dsub_rn(__dmul_rn(116.0, y), 16.0) * (1.0 / 100.0);   // unfused: 116*(16/116) - 16 must be exactly 0 (black)
-      Y = (500.0 * (x - y)) * (1.0 / 255.0) + 0.5;
-      Z = (200.0 * (y - z)) * (1.0 / 255.0) + 0.5;
+      const double x = lab_f(X * kk.inv_ill_x, X, kIllX), y = lab_f(Y, Y, 1.0), z = lab_f(Z * kk.inv_ill_z, Z, kIllZ);
+      X = __dsub_rn(__dmul_rn(kk.c116, y), kk.c16) * kk.inv100;   // unfused: 116*(16/116) - 16 must be exactly 0 (black)
+      Y = fma(kk.c500 * (x - y), kk.inv255, kk.half);
+      Z = fma(kk.c200 * (y - z), kk.inv255, kk.half);
     }
-    o0 = QR * X; o1 = QR * Y; o2 = QR * Z;
+    o0 = kk.qr * X; o1 = kk.qr * Y; o2 = kk.qr * Z;
   } else {
     double X = QS * in0, Y = QS * in1, Z = QS * in2;
     if (MODE == kFromLab) {                                  // colorspace-private.h:559-570, :531-557
@@ -186,8 +238,34 @@ __global__ void __launch_bounds__(256) colorspace_kernel(float *buf, size_t npix
   else { q[0] = static_cast<float>(o0); q[1] = static_cast<float>(o1); q[2] = static_cast<float>(o2); }
 }
 
+// kDecodeScale is per-device constant memory: filled once per device, before the first launch that reads it.
+int ensure_decode_scale() {
+  static std::mutex m;
+  static bool done[16] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return fail(MB200_ENODEVICE, "colorspace: no device");
+  std::lock_guard<std::mutex> lock(m);
+  if (done[dev]) return MB200_OK;
+  static const double p2[5] = {1.0, 2.6390158215457883983, 6.9644045063689921093, 1.8379173679952558018e+01,
+                               4.8502930128332728543e+01};            // kDecodeP2 (pixel.c:266-270)
+  double host[128];
+  for (int e = -64; e < 64; ++e) {
+    int q = (e - 1) / 5, r = (e - 1) - q * 5;                          // C div() + the reference's fix-up (pixel.c:310-315)
+    if (r < 0) { q -= 1; r += 5; }
+    host[e + 64] = std::ldexp(p2[r], 7 * q);
+  }
+  const cudaError_t err = cudaMemcpyToSymbol(kDecodeScale, host, sizeof(host));
+  if (err != cudaSuccess) return cuda_fail(err, "colorspace: table upload");
+  done[dev] = true;
+  return MB200_OK;
+}
+
 template <int MODE>
 int launch_mode(float *buf, size_t npixels, int channels, cudaStream_t s) {
+  if (MODE == kToLinear || MODE == kToLab || MODE == kToXyz) {
+    const int rc = ensure_decode_scale();
+    if (rc) return rc;
+  }
   const unsigned blocks = static_cast<unsigned>((npixels + 255) / 256);
   if (channels == 4) colorspace_kernel<4, MODE><<<blocks, 256, 0, s>>>(buf, npixels);
   else colorspace_kernel<3, MODE><<<blocks, 256, 0, s>>>(buf, npixels);

@@ -127,6 +127,10 @@ int launch_rotational_blur(const float *src, float *dst, size_t w, size_t h, int
 int launch_bilateral_blur(const float *src, float *dst, size_t w, size_t h, int channels, size_t width, size_t height,
                           double intensity_sigma, double spatial_sigma, void *stream);
 
+// ScaleImage (resize.c:4106): CSR contribution lists of both axes (mb200_scale_contributions), bit exact
+int launch_scale(const float *src, size_t w, size_t h, int channels, float *dst, size_t ow, size_t oh, const int *d_xoff,
+                 const int *d_xidx, const double *d_xwt, const int *d_yoff, const int *d_yidx, const double *d_ywt, void *stream);
+
 // SampleImage (resize.c:3907): nearest-sample gather, bit exact
 int launch_sample(const float *src, size_t w, size_t h, int channels, float *dst, size_t ow, size_t oh, void *stream);
 

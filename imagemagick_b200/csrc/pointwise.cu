@@ -395,6 +395,96 @@ int launch_resize_copy_channels(float *dst, const float *src, size_t w, size_t o
   return e == cudaSuccess ? MB200_OK : cuda_fail(e, "resize copy channels launch");
 }
 
+// ScaleImage (resize.c:4106): thread = output pixel; out = fold over its column list of (fold over its row list of the
+// premultiplied source samples), both folds as acc = acc + w * v with unfused double operations starting from 0 -- the
+// reference's y_vector / pixel accumulation -- then the alpha division of :4482-4503.  Bit exact.
+namespace {
+struct ScaleArgs {
+  const float *src;
+  float *dst;
+  int w, h, ow, oh;
+  const int *xoff, *xidx, *yoff, *yidx;     // CSR lists of both axes (device)
+  const double *xwt, *ywt;
+};
+
+template <int CH>
+__global__ void __launch_bounds__(128) scale_kernel(const ScaleArgs a) {
+  const int t = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
+  if (t >= a.ow) return;
+  constexpr bool kAlpha = (CH == 2 || CH == 4);
+  constexpr double kQS = 1.0 / 65535.0, kEps = 1.0e-12;
+  const int x0 = __ldg(a.xoff + t), x1 = __ldg(a.xoff + t + 1), y0 = __ldg(a.yoff + y), y1 = __ldg(a.yoff + y + 1);
+  double pixel[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) pixel[c] = 0.0;
+  for (int j = x0; j < x1; ++j) {
+    const int x = __ldg(a.xidx + j);
+    double col[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) col[c] = 0.0;
+    for (int k = y0; k < y1; ++k) {
+      const float *p = a.src + (static_cast<size_t>(__ldg(a.yidx + k)) * a.w + x) * CH;
+      const double wy = __ldg(a.ywt + k);
+      float v[CH];
+      if (CH == 4) { const float4 q = __ldg(reinterpret_cast<const float4 *>(p)); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[CH - 1] = q.w; }
+      else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) v[c] = __ldg(p + c);
+      }
+      const double alpha = kAlpha ? __dmul_rn(kQS, static_cast<double>(v[CH - 1])) : 1.0;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const double xv = (kAlpha && c != CH - 1) ? __dmul_rn(alpha, static_cast<double>(v[c])) : static_cast<double>(v[c]);
+        col[c] = __dadd_rn(col[c], __dmul_rn(wy, xv));
+      }
+    }
+    const double wx = __ldg(a.xwt + j);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) pixel[c] = __dadd_rn(pixel[c], __dmul_rn(wx, col[c]));
+  }
+  float o[CH];
+  if (kAlpha) {
+    const double g = __dmul_rn(kQS, pixel[CH - 1]);
+    const double sign = g < 0.0 ? -1.0 : 1.0;
+    const double r = __dmul_rn(sign, g) >= kEps ? __ddiv_rn(1.0, g) : __ddiv_rn(sign, kEps);
+#pragma unroll
+    for (int c = 0; c < CH - 1; ++c) o[c] = static_cast<float>(__dmul_rn(r, pixel[c]));
+    o[CH - 1] = static_cast<float>(pixel[CH - 1]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) o[c] = static_cast<float>(pixel[c]);
+  }
+  float *q = a.dst + (static_cast<size_t>(y) * a.ow + t) * CH;
+  if (CH == 4) *reinterpret_cast<float4 *>(q) = make_float4(o[0], o[1], o[2], o[CH - 1]);
+  else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) q[c] = o[c];
+  }
+}
+}  // namespace
+
+int launch_scale(const float *src, size_t w, size_t h, int channels, float *dst, size_t ow, size_t oh, const int *d_xoff,
+                 const int *d_xidx, const double *d_xwt, const int *d_yoff, const int *d_yidx, const double *d_ywt, void *stream) {
+  if (w > 0x3fffffffull || h > 0x3fffffffull || ow > 0x3fffffffull) return fail(MB200_EINVAL, "scale: image too large");
+  if (oh > 65535) return fail(MB200_EUNSUPPORTED, "scale: more than 65535 output rows");
+  if (channels == 4 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) != 0)
+    return fail(MB200_EINVAL, "scale: RGBA buffers must be 16-byte aligned");
+  ScaleArgs a{src, dst, static_cast<int>(w), static_cast<int>(h), static_cast<int>(ow), static_cast<int>(oh),
+              d_xoff, d_xidx, d_yoff, d_yidx, d_xwt, d_ywt};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 grid(static_cast<unsigned>((ow + 127) / 128), static_cast<unsigned>(oh));
+  switch (channels) {
+    case 1: scale_kernel<1><<<grid, 128, 0, s>>>(a); break;
+    case 2: scale_kernel<2><<<grid, 128, 0, s>>>(a); break;
+    case 3: scale_kernel<3><<<grid, 128, 0, s>>>(a); break;
+    case 4: scale_kernel<4><<<grid, 128, 0, s>>>(a); break;
+    default: return fail(MB200_EINVAL, "scale: 1..4 channels");
+  }
+  count_launch();
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MB200_OK : cuda_fail(e, "scale launch");
+}
+
 int launch_unsharp_combine(const float *src, float *blur_inout, size_t n, double gain, double quantum_threshold,
                            void *stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);

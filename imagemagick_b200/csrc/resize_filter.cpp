@@ -14,6 +14,8 @@
 #include "mb200_internal.h"
 
 #include <cmath>
+#include <utility>
+#include <vector>
 #include <vector>
 
 namespace {
@@ -265,6 +267,69 @@ long mb200_resize_contributions(int filter, size_t in_n, size_t out_n, double fa
     count[o] = static_cast<int>(n);
   }
   return need;
+}
+
+// ScaleImage (resize.c:4106-4530) is a sequential state machine whose weights do not depend on the pixels: the running
+// (span, scale) pairs are simulated here in the reference's own order and arithmetic, and recorded per output as a list of
+// (source index, weight) terms in accumulation order.  axis 1 = rows (the y machine pulls source rows per output row,
+// :4229-4330), axis 0 = columns (the x machine pushes every source column into the outputs it overlaps, :4378-4440).
+// offsets has out_n + 1 entries; index / weight hold offsets[out_n] terms (query the count with index == NULL).
+long mb200_scale_contributions(int axis, size_t in_n, size_t out_n, long *offsets, int *index, double *weight, size_t max_terms) {
+  if (in_n == 0 || out_n == 0 || !offsets) return mb200::fail(MB200_EINVAL, "bad scale geometry");
+  std::vector<std::vector<std::pair<int, double>>> lists(out_n);
+  const double factor = static_cast<double>(out_n) / static_cast<double>(in_n);
+  if (in_n == out_n) {
+    for (size_t o = 0; o < out_n; ++o) lists[o].emplace_back(static_cast<int>(o), 1.0);      // taken as is (:4190, :4336)
+  } else if (axis == 1) {
+    long number_rows = 0, next = 0;
+    int cur = 0;
+    bool next_row = true;
+    double span = 1.0, scale = factor;
+    for (size_t y = 0; y < out_n; ++y) {
+      while (scale < span) {
+        if (next_row && number_rows < static_cast<long>(in_n)) { cur = static_cast<int>(next++); ++number_rows; }
+        lists[y].emplace_back(cur, scale);                       // y_vector += scale.y * x_vector
+        span -= scale;
+        scale = factor;
+        next_row = true;
+      }
+      if (next_row && number_rows < static_cast<long>(in_n)) { cur = static_cast<int>(next++); ++number_rows; next_row = false; }
+      lists[y].emplace_back(cur, span);                          // pixel = y_vector + span.y * x_vector
+      scale -= span;
+      if (scale <= 0) { scale = factor; next_row = true; }
+      span = 1.0;
+    }
+  } else {
+    long t = 0;
+    bool next_column = false;
+    double span = 1.0;
+    auto add = [&](long out, size_t x, double w) { if (out >= 0 && out < static_cast<long>(out_n)) lists[static_cast<size_t>(out)].emplace_back(static_cast<int>(x), w); };
+    for (size_t x = 0; x < in_n; ++x) {
+      double scale = factor;
+      while (scale >= span) {
+        if (next_column) ++t;                                    // pixel = 0 for a new output
+        add(t, x, span);
+        scale -= span;
+        span = 1.0;
+        next_column = true;
+      }
+      if (scale > 0) {
+        if (next_column) { next_column = false; ++t; }
+        add(t, x, scale);
+        span -= scale;
+      }
+    }
+    if (span > 0 && !next_column) add(t, in_n - 1, span);         // :4433-4440 (only a still-open output is stored again)
+  }
+  long total = 0;
+  for (size_t o = 0; o < out_n; ++o) { offsets[o] = total; total += static_cast<long>(lists[o].size()); }
+  offsets[out_n] = total;
+  if (!index || !weight) return total;
+  if (static_cast<long>(max_terms) < total) return mb200::fail(MB200_EINVAL, "max_terms %zu < %ld", max_terms, total);
+  long k = 0;
+  for (size_t o = 0; o < out_n; ++o)
+    for (const auto &term : lists[o]) { index[k] = term.first; weight[k] = term.second; ++k; }
+  return total;
 }
 
 // The source sample a Copy-trait channel takes for every output of one axis (resize.c:3697-3707):

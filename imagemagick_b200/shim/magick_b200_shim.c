@@ -7,7 +7,7 @@
           --wrap=MorphologyImage,--wrap=ResizeImage,--wrap=TransformImageColorspace,\
           --wrap=BilevelImage,--wrap=BlackThresholdImage,--wrap=WhiteThresholdImage,--wrap=ClampImage,\
           --wrap=SharpenImage,--wrap=EdgeImage,--wrap=SampleImage,--wrap=ThumbnailImage,--wrap=MinifyImage,--wrap=ResampleImage,--wrap=MotionBlurImage,\
-          --wrap=EmbossImage,--wrap=EqualizeImage,--wrap=StatisticImage,--wrap=RotationalBlurImage,--wrap=BilateralBlurImage
+          --wrap=EmbossImage,--wrap=EqualizeImage,--wrap=StatisticImage,--wrap=RotationalBlurImage,--wrap=BilateralBlurImage,--wrap=ScaleImage
   and every caller of those exported functions (effect.c:765/1709/1170/4256, morphology.c:4129,
   resize.c:3761, colorspace.c:1751, threshold.c:805/927/2518/1087) reaches __wrap_X below.  Each wrapper follows the accelerate
   hook contract of effect.c:783-787 / resize.c:3818-3826: try the GPU; if the image is not
@@ -340,6 +340,34 @@ Image *B200AccelerateSampleImage(const Image *image, const size_t columns, const
       q = GetAuthenticPixels(out, 0, 0, columns, rows, attempt);
       if (q == (Quantum *) NULL || b200_cache_pixels(out, ch, attempt) != (float *) q ||
           mb200_sample_image(p, image->columns, image->rows, ch, (float *) q, columns, rows) != MB200_OK ||
+          SyncAuthenticPixels(out, attempt) == MagickFalse)
+        out = DestroyImage(out);
+    }
+    B200_ATTEMPT_END;
+  }
+  if (out != (Image *) NULL) out->type = image->type;
+  return out;
+}
+
+/* ---- ScaleImage (resize.c:4106) --------------------------------------------------------------------------------------------- */
+Image *B200AccelerateScaleImage(const Image *image, const size_t columns, const size_t rows, ExceptionInfo *exception)
+{
+  const int ch = b200_channels(image);
+  const float *p;
+  Quantum *q;
+  Image *out;
+  (void) exception;
+  if (ch == 0 || columns == 0 || rows == 0 || mb200_device_count() <= 0) return (Image *) NULL;
+  if ((columns == image->columns) && (rows == image->rows)) return (Image *) NULL;      /* plain clone: CPU */
+  {
+    B200_ATTEMPT_BEGIN;
+    out = (Image *) NULL;
+    p = b200_cache_pixels(image, ch, attempt);
+    if (p != (const float *) NULL) out = new_result(image, columns, rows, attempt);
+    if (out != (Image *) NULL) {
+      q = GetAuthenticPixels(out, 0, 0, columns, rows, attempt);
+      if (q == (Quantum *) NULL || b200_cache_pixels(out, ch, attempt) != (float *) q ||
+          mb200_scale_image(p, image->columns, image->rows, ch, (float *) q, columns, rows) != MB200_OK ||
           SyncAuthenticPixels(out, attempt) == MagickFalse)
         out = DestroyImage(out);
     }
@@ -723,6 +751,13 @@ MagickBooleanType __wrap_EqualizeImage(Image *image, ExceptionInfo *exception)
 {
   TRY_BOOL(B200AccelerateEqualizeImage(image, exception));
   return __real_EqualizeImage(image, exception);
+}
+
+extern Image *__real_ScaleImage(const Image *, const size_t, const size_t, ExceptionInfo *);
+Image *__wrap_ScaleImage(const Image *image, const size_t columns, const size_t rows, ExceptionInfo *exception)
+{
+  TRY(B200AccelerateScaleImage(image, columns, rows, exception));
+  return __real_ScaleImage(image, columns, rows, exception);
 }
 
 Image *__wrap_SampleImage(const Image *image, const size_t columns, const size_t rows, ExceptionInfo *exception)

@@ -20,6 +20,7 @@ extern Image *__real_MorphologyImage(const Image *, const MorphologyMethod, cons
 extern Image *__real_ResizeImage(const Image *, const size_t, const size_t, const FilterType, ExceptionInfo *);
 extern MagickBooleanType __real_TransformImageColorspace(Image *, const ColorspaceType, ExceptionInfo *);
 extern Image *__real_SampleImage(const Image *, const size_t, const size_t, ExceptionInfo *);
+extern Image *__real_ScaleImage(const Image *, const size_t, const size_t, ExceptionInfo *);
 extern Image *__real_ThumbnailImage(const Image *, const size_t, const size_t, ExceptionInfo *);
 extern Image *__real_MinifyImage(const Image *, ExceptionInfo *);
 extern Image *__real_MotionBlurImage(const Image *, const double, const double, const double, ExceptionInfo *);
@@ -107,6 +108,8 @@ int main(void)
   CHECK("MinifyImage RGBA (Spline 2x)", 1, MinifyImage(rgba, ex), CPU(__real_MinifyImage(rgba, ex)));
   CHECK("ResampleImage 36 dpi RGB (Lanczos)", 1, ResampleImage(rgb, 36.0, 36.0, LanczosFilter, ex), CPU(__real_ResampleImage(rgb, 36.0, 36.0, LanczosFilter, ex)));
   CHECK("SampleImage 517x389 -> 100x77 RGBA", 0, SampleImage(rgba, 100, 77, ex), CPU(__real_SampleImage(rgba, 100, 77, ex)));
+  CHECK("ScaleImage 517x389 -> 200x150 RGBA", 0, ScaleImage(rgba, 200, 150, ex), CPU(__real_ScaleImage(rgba, 200, 150, ex)));
+  CHECK("ScaleImage 300x200 -> 450x333 RGB", 0, ScaleImage(rgb, 450, 333, ex), CPU(__real_ScaleImage(rgb, 450, 333, ex)));
   CHECK("SharpenImage(0,1) RGBA", 1, SharpenImage(rgba, 0.0, 1.0, ex), CPU(__real_SharpenImage(rgba, 0.0, 1.0, ex)));
   CHECK("EdgeImage(1) RGB", 1, EdgeImage(rgb, 1.0, ex), CPU(__real_EdgeImage(rgb, 1.0, ex)));
   CHECK("StatisticImage Median 3x3 RGBA", 0, StatisticImage(rgba, MedianStatistic, 3, 3, ex), CPU(__real_StatisticImage(rgba, MedianStatistic, 3, 3, ex)));
@@ -246,7 +249,7 @@ int main(void)
     t = DestroyImage(t);
   }
   printf("gpu hits %ld, cpu fallbacks %ld\n", B200ShimHits(), B200ShimFallbacks());
-  if (mb200_device_count() > 0 && B200ShimHits() < 30) { printf("FAIL: operators did not reach the GPU path\n"); failures++; }
+  if (mb200_device_count() > 0 && B200ShimHits() < 32) { printf("FAIL: operators did not reach the GPU path\n"); failures++; }
   rgba = DestroyImage(rgba); rgb = DestroyImage(rgb);
   ex = DestroyExceptionInfo(ex);
   MagickCoreTerminus();

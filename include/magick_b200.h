@@ -151,7 +151,7 @@ MB200_API int mb200_trim(size_t keep_bytes);
    the co-limit of the FP64-accumulating convolution kernels (bench.py's second roofline entry). */
 MB200_API int mb200_probe_fp64_fma_rate(double *fma_per_second);
 /* Test / developer hook: force the generic kernels ("no_rank1", "no_morph_stream", "no_resize_stream",
-   "resize_regular_h", "no_fused_unsharp"; initialised from the MB200_<NAME> environment variables). */
+   "resize_regular_h", "no_fused_unsharp", "resize_fused"; initialised from the MB200_<NAME> environment variables). */
 MB200_API int mb200_set_option(const char *name, int value);
 
 /* ------------------------------------------ pixel cache staged into HBM ---- */
@@ -300,6 +300,13 @@ MB200_API int mb200_resize_image_dev(const float *src, size_t width, size_t heig
    (0.5 - MagickEpsilon; the "sample:offset" artifact is the shim's decline), bit exact. */
 MB200_API int mb200_sample_image_dev(const float *src, size_t width, size_t height, int channels,
     float *dst, size_t out_width, size_t out_height, void *stream);
+/* ScaleImage (MagickCore/resize.c:4106): box scaling.  The reference's sequential (span, scale) state machines are
+   simulated on the host (mb200_scale_contributions) into per-output term lists; the gather kernel accumulates them in
+   the reference's order with unfused double operations: bit exact, reductions and enlargements alike. */
+MB200_API int mb200_scale_image_dev(const float *src, size_t width, size_t height, int channels,
+    float *dst, size_t out_width, size_t out_height, void *stream);
+MB200_API long mb200_scale_contributions(int axis, size_t in_n, size_t out_n, long *offsets, int *index,
+    double *weight, size_t max_terms);
 /* ThumbnailImage (MagickCore/resize.c:4591-4650), pixel path only: SampleImage to 4x the target when both
    integer reduction factors exceed 4, ResizeImage(BoxFilter) to 2x when they exceed 2, then
    ResizeImage(`filter` = image->filter; UndefinedFilter selects LanczosSharp like the reference).  The
@@ -375,6 +382,8 @@ MB200_API int mb200_emboss_image(const float *src, float *dst, size_t width, siz
 MB200_API int mb200_resize_image(const float *src, size_t width, size_t height, int channels,
     float *dst, size_t out_width, size_t out_height, int filter);
 MB200_API int mb200_sample_image(const float *src, size_t width, size_t height, int channels,
+    float *dst, size_t out_width, size_t out_height);
+MB200_API int mb200_scale_image(const float *src, size_t width, size_t height, int channels,
     float *dst, size_t out_width, size_t out_height);
 MB200_API int mb200_thumbnail_image(const float *src, size_t width, size_t height, int channels,
     float *dst, size_t columns, size_t rows, int filter);

@@ -1410,6 +1410,95 @@ int orc_emboss(const float *src, float *dst, size_t w, size_t h, int ch, double 
   return orc_equalize(dst, w, h, ch, 1);
 }
 
+/* ------------------------------------------------------------------------------------------
+   resize.c:4106-4530 ScaleImage: box scaling as a sequential state machine -- rows are accumulated into y_vector with
+   the running (span.y, scale.y) pair, each finished scanline is then accumulated along x with (span.x, scale.x); colour
+   channels of images with alpha are premultiplied by QS*alpha on the way in (:4199-4215) and divided by the scaled alpha
+   on the way out (:4482-4503).  Restated literally (same state updates, same multiply-then-add order).
+   ------------------------------------------------------------------------------------------ */
+int orc_scale(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh)
+{
+  const int has_alpha = (ch == 2 || ch == 4);
+  const size_t n = w * (size_t) ch, on = ow * (size_t) ch;
+  double *x_vector, *y_vector, *scanline, *scale_scanline, pixel[4];
+  double span_x, span_y = 1.0, scale_x, scale_y;
+  long number_rows = 0, row = 0, y;
+  int next_row = 1, next_column, c;
+  if (ow == 0 || oh == 0 || ch < 1 || ch > 4) return -1;
+  if (ow == w && oh == h) { memcpy(dst, src, n * h * sizeof(float)); return 0; }
+  x_vector = (double *) malloc(n * sizeof(double));
+  y_vector = (double *) calloc(n, sizeof(double));
+  scanline = (h != oh) ? (double *) malloc(n * sizeof(double)) : x_vector;
+  scale_scanline = (double *) malloc((on > n ? on : n) * sizeof(double) + 4 * sizeof(double));
+  if (!x_vector || !y_vector || !scanline || !scale_scanline) return -1;
+  scale_y = (double) oh / (double) h;
+#define ORC_READ_ROW() do { const float *p = src + (size_t) row * n; size_t x_; double alpha_ = 1.0; row++; \
+    for (x_ = 0; x_ < w; x_++, p += ch) { if (has_alpha) alpha_ = QS * (double) p[ch - 1]; \
+      for (c = 0; c < ch; c++) x_vector[x_ * ch + c] = (has_alpha && c != ch - 1) ? alpha_ * (double) p[c] : (double) p[c]; } } while (0)
+  for (y = 0; y < (long) oh; y++) {
+    float *q = dst + (size_t) y * on;
+    size_t x;
+    if (oh == h) {
+      ORC_READ_ROW();
+    } else {
+      while (scale_y < span_y) {
+        if (next_row && number_rows < (long) h) { ORC_READ_ROW(); number_rows++; }
+        for (x = 0; x < n; x++) y_vector[x] += scale_y * x_vector[x];
+        span_y -= scale_y;
+        scale_y = (double) oh / (double) h;
+        next_row = 1;
+      }
+      if (next_row && number_rows < (long) h) { ORC_READ_ROW(); number_rows++; next_row = 0; }
+      for (x = 0; x < n; x++) { scanline[x] = y_vector[x] + span_y * x_vector[x]; y_vector[x] = 0.0; }
+      scale_y -= span_y;
+      if (scale_y <= 0) { scale_y = (double) oh / (double) h; next_row = 1; }
+      span_y = 1.0;
+    }
+    if (ow == w) {
+      for (x = 0; x < ow; x++, q += ch) {
+        double alpha = 1.0;
+        if (has_alpha) alpha = perceptible_reciprocal(QS * scanline[x * ch + ch - 1]);
+        for (c = 0; c < ch; c++)
+          q[c] = (float) ((has_alpha && c != ch - 1) ? alpha * scanline[x * ch + c] : scanline[x * ch + c]);
+      }
+      continue;
+    }
+    {
+      long t = 0;
+      for (c = 0; c < ch; c++) pixel[c] = 0.0;
+      next_column = 0;
+      span_x = 1.0;
+      for (x = 0; x < w; x++) {
+        scale_x = (double) ow / (double) w;
+        while (scale_x >= span_x) {
+          if (next_column) { for (c = 0; c < ch; c++) pixel[c] = 0.0; t++; }
+          for (c = 0; c < ch; c++) { pixel[c] += span_x * scanline[x * ch + c]; if (t < (long) ow) scale_scanline[t * ch + c] = pixel[c]; }
+          scale_x -= span_x;
+          span_x = 1.0;
+          next_column = 1;
+        }
+        if (scale_x > 0) {
+          if (next_column) { for (c = 0; c < ch; c++) pixel[c] = 0.0; next_column = 0; t++; }
+          for (c = 0; c < ch; c++) pixel[c] += scale_x * scanline[x * ch + c];
+          span_x -= scale_x;
+        }
+      }
+      if (span_x > 0) for (c = 0; c < ch; c++) pixel[c] += span_x * scanline[(x - 1) * ch + c];
+      if (!next_column && t < (long) ow) for (c = 0; c < ch; c++) scale_scanline[t * ch + c] = pixel[c];
+      for (x = 0; x < ow; x++, q += ch) {
+        double alpha = 1.0;
+        if (has_alpha) alpha = perceptible_reciprocal(QS * scale_scanline[x * ch + ch - 1]);
+        for (c = 0; c < ch; c++)
+          q[c] = (float) ((has_alpha && c != ch - 1) ? alpha * scale_scanline[x * ch + c] : scale_scanline[x * ch + c]);
+      }
+    }
+  }
+#undef ORC_READ_ROW
+  if (scanline != x_vector) free(scanline);
+  free(x_vector); free(y_vector); free(scale_scanline);
+  return 0;
+}
+
 /* resize.c:3907-4090 SampleImage (default sample:offset = 0.5 - MagickEpsilon) */
 int orc_sample(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh)
 {

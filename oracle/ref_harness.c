@@ -242,6 +242,15 @@ int ref_sample(const float *src, size_t w, size_t h, int ch, float *dst, size_t 
 }
 
 __attribute__((visibility("default")))
+int ref_scale(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh)
+{
+  BEGIN
+  im = make_image(src, w, h, ch, -1, ex);
+  if (im) { out = ScaleImage(im, ow, oh, ex); rc = export_image(out, dst, ow, oh, ch, ex); }
+  END
+}
+
+__attribute__((visibility("default")))
 int ref_thumbnail(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh)
 {
   BEGIN

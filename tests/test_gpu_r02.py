@@ -380,12 +380,12 @@ def test_fused_resize_matches_the_oracle_and_the_two_pass_kernels(filt, size, ki
     w, h = size
     src = make_image(w, h, 4, seed=71, kind=kind)
     d = _dev(src)
+    two_pass = _host(im.ResizeImage(d, w // 2, h // 2, filt))
+    util.set_option("resize_fused", 1)                    # opt-in kernel (measured slower than the two passes)
     n0 = im.launch_count()
     got = _host(im.ResizeImage(d, w // 2, h // 2, filt))
     launches = im.launch_count() - n0
-    util.set_option("no_resize_fused", 1)
-    two_pass = _host(im.ResizeImage(d, w // 2, h // 2, filt))
-    util.set_option("no_resize_fused", 0)
+    util.set_option("resize_fused", 0)
     assert launches == 2                                  # the fused kernel + the border outputs
     # same arithmetic in the same order, same float rounding between the passes: identical bits
     assert np.array_equal(got, two_pass)
@@ -394,3 +394,18 @@ def test_fused_resize_matches_the_oracle_and_the_two_pass_kernels(filt, size, ki
     d_ = util.ulp_distance(got, want)
     assert d_.max() <= 1
     assert (d_ == 0).mean() > 0.9999
+
+
+# ---- ScaleImage (resize.c:4106): the reference's sequential state machine as host-built term lists + a gather kernel ------
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("sizes", [((640, 480), (320, 240)), ((673, 451), (291, 313)), ((400, 300), (1000, 750)),
+                                   ((530, 370), (530, 200)), ((530, 370), (170, 370)), ((333, 211), (334, 212)),
+                                   ((1000, 30), (70, 90)), ((1024, 1024), (341, 341))])
+def test_scale_image_bit_exact(ch, sizes):
+    (w, h), (ow, oh) = sizes
+    src = make_image(w, h, ch, seed=91, kind="alpha_blocks" if ch in (2, 4) else "noise")
+    want = np.empty((oh, ow, ch), np.float32)
+    assert oracle().orc_scale(P(src), w, h, ch, P(want), ow, oh) == 0
+    got = _host(im.ScaleImage(_dev(src), ow, oh))
+    assert np.array_equal(got, want)
+    assert np.array_equal(im.ScaleImage(im.Image(src), ow, oh).pixels, want)       # host-buffer entry point

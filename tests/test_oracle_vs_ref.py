@@ -243,3 +243,16 @@ def test_emboss_bit_exact(ch, radius, sigma):
     assert util.oracle().orc_emboss(util.P(src), util.P(a), 83, 59, ch, radius, sigma) == 0
     assert util.ref().ref_emboss(util.P(src), util.P(b), 83, 59, ch, radius, sigma) == 0
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("sizes", [((64, 48), (32, 24)), ((67, 45), (29, 31)), ((40, 30), (100, 75)), ((53, 37), (53, 20)),
+                                   ((53, 37), (17, 37)), ((33, 21), (34, 22)), ((100, 3), (7, 9)), ((256, 256), (85, 85))])
+def test_scale_image_bit_exact(ch, sizes):
+    """ScaleImage (resize.c:4106): the box-scaling state machine restated literally."""
+    (w, h), (ow, oh) = sizes
+    src = util.make_image(w, h, ch, seed=81, kind="alpha_blocks" if ch in (2, 4) else "noise")
+    a, b = np.empty((oh, ow, ch), np.float32), np.empty((oh, ow, ch), np.float32)
+    assert util.oracle().orc_scale(util.P(src), w, h, ch, util.P(a), ow, oh) == 0
+    assert util.ref().ref_scale(util.P(src), w, h, ch, util.P(b), ow, oh) == 0
+    assert np.array_equal(a, b)
