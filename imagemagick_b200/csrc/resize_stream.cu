@@ -574,6 +574,10 @@ int launch_sn(StreamArgs a, int axis, cudaStream_t s) {
   if (nstrips <= 0 || nstrips > 65535 || lanes_blocks > 65535) return MB200_EUNSUPPORTED;
   if (axis == 1) {
     resize_v_stream_kernel<S, N><<<dim3(lanes_blocks, nstrips), 128, 0, s>>>(a);
+  } else if (chunk_env == 16 && slots_env == 2) {  // experiment: 256-byte chunks, 2-slot rings, 3 CTAs / SM
+    constexpr int smem = 4 * 2 * HRing<16>::kSlotBytes;
+    cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 2, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    resize_h_stream_kernel<S, N, 2, 3, 16><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a);
   } else if (chunk_env == 16) {                    // 256-byte chunks, 3-slot rings, 2 CTAs / SM
     constexpr int smem = 4 * 3 * HRing<16>::kSlotBytes;
     cudaFuncSetAttribute(resize_h_stream_kernel<S, N, 3, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device; cheap
