@@ -250,6 +250,12 @@ def BilateralBlurImage(image: Image, width: int, height: int, intensity_sigma: f
                          float(intensity_sigma), float(spatial_sigma))
 
 
+def SelectiveBlurImage(image: Image, radius: float, sigma: float, threshold: float) -> Image:
+    """MagickCore/effect.c:3406 (threshold in quantum units)."""
+    return _same_size_op(image, "mb200_selective_blur_image_dev", "mb200_selective_blur_image", float(radius), float(sigma),
+                         float(threshold))
+
+
 def MotionBlurImage(image: Image, radius: float, sigma: float, angle: float) -> Image:
     """MagickCore/effect.c:2347."""
     return _same_size_op(image, "mb200_motion_blur_image_dev", "mb200_motion_blur_image", float(radius), float(sigma),

@@ -126,6 +126,9 @@ int launch_statistic(const float *src, float *dst, size_t w, size_t h, int chann
 int launch_rotational_blur(const float *src, float *dst, size_t w, size_t h, int channels, double angle, void *stream);
 int launch_bilateral_blur(const float *src, float *dst, size_t w, size_t h, int channels, size_t width, size_t height,
                           double intensity_sigma, double spatial_sigma, void *stream);
+// SelectiveBlurImage (effect.c:3406)
+int launch_selective_blur(const float *src, float *dst, size_t w, size_t h, int channels, double radius, double sigma,
+                          double threshold, void *stream);
 
 // ScaleImage (resize.c:4106): CSR contribution lists of both axes (mb200_scale_contributions), bit exact
 int launch_scale(const float *src, size_t w, size_t h, int channels, float *dst, size_t ow, size_t oh, const int *d_xoff,

@@ -3,6 +3,7 @@
 //                                                             StandardDeviation, Contrast)
 //   RotationalBlurImage  MagickCore/effect.c:3129-3400
 //   BilateralBlurImage   MagickCore/effect.c:821-1165
+//   SelectiveBlurImage   MagickCore/effect.c:3406-3700
 // One thread per output pixel, all channels of the pixel in one pass over the window (the per-channel accumulation
 // order of the reference -- window order, sequential double adds -- is kept, and every operation is an UNFUSED IEEE double
 // operation, so the results are bit-identical to the reference's).  Neighbours are fetched through the read-only path
@@ -261,6 +262,73 @@ __global__ void __launch_bounds__(128) bilateral_kernel(const float *__restrict_
   store_pixel<CH>(dst, centre, o);
 }
 
+// -------------------------------------------------------------------------------------------- SelectiveBlurImage
+// Double intensity plane (one pre-pass): the reference compares the centre's double intensity with, for the alpha-blended
+// colour channels, the neighbour's double intensity (:3640) and, for the others, the FLOAT it stored in its GRAY clone
+// (colorspace.c:943) -- which is the same double rounded to float, so one plane serves both.
+template <int CH>
+__global__ void __launch_bounds__(256) intensity_plane_kernel(const float *__restrict__ src, double *__restrict__ out, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  float v[CH];
+  load_pixel<CH>(src, i, v);
+  out[i] = pixel_intensity<CH>(v);
+}
+
+// window top-left (x - j, y - j), j = (width-1)/2, edge replicated; taps in window order, unfused.
+template <int CH>
+__global__ void __launch_bounds__(128) selective_blur_kernel(const float *__restrict__ src, const double *__restrict__ lum,
+                                                             float *__restrict__ dst, int w, int h, int W,
+                                                             const double *__restrict__ taps, double threshold) {
+  const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  constexpr bool kAlpha = (CH == 2 || CH == 4);
+  const int j = (W - 1) / 2;
+  const size_t centre = static_cast<size_t>(y) * w + x;
+  const double intensity = lum[centre];
+  double plain[CH], blend[CH], gamma_plain = 0.0, gamma_blend = 0.0;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) plain[c] = blend[c] = 0.0;
+  int k = 0;
+  for (int v = 0; v < W; ++v) {
+    const size_t row = static_cast<size_t>(min(max(y - j + v, 0), h - 1)) * w;
+    for (int u = 0; u < W; ++u, ++k) {
+      const size_t idx = row + min(max(x - j + u, 0), w - 1);
+      const double li = __ldg(lum + idx);
+      const bool take_plain = fabs(__dsub_rn(static_cast<double>(static_cast<float>(li)), intensity)) < threshold;
+      const bool take_blend = kAlpha && fabs(__dsub_rn(li, intensity)) < threshold;
+      if (!take_plain && !take_blend) continue;
+      const double t = __ldg(taps + k);
+      float r[CH];
+      load_pixel<CH>(src, idx, r);
+      if (take_plain) {
+        gamma_plain = __dadd_rn(gamma_plain, t);
+        if (kAlpha) plain[CH - 1] = __dadd_rn(plain[CH - 1], __dmul_rn(t, static_cast<double>(r[CH - 1])));
+        else {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) plain[c] = __dadd_rn(plain[c], __dmul_rn(t, static_cast<double>(r[c])));
+        }
+      }
+      if (take_blend) {
+        const double ta = __dmul_rn(t, __dmul_rn(kQS, static_cast<double>(r[CH - 1])));
+        gamma_blend = __dadd_rn(gamma_blend, ta);
+#pragma unroll
+        for (int c = 0; c < CH - 1; ++c) blend[c] = __dadd_rn(blend[c], __dmul_rn(ta, static_cast<double>(r[c])));
+      }
+    }
+  }
+  float p[CH], o[CH];
+  load_pixel<CH>(src, centre, p);
+  const bool keep_plain = fabs(gamma_plain) < kEps, keep_blend = fabs(gamma_blend) < kEps;
+  const double gp = perceptible_reciprocal(gamma_plain), gb = perceptible_reciprocal(gamma_blend);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    if (kAlpha && c != CH - 1) o[c] = keep_blend ? p[c] : static_cast<float>(__dmul_rn(gb, blend[c]));
+    else o[c] = keep_plain ? p[c] : static_cast<float>(__dmul_rn(gp, plain[c]));
+  }
+  store_pixel<CH>(dst, centre, o);
+}
+
 int check_image(const float *src, float *dst, size_t w, size_t h, int channels, const char *what) {
   if (!src || !dst || w == 0 || h == 0 || w > 0x3fffffffull || h > 65535ull * 32768ull) return fail(MB200_EINVAL, "%s: bad geometry", what);
   if (h > 65535) return fail(MB200_EUNSUPPORTED, "%s: more than 65535 rows", what);
@@ -387,6 +455,48 @@ int launch_bilateral_blur(const float *src, float *dst, size_t w, size_t h, int 
   cudaFreeAsync(d_i8, s);
   cudaFreeAsync(d_tables, s);
   return e == cudaSuccess ? MB200_OK : cuda_fail(e, "bilateral blur launch");
+}
+
+int launch_selective_blur(const float *src, float *dst, size_t w, size_t h, int channels, double radius, double sigma,
+                          double threshold, void *stream) {
+  int rc = check_image(src, dst, w, h, channels, "selective blur");
+  if (rc) return rc;
+  const size_t W = mb200_optimal_kernel_width_1d(radius, sigma);
+  if (W > 255) return fail(MB200_EUNSUPPORTED, "selective blur: window larger than 255");
+  // effect.c:3467-3478: exp(-(u^2+v^2)/(2 s^2)) / (2 pi s^2), not normalised (gamma does that per pixel)
+  const double kPi = 3.14159265358979323846264338327950288419716939937510;
+  const double sg = std::fabs(sigma) < kEps ? kEps : sigma;
+  const long j = static_cast<long>(W - 1) / 2;
+  std::vector<double> taps(W * W);
+  size_t n = 0;
+  for (long v = -j; v <= j; ++v)
+    for (long u = -j; u <= j; ++u)
+      taps[n++] = std::exp(-(static_cast<double>(u) * u + v * v) / (2.0 * sg * sg)) / (2.0 * kPi * sg * sg);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  double *d_taps = nullptr, *d_lum = nullptr;
+  rc = upload_table(taps, &d_taps, s);
+  if (rc) return rc;
+  const size_t npix = w * h;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&d_lum), npix * sizeof(double), temp_pool(), s);
+  if (e != cudaSuccess) { cudaFreeAsync(d_taps, s); return cuda_fail(e, "selective blur: intensity plane"); }
+  const unsigned pgrid = static_cast<unsigned>((npix + 255) / 256);
+  dim3 grid(static_cast<unsigned>((w + 127) / 128), static_cast<unsigned>(h));
+  const int iw = static_cast<int>(w), ih = static_cast<int>(h), iW = static_cast<int>(W);
+  switch (channels) {
+    case 1: intensity_plane_kernel<1><<<pgrid, 256, 0, s>>>(src, d_lum, npix);
+            selective_blur_kernel<1><<<grid, 128, 0, s>>>(src, d_lum, dst, iw, ih, iW, d_taps, threshold); break;
+    case 2: intensity_plane_kernel<2><<<pgrid, 256, 0, s>>>(src, d_lum, npix);
+            selective_blur_kernel<2><<<grid, 128, 0, s>>>(src, d_lum, dst, iw, ih, iW, d_taps, threshold); break;
+    case 3: intensity_plane_kernel<3><<<pgrid, 256, 0, s>>>(src, d_lum, npix);
+            selective_blur_kernel<3><<<grid, 128, 0, s>>>(src, d_lum, dst, iw, ih, iW, d_taps, threshold); break;
+    default: intensity_plane_kernel<4><<<pgrid, 256, 0, s>>>(src, d_lum, npix);
+             selective_blur_kernel<4><<<grid, 128, 0, s>>>(src, d_lum, dst, iw, ih, iW, d_taps, threshold); break;
+  }
+  count_launch(2);
+  e = cudaGetLastError();
+  cudaFreeAsync(d_lum, s);
+  cudaFreeAsync(d_taps, s);
+  return e == cudaSuccess ? MB200_OK : cuda_fail(e, "selective blur launch");
 }
 
 }  // namespace mb200

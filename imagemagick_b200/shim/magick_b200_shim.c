@@ -7,7 +7,7 @@
           --wrap=MorphologyImage,--wrap=ResizeImage,--wrap=TransformImageColorspace,\
           --wrap=BilevelImage,--wrap=BlackThresholdImage,--wrap=WhiteThresholdImage,--wrap=ClampImage,\
           --wrap=SharpenImage,--wrap=EdgeImage,--wrap=SampleImage,--wrap=ThumbnailImage,--wrap=MinifyImage,--wrap=ResampleImage,--wrap=MotionBlurImage,\
-          --wrap=EmbossImage,--wrap=EqualizeImage,--wrap=StatisticImage,--wrap=RotationalBlurImage,--wrap=BilateralBlurImage,--wrap=ScaleImage
+          --wrap=EmbossImage,--wrap=EqualizeImage,--wrap=StatisticImage,--wrap=RotationalBlurImage,--wrap=BilateralBlurImage,--wrap=ScaleImage,--wrap=SelectiveBlurImage
   and every caller of those exported functions (effect.c:765/1709/1170/4256, morphology.c:4129,
   resize.c:3761, colorspace.c:1751, threshold.c:805/927/2518/1087) reaches __wrap_X below.  Each wrapper follows the accelerate
   hook contract of effect.c:783-787 / resize.c:3818-3826: try the GPU; if the image is not
@@ -551,7 +551,7 @@ Image *B200AccelerateEmbossImage(const Image *image, const double radius, const 
 }
 
 /* ---- StatisticImage (statistic.c:2918), RotationalBlurImage (effect.c:3129), BilateralBlurImage (effect.c:821) -------------- */
-typedef struct { int type; size_t width, height; double a, b; } stencil_args;
+typedef struct { int type; size_t width, height; double a, b, c; } stencil_args;
 static int op_statistic(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
 { const stencil_args *t = (const stencil_args *) a; return mb200_statistic_image(s, d, w, h, ch, t->type, t->width, t->height); }
 static int op_rotational(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
@@ -568,14 +568,14 @@ Image *B200AccelerateStatisticImage(const Image *image, const StatisticType type
     case RootMeanSquareStatistic: case StandardDeviationStatistic: case ContrastStatistic: break;
     default: return (Image *) NULL;               /* Mode / Nonpeak walk the reference's skip list: CPU */
   }
-  a.type = (int) type; a.width = width; a.height = height; a.a = a.b = 0.0;
+  a.type = (int) type; a.width = width; a.height = height; a.a = a.b = a.c = 0.0;
   return run_same_size(image, op_statistic, &a, exception);
 }
 
 Image *B200AccelerateRotationalBlurImage(const Image *image, const double angle, ExceptionInfo *exception)
 {
   stencil_args a;
-  a.type = 0; a.width = a.height = 0; a.a = angle; a.b = 0.0;
+  a.type = 0; a.width = a.height = 0; a.a = angle; a.b = a.c = 0.0;
   return run_same_size(image, op_rotational, &a, exception);
 }
 
@@ -584,8 +584,21 @@ Image *B200AccelerateBilateralBlurImage(const Image *image, const size_t width, 
 {
   stencil_args a;
   if (equalize_eligible(image) == MagickFalse) return (Image *) NULL;        /* tonal weights use GetPixelIntensity */
-  a.type = 0; a.width = width; a.height = height; a.a = intensity_sigma; a.b = spatial_sigma;
+  a.type = 0; a.width = width; a.height = height; a.a = intensity_sigma; a.b = spatial_sigma; a.c = 0.0;
   return run_same_size(image, op_bilateral, &a, exception);
+}
+
+/* SelectiveBlurImage (effect.c:3406): one stage, so channel selections are exact (unselected channels copy the centre) */
+static int op_selective(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
+{ const stencil_args *t = (const stencil_args *) a; return mb200_selective_blur_image(s, d, w, h, ch, t->a, t->b, t->c); }
+
+Image *B200AccelerateSelectiveBlurImage(const Image *image, const double radius, const double sigma, const double threshold,
+                                        ExceptionInfo *exception)
+{
+  stencil_args a;
+  if (equalize_eligible(image) == MagickFalse) return (Image *) NULL;        /* contrast uses GetPixelIntensity */
+  a.type = 0; a.width = a.height = 0; a.a = radius; a.b = sigma; a.c = threshold;
+  return run_same_size_masked(image, op_selective, &a, 1, exception);
 }
 
 /* ---- ld --wrap entry points ------------------------------------------------------------------------------ */
@@ -736,6 +749,14 @@ Image *__wrap_BilateralBlurImage(const Image *image, const size_t width, const s
 {
   TRY(B200AccelerateBilateralBlurImage(image, width, height, intensity_sigma, spatial_sigma, exception));
   return __real_BilateralBlurImage(image, width, height, intensity_sigma, spatial_sigma, exception);
+}
+
+extern Image *__real_SelectiveBlurImage(const Image *, const double, const double, const double, ExceptionInfo *);
+Image *__wrap_SelectiveBlurImage(const Image *image, const double radius, const double sigma, const double threshold,
+                                 ExceptionInfo *exception)
+{
+  TRY(B200AccelerateSelectiveBlurImage(image, radius, sigma, threshold, exception));
+  return __real_SelectiveBlurImage(image, radius, sigma, threshold, exception);
 }
 
 extern Image *__real_EmbossImage(const Image *, const double, const double, ExceptionInfo *);

@@ -289,6 +289,9 @@ MB200_API int mb200_rotational_blur_image_dev(const float *src, float *dst, size
 /* BilateralBlurImage (MagickCore/effect.c:821), odd window sizes (even ones return MB200_EUNSUPPORTED), bit exact. */
 MB200_API int mb200_bilateral_blur_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
     size_t window_width, size_t window_height, double intensity_sigma, double spatial_sigma, void *stream);
+/* SelectiveBlurImage (MagickCore/effect.c:3406): contrast-gated Gaussian (threshold in quantum units), bit exact. */
+MB200_API int mb200_selective_blur_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
+    double radius, double sigma, double threshold, void *stream);
 /* MotionBlurImage (MagickCore/effect.c:2347) == AccelerateMotionBlurImage (accelerate-private.h). */
 MB200_API int mb200_motion_blur_image_dev(const float *src, float *dst, size_t width, size_t height,
     int channels, double radius, double sigma, double angle, void *stream);
@@ -376,6 +379,8 @@ MB200_API int mb200_rotational_blur_image(const float *src, float *dst, size_t w
     double angle);
 MB200_API int mb200_bilateral_blur_image(const float *src, float *dst, size_t width, size_t height, int channels,
     size_t window_width, size_t window_height, double intensity_sigma, double spatial_sigma);
+MB200_API int mb200_selective_blur_image(const float *src, float *dst, size_t width, size_t height, int channels,
+    double radius, double sigma, double threshold);
 MB200_API int mb200_equalize_image(float *buf, size_t width, size_t height, int channels, int sync_channels);
 MB200_API int mb200_emboss_image(const float *src, float *dst, size_t width, size_t height, int channels,
     double radius, double sigma);

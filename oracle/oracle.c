@@ -1693,6 +1693,66 @@ int orc_bilateral_blur(const float *src, float *dst, size_t w, size_t h, int ch,
 
 
 /* ------------------------------------------------------------------------------------------
+   effect.c:3406-3700 SelectiveBlurImage: a width x width Gaussian (GetOptimalKernelWidth1D, not normalised) of which only
+   the taps whose intensity differs from the centre pixel's by less than `threshold` take part.  Channels without the
+   Blend trait (no alpha, or the alpha channel) compare the FLOAT-rounded luminance of the neighbour -- the reference reads
+   it from a clone transformed to GRAYColorspace (colorspace.c:943-945) -- with the centre's double intensity; the
+   alpha-blended colour channels compare double intensities (:3640).  gamma == 0 (no tap qualifies) copies the centre.
+   ------------------------------------------------------------------------------------------ */
+int orc_selective_blur(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma, double threshold)
+{
+  const size_t width = orc_optimal_kernel_width_1d(radius, sigma);
+  const double s = fabs(sigma) < EPS ? EPS : sigma;
+  const long j = (long) (width - 1) / 2;
+  const int has_alpha = (ch == 2 || ch == 4);
+  double *kernel = (double *) malloc(width * width * sizeof(double));
+  long u, v, y;
+  size_t i = 0;
+  if (!kernel) return -1;
+  for (v = -j; v <= j; v++)
+    for (u = -j; u <= j; u++)
+      kernel[i++] = exp(-((double) u * u + v * v) / (2.0 * s * s)) / (2.0 * PI_ * s * s);
+#pragma omp parallel for schedule(static) private(u, v)
+  for (y = 0; y < (long) h; y++) {
+    long x;
+    for (x = 0; x < (long) w; x++) {
+      const float *p = src + ((size_t) y * w + (size_t) x) * ch;
+      const double intensity = pixel_intensity(p, ch);
+      int c;
+      for (c = 0; c < ch; c++) {
+        const int blend = has_alpha && c != ch - 1;
+        double pixel = 0.0, gamma = 0.0;
+        const double *k = kernel;
+        for (v = 0; v < (long) width; v++)
+          for (u = 0; u < (long) width; u++, k++) {
+            long xx = x - j + u, yy = y - j + v;
+            const float *r;
+            double contrast;
+            xx = xx < 0 ? 0 : (xx >= (long) w ? (long) w - 1 : xx);
+            yy = yy < 0 ? 0 : (yy >= (long) h ? (long) h - 1 : yy);
+            r = src + ((size_t) yy * w + (size_t) xx) * ch;
+            if (!blend) {
+              contrast = (double) (float) pixel_intensity(r, ch) - intensity;
+              if (fabs(contrast) < threshold) { pixel += (*k) * (double) r[c]; gamma += (*k); }
+            } else {
+              contrast = pixel_intensity(r, ch) - intensity;
+              if (fabs(contrast) < threshold) {
+                const double alpha = QS * (double) r[ch - 1];
+                pixel += (*k) * alpha * (double) r[c];
+                gamma += (*k) * alpha;
+              }
+            }
+          }
+        if (fabs(gamma) < EPS) dst[((size_t) y * w + (size_t) x) * ch + c] = p[c];
+        else dst[((size_t) y * w + (size_t) x) * ch + c] = (float) (perceptible_reciprocal(gamma) * pixel);
+      }
+    }
+  }
+  free(kernel);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
    effect.c:3129-3400 RotationalBlurImage (groundwork): n samples on the arc through the
    pixel about the image centre (cos/sin tables of theta*w - offset), every `step`-th one taken
    (step = blur_radius / radius, clamped to [1, n-1]); sample coordinates are (ssize_t)(value + 0.5)

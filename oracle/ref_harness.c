@@ -134,6 +134,15 @@ int ref_edge(const float *src, float *dst, size_t w, size_t h, int ch, double ra
 }
 
 __attribute__((visibility("default")))
+int ref_selective_blur(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma, double threshold)
+{
+  BEGIN
+  im = make_image(src, w, h, ch, -1, ex);
+  if (im) { out = SelectiveBlurImage(im, radius, sigma, threshold, ex); rc = export_image(out, dst, w, h, ch, ex); }
+  END
+}
+
+__attribute__((visibility("default")))
 int ref_emboss(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma)
 {
   BEGIN

@@ -372,6 +372,26 @@ def test_bilateral_blur_bit_exact(ch, win, isig, ssig):
     assert e.value.code == -5
 
 
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("args", [(0.0, 1.0, 6553.5), (0.0, 2.0, 20000.0), (2.0, 1.0, 1000.0), (0.0, 1.5, 131070.0), (0.0, 1.0, 0.0)])
+@pytest.mark.parametrize("kind", ["gradient", "noise"])
+def test_selective_blur_bit_exact(ch, args, kind):
+    """SelectiveBlurImage (effect.c:3406); threshold 0 selects no tap (every pixel keeps its centre value)."""
+    src = make_image(90, 70, ch, seed=64, kind="alpha_blocks" if ch in (2, 4) and kind == "gradient" else kind)
+    want = orc("orc_selective_blur", src, *args)
+    got = _host(im.SelectiveBlurImage(_dev(src), *args))
+    assert max_ulp(got, want) == 0
+
+
+def test_selective_blur_host_buffers_through_the_c_abi():
+    src = make_image(64, 48, 4, seed=65, kind="alpha_blocks")
+    want = orc("orc_selective_blur", src, 0.0, 1.5, 9000.0)
+    got = np.empty_like(src)
+    from imagemagick_b200 import _lib
+    rc = _lib.load().mb200_selective_blur_image(C.c_void_p(src.ctypes.data), C.c_void_p(got.ctypes.data), 64, 48, 4, 0.0, 1.5, 9000.0)
+    assert rc == 0 and max_ulp(got, want) == 0
+
+
 # ---- fused vertical + horizontal ResizeImage (equal integer reduction on both axes) ------------------------------------
 @pytest.mark.parametrize("filt", [22, 12, 11])            # Lanczos (12 taps at 2x), Mitchell, Catrom (8 taps)
 @pytest.mark.parametrize("size", [(2048, 1536), (2222, 1554), (4096, 130), (140, 4100)])

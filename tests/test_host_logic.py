@@ -239,3 +239,38 @@ def test_motion_blur_taps_and_offsets_match_the_reference(rad, sig, ang):
     for j in range(n):                      # out[y][x] = sum_j k_j * src[y + oy_j][x + ox_j], accumulated in tap order
         want[c - oy[j], c - ox[j]] += t[j]
     assert np.array_equal(dst[..., 0], want.astype(np.float32))
+
+
+@pytest.mark.parametrize("sizes", [((37, 23), (19, 11)), ((20, 14), (53, 31)), ((31, 17), (31, 9)), ((64, 8), (21, 8))])
+def test_scale_contribution_lists_reproduce_the_oracle(sizes):
+    """ScaleImage's term lists are host logic (resize_filter.cpp mb200_scale_contributions): folding them in float64 --
+    acc = acc + w * v, the arithmetic the gather kernel performs -- must reproduce the oracle's literal restatement of
+    the reference's state machine bit for bit (the oracle itself is pinned to the compiled reference)."""
+    (w, h), (ow, oh) = sizes
+    lib = _lib.load()
+    src = util.make_image(w, h, 3, seed=12)
+
+    def lists(axis, n_in, n_out):
+        off = (C.c_long * (n_out + 1))()
+        total = lib.mb200_scale_contributions(axis, n_in, n_out, off, None, None, 0)
+        assert total > 0
+        idx, wt = (C.c_int * total)(), (C.c_double * total)()
+        assert lib.mb200_scale_contributions(axis, n_in, n_out, off, idx, wt, total) == total
+        return list(off), list(idx), list(wt)
+
+    xo, xi, xw = lists(0, w, ow)
+    yo, yi, yw = lists(1, h, oh)
+    got = np.empty((oh, ow, 3), np.float32)
+    s64 = src.astype(np.float64)
+    for y in range(oh):
+        for t in range(ow):
+            pixel = np.zeros(3)
+            for j in range(xo[t], xo[t + 1]):
+                col = np.zeros(3)
+                for k in range(yo[y], yo[y + 1]):
+                    col = col + yw[k] * s64[yi[k], xi[j]]
+                pixel = pixel + xw[j] * col
+            got[y, t] = pixel.astype(np.float32)
+    want = np.empty((oh, ow, 3), np.float32)
+    assert util.oracle().orc_scale(util.P(src), w, h, 3, util.P(want), ow, oh) == 0
+    assert np.array_equal(got, want)

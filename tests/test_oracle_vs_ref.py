@@ -256,3 +256,14 @@ def test_scale_image_bit_exact(ch, sizes):
     assert util.oracle().orc_scale(util.P(src), w, h, ch, util.P(a), ow, oh) == 0
     assert util.ref().ref_scale(util.P(src), w, h, ch, util.P(b), ow, oh) == 0
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("args", [(0.0, 1.0, 6553.5), (0.0, 2.0, 20000.0), (2.0, 1.0, 1000.0), (0.0, 1.5, 65535.0 * 2)])
+def test_selective_blur_bit_exact(ch, args):
+    """SelectiveBlurImage (effect.c:3406): contrast-gated Gaussian; gray image clone + double intensities restated."""
+    src = util.make_image(61, 43, ch, seed=82, kind="alpha_blocks" if ch in (2, 4) else "gradient")
+    a, b = np.empty_like(src), np.empty_like(src)
+    assert util.oracle().orc_selective_blur(util.P(src), util.P(a), 61, 43, ch, *args) == 0
+    assert util.ref().ref_selective_blur(util.P(src), util.P(b), 61, 43, ch, *args) == 0
+    assert np.array_equal(a, b)

@@ -55,6 +55,7 @@ def oracle() -> C.CDLL:
         o.orc_colorspace.argtypes = [_fp, _sz, _sz, _i, _i, _i]
         o.orc_sample.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         o.orc_scale.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
+        o.orc_selective_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d, _d]
         o.orc_thumbnail.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         o.orc_kernel_builtin.argtypes = [_i, _d, _d, _d, _d, C.POINTER(OrcKernel)]
         o.orc_kernel_user.argtypes = [_sz, _sz, _l, _l, C.POINTER(_d), C.POINTER(OrcKernel)]
@@ -103,6 +104,7 @@ def ref() -> C.CDLL:
         r.ref_colorspace.argtypes = [_fp, _sz, _sz, _i, _i, _i]
         r.ref_sample.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         r.ref_scale.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
+        r.ref_selective_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d, _d]
         r.ref_thumbnail.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         r.ref_kernel.argtypes = [C.c_char_p, _i, C.POINTER(_d), _sz, C.POINTER(_sz), C.POINTER(_sz),
                                  C.POINTER(_l), C.POINTER(_l)]
