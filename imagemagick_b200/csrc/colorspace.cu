@@ -34,13 +34,23 @@ struct LabConstants {
   double third, qs, qr, toe_limit, inv_12_92, c055, inv_1055, four, three;
   double m[3][3];
   double inv_ill_x, inv_ill_z, cie_eps, c116, c16, inv100, c500, c200, inv255, half;
+  // folded forms of the sRGB -> Lab leg (see rgb_to_lab_unit): decode to [0, 1], white point inside the matrix rows,
+  // QuantumRange inside the L / a / b scale factors
+  double toe_unit, slope_unit, offset_unit, two_thirds;
+  double mw[3][3];
+  double l_scale, a_scale, b_scale, half_qr;
 };
 __constant__ LabConstants kk = {
     1.0 / 3.0, 1.0 / 65535.0, 65535.0, 0.0404482362771076 * 65535.0, 1.0 / 12.92, 0.055, 1.0 / 1.055, 4.0, 3.0,
     {{0.4123955889674142161, 0.3575834307637148171, 0.1804926473817015735},
      {0.2125862307855955516, 0.7151703037034108499, 0.07220049864333622685},
      {0.01929721549174694484, 0.1191838645808485318, 0.9504971251315797660}},
-    1.0 / 0.95047, 1.0 / 1.08883, 216.0 / 24389.0, 116.0, 16.0, 1.0 / 100.0, 500.0, 200.0, 1.0 / 255.0, 0.5};
+    1.0 / 0.95047, 1.0 / 1.08883, 216.0 / 24389.0, 116.0, 16.0, 1.0 / 100.0, 500.0, 200.0, 1.0 / 255.0, 0.5,
+    (1.0 / 65535.0) / 12.92, (1.0 / 65535.0) / 1.055, 0.055 / 1.055, 2.0 / 3.0,
+    {{0.4123955889674142161 / 0.95047, 0.3575834307637148171 / 0.95047, 0.1804926473817015735 / 0.95047},
+     {0.2125862307855955516, 0.7151703037034108499, 0.07220049864333622685},
+     {0.01929721549174694484 / 1.08883, 0.1191838645808485318 / 1.08883, 0.9504971251315797660 / 1.08883}},
+    65535.0 / 100.0, 65535.0 * 500.0 / 255.0, 65535.0 * 200.0 / 255.0, 0.5 * 65535.0};
 
 __constant__ double kDecodeCf[9] = {1.7917488588043277509, 0.82045614371976854984, 0.027694100686325412819,
                                     -0.00094244335181762134018, 0.000064355540911469709545,
@@ -144,28 +154,20 @@ __device__ __forceinline__ double encode_pixel_gamma(double pixel) {   // pixel.
 constexpr double kIllX = 0.95047, kIllY = 1.00000, kIllZ = 1.08883;   // D65
 constexpr double kCieEps = 216.0 / 24389.0, kCieK = 24389.0 / 27.0;
 
-// t^(1/3) for t in (216/24389, ~1.3]: z0 = 2^(-log2(t)/3) in fp32 (MUFU, ~2^-21), one Newton step
-// on z = t^(-1/3) (z1 = z0 + z0*(1 - t*z0^3)/3, error ~2^-41), result t*z1^2.
+// t^(1/3) for t in (216/24389, ~1.3]: z0 = 2^(-log2(t)/3) in fp32 (MUFU, ~2^-21), then one Newton step on
+// z = t^(-1/3) folded into the result: t*z1^2 with z1 = z0*(1 + e/3) is w*(1 + 2e/3) + O(e^2), w = t*z0^2, e = 1 - w*z0
+// (|e| < 2^-20, so the dropped e^2/9 term is below 2^-43) -- five FP64 operations.
 // (lg2 / ex2 as the bare MUFU instructions: t is in (0.0088, ~1.4], so neither needs the range handling of log2f / exp2f,
 // which costs two divergent-branch regions per call.)
-__device__ __forceinline__ double cube_root(double t) {
+__device__ __forceinline__ double cube_root5(double t) {
   const float tf = static_cast<float>(t);
   float l, zf;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(tf));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(zf) : "f"(l * (-1.0f / 3.0f)));
   const double z0 = static_cast<double>(zf);
-  const double z2 = z0 * z0;
-  const double e = fma(-t, z2 * z0, 1.0);
-  const double z1 = fma(z0 * kk.third, e, z0);
-  return t * z1 * z1;
-}
-
-// colorspace-private.h:1075-1086.  t = v / white.  The linear toe is evaluated exactly as the reference writes
-// it -- (CIEK*v/white + 16)/116 with IEEE divisions -- because L = 116*f(Y) - 16 cancels there: a black pixel
-// must give exactly 0, not -1e-13 (a huge ULP distance for a very common value).
-__device__ __forceinline__ double lab_f(double t, double v, double white) {
-  if (t > kk.cie_eps) return cube_root(t);
-  return (kCieK * v / white + 16.0) / 116.0;
+  const double w = t * (z0 * z0);
+  const double e = fma(-w, z0, 1.0);
+  return fma(w * e, kk.two_thirds, w);
 }
 
 __device__ __forceinline__ void rgb_to_xyz(double R, double G, double B, double &X, double &Y, double &Z, const double *s_scale) {
@@ -174,6 +176,51 @@ __device__ __forceinline__ void rgb_to_xyz(double R, double G, double B, double 
   X = fma(kk.m[0][2], b, fma(kk.m[0][1], g, kk.m[0][0] * r));
   Y = fma(kk.m[1][2], b, fma(kk.m[1][1], g, kk.m[1][0] * r));
   Z = fma(kk.m[2][2], b, fma(kk.m[2][1], g, kk.m[2][0] * r));
+}
+
+// sRGB -> Lab with the constant factors folded (the reference's chain, colorspace-private.h:1075-1107 on top of
+// ConvertRGBToXYZ :1551, multiplies by QuantumScale, 1/white, 1/100, 1/255 and QuantumRange one at a time; each folded
+// product differs from the chain by a relative 1e-16, nine orders of magnitude below the float ULP of the result):
+// 58 instead of 82 FP64 operations per pixel.  Exact zeros survive: black decodes to 0, (0 + 16)/116 is the reference's
+// own toe expression (colorspace-private.h:1075-1086 with IEEE divisions), and 116*f - 16 stays unfused -- L = 116*f(Y) - 16
+// cancels there, and a black pixel must give exactly 0, not -1e-13 (a huge ULP distance for a very common value).
+// The fast path is straight-line code (no divergent region per channel: the three Horner chains interleave and the
+// BSSY / BSYNC / BRA scaffolding of six conditionals disappears): the toe is a select, and the two rare cases -- an
+// HDRI sample whose gamma argument leaves the tabled exponents, a Lab argument below the CIE epsilon -- are collected
+// into one flag each and handled per pixel by out-of-line code.
+__device__ __forceinline__ double decode_unit(double pixel, const double *s_scale, bool &far) {   // QuantumScale * DecodePixelGamma
+  const double x = fma(pixel, kk.slope_unit, kk.offset_unit);
+  const int hi = __double2hiint(x);
+  const int idx = ((hi >> 20) & 0x7ff) - (1022 - 64);
+  const bool toe = pixel <= kk.toe_limit;
+  far = far || (!toe && static_cast<unsigned>(idx) >= 128u);
+  const double mant = __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(x));
+  const double p = cheb9(kDecodeMono, fma(kk.four, mant, -kk.three));
+  const double curve = x * (s_scale[idx & 127] * p);
+  return toe ? pixel * kk.toe_unit : curve;
+}
+__device__ __noinline__ double decode_unit_far(double pixel) {
+  if (pixel <= kk.toe_limit) return pixel * kk.toe_unit;
+  return decode_gamma(fma(pixel, kk.slope_unit, kk.offset_unit));
+}
+__device__ __noinline__ double lab_f_toe(double t) {
+  if (t > kk.cie_eps) return cube_root5(t);
+  return (kCieK * t + 16.0) / 116.0;
+}
+__device__ __forceinline__ void rgb_to_lab_unit(double R, double G, double B, double &o0, double &o1, double &o2,
+                                                const double *s_scale) {
+  bool far = false;
+  double r = decode_unit(R, s_scale, far), g = decode_unit(G, s_scale, far), b = decode_unit(B, s_scale, far);
+  if (far) { r = decode_unit_far(R); g = decode_unit_far(G); b = decode_unit_far(B); }
+  const double tx = fma(kk.mw[0][2], b, fma(kk.mw[0][1], g, kk.mw[0][0] * r));
+  const double ty = fma(kk.mw[1][2], b, fma(kk.mw[1][1], g, kk.mw[1][0] * r));
+  const double tz = fma(kk.mw[2][2], b, fma(kk.mw[2][1], g, kk.mw[2][0] * r));
+  double x, y, z;
+  if (fmin(tx, fmin(ty, tz)) > kk.cie_eps) { x = cube_root5(tx); y = cube_root5(ty); z = cube_root5(tz); }
+  else { x = lab_f_toe(tx); y = lab_f_toe(ty); z = lab_f_toe(tz); }       // also taken by NaN samples
+  o0 = __dsub_rn(__dmul_rn(kk.c116, y), kk.c16) * kk.l_scale;     // unfused: 116*(16/116) - 16 must be exactly 0 (black)
+  o1 = fma(x - y, kk.a_scale, kk.half_qr);
+  o2 = fma(y - z, kk.b_scale, kk.half_qr);
 }
 
 __device__ __forceinline__ void xyz_to_rgb(double X, double Y, double Z, double &R, double &G, double &B) {
@@ -189,6 +236,7 @@ __device__ __forceinline__ void xyz_to_rgb(double X, double Y, double Z, double 
 }
 
 enum Mode { kToLab, kToXyz, kToLinear, kFromLab, kFromXyz, kFromLinear };
+constexpr int kPixels = 4;
 
 template <int CH, int MODE>
 __global__ void __launch_bounds__(256) colorspace_kernel(float *buf, size_t npixels) {
@@ -197,7 +245,11 @@ __global__ void __launch_bounds__(256) colorspace_kernel(float *buf, size_t npix
     if (threadIdx.x < 128) s_scale[threadIdx.x] = kDecodeScale[threadIdx.x];
     __syncthreads();
   }
-  const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  // kPixels pixels per thread, 256 apart (coalesced): the constant-bank loads, the table fill and the address set-up
+  // are paid once per thread instead of once per pixel (the kernel is issue bound, see LabConstants)
+  size_t i = static_cast<size_t>(blockIdx.x) * (256 * kPixels) + threadIdx.x;
+#pragma unroll 1
+  for (int k = 0; k < kPixels; ++k, i += 256) {
   if (i >= npixels) return;
   float *q = buf + i * CH;
   float in0, in1, in2, in3 = 0.f;
@@ -208,15 +260,11 @@ __global__ void __launch_bounds__(256) colorspace_kernel(float *buf, size_t npix
     o0 = decode_pixel_gamma_tab(in0, s_scale); o1 = decode_pixel_gamma_tab(in1, s_scale); o2 = decode_pixel_gamma_tab(in2, s_scale);
   } else if (MODE == kFromLinear) {
     o0 = encode_pixel_gamma(in0); o1 = encode_pixel_gamma(in1); o2 = encode_pixel_gamma(in2);
-  } else if (MODE == kToLab || MODE == kToXyz) {
+  } else if (MODE == kToLab) {
+    rgb_to_lab_unit(in0, in1, in2, o0, o1, o2, s_scale);
+  } else if (MODE == kToXyz) {
     double X, Y, Z;
     rgb_to_xyz(in0, in1, in2, X, Y, Z, s_scale);
-    if (MODE == kToLab) {
-      const double x = lab_f(X * kk.inv_ill_x, X, kIllX), y = lab_f(Y, Y, 1.0), z = lab_f(Z * kk.inv_ill_z, Z, kIllZ);
-      X = __dsub_rn(__dmul_rn(kk.c116, y), kk.c16) * kk.inv100;   // unfused: 116*(16/116) - 16 must be exactly 0 (black)
-      Y = fma(kk.c500 * (x - y), kk.inv255, kk.half);
-      Z = fma(kk.c200 * (y - z), kk.inv255, kk.half);
-    }
     o0 = kk.qr * X; o1 = kk.qr * Y; o2 = kk.qr * Z;
   } else {
     double X = QS * in0, Y = QS * in1, Z = QS * in2;
@@ -236,6 +284,7 @@ __global__ void __launch_bounds__(256) colorspace_kernel(float *buf, size_t npix
   }
   if (CH == 4) *reinterpret_cast<float4 *>(q) = make_float4(static_cast<float>(o0), static_cast<float>(o1), static_cast<float>(o2), in3);
   else { q[0] = static_cast<float>(o0); q[1] = static_cast<float>(o1); q[2] = static_cast<float>(o2); }
+  }
 }
 
 // kDecodeScale is per-device constant memory: filled once per device, before the first launch that reads it.
@@ -266,7 +315,7 @@ int launch_mode(float *buf, size_t npixels, int channels, cudaStream_t s) {
     const int rc = ensure_decode_scale();
     if (rc) return rc;
   }
-  const unsigned blocks = static_cast<unsigned>((npixels + 255) / 256);
+  const unsigned blocks = static_cast<unsigned>((npixels + 256 * kPixels - 1) / (256 * kPixels));
   if (channels == 4) colorspace_kernel<4, MODE><<<blocks, 256, 0, s>>>(buf, npixels);
   else colorspace_kernel<3, MODE><<<blocks, 256, 0, s>>>(buf, npixels);
   count_launch();
