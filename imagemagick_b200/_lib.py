@@ -102,6 +102,10 @@ PROTOTYPES = {
     "mb200_statistic_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _i, _sz, _sz, _vp]),
     "mb200_rotational_blur_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _d, _vp]),
     "mb200_bilateral_blur_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _sz, _sz, _d, _d, _vp]),
+    "mb200_adaptive_blur_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d, _vp]),
+    "mb200_adaptive_sharpen_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d, _vp]),
+    "mb200_adaptive_blur_image": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d]),
+    "mb200_adaptive_sharpen_image": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d]),
     "mb200_selective_blur_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d, _d, _vp]),
     "mb200_selective_blur_image": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d, _d]),
     "mb200_statistic_image": (_i, [_vp, _vp, _sz, _sz, _i, _i, _sz, _sz]),

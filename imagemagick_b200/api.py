@@ -250,6 +250,16 @@ def BilateralBlurImage(image: Image, width: int, height: int, intensity_sigma: f
                          float(intensity_sigma), float(spatial_sigma))
 
 
+def AdaptiveBlurImage(image: Image, radius: float, sigma: float) -> Image:
+    """MagickCore/effect.c:128."""
+    return _same_size_op(image, "mb200_adaptive_blur_image_dev", "mb200_adaptive_blur_image", float(radius), float(sigma))
+
+
+def AdaptiveSharpenImage(image: Image, radius: float, sigma: float) -> Image:
+    """MagickCore/effect.c:447."""
+    return _same_size_op(image, "mb200_adaptive_sharpen_image_dev", "mb200_adaptive_sharpen_image", float(radius), float(sigma))
+
+
 def SelectiveBlurImage(image: Image, radius: float, sigma: float, threshold: float) -> Image:
     """MagickCore/effect.c:3406 (threshold in quantum units)."""
     return _same_size_op(image, "mb200_selective_blur_image_dev", "mb200_selective_blur_image", float(radius), float(sigma),

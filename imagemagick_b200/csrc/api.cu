@@ -1033,6 +1033,40 @@ int mb200_bilateral_blur_image_dev(const float *src, float *dst, size_t width, s
   return launch_bilateral_blur(src, dst, width, height, channels, window_width, window_height, intensity_sigma, spatial_sigma, s);
 }
 
+int mb200_adaptive_blur_image_dev(const float *src, float *dst, size_t width, size_t height, int channels, double radius,
+                                  double sigma, void *stream) {
+  if (!src || !dst || src == dst || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "adaptive blur: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  return launch_adaptive(src, dst, width, height, channels, radius, sigma, 0, s);
+}
+
+int mb200_adaptive_sharpen_image_dev(const float *src, float *dst, size_t width, size_t height, int channels, double radius,
+                                     double sigma, void *stream) {
+  if (!src || !dst || src == dst || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "adaptive sharpen: bad arguments");
+  cudaStream_t s;
+  int rc = prepare(stream, &s);
+  if (rc) return rc;
+  return launch_adaptive(src, dst, width, height, channels, radius, sigma, 1, s);
+}
+
+int mb200_adaptive_blur_image(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma) {
+  if (!src || !dst || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "adaptive blur: bad arguments");
+  const size_t bytes = w * h * ch * sizeof(float);
+  return with_staging(src, bytes, dst, bytes, [&](const float *s, float *d, cudaStream_t st) {
+    return mb200_adaptive_blur_image_dev(s, d, w, h, ch, radius, sigma, st);
+  });
+}
+
+int mb200_adaptive_sharpen_image(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma) {
+  if (!src || !dst || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "adaptive sharpen: bad arguments");
+  const size_t bytes = w * h * ch * sizeof(float);
+  return with_staging(src, bytes, dst, bytes, [&](const float *s, float *d, cudaStream_t st) {
+    return mb200_adaptive_sharpen_image_dev(s, d, w, h, ch, radius, sigma, st);
+  });
+}
+
 int mb200_selective_blur_image_dev(const float *src, float *dst, size_t width, size_t height, int channels, double radius,
                                    double sigma, double threshold, void *stream) {
   if (!src || !dst || src == dst || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "selective blur: bad arguments");

@@ -188,11 +188,17 @@ __device__ __forceinline__ void rgb_to_xyz(double R, double G, double B, double 
 // BSSY / BSYNC / BRA scaffolding of six conditionals disappears): the toe is a select, and the two rare cases -- an
 // HDRI sample whose gamma argument leaves the tabled exponents, a Lab argument below the CIE epsilon -- are collected
 // into one flag each and handled per pixel by out-of-line code.
-__device__ __forceinline__ double decode_unit(double pixel, const double *s_scale, bool &far) {   // QuantumScale * DecodePixelGamma
+// (toe test in float: for a float sample p, (double)p <= 0.0404482362771076*QuantumRange  <=>  p <= 2650.775146484375f,
+// the largest float below that limit; the Lab test on the high words: positive doubles order like their bit patterns,
+// and anything at or below the word of the CIE epsilon -- or negative -- takes the exact out-of-line code.)
+constexpr float kToeLimitF = 2650.775146484375f;
+constexpr int kCieEpsHi = 0x3f822354;          // high word of 216/24389 = 0x3f822354d28f7cd6
+__device__ __forceinline__ double decode_unit(float sample, const double *s_scale, bool &far) {   // QuantumScale * DecodePixelGamma
+  const double pixel = static_cast<double>(sample);
   const double x = fma(pixel, kk.slope_unit, kk.offset_unit);
   const int hi = __double2hiint(x);
   const int idx = ((hi >> 20) & 0x7ff) - (1022 - 64);
-  const bool toe = pixel <= kk.toe_limit;
+  const bool toe = sample <= kToeLimitF;
   far = far || (!toe && static_cast<unsigned>(idx) >= 128u);
   const double mant = __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(x));
   const double p = cheb9(kDecodeMono, fma(kk.four, mant, -kk.three));
@@ -207,7 +213,7 @@ __device__ __noinline__ double lab_f_toe(double t) {
   if (t > kk.cie_eps) return cube_root5(t);
   return (kCieK * t + 16.0) / 116.0;
 }
-__device__ __forceinline__ void rgb_to_lab_unit(double R, double G, double B, double &o0, double &o1, double &o2,
+__device__ __forceinline__ void rgb_to_lab_unit(float R, float G, float B, double &o0, double &o1, double &o2,
                                                 const double *s_scale) {
   bool far = false;
   double r = decode_unit(R, s_scale, far), g = decode_unit(G, s_scale, far), b = decode_unit(B, s_scale, far);
@@ -216,8 +222,9 @@ __device__ __forceinline__ void rgb_to_lab_unit(double R, double G, double B, do
   const double ty = fma(kk.mw[1][2], b, fma(kk.mw[1][1], g, kk.mw[1][0] * r));
   const double tz = fma(kk.mw[2][2], b, fma(kk.mw[2][1], g, kk.mw[2][0] * r));
   double x, y, z;
-  if (fmin(tx, fmin(ty, tz)) > kk.cie_eps) { x = cube_root5(tx); y = cube_root5(ty); z = cube_root5(tz); }
-  else { x = lab_f_toe(tx); y = lab_f_toe(ty); z = lab_f_toe(tz); }       // also taken by NaN samples
+  if (min(__double2hiint(tx), min(__double2hiint(ty), __double2hiint(tz))) > kCieEpsHi) {
+    x = cube_root5(tx); y = cube_root5(ty); z = cube_root5(tz);
+  } else { x = lab_f_toe(tx); y = lab_f_toe(ty); z = lab_f_toe(tz); }
   o0 = __dsub_rn(__dmul_rn(kk.c116, y), kk.c16) * kk.l_scale;     // unfused: 116*(16/116) - 16 must be exactly 0 (black)
   o1 = fma(x - y, kk.a_scale, kk.half_qr);
   o2 = fma(y - z, kk.b_scale, kk.half_qr);
@@ -247,14 +254,26 @@ __global__ void __launch_bounds__(256) colorspace_kernel(float *buf, size_t npix
   }
   // kPixels pixels per thread, 256 apart (coalesced): the constant-bank loads, the table fill and the address set-up
   // are paid once per thread instead of once per pixel (the kernel is issue bound, see LabConstants)
+  // The next pixel is loaded before the current one is evaluated (ncu r02: with the load at the top of the iteration
+  // long_scoreboard was the largest stall, 6.8 cycles per instruction, at 69 % issue utilisation).
   size_t i = static_cast<size_t>(blockIdx.x) * (256 * kPixels) + threadIdx.x;
+  if (i >= npixels) return;
+  float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    const float *q0 = buf + i * CH;
+    if (CH == 4) nxt = *reinterpret_cast<const float4 *>(q0);
+    else { nxt.x = q0[0]; nxt.y = q0[1]; nxt.z = q0[2]; }
+  }
 #pragma unroll 1
   for (int k = 0; k < kPixels; ++k, i += 256) {
   if (i >= npixels) return;
   float *q = buf + i * CH;
-  float in0, in1, in2, in3 = 0.f;
-  if (CH == 4) { const float4 t = *reinterpret_cast<const float4 *>(q); in0 = t.x; in1 = t.y; in2 = t.z; in3 = t.w; }
-  else { in0 = q[0]; in1 = q[1]; in2 = q[2]; }
+  const float in0 = nxt.x, in1 = nxt.y, in2 = nxt.z, in3 = nxt.w;
+  if (k + 1 < kPixels && i + 256 < npixels) {
+    const float *q1 = q + 256 * CH;
+    if (CH == 4) nxt = *reinterpret_cast<const float4 *>(q1);
+    else { nxt.x = q1[0]; nxt.y = q1[1]; nxt.z = q1[2]; }
+  }
   double o0, o1, o2;
   if (MODE == kToLinear) {
     o0 = decode_pixel_gamma_tab(in0, s_scale); o1 = decode_pixel_gamma_tab(in1, s_scale); o2 = decode_pixel_gamma_tab(in2, s_scale);

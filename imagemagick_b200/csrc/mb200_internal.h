@@ -126,6 +126,9 @@ int launch_statistic(const float *src, float *dst, size_t w, size_t h, int chann
 int launch_rotational_blur(const float *src, float *dst, size_t w, size_t h, int channels, double angle, void *stream);
 int launch_bilateral_blur(const float *src, float *dst, size_t w, size_t h, int channels, size_t width, size_t height,
                           double intensity_sigma, double spatial_sigma, void *stream);
+// AdaptiveBlurImage (effect.c:128) / AdaptiveSharpenImage (:447): edge map + per-pixel kernel size, bit exact
+int launch_adaptive(const float *src, float *dst, size_t w, size_t h, int channels, double radius, double sigma, int sharpen,
+                    void *stream);
 // SelectiveBlurImage (effect.c:3406)
 int launch_selective_blur(const float *src, float *dst, size_t w, size_t h, int channels, double radius, double sigma,
                           double threshold, void *stream);

@@ -7,7 +7,7 @@
           --wrap=MorphologyImage,--wrap=ResizeImage,--wrap=TransformImageColorspace,\
           --wrap=BilevelImage,--wrap=BlackThresholdImage,--wrap=WhiteThresholdImage,--wrap=ClampImage,\
           --wrap=SharpenImage,--wrap=EdgeImage,--wrap=SampleImage,--wrap=ThumbnailImage,--wrap=MinifyImage,--wrap=ResampleImage,--wrap=MotionBlurImage,\
-          --wrap=EmbossImage,--wrap=EqualizeImage,--wrap=StatisticImage,--wrap=RotationalBlurImage,--wrap=BilateralBlurImage,--wrap=ScaleImage,--wrap=SelectiveBlurImage
+          --wrap=EmbossImage,--wrap=EqualizeImage,--wrap=StatisticImage,--wrap=RotationalBlurImage,--wrap=BilateralBlurImage,--wrap=ScaleImage,--wrap=SelectiveBlurImage,--wrap=AdaptiveBlurImage,--wrap=AdaptiveSharpenImage
   and every caller of those exported functions (effect.c:765/1709/1170/4256, morphology.c:4129,
   resize.c:3761, colorspace.c:1751, threshold.c:805/927/2518/1087) reaches __wrap_X below.  Each wrapper follows the accelerate
   hook contract of effect.c:783-787 / resize.c:3818-3826: try the GPU; if the image is not
@@ -588,6 +588,27 @@ Image *B200AccelerateBilateralBlurImage(const Image *image, const size_t width, 
   return run_same_size(image, op_bilateral, &a, exception);
 }
 
+/* AdaptiveBlurImage (effect.c:128) / AdaptiveSharpenImage (:447).  AutoLevelImage takes its all-channels branch only for the
+   default mask (histogram.c:942) and EdgeImage / BlurImage read the convolve artifacts: anything else declines. */
+static int op_adaptive_blur(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
+{ const blur_args *b = (const blur_args *) a; return mb200_adaptive_blur_image(s, d, w, h, ch, b->radius, b->sigma); }
+static int op_adaptive_sharpen(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
+{ const blur_args *b = (const blur_args *) a; return mb200_adaptive_sharpen_image(s, d, w, h, ch, b->radius, b->sigma); }
+
+static Image *adaptive(const Image *image, same_size_op op, const double radius, const double sigma, ExceptionInfo *exception)
+{
+  blur_args a;
+  if (has_artifact(image, morphology_artifacts) != MagickFalse) return (Image *) NULL;
+  if (equalize_eligible(image) == MagickFalse || image->channel_mask != AllChannels) return (Image *) NULL;
+  a.radius = radius; a.sigma = sigma; a.gain = 0.0; a.threshold = 0.0;
+  return run_same_size(image, op, &a, exception);
+}
+
+Image *B200AccelerateAdaptiveBlurImage(const Image *image, const double radius, const double sigma, ExceptionInfo *exception)
+{ return adaptive(image, op_adaptive_blur, radius, sigma, exception); }
+Image *B200AccelerateAdaptiveSharpenImage(const Image *image, const double radius, const double sigma, ExceptionInfo *exception)
+{ return adaptive(image, op_adaptive_sharpen, radius, sigma, exception); }
+
 /* SelectiveBlurImage (effect.c:3406): one stage, so channel selections are exact (unselected channels copy the centre) */
 static int op_selective(const float *s, float *d, size_t w, size_t h, int ch, const void *a)
 { const stencil_args *t = (const stencil_args *) a; return mb200_selective_blur_image(s, d, w, h, ch, t->a, t->b, t->c); }
@@ -749,6 +770,19 @@ Image *__wrap_BilateralBlurImage(const Image *image, const size_t width, const s
 {
   TRY(B200AccelerateBilateralBlurImage(image, width, height, intensity_sigma, spatial_sigma, exception));
   return __real_BilateralBlurImage(image, width, height, intensity_sigma, spatial_sigma, exception);
+}
+
+extern Image *__real_AdaptiveBlurImage(const Image *, const double, const double, ExceptionInfo *);
+extern Image *__real_AdaptiveSharpenImage(const Image *, const double, const double, ExceptionInfo *);
+Image *__wrap_AdaptiveBlurImage(const Image *image, const double radius, const double sigma, ExceptionInfo *exception)
+{
+  TRY(B200AccelerateAdaptiveBlurImage(image, radius, sigma, exception));
+  return __real_AdaptiveBlurImage(image, radius, sigma, exception);
+}
+Image *__wrap_AdaptiveSharpenImage(const Image *image, const double radius, const double sigma, ExceptionInfo *exception)
+{
+  TRY(B200AccelerateAdaptiveSharpenImage(image, radius, sigma, exception));
+  return __real_AdaptiveSharpenImage(image, radius, sigma, exception);
 }
 
 extern Image *__real_SelectiveBlurImage(const Image *, const double, const double, const double, ExceptionInfo *);

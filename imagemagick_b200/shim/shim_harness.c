@@ -31,6 +31,8 @@ extern Image *__real_SharpenImage(const Image *, const double, const double, Exc
 extern Image *__real_EmbossImage(const Image *, const double, const double, ExceptionInfo *);
 extern Image *__real_StatisticImage(const Image *, const StatisticType, const size_t, const size_t, ExceptionInfo *);
 extern Image *__real_RotationalBlurImage(const Image *, const double, ExceptionInfo *);
+extern Image *__real_AdaptiveBlurImage(const Image *, const double, const double, ExceptionInfo *);
+extern Image *__real_AdaptiveSharpenImage(const Image *, const double, const double, ExceptionInfo *);
 extern Image *__real_SelectiveBlurImage(const Image *, const double, const double, const double, ExceptionInfo *);
 extern Image *__real_BilateralBlurImage(const Image *, const size_t, const size_t, const double, const double, ExceptionInfo *);
 extern MagickBooleanType __real_EqualizeImage(Image *, ExceptionInfo *);
@@ -116,6 +118,8 @@ int main(void)
   CHECK("StatisticImage Median 3x3 RGBA", 0, StatisticImage(rgba, MedianStatistic, 3, 3, ex), CPU(__real_StatisticImage(rgba, MedianStatistic, 3, 3, ex)));
   CHECK("StatisticImage StdDev 5x3 RGB", 0, StatisticImage(rgb, StandardDeviationStatistic, 5, 3, ex), CPU(__real_StatisticImage(rgb, StandardDeviationStatistic, 5, 3, ex)));
   CHECK("RotationalBlurImage(7) RGBA", 0, RotationalBlurImage(rgba, 7.0, ex), CPU(__real_RotationalBlurImage(rgba, 7.0, ex)));
+  CHECK("AdaptiveBlurImage 0x1.5 RGBA", 0, AdaptiveBlurImage(rgba, 0.0, 1.5, ex), CPU(__real_AdaptiveBlurImage(rgba, 0.0, 1.5, ex)));
+  CHECK("AdaptiveSharpenImage 0x1 RGB", 0, AdaptiveSharpenImage(rgb, 0.0, 1.0, ex), CPU(__real_AdaptiveSharpenImage(rgb, 0.0, 1.0, ex)));
   CHECK("SelectiveBlurImage 0x1.5 t=10% RGBA", 0, SelectiveBlurImage(rgba, 0.0, 1.5, 6553.5, ex),
         CPU(__real_SelectiveBlurImage(rgba, 0.0, 1.5, 6553.5, ex)));
   CHECK("BilateralBlurImage 5x5 RGB", 0, BilateralBlurImage(rgb, 5, 5, 20.0, 2.0, ex), CPU(__real_BilateralBlurImage(rgb, 5, 5, 20.0, 2.0, ex)));

@@ -289,6 +289,13 @@ MB200_API int mb200_rotational_blur_image_dev(const float *src, float *dst, size
 /* BilateralBlurImage (MagickCore/effect.c:821), odd window sizes (even ones return MB200_EUNSUPPORTED), bit exact. */
 MB200_API int mb200_bilateral_blur_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
     size_t window_width, size_t window_height, double intensity_sigma, double spatial_sigma, void *stream);
+/* AdaptiveBlurImage (MagickCore/effect.c:128) / AdaptiveSharpenImage (:447): EdgeImage -> AutoLevelImage -> BlurImage ->
+   AutoLevelImage gives the edge map that selects a kernel size per pixel; every stage in the reference's operation
+   order, bit exact. */
+MB200_API int mb200_adaptive_blur_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
+    double radius, double sigma, void *stream);
+MB200_API int mb200_adaptive_sharpen_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
+    double radius, double sigma, void *stream);
 /* SelectiveBlurImage (MagickCore/effect.c:3406): contrast-gated Gaussian (threshold in quantum units), bit exact. */
 MB200_API int mb200_selective_blur_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
     double radius, double sigma, double threshold, void *stream);
@@ -379,6 +386,10 @@ MB200_API int mb200_rotational_blur_image(const float *src, float *dst, size_t w
     double angle);
 MB200_API int mb200_bilateral_blur_image(const float *src, float *dst, size_t width, size_t height, int channels,
     size_t window_width, size_t window_height, double intensity_sigma, double spatial_sigma);
+MB200_API int mb200_adaptive_blur_image(const float *src, float *dst, size_t width, size_t height, int channels,
+    double radius, double sigma);
+MB200_API int mb200_adaptive_sharpen_image(const float *src, float *dst, size_t width, size_t height, int channels,
+    double radius, double sigma);
 MB200_API int mb200_selective_blur_image(const float *src, float *dst, size_t width, size_t height, int channels,
     double radius, double sigma, double threshold);
 MB200_API int mb200_equalize_image(float *buf, size_t width, size_t height, int channels, int sync_channels);

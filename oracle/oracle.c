@@ -8,6 +8,7 @@
   by tests/test_oracle_vs_ref.py and by the golden vectors in tests/golden/.
 */
 #include "oracle.h"
+#include <limits.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1889,3 +1890,112 @@ int orc_statistic(const float *src, float *dst, size_t w, size_t h, int ch, int 
   }
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+   effect.c:128-416 AdaptiveBlurImage / :447-735 AdaptiveSharpenImage (sharpen != 0).
+     edge  = EdgeImage(image, radius)                              (:181)
+     AutoLevelImage(edge) = MinMaxStretchImage(edge, 0, 0, 1.0)    (enhance.c:266, histogram.c:927): the default channel
+             mask is AllChannels, so ONE range over every channel (GetImageRange statistic.c:1851: plain comparisons, NaN never
+             wins), LevelImage (enhance.c:2913: QuantumRange * (PerceptibleReciprocal(max - min) * (pixel - min)), gamma 1 so
+             gamma_pow is the identity; skipped when |min - max| < MagickEpsilon) and ClampImage (threshold.c:1087)
+     edge  = BlurImage(edge, radius, sigma); AutoLevelImage(edge)  (:188-194)
+     width = GetOptimalKernelWidth2D(radius, sigma); kernel[j], j = 0, 2, ..: (width - j)^2 Gaussians, the centre absorbs
+             1 - sum (blur) or is set to -2 * sum of the negated Gaussian (sharpen)                     (:199-236)
+     per pixel: j = ceil(width * (1 - QS * intensity(edge)) - 0.5) clipped to [0, width], made even; the (width - j)^2
+             window around the pixel is weighted with kernel[j] in plain (not reflected) order            (:279-372)
+   ------------------------------------------------------------------------------------------ */
+static void auto_level(float *buf, size_t w, size_t h, int ch)
+{
+  const size_t n = w * h * (size_t) ch;
+  double minima = 1.7976931348623157e308, maxima = -1.7976931348623157e308, scale;   /* MagickMaximumValue / Minimum */
+  size_t i;
+  for (i = 0; i < n; i++) {
+    if ((double) buf[i] < minima) minima = (double) buf[i];
+    if ((double) buf[i] > maxima) maxima = (double) buf[i];
+  }
+  if (!(fabs(minima - maxima) >= EPS)) return;
+  scale = perceptible_reciprocal(maxima - minima);
+  for (i = 0; i < n; i++) {
+    const double level = QR * (scale * ((double) buf[i] - minima));
+    buf[i] = clamp_pixel((double) (float) level);
+  }
+}
+
+static int adaptive_filter(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma, int sharpen)
+{
+  const size_t n = w * h * (size_t) ch, width = orc_optimal_kernel_width_2d(radius, sigma);
+  const double s = fabs(sigma) < EPS ? EPS : sigma;
+  const int has_alpha = (ch == 2 || ch == 4);
+  float *edge, *tmp;
+  double **kernel;
+  long jw, y;
+  int rc = -1;
+  if (fabs(sigma) < EPS) { memcpy(dst, src, n * sizeof(float)); return 0; }
+  edge = (float *) malloc(n * sizeof(float));
+  tmp = (float *) malloc(n * sizeof(float));
+  kernel = (double **) calloc(width, sizeof(*kernel));
+  if (!edge || !tmp || !kernel) goto done;
+  if (orc_edge(src, edge, w, h, ch, radius)) goto done;
+  auto_level(edge, w, h, ch);
+  if (orc_blur(edge, tmp, w, h, ch, radius, sigma)) goto done;
+  auto_level(tmp, w, h, ch);
+  for (jw = 0; jw < (long) width; jw += 2) {
+    const long size = (long) width - jw, j = (size - 1) / 2;
+    double normalize = 0.0;
+    long u, v, k = 0;
+    kernel[jw] = (double *) malloc((size_t) (size * size) * sizeof(double));
+    if (!kernel[jw]) goto done;
+    for (v = -j; v <= j; v++)
+      for (u = -j; u <= j; u++) {
+        const double g = exp(-((double) u * u + v * v) / (2.0 * s * s)) / (2.0 * PI_ * s * s);
+        kernel[jw][k] = sharpen ? -g : g;
+        normalize += kernel[jw][k];
+        k++;
+      }
+    if (sharpen) kernel[jw][(k - 1) / 2] = (-2.0) * normalize;
+    else kernel[jw][(k - 1) / 2] += 1.0 - normalize;
+    if (sigma < EPS) kernel[jw][(k - 1) / 2] = 1.0;
+  }
+#pragma omp parallel for schedule(static)
+  for (y = 0; y < (long) h; y++) {
+    long x;
+    for (x = 0; x < (long) w; x++) {
+      const float *r = tmp + ((size_t) y * w + (size_t) x) * ch;
+      double t = ceil((double) width * (1.0 - QS * pixel_intensity(r, ch)) - 0.5);
+      long j, size, x0, y0, u, v;
+      int c;
+      j = t != t ? 0 : (t >= 9.2233720368547758e18 ? LONG_MAX : (t <= -9.2233720368547758e18 ? LONG_MIN : (long) t));
+      if (j < 0) j = 0; else if (j > (long) width) j = (long) width;
+      if ((j & 0x01) != 0) j--;
+      size = (long) width - j;
+      x0 = x - size / 2; y0 = y - size / 2;
+      for (c = 0; c < ch; c++) {
+        const int blend = has_alpha && c != ch - 1;
+        const double *k = kernel[j];
+        double pixel = 0.0, gamma = 0.0;
+        for (v = 0; v < size; v++)
+          for (u = 0; u < size; u++, k++) {
+            const float *p = src + ((size_t) clampl(y0 + v, 0, (long) h - 1) * w + (size_t) clampl(x0 + u, 0, (long) w - 1)) * ch;
+            if (!blend) { pixel += (*k) * (double) p[c]; gamma += (*k); }
+            else {
+              const double alpha = (double) (QS * (double) p[ch - 1]);
+              pixel += (*k) * alpha * (double) p[c];
+              gamma += (*k) * alpha;
+            }
+          }
+        gamma = perceptible_reciprocal(gamma);
+        dst[((size_t) y * w + (size_t) x) * ch + c] = (float) (gamma * pixel);
+      }
+    }
+  }
+  rc = 0;
+done:
+  if (kernel) { for (jw = 0; jw < (long) width; jw++) free(kernel[jw]); free(kernel); }
+  free(edge); free(tmp);
+  return rc;
+}
+
+int orc_adaptive_blur(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma)
+{ return adaptive_filter(src, dst, w, h, ch, radius, sigma, 0); }
+int orc_adaptive_sharpen(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma)
+{ return adaptive_filter(src, dst, w, h, ch, radius, sigma, 1); }

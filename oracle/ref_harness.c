@@ -134,6 +134,24 @@ int ref_edge(const float *src, float *dst, size_t w, size_t h, int ch, double ra
 }
 
 __attribute__((visibility("default")))
+int ref_adaptive_blur(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma)
+{
+  BEGIN
+  im = make_image(src, w, h, ch, -1, ex);
+  if (im) { out = AdaptiveBlurImage(im, radius, sigma, ex); rc = export_image(out, dst, w, h, ch, ex); }
+  END
+}
+
+__attribute__((visibility("default")))
+int ref_adaptive_sharpen(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma)
+{
+  BEGIN
+  im = make_image(src, w, h, ch, -1, ex);
+  if (im) { out = AdaptiveSharpenImage(im, radius, sigma, ex); rc = export_image(out, dst, w, h, ch, ex); }
+  END
+}
+
+__attribute__((visibility("default")))
 int ref_selective_blur(const float *src, float *dst, size_t w, size_t h, int ch, double radius, double sigma, double threshold)
 {
   BEGIN

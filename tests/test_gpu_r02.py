@@ -383,6 +383,20 @@ def test_selective_blur_bit_exact(ch, args, kind):
     assert max_ulp(got, want) == 0
 
 
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("fn", ["adaptive_blur", "adaptive_sharpen"])
+@pytest.mark.parametrize("args", [(0.0, 1.0), (0.0, 2.0), (3.0, 1.5), (0.0, 0.0)])
+@pytest.mark.parametrize("kind", ["gradient", "noise"])
+def test_adaptive_blur_and_sharpen_bit_exact(ch, fn, args, kind):
+    """AdaptiveBlurImage / AdaptiveSharpenImage (effect.c:128 / :447): the edge map (edge -> auto-level -> blur ->
+    auto-level) selects a kernel size per pixel, so every stage has to be bit exact; sigma 0 is a plain copy."""
+    src = make_image(97, 64, ch, seed=66, kind="alpha_blocks" if ch in (2, 4) and kind == "gradient" else kind)
+    want = orc("orc_" + fn, src, *args)
+    op = im.AdaptiveBlurImage if fn == "adaptive_blur" else im.AdaptiveSharpenImage
+    got = _host(op(_dev(src), *args))
+    assert max_ulp(got, want) == 0
+
+
 def test_selective_blur_host_buffers_through_the_c_abi():
     src = make_image(64, 48, 4, seed=65, kind="alpha_blocks")
     want = orc("orc_selective_blur", src, 0.0, 1.5, 9000.0)

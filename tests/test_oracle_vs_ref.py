@@ -267,3 +267,16 @@ def test_selective_blur_bit_exact(ch, args):
     assert util.oracle().orc_selective_blur(util.P(src), util.P(a), 61, 43, ch, *args) == 0
     assert util.ref().ref_selective_blur(util.P(src), util.P(b), 61, 43, ch, *args) == 0
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("fn", ["adaptive_blur", "adaptive_sharpen"])
+@pytest.mark.parametrize("args", [(0.0, 1.0), (0.0, 2.0), (3.0, 1.5), (0.0, 0.0)])
+def test_adaptive_blur_and_sharpen_bit_exact(ch, fn, args):
+    """AdaptiveBlurImage / AdaptiveSharpenImage (effect.c:128 / :447): edge -> auto-level -> blur -> auto-level selects a
+    kernel size per pixel."""
+    src = util.make_image(75, 52, ch, seed=83, kind="alpha_blocks" if ch in (2, 4) else "gradient")
+    a, b = np.empty_like(src), np.empty_like(src)
+    assert getattr(util.oracle(), "orc_" + fn)(util.P(src), util.P(a), 75, 52, ch, *args) == 0
+    assert getattr(util.ref(), "ref_" + fn)(util.P(src), util.P(b), 75, 52, ch, *args) == 0
+    assert np.array_equal(a, b)

@@ -56,6 +56,8 @@ def oracle() -> C.CDLL:
         o.orc_sample.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         o.orc_scale.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         o.orc_selective_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d, _d]
+        o.orc_adaptive_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d]
+        o.orc_adaptive_sharpen.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d]
         o.orc_thumbnail.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         o.orc_kernel_builtin.argtypes = [_i, _d, _d, _d, _d, C.POINTER(OrcKernel)]
         o.orc_kernel_user.argtypes = [_sz, _sz, _l, _l, C.POINTER(_d), C.POINTER(OrcKernel)]
@@ -105,6 +107,8 @@ def ref() -> C.CDLL:
         r.ref_sample.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         r.ref_scale.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         r.ref_selective_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d, _d]
+        r.ref_adaptive_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d]
+        r.ref_adaptive_sharpen.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d]
         r.ref_thumbnail.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         r.ref_kernel.argtypes = [C.c_char_p, _i, C.POINTER(_d), _sz, C.POINTER(_sz), C.POINTER(_sz),
                                  C.POINTER(_l), C.POINTER(_l)]

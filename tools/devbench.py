@@ -78,6 +78,8 @@ if which in ("stencils", "all"):
     ms = timeit(lambda: im.StatisticImage(x, im.MedianStatistic, 3, 3), iters=3); report(f"StatisticImage Median 3x3 {s}^2", ms, s * s, 32)
     ms = timeit(lambda: im.StatisticImage(x, im.MeanStatistic, 5, 5), iters=3); report(f"StatisticImage Mean 5x5 {s}^2", ms, s * s, 32)
     ms = timeit(lambda: im.BilateralBlurImage(x, 7, 7, 20.0, 2.0), iters=3); report(f"BilateralBlurImage 7x7 {s}^2", ms, s * s, 32)
+    ms = timeit(lambda: im.SelectiveBlurImage(x, 0.0, 1.5, 6553.5), iters=3); report(f"SelectiveBlurImage 0x1.5 t=10% {s}^2", ms, s * s, 32)
+    ms = timeit(lambda: im.AdaptiveBlurImage(x, 0.0, 1.5), iters=3); report(f"AdaptiveBlurImage 0x1.5 {s}^2", ms, s * s, 32)
     ms = timeit(lambda: im.RotationalBlurImage(x, 5.0), iters=3); report(f"RotationalBlurImage(5) {s}^2", ms, s * s, 32)
     ms = timeit(lambda: im.MotionBlurImage(x, 0.0, 4.0, 30.0), iters=3); report(f"MotionBlurImage(0,4,30) {s}^2", ms, s * s, 32)
     ms = timeit(lambda: im.EqualizeImage(x), iters=3); report(f"EqualizeImage {s}^2", ms, s * s, 32)
