@@ -60,6 +60,7 @@ PROTOTYPES = {
     "mb200_trim": (_i, [_sz]),
     "mb200_probe_fp64_fma_rate": (_i, [C.POINTER(_d)]),
     "mb200_set_option": (_i, [C.c_char_p, _i]),
+    "mb200_get_option": (_i, [C.c_char_p, C.POINTER(_i)]),
     "mb200_cache_attach": (_i, [_vp, _sz, _i]),
     "mb200_cache_detach": (_i, [_vp]),
     "mb200_cache_sync": (_i, [_vp]),

@@ -26,7 +26,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off",
               "-Xptxas", "-v"]
 
-SOURCES = ["runtime.cu", "kernel_info.cpp", "resize_filter.cpp", "conv1d.cu", "morph2d.cu", "morph_stream.cu", "cache.cu",
+SOURCES = ["runtime.cu", "kernel_info.cpp", "resize_filter.cpp", "conv1d.cu", "conv_mma.cu", "morph2d.cu", "morph_stream.cu", "cache.cu",
            "resize.cu", "resize_stream.cu", "colorspace.cu", "pointwise.cu", "equalize.cu", "stencils.cu", "api.cu"]
 
 
@@ -47,7 +47,7 @@ def _stale(target: Path, deps: list[Path]) -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
     OBJDIR.mkdir(parents=True, exist_ok=True)
-    headers = list(CSRC.glob("*.h")) + list((ROOT / "include").glob("*.h"))
+    headers = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + list((ROOT / "include").glob("*.h"))
     jobs = []
     for name in SOURCES:
         src = CSRC / name

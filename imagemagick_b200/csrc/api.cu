@@ -369,7 +369,24 @@ int mb200_set_option(const char *name, int value) {
   else if (n == "resize_regular_h") k.resize_regular_h = v;
   else if (n == "no_fused_unsharp") k.no_fused_unsharp = v;
   else if (n == "resize_fused") k.resize_fused = v;
+  else if (n == "conv_mma") set_conv_mma(value);
   else return fail(MB200_EINVAL, "set_option: unknown option '%s'", name);
+  return MB200_OK;
+}
+
+int mb200_get_option(const char *name, int *value) {
+  if (!name || !value) return fail(MB200_EINVAL, "get_option: null argument");
+  const Knobs &k = knobs();
+  const std::string n(name);
+  if (n == "no_rank1") *value = k.no_rank1;
+  else if (n == "no_morph_stream") *value = k.no_morph_stream;
+  else if (n == "no_resize_stream") *value = k.no_resize_stream;
+  else if (n == "resize_regular_h") *value = k.resize_regular_h;
+  else if (n == "no_fused_unsharp") *value = k.no_fused_unsharp;
+  else if (n == "resize_fused") *value = k.resize_fused;
+  else if (n == "conv_mma") *value = conv_mma_enabled();
+  else if (n == "conv_mma_launches") *value = static_cast<int>(conv_mma_launches() & 0x7fffffff);
+  else return fail(MB200_EINVAL, "get_option: unknown option '%s'", name);
   return MB200_OK;
 }
 

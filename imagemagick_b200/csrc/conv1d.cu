@@ -25,6 +25,7 @@
 //    lane layout).
 // No tensor cores: this is not a dense contraction.
 #include "mb200_internal.h"
+#include "conv_common.cuh"
 
 #include <cuda_runtime.h>
 
@@ -34,9 +35,6 @@
 
 namespace mb200 {
 namespace {
-
-constexpr double kQuantumScale = 1.0 / 65535.0;
-constexpr double kEpsilon = 1.0e-12;
 
 template <int NT>
 struct Taps { double k[NT]; };
@@ -58,53 +56,6 @@ struct Conv1dArgs {
   const float *aux;
   double gain, qthreshold;
 };
-
-// A zero-padded tap multiplies a sample OUTSIDE the reference's window; 0 * (+-inf | NaN) = NaN would poison outputs
-// the reference computes from finite samples only (HDRI pixels may be non-finite).  Padded launches therefore test
-// every sample (exponent field all ones) and take a predicated slow path for the few steps that carry one.
-__device__ __forceinline__ bool nonfinite_bits(float v) { return (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u; }
-__device__ __forceinline__ bool nonfinite_bits(double v) {
-  return (static_cast<unsigned>(__double2hiint(v)) & 0x7ff00000u) == 0x7ff00000u;
-}
-
-// PerceptibleReciprocal's clamp (pixel-accessor.h:242-254: 1/x if |x| >= MagickEpsilon else sign/MagickEpsilon) applied
-// to gamma = QS * den, i.e. |den| is raised to MagickEpsilon / QuantumScale, exactly.
-__device__ __forceinline__ double clamp_denominator(double den) {
-  // |den| < eps/QS decided exactly as ONE 64-bit unsigned comparison of the magnitude bits (positive doubles order like
-  // their bit patterns): ISETP + ISETP.EX, then two selects -- one instruction more than r01's high-word-only test.
-  constexpr double kTiny = kEpsilon / kQuantumScale;           // 6.5535e-8
-  const unsigned hi = static_cast<unsigned>(__double2hiint(den));
-  const unsigned long long mag = (static_cast<unsigned long long>(hi & 0x7fffffffu) << 32) | static_cast<unsigned>(__double2loint(den));
-  const unsigned long long tiny = static_cast<unsigned long long>(__double_as_longlong(kTiny));
-  if (mag < tiny)
-    den = __hiloint2double(static_cast<int>((hi & 0x80000000u) | static_cast<unsigned>(tiny >> 32)), static_cast<int>(tiny & 0xffffffffu));
-  return den;
-}
-
-// UnsharpMaskImage's point pass (effect.c:4358-4364) on the float-rounded blur value, in the reference's operation
-// order with unfused double arithmetic: bit-identical to running it as a separate pass.
-__device__ __forceinline__ float unsharp_point(float p, float blurred, double gain, double qthreshold) {
-  const double d = __dsub_rn(static_cast<double>(p), static_cast<double>(blurred));
-  if (fabs(__dmul_rn(2.0, d)) < qthreshold) return p;
-  return static_cast<float>(__dadd_rn(static_cast<double>(p), __dmul_rn(gain, d)));
-}
-
-// 1/g to ~1 ulp: MUFU.RCP64H seed (one XU op, ~20 bits) + two FP64 Newton steps.
-__device__ __forceinline__ double fast_reciprocal(double g) {
-  double r0;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(g));
-  const double e0 = fma(-g, r0, 1.0);
-  const double r1 = fma(r0, e0, r0);              // ~2^-40
-  const double e1 = fma(-g, r1, 1.0);
-  return fma(r1, e1, r1);                         // ~1 ulp of double: keeps the first pass of a two-pass operator
-}                                                 // bit-identical to the reference's quotient in all but ~1e-8 of the samples
-
-__device__ __forceinline__ double shfl_double(double v, int lane) {
-  int lo = __double2loint(v), hi = __double2hiint(v);
-  lo = __shfl_sync(0xffffffffu, lo, lane);
-  hi = __shfl_sync(0xffffffffu, hi, lane);
-  return __hiloint2double(hi, lo);
-}
 
 // Per-thread constants of the output stage.  With sum' = sum K*(A*p) and gsum' = sum K*A the
 // reference's  PerceptibleReciprocal(QS*gsum') * (bias + QS*sum')  (morphology.c:3197) equals
@@ -820,6 +771,11 @@ int launch_conv1d(const float *src, float *dst, size_t width, size_t height, int
     return fail(MB200_EINVAL, "conv1d: bad geometry");
   if (width * channels > 0x1fffffffull || height > 0x7fffffffull) return MB200_EUNSUPPORTED;   // 32-bit byte pitch
   if (d_changed != nullptr) return MB200_EUNSUPPORTED;   // `changed` counting lives in the generic kernel
+  if (channels == 4 && bias == 0.0 && ntaps <= 33) {     // RGBA: the FP64 matrix path (conv_mma.cu) when enabled
+    const int rc = launch_conv_mma(src, dst, width, height, axis, taps, ntaps, origin_offset, stream, io, epilogue,
+                                   epilogue_fused);
+    if (rc != MB200_EUNSUPPORTED) return rc;
+  }
   Conv1dArgs a{};
   a.src = src; a.dst = dst;
   a.width = static_cast<int>(width); a.height = static_cast<int>(height); a.channels = channels;

@@ -66,6 +66,15 @@ int launch_conv1d(const float *src, float *dst, size_t width, size_t height, int
                   int io = 0,    // io: 0 float->float, 1 float->raw double sums, 2 raw double sums->float (RGBA only)
                   const UnsharpEpilogue *epilogue = nullptr, bool *epilogue_fused = nullptr);
 
+// conv_mma.cu: the same pass on the FP64 matrix path (mma.sync m8n8k4) for RGBA images, bias 0, <= 33 taps; src / dst are
+// float4 pixels (io 0), double4 sums out (io 1) or in (io 2).  MB200_EUNSUPPORTED => use launch_conv1d's DFMA kernels.
+int launch_conv_mma(const void *src, void *dst, size_t width, size_t height, int axis, const double *taps_window_order,
+                    int ntaps, int origin_offset, void *stream, int io, const UnsharpEpilogue *epilogue,
+                    bool *epilogue_fused);
+void set_conv_mma(int enable);
+int conv_mma_enabled();
+unsigned long long conv_mma_launches();
+
 // conv2d.cu: general 2-D convolution / erode / dilate (MorphologyPrimitive row path)
 int launch_morph2d(const float *src, float *dst, size_t width, size_t height, int channels,
                    int method, const double *kernel_window_order, int kw, int kh, int ox, int oy,

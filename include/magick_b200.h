@@ -151,8 +151,11 @@ MB200_API int mb200_trim(size_t keep_bytes);
    the co-limit of the FP64-accumulating convolution kernels (bench.py's second roofline entry). */
 MB200_API int mb200_probe_fp64_fma_rate(double *fma_per_second);
 /* Test / developer hook: force the generic kernels ("no_rank1", "no_morph_stream", "no_resize_stream",
-   "resize_regular_h", "no_fused_unsharp", "resize_fused"; initialised from the MB200_<NAME> environment variables). */
+   "resize_regular_h", "no_fused_unsharp", "resize_fused", "conv_mma" = the FP64 mma.sync kernels of conv_mma.cu for
+   RGBA 1-D passes: 1 whenever possible, 0 never, -1 automatic = windows of <= 17 taps; initialised from the MB200_<NAME> environment variables).  mb200_get_option reads a switch back;
+   "conv_mma_launches" counts the passes the mma.sync kernels have served since process start. */
 MB200_API int mb200_set_option(const char *name, int value);
+MB200_API int mb200_get_option(const char *name, int *value);
 
 /* ------------------------------------------ pixel cache staged into HBM ---- */
 /* Residency of HOST pixel caches in HBM -- the CUDA analogue of the reference's OpenCL cache plumbing:

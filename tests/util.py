@@ -213,19 +213,27 @@ def orc_threshold(src: np.ndarray, op: int, thr) -> np.ndarray:
 
 
 # ---- run-time switches of the product library (mb200_set_option): restored after every test by conftest.py
-_touched_options = set()
+_touched_options = {}
+
+
+def get_option(name: str) -> int:
+    from imagemagick_b200 import _lib
+    v = C.c_int(0)
+    _lib.check(_lib.load().mb200_get_option(name.encode(), C.byref(v)))
+    return int(v.value)
 
 
 def set_option(name: str, value: int) -> None:
     from imagemagick_b200 import _lib
+    if name not in _touched_options:
+        _touched_options[name] = get_option(name)       # the process default (environment), restored after the test
     _lib.check(_lib.load().mb200_set_option(name.encode(), int(value)))
-    _touched_options.add(name)
 
 
 def reset_options() -> None:
     if not _touched_options:
         return
     from imagemagick_b200 import _lib
-    for name in list(_touched_options):
-        _lib.load().mb200_set_option(name.encode(), 0)
+    for name, value in list(_touched_options.items()):
+        _lib.load().mb200_set_option(name.encode(), value)
     _touched_options.clear()

@@ -40,6 +40,19 @@ if which in ("blur", "all"):
     k = im.AcquireKernelInfo("blur:0x4+90")
     ms = timeit(lambda: im.ConvolveImage(x, k)); report("  column pass only (33 taps)", ms, size * size, 32)
     del x
+if which == "taps":          # DFMA streaming kernels against the FP64 mma.sync kernels, per window length
+    from imagemagick_b200 import _lib
+    x = im.Image(torch.rand(size, size, 4, device="cuda") * 65535)
+    for mma in (0, 1):
+        _lib.check(_lib.load().mb200_set_option(b"conv_mma", mma))
+        for sigma in (1.0, 2.0, 3.0, 4.0):
+            ms = timeit(lambda: im.BlurImage(x, 0.0, sigma))
+            report(f"mma={mma} BlurImage sigma={sigma}", ms, size * size, 64)
+        ms = timeit(lambda: im.GaussianBlurImage(x, 0.0, 4.0)); report(f"mma={mma} GaussianBlurImage(0,4) rank-1", ms, size * size, 32)
+        ms = timeit(lambda: im.GaussianBlurImage(x, 0.0, 2.0)); report(f"mma={mma} GaussianBlurImage(0,2) rank-1", ms, size * size, 32)
+        ms = timeit(lambda: im.UnsharpMaskImage(x, 0.0, 4.0, 1.5, 0.02)); report(f"mma={mma} UnsharpMaskImage(0,4)", ms, size * size, 80)
+        ms = timeit(lambda: im.UnsharpMaskImage(x, 0.0, 2.0, 1.5, 0.02)); report(f"mma={mma} UnsharpMaskImage(0,2)", ms, size * size, 80)
+    del x
 if which in ("resize", "all"):
     s2 = size * 2 if size <= 8192 else size
     x = im.Image(torch.rand(s2, s2, 4, device="cuda") * 65535)
