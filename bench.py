@@ -344,8 +344,17 @@ def run_gpu(args):
             ts.append(a.elapsed_time(b))
         return statistics.median(ts)
 
+    def mma_launches():
+        v = C.c_int(0)
+        _lib.check(lib.mb200_get_option(b"conv_mma_launches", C.byref(v)))
+        return v.value
+
+    n_mma = mma_launches()
     row_ms = time_op(lambda: im.ConvolveImage(batch[0], row_k))
     col_ms = time_op(lambda: im.ConvolveImage(batch[1], col_k))
+    blur_on_mma = mma_launches() > n_mma            # which kernels serve the 33-tap passes (conv_mma.cu / conv1d.cu)
+    blur_kernels = (("conv_mma_kernel<10,0,0,0,4>", "conv_mma_kernel<10,1,0,0,4>") if blur_on_mma else
+                    ("conv_pair_async_kernel<33,2,0,0>", "conv_pair_kernel<33,2,1,0,true>"))
     fma_rate = C.c_double(0.0)
     _lib.check(lib.mb200_probe_fp64_fma_rate(C.byref(fma_rate)))
 
@@ -362,8 +371,8 @@ def run_gpu(args):
 
         px = W * H
         entry("config2_blur_8192_sigma4", med(blur_ms), px, 64 * px, "row + column pass, 32 B/px each")
-        entry("config2_blur_row_pass", row_ms, px, 32 * px, "conv_pair_async_kernel<33,2,0,0>")
-        entry("config2_blur_column_pass", col_ms, px, 32 * px, "conv_pair_kernel<33,2,1,0,L2PF>")
+        entry("config2_blur_row_pass", row_ms, px, 32 * px, blur_kernels[0])
+        entry("config2_blur_column_pass", col_ms, px, 32 * px, blur_kernels[1])
         entry("resize_8192_to_4096_lanczos", med(resize_ms), px, 36 * px, "V pass 24 B + H pass 12 B per input px")
         x = batch[2]
         entry("blur_8192_sigma2", time_op(lambda: im.BlurImage(x, 0.0, 2.0)), px, 64 * px, "17 + 17 taps")
@@ -567,7 +576,7 @@ def run_gpu(args):
                    "e2e_modes": e2e_modes, "copy_threads": int(lib.mb200_copy_threads())},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None,
-                     "kernel": "conv_pair_async_kernel<33,2,0,0> (row pass) / conv_pair_kernel<33,2,1,0,true> (column pass) "
+                     "kernel": f"{blur_kernels[0]} (row pass) / {blur_kernels[1]} (column pass) "
                                "of BlurImage; average of the two launches (median over the batch)",
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
         "roofline_fp64": {"bound": "fp64", "achieved": fma_per_launch / (blur_launch_ms * 1e-3) / 1e12,
@@ -586,11 +595,11 @@ def run_gpu(args):
     }
     try:
         prof = json.loads((ROOT / "profiles" / "r02_blur_traffic.json").read_text())
-        line["roofline"]["traffic"] = prof.get("dram_bytes_per_launch")
+        line["roofline"]["traffic"] = prof["mma" if blur_on_mma else "dfma"].get("dram_bytes_per_launch")
     except Exception:
         try:
             prof = json.loads((ROOT / "profiles" / "r01_blur_traffic.json").read_text())
-            line["roofline"]["traffic"] = prof.get("dram_bytes_per_launch")
+            line["roofline"]["traffic"] = prof["mma" if blur_on_mma else "dfma"].get("dram_bytes_per_launch")
         except Exception:
             pass
     print(json.dumps(line), flush=True)

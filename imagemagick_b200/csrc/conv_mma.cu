@@ -9,10 +9,10 @@
 // (tools/micro/dmma.cu) but one instruction carries 256 FMAs: ~7 instructions per DMMA instead of 1.7 per DFMA, 8
 // accumulator registers per tile, four CTAs per SM.  The price is the band structure: 8 consecutive outputs of a 33-tap
 // window touch 40 source samples, i.e. ten 8x4 Toeplitz tiles of which 17.5 % of the cells are zero (17 taps: 29 %,
-// 9 taps: 44 %).  Measured (profiles/r02_conv_mma.md): the unit is saturated either way (math_pipe_throttle is the top
-// stall), so for 33 taps the zero cells cancel what the freed issue slots buy (0.78-0.80 ms per pass on both paths),
-// while short windows -- where the DFMA kernels are latency-bound far from both roofs -- gain 4-19 %.  The launcher
-// therefore takes this path for windows of <= 17 taps and leaves longer ones to conv1d.cu.
+// 9 taps: 44 %).  Measured (profiles/r02_conv_mma.md): the FP64 unit is saturated either way (math_pipe_throttle is the
+// top stall), so at burst clocks the zero cells cancel what the freed issue slots buy for 33 taps (0.78-0.80 ms per
+// pass on both paths) while short windows gain 4-19 %; under sustained load this path needs less power per FMA, keeps
+// the SM clock at its maximum where the DFMA kernels are power-capped, and is ~5 % faster for 33 taps as well.
 //
 //   D[m][n] += A[m][k] * B[k][n]     m = 8 consecutive outputs along the filter axis
 //                                    k = 4 consecutive source samples (one of NKS k-steps)
@@ -350,7 +350,7 @@ struct MmaTuning {
       const char *v = getenv(name);
       return (v && *v) ? atoi(v) : fallback;
     };
-    enable = get("MB200_MMA", -1);      // -1: automatic (windows of <= 17 taps, float in / float out), 0: never, 1: whenever possible
+    enable = get("MB200_MMA", -1);      // -1: automatic (float in / float out passes), 0: never, 1: whenever possible
     strip = get("MB200_MMA_STRIP", 512);
     minb = get("MB200_MMA_MINB", 4);
   }
@@ -407,11 +407,14 @@ unsigned long long conv_mma_launches() { return g_mma_launches.load(std::memory_
 int launch_conv_mma(const void *src, void *dst, size_t width, size_t height, int axis, const double *taps, int ntaps,
                     int origin_offset, void *stream, int io, const UnsharpEpilogue *epilogue, bool *epilogue_fused) {
   if (epilogue_fused) *epilogue_fused = false;
-  // Measured on 8192^2 (tools/devbench.py taps, profiles/r02_conv_mma.md): the matrix path wins for short windows
-  // (9 taps 1.04 vs 1.24 ms, 17 taps 1.18 vs 1.22 ms, UnsharpMask(0,2) 1.31 vs 1.43 ms) and loses from 25 taps on
-  // (33 taps 1.61 vs 1.56 ms: both paths saturate the FP64 unit and this one spends 17.5 % of it on zero cells).
+  // Default (-1): every float-in / float-out pass of <= 33 taps.  Measured on 8192^2 (profiles/r02_conv_mma.md): at burst
+  // clocks the matrix path wins for short windows (9 taps 1.04 vs 1.24 ms, 17 taps 1.18 vs 1.22 ms) and is 3 % behind for
+  // 33 taps (1.61 vs 1.56 ms: both paths saturate the FP64 unit, this one spends 17.5 % of it on zero cells) -- but it
+  // draws less power per FMA: in a >= 1.3 s region the DFMA kernels sit on the 1000 W cap at 1845 MHz while this path
+  // stays at 1965 MHz, and bench.py's step is 4.7 % faster (64.4 vs 67.4 ms per 32 images).  The rank-1 passes with a
+  // double intermediate (io 1 / 2) are equal under load and slower at burst clocks: they keep the DFMA kernels.
   const int mode = mma_tuning().enable;
-  if (mode == 0 || (mode < 0 && (ntaps > 17 || io != 0))) return MB200_EUNSUPPORTED;
+  if (mode == 0 || (mode < 0 && io != 0)) return MB200_EUNSUPPORTED;
   if (ntaps < 1 || ntaps > 33 || width * 32 > 0x7fffffffull || height > 0x3fffffffull) return MB200_EUNSUPPORTED;
   if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) != 0) return MB200_EUNSUPPORTED;
   MmaArgs a{};

@@ -16,7 +16,6 @@
 #include <cmath>
 #include <utility>
 #include <vector>
-#include <vector>
 
 namespace {
 
@@ -31,7 +30,7 @@ inline double perceptible_reciprocal(double x) {
 }
 
 enum class Fn { Box, Triangle, CubicBC, Hann, Hamming, Blackman, Gaussian, Quadratic, Sinc, SincFast,
-                Welch, Bohman, Lagrange, Cosine, CubicSpline, Mks2013, Mks2021, Unsupported };
+                Welch, Bohman, Lagrange, Cosine, CubicSpline, Mks2013, Mks2021, Jinc, Kaiser, Unsupported };
 
 struct FnEntry { Fn fn; double support, scale, B, C; };
 
@@ -50,10 +49,10 @@ const FnEntry kFunctions[MB200_SentinelFilter] = {
   {Fn::CubicBC, 2.0, 2.0, 1.0, 0.0},    // Cubic
   {Fn::CubicBC, 2.0, 1.0, 0.0, 0.5},    // Catrom
   {Fn::CubicBC, 2.0, 8.0 / 7.0, 1. / 3., 1. / 3.},   // Mitchell
-  {Fn::Unsupported, 3.0, 1.2196698912665045, 0, 0},  // Jinc (Bessel): not on the 1-D path
+  {Fn::Jinc, 3.0, 1.2196698912665045, 0, 0},         // Jinc: 3 lobes, converted to the third zero below
   {Fn::Sinc, 4.0, 1.0, 0, 0},
   {Fn::SincFast, 4.0, 1.0, 0, 0},
-  {Fn::Unsupported, 1.0, 1.0, 0, 0},    // Kaiser (needs I0)
+  {Fn::Kaiser, 1.0, 1.0, 0, 0},         // Kaiser window (I0)
   {Fn::Welch, 1.0, 1.0, 0, 0},
   {Fn::CubicBC, 2.0, 2.0, 1.0, 0.0},    // Parzen
   {Fn::Bohman, 1.0, 1.0, 0, 0},
@@ -116,6 +115,11 @@ struct ResizeFilter {
       coefficient[1] = perceptible_reciprocal(2.0 * sigma * sigma);
       coefficient[2] = perceptible_reciprocal(k2Pi * sigma * sigma);
     }
+    if (filter == Fn::Kaiser || window == Fn::Kaiser) {      // :1104-1120 with the default beta
+      coefficient[0] = 6.5;
+      coefficient[1] = perceptible_reciprocal(bessel_i0(6.5));
+    }
+    if (filter == Fn::Jinc) support = jinc_zero(static_cast<long>(support));   // :1135-1150 lobes -> support
     if (blur < kEps) blur = kEps;
     window_support = support;
     scale *= perceptible_reciprocal(window_support);
@@ -132,6 +136,66 @@ struct ResizeFilter {
       coefficient[6] = (-1.0 / 6.0) * B - C;
     }
     valid = true;
+  }
+
+  // ---- Bessel functions of the Jinc filter and the Kaiser window (resize.c:1385-1553).  The reference evaluates them
+  // with fixed rational approximations; the weights must come out bit-identical, so the coefficient tables and the
+  // association of every product are the reference's: p = ((p * u) * u) + c, one table pair per range.
+  template <int N>
+  static double rational(const double (&num)[N], const double (&den)[N], double u) {
+    double p = num[N - 1], q = den[N - 1];
+    for (int i = N - 2; i >= 0; --i) {
+      p = p * u * u + num[i];
+      q = q * u * u + den[i];
+    }
+    return p / q;
+  }
+  static double bessel_i0(double x) {          // :1385 power series, terms down to MagickEpsilon
+    const double y = x * x / 4.0;
+    double sum = 1.0, term = y;
+    for (long i = 2; term > kEps; ++i) {
+      sum += term;
+      term *= y / (static_cast<double>(i) * i);
+    }
+    return sum;
+  }
+  static double bessel_j1_signed(double x) {   // :1535 BesselOrderOne
+    static const double kJ1Num[9] = {
+      0.581199354001606143928050809e+21, -0.6672106568924916298020941484e+20, 0.2316433580634002297931815435e+19,
+      -0.3588817569910106050743641413e+17, 0.2908795263834775409737601689e+15, -0.1322983480332126453125473247e+13,
+      0.3413234182301700539091292655e+10, -0.4695753530642995859767162166e+7, 0.270112271089232341485679099e+4};
+    static const double kJ1Den[9] = {
+      0.11623987080032122878585294e+22, 0.1185770712190320999837113348e+20, 0.6092061398917521746105196863e+17,
+      0.2081661221307607351240184229e+15, 0.5243710262167649715406728642e+12, 0.1013863514358673989967045588e+10,
+      0.1501793594998585505921097578e+7, 0.1606931573481487801970916749e+4, 0.1e+1};
+    static const double kP1Num[6] = {
+      0.352246649133679798341724373e+5, 0.62758845247161281269005675e+5, 0.313539631109159574238669888e+5,
+      0.49854832060594338434500455e+4, 0.2111529182853962382105718e+3, 0.12571716929145341558495e+1};
+    static const double kP1Den[6] = {
+      0.352246649133679798068390431e+5, 0.626943469593560511888833731e+5, 0.312404063819041039923015703e+5,
+      0.4930396490181088979386097e+4, 0.2030775189134759322293574e+3, 0.1e+1};
+    static const double kQ1Num[6] = {
+      0.3511751914303552822533318e+3, 0.7210391804904475039280863e+3, 0.4259873011654442389886993e+3,
+      0.831898957673850827325226e+2, 0.45681716295512267064405e+1, 0.3532840052740123642735e-1};
+    static const double kQ1Den[6] = {
+      0.74917374171809127714519505e+4, 0.154141773392650970499848051e+5, 0.91522317015169922705904727e+4,
+      0.18111867005523513506724158e+4, 0.1038187585462133728776636e+3, 0.1e+1};
+    if (x == 0.0) return 0.0;
+    const double ax = x < 0.0 ? -x : x;
+    if (ax < 8.0) return x * rational(kJ1Num, kJ1Den, ax);
+    const double u = 8.0 / ax;
+    const double q = std::sqrt(2.0 / (kPi * ax)) *
+                     (rational(kP1Num, kP1Den, u) * (1.0 / std::sqrt(2.0) * (std::sin(ax) - std::cos(ax))) -
+                      8.0 / ax * rational(kQ1Num, kQ1Den, u) * (-1.0 / std::sqrt(2.0) * (std::sin(ax) + std::cos(ax))));
+    return x < 0.0 ? -q : q;
+  }
+  static double jinc_zero(long lobes) {        // :955-973 first zero crossings of the Jinc function
+    static const double kZeros[16] = {
+      1.2196698912665045, 2.2331305943815286, 3.2383154841662362, 4.2410628637960699, 5.2427643768701817,
+      6.2439216898644877, 7.2447598687199570, 8.2453949139520427, 9.2458926849494673, 10.246293348754916,
+      11.246622794877883, 12.246898461138105, 13.247132522181061, 14.247333735806849, 15.247508563037300,
+      16.247661874700962};
+    return lobes > 16 ? kZeros[15] : kZeros[lobes - 1];
   }
 
   // resize.c:493-587, Q16 coefficient set (:547-563)
@@ -192,6 +256,8 @@ struct ResizeFilter {
         if (x < 1.0) return ((x - 9.0 / 5.0) * x - 1.0 / 5.0) * x + 1.0;
         if (x < 2.0) return ((-1.0 / 3.0 * (x - 1.0) + 4.0 / 5.0) * (x - 1.0) - 7.0 / 15.0) * (x - 1.0);
         return 0.0;
+      case Fn::Jinc: return x == 0.0 ? 0.5 * kPi : bessel_j1_signed(kPi * x) / x;                    // :348
+      case Fn::Kaiser: return coefficient[1] * bessel_i0(coefficient[0] * std::sqrt(1.0 - x * x));    // :366
       case Fn::Mks2013:
         if (x < 0.5) return 0.625 + 1.75 * (0.5 - x) * (0.5 + x);
         if (x < 1.5) return (1.0 - x) * (1.75 - x);

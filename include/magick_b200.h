@@ -152,7 +152,7 @@ MB200_API int mb200_trim(size_t keep_bytes);
 MB200_API int mb200_probe_fp64_fma_rate(double *fma_per_second);
 /* Test / developer hook: force the generic kernels ("no_rank1", "no_morph_stream", "no_resize_stream",
    "resize_regular_h", "no_fused_unsharp", "resize_fused", "conv_mma" = the FP64 mma.sync kernels of conv_mma.cu for
-   RGBA 1-D passes: 1 whenever possible, 0 never, -1 automatic = windows of <= 17 taps; initialised from the MB200_<NAME> environment variables).  mb200_get_option reads a switch back;
+   RGBA 1-D passes: 1 whenever possible, 0 never, -1 automatic = float-in / float-out passes; initialised from the MB200_<NAME> environment variables).  mb200_get_option reads a switch back;
    "conv_mma_launches" counts the passes the mma.sync kernels have served since process start. */
 MB200_API int mb200_set_option(const char *name, int value);
 MB200_API int mb200_get_option(const char *name, int *value);

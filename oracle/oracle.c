@@ -606,7 +606,7 @@ int orc_unsharp(const float *src, float *dst, size_t w, size_t h, int ch,
 
 enum { FN_BOX, FN_TRIANGLE, FN_CUBICBC, FN_HANN, FN_HAMMING, FN_BLACKMAN, FN_GAUSSIAN,
        FN_QUADRATIC, FN_SINC, FN_SINCFAST, FN_WELCH, FN_BOHMAN, FN_LAGRANGE, FN_COSINE,
-       FN_CUBICSPLINE, FN_MKS2013, FN_MKS2021, FN_UNSUPPORTED };
+       FN_CUBICSPLINE, FN_MKS2013, FN_MKS2021, FN_JINC, FN_KAISER, FN_UNSUPPORTED };
 
 typedef struct { int fn; double support, scale, B, C; } fn_entry;
 
@@ -616,8 +616,8 @@ static const fn_entry fn_table[ORC_F_SENTINEL] = {
   { FN_TRIANGLE, 1.0, 1.0, 0, 0 }, { FN_CUBICBC, 1.0, 1.0, 0, 0 }, { FN_HANN, 1.0, 1.0, 0, 0 },
   { FN_HAMMING, 1.0, 1.0, 0, 0 }, { FN_BLACKMAN, 1.0, 1.0, 0, 0 }, { FN_GAUSSIAN, 2.0, 1.5, 0, 0 },
   { FN_QUADRATIC, 1.5, 1.5, 0, 0 }, { FN_CUBICBC, 2.0, 2.0, 1.0, 0.0 }, { FN_CUBICBC, 2.0, 1.0, 0.0, 0.5 },
-  { FN_CUBICBC, 2.0, 8.0 / 7.0, 1. / 3., 1. / 3. }, { FN_UNSUPPORTED, 3.0, 1.2196698912665045, 0, 0 },
-  { FN_SINC, 4.0, 1.0, 0, 0 }, { FN_SINCFAST, 4.0, 1.0, 0, 0 }, { FN_UNSUPPORTED, 1.0, 1.0, 0, 0 },
+  { FN_CUBICBC, 2.0, 8.0 / 7.0, 1. / 3., 1. / 3. }, { FN_JINC, 3.0, 1.2196698912665045, 0, 0 },
+  { FN_SINC, 4.0, 1.0, 0, 0 }, { FN_SINCFAST, 4.0, 1.0, 0, 0 }, { FN_KAISER, 1.0, 1.0, 0, 0 },
   { FN_WELCH, 1.0, 1.0, 0, 0 }, { FN_CUBICBC, 2.0, 2.0, 1.0, 0.0 }, { FN_BOHMAN, 1.0, 1.0, 0, 0 },
   { FN_TRIANGLE, 1.0, 1.0, 0, 0 }, { FN_LAGRANGE, 2.0, 1.0, 0, 0 }, { FN_SINCFAST, 3.0, 1.0, 0, 0 },
   { FN_SINCFAST, 3.0, 1.0, 0, 0 }, { FN_SINCFAST, 2.0, 1.0, 0, 0 }, { FN_SINCFAST, 2.0, 1.0, 0, 0 },
@@ -647,6 +647,73 @@ typedef struct {
   double support, window_support, scale, blur, coef[7];
 } rfilter;
 
+/* resize.c:1385-1407 I0: zeroth-order modified Bessel function, power series until the term drops below MagickEpsilon */
+static double bessel_i0(double x)
+{
+  double sum = 1.0, y = x * x / 4.0, t = y;
+  long i;
+  for (i = 2; t > EPS; i++) {
+    sum += t;
+    t *= y / ((double) i * i);
+  }
+  return sum;
+}
+
+/* resize.c:1410-1453 J1 (|x| < 8: rational approximation in x*x), :1456-1533 P1 / Q1 (asymptotic range, in (8/x)^2) */
+static double ratio_xx(const double *pc, const double *qc, int n, double x)
+{
+  double p = pc[n - 1], q = qc[n - 1];
+  int i;
+  for (i = n - 2; i >= 0; i--) {
+    p = p * x * x + pc[i];
+    q = q * x * x + qc[i];
+  }
+  return p / q;
+}
+static double ratio_8x(const double *pc, const double *qc, int n, double x)
+{
+  double p = pc[n - 1], q = qc[n - 1];
+  int i;
+  for (i = n - 2; i >= 0; i--) {
+    p = p * (8.0 / x) * (8.0 / x) + pc[i];
+    q = q * (8.0 / x) * (8.0 / x) + qc[i];
+  }
+  return p / q;
+}
+/* resize.c:1535-1553 BesselOrderOne */
+static double bessel_order_one(double x)
+{
+  static const double j1p[9] = {
+    0.581199354001606143928050809e+21, -0.6672106568924916298020941484e+20, 0.2316433580634002297931815435e+19,
+    -0.3588817569910106050743641413e+17, 0.2908795263834775409737601689e+15, -0.1322983480332126453125473247e+13,
+    0.3413234182301700539091292655e+10, -0.4695753530642995859767162166e+7, 0.270112271089232341485679099e+4 };
+  static const double j1q[9] = {
+    0.11623987080032122878585294e+22, 0.1185770712190320999837113348e+20, 0.6092061398917521746105196863e+17,
+    0.2081661221307607351240184229e+15, 0.5243710262167649715406728642e+12, 0.1013863514358673989967045588e+10,
+    0.1501793594998585505921097578e+7, 0.1606931573481487801970916749e+4, 0.1e+1 };
+  static const double p1p[6] = {
+    0.352246649133679798341724373e+5, 0.62758845247161281269005675e+5, 0.313539631109159574238669888e+5,
+    0.49854832060594338434500455e+4, 0.2111529182853962382105718e+3, 0.12571716929145341558495e+1 };
+  static const double p1q[6] = {
+    0.352246649133679798068390431e+5, 0.626943469593560511888833731e+5, 0.312404063819041039923015703e+5,
+    0.4930396490181088979386097e+4, 0.2030775189134759322293574e+3, 0.1e+1 };
+  static const double q1p[6] = {
+    0.3511751914303552822533318e+3, 0.7210391804904475039280863e+3, 0.4259873011654442389886993e+3,
+    0.831898957673850827325226e+2, 0.45681716295512267064405e+1, 0.3532840052740123642735e-1 };
+  static const double q1q[6] = {
+    0.74917374171809127714519505e+4, 0.154141773392650970499848051e+5, 0.91522317015169922705904727e+4,
+    0.18111867005523513506724158e+4, 0.1038187585462133728776636e+3, 0.1e+1 };
+  double p, q;
+  if (x == 0.0) return 0.0;
+  p = x;
+  if (x < 0.0) x = -x;
+  if (x < 8.0) return p * ratio_xx(j1p, j1q, 9, x);
+  q = sqrt((double) (2.0 / (PI_ * x))) * (ratio_8x(p1p, p1q, 6, x) * (1.0 / sqrt(2.0) * (sin(x) - cos(x))) -
+      8.0 / x * ratio_8x(q1p, q1q, 6, x) * (-1.0 / sqrt(2.0) * (sin(x) + cos(x))));
+  if (p < 0.0) q = -q;
+  return q;
+}
+
 /* resize.c:803-1226 AcquireResizeFilter with no "filter:*" artifacts, not cylindrical */
 static int rfilter_init(rfilter *rf, int filter)
 {
@@ -668,6 +735,19 @@ static int rfilter_init(rfilter *rf, int filter)
     rf->coef[0] = value;
     rf->coef[1] = precip(2.0 * value * value);
     rf->coef[2] = precip(TWOPI_ * value * value);
+  }
+  if (rf->filter_fn == FN_KAISER || rf->window_fn == FN_KAISER) {       /* :1104-1120, default beta */
+    rf->coef[0] = 6.5;
+    rf->coef[1] = precip(bessel_i0(6.5));
+  }
+  if (rf->filter_fn == FN_JINC) {                                       /* :1135-1150: lobes -> first zeros of the Jinc */
+    static const double jinc_zeros[16] = {
+      1.2196698912665045, 2.2331305943815286, 3.2383154841662362, 4.2410628637960699, 5.2427643768701817,
+      6.2439216898644877, 7.2447598687199570, 8.2453949139520427, 9.2458926849494673, 10.246293348754916,
+      11.246622794877883, 12.246898461138105, 13.247132522181061, 14.247333735806849, 15.247508563037300,
+      16.247661874700962 };
+    if (rf->support > 16) rf->support = jinc_zeros[15];
+    else rf->support = jinc_zeros[((long) rf->support) - 1];
   }
   if (rf->blur < EPS) rf->blur = EPS;
   rf->window_support = rf->support;
@@ -753,6 +833,11 @@ static double eval_fn(int fn, double x, const rfilter *rf)
     if (x < 1.0) return ((x - 9.0 / 5.0) * x - 1.0 / 5.0) * x + 1.0;
     if (x < 2.0) return ((-1.0 / 3.0 * (x - 1.0) + 4.0 / 5.0) * (x - 1.0) - 7.0 / 15.0) * (x - 1.0);
     return 0.0;
+  case FN_JINC:                                                         /* :348-364 */
+    if (x == 0.0) return 0.5 * PI_;
+    return bessel_order_one(PI_ * x) / x;
+  case FN_KAISER:                                                       /* :366-382 */
+    return rf->coef[1] * bessel_i0(rf->coef[0] * sqrt((double) (1.0 - x * x)));
   case FN_MKS2013:                                                      /* :422-438 */
     if (x < 0.5) return 0.625 + 1.75 * (0.5 - x) * (0.5 + x);
     if (x < 1.5) return (1.0 - x) * (1.75 - x);

@@ -296,7 +296,7 @@ def test_thumbnail_pixel_path(ch):
     assert max_ulp(im.ThumbnailImage(im.Image(src), 100, 75).pixels, _host(im.ThumbnailImage(_dev(src), 100, 75))) == 0
 
 
-FILTERS = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33]
+FILTERS = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33]
 
 
 @pytest.mark.parametrize("ch", [1, 2, 3, 4])
@@ -502,7 +502,7 @@ def test_errors_are_loud():
     with pytest.raises(im.MagickB200Error):
         im.MorphologyImage(_dev(src), 18, 1, "Disk:1")                    # HitAndMiss: sequential primitive -> decline
     with pytest.raises(im.MagickB200Error):
-        im.ResizeImage(_dev(src), 8, 8, im.JincFilter)
+        im.ResizeImage(_dev(src), 8, 8, 34)                               # SentinelFilter: not a filter
     with pytest.raises(im.MagickB200Error):
         im.AcquireKernelInfo("nosuchkernel:3")
     with pytest.raises(im.MagickB200Error):

@@ -68,12 +68,11 @@ def test_optimal_widths_and_blur_taps_match_oracle(r, s):
     assert same_kernel(mine[0], util.orc_kernel("gaussian", r, s).array())
 
 
-@pytest.mark.parametrize("filt", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 17, 18, 19, 20, 21, 22, 23, 24, 25,
-                                  26, 27, 28, 29, 30, 31, 32, 33])
+@pytest.mark.parametrize("filt", list(range(1, 34)))     # every FilterType, Jinc (13) and Kaiser (16) included
 def test_filter_weights_match_oracle(filt):
     lib, o = _lib.load(), util.oracle()
     assert lib.mb200_resize_filter_support(filt) == o.orc_filter_support(filt)
-    for x in np.linspace(-5.0, 5.0, 401):
+    for x in np.concatenate([np.linspace(-5.0, 5.0, 401), [2.5464790894703255, 2.6, 3.2383154841662362, 0.999999, 1.0]]):
         a, b = lib.mb200_resize_filter_weight(filt, float(x)), o.orc_filter_weight(filt, float(x))
         assert a == b or (np.isnan(a) and np.isnan(b)), (filt, x)
 
@@ -95,7 +94,8 @@ def test_resize_contributions_lanczos_2x():
     scale = 1.0 / (1.0 / 0.5 + 1e-12)                   # resize.c:3363, :3386
     raw = np.array([o.orc_filter_weight(22, scale * ((start[10] + j) - ((10 + 0.5) / 0.5 + 1e-12) + 0.5)) for j in range(12)])
     assert np.allclose(w[10, :12], raw * (1.0 / raw.sum()), rtol=0, atol=1e-16)
-    assert lib.mb200_resize_contributions(13, n_in, n_out, 0.5, None, None, None, 0) == _lib.EUNSUPPORTED  # Jinc
+    assert lib.mb200_resize_contributions(13, n_in, n_out, 0.5, None, None, None, 0) == 15   # Jinc: support 3.238.. * 2 -> 2*6.48+3
+    assert lib.mb200_resize_contributions(0, n_in, n_out, 0.5, None, None, None, 0) == _lib.EUNSUPPORTED  # Undefined
 
 
 def test_no_gpu_means_loud_failure_not_cpu_fallback():

@@ -116,7 +116,7 @@ def test_thumbnail_pixel_path_bit_exact(ch):
 @pytest.mark.parametrize("ch", [1, 4])
 def test_resize_all_filters_bit_exact(ch):
     src = make_image(47, 33, ch, seed=5, kind="alpha_blocks")
-    for filt in [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33]:
+    for filt in [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33]:
         for ow, oh in ((23, 16), (24, 17), (94, 66), (47, 10), (13, 33)):
             a, b = np.empty((oh, ow, ch), np.float32), np.empty((oh, ow, ch), np.float32)
             assert util.ref().ref_resize(P(src), 47, 33, ch, P(a), ow, oh, filt) == 0
