@@ -53,6 +53,7 @@ EdgeInMorphology, EdgeOutMorphology, EdgeMorphology, TopHatMorphology, BottomHat
 LabColorspace, RGBColorspace, sRGBColorspace, XYZColorspace = 11, 21, 23, 26
 CMYColorspace, OHTAColorspace, Rec601YCbCrColorspace, Rec709YCbCrColorspace = 1, 18, 19, 20
 YCbCrColorspace, YDbDrColorspace, YIQColorspace, YPbPrColorspace, YUVColorspace = 27, 29, 30, 31, 32
+HCLColorspace, HCLpColorspace, HSBColorspace, HSIColorspace, HSLColorspace, HSVColorspace, HWBColorspace = 4, 5, 6, 7, 8, 9, 10
 
 # kernel types of include/magick_b200.h
 (UserDefinedKernel, BlurKernel, GaussianKernel, DiskKernel, SquareKernel, DiamondKernel, OctagonKernel,

@@ -27,7 +27,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibilit
               "-Xptxas", "-v"]
 
 SOURCES = ["runtime.cu", "kernel_info.cpp", "resize_filter.cpp", "conv1d.cu", "conv_mma.cu", "morph2d.cu", "morph_stream.cu", "cache.cu",
-           "resize.cu", "resize_stream.cu", "colorspace.cu", "pointwise.cu", "equalize.cu", "stencils.cu", "api.cu"]
+           "resize.cu", "resize_stream.cu", "colorspace.cu", "hexcone.cu", "pointwise.cu", "equalize.cu", "stencils.cu", "api.cu"]
 
 
 def _nvcc() -> str:

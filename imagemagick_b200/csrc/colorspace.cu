@@ -486,20 +486,23 @@ int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to
   auto core = [](int cs) { return cs == MB200_sRGBColorspace || cs == MB200_LabColorspace ||
                                   cs == MB200_XYZColorspace || cs == MB200_RGBColorspace; };
   MatrixLeg from_leg{}, to_leg{};
-  const bool from_matrix = !core(from) && matrix_leg(from, false, from_leg);
-  const bool to_matrix = !core(to) && matrix_leg(to, true, to_leg);
-  if ((!core(from) && !from_matrix) || (!core(to) && !to_matrix))
+  const bool from_hex = is_hexcone_colorspace(from), to_hex = is_hexcone_colorspace(to);
+  const bool from_matrix = !core(from) && !from_hex && matrix_leg(from, false, from_leg);
+  const bool to_matrix = !core(to) && !to_hex && matrix_leg(to, true, to_leg);
+  if ((!core(from) && !from_matrix && !from_hex) || (!core(to) && !to_matrix && !to_hex))
     return fail(MB200_EUNSUPPORTED, "colorspace %d -> %d not implemented", from, to);
   if (from == to) return MB200_OK;
   int rc = MB200_OK;
   if (from != MB200_sRGBColorspace) {          // colorspace.c:1773-1774: back to sRGB first
-    if (from_matrix) rc = launch_matrix_leg(buf, npixels, channels, from_leg, s);
+    if (from_hex) rc = launch_hexcone_leg(buf, npixels, channels, from, false, s);
+    else if (from_matrix) rc = launch_matrix_leg(buf, npixels, channels, from_leg, s);
     else if (from == MB200_LabColorspace) rc = launch_mode<kFromLab>(buf, npixels, channels, s);
     else if (from == MB200_XYZColorspace) rc = launch_mode<kFromXyz>(buf, npixels, channels, s);
     else rc = launch_mode<kFromLinear>(buf, npixels, channels, s);
     if (rc) return rc;
   }
-  if (to_matrix) rc = launch_matrix_leg(buf, npixels, channels, to_leg, s);
+  if (to_hex) rc = launch_hexcone_leg(buf, npixels, channels, to, true, s);
+  else if (to_matrix) rc = launch_matrix_leg(buf, npixels, channels, to_leg, s);
   else if (to == MB200_LabColorspace) rc = launch_mode<kToLab>(buf, npixels, channels, s);
   else if (to == MB200_XYZColorspace) rc = launch_mode<kToXyz>(buf, npixels, channels, s);
   else if (to == MB200_RGBColorspace) rc = launch_mode<kToLinear>(buf, npixels, channels, s);

@@ -112,6 +112,10 @@ int launch_resize_fused(const float *src, size_t width, size_t height, float *ds
 // colorspace.cu
 int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to, void *stream);
 
+// hexcone.cu: HCL, HCLp, HSB, HSI, HSL, HSV, HWB (one leg: sRGB -> space or space -> sRGB), in place
+bool is_hexcone_colorspace(int cs);
+int launch_hexcone_leg(float *buf, size_t npixels, int channels, int space, bool forward, void *stream);
+
 // pointwise.cu
 int launch_unsharp_combine(const float *src, float *blur_inout, size_t n, double gain,
                            double quantum_threshold, void *stream);

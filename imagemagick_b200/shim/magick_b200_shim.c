@@ -394,6 +394,13 @@ static int map_colorspace(ColorspaceType c)
     case YIQColorspace: return MB200_YIQColorspace;
     case YPbPrColorspace: return MB200_YPbPrColorspace;
     case YUVColorspace: return MB200_YUVColorspace;
+    case HCLColorspace: return MB200_HCLColorspace;
+    case HCLpColorspace: return MB200_HCLpColorspace;
+    case HSBColorspace: return MB200_HSBColorspace;
+    case HSIColorspace: return MB200_HSIColorspace;
+    case HSLColorspace: return MB200_HSLColorspace;
+    case HSVColorspace: return MB200_HSVColorspace;
+    case HWBColorspace: return MB200_HWBColorspace;
     default: return -1;
   }
 }

@@ -133,6 +133,19 @@ int main(void)
   if (TransformImageColorspace(a, LabColorspace, ex) == MagickFalse || a->colorspace != LabColorspace) failures++;
   B200ShimEnable(0); (void) __real_TransformImageColorspace(b, LabColorspace, ex); B200ShimEnable(1);
   CHECK("TransformImageColorspace sRGB->Lab", 1, a, b);
+  a = CloneImage(rgba, 0, 0, MagickTrue, ex); b = CloneImage(rgba, 0, 0, MagickTrue, ex);
+  if (TransformImageColorspace(a, HSLColorspace, ex) == MagickFalse || a->colorspace != HSLColorspace) failures++;
+  B200ShimEnable(0); (void) __real_TransformImageColorspace(b, HSLColorspace, ex); B200ShimEnable(1);
+  CHECK("TransformImageColorspace sRGB->HSL", 0, a, b);
+  a = CloneImage(rgb, 0, 0, MagickTrue, ex); b = CloneImage(rgb, 0, 0, MagickTrue, ex);
+  (void) SetImageColorspace(a, HWBColorspace, ex); (void) SetImageColorspace(b, HWBColorspace, ex);
+  if (TransformImageColorspace(a, HSVColorspace, ex) == MagickFalse || a->colorspace != HSVColorspace) failures++;
+  B200ShimEnable(0); (void) __real_TransformImageColorspace(b, HSVColorspace, ex); B200ShimEnable(1);
+  CHECK("TransformImageColorspace HWB->HSV", 0, a, b);
+  CHECK("ResizeImage Jinc 50% RGBA", 1, ResizeImage(rgba, rgba->columns / 2, rgba->rows / 2, JincFilter, ex),
+        CPU(__real_ResizeImage(rgba, rgba->columns / 2, rgba->rows / 2, JincFilter, ex)));
+  CHECK("ResizeImage Kaiser 150% RGB", 1, ResizeImage(rgb, rgb->columns * 3 / 2, rgb->rows * 3 / 2, KaiserFilter, ex),
+        CPU(__real_ResizeImage(rgb, rgb->columns * 3 / 2, rgb->rows * 3 / 2, KaiserFilter, ex)));
   /* threshold.c point operators: in place, bit exact */
   a = CloneImage(rgba, 0, 0, MagickTrue, ex); b = CloneImage(rgba, 0, 0, MagickTrue, ex);
   if (BilevelImage(a, 30000.0, ex) == MagickFalse) failures++;

@@ -81,6 +81,13 @@ typedef enum {
 /* MagickCore/colorspace.h:27-67 ColorspaceType -- same numeric values */
 typedef enum {
   MB200_CMYColorspace = 1,
+  MB200_HCLColorspace = 4,            /* hue / saturation family of the generic branch (colorspace-private.h:149-529, */
+  MB200_HCLpColorspace = 5,           /* :801-1064): bit exact, HSI <= 1 ULP                                        */
+  MB200_HSBColorspace = 6,
+  MB200_HSIColorspace = 7,
+  MB200_HSLColorspace = 8,
+  MB200_HSVColorspace = 9,
+  MB200_HWBColorspace = 10,
   MB200_LabColorspace = 11,
   MB200_OHTAColorspace = 18,          /* LUT branch, colorspace.c:1229-1494 */
   MB200_Rec601YCbCrColorspace = 19,   /* LUT branch */

@@ -1286,6 +1286,253 @@ static int colorspace_matrix_leg(float *buf, long n, int ch, int cs, int forward
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+   Hexcone colourspaces of the generic branch (colorspace.c:958-1054 forward, :2296-2390 inverse):
+   HCL, HCLp, HSB, HSI, HSL, HSV, HWB.  Forward takes Quantum-range R, G, B and returns unit-range
+   components that are stored as (float) (QuantumRange * X); inverse takes QuantumScale * sample and
+   returns Quantum-range values that are cast to float (HDRI ClampToQuantum).
+   ------------------------------------------------------------------------------------------ */
+#define ORC_MAX(x, y) (((x) > (y)) ? (x) : (y))
+#define ORC_MIN(x, y) (((x) < (y)) ? (x) : (y))
+
+static void rgb_to_hcl(double red, double green, double blue, double *hue, double *chroma, double *luma)
+{ /* colorspace-private.h:801-832 (HCL) and :834-865 (HCLp): identical forward transforms */
+  double c, h, max;
+  max = ORC_MAX(red, ORC_MAX(green, blue));
+  c = max - (double) ORC_MIN(red, ORC_MIN(green, blue));
+  h = 0.0;
+  if (fabs(c) < EPS) h = 0.0;
+  else if (fabs(red - max) < EPS) h = fmod((green - blue) / c + 6.0, 6.0);
+  else if (fabs(green - max) < EPS) h = ((blue - red) / c) + 2.0;
+  else if (fabs(blue - max) < EPS) h = ((red - green) / c) + 4.0;
+  *hue = (h / 6.0);
+  *chroma = QS * c;
+  *luma = QS * (0.298839 * red + 0.586811 * green + 0.114350 * blue);
+}
+
+static void hcl_to_rgb(double hue, double chroma, double luma, int clip, double *red, double *green, double *blue)
+{ /* colorspace-private.h:149-212 (HCL), :214-290 (HCLp: clip != 0) */
+  double b = 0.0, c, g = 0.0, h, m, r = 0.0, x, z;
+  h = 6.0 * hue;
+  c = chroma;
+  x = c * (1.0 - fabs(fmod(h, 2.0) - 1.0));
+  if ((0.0 <= h) && (h < 1.0)) { r = c; g = x; }
+  else if ((1.0 <= h) && (h < 2.0)) { r = x; g = c; }
+  else if ((2.0 <= h) && (h < 3.0)) { g = c; b = x; }
+  else if ((3.0 <= h) && (h < 4.0)) { g = x; b = c; }
+  else if ((4.0 <= h) && (h < 5.0)) { r = x; b = c; }
+  else if ((5.0 <= h) && (h < 6.0)) { r = c; b = x; }
+  m = luma - (0.298839 * r + 0.586811 * g + 0.114350 * b);
+  if (!clip) {
+    *red = QR * (r + m); *green = QR * (g + m); *blue = QR * (b + m);
+    return;
+  }
+  z = 1.0;
+  if (m < 0.0) { z = luma / (luma - m); m = 0.0; }
+  else if (m + c > 1.0) { z = (1.0 - luma) / (m + c - luma); m = 1.0 - z * c; }
+  *red = QR * (z * r + m); *green = QR * (z * g + m); *blue = QR * (z * b + m);
+}
+
+static void rgb_to_hsb(double red, double green, double blue, double *hue, double *saturation, double *brightness)
+{ /* colorspace-private.h:867-907 */
+  double delta, max, min;
+  *hue = 0.0; *saturation = 0.0; *brightness = 0.0;
+  min = red < green ? red : green;
+  if (blue < min) min = blue;
+  max = red > green ? red : green;
+  if (blue > max) max = blue;
+  if (fabs(max) < EPS) return;
+  delta = max - min;
+  *saturation = delta / max;
+  *brightness = QS * max;
+  if (fabs(delta) < EPS) return;
+  if (fabs(red - max) < EPS) *hue = (green - blue) / delta;
+  else if (fabs(green - max) < EPS) *hue = 2.0 + (blue - red) / delta;
+  else *hue = 4.0 + (red - green) / delta;
+  *hue /= 6.0;
+  if (*hue < 0.0) *hue += 1.0;
+}
+
+static void hsb_to_rgb(double hue, double saturation, double brightness, double *red, double *green, double *blue)
+{ /* colorspace-private.h:292-366 */
+  double f, h, p, q, t;
+  if (fabs(saturation) < EPS) {
+    *red = QR * brightness; *green = (*red); *blue = (*red);
+    return;
+  }
+  h = 6.0 * (hue - floor(hue));
+  f = h - floor((double) h);
+  p = brightness * (1.0 - saturation);
+  q = brightness * (1.0 - saturation * f);
+  t = brightness * (1.0 - (saturation * (1.0 - f)));
+  switch ((int) h) {
+    case 0: default: *red = QR * brightness; *green = QR * t; *blue = QR * p; break;
+    case 1: *red = QR * q; *green = QR * brightness; *blue = QR * p; break;
+    case 2: *red = QR * p; *green = QR * brightness; *blue = QR * t; break;
+    case 3: *red = QR * p; *green = QR * q; *blue = QR * brightness; break;
+    case 4: *red = QR * t; *green = QR * p; *blue = QR * brightness; break;
+    case 5: *red = QR * brightness; *green = QR * p; *blue = QR * q; break;
+  }
+}
+
+static void rgb_to_hsi(double red, double green, double blue, double *hue, double *saturation, double *intensity)
+{ /* colorspace-private.h:909-936 */
+  double alpha, beta;
+  *intensity = (QS * red + QS * green + QS * blue) / 3.0;
+  if (*intensity <= 0.0) { *hue = 0.0; *saturation = 0.0; return; }
+  *saturation = 1.0 - ORC_MIN(QS * red, ORC_MIN(QS * green, QS * blue)) / (*intensity);
+  alpha = 0.5 * (2.0 * QS * red - QS * green - QS * blue);
+  beta = 0.8660254037844385 * (QS * green - QS * blue);
+  *hue = atan2(beta, alpha) * (180.0 / PI_) / 360.0;
+  if (*hue < 0.0) *hue += 1.0;
+}
+
+static void hsi_to_rgb(double hue, double saturation, double intensity, double *red, double *green, double *blue)
+{ /* colorspace-private.h:368-412 */
+  double b, g, h, r;
+  h = 360.0 * hue;
+  h -= 360.0 * floor(h / 360.0);
+  if (h < 120.0) {
+    b = intensity * (1.0 - saturation);
+    r = intensity * (1.0 + saturation * cos(h * (PI_ / 180.0)) / cos((60.0 - h) * (PI_ / 180.0)));
+    g = 3.0 * intensity - r - b;
+  } else if (h < 240.0) {
+    h -= 120.0;
+    r = intensity * (1.0 - saturation);
+    g = intensity * (1.0 + saturation * cos(h * (PI_ / 180.0)) / cos((60.0 - h) * (PI_ / 180.0)));
+    b = 3.0 * intensity - r - g;
+  } else {
+    h -= 240.0;
+    g = intensity * (1.0 - saturation);
+    b = intensity * (1.0 + saturation * cos(h * (PI_ / 180.0)) / cos((60.0 - h) * (PI_ / 180.0)));
+    r = 3.0 * intensity - g - b;
+  }
+  *red = QR * r; *green = QR * g; *blue = QR * b;
+}
+
+static void rgb_to_hsl_hsv(double red, double green, double blue, int hsv, double *hue, double *saturation, double *third)
+{ /* ConvertRGBToHSL colorspace.c:597-640, ConvertRGBToHSV colorspace-private.h:994-1033 */
+  double c, max, min;
+  max = ORC_MAX(QS * red, ORC_MAX(QS * green, QS * blue));
+  min = ORC_MIN(QS * red, ORC_MIN(QS * green, QS * blue));
+  c = max - min;
+  *third = hsv ? max : (max + min) / 2.0;
+  if (c <= 0.0) { *hue = 0.0; *saturation = 0.0; return; }
+  if (fabs(max - QS * red) < EPS) {
+    *hue = (QS * green - QS * blue) / c;
+    if ((QS * green) < (QS * blue)) *hue += 6.0;
+  } else if (fabs(max - QS * green) < EPS) *hue = 2.0 + (QS * blue - QS * red) / c;
+  else *hue = 4.0 + (QS * red - QS * green) / c;
+  *hue *= 60.0 / 360.0;
+  if (hsv) *saturation = c * precip(max);
+  else if (*third <= 0.5) *saturation = c * precip(2.0 * (*third));
+  else *saturation = c * precip(2.0 - 2.0 * (*third));
+}
+
+static void hsl_hsv_to_rgb(double hue, double saturation, double third, int hsv, double *red, double *green, double *blue)
+{ /* ConvertHSLToRGB colorspace.c:307-385, ConvertHSVToRGB colorspace-private.h:414-481 */
+  double c, h, min, x;
+  h = hue * 360.0;
+  if (hsv) { c = third * saturation; min = third - c; }
+  else {
+    if (third <= 0.5) c = 2.0 * third * saturation;
+    else c = (2.0 - 2.0 * third) * saturation;
+    min = third - 0.5 * c;
+  }
+  h -= 360.0 * floor(h / 360.0);
+  h /= 60.0;
+  x = c * (1.0 - fabs(h - 2.0 * floor(h / 2.0) - 1.0));
+  switch ((int) floor(h)) {
+    case 0: default: *red = QR * (min + c); *green = QR * (min + x); *blue = QR * min; break;
+    case 1: *red = QR * (min + x); *green = QR * (min + c); *blue = QR * min; break;
+    case 2: *red = QR * min; *green = QR * (min + c); *blue = QR * (min + x); break;
+    case 3: *red = QR * min; *green = QR * (min + x); *blue = QR * (min + c); break;
+    case 4: *red = QR * (min + x); *green = QR * min; *blue = QR * (min + c); break;
+    case 5: *red = QR * (min + c); *green = QR * min; *blue = QR * (min + x); break;
+  }
+}
+
+static void rgb_to_hwb(double red, double green, double blue, double *hue, double *whiteness, double *blackness)
+{ /* colorspace-private.h:1035-1064 */
+  double f, p, v, w;
+  w = ORC_MIN(red, ORC_MIN(green, blue));
+  v = ORC_MAX(red, ORC_MAX(green, blue));
+  *blackness = 1.0 - QS * v;
+  *whiteness = QS * w;
+  if (fabs(v - w) < EPS) { *hue = (-1.0); return; }
+  f = (fabs(red - w) < EPS) ? green - blue : ((fabs(green - w) < EPS) ? blue - red : red - green);
+  p = (fabs(red - w) < EPS) ? 3.0 : ((fabs(green - w) < EPS) ? 5.0 : 1.0);
+  *hue = (p - f / (v - 1.0 * w)) / 6.0;
+}
+
+static void hwb_to_rgb(double hue, double whiteness, double blackness, double *red, double *green, double *blue)
+{ /* colorspace-private.h:483-529; CastDoubleToLong image-private.h:67 (NaN -> 0, saturating) */
+  double b, f, g, n, r, v, fl;
+  long i;
+  v = 1.0 - blackness;
+  if (fabs(hue - (-1.0)) < EPS) { *red = QR * v; *green = QR * v; *blue = QR * v; return; }
+  fl = floor(6.0 * hue);
+  if (fl != fl) i = 0;
+  else if (fl < -9223372036854775808.0) i = (-9223372036854775807L - 1);
+  else if (fl > 9223372036854775807.0) i = 9223372036854775807L;
+  else i = (long) fl;
+  f = 6.0 * hue - i;
+  if ((i & 0x01) != 0) f = 1.0 - f;
+  n = whiteness + f * (v - whiteness);
+  switch (i) {
+    case 0: default: r = v; g = n; b = whiteness; break;
+    case 1: r = n; g = v; b = whiteness; break;
+    case 2: r = whiteness; g = v; b = n; break;
+    case 3: r = whiteness; g = n; b = v; break;
+    case 4: r = n; g = whiteness; b = v; break;
+    case 5: r = v; g = whiteness; b = n; break;
+  }
+  *red = QR * r; *green = QR * g; *blue = QR * b;
+}
+
+static int is_hexcone_space(int cs)
+{
+  return cs == ORC_CS_HCL || cs == ORC_CS_HCLP || cs == ORC_CS_HSB || cs == ORC_CS_HSI || cs == ORC_CS_HSL ||
+         cs == ORC_CS_HSV || cs == ORC_CS_HWB;
+}
+
+/* one leg: sRGB -> `cs` (forward != 0, colorspace.c:1038-1043) or `cs` -> sRGB (:2373-2379) */
+static int colorspace_hexcone_leg(float *buf, long n, int ch, int cs, int forward)
+{
+  long i;
+  if (!is_hexcone_space(cs)) return -1;
+#pragma omp parallel for schedule(static)
+  for (i = 0; i < n; i++) {
+    float *q = buf + (size_t) i * ch;
+    double X, Y, Z;
+    if (forward) {
+      const double R = (double) q[0], G = (double) q[1], B = (double) q[2];
+      switch (cs) {
+        case ORC_CS_HCL: case ORC_CS_HCLP: rgb_to_hcl(R, G, B, &X, &Y, &Z); break;
+        case ORC_CS_HSB: rgb_to_hsb(R, G, B, &X, &Y, &Z); break;
+        case ORC_CS_HSI: rgb_to_hsi(R, G, B, &X, &Y, &Z); break;
+        case ORC_CS_HSL: rgb_to_hsl_hsv(R, G, B, 0, &X, &Y, &Z); break;
+        case ORC_CS_HSV: rgb_to_hsl_hsv(R, G, B, 1, &X, &Y, &Z); break;
+        default: rgb_to_hwb(R, G, B, &X, &Y, &Z); break;
+      }
+      q[0] = (float) (QR * X); q[1] = (float) (QR * Y); q[2] = (float) (QR * Z);
+    } else {
+      const double a = QS * q[0], b = QS * q[1], c = QS * q[2];
+      switch (cs) {
+        case ORC_CS_HCL: hcl_to_rgb(a, b, c, 0, &X, &Y, &Z); break;
+        case ORC_CS_HCLP: hcl_to_rgb(a, b, c, 1, &X, &Y, &Z); break;
+        case ORC_CS_HSB: hsb_to_rgb(a, b, c, &X, &Y, &Z); break;
+        case ORC_CS_HSI: hsi_to_rgb(a, b, c, &X, &Y, &Z); break;
+        case ORC_CS_HSL: hsl_hsv_to_rgb(a, b, c, 0, &X, &Y, &Z); break;
+        case ORC_CS_HSV: hsl_hsv_to_rgb(a, b, c, 1, &X, &Y, &Z); break;
+        default: hwb_to_rgb(a, b, c, &X, &Y, &Z); break;
+      }
+      q[0] = (float) X; q[1] = (float) Y; q[2] = (float) Z;
+    }
+  }
+  return 0;
+}
+
 /* colorspace.c:1751-1783 TransformImageColorspace: anything that is not sRGB goes back to sRGB
    first (TransformsRGBImage), then forward (sRGBTransformImage). */
 int orc_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to)
@@ -1297,10 +1544,12 @@ int orc_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to)
   if (is_core_space(from) && is_core_space(to)) return colorspace_core(buf, w, h, ch, from, to);
   if (from != ORC_CS_SRGB) {
     rc = is_core_space(from) ? colorspace_core(buf, w, h, ch, from, ORC_CS_SRGB)
-                             : colorspace_matrix_leg(buf, n, ch, from, 0);
+         : is_hexcone_space(from) ? colorspace_hexcone_leg(buf, n, ch, from, 0)
+                                  : colorspace_matrix_leg(buf, n, ch, from, 0);
     if (rc) return rc;
   }
   if (to == ORC_CS_SRGB) return 0;
+  if (is_hexcone_space(to)) return colorspace_hexcone_leg(buf, n, ch, to, 1);
   return is_core_space(to) ? colorspace_core(buf, w, h, ch, ORC_CS_SRGB, to) : colorspace_matrix_leg(buf, n, ch, to, 1);
 }
 

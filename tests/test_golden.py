@@ -169,7 +169,7 @@ def run_cuda(im, src, name, clamp_src):
 def test_cuda_path_matches_reference_golden(tag):
     """The product (through the C-ABI) against the REAL reference's outputs: bit exact for erode/dilate, the
     difference methods and the threshold operators, <= 1 ULP for convolution / resize / colourspace
-    (UnsharpMask: 2, its point pass amplifies the blur's 1 ULP by the gain)."""
+    (UnsharpMask included: its point pass runs on the float-rounded blur like the reference's)."""
     im = pytest.importorskip("imagemagick_b200")
     src = np.ascontiguousarray(G[tag + "/src"])
     clamp_src = np.ascontiguousarray(G[tag + "/clamp_src"])
@@ -177,4 +177,58 @@ def test_cuda_path_matches_reference_golden(tag):
         got, bar = run_cuda(im, src, key.split("/", 1)[1], clamp_src)
         want = G[key]
         assert got.shape == want.shape, key
+        assert util.max_ulp(got, want) <= bar, (key, util.max_ulp(got, want))
+
+
+# ---- second golden file: operators added late in round 2 (tests/golden/make_golden_r02b.py) ----------------------
+G2 = np.load(Path(__file__).resolve().parent / "golden" / "r02b_golden.npz")
+FILTERS2 = {"jinc": 13, "kaiser": 16}
+HEXCONE2 = {"hcl": 4, "hclp": 5, "hsb": 6, "hsi": 7, "hsl": 8, "hsv": 9, "hwb": 10, "srgb": 23}
+
+
+def _r02b_cases(tag):
+    return [k for k in G2.files if k.startswith(tag + "/") and not k.endswith("/src")]
+
+
+@pytest.mark.parametrize("tag", ["c3", "c4"])
+def test_oracle_matches_reference_golden_r02b(tag):
+    """Jinc / Kaiser ResizeImage and the hue / saturation colourspaces: the oracle against arrays the real reference
+    produced (bit exact)."""
+    o = oracle()
+    src = np.ascontiguousarray(G2[tag + "/src"])
+    h, w, ch = src.shape
+    for key in _r02b_cases(tag):
+        name = key.split("/", 1)[1]
+        want = G2[key]
+        if name.startswith("resize_"):
+            _, f, size = name.split("_")
+            ow, oh = map(int, size.split("x"))
+            got = np.empty((oh, ow, ch), np.float32)
+            assert o.orc_resize(P(src), w, h, ch, P(got), ow, oh, FILTERS2[f]) == 0
+        else:
+            _, a, b = name.split("_")
+            got = src.copy()
+            assert o.orc_colorspace(P(got), w, h, ch, HEXCONE2[a], HEXCONE2[b]) == 0
+        assert util.max_ulp(got, want) == 0, key
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["c3", "c4"])
+def test_cuda_path_matches_reference_golden_r02b(tag):
+    im = pytest.importorskip("imagemagick_b200")
+    import torch
+    src = np.ascontiguousarray(G2[tag + "/src"])
+    for key in _r02b_cases(tag):
+        name = key.split("/", 1)[1]
+        want = G2[key]
+        img = im.Image(torch.from_numpy(src.copy()).cuda())
+        if name.startswith("resize_"):
+            _, f, size = name.split("_")
+            ow, oh = map(int, size.split("x"))
+            got, bar = im.ResizeImage(img, ow, oh, FILTERS2[f]).pixels.cpu().numpy(), 1
+        else:
+            _, a, b = name.split("_")
+            img.colorspace = HEXCONE2[a]
+            im.TransformImageColorspace(img, HEXCONE2[b])
+            got, bar = img.pixels.cpu().numpy(), (1 if "hsi" in name else 0)
         assert util.max_ulp(got, want) <= bar, (key, util.max_ulp(got, want))

@@ -320,6 +320,48 @@ def test_resize_all_filters(filt):
         assert max_ulp(got, want) <= 1, (filt, ow, oh)
 
 
+HEXCONE = [4, 5, 6, 7, 8, 9, 10]      # HCL, HCLp, HSB, HSI, HSL, HSV, HWB
+
+
+def _hexcone_image(w, h, ch, kind, seed):
+    src = make_image(w, h, ch, seed=seed, kind=kind)
+    special = np.array([[0, 0, 0], [65535, 65535, 65535], [32768, 32768, 32768], [65535, 0, 0], [0, 65535, 0],
+                        [0, 0, 65535], [65535, 65535, 0], [0, 65535, 65535], [65535, 0, 65535], [40000, 40000, 100],
+                        [100, 40000, 40000], [40000, 100, 40000], [1, 0, 0], [65535, 65534, 65535], [10922.5, 0, 0],
+                        [21845, 30000, 30000], [43690, 65535, 65535], [54612.5, 20000, 50000], [0, 65535, 32767.5],
+                        [16383.75, 65535, 65535], [65535, 32768, 16384]], np.float32)
+    src[0, :len(special), :3] = special
+    return src
+
+
+@pytest.mark.parametrize("cs", HEXCONE)
+@pytest.mark.parametrize("kind", ["noise", "hdr"])
+def test_hexcone_colorspaces(cs, kind):
+    """HCL / HCLp / HSB / HSL / HSV / HWB are piecewise (sector of the hue, gray and black branches): every operation is
+    the reference's unfused double operation => bit exact in both directions, including a hop between two of them.
+    HSI takes atan2 / cos from the CUDA math library: <= 1 ULP."""
+    bar = 1 if cs == 7 else 0
+    for ch in (3, 4):
+        src = _hexcone_image(131, 67, ch, kind, seed=90 + cs)
+        for frm, to in ((23, cs), (cs, 23), (cs, 8 if cs != 8 else 9)):
+            want = src.copy()
+            assert oracle().orc_colorspace(P(want), 131, 67, ch, frm, to) == 0
+            img = _dev(src.copy())
+            img.colorspace = frm
+            assert im.TransformImageColorspace(img, to) is True and img.colorspace == to
+            got = _host(img)
+            assert np.array_equal(np.isnan(got), np.isnan(want)), (ch, frm, to)
+            ok = ~np.isnan(want)
+            assert max_ulp(np.where(ok, got, np.float32(0)), np.where(ok, want, np.float32(0))) <= bar, (ch, frm, to)
+            if ch == 4:
+                assert np.array_equal(got[..., 3], src[..., 3])                 # alpha is not part of the transform
+    h = im.Image(_hexcone_image(33, 21, 4, kind, seed=3))                       # host-buffer entry point
+    want = h.pixels.copy()
+    assert oracle().orc_colorspace(P(want), 33, 21, 4, 23, cs) == 0
+    im.TransformImageColorspace(h, cs)
+    assert max_ulp(h.pixels, want) <= bar
+
+
 def test_resize_lanczos_2x_down_2048():
     """configs[2] at 1/8 scale: Lanczos 2x downscale, 1-ULP check against the CPU result."""
     src = make_image(2048, 2048, 4, seed=42)

@@ -152,6 +152,37 @@ def test_colorspace_bit_exact(frm, to):
     assert max_ulp(a, b) == 0
 
 
+def hexcone_image(kind):
+    """Noise plus the pixels the hexcone formulae branch on: grays, black, white, primaries, two-way ties of the
+    maximum / minimum, hues on the sector boundaries."""
+    src = make_image(64, 48, 4, seed=8, kind=kind)
+    special = np.array([[0, 0, 0], [65535, 65535, 65535], [32768, 32768, 32768], [65535, 0, 0], [0, 65535, 0],
+                        [0, 0, 65535], [65535, 65535, 0], [0, 65535, 65535], [65535, 0, 65535], [40000, 40000, 100],
+                        [100, 40000, 40000], [40000, 100, 40000], [1, 0, 0], [65535, 65534, 65535], [10922.5, 0, 0],
+                        [21845, 30000, 30000], [43690, 65535, 65535], [54612.5, 20000, 50000], [0, 65535, 32767.5],
+                        [16383.75, 65535, 65535], [65535, 32768, 16384]], np.float32)
+    src[0, :len(special), :3] = special
+    return src
+
+
+HEXCONE = [4, 5, 6, 7, 8, 9, 10]      # HCL, HCLp, HSB, HSI, HSL, HSV, HWB (colorspace.h:27-67)
+
+
+@pytest.mark.parametrize("cs", HEXCONE)
+@pytest.mark.parametrize("kind", ["noise", "hdr"])
+def test_hexcone_colorspaces_bit_exact(cs, kind):
+    """colorspace.c:958-1054 / :2296-2390 with the gem-style conversions of colorspace-private.h: forward from sRGB,
+    inverse from arbitrary component values, and a hop between two hexcone spaces (through sRGB, :1773)."""
+    src = hexcone_image(kind)
+    for frm, to in ((23, cs), (cs, 23), (cs, 8 if cs != 8 else 9)):
+        a, b = src.copy(), src.copy()
+        assert util.ref().ref_colorspace(P(a), 64, 48, 4, frm, to) == 0
+        assert oracle().orc_colorspace(P(b), 64, 48, 4, frm, to) == 0
+        assert np.array_equal(np.isnan(a), np.isnan(b)), (frm, to)
+        ok = ~np.isnan(a)
+        assert max_ulp(np.where(ok, a, np.float32(0)), np.where(ok, b, np.float32(0))) == 0, (frm, to)
+
+
 @pytest.mark.parametrize("kind", ["alpha_blocks", "hdr"])
 def test_difference_methods_bit_exact_on_awkward_pixels(kind):
     """EdgeIn/EdgeOut/Edge/TopHat/BottomHat end in CompositeImage(Difference) (morphology.c:3995-4012):
