@@ -291,8 +291,27 @@ def run_gpu(args):
             step_eager()                                   # warm the side stream's allocator state
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        branches = [torch.cuda.Stream(device=dev) for _ in range(max(0, args.streams - 1))]
         with torch.cuda.graph(graph, stream=side):
-            graph_out = step_eager()
+            if not branches:
+                graph_out = step_eager()
+            else:
+                # independent images on separate streams: the FP64-bound blur of one image and the HBM-bound resize of
+                # another may share the SMs, and a kernel's last partial wave overlaps the next kernel's first
+                lanes = [side] + branches
+                for b_ in branches:
+                    b_.wait_stream(side)
+                outs = [None] * len(lanes)
+                for k, image in enumerate(batch):
+                    lane = k % len(lanes)
+                    with torch.cuda.stream(lanes[lane]):
+                        outs[lane] = one_image(image)
+                for b_ in branches:
+                    side.wait_stream(b_)
+                graph_out = outs[(len(batch) - 1) % len(lanes)]
+        if branches:
+            timing_mode = ("cuda graph of one step (batch of %d images on %d image-parallel streams), replayed K times"
+                           % (IMAGES, len(branches) + 1))
         graph.replay()
         torch.cuda.synchronize()
         assert np.array_equal(graph_out.pixels.reshape(-1)[:64].cpu().numpy(), check), "graph replay differs"
@@ -623,6 +642,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("BENCH_STREAMS", "1")),
+                    help="image-parallel branches of the timed step's CUDA graph (independent images on separate streams)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
