@@ -40,6 +40,9 @@ from ._lib import KernelPtr, MagickB200Error, check
 UndefinedMorphology, ConvolveMorphology, CorrelateMorphology, ErodeMorphology, DilateMorphology = 0, 1, 2, 3, 4
 OpenMorphology, CloseMorphology, SmoothMorphology = 8, 9, 12
 EdgeInMorphology, EdgeOutMorphology, EdgeMorphology, TopHatMorphology, BottomHatMorphology = 13, 14, 15, 16, 17
+ErodeIntensityMorphology, DilateIntensityMorphology, IterativeDistanceMorphology = 5, 6, 7
+OpenIntensityMorphology, CloseIntensityMorphology = 10, 11
+HitAndMissMorphology, ThinningMorphology, ThickenMorphology = 18, 19, 20
 
 # MagickCore/resample.h:32-69
 (UndefinedFilter, PointFilter, BoxFilter, TriangleFilter, HermiteFilter, HannFilter, HammingFilter,

@@ -117,11 +117,14 @@ int primitive(const float *src, float *dst, size_t w, size_t h, int ch, int meth
   std::vector<double> win(n);
   int ox, oy;
   bool has_nan = false;
-  if (method == MB200_ConvolveMorphology || method == MB200_DilateMorphology) {   // reflected, :2612-2626
+  if (method == MB200_ConvolveMorphology || method == MB200_DilateMorphology || method == MB200_DilateIntensityMorphology ||
+      method == MB200_IterativeDistanceMorphology) {                              // reflected, :2612-2626
     for (size_t i = 0; i < n; ++i) win[i] = k->values[n - 1 - i];
     ox = kw - static_cast<int>(k->x) - 1;
     oy = kh - static_cast<int>(k->y) - 1;
-  } else if (method == MB200_ErodeMorphology) {
+  } else if (method == MB200_ErodeMorphology || method == MB200_ErodeIntensityMorphology ||
+             method == MB200_HitAndMissMorphology || method == MB200_ThinningMorphology ||
+             method == MB200_ThickenMorphology) {
     for (size_t i = 0; i < n; ++i) win[i] = k->values[i];
     ox = static_cast<int>(k->x);
     oy = static_cast<int>(k->y);
@@ -207,6 +210,61 @@ mb200_kernel_info *reflected_clone(const mb200_kernel_info *kernel) {
 
 struct Stage { int primitive; const mb200_kernel_info *kernel; };
 
+// HitAndMiss / Thinning / Thicken (morphology.c:3722-3729): `iterations` repeats the WHOLE method (every kernel of the list
+// once per round) while anything changes.  Thinning / Thicken re-iterate: each kernel works on the previous kernel's
+// result.  HitAndMiss unites the kernels' results with LightenCompositeOp (:4016-4052): the first result is kept, every
+// further one -- computed from the ORIGINAL image -- is composited onto it; a one-kernel list iterates on its own result.
+int apply_hit_and_miss_family(const float *src, float *dst, size_t w, size_t h, int ch, int method, long iterations,
+                              const mb200_kernel_info *kernel, cudaStream_t s) {
+  const size_t method_limit = iterations < 0 ? (w > h ? w : h) : static_cast<size_t>(iterations);
+  const bool unite = method == MB200_HitAndMissMorphology && kernel->next != nullptr;
+  const size_t bytes = w * h * static_cast<size_t>(ch) * sizeof(float), npix = w * h;
+  StreamAlloc a(s), b(s), united(s), counter(s);
+  int rc = a.alloc(bytes);
+  if (!rc) rc = b.alloc(bytes);
+  if (!rc && unite) rc = united.alloc(bytes);
+  if (!rc) rc = counter.alloc(sizeof(unsigned long long));
+  if (rc) return rc;
+  float *bufs[2] = {static_cast<float *>(a.ptr), static_cast<float *>(b.ptr)};
+  unsigned long long *d_counter = static_cast<unsigned long long *>(counter.ptr);
+  const float *cur = src;
+  int next = 0;
+  bool have_united = false;
+  size_t round = 0;
+  long long round_changed = 1;
+  while (round < method_limit && round_changed > 0) {
+    ++round;
+    round_changed = 0;
+    for (const mb200_kernel_info *k = kernel; k; k = k->next) {
+      const bool count = method_limit > 1;                   // the count only decides whether another round runs
+      if (count) cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), s);
+      rc = primitive(cur, bufs[next], w, h, ch, method, k, 0.0, count ? d_counter : nullptr, s);
+      if (rc) return rc;
+      if (count) {
+        long long changed = 0;
+        rc = read_changed(d_counter, ch, &changed, s);
+        if (rc) return rc;
+        round_changed += changed;
+      }
+      cur = bufs[next];
+      next ^= 1;
+      if (unite) {
+        if (!have_united) {
+          const cudaError_t e = cudaMemcpyAsync(united.ptr, cur, bytes, cudaMemcpyDeviceToDevice, s);
+          if (e != cudaSuccess) return cuda_fail(e, "hit-and-miss: first result");
+          have_united = true;
+        } else {
+          rc = launch_composite_lighten(static_cast<float *>(united.ptr), cur, npix, ch, s);
+          if (rc) return rc;
+        }
+        cur = src;
+      }
+    }
+  }
+  const cudaError_t e = cudaMemcpyAsync(dst, unite ? united.ptr : cur, bytes, cudaMemcpyDeviceToDevice, s);
+  return e == cudaSuccess ? MB200_OK : cuda_fail(e, "hit-and-miss: result copy");
+}
+
 int morphology_apply(const float *src, float *dst, size_t w, size_t h, int ch, int method, long iterations,
                      const mb200_kernel_info *kernel, double bias, cudaStream_t s,
                      const UnsharpEpilogue *epilogue = nullptr, bool *epilogue_fused = nullptr) {
@@ -234,19 +292,25 @@ int morphology_apply(const float *src, float *dst, size_t w, size_t h, int ch, i
     return rc;
   }
   if (iterations == 0) return fail(MB200_EINVAL, "iterations == 0 is a null operation (reference returns NULL)");
+  if (method == MB200_HitAndMissMorphology || method == MB200_ThinningMorphology || method == MB200_ThickenMorphology)
+    return apply_hit_and_miss_family(src, dst, w, h, ch, method, iterations, kernel, s);
   size_t kernel_limit = iterations < 0 ? (w > h ? w : h) : static_cast<size_t>(iterations);
   int stage_limit = 1;
   switch (method) {
     case MB200_SmoothMorphology: stage_limit = 4; break;
-    case MB200_OpenMorphology: case MB200_CloseMorphology: stage_limit = 2; break;
+    case MB200_OpenMorphology: case MB200_CloseMorphology:
+    case MB200_OpenIntensityMorphology: case MB200_CloseIntensityMorphology: stage_limit = 2; break;
     case MB200_ConvolveMorphology: case MB200_CorrelateMorphology:
-    case MB200_ErodeMorphology: case MB200_DilateMorphology: break;
+    case MB200_ErodeMorphology: case MB200_DilateMorphology:
+    case MB200_ErodeIntensityMorphology: case MB200_DilateIntensityMorphology:
+    case MB200_IterativeDistanceMorphology: break;
     default:
-      return fail(MB200_EUNSUPPORTED, "morphology method %d is a sequential / intensity primitive; "
-                  "not on the GPU path", method);
+      return fail(MB200_EUNSUPPORTED, "morphology method %d (Distance / Voronoi: sequential two-pass primitives) is not on "
+                  "the GPU path", method);
   }
   mb200_kernel_info *reflected = nullptr;
-  if (method == MB200_CorrelateMorphology || method == MB200_CloseMorphology || method == MB200_SmoothMorphology) {
+  if (method == MB200_CorrelateMorphology || method == MB200_CloseMorphology || method == MB200_SmoothMorphology ||
+      method == MB200_CloseIntensityMorphology) {
     reflected = reflected_clone(kernel);
     if (!reflected) return fail(MB200_ENOMEM, "kernel clone failed");
   }
@@ -258,6 +322,13 @@ int morphology_apply(const float *src, float *dst, size_t w, size_t h, int ch, i
       switch (method) {
         case MB200_OpenMorphology: st.primitive = stage == 2 ? MB200_DilateMorphology : MB200_ErodeMorphology; break;
         case MB200_CloseMorphology: st.kernel = rk; st.primitive = stage == 2 ? MB200_ErodeMorphology : MB200_DilateMorphology; break;
+        case MB200_OpenIntensityMorphology:
+          st.primitive = stage == 2 ? MB200_DilateIntensityMorphology : MB200_ErodeIntensityMorphology;
+          break;
+        case MB200_CloseIntensityMorphology:
+          st.kernel = rk;
+          st.primitive = stage == 2 ? MB200_ErodeIntensityMorphology : MB200_DilateIntensityMorphology;
+          break;
         case MB200_SmoothMorphology:
           if (stage == 1) st.primitive = MB200_ErodeMorphology;
           else if (stage == 2) st.primitive = MB200_DilateMorphology;

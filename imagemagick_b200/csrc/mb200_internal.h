@@ -128,6 +128,8 @@ int launch_resize_copy_channels(float *dst, const float *src, size_t w, size_t o
 
 // CompositeImage(canvas, source, DifferenceCompositeOp) for same-size images (Edge/TopHat/BottomHat), in place on canvas
 int launch_composite_difference(float *canvas, const float *source, size_t npixels, int channels, void *stream);
+// ... LightenCompositeOp: the union of the results of a HitAndMiss kernel list (morphology.c:3722, :4044-4046)
+int launch_composite_lighten(float *canvas, const float *source, size_t npixels, int channels, void *stream);
 
 // MotionBlurImage (effect.c:2347): taps + integer offsets from the host, gather along the blur direction
 int launch_motion_blur(const float *src, float *dst, size_t w, size_t h, int channels, const double *taps, const long *ox,

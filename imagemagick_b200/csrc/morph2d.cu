@@ -110,6 +110,81 @@ __global__ void __launch_bounds__(kTileW *kTileH) morph2d_kernel(const Morph2dAr
         nchanged += fabs(pixel - static_cast<double>(centre[c])) >= kEpsilon;
       }
     }
+  } else if (a.method == MB200_HitAndMissMorphology || a.method == MB200_ThinningMorphology ||
+             a.method == MB200_ThickenMorphology) {
+    // morphology.c:3037-3083: least foreground sample (cells > 0.7) minus greatest background sample (cells < 0.3), never
+    // negative; Thinning / Thicken subtract it from / add it to the centre.  The host keeps foreground and background
+    // cells only (k = 1 / 0).  Selections of floats, one double subtraction / addition, one rounding: bit exact.
+    float lo[CH], hi[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { lo[c] = 65535.0f; hi[c] = 0.0f; }
+    for (int i = 0; i < a.ncells; ++i) {
+      const Cell cell = a.cells[i];
+      const float *p = win + (cell.dv * tw + cell.du) * CH;
+      const bool fg = cell.k > 0.5;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const float v = p[c];
+        if (fg) { if (v < lo[c]) lo[c] = v; }
+        else { if (v > hi[c]) hi[c] = v; }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      double m = __dsub_rn(static_cast<double>(lo[c]), static_cast<double>(hi[c]));
+      if (m < 0.0) m = 0.0;
+      const double centre_v = static_cast<double>(centre[c]);
+      double pixel = m;
+      if (a.method == MB200_ThinningMorphology) pixel = __dsub_rn(centre_v, m);
+      else if (a.method == MB200_ThickenMorphology) pixel = __dadd_rn(centre_v, m);
+      out[c] = static_cast<float>(pixel);
+      nchanged += fabs(__dsub_rn(pixel, centre_v)) >= kEpsilon;
+    }
+  } else if (a.method == MB200_ErodeIntensityMorphology || a.method == MB200_DilateIntensityMorphology) {
+    // :3084-3137: the whole pixel of least / greatest intensity (pixel.c:2356, Rec709 luma of an sRGB / gray image,
+    // three products summed left to right without contraction), first one in scan order; when no cell qualifies the
+    // reference stores 0 (Erode) or the centre (Dilate) and counts the change.  Copied pixels are not counted (:3186).
+    const bool erode = a.method == MB200_ErodeIntensityMorphology;
+    double best = erode ? 65535.0 : 0.0;
+    const float *pick = nullptr;
+    for (int i = 0; i < a.ncells; ++i) {
+      const Cell cell = a.cells[i];
+      const float *p = win + (cell.dv * tw + cell.du) * CH;
+      double intensity = static_cast<double>(p[0]);         // one channel: the gray value itself (pixel.c:2366)
+      if (CH >= 2) {                                        // gray + alpha evaluates the same expression on (g, g, g)
+        const double green = static_cast<double>(p[CH >= 3 ? 1 : 0]), blue = static_cast<double>(p[CH >= 3 ? 2 : 0]);
+        intensity = __dadd_rn(__dadd_rn(__dmul_rn(0.212656, intensity), __dmul_rn(0.715158, green)), __dmul_rn(0.072186, blue));
+      }
+      if (erode ? intensity < best : intensity > best) { best = intensity; pick = p; }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      if (pick != nullptr) out[c] = pick[c];
+      else {
+        const float v = erode ? 0.0f : centre[c];
+        out[c] = v;
+        nchanged += fabs(static_cast<double>(v) - static_cast<double>(centre[c])) >= kEpsilon;
+      }
+    }
+  } else if (a.method == MB200_IterativeDistanceMorphology) {
+    // :3138-3181: min over the cells of sample + k (reflected kernel), starting from the centre
+    double pix[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) pix[c] = static_cast<double>(centre[c]);
+    for (int i = 0; i < a.ncells; ++i) {
+      const Cell cell = a.cells[i];
+      const float *p = win + (cell.dv * tw + cell.du) * CH;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const double v = __dadd_rn(static_cast<double>(p[c]), cell.k);
+        if (v < pix[c]) pix[c] = v;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      out[c] = static_cast<float>(pix[c]);
+      nchanged += fabs(__dsub_rn(pix[c], static_cast<double>(centre[c]))) >= kEpsilon;
+    }
   } else {
     const bool dilate = a.method == MB200_DilateMorphology;
     float pix[CH];
@@ -389,7 +464,14 @@ int launch_morph2d(const float *src, float *dst, size_t width, size_t height, in
       if (k != k) continue;
       if (method == MB200_ErodeMorphology && !(k >= 0.5)) continue;
       if (method == MB200_DilateMorphology && !(k > 0.5)) continue;
-      host[n].du = static_cast<short>(u); host[n].dv = static_cast<short>(v); host[n].pad = 0.f; host[n].k = k;
+      if ((method == MB200_ErodeIntensityMorphology || method == MB200_DilateIntensityMorphology) && !(k >= 0.5)) continue;
+      double kept = k;
+      if (method == MB200_HitAndMissMorphology || method == MB200_ThinningMorphology || method == MB200_ThickenMorphology) {
+        if (k > 0.7) kept = 1.0;             // foreground
+        else if (k < 0.3) kept = 0.0;        // background
+        else continue;                       // don't care
+      }
+      host[n].du = static_cast<short>(u); host[n].dv = static_cast<short>(v); host[n].pad = 0.f; host[n].k = kept;
       ++n;
     }
   if (method == MB200_ConvolveMorphology && n == total &&
@@ -463,7 +545,7 @@ int launch_morph2d(const float *src, float *dst, size_t width, size_t height, in
   a.ox = ox; a.oy = oy; a.kw = kw; a.kh = kh; a.ncells = n;
   a.cells = static_cast<const Cell *>(d_cells);
   a.bias = bias; a.gamma_scale = gamma_scale; a.method = method; a.changed = d_changed;
-  if (method != MB200_ConvolveMorphology && n <= 1024 && kw <= kMmPitch - kMmTile + 1) {
+  if ((method == MB200_ErodeMorphology || method == MB200_DilateMorphology) && n <= 1024 && kw <= kMmPitch - kMmTile + 1) {
     const int th = kMmTile + kh - 1;
     const size_t msmem = static_cast<size_t>(kMmPitch) * th * channels * sizeof(float);
     if (msmem <= 160 * 1024) {

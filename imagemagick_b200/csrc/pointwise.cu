@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(256) threshold_kernel(float *__restrict__ buf,
 // operation order with unfused double arithmetic => bit exact.
 //   Sa, Da = QS*alpha (1 without alpha);  alpha = RoundToUnity(Sa+Da-Sa*Da);  gamma = PerceptibleReciprocal(alpha)
 //   colour: QR*gamma*(Sca+Dca-2*min(Sca*Da,Dca*Sa)), Sca = QS*Sa*Sc, Dca = QS*Da*Dc;  alpha: QR*|Sa-Da|;  ClampPixel.
-template <int CH>
+// OP 1 = LightenCompositeOp, the union MorphologyApply forms over a HitAndMiss kernel list (morphology.c:3722, :4044;
+// composite.c:3110-3124): colour (Sca*Da > Dca*Sa) ? QR*(Sca+Dca*(1-Sa)) : QR*(Dca+Sca*(1-Da)), alpha QR*alpha.
+template <int CH, int OP>
 __global__ void __launch_bounds__(256) difference_kernel(float *__restrict__ canvas, const float *__restrict__ source,
                                                          size_t npixels) {
   const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
@@ -119,12 +121,16 @@ __global__ void __launch_bounds__(256) difference_kernel(float *__restrict__ can
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
     double pixel;
-    if (kAlpha && c == CH - 1) pixel = __dmul_rn(kQR, fabs(__dsub_rn(Sa, Da)));
+    if (kAlpha && c == CH - 1) pixel = OP == 1 ? __dmul_rn(kQR, alpha) : __dmul_rn(kQR, fabs(__dsub_rn(Sa, Da)));
     else {
       const double Sca = __dmul_rn(__dmul_rn(kQS, Sa), static_cast<double>(p[c]));
       const double Dca = __dmul_rn(__dmul_rn(kQS, Da), static_cast<double>(q[c]));
       const double a = __dmul_rn(Sca, Da), b = __dmul_rn(Dca, Sa);
-      pixel = __dmul_rn(__dmul_rn(kQR, gamma), __dsub_rn(__dadd_rn(Sca, Dca), __dmul_rn(2.0, a < b ? a : b)));
+      if (OP == 1)
+        pixel = a > b ? __dmul_rn(kQR, __dadd_rn(Sca, __dmul_rn(Dca, __dsub_rn(1.0, Sa))))
+                      : __dmul_rn(kQR, __dadd_rn(Dca, __dmul_rn(Sca, __dsub_rn(1.0, Da))));
+      else
+        pixel = __dmul_rn(__dmul_rn(kQR, gamma), __dsub_rn(__dadd_rn(Sca, Dca), __dmul_rn(2.0, a < b ? a : b)));
     }
     out[c] = pixel < 0.0 ? 0.0f : (pixel >= kQR ? 65535.0f : static_cast<float>(pixel));
   }
@@ -277,20 +283,21 @@ int launch_sample(const float *src, size_t w, size_t h, int channels, float *dst
   return MB200_OK;
 }
 
-int launch_composite_difference(float *canvas, const float *source, size_t npixels, int channels, void *stream) {
+template <int OP>
+int launch_composite(float *canvas, const float *source, size_t npixels, int channels, void *stream) {
   if (npixels == 0) return MB200_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t blocks = (npixels + 255) / 256;
   if (blocks > 0x7fffffffull) return fail(MB200_EINVAL, "composite: image too large");
   const unsigned grid = static_cast<unsigned>(blocks);
   switch (channels) {
-    case 1: difference_kernel<1><<<grid, 256, 0, s>>>(canvas, source, npixels); break;
-    case 2: difference_kernel<2><<<grid, 256, 0, s>>>(canvas, source, npixels); break;
-    case 3: difference_kernel<3><<<grid, 256, 0, s>>>(canvas, source, npixels); break;
+    case 1: difference_kernel<1, OP><<<grid, 256, 0, s>>>(canvas, source, npixels); break;
+    case 2: difference_kernel<2, OP><<<grid, 256, 0, s>>>(canvas, source, npixels); break;
+    case 3: difference_kernel<3, OP><<<grid, 256, 0, s>>>(canvas, source, npixels); break;
     case 4:
       if (((reinterpret_cast<uintptr_t>(canvas) | reinterpret_cast<uintptr_t>(source)) & 15) != 0)
         return fail(MB200_EINVAL, "composite: RGBA buffers must be 16-byte aligned");
-      difference_kernel<4><<<grid, 256, 0, s>>>(canvas, source, npixels);
+      difference_kernel<4, OP><<<grid, 256, 0, s>>>(canvas, source, npixels);
       break;
     default: return fail(MB200_EINVAL, "composite: 1..4 channels");
   }
@@ -298,6 +305,13 @@ int launch_composite_difference(float *canvas, const float *source, size_t npixe
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "composite launch");
   return MB200_OK;
+}
+
+int launch_composite_difference(float *canvas, const float *source, size_t npixels, int channels, void *stream) {
+  return launch_composite<0>(canvas, source, npixels, channels, stream);
+}
+int launch_composite_lighten(float *canvas, const float *source, size_t npixels, int channels, void *stream) {
+  return launch_composite<1>(canvas, source, npixels, channels, stream);
 }
 
 int launch_threshold(float *buf, size_t npixels, int channels, int op, const double *thresholds, void *stream) {

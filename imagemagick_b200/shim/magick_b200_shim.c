@@ -278,7 +278,21 @@ Image *B200AccelerateMorphologyImage(const Image *image, const MorphologyMethod 
       if (has_artifact(image, compose_artifacts) != MagickFalse) return (Image *) NULL;
       allow_mask = 0;                        /* the composite step treats a channel selection on its own terms */
       break;
-    default: return (Image *) NULL;          /* sequential / intensity primitives: CPU */
+    case ErodeIntensityMorphology: case DilateIntensityMorphology: case OpenIntensityMorphology:
+    case CloseIntensityMorphology:           /* GetPixelIntensity (pixel.c:2356): the kernel implements the default Rec709 luma */
+      if (image->intensity != UndefinedPixelIntensityMethod && image->intensity != Rec709LumaPixelIntensityMethod)
+        return (Image *) NULL;
+      if (image->colorspace == RGBColorspace || image->colorspace == LinearGRAYColorspace) return (Image *) NULL;
+      allow_mask = 0;                        /* the intensity is taken from the masked-out channels as well */
+      break;
+    case IterativeDistanceMorphology: case ThinningMorphology: case ThickenMorphology: break;
+    case HitAndMissMorphology:               /* a kernel list is united with CompositeImage(Lighten), morphology.c:4044 */
+      if (kernel->next != (KernelInfo *) NULL) {
+        if (has_artifact(image, compose_artifacts) != MagickFalse) return (Image *) NULL;
+        allow_mask = 0;
+      }
+      break;
+    default: return (Image *) NULL;          /* Distance / Voronoi: sequential two-pass primitives stay on the CPU */
   }
   a.method = (int) method; a.iterations = (long) iterations; a.kernel = scaled != (KernelInfo *) NULL ? scaled : kernel;
   out = run_same_size_masked(image, op_morphology, &a, allow_mask, exception);

@@ -129,6 +129,18 @@ int main(void)
   CHECK("MorphologyImage Edge Disk:3 RGBA", 0, MorphologyImage(rgba, EdgeMorphology, 1, k, ex), CPU(__real_MorphologyImage(rgba, EdgeMorphology, 1, k, ex)));
   CHECK("MorphologyImage TopHat Disk:3 RGB", 0, MorphologyImage(rgb, TopHatMorphology, 1, k, ex), CPU(__real_MorphologyImage(rgb, TopHatMorphology, 1, k, ex)));
   k = DestroyKernelInfo(k);
+  k = AcquireKernelInfo("Corners", ex);
+  CHECK("MorphologyImage HitAndMiss Corners", 0, MorphologyImage(rgb, HitAndMissMorphology, 1, k, ex), CPU(__real_MorphologyImage(rgb, HitAndMissMorphology, 1, k, ex)));
+  k = DestroyKernelInfo(k);
+  k = AcquireKernelInfo("Skeleton", ex);
+  CHECK("MorphologyImage Thinning x3 Skeleton", 0, MorphologyImage(rgba, ThinningMorphology, 3, k, ex), CPU(__real_MorphologyImage(rgba, ThinningMorphology, 3, k, ex)));
+  k = DestroyKernelInfo(k);
+  k = AcquireKernelInfo("Disk:2", ex);
+  CHECK("MorphologyImage OpenIntensity Disk:2", 0, MorphologyImage(rgba, OpenIntensityMorphology, 1, k, ex), CPU(__real_MorphologyImage(rgba, OpenIntensityMorphology, 1, k, ex)));
+  k = DestroyKernelInfo(k);
+  k = AcquireKernelInfo("Euclidean:2", ex);
+  CHECK("MorphologyImage IterativeDistance x4", 0, MorphologyImage(rgb, IterativeDistanceMorphology, 4, k, ex), CPU(__real_MorphologyImage(rgb, IterativeDistanceMorphology, 4, k, ex)));
+  k = DestroyKernelInfo(k);
   a = CloneImage(rgba, 0, 0, MagickTrue, ex); b = CloneImage(rgba, 0, 0, MagickTrue, ex);
   if (TransformImageColorspace(a, LabColorspace, ex) == MagickFalse || a->colorspace != LabColorspace) failures++;
   B200ShimEnable(0); (void) __real_TransformImageColorspace(b, LabColorspace, ex); B200ShimEnable(1);

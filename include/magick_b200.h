@@ -54,14 +54,22 @@ typedef enum {
   MB200_CorrelateMorphology = 2,
   MB200_ErodeMorphology = 3,
   MB200_DilateMorphology = 4,
+  MB200_ErodeIntensityMorphology = 5,
+  MB200_DilateIntensityMorphology = 6,
+  MB200_IterativeDistanceMorphology = 7,
   MB200_OpenMorphology = 8,
   MB200_CloseMorphology = 9,
+  MB200_OpenIntensityMorphology = 10,
+  MB200_CloseIntensityMorphology = 11,
   MB200_SmoothMorphology = 12,
   MB200_EdgeInMorphology = 13,
   MB200_EdgeOutMorphology = 14,
   MB200_EdgeMorphology = 15,
   MB200_TopHatMorphology = 16,
-  MB200_BottomHatMorphology = 17
+  MB200_BottomHatMorphology = 17,
+  MB200_HitAndMissMorphology = 18,
+  MB200_ThinningMorphology = 19,
+  MB200_ThickenMorphology = 20
 } mb200_morphology_method;
 
 /* MagickCore/resample.h:32-69 FilterType -- same numeric values */

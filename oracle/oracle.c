@@ -288,6 +288,8 @@ static int kernel_reflect(const orc_kernel *in, orc_kernel *out)
 
 /* --------------------------------------------------------- MorphologyPrimitive */
 
+static double pixel_intensity(const float *q, int ch);      /* pixel.c:2356, below (threshold operators) */
+
 static int is_blend_channel(int ch, int i) { return (ch == 2 || ch == 4) && i != ch - 1; }
 static int update_channels(int ch) { return ch; }   /* image-private.h:147 all carry Update */
 
@@ -298,9 +300,11 @@ long orc_morphology_primitive(const float *src, float *dst, size_t w, size_t h, 
   const long W = (long) w, H = (long) h, kw = (long) k->width, kh = (long) k->height;
   const int alpha_i = ch - 1;
   long ox, oy, changed = 0;
-  if (method == ORC_CONVOLVE || method == ORC_DILATE) {   /* reflected (:2612-2626) */
+  if (method == ORC_CONVOLVE || method == ORC_DILATE || method == ORC_DILATE_INTENSITY ||
+      method == ORC_ITERATIVE_DISTANCE) {                   /* reflected (:2612-2626) */
     ox = kw - k->x - 1; oy = kh - k->y - 1;
-  } else if (method == ORC_ERODE) {
+  } else if (method == ORC_ERODE || method == ORC_ERODE_INTENSITY || method == ORC_HIT_AND_MISS ||
+             method == ORC_THINNING || method == ORC_THICKEN) {
     ox = k->x; oy = k->y;
   } else
     return -1;
@@ -362,8 +366,10 @@ long orc_morphology_primitive(const float *src, float *dst, size_t w, size_t h, 
           const double centre = (double) src[((size_t) y * w + x) * ch + i];
           double pixel, gamma = 1.0;
           long u, v;
+          const float *selected = NULL;              /* quantum_pixels (:2886): the *Intensity methods copy a whole pixel */
+          double minimum = QR, maximum = 0.0;        /* :2887-2888 */
           if (method == ORC_CONVOLVE) pixel = bias;
-          else if (method == ORC_DILATE) pixel = 0.0;
+          else if (method == ORC_DILATE || method == ORC_ERODE_INTENSITY) pixel = 0.0;     /* :2902-2907 */
           else pixel = centre;
           if (method == ORC_CONVOLVE) {
             const int blend = is_blend_channel(ch, i);
@@ -397,7 +403,7 @@ long orc_morphology_primitive(const float *src, float *dst, size_t w, size_t h, 
                 }
               }
             }
-          } else {                                   /* Dilate :3007-3036, reflected */
+          } else if (method == ORC_DILATE) {         /* :3007-3036, reflected */
             for (v = 0; v < kh; v++) {
               long yy = clampl(y - oy + v, 0, H - 1);
               for (u = 0; u < kw; u++) {
@@ -409,6 +415,68 @@ long orc_morphology_primitive(const float *src, float *dst, size_t w, size_t h, 
                 }
               }
             }
+          } else if (method == ORC_HIT_AND_MISS || method == ORC_THINNING || method == ORC_THICKEN) {
+            /* :3037-3083: minimum of the foreground cells (> 0.7) minus maximum of the background cells (< 0.3), never
+               negative; not reflected */
+            for (v = 0; v < kh; v++) {
+              long yy = clampl(y - oy + v, 0, H - 1);
+              for (u = 0; u < kw; u++) {
+                double kv = k->values[v * kw + u];
+                if (!isnan(kv)) {
+                  long xx = clampl(x - ox + u, 0, W - 1);
+                  double p = (double) src[((size_t) yy * w + xx) * ch + i];
+                  if (kv > 0.7) { if (p < minimum) minimum = p; }
+                  else if (kv < 0.3) { if (p > maximum) maximum = p; }
+                }
+              }
+            }
+            minimum -= maximum;
+            if (minimum < 0.0) minimum = 0.0;
+            pixel = minimum;
+            if (method == ORC_THINNING) pixel = centre - minimum;
+            else if (method == ORC_THICKEN) pixel = centre + minimum;
+          } else if (method == ORC_ERODE_INTENSITY) {   /* :3084-3110: the pixel of least intensity, not reflected */
+            for (v = 0; v < kh; v++) {
+              long yy = clampl(y - oy + v, 0, H - 1);
+              for (u = 0; u < kw; u++) {
+                double kv = k->values[v * kw + u];
+                if (!isnan(kv) && kv >= 0.5) {
+                  long xx = clampl(x - ox + u, 0, W - 1);
+                  const float *p = src + ((size_t) yy * w + xx) * ch;
+                  double intensity = pixel_intensity(p, ch);
+                  if (intensity < minimum) { selected = p; pixel = (double) p[i]; minimum = intensity; }
+                }
+              }
+            }
+          } else if (method == ORC_DILATE_INTENSITY) {  /* :3111-3137: the pixel of greatest intensity, reflected */
+            for (v = 0; v < kh; v++) {
+              long yy = clampl(y - oy + v, 0, H - 1);
+              for (u = 0; u < kw; u++) {
+                double kv = k->values[kw * kh - 1 - (v * kw + u)];
+                if (!isnan(kv) && kv >= 0.5) {
+                  long xx = clampl(x - ox + u, 0, W - 1);
+                  const float *p = src + ((size_t) yy * w + xx) * ch;
+                  double intensity = pixel_intensity(p, ch);
+                  if (intensity > maximum) { pixel = (double) p[i]; selected = p; maximum = intensity; }
+                }
+              }
+            }
+          } else {                                   /* IterativeDistance :3138-3181, reflected: min(pixel + k) */
+            for (v = 0; v < kh; v++) {
+              long yy = clampl(y - oy + v, 0, H - 1);
+              for (u = 0; u < kw; u++) {
+                double kv = k->values[kw * kh - 1 - (v * kw + u)];
+                if (!isnan(kv)) {
+                  long xx = clampl(x - ox + u, 0, W - 1);
+                  double p = (double) src[((size_t) yy * w + xx) * ch + i];
+                  if ((p + kv) < pixel) pixel = p + kv;
+                }
+              }
+            }
+          }
+          if (selected != NULL) {                    /* :3186-3190: copied verbatim, not counted as a change */
+            dst[((size_t) y * w + x) * ch + i] = selected[i];
+            continue;
           }
           gamma = precip(gamma);
           dst[((size_t) y * w + x) * ch + i] = (float) (gamma * pixel);
@@ -503,31 +571,73 @@ int orc_morphology_apply(const float *src, float *dst, size_t w, size_t h, int c
   return rc;
 }
 
+/* composite.c CompositeImage(canvas, source, LightenCompositeOp, clip_to_self = MagickTrue, 0, 0) as MorphologyApply
+   calls it to unite the results of a HitAndMiss kernel list (morphology.c:3722, :4044-4046); same assumptions as
+   composite_difference above.  alpha = RoundToUnity(Sa+Da-Sa*Da) (:2427); alpha channel = QR*alpha (:2702-2706);
+   colour (:3110-3124): (Sca*Da > Dca*Sa) ? QR*(Sca+Dca*(1-Sa)) : QR*(Dca+Sca*(1-Da));  ClampPixel. */
+static void composite_lighten(float *canvas, const float *source, size_t w, size_t h, int ch)
+{
+  const long n = (long) (w * h);
+  const int has_alpha = (ch == 2 || ch == 4);
+  long i;
+#pragma omp parallel for schedule(static)
+  for (i = 0; i < n; i++) {
+    float *q = canvas + (size_t) i * ch;
+    const float *p = source + (size_t) i * ch;
+    const double Sa = QS * (has_alpha ? (double) p[ch - 1] : 65535.0);
+    const double Da = QS * (has_alpha ? (double) q[ch - 1] : 65535.0);
+    double alpha = Sa + Da - Sa * Da;
+    int c;
+    alpha = alpha < 0.0 ? 0.0 : (alpha > 1.0 ? 1.0 : alpha);
+    for (c = 0; c < ch; c++) {
+      double pixel;
+      if (has_alpha && c == ch - 1) pixel = QR * alpha;
+      else {
+        const double Sc = (double) p[c], Dc = (double) q[c];
+        const double Sca = QS * Sa * Sc, Dca = QS * Da * Dc;
+        if ((Sca * Da) > (Dca * Sa)) pixel = QR * (Sca + Dca * (1.0 - Sa));
+        else pixel = QR * (Dca + Sca * (1.0 - Da));
+      }
+      q[c] = clamp_pixel(pixel);
+    }
+  }
+}
+
 static int morphology_apply_basic(const float *src, float *dst, size_t w, size_t h, int ch,
                          int method, long iterations, const orc_kernel *kernels, int nk,
                          double bias)
 {
   const size_t n = w * h * (size_t) ch;
-  size_t kernel_limit, stage_limit = 1;
-  float *cur, *work, *tmp;
+  size_t kernel_limit, method_limit = 1, method_loop = 0, method_changed = 1, stage_limit = 1;
+  float *cur, *work, *tmp, *rslt = NULL;
   orc_kernel *refl = NULL;
-  int kn, rc = 0;
+  int kn, rc = 0, lighten = 0;
   if (iterations == 0) return -1;
   kernel_limit = iterations < 0 ? (w > h ? w : h) : (size_t) iterations;
-  switch (method) {
+  switch (method) {                            /* :3711-3738 */
     case ORC_SMOOTH: stage_limit = 4; break;
-    case ORC_OPEN: case ORC_CLOSE: stage_limit = 2; break;
-    case ORC_CONVOLVE: case ORC_CORRELATE: case ORC_ERODE: case ORC_DILATE: break;
+    case ORC_OPEN: case ORC_CLOSE: case ORC_OPEN_INTENSITY: case ORC_CLOSE_INTENSITY: stage_limit = 2; break;
+    case ORC_HIT_AND_MISS: lighten = 1;        /* union of the kernel list's results */
+      /* fall through */
+    case ORC_THINNING: case ORC_THICKEN:
+      method_limit = kernel_limit;             /* iterate the whole method, each kernel once */
+      kernel_limit = 1;
+      break;
+    case ORC_CONVOLVE: case ORC_CORRELATE: case ORC_ERODE: case ORC_DILATE:
+    case ORC_ERODE_INTENSITY: case ORC_DILATE_INTENSITY: case ORC_ITERATIVE_DISTANCE: break;
     default: return -1;
   }
   cur = (float *) malloc(n * sizeof(float));
   work = (float *) malloc(n * sizeof(float));
   if (!cur || !work) { free(cur); free(work); return -1; }
   memcpy(cur, src, n * sizeof(float));
-  if (method == ORC_CORRELATE || method == ORC_CLOSE || method == ORC_SMOOTH) {
+  if (method == ORC_CORRELATE || method == ORC_CLOSE || method == ORC_SMOOTH || method == ORC_CLOSE_INTENSITY) {
     refl = (orc_kernel *) calloc((size_t) nk, sizeof(orc_kernel));
     for (kn = 0; kn < nk; kn++) kernel_reflect(&kernels[kn], &refl[kn]);
   }
+  while (method_loop < method_limit && method_changed > 0 && rc == 0) {       /* Loop 1 :3787 */
+  method_loop++;
+  method_changed = 0;
   for (kn = 0; kn < nk && rc == 0; kn++) {
     size_t stage;
     for (stage = 1; stage <= stage_limit && rc == 0; stage++) {
@@ -537,7 +647,9 @@ static int morphology_apply_basic(const float *src, float *dst, size_t w, size_t
       long changed = 1;
       switch (method) {                       /* :3813-3893 */
         case ORC_OPEN: prim = stage == 2 ? ORC_DILATE : ORC_ERODE; break;
+        case ORC_OPEN_INTENSITY: prim = stage == 2 ? ORC_DILATE_INTENSITY : ORC_ERODE_INTENSITY; break;
         case ORC_CLOSE: kk = &refl[kn]; prim = stage == 2 ? ORC_ERODE : ORC_DILATE; break;
+        case ORC_CLOSE_INTENSITY: kk = &refl[kn]; prim = stage == 2 ? ORC_ERODE_INTENSITY : ORC_DILATE_INTENSITY; break;
         case ORC_SMOOTH:
           if (stage == 1) prim = ORC_ERODE;
           else if (stage == 2) prim = ORC_DILATE;
@@ -551,10 +663,25 @@ static int morphology_apply_basic(const float *src, float *dst, size_t w, size_t
         loop++;
         changed = orc_morphology_primitive(cur, work, w, h, ch, prim, kk, bias);
         if (changed < 0) { rc = -1; break; }
+        method_changed += (size_t) changed;
         tmp = cur; cur = work; work = tmp;
       }
     }
+    /* multi-kernel handling (:4016-4052): a single kernel or compose == None re-iterates on the result; HitAndMiss
+       keeps the first result and lightens it with every further one, each computed from the ORIGINAL image */
+    if (rc == 0 && nk > 1 && lighten) {
+      if (rslt == NULL) {
+        rslt = (float *) malloc(n * sizeof(float));
+        if (!rslt) { rc = -1; break; }
+        memcpy(rslt, cur, n * sizeof(float));
+      } else
+        composite_lighten(rslt, cur, w, h, ch);
+      memcpy(cur, src, n * sizeof(float));
+    }
   }
+  }
+  if (rc == 0 && rslt != NULL) memcpy(cur, rslt, n * sizeof(float));
+  free(rslt);
   if (rc == 0) memcpy(dst, cur, n * sizeof(float));
   if (refl) { for (kn = 0; kn < nk; kn++) orc_kernel_free(&refl[kn]); free(refl); }
   free(cur); free(work);

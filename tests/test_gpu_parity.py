@@ -320,6 +320,54 @@ def test_resize_all_filters(filt):
         assert max_ulp(got, want) <= 1, (filt, ow, oh)
 
 
+def _kernel_list(arrays):
+    """The same kernel list for both sides: a 'WxH:...;WxH:...' string for the product's parser, oracle kernels (origin
+    at the centre) for the checker."""
+    parts, orc_list = [], []
+    for a in arrays:
+        a = np.asarray(a, np.float64)
+        h, w = a.shape
+        rows = [",".join("nan" if np.isnan(v) else repr(float(v)) for v in row) for row in a]
+        parts.append(f"{w}x{h}:" + " ".join(rows))
+        orc_list.append(util.orc_kernel_from_array(a, (w - 1) // 2, (h - 1) // 2))
+    return ";".join(parts), orc_list
+
+
+_N = np.nan
+_CORNER = np.array([[0, 0, _N], [0, 1, 1], [_N, 1, _N]])
+_LINE_END = np.array([[0, 0, _N], [0, 1, 1], [0, 0, _N]])
+_THIN1 = np.array([[0, 0, 0], [_N, 1, _N], [1, 1, 1]])
+_THIN2 = np.array([[_N, 0, 0], [1, 1, 0], [_N, 1, _N]])
+_DISK2 = np.array([[_N, 1, 1, 1, _N], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [_N, 1, 1, 1, _N]])
+_RECT = np.ones((2, 3))
+_EUCLID = np.array([[np.hypot(u, v) * 655.35 for u in (-2, -1, 0, 1, 2)] for v in (-2, -1, 0, 1, 2)])
+_rot4 = lambda a: [np.rot90(a, k) for k in range(4)]
+MORPH_SELECT = [(18, 1, _rot4(_CORNER)), (18, 2, [_LINE_END]), (18, 3, _rot4(_LINE_END)),
+                (19, 1, _rot4(_THIN1) + _rot4(_THIN2)), (19, -1, _rot4(_THIN1) + _rot4(_THIN2)), (19, 2, [_THIN1]),
+                (20, 1, _rot4(_CORNER)), (20, 3, [_CORNER, _LINE_END]),
+                (5, 1, [_DISK2]), (6, 1, [_DISK2]), (5, 2, [_RECT]), (6, 3, [_RECT, _DISK2]), (10, 1, [_DISK2]),
+                (11, 1, [_RECT]), (11, 2, [_DISK2]), (7, 1, [_EUCLID]), (7, 4, [_EUCLID]), (7, -1, [_EUCLID])]
+
+
+@pytest.mark.parametrize("case", range(len(MORPH_SELECT)))
+def test_hit_and_miss_intensity_and_distance_bit_exact(case):
+    """HitAndMiss / Thinning / Thicken (kernel lists united with Lighten or re-iterated, the whole method iterated until
+    nothing changes), Erode / Dilate / Open / CloseIntensity (a whole pixel is selected by its Rec709 intensity),
+    IterativeDistance: selections and single double operations => bit exact (morphology.c:3037-3181, :3722-3729, :4016-4052)."""
+    method, its, arrays = MORPH_SELECT[case]
+    string, kernels = _kernel_list(arrays)
+    for ch, kind in ((1, "binary"), (3, "binary"), (4, "alpha_blocks"), (2, "noise"), (3, "hdr"), (4, "noise")):
+        if method == 7 and kind == "hdr":
+            continue
+        src = make_image(83, 59, ch, seed=60 + ch + case, kind=kind)
+        want = util.orc_morphology(src, method, its, kernels)
+        got = _host(im.MorphologyImage(_dev(src), method, its, string))
+        assert max_ulp(got, want) == 0, (method, its, ch, kind)
+    src = make_image(40, 31, 4, seed=9, kind="binary")                      # host-buffer entry point
+    want = util.orc_morphology(src, method, its, kernels)
+    assert max_ulp(im.MorphologyImage(im.Image(src), method, its, string).pixels, want) == 0
+
+
 HEXCONE = [4, 5, 6, 7, 8, 9, 10]      # HCL, HCLp, HSB, HSI, HSL, HSV, HWB
 
 
@@ -542,7 +590,7 @@ def test_threshold_declines():
 def test_errors_are_loud():
     src = make_image(16, 16, 4)
     with pytest.raises(im.MagickB200Error):
-        im.MorphologyImage(_dev(src), 18, 1, "Disk:1")                    # HitAndMiss: sequential primitive -> decline
+        im.MorphologyImage(_dev(src), 21, 1, "Disk:1")                    # Distance: sequential two-pass primitive -> decline
     with pytest.raises(im.MagickB200Error):
         im.ResizeImage(_dev(src), 8, 8, 34)                               # SentinelFilter: not a filter
     with pytest.raises(im.MagickB200Error):

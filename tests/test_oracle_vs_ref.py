@@ -152,6 +152,41 @@ def test_colorspace_bit_exact(frm, to):
     assert max_ulp(a, b) == 0
 
 
+def ref_kernel_list(string):
+    """The reference's own (expanded) kernel list for a kernel string, as oracle kernels."""
+    out, idx = [], 0
+    while True:
+        k = util.ref_kernel(string, idx)
+        if k is None:
+            return out
+        out.append(util.orc_kernel_from_array(k[0], k[1], k[2]))
+        idx += 1
+
+
+HMT_CASES = [(18, 1, "Corners"), (18, 1, "LineEnds"), (18, 2, "3x3:1,1,1 0,1,0 -,0,-"), (18, 1, "Peaks:1.9"),
+             (18, 3, "Edges"), (19, 1, "Skeleton:2"), (19, -1, "Skeleton"), (19, 2, "LineEnds"), (19, 1, "ThinSE:482"),
+             (20, 1, "ConvexHull"), (20, 3, "Corners"), (5, 1, "Disk:2"), (6, 1, "Disk:2"), (5, 2, "Rectangle:3x2+0+1"),
+             (6, 3, "Octagon:2"), (10, 1, "Disk:2.5"), (11, 1, "Rectangle:4x3+1+0"), (11, 2, "Diamond:2"),
+             (7, 1, "Euclidean:2"), (7, 4, "Chebyshev:1"), (7, -1, "Manhattan")]
+
+
+@pytest.mark.parametrize("method,its,name", HMT_CASES)
+def test_hit_and_miss_intensity_distance_bit_exact(method, its, name):
+    """HitAndMiss / Thinning / Thicken (morphology.c:3037-3083, lists united with Lighten or re-iterated, the whole
+    method iterated: :3722-3729), Erode / Dilate / Open / CloseIntensity (:3084-3137: a whole pixel is copied),
+    IterativeDistance (:3138-3181) -- the kernels are the reference's own expansion of the kernel string."""
+    kernels = ref_kernel_list(name)
+    assert kernels
+    for ch, kind in ((1, "binary"), (3, "binary"), (4, "alpha_blocks"), (2, "noise"), (3, "hdr")):
+        if method == 7 and kind == "hdr":
+            continue
+        src = make_image(53, 37, ch, seed=40 + ch, kind=kind)
+        a = np.empty_like(src)
+        assert util.ref().ref_morphology(P(src), P(a), 53, 37, ch, method, its, name.encode()) == 0, (name, ch)
+        b = util.orc_morphology(src, method, its, kernels)
+        assert max_ulp(a, b) == 0, (method, its, name, ch, kind)
+
+
 def hexcone_image(kind):
     """Noise plus the pixels the hexcone formulae branch on: grays, black, white, primaries, two-way ties of the
     maximum / minimum, hues on the sector boundaries."""
