@@ -343,6 +343,133 @@ int launch_mode(float *buf, size_t npixels, int channels, cudaStream_t s) {
   return MB200_OK;
 }
 
+// ---- XYZ-derived spaces of the generic branch: Adobe98, DisplayP3, ProPhoto (an RGB matrix and the sRGB transfer curve on
+// either side of XYZ, colorspace-private.h:53-70, :675-737, :938-980, :1197-1211), LMS / CAT02LMS (:108-117, :655-661,
+// :751-757, :1225-1231; the CAT02 legs apply both matrices, colorspace.c:135-143, :424-433), xyY (:1258-1272, :1676-1690)
+// and Luv (:600-625, :1138-1161).  Smooth functions of the sample: <= 1 ULP like the Lab / XYZ legs they are built from.
+struct XyzFamilyConstants {
+  double to_rgb[3][3][3];     // XYZ -> Adobe98, DisplayP3, ProPhoto
+  double to_xyz[3][3][3];     // ... and back
+  double xyz_to_lms[3][3], lms_to_xyz[3][3];
+};
+__constant__ XyzFamilyConstants kx = {
+    {{{2.041587903810746500, -0.56500697427885960, -0.34473135077832956},
+      {-0.969243636280879500, 1.87596750150772020, 0.04155505740717557},
+      {0.013444280632031142, -0.11836239223101838, 1.01517499439120540}},
+     {{2.49349691194142500, -0.93138361791912390, -0.402710784450716840},
+      {-0.82948896956157470, 1.76266406031834630, 0.023624685841943577},
+      {0.03584583024378447, -0.07617238926804182, 0.956884524007687200}},
+     {{1.3457989731028281, -0.25558010007997534, -0.05110628506753401},
+      {-0.5446224939028347, 1.50823274131327810, 0.02053603239147973},
+      {0.0, 0.0, 1.21196754563894540}}},
+    {{{0.57666904291013050, 0.18555823790654630, 0.18822864623499470},
+      {0.29734497525053605, 0.62736356625546610, 0.07529145849399788},
+      {0.02703136138641234, 0.07068885253582723, 0.99133753683763880}},
+     {{0.4865709486482162, 0.26566769316909306, 0.1982172852343625},
+      {0.2289745640697488, 0.69173852183650640, 0.0792869140937450},
+      {0.0, 0.04511338185890264, 1.0439443689009760}},
+     {{0.7977604896723027, 0.13518583717574031, 0.03134934958152480000},
+      {0.2880711282292934, 0.71184321781010140, 0.00008565396060525902},
+      {0.0, 0.0, 0.82510460251046010000}}},
+    {{0.7328, 0.4296, -0.1624}, {-0.7036, 1.6975, 0.0061}, {0.0030, 0.0136, 0.9834}},
+    {{1.096123820835514, -0.278869000218287, 0.182745179382773},
+     {0.454369041975359, 0.473533154307412, 0.072097803717229},
+     {-0.009627608738429, -0.005698031216113, 1.015325639954543}}};
+
+__device__ __forceinline__ void mul3(const double (&m)[3][3], double x, double y, double z, double &a, double &b, double &c) {
+  a = m[0][0] * x + m[0][1] * y + m[0][2] * z;
+  b = m[1][0] * x + m[1][1] * y + m[1][2] * z;
+  c = m[2][0] * x + m[2][1] * y + m[2][2] * z;
+}
+__device__ __forceinline__ double perceptible_reciprocal_d(double x) {       // pixel-accessor.h:242
+  const double sign = x < 0.0 ? -1.0 : 1.0;
+  return (sign * x) >= 1.0e-12 ? 1.0 / x : sign / 1.0e-12;
+}
+constexpr double kLuvDen = kIllX + 15.0 * kIllY + 3.0 * kIllZ;
+constexpr double kLuvUn = 4.0 * kIllX / kLuvDen, kLuvVn = 9.0 * kIllY / kLuvDen;
+
+template <int CH>
+__global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npixels, int space, int forward) {
+  __shared__ double s_scale[128];
+  if (threadIdx.x < 128) s_scale[threadIdx.x] = kDecodeScale[threadIdx.x];
+  __syncthreads();
+  const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= npixels) return;
+  float *q = buf + i * CH;
+  float in0, in1, in2, in3 = 0.f;
+  if (CH == 4) { const float4 t = *reinterpret_cast<const float4 *>(q); in0 = t.x; in1 = t.y; in2 = t.z; in3 = t.w; }
+  else { in0 = q[0]; in1 = q[1]; in2 = q[2]; }
+  const int rgb = space == MB200_Adobe98Colorspace ? 0 : space == MB200_DisplayP3Colorspace ? 1 : space == MB200_ProPhotoColorspace ? 2 : -1;
+  double o0, o1, o2;
+  if (forward) {
+    double X, Y, Z, a, b, c;
+    rgb_to_xyz(in0, in1, in2, X, Y, Z, s_scale);
+    if (rgb >= 0) {
+      mul3(kx.to_rgb[rgb], X, Y, Z, a, b, c);
+      a = QS * encode_pixel_gamma(QR * a); b = QS * encode_pixel_gamma(QR * b); c = QS * encode_pixel_gamma(QR * c);
+    } else if (space == MB200_LMSColorspace) {
+      mul3(kx.xyz_to_lms, X, Y, Z, a, b, c);
+    } else if (space == MB200_CAT02LMSColorspace) {
+      double L, M, S;
+      mul3(kx.xyz_to_lms, X, Y, Z, L, M, S);
+      mul3(kx.lms_to_xyz, L, M, S, a, b, c);
+    } else if (space == MB200_xyYColorspace) {
+      const double gamma = perceptible_reciprocal_d(X + Y + Z);
+      a = gamma * X; b = gamma * Y; c = Y;
+    } else {                                                       // Luv
+      double L = Y > kCieEps ? __dsub_rn(__dmul_rn(116.0, cube_root5(Y)), 16.0) : kCieK * Y;
+      const double alpha = perceptible_reciprocal_d(X + 15.0 * Y + 3.0 * Z);
+      const double u = 13.0 * L * (4.0 * alpha * X - kLuvUn), v = 13.0 * L * (9.0 * alpha * Y - kLuvVn);
+      a = L / 100.0; b = (u + 134.0) / 354.0; c = (v + 140.0) / 262.0;
+    }
+    o0 = QR * a; o1 = QR * b; o2 = QR * c;
+  } else {
+    const double a = QS * static_cast<double>(in0), b = QS * static_cast<double>(in1), c = QS * static_cast<double>(in2);
+    double X, Y, Z;
+    if (rgb >= 0) {
+      const double r = QS * decode_pixel_gamma_tab(QR * a, s_scale), g = QS * decode_pixel_gamma_tab(QR * b, s_scale),
+                   bl = QS * decode_pixel_gamma_tab(QR * c, s_scale);
+      mul3(kx.to_xyz[rgb], r, g, bl, X, Y, Z);
+    } else if (space == MB200_LMSColorspace) {
+      mul3(kx.lms_to_xyz, a, b, c, X, Y, Z);
+    } else if (space == MB200_CAT02LMSColorspace) {
+      double L, M, S;
+      mul3(kx.xyz_to_lms, a, b, c, L, M, S);
+      mul3(kx.lms_to_xyz, L, M, S, X, Y, Z);
+    } else if (space == MB200_xyYColorspace) {
+      const double gamma = perceptible_reciprocal_d(b);
+      X = gamma * c * a; Y = c; Z = gamma * c * (1.0 - a - b);
+    } else {                                                       // Luv
+      const double L = 100.0 * a, u = 354.0 * b - 134.0, v = 262.0 * c - 140.0;
+      if (L > (kCieK * kCieEps)) { const double t = (L + 16.0) / 116.0; Y = t * t * t; } else Y = L / kCieK;
+      const double pu = ((52.0 * L * perceptible_reciprocal_d(u + 13.0 * L * kLuvUn)) - 1.0) / 3.0;
+      const double gamma = perceptible_reciprocal_d(pu - (-1.0 / 3.0));
+      X = gamma * ((Y * ((39.0 * L * perceptible_reciprocal_d(v + 13.0 * L * kLuvVn)) - 5.0)) + 5.0 * Y);
+      Z = (X * pu) - 5.0 * Y;
+    }
+    xyz_to_rgb(X, Y, Z, o0, o1, o2);
+  }
+  if (CH == 4) *reinterpret_cast<float4 *>(q) = make_float4(static_cast<float>(o0), static_cast<float>(o1), static_cast<float>(o2), in3);
+  else { q[0] = static_cast<float>(o0); q[1] = static_cast<float>(o1); q[2] = static_cast<float>(o2); }
+}
+
+bool is_xyz_family(int cs) {
+  return cs == MB200_Adobe98Colorspace || cs == MB200_DisplayP3Colorspace || cs == MB200_ProPhotoColorspace ||
+         cs == MB200_LMSColorspace || cs == MB200_CAT02LMSColorspace || cs == MB200_xyYColorspace || cs == MB200_LuvColorspace;
+}
+
+int launch_xyz_family_leg(float *buf, size_t npixels, int channels, int space, bool forward, cudaStream_t s) {
+  const int rc = ensure_decode_scale();
+  if (rc) return rc;
+  const unsigned blocks = static_cast<unsigned>((npixels + 255) / 256);
+  if (channels == 4) xyz_family_kernel<4><<<blocks, 256, 0, s>>>(buf, npixels, space, forward ? 1 : 0);
+  else xyz_family_kernel<3><<<blocks, 256, 0, s>>>(buf, npixels, space, forward ? 1 : 0);
+  count_launch();
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "colorspace launch");
+  return MB200_OK;
+}
+
 // ---- matrix colourspaces: CMY, YCbCr (= YPbPr), YDbDr, YIQ, YPbPr, YUV through the generic branch
 // (colorspace.c:958-1054 / :2296-2390, colorspace-private.h:793, :141, :1551-1593, :1637-1701) and the
 // LUT branch for OHTA, Rec601YCbCr, Rec709YCbCr (colorspace.c:1229-1494 / :2560-2830): samples quantised to a
@@ -487,14 +614,16 @@ int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to
                                   cs == MB200_XYZColorspace || cs == MB200_RGBColorspace; };
   MatrixLeg from_leg{}, to_leg{};
   const bool from_hex = is_hexcone_colorspace(from), to_hex = is_hexcone_colorspace(to);
-  const bool from_matrix = !core(from) && !from_hex && matrix_leg(from, false, from_leg);
-  const bool to_matrix = !core(to) && !to_hex && matrix_leg(to, true, to_leg);
-  if ((!core(from) && !from_matrix && !from_hex) || (!core(to) && !to_matrix && !to_hex))
+  const bool from_xyz = is_xyz_family(from), to_xyz = is_xyz_family(to);
+  const bool from_matrix = !core(from) && !from_hex && !from_xyz && matrix_leg(from, false, from_leg);
+  const bool to_matrix = !core(to) && !to_hex && !to_xyz && matrix_leg(to, true, to_leg);
+  if ((!core(from) && !from_matrix && !from_hex && !from_xyz) || (!core(to) && !to_matrix && !to_hex && !to_xyz))
     return fail(MB200_EUNSUPPORTED, "colorspace %d -> %d not implemented", from, to);
   if (from == to) return MB200_OK;
   int rc = MB200_OK;
   if (from != MB200_sRGBColorspace) {          // colorspace.c:1773-1774: back to sRGB first
     if (from_hex) rc = launch_hexcone_leg(buf, npixels, channels, from, false, s);
+    else if (from_xyz) rc = launch_xyz_family_leg(buf, npixels, channels, from, false, s);
     else if (from_matrix) rc = launch_matrix_leg(buf, npixels, channels, from_leg, s);
     else if (from == MB200_LabColorspace) rc = launch_mode<kFromLab>(buf, npixels, channels, s);
     else if (from == MB200_XYZColorspace) rc = launch_mode<kFromXyz>(buf, npixels, channels, s);
@@ -502,6 +631,7 @@ int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to
     if (rc) return rc;
   }
   if (to_hex) rc = launch_hexcone_leg(buf, npixels, channels, to, true, s);
+  else if (to_xyz) rc = launch_xyz_family_leg(buf, npixels, channels, to, true, s);
   else if (to_matrix) rc = launch_matrix_leg(buf, npixels, channels, to_leg, s);
   else if (to == MB200_LabColorspace) rc = launch_mode<kToLab>(buf, npixels, channels, s);
   else if (to == MB200_XYZColorspace) rc = launch_mode<kToXyz>(buf, npixels, channels, s);

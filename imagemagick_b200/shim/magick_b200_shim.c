@@ -408,6 +408,13 @@ static int map_colorspace(ColorspaceType c)
     case YIQColorspace: return MB200_YIQColorspace;
     case YPbPrColorspace: return MB200_YPbPrColorspace;
     case YUVColorspace: return MB200_YUVColorspace;
+    case LMSColorspace: return MB200_LMSColorspace;
+    case LuvColorspace: return MB200_LuvColorspace;
+    case xyYColorspace: return MB200_xyYColorspace;
+    case DisplayP3Colorspace: return MB200_DisplayP3Colorspace;
+    case Adobe98Colorspace: return MB200_Adobe98Colorspace;
+    case ProPhotoColorspace: return MB200_ProPhotoColorspace;
+    case CAT02LMSColorspace: return MB200_CAT02LMSColorspace;
     case HCLColorspace: return MB200_HCLColorspace;
     case HCLpColorspace: return MB200_HCLpColorspace;
     case HSBColorspace: return MB200_HSBColorspace;

@@ -154,6 +154,10 @@ int main(void)
   if (TransformImageColorspace(a, HSVColorspace, ex) == MagickFalse || a->colorspace != HSVColorspace) failures++;
   B200ShimEnable(0); (void) __real_TransformImageColorspace(b, HSVColorspace, ex); B200ShimEnable(1);
   CHECK("TransformImageColorspace HWB->HSV", 0, a, b);
+  a = CloneImage(rgba, 0, 0, MagickTrue, ex); b = CloneImage(rgba, 0, 0, MagickTrue, ex);
+  if (TransformImageColorspace(a, LuvColorspace, ex) == MagickFalse || a->colorspace != LuvColorspace) failures++;
+  B200ShimEnable(0); (void) __real_TransformImageColorspace(b, LuvColorspace, ex); B200ShimEnable(1);
+  CHECK("TransformImageColorspace sRGB->Luv", 1, a, b);
   CHECK("ResizeImage Jinc 50% RGBA", 1, ResizeImage(rgba, rgba->columns / 2, rgba->rows / 2, JincFilter, ex),
         CPU(__real_ResizeImage(rgba, rgba->columns / 2, rgba->rows / 2, JincFilter, ex)));
   CHECK("ResizeImage Kaiser 150% RGB", 1, ResizeImage(rgb, rgb->columns * 3 / 2, rgb->rows * 3 / 2, KaiserFilter, ex),

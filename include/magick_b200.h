@@ -97,17 +97,24 @@ typedef enum {
   MB200_HSVColorspace = 9,
   MB200_HWBColorspace = 10,
   MB200_LabColorspace = 11,
+  MB200_LMSColorspace = 16,           /* XYZ-derived spaces of the generic branch: <= 1 ULP */
+  MB200_LuvColorspace = 17,
   MB200_OHTAColorspace = 18,          /* LUT branch, colorspace.c:1229-1494 */
   MB200_Rec601YCbCrColorspace = 19,   /* LUT branch */
   MB200_Rec709YCbCrColorspace = 20,   /* LUT branch */
   MB200_RGBColorspace = 21,           /* linear RGB */
   MB200_sRGBColorspace = 23,
+  MB200_xyYColorspace = 25,
   MB200_XYZColorspace = 26,
   MB200_YCbCrColorspace = 27,
   MB200_YDbDrColorspace = 29,
   MB200_YIQColorspace = 30,
   MB200_YPbPrColorspace = 31,
-  MB200_YUVColorspace = 32
+  MB200_YUVColorspace = 32,
+  MB200_DisplayP3Colorspace = 35,
+  MB200_Adobe98Colorspace = 36,
+  MB200_ProPhotoColorspace = 37,
+  MB200_CAT02LMSColorspace = 40
 } mb200_colorspace;
 
 /* Mirror of KernelInfo (MagickCore/morphology.h:102-130): a singly linked list

@@ -1660,6 +1660,124 @@ static int colorspace_hexcone_leg(float *buf, long n, int ch, int cs, int forwar
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+   XYZ-derived colourspaces of the generic branch (colorspace.c:958-1054 / :2296-2390): Adobe98, DisplayP3, ProPhoto
+   (an RGB matrix + the sRGB transfer curve on either side of XYZ), LMS, CAT02LMS, xyY, Luv.
+   ------------------------------------------------------------------------------------------ */
+typedef struct { double m[3][3]; } mat3;
+/* colorspace-private.h:53-70 / :675-692 / :719-737 (X is assigned twice there: the second row set counts) */
+static const mat3 adobe98_to_xyz = {{{0.57666904291013050, 0.18555823790654630, 0.18822864623499470},
+                                     {0.29734497525053605, 0.62736356625546610, 0.07529145849399788},
+                                     {0.02703136138641234, 0.07068885253582723, 0.99133753683763880}}};
+static const mat3 displayp3_to_xyz = {{{0.4865709486482162, 0.26566769316909306, 0.1982172852343625},
+                                       {0.2289745640697488, 0.69173852183650640, 0.0792869140937450},
+                                       {0.0000000000000000, 0.04511338185890264, 1.0439443689009760}}};
+static const mat3 prophoto_to_xyz = {{{0.7977604896723027, 0.13518583717574031, 0.03134934958152480000},
+                                      {0.2880711282292934, 0.71184321781010140, 0.00008565396060525902},
+                                      {0.0000000000000000, 0.00000000000000000, 0.82510460251046010000}}};
+/* :938-952 / :966-980 / :1197-1211 */
+static const mat3 xyz_to_adobe98 = {{{2.041587903810746500, -0.56500697427885960, -0.34473135077832956},
+                                     {-0.969243636280879500, 1.87596750150772020, 0.04155505740717557},
+                                     {0.013444280632031142, -0.11836239223101838, 1.01517499439120540}}};
+static const mat3 xyz_to_displayp3 = {{{2.49349691194142500, -0.93138361791912390, -0.402710784450716840},
+                                       {-0.82948896956157470, 1.76266406031834630, 0.023624685841943577},
+                                       {0.03584583024378447, -0.07617238926804182, 0.956884524007687200}}};
+static const mat3 xyz_to_prophoto = {{{1.3457989731028281, -0.25558010007997534, -0.05110628506753401},
+                                      {-0.5446224939028347, 1.50823274131327810, 0.02053603239147973},
+                                      {0.0000000000000000, 0.0000000000000000, 1.21196754563894540}}};
+/* a*x + b*y + c*z exactly as the reference writes it: negative coefficients appear as subtractions there, which is the
+   same IEEE result as adding the product with the negated constant */
+static double row3(const double *r, double x, double y, double z) { return r[0] * x + r[1] * y + r[2] * z; }
+
+static void xyz_to_lms(double x, double y, double z, double *L, double *M, double *S)
+{ /* colorspace-private.h:1225-1231 (LMS) == :751-757 (CAT02LMS) */
+  *L = 0.7328 * x + 0.4296 * y - 0.1624 * z;
+  *M = (-0.7036 * x + 1.6975 * y + 0.0061 * z);
+  *S = 0.0030 * x + 0.0136 * y + 0.9834 * z;
+}
+static void lms_to_xyz(double L, double M, double S, double *X, double *Y, double *Z)
+{ /* :655-661 == :108-117 */
+  *X = 1.096123820835514 * L - 0.278869000218287 * M + 0.182745179382773 * S;
+  *Y = 0.454369041975359 * L + 0.473533154307412 * M + 0.072097803717229 * S;
+  *Z = (-0.009627608738429) * L - 0.005698031216113 * M + 1.015325639954543 * S;
+}
+
+#define LUV_UN (4.0 * ILL_X / (ILL_X + 15.0 * ILL_Y + 3.0 * ILL_Z))
+#define LUV_VN (9.0 * ILL_Y / (ILL_X + 15.0 * ILL_Y + 3.0 * ILL_Z))
+static void xyz_to_luv(double X, double Y, double Z, double *L, double *u, double *v)
+{ /* :1138-1161 */
+  double alpha;
+  if ((Y / ILL_Y) > CIE_EPS) *L = (double) (116.0 * pow(Y / ILL_Y, 1.0 / 3.0) - 16.0);
+  else *L = CIE_K * (Y / ILL_Y);
+  alpha = precip(X + 15.0 * Y + 3.0 * Z);
+  *u = 13.0 * (*L) * ((4.0 * alpha * X) - LUV_UN);
+  *v = 13.0 * (*L) * ((9.0 * alpha * Y) - LUV_VN);
+  *L /= 100.0;
+  *u = (*u + 134.0) / 354.0;
+  *v = (*v + 140.0) / 262.0;
+}
+static void luv_to_xyz(double L, double u, double v, double *X, double *Y, double *Z)
+{ /* :600-625 */
+  double gamma;
+  if (L > (CIE_K * CIE_EPS)) *Y = (double) pow((L + 16.0) / 116.0, 3.0);
+  else *Y = L / CIE_K;
+  gamma = precip((((52.0 * L * precip(u + 13.0 * L * LUV_UN)) - 1.0) / 3.0) - (-1.0 / 3.0));
+  *X = gamma * ((*Y * ((39.0 * L * precip(v + 13.0 * L * LUV_VN)) - 5.0)) + 5.0 * (*Y));
+  *Z = (*X * (((52.0 * L * precip(u + 13.0 * L * LUV_UN)) - 1.0) / 3.0)) - 5.0 * (*Y);
+}
+
+static int is_xyz_family_space(int cs)
+{
+  return cs == ORC_CS_ADOBE98 || cs == ORC_CS_DISPLAYP3 || cs == ORC_CS_PROPHOTO || cs == ORC_CS_LMS ||
+         cs == ORC_CS_CAT02LMS || cs == ORC_CS_XYY || cs == ORC_CS_LUV;
+}
+
+static int colorspace_xyz_family_leg(float *buf, long n, int ch, int cs, int forward)
+{
+  long i;
+  if (!is_xyz_family_space(cs)) return -1;
+#pragma omp parallel for schedule(static)
+  for (i = 0; i < n; i++) {
+    float *q = buf + (size_t) i * ch;
+    double X, Y, Z, a, b, c;
+    if (forward) {                       /* ConvertRGBToGeneric :411 -> (float) (QR * component) */
+      rgb_to_xyz((double) q[0], (double) q[1], (double) q[2], &X, &Y, &Z);
+      switch (cs) {
+        case ORC_CS_ADOBE98: case ORC_CS_DISPLAYP3: case ORC_CS_PROPHOTO: {
+          const mat3 *m = cs == ORC_CS_ADOBE98 ? &xyz_to_adobe98 : cs == ORC_CS_DISPLAYP3 ? &xyz_to_displayp3 : &xyz_to_prophoto;
+          a = QS * encode_pixel_gamma(QR * row3(m->m[0], X, Y, Z));
+          b = QS * encode_pixel_gamma(QR * row3(m->m[1], X, Y, Z));
+          c = QS * encode_pixel_gamma(QR * row3(m->m[2], X, Y, Z));
+          break;
+        }
+        case ORC_CS_LMS: xyz_to_lms(X, Y, Z, &a, &b, &c); break;
+        case ORC_CS_CAT02LMS: { double L, M, S; xyz_to_lms(X, Y, Z, &L, &M, &S); lms_to_xyz(L, M, S, &a, &b, &c); break; }  /* :424-433 */
+        case ORC_CS_XYY: { const double gamma = precip(X + Y + Z); a = gamma * X; b = gamma * Y; c = Y; break; }      /* :1258-1272 */
+        default: xyz_to_luv(X, Y, Z, &a, &b, &c); break;
+      }
+      q[0] = (float) (QR * a); q[1] = (float) (QR * b); q[2] = (float) (QR * c);
+    } else {                             /* ConvertGenericToRGB :122 on QuantumScale * sample */
+      double R, G, B;
+      a = QS * q[0]; b = QS * q[1]; c = QS * q[2];
+      switch (cs) {
+        case ORC_CS_ADOBE98: case ORC_CS_DISPLAYP3: case ORC_CS_PROPHOTO: {
+          const mat3 *m = cs == ORC_CS_ADOBE98 ? &adobe98_to_xyz : cs == ORC_CS_DISPLAYP3 ? &displayp3_to_xyz : &prophoto_to_xyz;
+          const double r = QS * decode_pixel_gamma(QR * a), g = QS * decode_pixel_gamma(QR * b), bl = QS * decode_pixel_gamma(QR * c);
+          X = row3(m->m[0], r, g, bl); Y = row3(m->m[1], r, g, bl); Z = row3(m->m[2], r, g, bl);
+          break;
+        }
+        case ORC_CS_LMS: lms_to_xyz(a, b, c, &X, &Y, &Z); break;
+        case ORC_CS_CAT02LMS: { double L, M, S; xyz_to_lms(a, b, c, &L, &M, &S); lms_to_xyz(L, M, S, &X, &Y, &Z); break; }  /* :135-143 */
+        case ORC_CS_XYY: { const double gamma = precip(b); X = gamma * c * a; Y = c; Z = gamma * c * (1.0 - a - b); break; }  /* :1676-1690 */
+        default: luv_to_xyz(100.0 * a, 354.0 * b - 134.0, 262.0 * c - 140.0, &X, &Y, &Z); break;                        /* :706-717 */
+      }
+      xyz_to_rgb(X, Y, Z, &R, &G, &B);
+      q[0] = (float) R; q[1] = (float) G; q[2] = (float) B;
+    }
+  }
+  return 0;
+}
+
 /* colorspace.c:1751-1783 TransformImageColorspace: anything that is not sRGB goes back to sRGB
    first (TransformsRGBImage), then forward (sRGBTransformImage). */
 int orc_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to)
@@ -1672,11 +1790,13 @@ int orc_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to)
   if (from != ORC_CS_SRGB) {
     rc = is_core_space(from) ? colorspace_core(buf, w, h, ch, from, ORC_CS_SRGB)
          : is_hexcone_space(from) ? colorspace_hexcone_leg(buf, n, ch, from, 0)
+         : is_xyz_family_space(from) ? colorspace_xyz_family_leg(buf, n, ch, from, 0)
                                   : colorspace_matrix_leg(buf, n, ch, from, 0);
     if (rc) return rc;
   }
   if (to == ORC_CS_SRGB) return 0;
   if (is_hexcone_space(to)) return colorspace_hexcone_leg(buf, n, ch, to, 1);
+  if (is_xyz_family_space(to)) return colorspace_xyz_family_leg(buf, n, ch, to, 1);
   return is_core_space(to) ? colorspace_core(buf, w, h, ch, ORC_CS_SRGB, to) : colorspace_matrix_leg(buf, n, ch, to, 1);
 }
 

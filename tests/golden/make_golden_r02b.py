@@ -1,6 +1,6 @@
 """Generates tests/golden/r02b_golden.npz from the REAL reference (oracle/_ref/libmagickref.so): the operators added
 late in round 2 -- ResizeImage with the Jinc and Kaiser filters, the hue / saturation colourspaces (HCL, HCLp, HSB, HSI,
-HSL, HSV, HWB) in both directions.  Run in the authoring container only:   python tests/golden/make_golden_r02b.py
+HSL, HSV, HWB) and the XYZ-derived ones (LMS, CAT02LMS, Luv, xyY, DisplayP3, Adobe98, ProPhoto) in both directions.  Run in the authoring container only:   python tests/golden/make_golden_r02b.py
 tests/test_golden.py pins the oracle (CPU) and the CUDA path (-m gpu) to these arrays."""
 import sys
 from pathlib import Path
@@ -12,7 +12,8 @@ import util  # noqa: E402
 
 OUT = Path(__file__).resolve().parent / "r02b_golden.npz"
 W, H = 41, 31
-HEXCONE = {"hcl": 4, "hclp": 5, "hsb": 6, "hsi": 7, "hsl": 8, "hsv": 9, "hwb": 10}
+HEXCONE = {"hcl": 4, "hclp": 5, "hsb": 6, "hsi": 7, "hsl": 8, "hsv": 9, "hwb": 10,
+           "lms": 16, "luv": 17, "xyy": 25, "displayp3": 35, "adobe98": 36, "prophoto": 37, "cat02lms": 40}
 
 
 def source(ch):

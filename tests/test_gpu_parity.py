@@ -410,6 +410,31 @@ def test_hexcone_colorspaces(cs, kind):
     assert max_ulp(h.pixels, want) <= bar
 
 
+XYZ_FAMILY = [16, 17, 25, 35, 36, 37, 40]      # LMS, Luv, xyY, DisplayP3, Adobe98, ProPhoto, CAT02LMS
+
+
+@pytest.mark.parametrize("cs", XYZ_FAMILY)
+@pytest.mark.parametrize("kind", ["noise", "hdr"])
+def test_xyz_family_colorspaces(cs, kind):
+    """Matrix / transfer-curve / chromaticity spaces derived from XYZ (colorspace-private.h:53-130, :600-760, :938-1272):
+    smooth functions of the sample, <= 1 ULP like the Lab / XYZ legs they are built from."""
+    for ch in (3, 4):
+        src = _hexcone_image(131, 67, ch, kind, seed=120 + cs)
+        for frm, to in ((23, cs), (cs, 23), (cs, 17 if cs != 17 else 25), (11, cs)):
+            want = src.copy()
+            assert oracle().orc_colorspace(P(want), 131, 67, ch, frm, to) == 0
+            img = _dev(src.copy())
+            img.colorspace = frm
+            assert im.TransformImageColorspace(img, to) is True and img.colorspace == to
+            got = _host(img)
+            ok = np.isfinite(want)
+            assert np.array_equal(np.isfinite(got), ok), (ch, frm, to)
+            d = util.ulp_or_noise(np.where(ok, got, np.float32(0)), np.where(ok, want, np.float32(0)))
+            # a hop through two <= 1 ULP legs can add up; single legs must stay within 1 ULP
+            assert d.max() <= (1 if 23 in (frm, to) else 4), (ch, frm, to, int(d.max()))
+            assert (d == 0).mean() > 0.99, (ch, frm, to, float((d == 0).mean()))
+
+
 def test_resize_lanczos_2x_down_2048():
     """configs[2] at 1/8 scale: Lanczos 2x downscale, 1-ULP check against the CPU result."""
     src = make_image(2048, 2048, 4, seed=42)

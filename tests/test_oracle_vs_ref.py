@@ -218,6 +218,24 @@ def test_hexcone_colorspaces_bit_exact(cs, kind):
         assert max_ulp(np.where(ok, a, np.float32(0)), np.where(ok, b, np.float32(0))) == 0, (frm, to)
 
 
+XYZ_FAMILY = [16, 17, 25, 35, 36, 37, 40]      # LMS, Luv, xyY, DisplayP3, Adobe98, ProPhoto, CAT02LMS
+
+
+@pytest.mark.parametrize("cs", XYZ_FAMILY)
+@pytest.mark.parametrize("kind", ["noise", "hdr"])
+def test_xyz_family_colorspaces_bit_exact(cs, kind):
+    """The generic branch's XYZ-derived spaces (colorspace-private.h:53-130, :600-760, :938-1272): forward, inverse and a
+    hop to another space of the family."""
+    src = hexcone_image(kind)
+    for frm, to in ((23, cs), (cs, 23), (cs, 17 if cs != 17 else 25)):
+        a, b = src.copy(), src.copy()
+        assert util.ref().ref_colorspace(P(a), 64, 48, 4, frm, to) == 0
+        assert oracle().orc_colorspace(P(b), 64, 48, 4, frm, to) == 0
+        assert np.array_equal(np.isnan(a), np.isnan(b)), (frm, to)
+        ok = ~np.isnan(a)
+        assert max_ulp(np.where(ok, a, np.float32(0)), np.where(ok, b, np.float32(0))) == 0, (frm, to)
+
+
 @pytest.mark.parametrize("kind", ["alpha_blocks", "hdr"])
 def test_difference_methods_bit_exact_on_awkward_pixels(kind):
     """EdgeIn/EdgeOut/Edge/TopHat/BottomHat end in CompositeImage(Difference) (morphology.c:3995-4012):

@@ -166,6 +166,15 @@ def max_ulp(a, b) -> int:
     return int(ulp_distance(np.ascontiguousarray(a), np.ascontiguousarray(b)).max())
 
 
+def ulp_or_noise(a, b, tiny=1.0e-6) -> np.ndarray:
+    """ULP distance, except where BOTH values are rounding noise around zero (|v| < tiny Quantum units = 1.5e-11 of full
+    scale): a component the reference computes as the difference of two equal numbers -- e.g. the red channel of an
+    Adobe98 blue taken to sRGB, whose primaries coincide -- has no significant bits to compare; 0 is returned there."""
+    d = ulp_distance(np.ascontiguousarray(a), np.ascontiguousarray(b))
+    noise = (np.abs(a) < tiny) & (np.abs(b) < tiny)
+    return np.where(noise, 0, d)
+
+
 def frac_exact(a, b) -> float:
     return float((ulp_distance(np.ascontiguousarray(a), np.ascontiguousarray(b)) == 0).mean())
 
