@@ -20,14 +20,18 @@
 //
 //  vertical (axis 1): lane = pixel column, 512-byte coalesced row reads, register prefetch ring.
 //  horizontal (axis 0): lane = image row.  Each warp stages 16-pixel (256-byte, line-aligned)
-//    chunks of its 32 rows into a private shared-memory ring with cp.async (LDGSTS) -- full-line
-//    global requests, no block barriers -- and reads its own row back with conflict-free LDS.128
-//    (row pitch 272 B).  Outputs are 16-byte stores; eight consecutive steps of a lane fill a line.
+//    chunks of its 32 rows into a private shared-memory ring -- by TMA (two cp.async.bulk.tensor.2d boxes of
+//    8 pixels x 32 rows per chunk, 128-byte swizzle, mbarrier transaction counts; resize_h_tma_kernel, the default) or
+//    with per-lane cp.async (LDGSTS; resize_h_stream_kernel) -- full-line global requests, no block barriers -- and
+//    reads its own row back with conflict-free LDS.128.  Outputs are 16-byte stores; eight consecutive steps of a lane
+//    fill a line.
 //
 // Outputs outside the streamed runs (the image borders, where the window is clipped, and the very
 // short low-binade runs) are produced by the generic gather kernels of resize.cu.
 #include "mb200_internal.h"
 
+#include <cuda.h>                 // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -315,6 +319,148 @@ __global__ void __launch_bounds__(128, MINB) resize_h_stream_kernel(const Stream
   cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------ horizontal, TMA staging
+// The same streaming loop as resize_h_stream_kernel; only the way the 16-pixel chunks reach the warp's ring differs.
+// One elected lane issues two cp.async.bulk.tensor.2d loads per chunk (box = 8 pixels x 32 rows = 128 B x 32 with the
+// 128-byte swizzle: the 16-byte word a lane reads from its row is XORed with row % 8, so the eight rows of a quarter warp
+// hit eight different bank groups -- conflict-free LDS.128 without the padded pitch) and the chunk's arrival is an
+// mbarrier transaction count instead of cp.async groups: no per-lane copy instructions, no bank-conflicted ring writes
+// (the cp.async ring: 34 % of the shared-memory wavefronts of its writes conflict, profiles/r02_resize_raw.csv).
+// Rows / pixels outside the image are zero-filled by the TMA unit; the streamed runs never read them into a stored
+// output (clipped windows are border outputs, gathered by the extra CTAs).
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MB200_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MB200_DONE;\n"
+      "bra MB200_WAIT;\n"
+      "MB200_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map, int c0, int c1, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+template <int S, int N, int NSLOT, int MINB, int BOXES = 2>
+__global__ void __launch_bounds__(128, MINB) resize_h_tma_kernel(const StreamArgs a, const __grid_constant__ CUtensorMap tmap) {
+  using T = Rot<S, N>;
+  constexpr int kChunkPx = 8 * BOXES, kBoxBytes = 32 * 128, kSlotBytes = BOXES * kBoxBytes;
+  constexpr int R = T::R, P = T::P, BODY = T::BODY;
+  extern __shared__ __align__(1024) unsigned char ring_all[];
+  __shared__ __align__(8) unsigned long long bars[4][NSLOT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the 128-byte swizzle is a function of the shared-memory ADDRESS: slots must start on 1024-byte boundaries
+  const unsigned ring_base = (static_cast<unsigned>(__cvta_generic_to_shared(ring_all)) + 1023u) & ~1023u;
+  const unsigned ring_s = ring_base + static_cast<unsigned>(warp) * NSLOT * kSlotBytes;
+  const unsigned bar_s = static_cast<unsigned>(__cvta_generic_to_shared(&bars[warp][0]));
+  const int row0 = blockIdx.y * 128 + warp * 32;
+  if (row0 >= a.height) return;
+  if (static_cast<int>(blockIdx.x) >= a.nstrips) {
+    if (row0 + lane < a.height) border_output<0>(a, __ldg(a.border + (blockIdx.x - a.nstrips)), row0 + lane);
+    return;
+  }
+  const Strip st = locate(a, blockIdx.x, S);
+  double W[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) W[j] = __ldg(a.wsets + st.set * N + j);
+  const int niter = (S * (st.nout - 1) + N + BODY - 1) / BODY;
+  const int p0 = st.src0;
+  const int c0 = p0 / kChunkPx;
+  const int nchunks = (p0 + S * (st.nout - 1) + N + kChunkPx - 1) / kChunkPx - c0;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k) mbar_init(bar_s + 8 * k, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto issue = [&](int chunk_rel) {                 // elected lane: two boxes of 8 pixels x 32 rows into the chunk's slot
+    if (lane == 0 && chunk_rel < nchunks) {
+      const int k = chunk_rel % NSLOT;
+      const unsigned slot = ring_s + static_cast<unsigned>(k) * kSlotBytes, bar = bar_s + 8 * k;
+      const int x = (c0 + chunk_rel) * kChunkPx * 4;  // float index of the chunk's first pixel
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot's last generic-proxy reads precede the refill
+      mbar_expect_tx(bar, kSlotBytes);
+      tma_load_2d(slot, &tmap, x, row0, bar);
+      if (BOXES == 2) tma_load_2d(slot + kBoxBytes, &tmap, x + 32, row0, bar);
+    }
+  };
+#pragma unroll
+  for (int c = 0; c < NSLOT; ++c) issue(c);
+
+  const int y = row0 + lane;
+  const bool active = y < a.height;
+  double acc[R][4];
+#pragma unroll
+  for (int q = 0; q < R; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0; }
+  int c = -R;
+  float *outp = a.dst + (static_cast<ptrdiff_t>(active ? y : 0) * a.out_w + (st.o0 - (R - 1))) * 4;
+  int chunk = 0;
+  int px_in = p0 - c0 * kChunkPx;
+  const unsigned row_off = lane * 128, swz = lane & 7;
+  // address of pixel p (0..15) of this lane's row inside a slot: box p/8, 16-byte word (p%8) ^ (row%8)
+  auto addr = [&](unsigned slot, int p) {
+    return slot + static_cast<unsigned>(p >> 3) * kBoxBytes + row_off + ((static_cast<unsigned>(p & 7) ^ swz) << 4);
+  };
+  mbar_wait(bar_s, 0);
+  unsigned slot_s = ring_s;
+  float4 vnext;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(vnext.x), "=f"(vnext.y), "=f"(vnext.z), "=f"(vnext.w) : "r"(addr(slot_s, px_in)));
+#pragma unroll 1
+  for (int t = 0; t < niter; ++t) {
+#pragma unroll
+    for (int b = 0; b < BODY; ++b) {
+      const int m = b % P;
+      const float4 v = vnext;
+      if (++px_in == kChunkPx) {                    // warp-uniform: chunk exhausted
+        px_in = 0;
+        __syncwarp();                               // every lane is done reading the slot
+        issue(chunk + NSLOT);                       // refill it
+        ++chunk;
+        const int k = chunk % NSLOT;
+        if (chunk < nchunks) mbar_wait(bar_s + 8 * k, static_cast<unsigned>(chunk / NSLOT) & 1u);
+        slot_s = ring_s + static_cast<unsigned>(k) * kSlotBytes;
+      }
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(vnext.x), "=f"(vnext.y), "=f"(vnext.z), "=f"(vnext.w) : "r"(addr(slot_s, px_in)));
+      feed<S, N>(acc, W, v, m);
+      const int qd = done_slot<S, N>(m);
+      if (qd >= 0) {
+        ++c;
+        if (c >= 0 && c < st.nout && active) *reinterpret_cast<float4 *>(outp) = finish_rgba(acc[qd]);
+        outp += 4;
+      }
+    }
+  }
+}
+
+// Tensor map of an RGBA float image as a 2-D array of floats (4 * width x height), box = 32 floats x 32 rows, 128-byte
+// swizzle.  The encoder is a driver entry point; the library links the runtime only, so it is fetched by name.
+bool make_row_tensor_map(const float *src, int width, int height, CUtensorMap *map) {
+  static PFN_cuTensorMapEncodeTiled encode = [] {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+  }();
+  if (encode == nullptr) return false;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(width) * 4, static_cast<cuuint64_t>(height)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(width) * 16};
+  const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(src), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // ------------------------------------------------------------------------------------------ fused V + H
 // ResizeImage with the SAME integer reduction on both axes (x_factor == y_factor: the reference filters vertically
 // first, resize.c:3854-3861).  The two-pass form moves 36 B per input pixel through HBM (16 + 8 for the vertical pass,
@@ -572,7 +718,23 @@ int launch_sn(StreamArgs a, int axis, cudaStream_t s) {
   a.nstrips = nstrips;
   nstrips += a.nborder;
   if (nstrips <= 0 || nstrips > 65535 || lanes_blocks > 65535) return MB200_EUNSUPPORTED;
-  if (axis == 1) {
+  // default: the TMA-staged ring (measured 8192^2 -> 4096^2: 0.477 vs 0.490 ms for the whole operator, 16384^2 -> 8192^2:
+  // 1.836 vs 1.845 ms; 110 instead of 168 registers; profiles/r02b_resize_tma.md).  0 = the cp.async ring.
+  static const int tma_env = [] { const char *t = std::getenv("MB200_RESIZE_TMA"); return t ? std::atoi(t) : 1; }();
+  CUtensorMap tmap;
+  if (axis == 0 && tma_env != 0 && (reinterpret_cast<uintptr_t>(a.src) & 15) == 0 &&
+      make_row_tensor_map(a.src, a.width, a.height, &tmap)) {
+    // TMA-staged ring: 3 slots x 8 KB per warp, 2 CTAs / SM (tma_env == 2: 2 slots, 3 CTAs / SM)
+    if (tma_env == 2) {
+      constexpr int smem = 4 * 2 * 8192 + 1024;
+      cudaFuncSetAttribute(resize_h_tma_kernel<S, N, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      resize_h_tma_kernel<S, N, 2, 3><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a, tmap);
+    } else {
+      constexpr int smem = 4 * 3 * 8192 + 1024;
+      cudaFuncSetAttribute(resize_h_tma_kernel<S, N, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      resize_h_tma_kernel<S, N, 3, 2><<<dim3(nstrips, lanes_blocks), 128, smem, s>>>(a, tmap);
+    }
+  } else if (axis == 1) {
     resize_v_stream_kernel<S, N><<<dim3(lanes_blocks, nstrips), 128, 0, s>>>(a);
   } else if (chunk_env == 16 && slots_env == 2) {  // experiment: 256-byte chunks, 2-slot rings, 3 CTAs / SM
     constexpr int smem = 4 * 2 * HRing<16>::kSlotBytes;
