@@ -388,6 +388,37 @@ __device__ __forceinline__ double perceptible_reciprocal_d(double x) {       // 
 constexpr double kLuvDen = kIllX + 15.0 * kIllY + 3.0 * kIllZ;
 constexpr double kLuvUn = 4.0 * kIllX / kLuvDen, kLuvVn = 9.0 * kIllY / kLuvDen;
 
+// Lab in unit range (colorspace-private.h:1066-1089) and back (:531-557), for the polar LCHab space
+__device__ __forceinline__ double lab_f(double t) { return t > kCieEps ? cube_root5(t) : (kCieK * t + 16.0) / 116.0; }
+__device__ __forceinline__ void xyz_to_lab_unit(double X, double Y, double Z, double &L, double &a, double &b) {
+  const double x = lab_f(X / kIllX), y = lab_f(Y / kIllY), z = lab_f(Z / kIllZ);
+  L = __dsub_rn(__dmul_rn(116.0, y), 16.0) / 100.0;
+  a = (500.0 * (x - y)) / 255.0 + 0.5;
+  b = (200.0 * (y - z)) / 255.0 + 0.5;
+}
+__device__ __forceinline__ void lab_to_xyz_d(double L, double a, double b, double &X, double &Y, double &Z) {
+  double y = (L + 16.0) / 116.0;
+  double x = y + a / 500.0, z = y - b / 200.0;
+  x = (x * x * x) > kCieEps ? x * x * x : __dsub_rn(__dmul_rn(116.0, x), 16.0) / kCieK;
+  y = L > (kCieK * kCieEps) ? y * y * y : L / kCieK;
+  z = (z * z * z) > kCieEps ? z * z * z : __dsub_rn(__dmul_rn(116.0, z), 16.0) / kCieK;
+  X = kIllX * x; Y = kIllY * y; Z = kIllZ * z;
+}
+__device__ __forceinline__ void xyz_to_luv_unit(double X, double Y, double Z, double &L, double &u, double &v) {
+  double l = Y > kCieEps ? __dsub_rn(__dmul_rn(116.0, cube_root5(Y)), 16.0) : kCieK * Y;
+  const double alpha = perceptible_reciprocal_d(X + 15.0 * Y + 3.0 * Z);
+  const double uu = 13.0 * l * (4.0 * alpha * X - kLuvUn), vv = 13.0 * l * (9.0 * alpha * Y - kLuvVn);
+  L = l / 100.0; u = (uu + 134.0) / 354.0; v = (vv + 140.0) / 262.0;
+}
+__device__ __forceinline__ void luv_to_xyz_d(double L, double u, double v, double &X, double &Y, double &Z) {
+  if (L > (kCieK * kCieEps)) { const double t = (L + 16.0) / 116.0; Y = t * t * t; } else Y = L / kCieK;
+  const double pu = ((52.0 * L * perceptible_reciprocal_d(u + 13.0 * L * kLuvUn)) - 1.0) / 3.0;
+  const double gamma = perceptible_reciprocal_d(pu - (-1.0 / 3.0));
+  X = gamma * ((Y * ((39.0 * L * perceptible_reciprocal_d(v + 13.0 * L * kLuvVn)) - 5.0)) + 5.0 * Y);
+  Z = (X * pu) - 5.0 * Y;
+}
+constexpr double kPiD = 3.14159265358979323846264338327950288419716939937510;
+
 template <int CH>
 __global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npixels, int space, int forward) {
   __shared__ double s_scale[128];
@@ -401,10 +432,53 @@ __global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npix
   else { in0 = q[0]; in1 = q[1]; in2 = q[2]; }
   const int rgb = space == MB200_Adobe98Colorspace ? 0 : space == MB200_DisplayP3Colorspace ? 1 : space == MB200_ProPhotoColorspace ? 2 : -1;
   double o0, o1, o2;
-  if (forward) {
+  if (space == MB200_OklabColorspace || space == MB200_OklchColorspace) {      // colorspace-private.h:1480-1549
+    if (forward) {
+      const double R = QS * decode_pixel_gamma_tab(in0, s_scale), G = QS * decode_pixel_gamma_tab(in1, s_scale),
+                   B = QS * decode_pixel_gamma_tab(in2, s_scale);
+      const double l = cbrt(0.4122214708 * R + 0.5363325363 * G + 0.0514459929 * B);
+      const double m = cbrt(0.2119034982 * R + 0.6806995451 * G + 0.1073969566 * B);
+      const double t = cbrt(0.0883024619 * R + 0.2817188376 * G + 0.6299787005 * B);
+      const double L = 0.2104542553 * l + 0.7936177850 * m - 0.0040720468 * t;
+      double a = 1.9779984951 * l - 2.4285922050 * m + 0.4505937099 * t + 0.5;
+      double b = 0.0259040371 * l + 0.7827717662 * m - 0.8086757660 * t + 0.5;
+      if (space == MB200_OklchColorspace) {
+        const double C = sqrt(a * a + b * b), h = 0.5 + 0.5 * atan2(-b, -a) / kPiD;
+        a = C; b = h;
+      }
+      o0 = QR * L; o1 = QR * a; o2 = QR * b;
+    } else {
+      const double L = QS * static_cast<double>(in0);
+      double a = QS * static_cast<double>(in1), b = QS * static_cast<double>(in2);
+      if (space == MB200_OklchColorspace) {
+        const double C = a, h = b;
+        a = C * cos(2.0 * kPiD * h); b = C * sin(2.0 * kPiD * h);
+      }
+      double l = L + 0.3963377774 * (a - 0.5) + 0.2158037573 * (b - 0.5);
+      double m = L - 0.1055613458 * (a - 0.5) - 0.0638541728 * (b - 0.5);
+      double t = L - 0.0894841775 * (a - 0.5) - 1.2914855480 * (b - 0.5);
+      l *= l * l; m *= m * m; t *= t * t;
+      o0 = encode_pixel_gamma(QR * (4.0767416621 * l - 3.3077115913 * m + 0.2309699292 * t));
+      o1 = encode_pixel_gamma(QR * (-1.2684380046 * l + 2.6097574011 * m - 0.3413193965 * t));
+      o2 = encode_pixel_gamma(QR * (-0.0041960863 * l - 0.7034186147 * m + 1.7076147010 * t));
+    }
+  } else if (forward) {
     double X, Y, Z, a, b, c;
     rgb_to_xyz(in0, in1, in2, X, Y, Z, s_scale);
-    if (rgb >= 0) {
+    if (space == MB200_LCHColorspace || space == MB200_LCHabColorspace) {       // :1104-1117
+      double la, lb;
+      xyz_to_lab_unit(X, Y, Z, a, la, lb);
+      b = hypot(la - 0.5, lb - 0.5) + 0.5;
+      c = 180.0 * atan2(lb - 0.5, la - 0.5) / kPiD / 360.0;
+      if (c < 0.0) c += 1.0;
+    } else if (space == MB200_LCHuvColorspace) {                               // :1163-1176
+      double u, v;
+      xyz_to_luv_unit(X, Y, Z, a, u, v);
+      const double du = 354.0 * u - 134.0, dv = 262.0 * v - 140.0;
+      b = hypot(du, dv) / 255.0 + 0.5;
+      c = 180.0 * atan2(dv, du) / kPiD / 360.0;
+      if (c < 0.0) c += 1.0;
+    } else if (rgb >= 0) {
       mul3(kx.to_rgb[rgb], X, Y, Z, a, b, c);
       a = QS * encode_pixel_gamma(QR * a); b = QS * encode_pixel_gamma(QR * b); c = QS * encode_pixel_gamma(QR * c);
     } else if (space == MB200_LMSColorspace) {
@@ -417,16 +491,18 @@ __global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npix
       const double gamma = perceptible_reciprocal_d(X + Y + Z);
       a = gamma * X; b = gamma * Y; c = Y;
     } else {                                                       // Luv
-      double L = Y > kCieEps ? __dsub_rn(__dmul_rn(116.0, cube_root5(Y)), 16.0) : kCieK * Y;
-      const double alpha = perceptible_reciprocal_d(X + 15.0 * Y + 3.0 * Z);
-      const double u = 13.0 * L * (4.0 * alpha * X - kLuvUn), v = 13.0 * L * (9.0 * alpha * Y - kLuvVn);
-      a = L / 100.0; b = (u + 134.0) / 354.0; c = (v + 140.0) / 262.0;
+      xyz_to_luv_unit(X, Y, Z, a, b, c);
     }
     o0 = QR * a; o1 = QR * b; o2 = QR * c;
   } else {
     const double a = QS * static_cast<double>(in0), b = QS * static_cast<double>(in1), c = QS * static_cast<double>(in2);
     double X, Y, Z;
-    if (rgb >= 0) {
+    if (space == MB200_LCHColorspace || space == MB200_LCHabColorspace || space == MB200_LCHuvColorspace) {   // :572-653
+      const double luma = 100.0 * a, chroma = 255.0 * (b - 0.5), rad = kPiD * (360.0 * c) / 180.0;
+      const double p = chroma * cos(rad), q2 = chroma * sin(rad);
+      if (space == MB200_LCHuvColorspace) luv_to_xyz_d(luma, p, q2, X, Y, Z);
+      else lab_to_xyz_d(luma, p, q2, X, Y, Z);
+    } else if (rgb >= 0) {
       const double r = QS * decode_pixel_gamma_tab(QR * a, s_scale), g = QS * decode_pixel_gamma_tab(QR * b, s_scale),
                    bl = QS * decode_pixel_gamma_tab(QR * c, s_scale);
       mul3(kx.to_xyz[rgb], r, g, bl, X, Y, Z);
@@ -440,12 +516,7 @@ __global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npix
       const double gamma = perceptible_reciprocal_d(b);
       X = gamma * c * a; Y = c; Z = gamma * c * (1.0 - a - b);
     } else {                                                       // Luv
-      const double L = 100.0 * a, u = 354.0 * b - 134.0, v = 262.0 * c - 140.0;
-      if (L > (kCieK * kCieEps)) { const double t = (L + 16.0) / 116.0; Y = t * t * t; } else Y = L / kCieK;
-      const double pu = ((52.0 * L * perceptible_reciprocal_d(u + 13.0 * L * kLuvUn)) - 1.0) / 3.0;
-      const double gamma = perceptible_reciprocal_d(pu - (-1.0 / 3.0));
-      X = gamma * ((Y * ((39.0 * L * perceptible_reciprocal_d(v + 13.0 * L * kLuvVn)) - 5.0)) + 5.0 * Y);
-      Z = (X * pu) - 5.0 * Y;
+      luv_to_xyz_d(100.0 * a, 354.0 * b - 134.0, 262.0 * c - 140.0, X, Y, Z);
     }
     xyz_to_rgb(X, Y, Z, o0, o1, o2);
   }
@@ -454,6 +525,9 @@ __global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npix
 }
 
 bool is_xyz_family(int cs) {
+  if (cs == MB200_LCHColorspace || cs == MB200_LCHabColorspace || cs == MB200_LCHuvColorspace || cs == MB200_OklabColorspace ||
+      cs == MB200_OklchColorspace)
+    return true;
   return cs == MB200_Adobe98Colorspace || cs == MB200_DisplayP3Colorspace || cs == MB200_ProPhotoColorspace ||
          cs == MB200_LMSColorspace || cs == MB200_CAT02LMSColorspace || cs == MB200_xyYColorspace || cs == MB200_LuvColorspace;
 }

@@ -408,6 +408,11 @@ static int map_colorspace(ColorspaceType c)
     case YIQColorspace: return MB200_YIQColorspace;
     case YPbPrColorspace: return MB200_YPbPrColorspace;
     case YUVColorspace: return MB200_YUVColorspace;
+    case LCHColorspace: return MB200_LCHColorspace;
+    case LCHabColorspace: return MB200_LCHabColorspace;
+    case LCHuvColorspace: return MB200_LCHuvColorspace;
+    case OklabColorspace: return MB200_OklabColorspace;
+    case OklchColorspace: return MB200_OklchColorspace;
     case LMSColorspace: return MB200_LMSColorspace;
     case LuvColorspace: return MB200_LuvColorspace;
     case xyYColorspace: return MB200_xyYColorspace;

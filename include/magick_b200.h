@@ -97,6 +97,9 @@ typedef enum {
   MB200_HSVColorspace = 9,
   MB200_HWBColorspace = 10,
   MB200_LabColorspace = 11,
+  MB200_LCHColorspace = 12,           /* polar Lab (alias of LCHab) and Luv: the hue of an achromatic pixel is */
+  MB200_LCHabColorspace = 13,         /* rounding noise in the reference as well                               */
+  MB200_LCHuvColorspace = 14,
   MB200_LMSColorspace = 16,           /* XYZ-derived spaces of the generic branch: <= 1 ULP */
   MB200_LuvColorspace = 17,
   MB200_OHTAColorspace = 18,          /* LUT branch, colorspace.c:1229-1494 */
@@ -114,6 +117,8 @@ typedef enum {
   MB200_DisplayP3Colorspace = 35,
   MB200_Adobe98Colorspace = 36,
   MB200_ProPhotoColorspace = 37,
+  MB200_OklabColorspace = 38,
+  MB200_OklchColorspace = 39,
   MB200_CAT02LMSColorspace = 40
 } mb200_colorspace;
 

@@ -1726,8 +1726,42 @@ static void luv_to_xyz(double L, double u, double v, double *X, double *Y, doubl
   *Z = (*X * (((52.0 * L * precip(u + 13.0 * L * LUV_UN)) - 1.0) / 3.0)) - 5.0 * (*Y);
 }
 
+/* Oklab / Oklch (colorspace-private.h:1480-1549): cube roots of an LMS-like matrix of linear RGB; the polar form is taken
+   of the OFFSET a, b (0.5 + ...), so the hue of an achromatic pixel is atan2(-0.5, -0.5), not noise */
+static void rgb_to_oklab(double red, double green, double blue, double *L, double *a, double *b)
+{
+  double B, G, l, m, R, s;
+  R = QS * decode_pixel_gamma(red);
+  G = QS * decode_pixel_gamma(green);
+  B = QS * decode_pixel_gamma(blue);
+  l = cbrt(0.4122214708 * R + 0.5363325363 * G + 0.0514459929 * B);
+  m = cbrt(0.2119034982 * R + 0.6806995451 * G + 0.1073969566 * B);
+  s = cbrt(0.0883024619 * R + 0.2817188376 * G + 0.6299787005 * B);
+  *L = 0.2104542553 * l + 0.7936177850 * m - 0.0040720468 * s;
+  *a = 1.9779984951 * l - 2.4285922050 * m + 0.4505937099 * s + 0.5;
+  *b = 0.0259040371 * l + 0.7827717662 * m - 0.8086757660 * s + 0.5;
+}
+static void oklab_to_rgb(double L, double a, double b, double *red, double *green, double *blue)
+{
+  double B, G, l, m, R, s;
+  l = L + 0.3963377774 * (a - 0.5) + 0.2158037573 * (b - 0.5);
+  m = L - 0.1055613458 * (a - 0.5) - 0.0638541728 * (b - 0.5);
+  s = L - 0.0894841775 * (a - 0.5) - 1.2914855480 * (b - 0.5);
+  l *= l * l;
+  m *= m * m;
+  s *= s * s;
+  R = 4.0767416621 * l - 3.3077115913 * m + 0.2309699292 * s;
+  G = (-1.2684380046) * l + 2.6097574011 * m - 0.3413193965 * s;
+  B = (-0.0041960863) * l - 0.7034186147 * m + 1.7076147010 * s;
+  *red = encode_pixel_gamma(QR * R);
+  *green = encode_pixel_gamma(QR * G);
+  *blue = encode_pixel_gamma(QR * B);
+}
+static double degrees_to_radians(double degrees) { return (double) (PI_ * degrees / 180.0); }   /* image-private.h:142 */
+
 static int is_xyz_family_space(int cs)
 {
+  if (cs == ORC_CS_OKLAB || cs == ORC_CS_OKLCH || cs == ORC_CS_LCH || cs == ORC_CS_LCHAB || cs == ORC_CS_LCHUV) return 1;
   return cs == ORC_CS_ADOBE98 || cs == ORC_CS_DISPLAYP3 || cs == ORC_CS_PROPHOTO || cs == ORC_CS_LMS ||
          cs == ORC_CS_CAT02LMS || cs == ORC_CS_XYY || cs == ORC_CS_LUV;
 }
@@ -1740,9 +1774,47 @@ static int colorspace_xyz_family_leg(float *buf, long n, int ch, int cs, int for
   for (i = 0; i < n; i++) {
     float *q = buf + (size_t) i * ch;
     double X, Y, Z, a, b, c;
+    if (cs == ORC_CS_OKLAB || cs == ORC_CS_OKLCH) {          /* not routed through XYZ */
+      if (forward) {
+        rgb_to_oklab((double) q[0], (double) q[1], (double) q[2], &a, &b, &c);
+        if (cs == ORC_CS_OKLCH) {                            /* :1539-1549 */
+          const double C = sqrt(b * b + c * c), h = 0.5 + 0.5 * atan2(-c, -b) / PI_;
+          b = C; c = h;
+        }
+        q[0] = (float) (QR * a); q[1] = (float) (QR * b); q[2] = (float) (QR * c);
+      } else {
+        double R, G, B;
+        a = QS * q[0]; b = QS * q[1]; c = QS * q[2];
+        if (cs == ORC_CS_OKLCH) {                            /* :1527-1537 */
+          const double ca = b * cos(2.0 * PI_ * c), cb = b * sin(2.0 * PI_ * c);
+          b = ca; c = cb;
+        }
+        oklab_to_rgb(a, b, c, &R, &G, &B);
+        q[0] = (float) R; q[1] = (float) G; q[2] = (float) B;
+      }
+      continue;
+    }
     if (forward) {                       /* ConvertRGBToGeneric :411 -> (float) (QR * component) */
       rgb_to_xyz((double) q[0], (double) q[1], (double) q[2], &X, &Y, &Z);
       switch (cs) {
+        case ORC_CS_LCH: case ORC_CS_LCHAB: {                /* :1104-1117: polar Lab */
+          double L, la, lb;
+          xyz_to_lab(X, Y, Z, &L, &la, &lb);
+          a = L;
+          b = hypot(la - 0.5, lb - 0.5) / 1.0 + 0.5;
+          c = 180.0 * atan2(lb - 0.5, la - 0.5) / PI_ / 360.0;
+          if (c < 0.0) c += 1.0;
+          break;
+        }
+        case ORC_CS_LCHUV: {                                 /* :1163-1176: polar Luv */
+          double L, u, v;
+          xyz_to_luv(X, Y, Z, &L, &u, &v);
+          a = L;
+          b = hypot(354.0 * u - 134.0, 262.0 * v - 140.0) / 255.0 + 0.5;
+          c = 180.0 * atan2(262.0 * v - 140.0, 354.0 * u - 134.0) / PI_ / 360.0;
+          if (c < 0.0) c += 1.0;
+          break;
+        }
         case ORC_CS_ADOBE98: case ORC_CS_DISPLAYP3: case ORC_CS_PROPHOTO: {
           const mat3 *m = cs == ORC_CS_ADOBE98 ? &xyz_to_adobe98 : cs == ORC_CS_DISPLAYP3 ? &xyz_to_displayp3 : &xyz_to_prophoto;
           a = QS * encode_pixel_gamma(QR * row3(m->m[0], X, Y, Z));
@@ -1764,6 +1836,16 @@ static int colorspace_xyz_family_leg(float *buf, long n, int ch, int cs, int for
           const mat3 *m = cs == ORC_CS_ADOBE98 ? &adobe98_to_xyz : cs == ORC_CS_DISPLAYP3 ? &displayp3_to_xyz : &prophoto_to_xyz;
           const double r = QS * decode_pixel_gamma(QR * a), g = QS * decode_pixel_gamma(QR * b), bl = QS * decode_pixel_gamma(QR * c);
           X = row3(m->m[0], r, g, bl); Y = row3(m->m[1], r, g, bl); Z = row3(m->m[2], r, g, bl);
+          break;
+        }
+        case ORC_CS_LCH: case ORC_CS_LCHAB: {                /* :572-598 */
+          const double luma = 100.0 * a, chroma = 255.0 * (b - 0.5), hue = 360.0 * c;
+          lab_to_xyz(luma, chroma * cos(degrees_to_radians(hue)), chroma * sin(degrees_to_radians(hue)), &X, &Y, &Z);
+          break;
+        }
+        case ORC_CS_LCHUV: {                                 /* :627-653 */
+          const double luma = 100.0 * a, chroma = 255.0 * (b - 0.5), hue = 360.0 * c;
+          luv_to_xyz(luma, chroma * cos(degrees_to_radians(hue)), chroma * sin(degrees_to_radians(hue)), &X, &Y, &Z);
           break;
         }
         case ORC_CS_LMS: lms_to_xyz(a, b, c, &X, &Y, &Z); break;

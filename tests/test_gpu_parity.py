@@ -410,7 +410,21 @@ def test_hexcone_colorspaces(cs, kind):
     assert max_ulp(h.pixels, want) <= bar
 
 
-XYZ_FAMILY = [16, 17, 25, 35, 36, 37, 40]      # LMS, Luv, xyY, DisplayP3, Adobe98, ProPhoto, CAT02LMS
+XYZ_FAMILY = [12, 13, 14, 16, 17, 25, 35, 36, 37, 38, 39, 40]   # LCH, LCHab, LCHuv, LMS, Luv, xyY, DisplayP3, Adobe98, ProPhoto, Oklab, Oklch, CAT02LMS
+POLAR = (12, 13, 14)                            # hue = atan2 of two differences that cancel for achromatic pixels
+
+
+def _mask_achromatic_hue(got, want, to):
+    """LCHab / LCHuv: where the chroma is rounding noise (|C - 0.5| < 1e-9 of the range) the reference's hue is the atan2 of
+    two residues of the XYZ chain -- arbitrary, and only a bit-identical chain (glibc pow included) reproduces it."""
+    if to not in POLAR:
+        return got, want
+    got, want = got.copy(), want.copy()
+    achromatic = np.abs(want[..., 1].astype(np.float64) - 32767.5) < 1.0e-4
+    got[..., 2] = np.where(achromatic, np.float32(0), got[..., 2])
+    want[..., 2] = np.where(achromatic, np.float32(0), want[..., 2])
+    return got, want
+
 
 
 @pytest.mark.parametrize("cs", XYZ_FAMILY)
@@ -420,13 +434,13 @@ def test_xyz_family_colorspaces(cs, kind):
     smooth functions of the sample, <= 1 ULP like the Lab / XYZ legs they are built from."""
     for ch in (3, 4):
         src = _hexcone_image(131, 67, ch, kind, seed=120 + cs)
-        for frm, to in ((23, cs), (cs, 23), (cs, 17 if cs != 17 else 25), (11, cs)):
+        for frm, to in ((23, cs), (cs, 23), (cs, 17 if cs != 17 else 25), (11, cs if cs not in POLAR else 17)):
             want = src.copy()
             assert oracle().orc_colorspace(P(want), 131, 67, ch, frm, to) == 0
             img = _dev(src.copy())
             img.colorspace = frm
             assert im.TransformImageColorspace(img, to) is True and img.colorspace == to
-            got = _host(img)
+            got, want = _mask_achromatic_hue(_host(img), want, to)
             ok = np.isfinite(want)
             assert np.array_equal(np.isfinite(got), ok), (ch, frm, to)
             d = util.ulp_or_noise(np.where(ok, got, np.float32(0)), np.where(ok, want, np.float32(0)))

@@ -218,7 +218,7 @@ def test_hexcone_colorspaces_bit_exact(cs, kind):
         assert max_ulp(np.where(ok, a, np.float32(0)), np.where(ok, b, np.float32(0))) == 0, (frm, to)
 
 
-XYZ_FAMILY = [16, 17, 25, 35, 36, 37, 40]      # LMS, Luv, xyY, DisplayP3, Adobe98, ProPhoto, CAT02LMS
+XYZ_FAMILY = [12, 13, 14, 16, 17, 25, 35, 36, 37, 38, 39, 40]   # LCH, LCHab, LCHuv, LMS, Luv, xyY, DisplayP3, Adobe98, ProPhoto, Oklab, Oklch, CAT02LMS
 
 
 @pytest.mark.parametrize("cs", XYZ_FAMILY)
