@@ -157,16 +157,21 @@ std::string lower(std::string s) {
   return s;
 }
 
+void rotate_kernel(mb200_kernel_info *k, double angle);
+void expand_rotated(mb200_kernel_info *kernel, double angle);
+void expand_mirrored(mb200_kernel_info *kernel);
+
 // morphology.c:213 ParseKernelArray: "WxH+X+Y:v,v,.." or old style "v,v,v,..."
 mb200_kernel_info *parse_user_kernel(const std::string &def) {
   std::string body = def;
+  int expand = 0;                                        // '@' / '>' / '<' in the size part (:361-366)
   size_t w = 0, h = 0; long ox = -1, oy = -1;
   const size_t colon = def.find(':');
   bool have_geometry = false;
   if (colon != std::string::npos) {
     Geometry g = parse_geometry(def.substr(0, colon));
     if (!g.ok) return nullptr;
-    if (g.area || g.greater || g.less) return nullptr;   // rotation expansion: not supported
+    expand = g.area ? 1 : g.greater ? 2 : g.less ? 3 : 0;
     if (!g.has_rho) g.rho = g.sigma;
     if (g.rho < 1.0) g.rho = 1.0;
     if (g.sigma < 1.0) g.sigma = g.rho;
@@ -217,6 +222,9 @@ mb200_kernel_info *parse_user_kernel(const std::string &def) {
     if (vals[n] > k->maximum) k->maximum = vals[n];
   }
   if (!any) { mb200_destroy_kernel_info(k); return nullptr; }
+  if (expand == 1) expand_rotated(k, 45.0);
+  else if (expand == 2) expand_rotated(k, 90.0);
+  else if (expand == 3) expand_mirrored(k);
   return k;
 }
 
@@ -226,7 +234,14 @@ const NamedKernel kNames[] = {
   {"log", MB200_LoGKernel}, {"disk", MB200_DiskKernel}, {"square", MB200_SquareKernel},
   {"diamond", MB200_DiamondKernel}, {"octagon", MB200_OctagonKernel}, {"plus", MB200_PlusKernel},
   {"cross", MB200_CrossKernel}, {"rectangle", MB200_RectangleKernel}, {"unity", MB200_UnityKernel},
-  {"binomial", MB200_BinomialKernel},
+  {"binomial", MB200_BinomialKernel}, {"comet", MB200_CometKernel}, {"laplacian", MB200_LaplacianKernel},
+  {"sobel", MB200_SobelKernel}, {"freichen", MB200_FreiChenKernel}, {"roberts", MB200_RobertsKernel},
+  {"prewitt", MB200_PrewittKernel}, {"compass", MB200_CompassKernel}, {"kirsch", MB200_KirschKernel},
+  {"ring", MB200_RingKernel}, {"peaks", MB200_PeaksKernel}, {"edges", MB200_EdgesKernel},
+  {"corners", MB200_CornersKernel}, {"diagonals", MB200_DiagonalsKernel}, {"lineends", MB200_LineEndsKernel},
+  {"linejunctions", MB200_LineJunctionsKernel}, {"ridges", MB200_RidgesKernel}, {"convexhull", MB200_ConvexHullKernel},
+  {"thinse", MB200_ThinSEKernel}, {"skeleton", MB200_SkeletonKernel}, {"chebyshev", MB200_ChebyshevKernel},
+  {"manhattan", MB200_ManhattanKernel}, {"octagonal", MB200_OctagonalKernel}, {"euclidean", MB200_EuclideanKernel},
 };
 
 // morphology.c:372 ParseKernelName (+ the per-type argument defaults :426-470)
@@ -237,15 +252,23 @@ mb200_kernel_info *parse_named_kernel(const std::string &def, bool *was_named) {
   while (j < def.size() && std::isalpha(static_cast<unsigned char>(def[j]))) ++j;
   const std::string name = lower(def.substr(i, j - i));
   int type = -1;
-  for (const NamedKernel &n : kNames) if (name == n.name) type = n.type;
+  // GetNextToken ends the name at white space, ',' or ':' only: "Sobel@" is one token and names no kernel (:395-398)
+  const bool clean_end = j >= def.size() || std::isspace(static_cast<unsigned char>(def[j])) || def[j] == ',' || def[j] == ':';
+  if (clean_end)
+    for (const NamedKernel &n : kNames) if (name == n.name) type = n.type;
   *was_named = (type >= 0);
   if (type < 0) return nullptr;
   while (j < def.size() && (std::isspace(static_cast<unsigned char>(def[j])) || def[j] == ',' || def[j] == ':')) ++j;
   Geometry g = parse_geometry(def.substr(j));
   if (!g.ok) return nullptr;
-  if (g.area || g.greater || g.less) return nullptr;     // rotated kernel lists: unsupported
   switch (type) {
     case MB200_UnityKernel: if (!g.has_rho) g.rho = 1.0; break;
+    case MB200_RingKernel: if (!g.has_xi) g.xi = 1.0; break;
+    case MB200_ChebyshevKernel: case MB200_ManhattanKernel: case MB200_OctagonalKernel: case MB200_EuclideanKernel:
+      if (!g.has_sigma) g.sigma = 100.0;                              // default distance scale (:453-464)
+      else if (g.aspect) g.sigma = 65535.0 / (g.sigma + 1);           // '!': the maximum pixel distance
+      else if (g.percent) g.sigma *= 65535.0 / 100.0;                 // '%' of the colour range
+      break;
     case MB200_SquareKernel: case MB200_DiamondKernel: case MB200_OctagonKernel:
     case MB200_DiskKernel: case MB200_PlusKernel: case MB200_CrossKernel:
       if (!g.has_sigma) g.sigma = 1.0; break;
@@ -258,7 +281,13 @@ mb200_kernel_info *parse_named_kernel(const std::string &def, bool *was_named) {
       break;
     default: break;
   }
-  return mb200_acquire_kernel_builtin(type, g.rho, g.sigma, g.xi, g.psi);
+  mb200_kernel_info *k = mb200_acquire_kernel_builtin(type, g.rho, g.sigma, g.xi, g.psi);
+  if (k && k->next == nullptr) {                         // '@' '>' '<': rotated / mirrored lists of a single kernel (:473-481)
+    if (g.area) expand_rotated(k, 45.0);
+    else if (g.greater) expand_rotated(k, 90.0);
+    else if (g.less) expand_mirrored(k);
+  }
+  return k;
 }
 
 // RotateKernelInfo (morphology.c:4258) as what it amounts to for the angles the hot path uses: a rotation by q quarter
@@ -272,17 +301,38 @@ mb200_kernel_info *parse_named_kernel(const std::string &def, bool *was_named) {
 void rotate_kernel(mb200_kernel_info *k, double angle) {
   angle = std::fmod(angle, 360.0);
   if (angle < 0) angle += 360.0;
-  int q = angle > 45.0 && angle <= 135.0 ? 1 : angle > 135.0 && angle <= 225.0 ? 2 : angle > 225.0 && angle <= 315.0 ? 3 : 0;
-  switch (k->type) {
+  if (337.5 < angle || angle <= 22.5) return;
+  switch (k->type) {                                       // cylindrical / fourfold-symmetric built-ins never turn (:4281-4305)
     case MB200_GaussianKernel: case MB200_DoGKernel: case MB200_LoGKernel: case MB200_DiskKernel:
+    case MB200_PeaksKernel: case MB200_LaplacianKernel: case MB200_ChebyshevKernel: case MB200_ManhattanKernel:
+    case MB200_EuclideanKernel:
     case MB200_SquareKernel: case MB200_DiamondKernel: case MB200_PlusKernel: case MB200_CrossKernel:
       return;
     case MB200_BlurKernel:
-      if (q == 2) return;
-      if (q == 3) q = 1;
+      if (135.0 < angle && angle <= 225.0) return;
+      if (225.0 < angle && angle <= 315.0) angle -= 180;
       break;
     default: break;
   }
+  // An eighth of a turn exists for 3x3 kernels only (:4307-4340): the eight perimeter cells -- and an origin that sits
+  // on the perimeter -- move one place clockwise along the ring.
+  const double within = std::fmod(angle, 90.0);
+  if (22.5 < within && within <= 67.5) {
+    if (k->width == 3 && k->height == 3) {
+      static const int ring[8] = {0, 1, 2, 5, 8, 7, 6, 3};
+      double old[9];
+      for (int i = 0; i < 9; ++i) old[i] = k->values[i];
+      for (int i = 0; i < 8; ++i) k->values[ring[(i + 1) % 8]] = old[ring[i]];
+      const int at = static_cast<int>(k->x + 3 * k->y);
+      if (at != 4)
+        for (int i = 0; i < 8; ++i)
+          if (ring[i] == at) { const int to = ring[(i + 1) % 8]; k->x = to % 3; k->y = to / 3; break; }
+      angle = std::fmod(angle + 315.0, 360.0);
+      k->angle = std::fmod(k->angle + 45.0, 360.0);
+    }
+    // (any other size: the reference prints a complaint and goes on with the quarter turns)
+  }
+  int q = angle > 45.0 && angle <= 135.0 ? 1 : angle > 135.0 && angle <= 225.0 ? 2 : angle > 225.0 && angle <= 315.0 ? 3 : 0;
   const long W = static_cast<long>(k->width), H = static_cast<long>(k->height);
   if ((q & 1) && W != H && W != 1 && H != 1) return;        // the reference cannot turn such a kernel either
   if (q == 0) return;
@@ -303,6 +353,150 @@ void rotate_kernel(mb200_kernel_info *k, double angle) {
   k->width = static_cast<size_t>(Wn);
   k->height = static_cast<size_t>(Hn);
   k->angle = std::fmod(k->angle + 90.0 * q, 360.0);
+}
+
+void rotate_list(mb200_kernel_info *k, double angle) { for (; k; k = k->next) rotate_kernel(k, angle); }
+mb200_kernel_info *last_of(mb200_kernel_info *k) { while (k->next) k = k->next; return k; }
+
+// SameKernelInfo (:2396): same geometry, NaN in the same cells, values within MagickEpsilon
+bool same_kernel(const mb200_kernel_info *a, const mb200_kernel_info *b) {
+  if (a->width != b->width || a->height != b->height || a->x != b->x || a->y != b->y) return false;
+  for (size_t i = 0; i < a->width * a->height; ++i) {
+    const bool na = std::isnan(a->values[i]), nb = std::isnan(b->values[i]);
+    if (na != nb) return false;
+    if (!na && std::fabs(a->values[i] - b->values[i]) >= kEps) return false;
+  }
+  return true;
+}
+
+// ExpandRotateKernelInfo (:2424): append turned copies of the LAST element (the clone carries the rest of the list with
+// it, like CloneKernelInfo) until a turn reproduces the first kernel.
+void expand_rotated(mb200_kernel_info *kernel, double angle) {
+  mb200_kernel_info *last = kernel;
+  for (int guard = 0; guard < 64; ++guard) {
+    mb200_kernel_info *turned = mb200_clone_kernel_info(last);
+    if (!turned) return;
+    rotate_list(turned, angle);
+    if (same_kernel(kernel, turned)) { mb200_destroy_kernel_info(turned); return; }
+    last_of(last)->next = turned;
+    last = turned;
+  }
+}
+
+// ExpandMirrorKernelInfo (:2332): the kernel, its half turn, that one's quarter turn, and the half turn of the latter
+void expand_mirrored(mb200_kernel_info *kernel) {
+  mb200_kernel_info *last = kernel;
+  for (double angle : {180.0, 90.0, 180.0}) {
+    mb200_kernel_info *c = mb200_clone_kernel_info(last);
+    if (!c) return;
+    rotate_list(c, angle);
+    last_of(last)->next = c;
+    last = c;
+  }
+}
+
+// ---- kernels the reference defines by a literal array (morphology.c:1333-1535, :1748-2088): the strings are data -------
+mb200_kernel_info *from_array(int type, const char *text) {
+  mb200_kernel_info *k = parse_user_kernel(text);
+  if (k) k->type = type;
+  return k;
+}
+mb200_kernel_info *list_of(int type, std::initializer_list<const char *> texts) {
+  mb200_kernel_info *head = nullptr;
+  for (const char *t : texts) {
+    mb200_kernel_info *k = from_array(type, t);
+    if (!k) { mb200_destroy_kernel_info(head); return nullptr; }
+    if (!head) head = k; else last_of(head)->next = k;
+  }
+  return head;
+}
+void retype(mb200_kernel_info *k, int type) { for (; k; k = k->next) k->type = type; }
+
+const char *laplacian_array(int which) {
+  switch (which) {
+    case 1: return "3: 0,-1,0  -1,4,-1  0,-1,0";
+    case 2: return "3: -2,1,-2  1,4,1  -2,1,-2";
+    case 3: return "3: 1,-2,1  -2,4,-2  1,-2,1";
+    case 5: return "5: -4,-1,0,-1,-4  -1,2,3,2,-1  0,3,4,3,0  -1,2,3,2,-1  -4,-1,0,-1,-4";
+    case 7: return "7:-10,-5,-2,-1,-2,-5,-10 -5,0,3,4,3,0,-5 -2,3,6,7,6,3,-2 -1,4,7,8,7,4,-1 -2,3,6,7,6,3,-2 -5,0,3,4,3,0,-5 -10,-5,-2,-1,-2,-5,-10";
+    case 15: return "5: 0,0,-1,0,0  0,-1,-2,-1,0  -1,-2,16,-2,-1  0,-1,-2,-1,0  0,0,-1,0,0";
+    case 19: return "9: 0,-1,-1,-2,-2,-2,-1,-1,0  -1,-2,-4,-5,-5,-5,-4,-2,-1  -1,-4,-5,-3,-0,-3,-5,-4,-1  -2,-5,-3,12,24,12,-3,-5,-2  -2,-5,-0,24,40,24,-0,-5,-2  -2,-5,-3,12,24,12,-3,-5,-2  -1,-4,-5,-3,-0,-3,-5,-4,-1  -1,-2,-4,-5,-5,-5,-4,-2,-1  0,-1,-1,-2,-2,-2,-1,-1,0";
+    default: return "3: -1,-1,-1  -1,8,-1  -1,-1,-1";
+  }
+}
+const char *thin_se_array(int which) {            // Bloomberg's structuring elements (:1998-2088)
+  switch (which) {
+    case 41: return "3: -,-,1  0,-,1  -,-,1";
+    case 42: return "3: -,-,1  0,-,1  -,0,-";
+    case 43: return "3: -,0,-  0,-,1  -,-,1";
+    case 44: return "3: -,0,-  0,-,1  -,0,-";
+    case 45: return "3: -,0,1  0,-,1  -,0,-";
+    case 46: return "3: -,0,-  0,-,1  -,0,1";
+    case 47: return "3: -,1,1  0,-,1  -,0,-";
+    case 48: return "3: -,-,1  0,-,1  0,-,1";
+    case 49: return "3: 0,-,1  0,-,1  -,-,1";
+    case 81: return "3: -,1,-  0,-,1  -,1,-";
+    case 82: return "3: -,1,-  0,-,1  0,-,-";
+    case 83: return "3: 0,-,-  0,-,1  -,1,-";
+    case 84: return "3: 0,-,-  0,-,1  0,-,-";
+    case 85: return "3: 0,-,1  0,-,1  0,-,-";
+    case 86: return "3: 0,-,-  0,-,1  0,-,1";
+    case 87: return "3: -,1,-  0,-,1  0,0,-";
+    case 88: return "3: -,1,-  0,-,1  0,1,-";
+    case 89: return "3: 0,1,-  0,-,1  -,1,-";
+    case 423: return "3: -,-,1  0,-,-  -,0,-";
+    case 823: return "3: -,1,-  -,-,1  0,-,-";
+    case 481: return "3: -,1,1  0,-,1  0,0,-";
+    default: return "3: 0,-,1  0,-,1  0,-,1";     // 482, the general edge element
+  }
+}
+mb200_kernel_info *thin_se(int which, double angle, int type) {
+  mb200_kernel_info *k = from_array(MB200_ThinSEKernel, thin_se_array(which));
+  if (k) { rotate_kernel(k, angle); k->type = type; }
+  return k;
+}
+
+// FreiChen (:1416-1535): Sobel-like arrays with sqrt(2) written into some cells, most of them rescaled
+mb200_kernel_info *frei_chen(double rho, double sigma) {
+  constexpr double kSq2 = 1.41421356237309504880168872420969807856967187537695;
+  const int which = static_cast<int>(rho);
+  struct Variant { const char *text; int plus[2], minus[2]; double scale; };
+  auto build = [&](const Variant &v) -> mb200_kernel_info * {
+    mb200_kernel_info *k = from_array(MB200_FreiChenKernel, v.text);
+    if (!k) return nullptr;
+    bool touched = false;
+    for (int c : v.plus) if (c >= 0) { k->values[c] = +kSq2; touched = true; }
+    for (int c : v.minus) if (c >= 0) { k->values[c] = -kSq2; touched = true; }
+    if (touched) calc_meta(k);
+    if (v.scale != 0.0) mb200_scale_kernel_info(k, v.scale, 0);
+    return k;
+  };
+  mb200_kernel_info *k = nullptr;
+  switch (which) {
+    case 2: k = build({"3: 1,2,0  2,0,-2  0,-2,-1", {1, 3}, {5, 7}, 1.0 / 2.0 * kSq2}); break;
+    case 10: {
+      for (int v = 11; v <= 19; ++v) {
+        mb200_kernel_info *one = frei_chen(static_cast<double>(v), 0.0);
+        if (!one) { mb200_destroy_kernel_info(k); return nullptr; }
+        if (!k) k = one; else last_of(k)->next = one;
+      }
+      break;
+    }
+    case 1: case 11: k = build({"3: 1,0,-1  2,0,-2  1,0,-1", {3, -1}, {5, -1}, 1.0 / 2.0 * kSq2}); break;
+    case 12: k = build({"3: 1,2,1  0,0,0  1,2,1", {1, 7}, {-1, -1}, 1.0 / 2.0 * kSq2}); break;
+    case 13: k = build({"3: 2,-1,0  -1,0,1  0,1,-2", {0, -1}, {8, -1}, 1.0 / 2.0 * kSq2}); break;
+    case 14: k = build({"3: 0,1,-2  -1,0,1  2,-1,0", {6, -1}, {2, -1}, 1.0 / 2.0 * kSq2}); break;
+    case 15: k = build({"3: 0,-1,0  1,0,1  0,-1,0", {-1, -1}, {-1, -1}, 1.0 / 2.0}); break;
+    case 16: k = build({"3: 1,0,-1  0,0,0  -1,0,1", {-1, -1}, {-1, -1}, 1.0 / 2.0}); break;
+    case 17: k = build({"3: 1,-2,1  -2,4,-2  -1,-2,1", {-1, -1}, {-1, -1}, 1.0 / 6.0}); break;
+    case 18: k = build({"3: -2,1,-2  1,4,1  -2,1,-2", {-1, -1}, {-1, -1}, 1.0 / 6.0}); break;
+    case 19: k = build({"3: 1,1,1  1,1,1  1,1,1", {-1, -1}, {-1, -1}, 1.0 / 3.0}); break;
+    default: k = build({"3: 1,0,-1  2,0,-2  1,0,-1", {3, -1}, {5, -1}, 0.0}); break;
+  }
+  if (!k) return nullptr;
+  if (std::fabs(sigma) >= kEps) rotate_list(k, sigma);
+  else if (rho > 30.0 || rho < -30.0) rotate_list(k, rho);
+  return k;
 }
 
 }  // namespace
@@ -527,6 +721,189 @@ mb200_kernel_info *mb200_acquire_kernel_builtin(int type, double rho, double sig
       for (long i = 0; i < n; ++i) k->values[i] = scale;
       k->minimum = k->maximum = scale;
       k->positive_range = scale * n;
+      return k;
+    }
+    case MB200_CometKernel: {                                   // :1228 half a 1-D Gaussian, normalised, turned by xi
+      double sigma = std::fabs(sigma_arg);
+      const size_t w = rho < 1.0 ? (mb200_optimal_kernel_width_1d(rho, sigma) - 1) / 2 + 1 : static_cast<size_t>(rho);
+      mb200_kernel_info *k = new_kernel(type, w, 1);
+      if (!k) return nullptr;
+      k->x = k->y = 0;
+      if (sigma > kEps) {
+        constexpr long kRank = 3;
+        const long v = static_cast<long>(w) * kRank;
+        sigma *= kRank;
+        const double A = 1.0 / (2.0 * sigma * sigma);
+        for (long u = 0; u < v; ++u) k->values[u / kRank] += std::exp(-(static_cast<double>(u * u)) * A);
+        for (size_t i = 0; i < w; ++i) k->positive_range += k->values[i];
+      } else {
+        k->values[0] = 1.0;
+        k->positive_range = 1.0;
+      }
+      k->minimum = 0.0;
+      k->maximum = k->values[0];
+      k->negative_range = 0.0;
+      mb200_scale_kernel_info(k, 1.0, 1);                       // NormalizeValue
+      rotate_kernel(k, xi);
+      return k;
+    }
+    case MB200_LaplacianKernel: return from_array(type, laplacian_array(static_cast<int>(rho)));     // :1333
+    case MB200_SobelKernel: case MB200_RobertsKernel: case MB200_PrewittKernel: case MB200_CompassKernel:
+    case MB200_KirschKernel: {                                  // :1371-1414: one 3x3 array, turned by rho
+      const char *text = type == MB200_SobelKernel ? "3: 1,0,-1  2,0,-2  1,0,-1"
+                         : type == MB200_RobertsKernel ? "3: 0,0,0  1,-1,0  0,0,0"
+                         : type == MB200_PrewittKernel ? "3: 1,0,-1  1,0,-1  1,0,-1"
+                         : type == MB200_CompassKernel ? "3: 1,1,-1  1,-2,-1  1,1,-1" : "3: 5,-3,-3  5,0,-3  5,-3,-3";
+      mb200_kernel_info *k = from_array(type, text);
+      if (k) rotate_kernel(k, rho);
+      return k;
+    }
+    case MB200_FreiChenKernel: return frei_chen(rho, sigma_arg);
+    case MB200_RingKernel: case MB200_PeaksKernel: {            // :1698
+      long limit1, limit2;
+      size_t w;
+      if (rho < sigma_arg) {
+        w = static_cast<size_t>(sigma_arg) * 2 + 1;
+        limit1 = static_cast<long>(rho * rho); limit2 = static_cast<long>(sigma_arg * sigma_arg);
+      } else {
+        w = static_cast<size_t>(rho) * 2 + 1;
+        limit1 = static_cast<long>(sigma_arg * sigma_arg); limit2 = static_cast<long>(rho * rho);
+      }
+      if (limit2 <= 0) { w = 7; limit1 = 7; limit2 = 11; }
+      const double scale = static_cast<double>(static_cast<long>(type == MB200_PeaksKernel ? 0.0 : xi));
+      mb200_kernel_info *k = shape_kernel(type, w, scale, [limit1, limit2](long u, long v, const mb200_kernel_info *) {
+        const long r = u * u + v * v;
+        return limit1 < r && r <= limit2;
+      }, true);
+      if (k && type == MB200_PeaksKernel) {
+        k->values[k->x + k->y * static_cast<long>(w)] = 1.0;
+        k->positive_range = 1.0;
+        k->maximum = 1.0;
+      }
+      return k;
+    }
+    case MB200_EdgesKernel: {                                   // :1748 the general edge element and its mirror images
+      mb200_kernel_info *k = thin_se(482, 0.0, type);
+      if (k) expand_mirrored(k);
+      return k;
+    }
+    case MB200_CornersKernel: {                                 // :1757
+      mb200_kernel_info *k = thin_se(87, 0.0, type);
+      if (k) expand_rotated(k, 90.0);
+      return k;
+    }
+    case MB200_DiagonalsKernel: {                               // :1766
+      const int which = static_cast<int>(rho);
+      if (which == 1 || which == 2) {
+        mb200_kernel_info *k = from_array(type, which == 1 ? "3: 0,0,0  0,-,1  1,1,-" : "3: 0,0,1  0,-,1  0,1,-");
+        if (k) rotate_kernel(k, sigma_arg);
+        return k;
+      }
+      mb200_kernel_info *k = list_of(type, {"3: 0,0,0  0,-,1  1,1,-", "3: 0,0,1  0,-,1  0,1,-"});
+      if (k) expand_mirrored(k);
+      return k;
+    }
+    case MB200_LineEndsKernel: {                                // :1798
+      const char *text = nullptr;
+      switch (static_cast<int>(rho)) {
+        case 1: text = "3: 0,0,-  0,1,1  0,0,-"; break;
+        case 2: text = "3: 0,0,0  0,1,0  0,0,1"; break;
+        case 3: text = "3: 0,0,0  0,1,1  0,0,0"; break;
+        case 4: text = "3: 0,0,0  0,1,-  0,0,-"; break;
+        default: return mb200_acquire_kernel_info("LineEnds:1>;LineEnds:2>");
+      }
+      mb200_kernel_info *k = from_array(type, text);
+      if (k) rotate_kernel(k, sigma_arg);
+      return k;
+    }
+    case MB200_LineJunctionsKernel: {                           // :1828
+      const char *text = nullptr;
+      switch (static_cast<int>(rho)) {
+        case 1: text = "3: 1,-,1  -,1,-  -,1,-"; break;
+        case 2: text = "3: 1,-,-  -,1,-  1,-,1"; break;
+        case 3: text = "3: -,-,-  1,1,1  -,1,-"; break;
+        case 4: text = "3: 1,-,1  -,1,-  1,-,1"; break;
+        case 5: text = "3: -,1,-  1,1,1  -,1,-"; break;
+        default: return mb200_acquire_kernel_info("LineJunctions:1@;LineJunctions:2>");
+      }
+      mb200_kernel_info *k = from_array(type, text);
+      if (k) rotate_kernel(k, sigma_arg);
+      return k;
+    }
+    case MB200_RidgesKernel: {                                  // :1862
+      if (static_cast<int>(rho) == 2) {
+        mb200_kernel_info *k = from_array(type, "4x1:0,1,1,0");
+        if (!k) return nullptr;
+        expand_rotated(k, 90.0);
+        mb200_kernel_info *thick = list_of(type, {"4x3+1+1:0,1,1,- -,1,1,- -,1,1,0", "4x3+2+1:0,1,1,- -,1,1,- -,1,1,0",
+                                                  "4x3+1+1:-,1,1,0 -,1,1,- 0,1,1,-", "4x3+2+1:-,1,1,0 -,1,1,- 0,1,1,-",
+                                                  "3x4+1+1:0,-,- 1,1,1 1,1,1 -,-,0", "3x4+1+2:0,-,- 1,1,1 1,1,1 -,-,0",
+                                                  "3x4+1+1:-,-,0 1,1,1 1,1,1 0,-,-", "3x4+1+2:-,-,0 1,1,1 1,1,1 0,-,-"});
+        if (!thick) return mb200_destroy_kernel_info(k);
+        last_of(k)->next = thick;
+        return k;
+      }
+      mb200_kernel_info *k = from_array(type, "3x1:0,1,0");
+      if (k) expand_rotated(k, 90.0);
+      return k;
+    }
+    case MB200_ConvexHullKernel: {                              // :1929 eight kernels: four turns of an element and of its mirror
+      mb200_kernel_info *k = from_array(type, "3: 1,1,-  1,0,-  1,-,0");
+      mb200_kernel_info *m = from_array(type, "3: 1,1,1  1,0,-  -,-,0");
+      if (!k || !m) { mb200_destroy_kernel_info(k); return mb200_destroy_kernel_info(m); }
+      expand_rotated(k, 90.0);
+      expand_rotated(m, 90.0);
+      last_of(k)->next = m;
+      return k;
+    }
+    case MB200_SkeletonKernel: {                                // :1948
+      mb200_kernel_info *k = nullptr;
+      switch (static_cast<int>(rho)) {
+        case 2: {                                               // HIPR variation: the edge element and a corner, four turns
+          k = thin_se(482, 0.0, type);
+          mb200_kernel_info *c = thin_se(87, 90.0, type);
+          if (!k || !c) { mb200_destroy_kernel_info(k); return mb200_destroy_kernel_info(c); }
+          k->next = c;
+          expand_rotated(k, 90.0);
+          break;
+        }
+        case 3: {                                               // Bloomberg's 4-connected elements and their mirror images
+          k = thin_se(41, 0.0, type);
+          mb200_kernel_info *b = thin_se(42, 0.0, type), *c = thin_se(43, 0.0, type);
+          if (!k || !b || !c) { mb200_destroy_kernel_info(k); mb200_destroy_kernel_info(b); return mb200_destroy_kernel_info(c); }
+          k->next = b; b->next = c;
+          expand_mirrored(k);
+          break;
+        }
+        default:                                                // the edge element through eight eighth turns
+          k = thin_se(482, 0.0, type);
+          if (k) expand_rotated(k, 45.0);
+          break;
+      }
+      return k;
+    }
+    case MB200_ThinSEKernel: return thin_se(static_cast<int>(rho), sigma_arg, type);
+    case MB200_ChebyshevKernel: case MB200_ManhattanKernel: case MB200_OctagonalKernel:
+    case MB200_EuclideanKernel: {                               // :2090-2178 distance to the origin, scaled by sigma
+      const size_t w = type == MB200_OctagonalKernel ? (rho < 2.0 ? 5 : static_cast<size_t>(rho) * 2 + 1)
+                                                     : (rho < 1.0 ? 3 : static_cast<size_t>(rho) * 2 + 1);
+      mb200_kernel_info *k = new_kernel(type, w, w);
+      if (!k) return nullptr;
+      centre_origin(k);
+      size_t i = 0;
+      for (long v = -k->y; v <= k->y; ++v)
+        for (long u = -k->x; u <= k->x; ++u, ++i) {
+          const double au = std::fabs(static_cast<double>(u)), av = std::fabs(static_cast<double>(v));
+          double d;
+          if (type == MB200_ChebyshevKernel) d = au > av ? au : av;
+          else if (type == MB200_ManhattanKernel) d = static_cast<double>(std::labs(u) + std::labs(v));
+          else if (type == MB200_OctagonalKernel) {
+            const double r1 = au > av ? au : av, r2 = std::floor(static_cast<double>(std::labs(u) + std::labs(v) + 1) / 1.5);
+            d = r1 > r2 ? r1 : r2;
+          } else d = std::sqrt(static_cast<double>(u * u + v * v));
+          k->positive_range += (k->values[i] = sigma_arg * d);
+        }
+      k->maximum = k->values[0];
       return k;
     }
     default:

@@ -131,7 +131,13 @@ typedef enum {
   MB200_UserDefinedKernel = 0, MB200_BlurKernel, MB200_GaussianKernel, MB200_DiskKernel,
   MB200_SquareKernel, MB200_DiamondKernel, MB200_OctagonKernel, MB200_PlusKernel,
   MB200_CrossKernel, MB200_RectangleKernel, MB200_UnityKernel, MB200_DoGKernel,
-  MB200_LoGKernel, MB200_BinomialKernel
+  MB200_LoGKernel, MB200_BinomialKernel,
+  /* the rest of KernelInfoType (MagickCore/morphology.h:27-68): named convolution kernels, hit-and-miss lists, distances */
+  MB200_CometKernel, MB200_LaplacianKernel, MB200_SobelKernel, MB200_FreiChenKernel, MB200_RobertsKernel,
+  MB200_PrewittKernel, MB200_CompassKernel, MB200_KirschKernel, MB200_RingKernel, MB200_PeaksKernel, MB200_EdgesKernel,
+  MB200_CornersKernel, MB200_DiagonalsKernel, MB200_LineEndsKernel, MB200_LineJunctionsKernel, MB200_RidgesKernel,
+  MB200_ConvexHullKernel, MB200_ThinSEKernel, MB200_SkeletonKernel, MB200_ChebyshevKernel, MB200_ManhattanKernel,
+  MB200_OctagonalKernel, MB200_EuclideanKernel
 } mb200_kernel_type;
 
 typedef struct mb200_kernel_info {

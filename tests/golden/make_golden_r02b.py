@@ -25,9 +25,42 @@ def source(ch):
     return src
 
 
+KERNEL_STRINGS = [
+    "Comet:0x2", "Comet:0x1.5+90", "Comet:5x2+180", "Laplacian", "Laplacian:1", "Laplacian:2", "Laplacian:3", "Laplacian:5",
+    "Laplacian:7", "Laplacian:15", "Laplacian:19", "Sobel", "Sobel:90", "Sobel:45", "Sobel:180", "Sobel:270", "Sobel:135",
+    "Roberts", "Roberts:90", "Prewitt:45", "Compass:270", "Kirsch:315", "Sobel:@", "Sobel:0>", "Kirsch:<",
+    "FreiChen", "FreiChen:1", "FreiChen:2", "FreiChen:10", "FreiChen:13", "FreiChen:17,45", "FreiChen:19", "FreiChen:0,90",
+    "FreiChen:90", "Ring:2,3.5", "Ring:1,2.5,3", "Ring", "Ring:0,0", "Peaks:1.9", "Peaks:2,4", "Peaks", "Edges", "Corners",
+    "Diagonals", "Diagonals:1", "Diagonals:2,90", "LineEnds", "LineEnds:1", "LineEnds:2,90", "LineEnds:3>", "LineEnds:4@",
+    "LineJunctions", "LineJunctions:1", "LineJunctions:3,180", "LineJunctions:4", "LineJunctions:5@", "Ridges", "Ridges:2",
+    "ConvexHull", "Skeleton", "Skeleton:1", "Skeleton:2", "Skeleton:3", "ThinSE:482", "ThinSE:41", "ThinSE:87x90",
+    "ThinSE:481,45", "ThinSE:823>", "ThinSE:49<", "ThinSE:44@", "Chebyshev", "Chebyshev:2", "Chebyshev:1,50%",
+    "Manhattan:2,100", "Manhattan:3,4!", "Octagonal", "Octagonal:3", "Euclidean", "Euclidean:2", "Euclidean:4,10!",
+    "3>: 0,0,nan 0,1,1 nan,1,nan", "3@: 1,0,0 0,1,0 0,0,-", "3<: 1,2,3 4,5,6 7,8,9", "3x1>: 1,2,3", "2x2>: 1,2,3,4",
+    "4x3+1+1<: 1,2,3,4,5,6,7,8,9,10,11,12", "Unity", "Binomial:2", "Disk:2.5", "Square:2>", "Plus:2@", "Blur:0x2>",
+    "Gaussian:0x1@", "Rectangle:3x2+1+0>", "Octagon:2>", "Sobel@", "Kirsch@"]
+
+
+def kernel_goldens(out):
+    """The reference's own expansion of kernel strings (AcquireKernelInfo, morphology.c:485): every list element's values
+    and origin; a string the reference rejects is recorded with count 0."""
+    for n, name in enumerate(KERNEL_STRINGS):
+        idx = 0
+        while True:
+            k = util.ref_kernel(name, idx)
+            if k is None:
+                break
+            out[f"kernel/{n}/{idx}/values"] = k[0]
+            out[f"kernel/{n}/{idx}/origin"] = np.array([k[1], k[2]], np.int64)
+            idx += 1
+        out[f"kernel/{n}/count"] = np.array([idx], np.int64)
+    out["kernel/strings"] = np.array(KERNEL_STRINGS)
+
+
 def main():
     r, P = util.ref(), util.P
     out = {}
+    kernel_goldens(out)
     for ch in (3, 4):
         src = source(ch)
         out[f"c{ch}/src"] = src

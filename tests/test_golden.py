@@ -192,6 +192,28 @@ def _r02b_cases(tag):
     return [k for k in G2.files if k.startswith(tag + "/") and not k.endswith("/src")]
 
 
+def test_kernel_strings_expand_like_the_reference():
+    """AcquireKernelInfo (morphology.c:485): every named kernel of KernelInfoType, the '@' / '>' / '<' expansions (eighth
+    and quarter turns, mirror images) of named and user kernels, the distance-kernel scale flags -- bit-identical values
+    and origins for every list element; strings the reference rejects are rejected."""
+    im = pytest.importorskip("imagemagick_b200")
+    strings = [str(x) for x in G2["kernel/strings"]]
+    assert len(strings) > 90
+    for n, name in enumerate(strings):
+        count = int(G2[f"kernel/{n}/count"][0])
+        try:
+            mine = im.AcquireKernelInfo(name).arrays()
+        except im.MagickB200Error:
+            mine = []
+        assert len(mine) == count, (name, len(mine), count)
+        for idx, (vals, x, y) in enumerate(mine):
+            want = G2[f"kernel/{n}/{idx}/values"]
+            assert vals.shape == want.shape, (name, idx)
+            assert np.array_equal(np.isnan(vals), np.isnan(want)), (name, idx)
+            assert np.array_equal(np.nan_to_num(vals), np.nan_to_num(want)), (name, idx)
+            assert [x, y] == list(G2[f"kernel/{n}/{idx}/origin"]), (name, idx)
+
+
 @pytest.mark.parametrize("tag", ["c3", "c4"])
 def test_oracle_matches_reference_golden_r02b(tag):
     """Jinc / Kaiser ResizeImage and the hue / saturation colourspaces: the oracle against arrays the real reference
