@@ -78,6 +78,9 @@ PROTOTYPES = {
     "mb200_optimal_kernel_width_2d": (_sz, [_d, _d]),
     "mb200_resize_contributions": (_l, [_i, _sz, _sz, _d, C.POINTER(_l), C.POINTER(_i), C.POINTER(_d), _sz]),
     "mb200_resize_filter_weight": (_d, [_i, _d]),
+    "mb200_resize_filter_weight_ex": (_d, [_i, _vp, _d]),
+    "mb200_resize_filter_support_ex": (_d, [_i, _vp]),
+    "mb200_resize_contributions_ex": (_l, [_i, _vp, _sz, _sz, _d, C.POINTER(_l), C.POINTER(_i), C.POINTER(_d), _sz]),
     "mb200_resize_filter_support": (_d, [_i]),
     "mb200_morphology_primitive_dev": (_i, [_vp, _vp, _sz, _sz, _i, _i, KernelPtr, _d, C.POINTER(C.c_longlong), _vp]),
     "mb200_morphology_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _i, _l, KernelPtr, _d, _vp]),
@@ -86,6 +89,8 @@ PROTOTYPES = {
     "mb200_gaussian_blur_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d, _vp]),
     "mb200_unsharp_mask_image_dev": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d, _d, _d, _vp]),
     "mb200_resize_image_dev": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i, _vp]),
+    "mb200_resize_image_ex_dev": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i, _vp, _vp]),
+    "mb200_resize_image_ex": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i, _vp]),
     "mb200_transform_colorspace_dev": (_i, [_vp, _sz, _sz, _i, _i, _i, _vp]),
     "mb200_blur_image": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d]),
     "mb200_gaussian_blur_image": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d]),

@@ -278,19 +278,54 @@ def MotionBlurImage(image: Image, radius: float, sigma: float, angle: float) -> 
                          float(angle))
 
 
-def ResizeImage(image: Image, columns: int, rows: int, filter: int = UndefinedFilter) -> Image:
-    """MagickCore/resize.c:3761."""
+class FilterOptions(C.Structure):
+    """mb200_filter_options: the "filter:*" expert settings of AcquireResizeFilter (MagickCore/resize.c:999-1226) as values."""
+    _fields_ = [("set", C.c_uint), ("window", C.c_int), ("keep_filter", C.c_int), ("lobes", C.c_long), ("sigma", C.c_double),
+                ("kaiser_beta", C.c_double), ("blur", C.c_double), ("support", C.c_double), ("win_support", C.c_double),
+                ("b", C.c_double), ("c", C.c_double)]
+
+
+_FILTER_NAMES = {n[:-len("Filter")].lower(): v for n, v in list(globals().items())
+                 if n.endswith("Filter") and isinstance(v, int)}
+
+
+def filter_options_from_artifacts(artifacts) -> "FilterOptions | None":
+    """What the shim does in C (b200_filter_options): read the -define filter:* strings the way the reference does."""
+    if not artifacts:
+        return None
+    o = FilterOptions()
+    truthy = str(artifacts.get("filter:filter", "")).strip().lower() in ("true", "yes", "on", "1")
+    w = artifacts.get("filter:window")
+    if w is not None and str(w).strip().lower() in _FILTER_NAMES and _FILTER_NAMES[str(w).strip().lower()] > 0:
+        o.window, o.keep_filter, o.set = _FILTER_NAMES[str(w).strip().lower()], int(truthy), o.set | 1
+    for key, field, bit in (("filter:sigma", "sigma", 2), ("filter:alpha", "kaiser_beta", 4), ("filter:kaiser-beta", "kaiser_beta", 4),
+                            ("filter:blur", "blur", 16), ("filter:support", "support", 32), ("filter:win-support", "win_support", 64),
+                            ("filter:b", "b", 128), ("filter:c", "c", 256)):
+        if key in artifacts:
+            setattr(o, field, float(artifacts[key]))
+            o.set |= bit
+    if "filter:kaiser-alpha" in artifacts:
+        o.kaiser_beta, o.set = float(artifacts["filter:kaiser-alpha"]) * 3.14159265358979323846264338327950288419716939937510, o.set | 4
+    if "filter:lobes" in artifacts:
+        o.lobes, o.set = int(float(artifacts["filter:lobes"])), o.set | 8
+    return o if o.set else None
+
+
+def ResizeImage(image: Image, columns: int, rows: int, filter: int = UndefinedFilter, artifacts=None) -> Image:
+    """MagickCore/resize.c:3761.  `artifacts`: the image's "-define filter:*" settings, e.g. {"filter:blur": "0.8"}."""
     if columns <= 0 or rows <= 0:
         raise MagickB200Error(_lib.EINVAL, "NegativeOrZeroImageSize")
     lib = _lib.load()
     out = image._new_like(rows=rows, columns=columns)
+    opts = filter_options_from_artifacts(artifacts)
+    ref = C.byref(opts) if opts is not None else None
     if image.on_device:
         _activate(image)
-        check(lib.mb200_resize_image_dev(image._ptr(), image.columns, image.rows, image.channels, out._ptr(),
-                                         columns, rows, int(filter), _stream(image)))
+        check(lib.mb200_resize_image_ex_dev(image._ptr(), image.columns, image.rows, image.channels, out._ptr(),
+                                            columns, rows, int(filter), ref, _stream(image)))
     else:
-        check(lib.mb200_resize_image(image._ptr(), image.columns, image.rows, image.channels, out._ptr(), columns,
-                                     rows, int(filter)))
+        check(lib.mb200_resize_image_ex(image._ptr(), image.columns, image.rows, image.channels, out._ptr(), columns,
+                                        rows, int(filter), ref))
     return out
 
 

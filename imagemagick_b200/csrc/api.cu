@@ -32,6 +32,7 @@ namespace {
 // equally sized images (BASELINE configs[4]) rebuild neither the weights on the host nor upload them.
 struct ResizeTables {
   int device = -1, filter = 0;
+  mb200_filter_options options{};     // expert settings the table was built with (all zero: none)
   size_t in_n = 0, out_n = 0;
   long taps = 0;
   int max_span = 0, reg_stride = 0, reg_taps = 0;
@@ -545,6 +546,26 @@ int mb200_unsharp_mask_image_dev(const float *src, float *dst, size_t width, siz
 
 int mb200_resize_image_dev(const float *src, size_t width, size_t height, int channels, float *dst,
                            size_t out_width, size_t out_height, int filter, void *stream) {
+  return mb200_resize_image_ex_dev(src, width, height, channels, dst, out_width, out_height, filter, nullptr, stream);
+}
+
+int mb200_resize_image_ex_dev(const float *src, size_t width, size_t height, int channels, float *dst,
+                              size_t out_width, size_t out_height, int filter, const mb200_filter_options *options,
+                              void *stream) {
+  mb200_filter_options opt{};           // normalised copy: the cache compares the bytes
+  if (options) {
+    opt.set = options->set;
+    if (opt.set & MB200_FO_WINDOW) { opt.window = options->window; opt.keep_filter = options->keep_filter ? 1 : 0; }
+    if (opt.set & MB200_FO_LOBES) opt.lobes = options->lobes;
+    if (opt.set & MB200_FO_SIGMA) opt.sigma = options->sigma;
+    if (opt.set & MB200_FO_KAISER_BETA) opt.kaiser_beta = options->kaiser_beta;
+    if (opt.set & MB200_FO_BLUR) opt.blur = options->blur;
+    if (opt.set & MB200_FO_SUPPORT) opt.support = options->support;
+    if (opt.set & MB200_FO_WIN_SUPPORT) opt.win_support = options->win_support;
+    if (opt.set & MB200_FO_B) opt.b = options->b;
+    if (opt.set & MB200_FO_C) opt.c = options->c;
+  }
+
   if (!src || !dst || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "resize: bad arguments");
   if (out_width == 0 || out_height == 0) return fail(MB200_EINVAL, "NegativeOrZeroImageSize");   // :3791
   cudaStream_t s;
@@ -569,7 +590,8 @@ int mb200_resize_image_dev(const float *src, size_t width, size_t height, int ch
     auto find = [&]() -> std::shared_ptr<ResizeTables> {
       for (size_t i = 0; i < g_tables.size(); ++i) {
         const std::shared_ptr<ResizeTables> &t = g_tables[i];
-        if (t->device == dev && t->filter == filter_type && t->in_n == in_n && t->out_n == out_n) {
+        if (t->device == dev && t->filter == filter_type && t->in_n == in_n && t->out_n == out_n &&
+            std::memcmp(&t->options, &opt, sizeof(opt)) == 0) {
           std::shared_ptr<ResizeTables> hit = t;
           if (i + 1 != g_tables.size()) { g_tables.erase(g_tables.begin() + i); g_tables.push_back(hit); }   // most recent last
           return hit;
@@ -581,17 +603,17 @@ int mb200_resize_image_dev(const float *src, size_t width, size_t height, int ch
       std::lock_guard<std::mutex> lock(g_tables_mutex);
       if ((*out = find())) return MB200_OK;
     }
-    const long taps = mb200_resize_contributions(filter_type, in_n, out_n, factor, nullptr, nullptr, nullptr, 0);
+    const long taps = mb200_resize_contributions_ex(filter_type, &opt, in_n, out_n, factor, nullptr, nullptr, nullptr, 0);
     if (taps < 0) return static_cast<int>(taps);
     std::vector<long> start(out_n);
     std::vector<int> istart(out_n), count(out_n);
     std::vector<double> w(out_n * static_cast<size_t>(taps)), wt(out_n * static_cast<size_t>(taps)), wreg, wsets;
     std::vector<int> border;
-    const long r = mb200_resize_contributions(filter_type, in_n, out_n, factor, start.data(), count.data(), w.data(),
-                                              static_cast<size_t>(taps));
+    const long r = mb200_resize_contributions_ex(filter_type, &opt, in_n, out_n, factor, start.data(), count.data(), w.data(),
+                                                 static_cast<size_t>(taps));
     if (r < 0) return static_cast<int>(r);
     std::shared_ptr<ResizeTables> t = std::make_shared<ResizeTables>();
-    t->device = dev; t->filter = filter_type; t->in_n = in_n; t->out_n = out_n; t->taps = taps;
+    t->device = dev; t->filter = filter_type; t->options = opt; t->in_n = in_n; t->out_n = out_n; t->taps = taps;
     // widest source span of any aligned block of 32 outputs (tile width of the tiled horizontal kernel)
     for (size_t o = 0; o < out_n; o += 32) {
       const size_t last = std::min(o + 32, out_n) - 1;
@@ -808,12 +830,16 @@ int mb200_unsharp_mask_image(const float *src, float *dst, size_t w, size_t h, i
   });
 }
 
-int mb200_resize_image(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh, int filter) {
+int mb200_resize_image_ex(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh, int filter,
+                          const mb200_filter_options *options) {
   if (!src || !dst || !valid_image(w, h, ch) || ow == 0 || oh == 0) return fail(MB200_EINVAL, "resize: bad arguments");
   return with_staging(src, w * h * ch * sizeof(float), dst, ow * oh * ch * sizeof(float),
                       [&](const float *s, float *d, cudaStream_t st) {
-                        return mb200_resize_image_dev(s, w, h, ch, d, ow, oh, filter, st);
+                        return mb200_resize_image_ex_dev(s, w, h, ch, d, ow, oh, filter, options, st);
                       });
+}
+int mb200_resize_image(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh, int filter) {
+  return mb200_resize_image_ex(src, w, h, ch, dst, ow, oh, filter, nullptr);
 }
 
 int mb200_transform_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to) {

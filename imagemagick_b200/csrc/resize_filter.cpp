@@ -99,9 +99,16 @@ struct ResizeFilter {
   double support = 0, window_support = 0, scale = 1, blur = 1, coefficient[7] = {0};
   bool valid = false;
 
-  explicit ResizeFilter(int requested) {
+  // The expert settings take effect in the reference's order (resize.c:999-1226): window override, sharpening, Gaussian
+  // sigma (widens the support), Kaiser beta, lobes, Jinc zeros, blur, support, window support, window scale, cubic B / C.
+  explicit ResizeFilter(int requested, const mb200_filter_options *opt = nullptr) {
     if (requested <= MB200_UndefinedFilter || requested >= MB200_SentinelFilter) return;
-    const int ft = kMapping[requested].filter, wt = kMapping[requested].window;
+    const unsigned set = opt ? opt->set : 0u;
+    int ft = kMapping[requested].filter, wt = kMapping[requested].window;
+    if ((set & MB200_FO_WINDOW) && opt->window > MB200_UndefinedFilter && opt->window < MB200_SentinelFilter) {
+      if (!opt->keep_filter) ft = MB200_SincFastFilter;     // a window without a filter: windowed Sinc (:1024-1041)
+      wt = opt->window;
+    }
     filter = kFunctions[ft].fn;
     window = kFunctions[wt].fn;
     if (filter == Fn::Unsupported || window == Fn::Unsupported) return;
@@ -110,22 +117,35 @@ struct ResizeFilter {
     if (ft == MB200_LanczosSharpFilter) blur *= 0.9812505644269356;
     if (ft == MB200_Lanczos2SharpFilter) blur *= 0.9549963639785485;
     if (filter == Fn::Gaussian || window == Fn::Gaussian) {
-      const double sigma = 0.5;
+      const double sigma = (set & MB200_FO_SIGMA) ? opt->sigma : 0.5;
       coefficient[0] = sigma;
       coefficient[1] = perceptible_reciprocal(2.0 * sigma * sigma);
       coefficient[2] = perceptible_reciprocal(k2Pi * sigma * sigma);
+      if (sigma > 0.5) support *= 2 * sigma;                 // :1097-1098
     }
-    if (filter == Fn::Kaiser || window == Fn::Kaiser) {      // :1104-1120 with the default beta
-      coefficient[0] = 6.5;
-      coefficient[1] = perceptible_reciprocal(bessel_i0(6.5));
+    if (filter == Fn::Kaiser || window == Fn::Kaiser) {      // :1104-1120
+      const double beta = (set & MB200_FO_KAISER_BETA) ? opt->kaiser_beta : 6.5;
+      coefficient[0] = beta;
+      coefficient[1] = perceptible_reciprocal(bessel_i0(beta));
     }
+    if (set & MB200_FO_LOBES) support = static_cast<double>(opt->lobes < 1 ? 1 : opt->lobes);   // :1123-1133
     if (filter == Fn::Jinc) support = jinc_zero(static_cast<long>(support));   // :1135-1150 lobes -> support
+    if (set & MB200_FO_BLUR) blur *= opt->blur;              // :1155-1157
     if (blur < kEps) blur = kEps;
-    window_support = support;
+    if (set & MB200_FO_SUPPORT) support = std::fabs(opt->support);             // :1163-1165
+    window_support = (set & MB200_FO_WIN_SUPPORT) ? std::fabs(opt->win_support) : support;   // :1170-1173
     scale *= perceptible_reciprocal(window_support);
     if (filter == Fn::CubicBC || window == Fn::CubicBC) {
       double B = kFunctions[ft].B, C = kFunctions[ft].C;
       if (kFunctions[wt].fn == Fn::CubicBC) { B = kFunctions[wt].B; C = kFunctions[wt].C; }
+      if (set & MB200_FO_B) {                                // :1196-1212: one of them given => a Keys cubic
+        B = opt->b;
+        C = (1.0 - B) / 2.0;
+        if (set & MB200_FO_C) C = opt->c;
+      } else if (set & MB200_FO_C) {
+        C = opt->c;
+        B = 1.0 - 2.0 * C;
+      }
       const double twoB = B + B;
       coefficient[0] = 1.0 - (1.0 / 3.0) * B;
       coefficient[1] = -3.0 + twoB + C;
@@ -288,21 +308,28 @@ struct ResizeFilter {
 
 extern "C" {
 
-double mb200_resize_filter_weight(int filter, double x) {
-  ResizeFilter rf(filter);
+double mb200_resize_filter_weight_ex(int filter, const mb200_filter_options *options, double x) {
+  ResizeFilter rf(filter, options);
   if (!rf.valid) return std::nan("");
   return rf.weight(x);
 }
+double mb200_resize_filter_weight(int filter, double x) { return mb200_resize_filter_weight_ex(filter, nullptr, x); }
 
-double mb200_resize_filter_support(int filter) {
-  ResizeFilter rf(filter);
+double mb200_resize_filter_support_ex(int filter, const mb200_filter_options *options) {
+  ResizeFilter rf(filter, options);
   if (!rf.valid) return std::nan("");
   return rf.practical_support();
 }
+double mb200_resize_filter_support(int filter) { return mb200_resize_filter_support_ex(filter, nullptr); }
 
 long mb200_resize_contributions(int filter, size_t in_n, size_t out_n, double factor, long *start,
                                 int *count, double *weights, size_t max_taps) {
-  ResizeFilter rf(filter);
+  return mb200_resize_contributions_ex(filter, nullptr, in_n, out_n, factor, start, count, weights, max_taps);
+}
+
+long mb200_resize_contributions_ex(int filter, const mb200_filter_options *options, size_t in_n, size_t out_n, double factor,
+                                   long *start, int *count, double *weights, size_t max_taps) {
+  ResizeFilter rf(filter, options);
   if (!rf.valid) return mb200::fail(MB200_EUNSUPPORTED, "resize filter %d is not supported on the 1-D GPU path", filter);
   if (in_n == 0 || out_n == 0 || !(factor > 0.0)) return mb200::fail(MB200_EINVAL, "bad resize geometry");
   // resize.c:3363-3386 / :3578-3601

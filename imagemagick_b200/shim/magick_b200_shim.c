@@ -301,9 +301,53 @@ Image *B200AccelerateMorphologyImage(const Image *image, const MorphologyMethod 
 }
 
 /* ---- ResizeImage -------------------------------------------------------------------------------------- */
+/* The "filter:*" expert settings (-define filter:blur=0.8 ...), read exactly as AcquireResizeFilter reads them
+   (resize.c:999-1226: GetImageArtifact + IsStringTrue / ParseCommandOption / StringToDouble / StringToLong) and handed to
+   the library as values.  MagickFalse: a setting the GPU path does not serve (filter:verbose prints the filter). */
+static MagickBooleanType b200_filter_options(const Image *image, mb200_filter_options *o)
+{
+  const char *a;
+  (void) memset(o, 0, sizeof(*o));
+  if (IsStringTrue(GetImageArtifact(image, "filter:verbose")) != MagickFalse) return MagickFalse;
+  o->keep_filter = IsStringTrue(GetImageArtifact(image, "filter:filter")) != MagickFalse ? 1 : 0;
+  if (o->keep_filter != 0) {
+    /* :1000-1011: a truthy string is parsed as a filter name; a name that parses would replace the filter itself */
+    ssize_t option = ParseCommandOption(MagickFilterOptions, MagickFalse, GetImageArtifact(image, "filter:filter"));
+    if ((UndefinedFilter < option) && (option < SentinelFilter)) return MagickFalse;
+  }
+  a = GetImageArtifact(image, "filter:window");
+  if (a != (const char *) NULL) {
+    ssize_t option = ParseCommandOption(MagickFilterOptions, MagickFalse, a);
+    if ((UndefinedFilter < option) && (option < SentinelFilter)) { o->window = (int) option; o->set |= MB200_FO_WINDOW; }
+  }
+  a = GetImageArtifact(image, "filter:sigma");
+  if (a != (const char *) NULL) { o->sigma = StringToDouble(a, (char **) NULL); o->set |= MB200_FO_SIGMA; }
+  a = GetImageArtifact(image, "filter:alpha");
+  if (a != (const char *) NULL) { o->kaiser_beta = StringToDouble(a, (char **) NULL); o->set |= MB200_FO_KAISER_BETA; }
+  a = GetImageArtifact(image, "filter:kaiser-beta");
+  if (a != (const char *) NULL) { o->kaiser_beta = StringToDouble(a, (char **) NULL); o->set |= MB200_FO_KAISER_BETA; }
+  a = GetImageArtifact(image, "filter:kaiser-alpha");
+  if (a != (const char *) NULL) { o->kaiser_beta = StringToDouble(a, (char **) NULL) * 3.14159265358979323846264338327950288419716939937510; o->set |= MB200_FO_KAISER_BETA; }
+  a = GetImageArtifact(image, "filter:lobes");
+  if (a != (const char *) NULL) { o->lobes = (long) StringToLong(a); o->set |= MB200_FO_LOBES; }
+  a = GetImageArtifact(image, "filter:blur");
+  if (a != (const char *) NULL) { o->blur = StringToDouble(a, (char **) NULL); o->set |= MB200_FO_BLUR; }
+  a = GetImageArtifact(image, "filter:support");
+  if (a != (const char *) NULL) { o->support = StringToDouble(a, (char **) NULL); o->set |= MB200_FO_SUPPORT; }
+  a = GetImageArtifact(image, "filter:win-support");
+  if (a != (const char *) NULL) { o->win_support = StringToDouble(a, (char **) NULL); o->set |= MB200_FO_WIN_SUPPORT; }
+  a = GetImageArtifact(image, "filter:b");
+  if (a != (const char *) NULL) { o->b = StringToDouble(a, (char **) NULL); o->set |= MB200_FO_B; }
+  a = GetImageArtifact(image, "filter:c");
+  if (a != (const char *) NULL) { o->c = StringToDouble(a, (char **) NULL); o->set |= MB200_FO_C; }
+  if ((o->set & MB200_FO_WINDOW) == 0) o->keep_filter = 0;
+  return MagickTrue;
+}
+
 Image *B200AccelerateResizeImage(const Image *image, const size_t columns, const size_t rows,
                                  const FilterType filter, ExceptionInfo *exception)
 {
+  mb200_filter_options fopt;
   unsigned update_mask = 0xfu;
   const int ch = b200_channels_masked(image, &update_mask);
   const float *p;
@@ -311,7 +355,8 @@ Image *B200AccelerateResizeImage(const Image *image, const size_t columns, const
   Image *out;
   (void) exception;
   if (ch == 0 || columns == 0 || rows == 0 || mb200_device_count() <= 0) return (Image *) NULL;
-  if (has_artifact(image, filter_artifacts) != MagickFalse) return (Image *) NULL;
+  if (b200_filter_options(image, &fopt) == MagickFalse) return (Image *) NULL;       /* filter:verbose: stdout belongs to the CPU path */
+  if (fopt.set != 0 && (update_mask & ((1u << ch) - 1u)) != ((1u << ch) - 1u)) return (Image *) NULL;
   if (image->storage_class == PseudoClass) return (Image *) NULL;
   {
     B200_ATTEMPT_BEGIN;
@@ -321,7 +366,8 @@ Image *B200AccelerateResizeImage(const Image *image, const size_t columns, const
     if (out != (Image *) NULL) {
       q = GetAuthenticPixels(out, 0, 0, columns, rows, attempt);
       if (q == (Quantum *) NULL || b200_cache_pixels(out, ch, attempt) != (float *) q ||
-          mb200_resize_image(p, image->columns, image->rows, ch, (float *) q, columns, rows, (int) filter) != MB200_OK ||
+          mb200_resize_image_ex(p, image->columns, image->rows, ch, (float *) q, columns, rows, (int) filter,
+                                fopt.set != 0 ? &fopt : (const mb200_filter_options *) NULL) != MB200_OK ||
           ((update_mask & ((1u << ch) - 1u)) != ((1u << ch) - 1u) &&
            mb200_resize_copy_channels(p, image->columns, image->rows, ch, (float *) q, columns, rows, (int) filter,
                                       update_mask) != MB200_OK) ||

@@ -160,6 +160,10 @@ int main(void)
   CHECK("TransformImageColorspace sRGB->Luv", 1, a, b);
   CHECK("ResizeImage Jinc 50% RGBA", 1, ResizeImage(rgba, rgba->columns / 2, rgba->rows / 2, JincFilter, ex),
         CPU(__real_ResizeImage(rgba, rgba->columns / 2, rgba->rows / 2, JincFilter, ex)));
+  (void) SetImageArtifact(rgba, "filter:blur", "0.85"); (void) SetImageArtifact(rgba, "filter:lobes", "2");
+  CHECK("ResizeImage Lanczos 50% blur=.85 lobes=2", 1, ResizeImage(rgba, rgba->columns / 2, rgba->rows / 2, LanczosFilter, ex),
+        CPU(__real_ResizeImage(rgba, rgba->columns / 2, rgba->rows / 2, LanczosFilter, ex)));
+  (void) DeleteImageArtifact(rgba, "filter:blur"); (void) DeleteImageArtifact(rgba, "filter:lobes");
   CHECK("ResizeImage Kaiser 150% RGB", 1, ResizeImage(rgb, rgb->columns * 3 / 2, rgb->rows * 3 / 2, KaiserFilter, ex),
         CPU(__real_ResizeImage(rgb, rgb->columns * 3 / 2, rgb->rows * 3 / 2, KaiserFilter, ex)));
   /* threshold.c point operators: in place, bit exact */

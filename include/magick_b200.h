@@ -258,6 +258,26 @@ MB200_API long mb200_motion_blur_kernel(double radius, double sigma, double angl
 MB200_API long mb200_resize_contributions(int filter, size_t in_n, size_t out_n, double factor,
                                          long *start, int *count, double *weights,
                                          size_t max_taps);
+/* The "filter:*" expert settings AcquireResizeFilter reads from the image artifacts (MagickCore/resize.c:999-1226), as
+   values: the caller (the shim, with the reference's own StringToDouble / ParseCommandOption) does the string parsing.
+   `set` says which fields are meaningful.  window + keep_filter restate :999-1043: a "filter:window" alone turns the
+   weighting function into SincFast; with a truthy "filter:filter" the requested filter keeps its weighting function. */
+enum { MB200_FO_WINDOW = 1, MB200_FO_SIGMA = 2, MB200_FO_KAISER_BETA = 4, MB200_FO_LOBES = 8, MB200_FO_BLUR = 16,
+       MB200_FO_SUPPORT = 32, MB200_FO_WIN_SUPPORT = 64, MB200_FO_B = 128, MB200_FO_C = 256 };
+typedef struct mb200_filter_options {
+  unsigned set;
+  int window;              /* FilterType of "filter:window" */
+  int keep_filter;         /* "filter:filter" was a truthy string (:1000) */
+  long lobes;              /* "filter:lobes" */
+  double sigma;            /* "filter:sigma" (Gaussian) */
+  double kaiser_beta;      /* "filter:alpha" / "filter:kaiser-beta" / pi * "filter:kaiser-alpha", last one wins (:1104-1117) */
+  double blur, support, win_support, b, c;
+} mb200_filter_options;
+/* ... with expert settings (options == NULL: none) */
+MB200_API long mb200_resize_contributions_ex(int filter, const mb200_filter_options *options, size_t in_n, size_t out_n,
+                                            double factor, long *start, int *count, double *weights, size_t max_taps);
+MB200_API double mb200_resize_filter_weight_ex(int filter, const mb200_filter_options *options, double x);
+MB200_API double mb200_resize_filter_support_ex(int filter, const mb200_filter_options *options);
 /* GetResizeFilterWeight / GetResizeFilterSupport (MagickCore/resize.c:1690, :1656). */
 MB200_API double mb200_resize_filter_weight(int filter, double x);
 MB200_API double mb200_resize_filter_support(int filter);
@@ -340,6 +360,9 @@ MB200_API int mb200_motion_blur_image_dev(const float *src, float *dst, size_t w
     int channels, double radius, double sigma, double angle, void *stream);
 /* ResizeImage (MagickCore/resize.c:3761) == AccelerateResizeImage (:43).  filter
    UndefinedFilter applies the reference's own default choice (:3806-3816). */
+MB200_API int mb200_resize_image_ex_dev(const float *src, size_t width, size_t height, int channels, float *dst,
+                                       size_t out_width, size_t out_height, int filter,
+                                       const mb200_filter_options *options, void *stream);
 MB200_API int mb200_resize_image_dev(const float *src, size_t width, size_t height, int channels,
     float *dst, size_t out_width, size_t out_height, int filter, void *stream);
 /* SampleImage (MagickCore/resize.c:3907): nearest-sample gather with the default sampling offset
@@ -431,6 +454,8 @@ MB200_API int mb200_selective_blur_image(const float *src, float *dst, size_t wi
 MB200_API int mb200_equalize_image(float *buf, size_t width, size_t height, int channels, int sync_channels);
 MB200_API int mb200_emboss_image(const float *src, float *dst, size_t width, size_t height, int channels,
     double radius, double sigma);
+MB200_API int mb200_resize_image_ex(const float *src, size_t width, size_t height, int channels, float *dst,
+                                   size_t out_width, size_t out_height, int filter, const mb200_filter_options *options);
 MB200_API int mb200_resize_image(const float *src, size_t width, size_t height, int channels,
     float *dst, size_t out_width, size_t out_height, int filter);
 MB200_API int mb200_sample_image(const float *src, size_t width, size_t height, int channels,

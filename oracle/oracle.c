@@ -842,12 +842,17 @@ static double bessel_order_one(double x)
 }
 
 /* resize.c:803-1226 AcquireResizeFilter with no "filter:*" artifacts, not cylindrical */
-static int rfilter_init(rfilter *rf, int filter)
+static int rfilter_init_ex(rfilter *rf, int filter, const orc_filter_options *opt)
 {
   int ft, wt;
+  const unsigned set = opt ? opt->set : 0u;
   double B = 0.0, C = 0.0;
   if (filter <= ORC_F_UNDEFINED || filter >= ORC_F_SENTINEL) return -1;
   ft = map_filter[filter]; wt = map_window[filter];
+  if ((set & ORC_FO_WINDOW) && opt->window > ORC_F_UNDEFINED && opt->window < ORC_F_SENTINEL) {   /* :999-1043 */
+    if (!opt->keep_filter) ft = ORC_F_SINCFAST;
+    wt = opt->window;
+  }
   memset(rf, 0, sizeof(*rf));
   rf->blur = 1.0;
   rf->filter_fn = fn_table[ft].fn;
@@ -859,13 +864,22 @@ static int rfilter_init(rfilter *rf, int filter)
   if (ft == ORC_F_LANCZOS2_SHARP) rf->blur *= 0.9549963639785485;
   if (rf->filter_fn == FN_GAUSSIAN || rf->window_fn == FN_GAUSSIAN) {   /* :1083-1097 */
     double value = 0.5;
+    if (set & ORC_FO_SIGMA) value = opt->sigma;
     rf->coef[0] = value;
     rf->coef[1] = precip(2.0 * value * value);
     rf->coef[2] = precip(TWOPI_ * value * value);
+    if (value > 0.5) rf->support *= 2 * value;                         /* :1097-1098 */
   }
-  if (rf->filter_fn == FN_KAISER || rf->window_fn == FN_KAISER) {       /* :1104-1120, default beta */
-    rf->coef[0] = 6.5;
-    rf->coef[1] = precip(bessel_i0(6.5));
+  if (rf->filter_fn == FN_KAISER || rf->window_fn == FN_KAISER) {       /* :1104-1120 */
+    double value = 6.5;
+    if (set & ORC_FO_KAISER_BETA) value = opt->kaiser_beta;
+    rf->coef[0] = value;
+    rf->coef[1] = precip(bessel_i0(value));
+  }
+  if (set & ORC_FO_LOBES) {                                             /* :1123-1133 */
+    long lobes = opt->lobes;
+    if (lobes < 1) lobes = 1;
+    rf->support = (double) lobes;
   }
   if (rf->filter_fn == FN_JINC) {                                       /* :1135-1150: lobes -> first zeros of the Jinc */
     static const double jinc_zeros[16] = {
@@ -876,12 +890,23 @@ static int rfilter_init(rfilter *rf, int filter)
     if (rf->support > 16) rf->support = jinc_zeros[15];
     else rf->support = jinc_zeros[((long) rf->support) - 1];
   }
+  if (set & ORC_FO_BLUR) rf->blur *= opt->blur;                         /* :1155-1157 */
   if (rf->blur < EPS) rf->blur = EPS;
+  if (set & ORC_FO_SUPPORT) rf->support = fabs(opt->support);           /* :1163-1165 */
   rf->window_support = rf->support;
+  if (set & ORC_FO_WIN_SUPPORT) rf->window_support = fabs(opt->win_support);   /* :1170-1173 */
   rf->scale *= precip(rf->window_support);                              /* :1177 */
   if (rf->filter_fn == FN_CUBICBC || rf->window_fn == FN_CUBICBC) {     /* :1181-1226 */
     B = fn_table[ft].B; C = fn_table[ft].C;
     if (fn_table[wt].fn == FN_CUBICBC) { B = fn_table[wt].B; C = fn_table[wt].C; }
+    if (set & ORC_FO_B) {                                               /* :1196-1212 */
+      B = opt->b;
+      C = (1.0 - B) / 2.0;
+      if (set & ORC_FO_C) C = opt->c;
+    } else if (set & ORC_FO_C) {
+      C = opt->c;
+      B = 1.0 - 2.0 * C;
+    }
     {
       const double twoB = B + B;
       rf->coef[0] = 1.0 - (1.0 / 3.0) * B;
@@ -895,6 +920,8 @@ static int rfilter_init(rfilter *rf, int filter)
   }
   return 0;
 }
+
+static int rfilter_init(rfilter *rf, int filter) { return rfilter_init_ex(rf, filter, NULL); }
 
 /* resize.c:493-587 SincFast, Q16 branch (:547-563) */
 static double sinc_fast(double x)
@@ -997,6 +1024,20 @@ double orc_filter_weight(int f, double x)
   return rfilter_weight(&rf, x);
 }
 
+double orc_filter_weight_ex(int f, const orc_filter_options *options, double x)
+{
+  rfilter rf;
+  if (rfilter_init_ex(&rf, f, options)) return NAN;
+  return rfilter_weight(&rf, x);
+}
+
+double orc_filter_support_ex(int f, const orc_filter_options *options)
+{
+  rfilter rf;
+  if (rfilter_init_ex(&rf, f, options)) return NAN;
+  return rf.support * rf.blur;
+}
+
 double orc_filter_support(int f)
 {
   rfilter rf;
@@ -1074,6 +1115,12 @@ static int resize_axis(const rfilter *rf, const float *src, size_t w, size_t h, 
 int orc_resize(const float *src, size_t w, size_t h, int ch,
                float *dst, size_t ow, size_t oh, int filter)
 {
+  return orc_resize_ex(src, w, h, ch, dst, ow, oh, filter, NULL);
+}
+
+int orc_resize_ex(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh, int filter,
+                  const orc_filter_options *options)
+{
   rfilter rf;
   double xf, yf;
   float *tmp;
@@ -1088,7 +1135,7 @@ int orc_resize(const float *src, size_t w, size_t h, int ch,
   if (filter != ORC_F_UNDEFINED) ft = filter;
   else if (xf == 1.0 && yf == 1.0) ft = ORC_F_POINT;
   else if ((ch == 2 || ch == 4) || (xf * yf) > 1.0) ft = ORC_F_MITCHELL;
-  if (rfilter_init(&rf, ft)) return -1;
+  if (rfilter_init_ex(&rf, ft, options)) return -1;
   if (xf > yf) {
     tmp = (float *) malloc(ow * h * (size_t) ch * sizeof(float));
     if (!tmp) return -1;

@@ -248,6 +248,29 @@ int ref_morphology(const float *src, float *dst, size_t w, size_t h, int ch,
   END
 }
 
+/* ResizeImage with "-define" artifacts: defines = "filter:blur=0.8;filter:lobes=2" (set with SetImageArtifact, like the CLI) */
+__attribute__((visibility("default")))
+int ref_resize_defines(const float *src, size_t w, size_t h, int ch, float *dst, size_t ow, size_t oh, int filter,
+                       const char *defines)
+{
+  BEGIN
+  im = make_image(src, w, h, ch, -1, ex);
+  if (im) {
+    char *copy = AcquireString(defines), *p = copy;
+    while (p != (char *) NULL && *p != '\0') {
+      char *end = strchr(p, ';'), *eq;
+      if (end != (char *) NULL) *end = '\0';
+      eq = strchr(p, '=');
+      if (eq != (char *) NULL) { *eq = '\0'; (void) SetImageArtifact(im, p, eq + 1); }
+      p = end != (char *) NULL ? end + 1 : (char *) NULL;
+    }
+    copy = DestroyString(copy);
+    out = ResizeImage(im, ow, oh, (FilterType) filter, ex);
+    rc = export_image(out, dst, ow, oh, ch, ex);
+  }
+  END
+}
+
 /* filter: FilterType enum value (resample.h:32-69) */
 __attribute__((visibility("default")))
 int ref_resize(const float *src, size_t w, size_t h, int ch,

@@ -57,10 +57,22 @@ def kernel_goldens(out):
     out["kernel/strings"] = np.array(KERNEL_STRINGS)
 
 
+# ResizeImage with "-define filter:*" artifacts (AcquireResizeFilter, resize.c:999-1226): (filter, defines)
+RESIZE_DEFINES = [(22, "filter:blur=0.8"), (22, "filter:lobes=2"), (8, "filter:sigma=0.75"), (16, "filter:kaiser-beta=4.5"),
+                  (12, "filter:b=0.2;filter:c=0.6"), (3, "filter:window=Hann"), (13, "filter:lobes=5;filter:blur=0.9")]
+
+
 def main():
     r, P = util.ref(), util.P
     out = {}
     kernel_goldens(out)
+    src4 = source(4)
+    for n, (filt, defines) in enumerate(RESIZE_DEFINES):
+        for (ow, oh) in ((20, 15), (82, 62)):
+            dst = np.empty((oh, ow, 4), np.float32)
+            assert r.ref_resize_defines(P(src4), W, H, 4, P(dst), ow, oh, filt, defines.encode()) == 0
+            out[f"resizedef/{n}/{ow}x{oh}"] = dst
+    out["resizedef/defines"] = np.array([f"{f}|{d}" for f, d in RESIZE_DEFINES])
     for ch in (3, 4):
         src = source(ch)
         out[f"c{ch}/src"] = src

@@ -262,3 +262,24 @@ def test_cuda_path_matches_reference_golden_r02b(tag):
                 want[..., 2][grey] = 0
         d = util.ulp_or_noise(got, want) if bar else util.ulp_distance(got, want)
         assert int(d.max()) <= bar, (key, int(d.max()))
+
+
+def _defines_to_dict(text):
+    return dict(kv.split("=", 1) for kv in text.split(";"))
+
+
+@pytest.mark.gpu
+def test_cuda_resize_with_defines_matches_reference_golden():
+    """ResizeImage under -define filter:* : the product (python mirror parsing the strings like the shim) against arrays
+    the real reference produced with the same artifacts set."""
+    im = pytest.importorskip("imagemagick_b200")
+    import torch
+    src = np.ascontiguousarray(G2["c4/src"])
+    for n, entry in enumerate(str(x) for x in G2["resizedef/defines"]):
+        filt, defines = entry.split("|", 1)
+        for size in ("20x15", "82x62"):
+            want = G2[f"resizedef/{n}/{size}"]
+            ow, oh = map(int, size.split("x"))
+            got = im.ResizeImage(im.Image(torch.from_numpy(src.copy()).cuda()), ow, oh, int(filt),
+                                 artifacts=_defines_to_dict(defines)).pixels.cpu().numpy()
+            assert util.max_ulp(got, want) <= 1, (entry, size, util.max_ulp(got, want))

@@ -449,6 +449,40 @@ def test_xyz_family_colorspaces(cs, kind):
             assert (d == 0).mean() > 0.99, (ch, frm, to, float((d == 0).mean()))
 
 
+EXPERT_RESIZE = [(22, {"filter:blur": "0.8"}, dict(blur=0.8)), (22, {"filter:lobes": "2"}, dict(lobes=2)),
+                 (8, {"filter:sigma": "0.75"}, dict(sigma=0.75)), (16, {"filter:kaiser-beta": "4.5"}, dict(kaiser_beta=4.5)),
+                 (10, {"filter:b": "0.5"}, dict(b=0.5)), (12, {"filter:b": "0.2", "filter:c": "0.6"}, dict(b=0.2, c=0.6)),
+                 (3, {"filter:window": "Hann"}, dict(window=5)),
+                 (11, {"filter:filter": "true", "filter:window": "Welch"}, dict(window=17, keep_filter=1)),
+                 (13, {"filter:lobes": "5", "filter:blur": "0.9"}, dict(lobes=5, blur=0.9)),
+                 (14, {"filter:support": "2.5", "filter:win-support": "4"}, dict(support=2.5, win_support=4.0)),
+                 (22, {"filter:lobes": "2", "filter:blur": "1.0"}, dict(lobes=2, blur=1.0))]
+
+
+@pytest.mark.parametrize("case", range(len(EXPERT_RESIZE)))
+def test_resize_with_expert_filter_settings(case):
+    """-define filter:* (AcquireResizeFilter, resize.c:999-1226): the python mirror parses the strings like the shim, the
+    library builds the reference's weights from the values; integer reductions take the streaming / TMA kernels."""
+    import ctypes as C
+    filt, artifacts, values = EXPERT_RESIZE[case]
+    opts = util.FilterOptions.of(**values)
+    for ch in (3, 4):
+        src = make_image(256, 192, ch, seed=80 + case, kind="alpha_blocks" if ch == 4 else "noise")
+        for (ow, oh) in ((128, 96), (100, 77), (384, 300)):
+            want = np.empty((oh, ow, ch), np.float32)
+            assert oracle().orc_resize_ex(P(src), 256, 192, ch, P(want), ow, oh, filt, C.byref(opts)) == 0
+            got = _host(im.ResizeImage(_dev(src), ow, oh, filt, artifacts=artifacts))
+            assert max_ulp(got, want) <= 1, (filt, artifacts, ch, ow, oh)
+    src = make_image(64, 48, 4, seed=2)
+    want = np.empty((24, 32, 4), np.float32)
+    assert oracle().orc_resize_ex(P(src), 64, 48, 4, P(want), 32, 24, filt, C.byref(opts)) == 0
+    assert max_ulp(im.ResizeImage(im.Image(src), 32, 24, filt, artifacts=artifacts).pixels, want) <= 1
+    # the table cache keys on the settings: the plain filter right after must not see them
+    plain = np.empty((24, 32, 4), np.float32)
+    assert oracle().orc_resize(P(src), 64, 48, 4, P(plain), 32, 24, filt) == 0
+    assert max_ulp(im.ResizeImage(im.Image(src), 32, 24, filt).pixels, plain) <= 1
+
+
 def test_resize_lanczos_2x_down_2048():
     """configs[2] at 1/8 scale: Lanczos 2x downscale, 1-ULP check against the CPU result."""
     src = make_image(2048, 2048, 4, seed=42)

@@ -51,7 +51,9 @@ def test_kernel_list_and_user_arrays():
     assert (x, y) == (0, 2) and np.isnan(v[1, 2]) and np.isnan(v[2, 2]) and v[2, 0] == 3
     (v, x, y), = im.AcquireKernelInfo("1,1,1,1,4,1,1,1,1").arrays()
     assert v.shape == (3, 3) and (x, y) == (1, 1) and v[1, 1] == 4
-    for bad in ("nosuch:3", "3x3: 1,2,3", "", "Disk:3>"):
+    assert len(im.AcquireKernelInfo("Disk:3>").arrays()) == 1        # a disk turned by 90 degrees is the same disk: no list
+    assert len(im.AcquireKernelInfo("3>: 0,0,nan 0,1,1 nan,1,nan").arrays()) == 4
+    for bad in ("nosuch:3", "3x3: 1,2,3", "", "Sobel@"):
         with pytest.raises(im.MagickB200Error):
             im.AcquireKernelInfo(bad)
 
@@ -75,6 +77,40 @@ def test_filter_weights_match_oracle(filt):
     for x in np.concatenate([np.linspace(-5.0, 5.0, 401), [2.5464790894703255, 2.6, 3.2383154841662362, 0.999999, 1.0]]):
         a, b = lib.mb200_resize_filter_weight(filt, float(x)), o.orc_filter_weight(filt, float(x))
         assert a == b or (np.isnan(a) and np.isnan(b)), (filt, x)
+
+
+EXPERT = [(22, dict(blur=0.8)), (22, dict(lobes=2)), (22, dict(lobes=5, blur=1.1)), (8, dict(sigma=0.75)),
+          (8, dict(sigma=0.3, support=1.25)), (16, dict(kaiser_beta=4.5)), (16, dict(kaiser_beta=8.0, lobes=4)), (10, dict(b=0.5)),
+          (10, dict(c=0.75)), (12, dict(b=0.2, c=0.6)), (3, dict(window=5)), (22, dict(window=7, win_support=2.0)),
+          (11, dict(window=17, keep_filter=1)), (13, dict(lobes=2)), (13, dict(lobes=20, blur=0.9)), (21, dict(support=3.0)),
+          (14, dict(support=2.5, win_support=4.0))]
+
+
+@pytest.mark.parametrize("filt,values", EXPERT)
+def test_expert_filter_settings_match_oracle(filt, values):
+    """The "filter:*" settings as values (mb200_filter_options): weights, support and whole contribution tables are the
+    oracle's -- which is pinned to the reference with the artifacts set (test_resize_expert_settings_bit_exact)."""
+    lib, o = _lib.load(), util.oracle()
+    opts = util.FilterOptions.of(**values)
+    ref = C.byref(opts)
+    assert lib.mb200_resize_filter_support_ex(filt, ref) == o.orc_filter_support_ex(filt, ref)
+    for x in np.linspace(-6.0, 6.0, 241):
+        a, b = lib.mb200_resize_filter_weight_ex(filt, ref, float(x)), o.orc_filter_weight_ex(filt, ref, float(x))
+        assert a == b or (np.isnan(a) and np.isnan(b)), (filt, values, x)
+    # the image-level oracle and the host table builder agree on which taps exist (a 1-D image makes the table visible)
+    n_in, n_out = 97, 41
+    taps = lib.mb200_resize_contributions_ex(filt, ref, n_in, n_out, n_out / n_in, None, None, None, 0)
+    assert taps > 0
+    start, count = (C.c_long * n_out)(), (C.c_int * n_out)()
+    w = (C.c_double * (n_out * taps))()
+    assert lib.mb200_resize_contributions_ex(filt, ref, n_in, n_out, n_out / n_in, start, count, w, taps) == taps
+    w = np.array(w).reshape(n_out, taps)
+    src = util.make_image(n_in, 1, 1, seed=3)
+    want = np.empty((1, n_out, 1), np.float32)
+    assert o.orc_resize_ex(util.P(src), n_in, 1, 1, util.P(want), n_out, 1, filt, ref) == 0
+    line = src[0, :, 0].astype(np.float64)
+    got = np.array([np.float32(sum(w[k, j] * line[start[k] + j] for j in range(count[k]))) for k in range(n_out)], np.float32)
+    assert util.max_ulp(got.reshape(1, n_out, 1), want) <= 1
 
 
 def test_resize_contributions_lanczos_2x():

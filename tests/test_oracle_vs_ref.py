@@ -218,6 +218,45 @@ def test_hexcone_colorspaces_bit_exact(cs, kind):
         assert max_ulp(np.where(ok, a, np.float32(0)), np.where(ok, b, np.float32(0))) == 0, (frm, to)
 
 
+# (filter, "-define" string as the CLI would set it, the same settings as values)
+FILTER_DEFINES = [
+    (22, "filter:blur=0.8", dict(blur=0.8)),
+    (22, "filter:lobes=2", dict(lobes=2)),
+    (22, "filter:lobes=5;filter:blur=1.1", dict(lobes=5, blur=1.1)),
+    (8, "filter:sigma=0.75", dict(sigma=0.75)),
+    (8, "filter:sigma=0.3;filter:support=1.25", dict(sigma=0.3, support=1.25)),
+    (16, "filter:kaiser-beta=4.5", dict(kaiser_beta=4.5)),
+    (16, "filter:kaiser-alpha=2.0", dict(kaiser_beta=2.0 * 3.14159265358979323846264338327950288419716939937510)),
+    (16, "filter:alpha=8;filter:lobes=4", dict(kaiser_beta=8.0, lobes=4)),
+    (10, "filter:b=0.5", dict(b=0.5)),
+    (10, "filter:c=0.75", dict(c=0.75)),
+    (12, "filter:b=0.2;filter:c=0.6", dict(b=0.2, c=0.6)),
+    (3, "filter:window=Hann", dict(window=5)),
+    (22, "filter:window=Blackman;filter:win-support=2", dict(window=7, win_support=2.0)),
+    (11, "filter:filter=true;filter:window=Welch", dict(window=17, keep_filter=1)),
+    (13, "filter:lobes=2", dict(lobes=2)),
+    (13, "filter:lobes=20;filter:blur=0.9", dict(lobes=20, blur=0.9)),
+    (21, "filter:support=3", dict(support=3.0)),
+    (14, "filter:support=2.5;filter:win-support=4", dict(support=2.5, win_support=4.0)),
+    (22, "filter:filter=Mitchell", dict()),                 # not a truthy string: ignored by this version (resize.c:1000)
+]
+
+
+@pytest.mark.parametrize("case", range(len(FILTER_DEFINES)))
+def test_resize_expert_settings_bit_exact(case):
+    """AcquireResizeFilter's "filter:*" artifacts (resize.c:999-1226): the reference with the artifacts set as the CLI's
+    -define does, the oracle with the same settings as values."""
+    filt, defines, values = FILTER_DEFINES[case]
+    opts = util.FilterOptions.of(**values)
+    for ch in (3, 4):
+        src = make_image(47, 33, ch, seed=5 + case, kind="alpha_blocks" if ch == 4 else "noise")
+        for ow, oh in ((23, 16), (94, 66), (47, 10), (31, 33)):
+            a, b = np.empty((oh, ow, ch), np.float32), np.empty((oh, ow, ch), np.float32)
+            assert util.ref().ref_resize_defines(P(src), 47, 33, ch, P(a), ow, oh, filt, defines.encode()) == 0
+            assert oracle().orc_resize_ex(P(src), 47, 33, ch, P(b), ow, oh, filt, C.byref(opts)) == 0
+            assert max_ulp(a, b) == 0, (filt, defines, ow, oh)
+
+
 XYZ_FAMILY = [12, 13, 14, 16, 17, 25, 35, 36, 37, 38, 39, 40]   # LCH, LCHab, LCHuv, LMS, Luv, xyY, DisplayP3, Adobe98, ProPhoto, Oklab, Oklch, CAT02LMS
 
 

@@ -52,6 +52,11 @@ def oracle() -> C.CDLL:
         o.orc_emboss_kernel.argtypes = [_d, _d, C.POINTER(OrcKernel)]
         o.orc_equalize.argtypes = [_fp, _sz, _sz, _i, _i]
         o.orc_resize.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz, _i]
+        o.orc_resize_ex.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz, _i, C.c_void_p]
+        o.orc_filter_weight_ex.argtypes = [_i, C.c_void_p, _d]
+        o.orc_filter_weight_ex.restype = _d
+        o.orc_filter_support_ex.argtypes = [_i, C.c_void_p]
+        o.orc_filter_support_ex.restype = _d
         o.orc_colorspace.argtypes = [_fp, _sz, _sz, _i, _i, _i]
         o.orc_sample.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         o.orc_scale.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
@@ -103,6 +108,7 @@ def ref() -> C.CDLL:
         r.ref_convolve.argtypes = [_fp, _fp, _sz, _sz, _i, C.c_char_p]
         r.ref_morphology.argtypes = [_fp, _fp, _sz, _sz, _i, _i, _l, C.c_char_p]
         r.ref_resize.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz, _i]
+        r.ref_resize_defines.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz, _i, C.c_char_p]
         r.ref_colorspace.argtypes = [_fp, _sz, _sz, _i, _i, _i]
         r.ref_sample.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         r.ref_scale.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
@@ -164,6 +170,26 @@ def ulp_distance(a: np.ndarray, b: np.ndarray) -> np.ndarray:
 
 def max_ulp(a, b) -> int:
     return int(ulp_distance(np.ascontiguousarray(a), np.ascontiguousarray(b)).max())
+
+
+class FilterOptions(C.Structure):
+    """mb200_filter_options == orc_filter_options: the "filter:*" expert settings as values."""
+    _fields_ = [("set", C.c_uint), ("window", C.c_int), ("keep_filter", C.c_int), ("lobes", C.c_long), ("sigma", C.c_double),
+                ("kaiser_beta", C.c_double), ("blur", C.c_double), ("support", C.c_double), ("win_support", C.c_double),
+                ("b", C.c_double), ("c", C.c_double)]
+
+    BITS = {"window": 1, "sigma": 2, "kaiser_beta": 4, "lobes": 8, "blur": 16, "support": 32, "win_support": 64, "b": 128, "c": 256}
+
+    @classmethod
+    def of(cls, **kw):
+        o = cls()
+        for k, v in kw.items():
+            if k == "keep_filter":
+                o.keep_filter = int(v)
+                continue
+            setattr(o, k, v)
+            o.set |= cls.BITS[k]
+        return o
 
 
 def ulp_or_noise(a, b, tiny=1.0e-6) -> np.ndarray:
