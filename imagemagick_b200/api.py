@@ -56,7 +56,7 @@ HitAndMissMorphology, ThinningMorphology, ThickenMorphology = 18, 19, 20
 LabColorspace, RGBColorspace, sRGBColorspace, XYZColorspace = 11, 21, 23, 26
 CMYColorspace, OHTAColorspace, Rec601YCbCrColorspace, Rec709YCbCrColorspace = 1, 18, 19, 20
 YCbCrColorspace, YDbDrColorspace, YIQColorspace, YPbPrColorspace, YUVColorspace = 27, 29, 30, 31, 32
-LCHColorspace, LCHabColorspace, LCHuvColorspace, OklabColorspace, OklchColorspace = 12, 13, 14, 38, 39
+LCHColorspace, LCHabColorspace, LCHuvColorspace, OklabColorspace, OklchColorspace, JzazbzColorspace = 12, 13, 14, 38, 39, 34
 LMSColorspace, LuvColorspace, xyYColorspace, DisplayP3Colorspace, Adobe98Colorspace, ProPhotoColorspace, CAT02LMSColorspace = 16, 17, 25, 35, 36, 37, 40
 HCLColorspace, HCLpColorspace, HSBColorspace, HSIColorspace, HSLColorspace, HSVColorspace, HWBColorspace = 4, 5, 6, 7, 8, 9, 10
 

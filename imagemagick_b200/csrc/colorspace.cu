@@ -419,6 +419,45 @@ __device__ __forceinline__ void luv_to_xyz_d(double L, double u, double v, doubl
 }
 constexpr double kPiD = 3.14159265358979323846264338327950288419716939937510;
 
+// Jzazbz (colorspace-private.h:1274-1478) with the default white luminance of 10000 (colorspace.c:995): a perceptual
+// quantiser (two pow() per LMS component) around an LMS matrix.  NaN results (negative bases) become 0 / 0.5 / 0.5.
+constexpr double kJzB = 1.15, kJzG = 0.66, kJzC1 = 3424.0 / 4096.0, kJzC2 = 2413.0 / 128.0, kJzC3 = 2392.0 / 128.0,
+                 kJzN = 2610.0 / 16384.0, kJzP = 1.7 * 2523.0 / 32.0, kJzD = -0.56, kJzD0 = 1.6295499532821566e-11,
+                 kJzWhite = 10000.0;
+__device__ __forceinline__ void xyz_to_jzazbz(double X, double Y, double Z, double &Jz, double &az, double &bz) {
+  const double wlr = perceptible_reciprocal_d(kJzWhite);
+  const double Xp = Z + kJzB * (X - Z), Yp = X + kJzG * (Y - X);
+  const double L = 0.0146480 * Z + 0.41478972 * Xp + 0.579999 * Yp;
+  const double M = 0.0531008 * Z + (-0.2015100) * Xp + 1.120649 * Yp;
+  const double S = 0.6684799 * Z + (-0.0166008) * Xp + 0.264800 * Yp;
+  auto pq = [](double v) { const double g = pow(v, kJzN); return pow((kJzC1 + kJzC2 * g) / (1.0 + kJzC3 * g), kJzP); };
+  const double Lp = pq(L * wlr), Mp = pq(M * wlr), Sp = pq(S * wlr);
+  const double Iz = (Lp + Mp) * 0.5, JdI = kJzD * Iz;
+  const double J = (JdI + Iz) / (JdI + 1.0) - kJzD0;
+  const double a = 0.5 + 3.52400 * Lp + (-4.066708) * Mp + 0.542708 * Sp;
+  const double b = 0.5 + 0.199076 * Lp + 1.096799 * Mp + (-1.295875) * Sp;
+  Jz = J != J ? 0.0 : J; az = a != a ? 0.5 : a; bz = b != b ? 0.5 : b;
+}
+__device__ __forceinline__ void jzazbz_to_xyz(double Jz, double az, double bz, double &X, double &Y, double &Z) {
+  const double g = Jz + kJzD0, azz = az - 0.5, bzz = bz - 0.5;
+  const double C = 0.138605043271539 * azz + 0.0580473161561189 * bzz;
+  double Sp = g / (1.0 + kJzD * (1.0 - g));
+  const double Lp = Sp + C, Mp = Sp - C;
+  Sp += (-0.0960192420263189) * azz;
+  Sp += (-0.811891896056039) * bzz;
+  auto inv = [](double v) { const double gg = pow(v, 1.0 / kJzP); return pow((gg - kJzC1) / (kJzC2 + (-2392.0 / 128.0) * gg), 1.0 / kJzN) * kJzWhite; };
+  const double L = inv(Lp), M = inv(Mp), S = inv(Sp);
+  double Zp = (-0.0909828109828476) * L + (-0.312728290523074) * M + 1.52276656130526 * S;
+  double Xp = 1.92422643578761 * L + (-1.00479231259537) * M + 0.037651404030618 * S;
+  double Yp = 0.350316762094999 * L + 0.726481193931655 * M + (-0.065384422948085) * S;
+  Zp = Zp != Zp ? 0.0 : Zp;
+  Xp = Zp + (Xp - Zp) / kJzB;
+  Xp = Xp != Xp ? 0.0 : Xp;
+  Yp = Xp + (Yp - Xp) / kJzG;
+  Yp = Yp != Yp ? 0.0 : Yp;
+  X = Xp; Y = Yp; Z = Zp;
+}
+
 template <int CH>
 __global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npixels, int space, int forward) {
   __shared__ double s_scale[128];
@@ -432,7 +471,18 @@ __global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npix
   else { in0 = q[0]; in1 = q[1]; in2 = q[2]; }
   const int rgb = space == MB200_Adobe98Colorspace ? 0 : space == MB200_DisplayP3Colorspace ? 1 : space == MB200_ProPhotoColorspace ? 2 : -1;
   double o0, o1, o2;
-  if (space == MB200_OklabColorspace || space == MB200_OklchColorspace) {      // colorspace-private.h:1480-1549
+  if (space == MB200_JzazbzColorspace) {          // the reference swaps green and blue on the way in and out (:1373, :1476)
+    double X, Y, Z;
+    if (forward) {
+      double J, a, b;
+      rgb_to_xyz(in0, in2, in1, X, Y, Z, s_scale);
+      xyz_to_jzazbz(X, Y, Z, J, a, b);
+      o0 = QR * J; o1 = QR * a; o2 = QR * b;
+    } else {
+      jzazbz_to_xyz(QS * static_cast<double>(in0), QS * static_cast<double>(in1), QS * static_cast<double>(in2), X, Y, Z);
+      xyz_to_rgb(X, Y, Z, o0, o2, o1);
+    }
+  } else if (space == MB200_OklabColorspace || space == MB200_OklchColorspace) {      // colorspace-private.h:1480-1549
     if (forward) {
       const double R = QS * decode_pixel_gamma_tab(in0, s_scale), G = QS * decode_pixel_gamma_tab(in1, s_scale),
                    B = QS * decode_pixel_gamma_tab(in2, s_scale);
@@ -526,7 +576,7 @@ __global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npix
 
 bool is_xyz_family(int cs) {
   if (cs == MB200_LCHColorspace || cs == MB200_LCHabColorspace || cs == MB200_LCHuvColorspace || cs == MB200_OklabColorspace ||
-      cs == MB200_OklchColorspace)
+      cs == MB200_OklchColorspace || cs == MB200_JzazbzColorspace)
     return true;
   return cs == MB200_Adobe98Colorspace || cs == MB200_DisplayP3Colorspace || cs == MB200_ProPhotoColorspace ||
          cs == MB200_LMSColorspace || cs == MB200_CAT02LMSColorspace || cs == MB200_xyYColorspace || cs == MB200_LuvColorspace;

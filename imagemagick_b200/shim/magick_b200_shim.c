@@ -457,6 +457,7 @@ static int map_colorspace(ColorspaceType c)
     case LCHColorspace: return MB200_LCHColorspace;
     case LCHabColorspace: return MB200_LCHabColorspace;
     case LCHuvColorspace: return MB200_LCHuvColorspace;
+    case JzazbzColorspace: return MB200_JzazbzColorspace;
     case OklabColorspace: return MB200_OklabColorspace;
     case OklchColorspace: return MB200_OklchColorspace;
     case LMSColorspace: return MB200_LMSColorspace;

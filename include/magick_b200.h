@@ -114,6 +114,7 @@ typedef enum {
   MB200_YIQColorspace = 30,
   MB200_YPbPrColorspace = 31,
   MB200_YUVColorspace = 32,
+  MB200_JzazbzColorspace = 34,
   MB200_DisplayP3Colorspace = 35,
   MB200_Adobe98Colorspace = 36,
   MB200_ProPhotoColorspace = 37,

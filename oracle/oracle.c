@@ -1804,11 +1804,73 @@ static void oklab_to_rgb(double L, double a, double b, double *red, double *gree
   *green = encode_pixel_gamma(QR * G);
   *blue = encode_pixel_gamma(QR * B);
 }
+/* Jzazbz (colorspace-private.h:1274-1478; white_luminance = 10000 unless the "white-luminance" property says otherwise,
+   colorspace.c:995-998).  Quirks kept: RGB -> XYZ is called with green and blue swapped, and so is XYZ -> RGB. */
+#define JZ_B 1.15
+#define JZ_G 0.66
+#define JZ_C1 (3424.0 / 4096.0)
+#define JZ_C2 (2413.0 / 128.0)
+#define JZ_C3 (2392.0 / 128.0)
+#define JZ_N (2610.0 / 16384.0)
+#define JZ_P (1.7 * 2523.0 / 32.0)
+#define JZ_D (-0.56)
+#define JZ_D0 1.6295499532821566e-11
+static void xyz_to_jzazbz(double X, double Y, double Z, double white_luminance, double *Jz, double *az, double *bz)
+{
+  double a, b, dL, dM, dS, gL, gM, gS, nL, nM, nS, Iz, J, JdI, L, Lp, M, Mp, S, Sp, WLr, Xp, Yp;
+  WLr = precip(white_luminance);
+  Xp = Z + JZ_B * (X - Z);
+  Yp = X + JZ_G * (Y - X);
+  L = 0.0146480 * Z; M = 0.0531008 * Z; S = 0.6684799 * Z;
+  L += 0.41478972 * Xp; M += (-0.2015100) * Xp; S += (-0.0166008) * Xp;
+  L += 0.579999 * Yp; M += 1.120649 * Yp; S += 0.264800 * Yp;
+  gL = pow(L * WLr, JZ_N); gM = pow(M * WLr, JZ_N); gS = pow(S * WLr, JZ_N);
+  nL = JZ_C1 + JZ_C2 * gL; nM = JZ_C1 + JZ_C2 * gM; nS = JZ_C1 + JZ_C2 * gS;
+  dL = 1.0 + JZ_C3 * gL; dM = 1.0 + JZ_C3 * gM; dS = 1.0 + JZ_C3 * gS;
+  Lp = pow(nL / dL, JZ_P); Mp = pow(nM / dM, JZ_P); Sp = pow(nS / dS, JZ_P);
+  Iz = (Lp + Mp) * 0.5;
+  JdI = JZ_D * Iz;
+  J = (JdI + Iz) / (JdI + 1.0) - JZ_D0;
+  a = 0.5 + 3.52400 * Lp; b = 0.5 + 0.199076 * Lp;
+  a += (-4.066708) * Mp; b += 1.096799 * Mp;
+  a += 0.542708 * Sp; b += (-1.295875) * Sp;
+  *Jz = isnan(J) ? 0.0 : J;
+  *az = isnan(a) ? 0.5 : a;
+  *bz = isnan(b) ? 0.5 : b;
+}
+static void jzazbz_to_xyz(double Jz, double az, double bz, double white_luminance, double *X, double *Y, double *Z)
+{
+  double azz, bzz, C, dL, dM, dS, g, gL, gM, gS, Jnr, Jpr, L, Lp, M, Mp, S, Sp, nL, nM, nS, Xp, Zp, Yp;
+  g = Jz + JZ_D0;
+  azz = az - 0.5; bzz = bz - 0.5;
+  C = 0.138605043271539 * azz + 0.0580473161561189 * bzz;
+  Sp = g / (1.0 + JZ_D * (1.0 - g));
+  Lp = Sp + C; Mp = Sp - C;
+  Sp += (-0.0960192420263189) * azz;
+  Sp += (-0.811891896056039) * bzz;
+  Jpr = 1.0 / JZ_P;
+  gL = pow(Lp, Jpr); gM = pow(Mp, Jpr); gS = pow(Sp, Jpr);
+  Jnr = 1.0 / JZ_N;
+  nL = gL - JZ_C1; nM = gM - JZ_C1; nS = gS - JZ_C1;
+  dL = JZ_C2 + (-2392.0 / 128.0) * gL; dM = JZ_C2 + (-2392.0 / 128.0) * gM; dS = JZ_C2 + (-2392.0 / 128.0) * gS;
+  L = pow(nL / dL, Jnr); M = pow(nM / dM, Jnr); S = pow(nS / dS, Jnr);
+  L *= white_luminance; M *= white_luminance; S *= white_luminance;
+  Zp = (-0.0909828109828476) * L; Xp = 1.92422643578761 * L; Yp = 0.350316762094999 * L;
+  Zp += (-0.312728290523074) * M; Xp += (-1.00479231259537) * M; Yp += 0.726481193931655 * M;
+  Zp += 1.52276656130526 * S; Xp += 0.037651404030618 * S; Yp += (-0.065384422948085) * S;
+  Zp = isnan(Zp) ? 0.0 : Zp;
+  Xp = Zp + (Xp - Zp) / JZ_B;
+  Xp = isnan(Xp) ? 0.0 : Xp;
+  Yp = Xp + (Yp - Xp) / JZ_G;
+  Yp = isnan(Yp) ? 0.0 : Yp;
+  *Z = Zp; *X = Xp; *Y = Yp;
+}
 static double degrees_to_radians(double degrees) { return (double) (PI_ * degrees / 180.0); }   /* image-private.h:142 */
 
 static int is_xyz_family_space(int cs)
 {
-  if (cs == ORC_CS_OKLAB || cs == ORC_CS_OKLCH || cs == ORC_CS_LCH || cs == ORC_CS_LCHAB || cs == ORC_CS_LCHUV) return 1;
+  if (cs == ORC_CS_OKLAB || cs == ORC_CS_OKLCH || cs == ORC_CS_LCH || cs == ORC_CS_LCHAB || cs == ORC_CS_LCHUV ||
+      cs == ORC_CS_JZAZBZ) return 1;
   return cs == ORC_CS_ADOBE98 || cs == ORC_CS_DISPLAYP3 || cs == ORC_CS_PROPHOTO || cs == ORC_CS_LMS ||
          cs == ORC_CS_CAT02LMS || cs == ORC_CS_XYY || cs == ORC_CS_LUV;
 }
@@ -1821,6 +1883,19 @@ static int colorspace_xyz_family_leg(float *buf, long n, int ch, int cs, int for
   for (i = 0; i < n; i++) {
     float *q = buf + (size_t) i * ch;
     double X, Y, Z, a, b, c;
+    if (cs == ORC_CS_JZAZBZ) {                               /* :1365-1376, :1467-1478: note the swapped arguments */
+      if (forward) {
+        rgb_to_xyz((double) q[0], (double) q[2], (double) q[1], &X, &Y, &Z);
+        xyz_to_jzazbz(X, Y, Z, 10000.0, &a, &b, &c);
+        q[0] = (float) (QR * a); q[1] = (float) (QR * b); q[2] = (float) (QR * c);
+      } else {
+        double R, G, B;
+        jzazbz_to_xyz(QS * q[0], QS * q[1], QS * q[2], 10000.0, &X, &Y, &Z);
+        xyz_to_rgb(X, Y, Z, &R, &B, &G);
+        q[0] = (float) R; q[1] = (float) G; q[2] = (float) B;
+      }
+      continue;
+    }
     if (cs == ORC_CS_OKLAB || cs == ORC_CS_OKLCH) {          /* not routed through XYZ */
       if (forward) {
         rgb_to_oklab((double) q[0], (double) q[1], (double) q[2], &a, &b, &c);

@@ -13,7 +13,7 @@ import util  # noqa: E402
 OUT = Path(__file__).resolve().parent / "r02b_golden.npz"
 W, H = 41, 31
 HEXCONE = {"hcl": 4, "hclp": 5, "hsb": 6, "hsi": 7, "hsl": 8, "hsv": 9, "hwb": 10,
-           "lch": 12, "lchab": 13, "lchuv": 14, "oklab": 38, "oklch": 39, "lms": 16, "luv": 17, "xyy": 25, "displayp3": 35, "adobe98": 36, "prophoto": 37, "cat02lms": 40}
+           "lch": 12, "lchab": 13, "lchuv": 14, "oklab": 38, "oklch": 39, "jzazbz": 34, "lms": 16, "luv": 17, "xyy": 25, "displayp3": 35, "adobe98": 36, "prophoto": 37, "cat02lms": 40}
 
 
 def source(ch):

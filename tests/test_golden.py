@@ -184,8 +184,8 @@ def test_cuda_path_matches_reference_golden(tag):
 G2 = np.load(Path(__file__).resolve().parent / "golden" / "r02b_golden.npz")
 FILTERS2 = {"jinc": 13, "kaiser": 16}
 HEXCONE2 = {"hcl": 4, "hclp": 5, "hsb": 6, "hsi": 7, "hsl": 8, "hsv": 9, "hwb": 10, "srgb": 23,
-            "lch": 12, "lchab": 13, "lchuv": 14, "oklab": 38, "oklch": 39, "lms": 16, "luv": 17, "xyy": 25, "displayp3": 35, "adobe98": 36, "prophoto": 37, "cat02lms": 40}
-SMOOTH2 = ("hsi", "lch", "lchab", "lchuv", "oklab", "oklch", "lms", "luv", "xyy", "displayp3", "adobe98", "prophoto", "cat02lms")    # <= 1 ULP; the others bit exact
+            "lch": 12, "lchab": 13, "lchuv": 14, "oklab": 38, "oklch": 39, "jzazbz": 34, "lms": 16, "luv": 17, "xyy": 25, "displayp3": 35, "adobe98": 36, "prophoto": 37, "cat02lms": 40}
+SMOOTH2 = ("hsi", "jzazbz", "lch", "lchab", "lchuv", "oklab", "oklch", "lms", "luv", "xyy", "displayp3", "adobe98", "prophoto", "cat02lms")    # <= 1 ULP; the others bit exact
 
 
 def _r02b_cases(tag):

@@ -410,7 +410,7 @@ def test_hexcone_colorspaces(cs, kind):
     assert max_ulp(h.pixels, want) <= bar
 
 
-XYZ_FAMILY = [12, 13, 14, 16, 17, 25, 35, 36, 37, 38, 39, 40]   # LCH, LCHab, LCHuv, LMS, Luv, xyY, DisplayP3, Adobe98, ProPhoto, Oklab, Oklch, CAT02LMS
+XYZ_FAMILY = [12, 13, 14, 16, 17, 25, 34, 35, 36, 37, 38, 39, 40]   # (34 = Jzazbz) LCH, LCHab, LCHuv, LMS, Luv, xyY, DisplayP3, Adobe98, ProPhoto, Oklab, Oklch, CAT02LMS
 POLAR = (12, 13, 14)                            # hue = atan2 of two differences that cancel for achromatic pixels
 
 

@@ -257,7 +257,7 @@ def test_resize_expert_settings_bit_exact(case):
             assert max_ulp(a, b) == 0, (filt, defines, ow, oh)
 
 
-XYZ_FAMILY = [12, 13, 14, 16, 17, 25, 35, 36, 37, 38, 39, 40]   # LCH, LCHab, LCHuv, LMS, Luv, xyY, DisplayP3, Adobe98, ProPhoto, Oklab, Oklch, CAT02LMS
+XYZ_FAMILY = [12, 13, 14, 16, 17, 25, 34, 35, 36, 37, 38, 39, 40]   # (34 = Jzazbz) LCH, LCHab, LCHuv, LMS, Luv, xyY, DisplayP3, Adobe98, ProPhoto, Oklab, Oklch, CAT02LMS
 
 
 @pytest.mark.parametrize("cs", XYZ_FAMILY)
