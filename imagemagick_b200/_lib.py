@@ -92,6 +92,7 @@ PROTOTYPES = {
     "mb200_resize_image_ex_dev": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i, _vp, _vp]),
     "mb200_resize_image_ex": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i, _vp]),
     "mb200_transform_colorspace_dev": (_i, [_vp, _sz, _sz, _i, _i, _i, _vp]),
+    "mb200_transform_colorspace_ex_dev": (_i, [_vp, _sz, _sz, _i, _i, _i, _vp, _vp]),
     "mb200_blur_image": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d]),
     "mb200_gaussian_blur_image": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d]),
     "mb200_convolve_image": (_i, [_vp, _vp, _sz, _sz, _i, KernelPtr]),
@@ -99,6 +100,7 @@ PROTOTYPES = {
     "mb200_unsharp_mask_image": (_i, [_vp, _vp, _sz, _sz, _i, _d, _d, _d, _d]),
     "mb200_resize_image": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i]),
     "mb200_transform_colorspace": (_i, [_vp, _sz, _sz, _i, _i, _i]),
+    "mb200_transform_colorspace_ex": (_i, [_vp, _sz, _sz, _i, _i, _i, _vp]),
     "mb200_sharpen_kernel": (KernelPtr, [_d, _d]),
     "mb200_edge_kernel": (KernelPtr, [_d]),
     "mb200_restore_channels_dev": (_i, [_vp, _vp, _sz, _sz, _i, C.c_uint, _vp]),

@@ -57,6 +57,7 @@ LabColorspace, RGBColorspace, sRGBColorspace, XYZColorspace = 11, 21, 23, 26
 CMYColorspace, OHTAColorspace, Rec601YCbCrColorspace, Rec709YCbCrColorspace = 1, 18, 19, 20
 YCbCrColorspace, YDbDrColorspace, YIQColorspace, YPbPrColorspace, YUVColorspace = 27, 29, 30, 31, 32
 LCHColorspace, LCHabColorspace, LCHuvColorspace, OklabColorspace, OklchColorspace, JzazbzColorspace = 12, 13, 14, 38, 39, 34
+LogColorspace, YCCColorspace = 15, 28
 LMSColorspace, LuvColorspace, xyYColorspace, DisplayP3Colorspace, Adobe98Colorspace, ProPhotoColorspace, CAT02LMSColorspace = 16, 17, 25, 35, 36, 37, 40
 HCLColorspace, HCLpColorspace, HSBColorspace, HSIColorspace, HSLColorspace, HSVColorspace, HWBColorspace = 4, 5, 6, 7, 8, 9, 10
 
@@ -375,18 +376,48 @@ def ThumbnailImage(image: Image, columns: int, rows: int, filter: int = Undefine
     return out
 
 
-def TransformImageColorspace(image: Image, colorspace: int) -> bool:
-    """MagickCore/colorspace.c:1751 -- in place; updates image.colorspace."""
+class ColorspaceOptions(C.Structure):
+    """mb200_colorspace_options: the image settings sRGBTransformImage / TransformsRGBImage read (MagickCore/colorspace.c:761,
+    :996, :1085-1095) as values."""
+    _fields_ = [("set", C.c_uint), ("illuminant", C.c_int), ("white_luminance", C.c_double), ("film_gamma", C.c_double),
+                ("reference_black", C.c_double), ("reference_white", C.c_double)]
+
+
+_ILLUMINANTS = {"a": 0, "b": 1, "c": 2, "d50": 3, "d55": 4, "d65": 5, "d75": 6, "e": 7, "f2": 8, "f7": 9, "f11": 10}
+
+
+def colorspace_options_from_settings(settings) -> "ColorspaceOptions | None":
+    """What the shim does in C (b200_colorspace_options): the "color:illuminant" artifact and the "white-luminance",
+    "film-gamma", "reference-black", "reference-white" properties.  An unparsable illuminant selects D65 like the
+    reference's UndefinedIlluminant (MagickCore/color.h:42)."""
+    if not settings:
+        return None
+    o = ColorspaceOptions()
+    if "color:illuminant" in settings:
+        o.illuminant, o.set = _ILLUMINANTS.get(str(settings["color:illuminant"]).strip().lower(), 5), o.set | 1
+    for key, field, bit in (("white-luminance", "white_luminance", 2), ("film-gamma", "film_gamma", 4),
+                            ("reference-black", "reference_black", 8), ("reference-white", "reference_white", 16)):
+        if key in settings:
+            setattr(o, field, float(settings[key]))
+            o.set |= bit
+    return o if o.set else None
+
+
+def TransformImageColorspace(image: Image, colorspace: int, settings=None) -> bool:
+    """MagickCore/colorspace.c:1751 -- in place; updates image.colorspace.  `settings`: the image's artifacts / properties
+    the transform reads, e.g. {"color:illuminant": "D50"} or {"reference-white": "700"}."""
     lib = _lib.load()
     if image.colorspace == colorspace:
         return True
+    opts = colorspace_options_from_settings(settings)
+    ref = C.byref(opts) if opts is not None else None
     if image.on_device:
         _activate(image)
-        check(lib.mb200_transform_colorspace_dev(image._ptr(), image.columns, image.rows, image.channels,
-                                                 image.colorspace, colorspace, _stream(image)))
+        check(lib.mb200_transform_colorspace_ex_dev(image._ptr(), image.columns, image.rows, image.channels,
+                                                    image.colorspace, colorspace, ref, _stream(image)))
     else:
-        check(lib.mb200_transform_colorspace(image._ptr(), image.columns, image.rows, image.channels,
-                                             image.colorspace, colorspace))
+        check(lib.mb200_transform_colorspace_ex(image._ptr(), image.columns, image.rows, image.channels,
+                                                image.colorspace, colorspace, ref))
     image.colorspace = colorspace
     return True
 

@@ -776,13 +776,18 @@ int mb200_resize_image_ex_dev(const float *src, size_t width, size_t height, int
   return rc;
 }
 
-int mb200_transform_colorspace_dev(float *buf, size_t width, size_t height, int channels, int from, int to,
-                                   void *stream) {
+int mb200_transform_colorspace_ex_dev(float *buf, size_t width, size_t height, int channels, int from, int to,
+                                      const mb200_colorspace_options *options, void *stream) {
   if (!buf || !valid_image(width, height, channels)) return fail(MB200_EINVAL, "colorspace: bad arguments");
   cudaStream_t s;
   int rc = prepare(stream, &s);
   if (rc) return rc;
-  return launch_colorspace(buf, width * height, channels, from, to, s);
+  return launch_colorspace(buf, width * height, channels, from, to, options, s);
+}
+
+int mb200_transform_colorspace_dev(float *buf, size_t width, size_t height, int channels, int from, int to,
+                                   void *stream) {
+  return mb200_transform_colorspace_ex_dev(buf, width, height, channels, from, to, nullptr, stream);
 }
 
 // ------------------------------------------------------------ host buffers
@@ -842,10 +847,15 @@ int mb200_resize_image(const float *src, size_t w, size_t h, int ch, float *dst,
   return mb200_resize_image_ex(src, w, h, ch, dst, ow, oh, filter, nullptr);
 }
 
-int mb200_transform_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to) {
+int mb200_transform_colorspace_ex(float *buf, size_t w, size_t h, int ch, int from, int to,
+                                  const mb200_colorspace_options *options) {
   if (!buf || !valid_image(w, h, ch)) return fail(MB200_EINVAL, "colorspace: bad arguments");
   return in_place_host(buf, w * h * ch * sizeof(float),
-                       [&](float *d, cudaStream_t st) { return launch_colorspace(d, w * h, ch, from, to, st); });
+                       [&](float *d, cudaStream_t st) { return launch_colorspace(d, w * h, ch, from, to, options, st); });
+}
+
+int mb200_transform_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to) {
+  return mb200_transform_colorspace_ex(buf, w, h, ch, from, to, nullptr);
 }
 
 }  // extern "C"

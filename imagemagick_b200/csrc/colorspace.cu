@@ -19,7 +19,10 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
+#include <vector>
 
 namespace mb200 {
 namespace {
@@ -385,47 +388,52 @@ __device__ __forceinline__ double perceptible_reciprocal_d(double x) {       // 
   const double sign = x < 0.0 ? -1.0 : 1.0;
   return (sign * x) >= 1.0e-12 ? 1.0 / x : sign / 1.0e-12;
 }
-constexpr double kLuvDen = kIllX + 15.0 * kIllY + 3.0 * kIllZ;
-constexpr double kLuvUn = 4.0 * kIllX / kLuvDen, kLuvVn = 9.0 * kIllY / kLuvDen;
+// Per-call settings of the XYZ-derived legs: the reference white (illuminant_tristimulus[], colorspace-private.h:32-46,
+// selected by the "color:illuminant" artifact, colorspace.c:761-773; D65 by default) with the Luv white point derived
+// from it (:608-624, :1150-1159), and Jzazbz's white luminance ("white-luminance" property, colorspace.c:996).
+struct XyzSettings {
+  double ill[3];
+  double un, vn;
+  double white_luminance;
+};
 
 // Lab in unit range (colorspace-private.h:1066-1089) and back (:531-557), for the polar LCHab space
 __device__ __forceinline__ double lab_f(double t) { return t > kCieEps ? cube_root5(t) : (kCieK * t + 16.0) / 116.0; }
-__device__ __forceinline__ void xyz_to_lab_unit(double X, double Y, double Z, double &L, double &a, double &b) {
-  const double x = lab_f(X / kIllX), y = lab_f(Y / kIllY), z = lab_f(Z / kIllZ);
+__device__ __forceinline__ void xyz_to_lab_unit(const XyzSettings &st, double X, double Y, double Z, double &L, double &a, double &b) {
+  const double x = lab_f(X / st.ill[0]), y = lab_f(Y / st.ill[1]), z = lab_f(Z / st.ill[2]);
   L = __dsub_rn(__dmul_rn(116.0, y), 16.0) / 100.0;
   a = (500.0 * (x - y)) / 255.0 + 0.5;
   b = (200.0 * (y - z)) / 255.0 + 0.5;
 }
-__device__ __forceinline__ void lab_to_xyz_d(double L, double a, double b, double &X, double &Y, double &Z) {
+__device__ __forceinline__ void lab_to_xyz_d(const XyzSettings &st, double L, double a, double b, double &X, double &Y, double &Z) {
   double y = (L + 16.0) / 116.0;
   double x = y + a / 500.0, z = y - b / 200.0;
   x = (x * x * x) > kCieEps ? x * x * x : __dsub_rn(__dmul_rn(116.0, x), 16.0) / kCieK;
   y = L > (kCieK * kCieEps) ? y * y * y : L / kCieK;
   z = (z * z * z) > kCieEps ? z * z * z : __dsub_rn(__dmul_rn(116.0, z), 16.0) / kCieK;
-  X = kIllX * x; Y = kIllY * y; Z = kIllZ * z;
+  X = st.ill[0] * x; Y = st.ill[1] * y; Z = st.ill[2] * z;
 }
-__device__ __forceinline__ void xyz_to_luv_unit(double X, double Y, double Z, double &L, double &u, double &v) {
+__device__ __forceinline__ void xyz_to_luv_unit(const XyzSettings &st, double X, double Y, double Z, double &L, double &u, double &v) {
   double l = Y > kCieEps ? __dsub_rn(__dmul_rn(116.0, cube_root5(Y)), 16.0) : kCieK * Y;
   const double alpha = perceptible_reciprocal_d(X + 15.0 * Y + 3.0 * Z);
-  const double uu = 13.0 * l * (4.0 * alpha * X - kLuvUn), vv = 13.0 * l * (9.0 * alpha * Y - kLuvVn);
+  const double uu = 13.0 * l * (4.0 * alpha * X - st.un), vv = 13.0 * l * (9.0 * alpha * Y - st.vn);
   L = l / 100.0; u = (uu + 134.0) / 354.0; v = (vv + 140.0) / 262.0;
 }
-__device__ __forceinline__ void luv_to_xyz_d(double L, double u, double v, double &X, double &Y, double &Z) {
+__device__ __forceinline__ void luv_to_xyz_d(const XyzSettings &st, double L, double u, double v, double &X, double &Y, double &Z) {
   if (L > (kCieK * kCieEps)) { const double t = (L + 16.0) / 116.0; Y = t * t * t; } else Y = L / kCieK;
-  const double pu = ((52.0 * L * perceptible_reciprocal_d(u + 13.0 * L * kLuvUn)) - 1.0) / 3.0;
+  const double pu = ((52.0 * L * perceptible_reciprocal_d(u + 13.0 * L * st.un)) - 1.0) / 3.0;
   const double gamma = perceptible_reciprocal_d(pu - (-1.0 / 3.0));
-  X = gamma * ((Y * ((39.0 * L * perceptible_reciprocal_d(v + 13.0 * L * kLuvVn)) - 5.0)) + 5.0 * Y);
+  X = gamma * ((Y * ((39.0 * L * perceptible_reciprocal_d(v + 13.0 * L * st.vn)) - 5.0)) + 5.0 * Y);
   Z = (X * pu) - 5.0 * Y;
 }
 constexpr double kPiD = 3.14159265358979323846264338327950288419716939937510;
 
-// Jzazbz (colorspace-private.h:1274-1478) with the default white luminance of 10000 (colorspace.c:995): a perceptual
+// Jzazbz (colorspace-private.h:1274-1478; white luminance 10000 unless the image says otherwise, colorspace.c:995): a perceptual
 // quantiser (two pow() per LMS component) around an LMS matrix.  NaN results (negative bases) become 0 / 0.5 / 0.5.
 constexpr double kJzB = 1.15, kJzG = 0.66, kJzC1 = 3424.0 / 4096.0, kJzC2 = 2413.0 / 128.0, kJzC3 = 2392.0 / 128.0,
-                 kJzN = 2610.0 / 16384.0, kJzP = 1.7 * 2523.0 / 32.0, kJzD = -0.56, kJzD0 = 1.6295499532821566e-11,
-                 kJzWhite = 10000.0;
-__device__ __forceinline__ void xyz_to_jzazbz(double X, double Y, double Z, double &Jz, double &az, double &bz) {
-  const double wlr = perceptible_reciprocal_d(kJzWhite);
+                 kJzN = 2610.0 / 16384.0, kJzP = 1.7 * 2523.0 / 32.0, kJzD = -0.56, kJzD0 = 1.6295499532821566e-11;
+__device__ __forceinline__ void xyz_to_jzazbz(double white, double X, double Y, double Z, double &Jz, double &az, double &bz) {
+  const double wlr = perceptible_reciprocal_d(white);
   const double Xp = Z + kJzB * (X - Z), Yp = X + kJzG * (Y - X);
   const double L = 0.0146480 * Z + 0.41478972 * Xp + 0.579999 * Yp;
   const double M = 0.0531008 * Z + (-0.2015100) * Xp + 1.120649 * Yp;
@@ -438,14 +446,14 @@ __device__ __forceinline__ void xyz_to_jzazbz(double X, double Y, double Z, doub
   const double b = 0.5 + 0.199076 * Lp + 1.096799 * Mp + (-1.295875) * Sp;
   Jz = J != J ? 0.0 : J; az = a != a ? 0.5 : a; bz = b != b ? 0.5 : b;
 }
-__device__ __forceinline__ void jzazbz_to_xyz(double Jz, double az, double bz, double &X, double &Y, double &Z) {
+__device__ __forceinline__ void jzazbz_to_xyz(double white, double Jz, double az, double bz, double &X, double &Y, double &Z) {
   const double g = Jz + kJzD0, azz = az - 0.5, bzz = bz - 0.5;
   const double C = 0.138605043271539 * azz + 0.0580473161561189 * bzz;
   double Sp = g / (1.0 + kJzD * (1.0 - g));
   const double Lp = Sp + C, Mp = Sp - C;
   Sp += (-0.0960192420263189) * azz;
   Sp += (-0.811891896056039) * bzz;
-  auto inv = [](double v) { const double gg = pow(v, 1.0 / kJzP); return pow((gg - kJzC1) / (kJzC2 + (-2392.0 / 128.0) * gg), 1.0 / kJzN) * kJzWhite; };
+  auto inv = [white](double v) { const double gg = pow(v, 1.0 / kJzP); return pow((gg - kJzC1) / (kJzC2 + (-2392.0 / 128.0) * gg), 1.0 / kJzN) * white; };
   const double L = inv(Lp), M = inv(Mp), S = inv(Sp);
   double Zp = (-0.0909828109828476) * L + (-0.312728290523074) * M + 1.52276656130526 * S;
   double Xp = 1.92422643578761 * L + (-1.00479231259537) * M + 0.037651404030618 * S;
@@ -459,7 +467,7 @@ __device__ __forceinline__ void jzazbz_to_xyz(double Jz, double az, double bz, d
 }
 
 template <int CH>
-__global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npixels, int space, int forward) {
+__global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npixels, int space, int forward, const XyzSettings st) {
   __shared__ double s_scale[128];
   if (threadIdx.x < 128) s_scale[threadIdx.x] = kDecodeScale[threadIdx.x];
   __syncthreads();
@@ -476,10 +484,10 @@ __global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npix
     if (forward) {
       double J, a, b;
       rgb_to_xyz(in0, in2, in1, X, Y, Z, s_scale);
-      xyz_to_jzazbz(X, Y, Z, J, a, b);
+      xyz_to_jzazbz(st.white_luminance, X, Y, Z, J, a, b);
       o0 = QR * J; o1 = QR * a; o2 = QR * b;
     } else {
-      jzazbz_to_xyz(QS * static_cast<double>(in0), QS * static_cast<double>(in1), QS * static_cast<double>(in2), X, Y, Z);
+      jzazbz_to_xyz(st.white_luminance, QS * static_cast<double>(in0), QS * static_cast<double>(in1), QS * static_cast<double>(in2), X, Y, Z);
       xyz_to_rgb(X, Y, Z, o0, o2, o1);
     }
   } else if (space == MB200_OklabColorspace || space == MB200_OklchColorspace) {      // colorspace-private.h:1480-1549
@@ -517,17 +525,19 @@ __global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npix
     rgb_to_xyz(in0, in1, in2, X, Y, Z, s_scale);
     if (space == MB200_LCHColorspace || space == MB200_LCHabColorspace) {       // :1104-1117
       double la, lb;
-      xyz_to_lab_unit(X, Y, Z, a, la, lb);
+      xyz_to_lab_unit(st, X, Y, Z, a, la, lb);
       b = hypot(la - 0.5, lb - 0.5) + 0.5;
       c = 180.0 * atan2(lb - 0.5, la - 0.5) / kPiD / 360.0;
       if (c < 0.0) c += 1.0;
     } else if (space == MB200_LCHuvColorspace) {                               // :1163-1176
       double u, v;
-      xyz_to_luv_unit(X, Y, Z, a, u, v);
+      xyz_to_luv_unit(st, X, Y, Z, a, u, v);
       const double du = 354.0 * u - 134.0, dv = 262.0 * v - 140.0;
       b = hypot(du, dv) / 255.0 + 0.5;
       c = 180.0 * atan2(dv, du) / kPiD / 360.0;
       if (c < 0.0) c += 1.0;
+    } else if (space == MB200_LabColorspace) {                                 // a reference white other than D65
+      xyz_to_lab_unit(st, X, Y, Z, a, b, c);
     } else if (rgb >= 0) {
       mul3(kx.to_rgb[rgb], X, Y, Z, a, b, c);
       a = QS * encode_pixel_gamma(QR * a); b = QS * encode_pixel_gamma(QR * b); c = QS * encode_pixel_gamma(QR * c);
@@ -541,7 +551,7 @@ __global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npix
       const double gamma = perceptible_reciprocal_d(X + Y + Z);
       a = gamma * X; b = gamma * Y; c = Y;
     } else {                                                       // Luv
-      xyz_to_luv_unit(X, Y, Z, a, b, c);
+      xyz_to_luv_unit(st, X, Y, Z, a, b, c);
     }
     o0 = QR * a; o1 = QR * b; o2 = QR * c;
   } else {
@@ -550,8 +560,10 @@ __global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npix
     if (space == MB200_LCHColorspace || space == MB200_LCHabColorspace || space == MB200_LCHuvColorspace) {   // :572-653
       const double luma = 100.0 * a, chroma = 255.0 * (b - 0.5), rad = kPiD * (360.0 * c) / 180.0;
       const double p = chroma * cos(rad), q2 = chroma * sin(rad);
-      if (space == MB200_LCHuvColorspace) luv_to_xyz_d(luma, p, q2, X, Y, Z);
-      else lab_to_xyz_d(luma, p, q2, X, Y, Z);
+      if (space == MB200_LCHuvColorspace) luv_to_xyz_d(st, luma, p, q2, X, Y, Z);
+      else lab_to_xyz_d(st, luma, p, q2, X, Y, Z);
+    } else if (space == MB200_LabColorspace) {                                 // colorspace-private.h:559-570
+      lab_to_xyz_d(st, 100.0 * a, 255.0 * (b - 0.5), 255.0 * (c - 0.5), X, Y, Z);
     } else if (rgb >= 0) {
       const double r = QS * decode_pixel_gamma_tab(QR * a, s_scale), g = QS * decode_pixel_gamma_tab(QR * b, s_scale),
                    bl = QS * decode_pixel_gamma_tab(QR * c, s_scale);
@@ -566,7 +578,7 @@ __global__ void __launch_bounds__(256) xyz_family_kernel(float *buf, size_t npix
       const double gamma = perceptible_reciprocal_d(b);
       X = gamma * c * a; Y = c; Z = gamma * c * (1.0 - a - b);
     } else {                                                       // Luv
-      luv_to_xyz_d(100.0 * a, 354.0 * b - 134.0, 262.0 * c - 140.0, X, Y, Z);
+      luv_to_xyz_d(st, 100.0 * a, 354.0 * b - 134.0, 262.0 * c - 140.0, X, Y, Z);
     }
     xyz_to_rgb(X, Y, Z, o0, o1, o2);
   }
@@ -582,12 +594,32 @@ bool is_xyz_family(int cs) {
          cs == MB200_LMSColorspace || cs == MB200_CAT02LMSColorspace || cs == MB200_xyYColorspace || cs == MB200_LuvColorspace;
 }
 
-int launch_xyz_family_leg(float *buf, size_t npixels, int channels, int space, bool forward, cudaStream_t s) {
+constexpr int kD65 = 5;          // IlluminantType (MagickCore/color.h:40-54); also what an unparsable artifact selects
+int illuminant_of(const mb200_colorspace_options *o) {
+  return (o && (o->set & MB200_CO_ILLUMINANT) && o->illuminant >= 0 && o->illuminant <= 10) ? o->illuminant : kD65;
+}
+XyzSettings xyz_settings(const mb200_colorspace_options *o) {
+  static const double table[11][3] = {                            // colorspace-private.h:32-46
+      {1.09850, 1.00000, 0.35585}, {0.99072, 1.00000, 0.85223}, {0.98074, 1.00000, 1.18232}, {0.96422, 1.00000, 0.82521},
+      {0.95682, 1.00000, 0.92149}, {0.95047, 1.00000, 1.08883}, {0.94972, 1.00000, 1.22638}, {1.00000, 1.00000, 1.00000},
+      {0.99186, 1.00000, 0.67393}, {0.95041, 1.00000, 1.08747}, {1.00962, 1.00000, 0.64350}};
+  XyzSettings st;
+  const double *t = table[illuminant_of(o)];
+  st.ill[0] = t[0]; st.ill[1] = t[1]; st.ill[2] = t[2];
+  const double den = t[0] + 15.0 * t[1] + 3.0 * t[2];
+  st.un = 4.0 * t[0] / den;
+  st.vn = 9.0 * t[1] / den;
+  st.white_luminance = (o && (o->set & MB200_CO_WHITE_LUMINANCE)) ? o->white_luminance : 10000.0;
+  return st;
+}
+
+int launch_xyz_family_leg(float *buf, size_t npixels, int channels, int space, bool forward, const XyzSettings &st,
+                          cudaStream_t s) {
   const int rc = ensure_decode_scale();
   if (rc) return rc;
   const unsigned blocks = static_cast<unsigned>((npixels + 255) / 256);
-  if (channels == 4) xyz_family_kernel<4><<<blocks, 256, 0, s>>>(buf, npixels, space, forward ? 1 : 0);
-  else xyz_family_kernel<3><<<blocks, 256, 0, s>>>(buf, npixels, space, forward ? 1 : 0);
+  if (channels == 4) xyz_family_kernel<4><<<blocks, 256, 0, s>>>(buf, npixels, space, forward ? 1 : 0, st);
+  else xyz_family_kernel<3><<<blocks, 256, 0, s>>>(buf, npixels, space, forward ? 1 : 0, st);
   count_launch();
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "colorspace launch");
@@ -725,41 +757,210 @@ int launch_matrix_leg(float *buf, size_t npixels, int channels, const MatrixLeg 
   return MB200_OK;
 }
 
+// ---- Log (colorspace.c:1055-1163 forward, :2391-2500 inverse): a 65536-entry Quantum table indexed by ScaleQuantumToMap
+// of the linearised (forward) or the stored (inverse) sample.  The table is built on the host with the C library's
+// log10 / pow exactly as the reference builds it (one table per call: 256 KB against an image of many MB), the pixel
+// pass is a gather.  The forward index is taken of the decoded sample rounded to float, as ClampToQuantum does (HDRI).
+// DisplayGamma = 1/1.7 is both density and gamma: the reference's "gamma" property lookup (:1081) cannot succeed,
+// SetImageProperty diverts that key to image->gamma (property.c:4583).
+double host_perceptible_reciprocal(double x) {
+  const double sign = x < 0.0 ? -1.0 : 1.0;
+  return (sign * x) >= 1.0e-12 ? 1.0 / x : sign / 1.0e-12;
+}
+float host_map_to_quantum(double v) { return v <= 0.0 ? 0.0f : v >= 65535.0 ? 65535.0f : static_cast<float>(v); }
+
+void build_log_table(bool forward, const mb200_colorspace_options *o, float *logmap) {
+  const double film_gamma = (o && (o->set & MB200_CO_FILM_GAMMA)) ? o->film_gamma : 0.6;
+  const double reference_black = (o && (o->set & MB200_CO_REFERENCE_BLACK)) ? o->reference_black : 95.0;
+  const double reference_white = (o && (o->set & MB200_CO_REFERENCE_WHITE)) ? o->reference_white : 685.0;
+  const double density = 1.0 / 1.7, gamma = 1.0 / 1.7;
+  const double black = std::pow(10.0, (reference_black - reference_white) * (gamma / density) * 0.002 *
+                                          host_perceptible_reciprocal(film_gamma));
+  long i = 0;
+  if (forward) {
+    for (; i <= 65535; ++i)
+      logmap[i] = host_map_to_quantum((65535.0 * (reference_white + std::log10(black + (1.0 * static_cast<double>(i) / 65535.0) *
+                                        (1.0 - black)) / ((gamma / density) * 0.002 * host_perceptible_reciprocal(film_gamma))) / 1024.0));
+    return;
+  }
+  for (; i <= 65535 && i <= static_cast<long>(reference_black * 65535.0 / 1024.0); ++i) logmap[i] = 0.0f;
+  for (; i <= 65535 && i < static_cast<long>(reference_white * 65535.0 / 1024.0); ++i)
+    logmap[i] = static_cast<float>(QR / (1.0 - black) * (std::pow(10.0, (1024.0 * static_cast<double>(i) / 65535.0 - reference_white) *
+                                   (gamma / density) * 0.002 * host_perceptible_reciprocal(film_gamma)) - black));
+  for (; i <= 65535; ++i) logmap[i] = static_cast<float>(QR);
+}
+
+__device__ __forceinline__ unsigned quantum_to_index(float q) {      // quantum-private.h:504-514 (HDRI)
+  if (q >= 65535.0f) return 65535u;
+  if (q != q || q <= 0.0f) return 0u;
+  return static_cast<unsigned>(__fadd_rn(q, 0.5f));
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) log_leg_kernel(float *buf, size_t npixels, const float *__restrict__ logmap, int forward) {
+  __shared__ double s_scale[128];
+  if (threadIdx.x < 128) s_scale[threadIdx.x] = kDecodeScale[threadIdx.x];
+  __syncthreads();
+  const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= npixels) return;
+  float *q = buf + i * CH;
+  float in[3], in3 = 0.f, o[3];
+  if (CH == 4) { const float4 t = *reinterpret_cast<const float4 *>(q); in[0] = t.x; in[1] = t.y; in[2] = t.z; in3 = t.w; }
+  else { in[0] = q[0]; in[1] = q[1]; in[2] = q[2]; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (forward) {
+      const float linear = static_cast<float>(decode_pixel_gamma_tab(static_cast<double>(in[k]), s_scale));
+      o[k] = __ldg(logmap + quantum_to_index(linear));
+    } else {
+      o[k] = static_cast<float>(encode_pixel_gamma(static_cast<double>(__ldg(logmap + quantum_to_index(in[k])))));
+    }
+  }
+  if (CH == 4) *reinterpret_cast<float4 *>(q) = make_float4(o[0], o[1], o[2], in3);
+  else { q[0] = o[0]; q[1] = o[1]; q[2] = o[2]; }
+}
+
+// ---- YCC (PhotoYCC) in the LUT branch (colorspace.c:1347-1389 forward, :2681-2711 + :2788-2796 inverse).  Forward: the
+// three tables are piecewise in the map index -- a linear toe up to (ssize_t) (0.018 * MaxMap) = 1179, then
+// c * (1.099 * i - 0.099) -- and are evaluated instead of stored, with the same single roundings as the table entries;
+// the C1 / C2 zeros are 156 and 137 on the 8-bit scale (x 257).  Inverse: a linear combination of the indices, scaled
+// to 0..1388 and looked up in the reference's 1389-entry float table, which is the sequence "%.6f" of (float) i / 1388
+// (regenerated on the host by that rule; tests/test_oracle_vs_ref.py pins the rule to the compiled reference).
+// Unfused double operations in the reference's order: bit exact.
+constexpr int kYccEntries = 1389;
+void build_ycc_table(float *table) {
+  char text[32];
+  for (int i = 0; i < kYccEntries; ++i) {
+    std::snprintf(text, sizeof(text), "%.6f", static_cast<double>(static_cast<float>(i) / 1388.0f));
+    table[i] = std::strtof(text, nullptr);
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) ycc_leg_kernel(float *buf, size_t npixels, const float *__restrict__ ycc, int forward) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= npixels) return;
+  float *q = buf + i * CH;
+  float in[3], in3 = 0.f, o[3];
+  if (CH == 4) { const float4 t = *reinterpret_cast<const float4 *>(q); in[0] = t.x; in[1] = t.y; in[2] = t.z; in3 = t.w; }
+  else { in[0] = q[0]; in[1] = q[1]; in[2] = q[2]; }
+  const double idx[3] = {quantum_to_map(in[0]), quantum_to_map(in[1]), quantum_to_map(in[2])};
+  constexpr double kC1Zero = 40092.0, kC2Zero = 35209.0;
+  if (forward) {
+    constexpr double toe[3][3] = {{0.005382, -0.003296, 0.009410}, {0.010566, -0.006471, -0.007880}, {0.002052, 0.009768, -0.001530}};
+    constexpr double curve[3][3] = {{0.298839, -0.298839, 0.70100}, {0.586811, -0.586811, -0.586811}, {0.114350, 0.88600, -0.114350}};
+    double t[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) t[c] = __dsub_rn(__dmul_rn(1.099, idx[c]), 0.099);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double e[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) e[c] = idx[c] <= 1179.0 ? __dmul_rn(toe[c][k], idx[c]) : __dmul_rn(curve[c][k], t[c]);
+      const double v = __dadd_rn(__dadd_rn(__dadd_rn(e[0], e[1]), e[2]), k == 0 ? 0.0 : k == 1 ? kC1Zero : kC2Zero);
+      o[k] = map_to_quantum(v);
+    }
+  } else {
+    const double y = __dmul_rn(1.3584000, idx[0]), c1 = __dsub_rn(idx[1], kC1Zero), c2 = __dsub_rn(idx[2], kC2Zero);
+    double v[3];
+    v[0] = __dadd_rn(y, __dmul_rn(1.8215000, c2));
+    v[1] = __dadd_rn(__dadd_rn(y, __dmul_rn(-0.4302726, c1)), __dmul_rn(-0.9271435, c2));
+    v[2] = __dadd_rn(y, __dmul_rn(2.2179000, c1));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double t = __ddiv_rn(__dmul_rn(1024.0, v[k]), 65535.0);
+      const int at = t <= 0.0 ? 0 : t >= 1388.0 ? 1388 : static_cast<int>(__dadd_rn(t, 0.5));        // RoundToYCC :1814
+      o[k] = static_cast<float>(__dmul_rn(QR, static_cast<double>(__ldg(ycc + at))));
+    }
+  }
+  if (CH == 4) *reinterpret_cast<float4 *>(q) = make_float4(o[0], o[1], o[2], in3);
+  else { q[0] = o[0]; q[1] = o[1]; q[2] = o[2]; }
+}
+
+// table (host, `entries` floats) -> stream-ordered device temporary -> gather kernel -> stream-ordered free
+template <typename Launch>
+int with_device_table(const float *host, size_t entries, cudaStream_t s, Launch &&launch) {
+  float *d = nullptr;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&d), entries * sizeof(float), temp_pool(), s);
+  if (e != cudaSuccess) return cuda_fail(e, "colorspace: table allocation");
+  e = cudaMemcpyAsync(d, host, entries * sizeof(float), cudaMemcpyHostToDevice, s);     // pageable source: staged before return
+  int rc = e == cudaSuccess ? MB200_OK : cuda_fail(e, "colorspace: table upload");
+  if (rc == MB200_OK) {
+    launch(d);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "colorspace launch");
+  }
+  cudaFreeAsync(d, s);
+  return rc;
+}
+
+int launch_log_leg(float *buf, size_t npixels, int channels, bool forward, const mb200_colorspace_options *o, cudaStream_t s) {
+  const int rc = ensure_decode_scale();
+  if (rc) return rc;
+  std::vector<float> table(65536);
+  build_log_table(forward, o, table.data());
+  const unsigned blocks = static_cast<unsigned>((npixels + 255) / 256);
+  return with_device_table(table.data(), table.size(), s, [&](const float *d) {
+    if (channels == 4) log_leg_kernel<4><<<blocks, 256, 0, s>>>(buf, npixels, d, forward ? 1 : 0);
+    else log_leg_kernel<3><<<blocks, 256, 0, s>>>(buf, npixels, d, forward ? 1 : 0);
+  });
+}
+
+int launch_ycc_leg(float *buf, size_t npixels, int channels, bool forward, cudaStream_t s) {
+  float table[kYccEntries];
+  build_ycc_table(table);
+  const unsigned blocks = static_cast<unsigned>((npixels + 255) / 256);
+  return with_device_table(table, kYccEntries, s, [&](const float *d) {
+    if (channels == 4) ycc_leg_kernel<4><<<blocks, 256, 0, s>>>(buf, npixels, d, forward ? 1 : 0);
+    else ycc_leg_kernel<3><<<blocks, 256, 0, s>>>(buf, npixels, d, forward ? 1 : 0);
+  });
+}
+
 }  // namespace
 
-int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to, void *stream) {
+int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to, const mb200_colorspace_options *options,
+                      void *stream) {
   if (channels != 3 && channels != 4) return fail(MB200_EUNSUPPORTED, "colorspace: %d channels", channels);
   if (npixels == 0) return MB200_OK;
   if (npixels > 0xffffffffull * 256) return fail(MB200_EINVAL, "colorspace: image too large");
   if (channels == 4 && (reinterpret_cast<uintptr_t>(buf) & 15) != 0)
     return fail(MB200_EINVAL, "colorspace: RGBA buffers must be 16-byte aligned");
+  if (options && (options->set & MB200_CO_ILLUMINANT) && (options->illuminant < 0 || options->illuminant > 10))
+    return fail(MB200_EINVAL, "colorspace: illuminant %d", options->illuminant);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  auto core = [](int cs) { return cs == MB200_sRGBColorspace || cs == MB200_LabColorspace ||
-                                  cs == MB200_XYZColorspace || cs == MB200_RGBColorspace; };
+  const XyzSettings st = xyz_settings(options);
+  const bool d65 = illuminant_of(options) == kD65;
+  enum Route { kNone, kCore, kLabGeneric, kHex, kXyz, kMatrix, kLog, kYcc };
   MatrixLeg from_leg{}, to_leg{};
-  const bool from_hex = is_hexcone_colorspace(from), to_hex = is_hexcone_colorspace(to);
-  const bool from_xyz = is_xyz_family(from), to_xyz = is_xyz_family(to);
-  const bool from_matrix = !core(from) && !from_hex && !from_xyz && matrix_leg(from, false, from_leg);
-  const bool to_matrix = !core(to) && !to_hex && !to_xyz && matrix_leg(to, true, to_leg);
-  if ((!core(from) && !from_matrix && !from_hex && !from_xyz) || (!core(to) && !to_matrix && !to_hex && !to_xyz))
-    return fail(MB200_EUNSUPPORTED, "colorspace %d -> %d not implemented", from, to);
+  auto route = [&](int cs, bool forward, MatrixLeg &leg) {
+    if (cs == MB200_LabColorspace) return d65 ? kCore : kLabGeneric;      // the specialised Lab kernels fold the D65 white
+    if (cs == MB200_sRGBColorspace || cs == MB200_XYZColorspace || cs == MB200_RGBColorspace) return kCore;
+    if (cs == MB200_LogColorspace) return kLog;
+    if (cs == MB200_YCCColorspace) return kYcc;
+    if (is_hexcone_colorspace(cs)) return kHex;
+    if (is_xyz_family(cs)) return kXyz;
+    return matrix_leg(cs, forward, leg) ? kMatrix : kNone;
+  };
+  const Route rf = route(from, false, from_leg), rt = route(to, true, to_leg);
+  if (rf == kNone || rt == kNone) return fail(MB200_EUNSUPPORTED, "colorspace %d -> %d not implemented", from, to);
   if (from == to) return MB200_OK;
+  auto leg = [&](Route r, int cs, bool forward, const MatrixLeg &m) -> int {
+    switch (r) {
+      case kHex: return launch_hexcone_leg(buf, npixels, channels, cs, forward, s);
+      case kXyz: case kLabGeneric: return launch_xyz_family_leg(buf, npixels, channels, cs, forward, st, s);
+      case kMatrix: return launch_matrix_leg(buf, npixels, channels, m, s);
+      case kLog: return launch_log_leg(buf, npixels, channels, forward, options, s);
+      case kYcc: return launch_ycc_leg(buf, npixels, channels, forward, s);
+      default: break;
+    }
+    if (cs == MB200_LabColorspace) return forward ? launch_mode<kToLab>(buf, npixels, channels, s) : launch_mode<kFromLab>(buf, npixels, channels, s);
+    if (cs == MB200_XYZColorspace) return forward ? launch_mode<kToXyz>(buf, npixels, channels, s) : launch_mode<kFromXyz>(buf, npixels, channels, s);
+    return forward ? launch_mode<kToLinear>(buf, npixels, channels, s) : launch_mode<kFromLinear>(buf, npixels, channels, s);
+  };
   int rc = MB200_OK;
-  if (from != MB200_sRGBColorspace) {          // colorspace.c:1773-1774: back to sRGB first
-    if (from_hex) rc = launch_hexcone_leg(buf, npixels, channels, from, false, s);
-    else if (from_xyz) rc = launch_xyz_family_leg(buf, npixels, channels, from, false, s);
-    else if (from_matrix) rc = launch_matrix_leg(buf, npixels, channels, from_leg, s);
-    else if (from == MB200_LabColorspace) rc = launch_mode<kFromLab>(buf, npixels, channels, s);
-    else if (from == MB200_XYZColorspace) rc = launch_mode<kFromXyz>(buf, npixels, channels, s);
-    else rc = launch_mode<kFromLinear>(buf, npixels, channels, s);
-    if (rc) return rc;
-  }
-  if (to_hex) rc = launch_hexcone_leg(buf, npixels, channels, to, true, s);
-  else if (to_xyz) rc = launch_xyz_family_leg(buf, npixels, channels, to, true, s);
-  else if (to_matrix) rc = launch_matrix_leg(buf, npixels, channels, to_leg, s);
-  else if (to == MB200_LabColorspace) rc = launch_mode<kToLab>(buf, npixels, channels, s);
-  else if (to == MB200_XYZColorspace) rc = launch_mode<kToXyz>(buf, npixels, channels, s);
-  else if (to == MB200_RGBColorspace) rc = launch_mode<kToLinear>(buf, npixels, channels, s);
+  if (from != MB200_sRGBColorspace) rc = leg(rf, from, false, from_leg);          // colorspace.c:1773-1774: back to sRGB first
+  if (rc == MB200_OK && to != MB200_sRGBColorspace) rc = leg(rt, to, true, to_leg);
   return rc;
 }
 

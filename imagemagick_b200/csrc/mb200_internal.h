@@ -110,7 +110,8 @@ int launch_resize_fused(const float *src, size_t width, size_t height, float *ds
                         const int *d_yborder, int nyborder, const unsigned char *d_row_is_border, void *stream);
 
 // colorspace.cu
-int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to, void *stream);
+int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to, const mb200_colorspace_options *options,
+                      void *stream);
 
 // hexcone.cu: HCL, HCLp, HSB, HSI, HSL, HSV, HWB (one leg: sRGB -> space or space -> sRGB), in place
 bool is_hexcone_colorspace(int cs);

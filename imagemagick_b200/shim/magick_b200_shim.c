@@ -457,6 +457,8 @@ static int map_colorspace(ColorspaceType c)
     case LCHColorspace: return MB200_LCHColorspace;
     case LCHabColorspace: return MB200_LCHabColorspace;
     case LCHuvColorspace: return MB200_LCHuvColorspace;
+    case LogColorspace: return MB200_LogColorspace;
+    case YCCColorspace: return MB200_YCCColorspace;
     case JzazbzColorspace: return MB200_JzazbzColorspace;
     case OklabColorspace: return MB200_OklabColorspace;
     case OklchColorspace: return MB200_OklchColorspace;
@@ -478,16 +480,43 @@ static int map_colorspace(ColorspaceType c)
   }
 }
 
+/* The image settings sRGBTransformImage / TransformsRGBImage read (colorspace.c:761-773, :996, :1081-1095), parsed with
+   the reference's own functions.  False: leave the image to the CPU path. */
+static MagickBooleanType b200_colorspace_options(const Image *image, mb200_colorspace_options *o, ExceptionInfo *exception)
+{
+  const char *value;
+  (void) memset(o, 0, sizeof(*o));
+  value = GetImageArtifact(image, "color:illuminant");
+  if (value != (const char *) NULL) {
+    const ssize_t type = ParseCommandOption(MagickIlluminantOptions, MagickFalse, value);
+    o->illuminant = type < 0 ? (int) UndefinedIlluminant : (int) type;      /* :769-772 */
+    o->set |= MB200_CO_ILLUMINANT;
+  }
+  value = GetImageProperty(image, "white-luminance", exception);
+  if (value != (const char *) NULL) { o->white_luminance = StringToDouble(value, (char **) NULL); o->set |= MB200_CO_WHITE_LUMINANCE; }
+  if (GetImageProperty(image, "gamma", exception) != (const char *) NULL) return MagickFalse;   /* unreachable through SetImageProperty */
+  value = GetImageProperty(image, "film-gamma", exception);
+  if (value != (const char *) NULL) { o->film_gamma = StringToDouble(value, (char **) NULL); o->set |= MB200_CO_FILM_GAMMA; }
+  value = GetImageProperty(image, "reference-black", exception);
+  if (value != (const char *) NULL) { o->reference_black = StringToDouble(value, (char **) NULL); o->set |= MB200_CO_REFERENCE_BLACK; }
+  value = GetImageProperty(image, "reference-white", exception);
+  if (value != (const char *) NULL) { o->reference_white = StringToDouble(value, (char **) NULL); o->set |= MB200_CO_REFERENCE_WHITE; }
+  /* the reference's table loops index past MaxMap for values outside the 10-bit scale */
+  if ((o->set & MB200_CO_REFERENCE_BLACK) != 0 && !(o->reference_black >= 0.0 && o->reference_black <= 1024.0)) return MagickFalse;
+  if ((o->set & MB200_CO_REFERENCE_WHITE) != 0 && !(o->reference_white >= 0.0 && o->reference_white <= 1024.0)) return MagickFalse;
+  return MagickTrue;
+}
+
 MagickBooleanType B200AccelerateTransformImageColorspace(Image *image, const ColorspaceType colorspace,
                                                          ExceptionInfo *exception)
 {
   const int from = map_colorspace(image->colorspace), to = map_colorspace(colorspace);
   ColorspaceType saved = image->colorspace;
+  mb200_colorspace_options copt;
   Quantum *q;
   int ch;
   if (from < 0 || to < 0 || from == to || mb200_device_count() <= 0) return MagickFalse;
-  if (GetImageArtifact(image, "color:illuminant") != (const char *) NULL) return MagickFalse;
-  if (GetImageProperty(image, "white-luminance", exception) != (const char *) NULL) return MagickFalse;
+  if (b200_colorspace_options(image, &copt, exception) == MagickFalse) return MagickFalse;
   /* the channel layout test is colourspace-agnostic for 3/4-channel images */
   image->colorspace = sRGBColorspace;
   ch = b200_channels(image);
@@ -499,7 +528,8 @@ MagickBooleanType B200AccelerateTransformImageColorspace(Image *image, const Col
     /* GetAuthenticPixels un-shares a copy-on-write cache (GetImagePixelCache, cache.c:1715) before it is written */
     q = GetAuthenticPixels(image, 0, 0, image->columns, image->rows, attempt);
     if (q != (Quantum *) NULL && b200_cache_pixels(image, ch, attempt) == (float *) q &&
-        mb200_transform_colorspace((float *) q, image->columns, image->rows, ch, from, to) == MB200_OK &&
+        mb200_transform_colorspace_ex((float *) q, image->columns, image->rows, ch, from, to,
+                                      copt.set != 0 ? &copt : (const mb200_colorspace_options *) NULL) == MB200_OK &&
         SyncAuthenticPixels(image, attempt) != MagickFalse)
       ok = MagickTrue;
     B200_ATTEMPT_END;

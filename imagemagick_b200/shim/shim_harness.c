@@ -158,6 +158,25 @@ int main(void)
   if (TransformImageColorspace(a, LuvColorspace, ex) == MagickFalse || a->colorspace != LuvColorspace) failures++;
   B200ShimEnable(0); (void) __real_TransformImageColorspace(b, LuvColorspace, ex); B200ShimEnable(1);
   CHECK("TransformImageColorspace sRGB->Luv", 1, a, b);
+  a = CloneImage(rgba, 0, 0, MagickTrue, ex); b = CloneImage(rgba, 0, 0, MagickTrue, ex);
+  (void) SetImageArtifact(a, "color:illuminant", "D50"); (void) SetImageArtifact(b, "color:illuminant", "D50");
+  if (TransformImageColorspace(a, LabColorspace, ex) == MagickFalse || a->colorspace != LabColorspace) failures++;
+  B200ShimEnable(0); (void) __real_TransformImageColorspace(b, LabColorspace, ex); B200ShimEnable(1);
+  CHECK("TransformImageColorspace sRGB->Lab (D50)", 1, a, b);
+  a = CloneImage(rgb, 0, 0, MagickTrue, ex); b = CloneImage(rgb, 0, 0, MagickTrue, ex);
+  (void) SetImageProperty(a, "reference-white", "700", ex); (void) SetImageProperty(b, "reference-white", "700", ex);
+  if (TransformImageColorspace(a, LogColorspace, ex) == MagickFalse || a->colorspace != LogColorspace) failures++;
+  B200ShimEnable(0); (void) __real_TransformImageColorspace(b, LogColorspace, ex); B200ShimEnable(1);
+  CHECK("TransformImageColorspace sRGB->Log (reference-white 700)", 1, a, b);
+  a = CloneImage(rgba, 0, 0, MagickTrue, ex); b = CloneImage(rgba, 0, 0, MagickTrue, ex);
+  if (TransformImageColorspace(a, YCCColorspace, ex) == MagickFalse || a->colorspace != YCCColorspace) failures++;
+  B200ShimEnable(0); (void) __real_TransformImageColorspace(b, YCCColorspace, ex); B200ShimEnable(1);
+  CHECK("TransformImageColorspace sRGB->YCC", 0, a, b);
+  a = CloneImage(rgba, 0, 0, MagickTrue, ex); b = CloneImage(rgba, 0, 0, MagickTrue, ex);
+  (void) SetImageColorspace(a, YCCColorspace, ex); (void) SetImageColorspace(b, YCCColorspace, ex);
+  if (TransformImageColorspace(a, sRGBColorspace, ex) == MagickFalse || a->colorspace != sRGBColorspace) failures++;
+  B200ShimEnable(0); (void) __real_TransformImageColorspace(b, sRGBColorspace, ex); B200ShimEnable(1);
+  CHECK("TransformImageColorspace YCC->sRGB", 0, a, b);
   CHECK("ResizeImage Jinc 50% RGBA", 1, ResizeImage(rgba, rgba->columns / 2, rgba->rows / 2, JincFilter, ex),
         CPU(__real_ResizeImage(rgba, rgba->columns / 2, rgba->rows / 2, JincFilter, ex)));
   (void) SetImageArtifact(rgba, "filter:blur", "0.85"); (void) SetImageArtifact(rgba, "filter:lobes", "2");

@@ -100,6 +100,7 @@ typedef enum {
   MB200_LCHColorspace = 12,           /* polar Lab (alias of LCHab) and Luv: the hue of an achromatic pixel is */
   MB200_LCHabColorspace = 13,         /* rounding noise in the reference as well                               */
   MB200_LCHuvColorspace = 14,
+  MB200_LogColorspace = 15,           /* table gather, colorspace.c:1055-1163 / :2391-2500 */
   MB200_LMSColorspace = 16,           /* XYZ-derived spaces of the generic branch: <= 1 ULP */
   MB200_LuvColorspace = 17,
   MB200_OHTAColorspace = 18,          /* LUT branch, colorspace.c:1229-1494 */
@@ -110,6 +111,7 @@ typedef enum {
   MB200_xyYColorspace = 25,
   MB200_XYZColorspace = 26,
   MB200_YCbCrColorspace = 27,
+  MB200_YCCColorspace = 28,           /* PhotoYCC, LUT branch :1347-1389 / :2681-2711, bit exact */
   MB200_YDbDrColorspace = 29,
   MB200_YIQColorspace = 30,
   MB200_YPbPrColorspace = 31,
@@ -386,6 +388,26 @@ MB200_API int mb200_thumbnail_image_dev(const float *src, size_t width, size_t h
 /* TransformImageColorspace (MagickCore/colorspace.c:1751), in place on `buf`. */
 MB200_API int mb200_transform_colorspace_dev(float *buf, size_t width, size_t height,
     int channels, int from_colorspace, int to_colorspace, void *stream);
+/* ... with the image settings the reference reads inside sRGBTransformImage / TransformsRGBImage, as values (the shim
+   parses them with the reference's own functions): the "color:illuminant" artifact (colorspace.c:761-773, :2093-2105) =
+   the reference white of Lab, LCH, LCHab, LCHuv and Luv; the "white-luminance" property (:996, :2331) of Jzazbz; the
+   "film-gamma", "reference-black" and "reference-white" properties (:1085-1095, :2416-2426) of Log.  (Log's "gamma"
+   property, :1081, cannot be set on an image: SetImageProperty diverts that key to image->gamma, property.c:4583.)
+   options == NULL or a clear `set` bit: the reference's default. */
+typedef enum {                          /* MagickCore/color.h:40-54 IlluminantType -- same numeric values */
+  MB200_AIlluminant = 0, MB200_BIlluminant, MB200_CIlluminant, MB200_D50Illuminant, MB200_D55Illuminant,
+  MB200_D65Illuminant, MB200_D75Illuminant, MB200_EIlluminant, MB200_F2Illuminant, MB200_F7Illuminant, MB200_F11Illuminant
+} mb200_illuminant;
+enum { MB200_CO_ILLUMINANT = 1, MB200_CO_WHITE_LUMINANCE = 2, MB200_CO_FILM_GAMMA = 4, MB200_CO_REFERENCE_BLACK = 8,
+       MB200_CO_REFERENCE_WHITE = 16 };
+typedef struct mb200_colorspace_options {
+  unsigned set;
+  int illuminant;                      /* mb200_illuminant */
+  double white_luminance;
+  double film_gamma, reference_black, reference_white;    /* reference_black / _white within 0..1024 */
+} mb200_colorspace_options;
+MB200_API int mb200_transform_colorspace_ex_dev(float *buf, size_t width, size_t height, int channels,
+    int from_colorspace, int to_colorspace, const mb200_colorspace_options *options, void *stream);
 
 /* Threshold point operators of MagickCore/threshold.c, in place on `buf`, bit exact.
    BilevelImage (:805): every channel (alpha included) := intensity <= threshold ? 0 : QuantumRange,
@@ -467,6 +489,8 @@ MB200_API int mb200_thumbnail_image(const float *src, size_t width, size_t heigh
     float *dst, size_t columns, size_t rows, int filter);
 MB200_API int mb200_transform_colorspace(float *buf, size_t width, size_t height, int channels,
     int from_colorspace, int to_colorspace);
+MB200_API int mb200_transform_colorspace_ex(float *buf, size_t width, size_t height, int channels,
+    int from_colorspace, int to_colorspace, const mb200_colorspace_options *options);
 MB200_API int mb200_bilevel_image(float *buf, size_t width, size_t height, int channels, double threshold);
 MB200_API int mb200_black_threshold_image(float *buf, size_t width, size_t height, int channels,
     int colorspace, const char *thresholds);

@@ -10,6 +10,7 @@
 #include "oracle.h"
 #include <limits.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -1208,9 +1209,17 @@ static double encode_pixel_gamma(double pixel)
   return (double) QR * (1.055 * encode_gamma((double) QS * pixel) - 0.055);
 }
 
-#define ILL_X 0.95047        /* colorspace-private.h:32-46, D65 */
-#define ILL_Y 1.00000
-#define ILL_Z 1.08883
+/* illuminant_tristimulus[] (colorspace-private.h:32-46), indexed by IlluminantType (color.h:40-54); D65 unless the
+   "color:illuminant" artifact names another (colorspace.c:761-773) */
+static const double illuminant_table[11][3] = {
+  {1.09850, 1.00000, 0.35585}, {0.99072, 1.00000, 0.85223}, {0.98074, 1.00000, 1.18232}, {0.96422, 1.00000, 0.82521},
+  {0.95682, 1.00000, 0.92149}, {0.95047, 1.00000, 1.08883}, {0.94972, 1.00000, 1.22638}, {1.00000, 1.00000, 1.00000},
+  {0.99186, 1.00000, 0.67393}, {0.95041, 1.00000, 1.08747}, {1.00962, 1.00000, 0.64350}};
+static double cs_ill[3] = {0.95047, 1.00000, 1.08883};
+static double cs_white_luminance = 10000.0;
+#define ILL_X cs_ill[0]
+#define ILL_Y cs_ill[1]
+#define ILL_Z cs_ill[2]
 #define CIE_EPS (216.0 / 24389.0)
 #define CIE_K   (24389.0 / 27.0)
 
@@ -1886,11 +1895,11 @@ static int colorspace_xyz_family_leg(float *buf, long n, int ch, int cs, int for
     if (cs == ORC_CS_JZAZBZ) {                               /* :1365-1376, :1467-1478: note the swapped arguments */
       if (forward) {
         rgb_to_xyz((double) q[0], (double) q[2], (double) q[1], &X, &Y, &Z);
-        xyz_to_jzazbz(X, Y, Z, 10000.0, &a, &b, &c);
+        xyz_to_jzazbz(X, Y, Z, cs_white_luminance, &a, &b, &c);
         q[0] = (float) (QR * a); q[1] = (float) (QR * b); q[2] = (float) (QR * c);
       } else {
         double R, G, B;
-        jzazbz_to_xyz(QS * q[0], QS * q[1], QS * q[2], 10000.0, &X, &Y, &Z);
+        jzazbz_to_xyz(QS * q[0], QS * q[1], QS * q[2], cs_white_luminance, &X, &Y, &Z);
         xyz_to_rgb(X, Y, Z, &R, &B, &G);
         q[0] = (float) R; q[1] = (float) G; q[2] = (float) B;
       }
@@ -1982,26 +1991,152 @@ static int colorspace_xyz_family_leg(float *buf, long n, int ch, int cs, int for
   return 0;
 }
 
+/* ---- Log (colorspace.c:1055-1163 forward, :2391-2500 inverse): a 65536-entry table of Quantum values indexed by
+   ScaleQuantumToMap of the linearised (forward) or stored (inverse) sample.  DisplayGamma = 1/1.7 is both the density and
+   the default gamma (the "gamma" property lookup of :1081 never succeeds: SetImageProperty diverts that key to image->gamma,
+   property.c:4583). */
+typedef struct { double gamma, film_gamma, reference_black, reference_white; } log_settings;
+static log_settings cs_log = {1.0 / 1.7, 0.6, 95.0, 685.0};
+
+static void log_forward_table(float *logmap)
+{
+  const double density = 1.0 / 1.7;
+  const double black = pow(10.0, (cs_log.reference_black - cs_log.reference_white) * (cs_log.gamma / density) * 0.002 *
+                                     precip(cs_log.film_gamma));
+  long i;
+  for (i = 0; i <= 65535; i++)
+    logmap[i] = scale_map_to_quantum(((double) 65535.0 * (cs_log.reference_white +
+                  log10(black + (1.0 * (double) i / 65535.0) * (1.0 - black)) / ((cs_log.gamma / density) * 0.002 *
+                  precip(cs_log.film_gamma))) / 1024.0));
+}
+
+static void log_inverse_table(float *logmap)
+{
+  const double density = 1.0 / 1.7;
+  const double black = pow(10.0, (cs_log.reference_black - cs_log.reference_white) * (cs_log.gamma / density) * 0.002 *
+                                     precip(cs_log.film_gamma));
+  long i;
+  for (i = 0; i <= 65535 && i <= (long) (cs_log.reference_black * 65535.0 / 1024.0); i++) logmap[i] = 0.0f;
+  for (; i <= 65535 && i < (long) (cs_log.reference_white * 65535.0 / 1024.0); i++)
+    logmap[i] = (float) ((double) QR / (1.0 - black) * (pow(10.0, (1024.0 * (double) i / 65535.0 - cs_log.reference_white) *
+                  (cs_log.gamma / density) * 0.002 * precip(cs_log.film_gamma)) - black));
+  for (; i <= 65535; i++) logmap[i] = (float) QR;
+}
+
+static int colorspace_log_leg(float *buf, long n, int ch, int forward)
+{
+  long i;
+  float *logmap = (float *) malloc(65536 * sizeof(float));
+  if (!logmap) return -1;
+  if (forward) log_forward_table(logmap); else log_inverse_table(logmap);
+#pragma omp parallel for schedule(static)
+  for (i = 0; i < n; i++) {
+    float *q = buf + (size_t) i * ch;
+    int k;
+    for (k = 0; k < 3; k++) {
+      if (forward) q[k] = logmap[scale_quantum_to_map((float) decode_pixel_gamma((double) q[k]))];
+      else q[k] = (float) encode_pixel_gamma((double) logmap[scale_quantum_to_map(q[k])]);
+    }
+  }
+  free(logmap);
+  return 0;
+}
+
+/* ---- YCC (PhotoYCC; colorspace.c:1347-1389 forward, :2681-2711 and :2788-2796 inverse) in the LUT branch: the forward
+   tables are piecewise (linear toe up to 0.018 * MaxMap, then the 1.099 * i - 0.099 curve), offsets 156 and 137 on the
+   8-bit scale; the inverse ends in a 1389-entry table of floats that is the sequence "%.6f" of (float) i / 1388 -- the
+   values are regenerated from that rule and compared with the compiled reference by tests/test_oracle_vs_ref.py. */
+#define YCC_C1_ZERO 40092.0      /* ScaleQuantumToMap(ScaleCharToQuantum(156)) = 156 * 257 */
+#define YCC_C2_ZERO 35209.0      /* 137 * 257 */
+static void ycc_map(float *table)
+{
+  int i;
+  char text[32];
+  for (i = 0; i < 1389; i++) {
+    snprintf(text, sizeof(text), "%.6f", (double) ((float) i / 1388.0f));
+    table[i] = strtof(text, NULL);
+  }
+}
+
+static int colorspace_ycc_leg(float *buf, long n, int ch, int forward)
+{
+  static const double toe[3][3] = {{0.005382, -0.003296, 0.009410}, {0.010566, -0.006471, -0.007880}, {0.002052, 0.009768, -0.001530}};
+  static const double curve[3][3] = {{0.298839, -0.298839, 0.70100}, {0.586811, -0.586811, -0.586811}, {0.114350, 0.88600, -0.114350}};
+  float ycc[1389];
+  long i;
+  ycc_map(ycc);
+#pragma omp parallel for schedule(static)
+  for (i = 0; i < n; i++) {
+    float *q = buf + (size_t) i * ch;
+    const unsigned int idx[3] = {scale_quantum_to_map(q[0]), scale_quantum_to_map(q[1]), scale_quantum_to_map(q[2])};
+    double v[3];
+    int k, c;
+    if (forward) {
+      for (k = 0; k < 3; k++) {           /* k: output component (.x, .y, .z); c: input channel (x_map, y_map, z_map) */
+        double e[3];
+        for (c = 0; c < 3; c++) {
+          const double di = (double) idx[c];
+          e[c] = idx[c] <= 1179u ? toe[c][k] * di : curve[c][k] * (1.099 * di - 0.099);     /* (ssize_t) (0.018 * MaxMap) = 1179 */
+        }
+        v[k] = ((e[0] + e[1]) + e[2]) + (k == 0 ? 0.0 : k == 1 ? YCC_C1_ZERO : YCC_C2_ZERO);
+        v[k] = (double) scale_map_to_quantum(v[k]);
+      }
+    } else {
+      const double r = (double) idx[0], g = (double) idx[1], b = (double) idx[2];
+      v[0] = (1.3584000 * r + 0.0000000) + 1.8215000 * (1.0 * b - YCC_C2_ZERO);
+      v[1] = (1.3584000 * r + (-0.4302726) * (1.0 * g - YCC_C1_ZERO)) + (-0.9271435) * (1.0 * b - YCC_C2_ZERO);
+      v[2] = (1.3584000 * r + 2.2179000 * (1.0 * g - YCC_C1_ZERO)) + 0.0000000;
+      for (k = 0; k < 3; k++) {
+        const double t = 1024.0 * v[k] / 65535.0;
+        const long at = t <= 0.0 ? 0 : t >= 1388.0 ? 1388 : (long) (t + 0.5);               /* RoundToYCC :1814 */
+        v[k] = (double) QR * (double) ycc[at];
+      }
+    }
+    q[0] = (float) v[0]; q[1] = (float) v[1]; q[2] = (float) v[2];
+  }
+  return 0;
+}
+
 /* colorspace.c:1751-1783 TransformImageColorspace: anything that is not sRGB goes back to sRGB
    first (TransformsRGBImage), then forward (sRGBTransformImage). */
-int orc_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to)
+static int colorspace_leg(float *buf, size_t w, size_t h, int ch, int cs, int forward)
 {
   const long n = (long) (w * h);
-  int rc;
+  if (cs == ORC_CS_LOG) return colorspace_log_leg(buf, n, ch, forward);
+  if (cs == ORC_CS_YCC) return colorspace_ycc_leg(buf, n, ch, forward);
+  if (is_hexcone_space(cs)) return colorspace_hexcone_leg(buf, n, ch, cs, forward);
+  if (is_xyz_family_space(cs)) return colorspace_xyz_family_leg(buf, n, ch, cs, forward);
+  if (is_core_space(cs)) return forward ? colorspace_core(buf, w, h, ch, ORC_CS_SRGB, cs) : colorspace_core(buf, w, h, ch, cs, ORC_CS_SRGB);
+  return colorspace_matrix_leg(buf, n, ch, cs, forward);
+}
+
+int orc_colorspace_ex(float *buf, size_t w, size_t h, int ch, int from, int to, const orc_colorspace_options *o)
+{
+  int rc = 0;
   if (ch < 3) return -1;
   if (from == to) return 0;
-  if (is_core_space(from) && is_core_space(to)) return colorspace_core(buf, w, h, ch, from, to);
-  if (from != ORC_CS_SRGB) {
-    rc = is_core_space(from) ? colorspace_core(buf, w, h, ch, from, ORC_CS_SRGB)
-         : is_hexcone_space(from) ? colorspace_hexcone_leg(buf, n, ch, from, 0)
-         : is_xyz_family_space(from) ? colorspace_xyz_family_leg(buf, n, ch, from, 0)
-                                  : colorspace_matrix_leg(buf, n, ch, from, 0);
-    if (rc) return rc;
+  {
+    const int ill = (o && (o->set & ORC_CO_ILLUMINANT) && o->illuminant >= 0 && o->illuminant <= 10) ? o->illuminant : 5;
+    cs_ill[0] = illuminant_table[ill][0]; cs_ill[1] = illuminant_table[ill][1]; cs_ill[2] = illuminant_table[ill][2];
+    cs_white_luminance = (o && (o->set & ORC_CO_WHITE_LUMINANCE)) ? o->white_luminance : 10000.0;
+    cs_log.gamma = 1.0 / 1.7;
+    cs_log.film_gamma = (o && (o->set & ORC_CO_FILM_GAMMA)) ? o->film_gamma : 0.6;
+    cs_log.reference_black = (o && (o->set & ORC_CO_REFERENCE_BLACK)) ? o->reference_black : 95.0;
+    cs_log.reference_white = (o && (o->set & ORC_CO_REFERENCE_WHITE)) ? o->reference_white : 685.0;
   }
-  if (to == ORC_CS_SRGB) return 0;
-  if (is_hexcone_space(to)) return colorspace_hexcone_leg(buf, n, ch, to, 1);
-  if (is_xyz_family_space(to)) return colorspace_xyz_family_leg(buf, n, ch, to, 1);
-  return is_core_space(to) ? colorspace_core(buf, w, h, ch, ORC_CS_SRGB, to) : colorspace_matrix_leg(buf, n, ch, to, 1);
+  if (is_core_space(from) && is_core_space(to)) rc = colorspace_core(buf, w, h, ch, from, to);
+  else {
+    if (from != ORC_CS_SRGB) rc = colorspace_leg(buf, w, h, ch, from, 0);
+    if (rc == 0 && to != ORC_CS_SRGB) rc = colorspace_leg(buf, w, h, ch, to, 1);
+  }
+  cs_ill[0] = illuminant_table[5][0]; cs_ill[1] = illuminant_table[5][1]; cs_ill[2] = illuminant_table[5][2];
+  cs_white_luminance = 10000.0;
+  return rc;
+}
+
+int orc_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to)
+{
+  return orc_colorspace_ex(buf, w, h, ch, from, to, NULL);
 }
 
 /* ------------------------------------------------------------------------------------------

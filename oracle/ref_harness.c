@@ -320,6 +320,33 @@ int ref_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to)
   END
 }
 
+/* ... with image settings: "key=value;key=value"; keys with a "color:" prefix are set as artifacts (-define), the
+   others as properties (-set), which is how TransformImageColorspace looks them up. */
+__attribute__((visibility("default")))
+int ref_colorspace_defines(float *buf, size_t w, size_t h, int ch, int from, int to, const char *defines)
+{
+  BEGIN
+  im = make_image(buf, w, h, ch, from, ex);
+  if (im) {
+    char *copy = AcquireString(defines), *p = copy;
+    while (p != (char *) NULL && *p != '\0') {
+      char *end = strchr(p, ';'), *eq;
+      if (end != (char *) NULL) *end = '\0';
+      eq = strchr(p, '=');
+      if (eq != (char *) NULL) {
+        *eq = '\0';
+        if (strncmp(p, "color:", 6) == 0) (void) SetImageArtifact(im, p, eq + 1);
+        else (void) SetImageProperty(im, p, eq + 1, ex);
+      }
+      p = end != (char *) NULL ? end + 1 : (char *) NULL;
+    }
+    copy = DestroyString(copy);
+    if (TransformImageColorspace(im, (ColorspaceType) to, ex) != MagickFalse)
+      rc = export_image(im, buf, w, h, ch, ex);
+  }
+  END
+}
+
 /* threshold.c point operators, in place.  op: 0 BilevelImage(threshold), 1 BlackThresholdImage(thresholds),
    2 WhiteThresholdImage(thresholds), 3 ClampImage.  The channel count must survive the call (gray
    images are promoted to sRGB by the black/white operators: rc = -2 then). */

@@ -1,6 +1,7 @@
 """Generates tests/golden/r02b_golden.npz from the REAL reference (oracle/_ref/libmagickref.so): the operators added
 late in round 2 -- ResizeImage with the Jinc and Kaiser filters, the hue / saturation colourspaces (HCL, HCLp, HSB, HSI,
-HSL, HSV, HWB) and the XYZ-derived ones (LMS, CAT02LMS, Luv, xyY, DisplayP3, Adobe98, ProPhoto) in both directions.  Run in the authoring container only:   python tests/golden/make_golden_r02b.py
+HSL, HSV, HWB) and the XYZ-derived ones (LMS, CAT02LMS, Luv, xyY, DisplayP3, Adobe98, ProPhoto) in both directions,
+TransformImageColorspace under image settings (illuminant, white luminance, the Log film settings) and the Log / YCC spaces.  Run in the authoring container only:   python tests/golden/make_golden_r02b.py
 tests/test_golden.py pins the oracle (CPU) and the CUDA path (-m gpu) to these arrays."""
 import sys
 from pathlib import Path
@@ -62,11 +63,25 @@ RESIZE_DEFINES = [(22, "filter:blur=0.8"), (22, "filter:lobes=2"), (8, "filter:s
                   (12, "filter:b=0.2;filter:c=0.6"), (3, "filter:window=Hann"), (13, "filter:lobes=5;filter:blur=0.9")]
 
 
+# TransformImageColorspace under image settings (colorspace.c:761, :996, :1085-1095) and the Log / YCC spaces:
+# (from, to, "key=value;..." -- "color:" keys are artifacts, the others properties)
+COLORSPACE_DEFINES = [(23, 11, "color:illuminant=D50"), (11, 23, "color:illuminant=D50"), (23, 13, "color:illuminant=F11"),
+                      (14, 23, "color:illuminant=E"), (23, 17, "color:illuminant=D75"), (17, 23, "color:illuminant=A"),
+                      (23, 34, "white-luminance=203"), (34, 23, "white-luminance=203"),
+                      (23, 15, ""), (15, 23, ""), (23, 15, "film-gamma=0.5;reference-black=64;reference-white=940"),
+                      (15, 23, "film-gamma=0.65;reference-white=700"), (23, 28, ""), (28, 23, ""), (21, 28, ""), (28, 11, "")]
+
+
 def main():
     r, P = util.ref(), util.P
     out = {}
     kernel_goldens(out)
     src4 = source(4)
+    for n, (frm, to, defines) in enumerate(COLORSPACE_DEFINES):
+        buf = src4.copy()
+        assert r.ref_colorspace_defines(P(buf), W, H, 4, frm, to, defines.encode()) == 0
+        out[f"colordef/{n}"] = buf
+    out["colordef/cases"] = np.array([f"{f}|{t}|{d}" for f, t, d in COLORSPACE_DEFINES])
     for n, (filt, defines) in enumerate(RESIZE_DEFINES):
         for (ow, oh) in ((20, 15), (82, 62)):
             dst = np.empty((oh, ow, 4), np.float32)

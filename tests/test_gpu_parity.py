@@ -449,6 +449,69 @@ def test_xyz_family_colorspaces(cs, kind):
             assert (d == 0).mean() > 0.99, (ch, frm, to, float((d == 0).mean()))
 
 
+# (colourspace, the image's settings as strings -- what the python mirror / the shim parse --, the same as values)
+COLORSPACE_SETTINGS = [
+    (11, {"color:illuminant": "D50"}, dict(illuminant="D50")),
+    (11, {"color:illuminant": "A"}, dict(illuminant="A")),
+    (13, {"color:illuminant": "F11"}, dict(illuminant="F11")),
+    (14, {"color:illuminant": "E"}, dict(illuminant="E")),
+    (12, {"color:illuminant": "C"}, dict(illuminant="C")),
+    (17, {"color:illuminant": "D75"}, dict(illuminant="D75")),
+    (17, {"color:illuminant": "nonsense"}, dict()),
+    (34, {"white-luminance": "203"}, dict(white_luminance=203.0)),
+    (15, {}, dict()),
+    (15, {"film-gamma": "0.5", "reference-black": "64", "reference-white": "940"}, dict(film_gamma=0.5, reference_black=64.0, reference_white=940.0)),
+    (15, {"film-gamma": "0.65", "reference-white": "700"}, dict(film_gamma=0.65, reference_white=700.0)),
+    (28, {}, dict()),
+]
+
+
+@pytest.mark.parametrize("case", range(len(COLORSPACE_SETTINGS)))
+@pytest.mark.parametrize("kind", ["noise", "hdr"])
+def test_colorspace_settings(case, kind):
+    """The settings TransformImageColorspace reads from the image (colorspace.c:761-773 illuminant, :996 white luminance,
+    :1085-1095 the Log film settings) and the two table spaces Log (:1055-1163, :2391-2500) and YCC (:1347-1389,
+    :2681-2711).  YCC is unfused arithmetic on map indices and a table => bit exact both ways; the forward Log leg is a
+    gather indexed by the linearised sample => bit exact; its inverse ends in EncodePixelGamma => <= 1 ULP; the
+    illuminant / white-luminance legs are the <= 1 ULP xyz_family kernels with other constants."""
+    cs, settings, values = COLORSPACE_SETTINGS[case]
+    opts = util.ColorspaceOptions.of(**values)
+    for ch in (3, 4):
+        src = _hexcone_image(131, 67, ch, kind, seed=160 + case)
+        src[1, :6, :3] = [[0, 0, 0], [65535, 65535, 65535], [0.4, 0.5, 0.6], [65534.6, 70000, -3], [1179.4, 1179.6, 1180.5], [40092, 35209, 100]]
+        for frm, to in ((23, cs), (cs, 23)):
+            want = src.copy()
+            assert oracle().orc_colorspace_ex(P(want), 131, 67, ch, frm, to, C.byref(opts)) == 0
+            img = _dev(src.copy())
+            img.colorspace = frm
+            assert im.TransformImageColorspace(img, to, settings=settings) is True and img.colorspace == to
+            got, want = _mask_achromatic_hue(_host(img), want, to)
+            ok = np.isfinite(want)
+            assert np.array_equal(np.isfinite(got), ok), (ch, frm, to)
+            got, want = np.where(ok, got, np.float32(0)), np.where(ok, want, np.float32(0))
+            exact = cs == 28 or (cs == 15 and to == 15)
+            d = util.ulp_distance(got, want) if exact else util.ulp_or_noise(got, want)
+            assert d.max() <= (0 if exact else 1), (ch, frm, to, int(d.max()))
+            assert (d == 0).mean() > 0.99, (ch, frm, to, float((d == 0).mean()))
+        if cs in (15, 28):
+            # linear RGB -> cs: the first leg (linear -> sRGB) is a <= 1 ULP operator in front of a quantiser, so pin the
+            # second leg on the product's own first leg (as test_matrix_and_lut_colorspaces does)
+            mid = _dev(src.copy())
+            mid.colorspace = 21
+            im.TransformImageColorspace(mid, 23)
+            want = _host(mid).copy()
+            assert oracle().orc_colorspace_ex(P(want), 131, 67, ch, 23, cs, C.byref(opts)) == 0
+            img = _dev(src.copy())
+            img.colorspace = 21
+            im.TransformImageColorspace(img, cs, settings=settings)
+            assert max_ulp(_host(img), want) == 0, (ch, 21, cs)
+    h = im.Image(make_image(33, 21, 4, seed=3))                      # host-buffer entry point
+    want = h.pixels.copy()
+    assert oracle().orc_colorspace_ex(P(want), 33, 21, 4, 23, cs, C.byref(opts)) == 0
+    im.TransformImageColorspace(h, cs, settings=settings)
+    assert util.ulp_or_noise(h.pixels, want).max() <= (0 if cs in (15, 28) else 1)
+
+
 EXPERT_RESIZE = [(22, {"filter:blur": "0.8"}, dict(blur=0.8)), (22, {"filter:lobes": "2"}, dict(lobes=2)),
                  (8, {"filter:sigma": "0.75"}, dict(sigma=0.75)), (16, {"filter:kaiser-beta": "4.5"}, dict(kaiser_beta=4.5)),
                  (10, {"filter:b": "0.5"}, dict(b=0.5)), (12, {"filter:b": "0.2", "filter:c": "0.6"}, dict(b=0.2, c=0.6)),

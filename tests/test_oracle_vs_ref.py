@@ -275,6 +275,45 @@ def test_xyz_family_colorspaces_bit_exact(cs, kind):
         assert max_ulp(np.where(ok, a, np.float32(0)), np.where(ok, b, np.float32(0))) == 0, (frm, to)
 
 
+# (colourspace, settings as the CLI would give them, the same settings as values)
+COLORSPACE_SETTINGS = [
+    (11, "color:illuminant=D50", dict(illuminant="D50")),
+    (11, "color:illuminant=A", dict(illuminant="A")),
+    (13, "color:illuminant=F11", dict(illuminant="F11")),
+    (14, "color:illuminant=E", dict(illuminant="E")),
+    (12, "color:illuminant=C", dict(illuminant="C")),
+    (17, "color:illuminant=D75", dict(illuminant="D75")),
+    (17, "color:illuminant=nonsense", dict()),                      # unparsable: UndefinedIlluminant == D65 (color.h:42)
+    (34, "white-luminance=203", dict(white_luminance=203.0)),
+    (34, "white-luminance=1000", dict(white_luminance=1000.0)),
+    (15, "", dict()),
+    (15, "gamma=2.2", dict()),          # SetImageProperty diverts "gamma" to image->gamma (property.c:4583): no effect
+    (15, "film-gamma=0.5;reference-black=64;reference-white=940", dict(film_gamma=0.5, reference_black=64.0, reference_white=940.0)),
+    (15, "film-gamma=0.65;reference-white=700", dict(film_gamma=0.65, reference_white=700.0)),
+    (28, "", dict()),
+]
+
+
+@pytest.mark.parametrize("case", range(len(COLORSPACE_SETTINGS)))
+@pytest.mark.parametrize("kind", ["noise", "hdr"])
+def test_colorspace_settings_bit_exact(case, kind):
+    """The settings TransformImageColorspace reads from the image -- "color:illuminant" (colorspace.c:761-773), "white-luminance"
+    (:996), "film-gamma" / "reference-black" / "reference-white" (:1085-1095) -- and the two LUT spaces that
+    complete the switch: Log (:1055-1163, :2391-2500) and YCC (:1347-1389, :2681-2711; the oracle regenerates the 1389-entry
+    PhotoYCC table from its rule, so this also pins that rule)."""
+    cs, defines, values = COLORSPACE_SETTINGS[case]
+    opts = util.ColorspaceOptions.of(**values)
+    src = hexcone_image(kind)
+    src[0, :6, :3] = [[0, 0, 0], [65535, 65535, 65535], [0.4, 0.5, 0.6], [65534.6, 70000, -3], [1179.4, 1179.6, 1180.5], [40092, 35209, 100]]
+    for frm, to in ((23, cs), (cs, 23), (cs, 26), (21, cs)):
+        a, b = src.copy(), src.copy()
+        assert util.ref().ref_colorspace_defines(P(a), 64, 48, 4, frm, to, defines.encode()) == 0
+        assert oracle().orc_colorspace_ex(P(b), 64, 48, 4, frm, to, C.byref(opts)) == 0
+        assert np.array_equal(np.isnan(a), np.isnan(b)), (frm, to)
+        ok = ~np.isnan(a)
+        assert max_ulp(np.where(ok, a, np.float32(0)), np.where(ok, b, np.float32(0))) == 0, (frm, to, defines)
+
+
 @pytest.mark.parametrize("kind", ["alpha_blocks", "hdr"])
 def test_difference_methods_bit_exact_on_awkward_pixels(kind):
     """EdgeIn/EdgeOut/Edge/TopHat/BottomHat end in CompositeImage(Difference) (morphology.c:3995-4012):

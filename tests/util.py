@@ -58,6 +58,7 @@ def oracle() -> C.CDLL:
         o.orc_filter_support_ex.argtypes = [_i, C.c_void_p]
         o.orc_filter_support_ex.restype = _d
         o.orc_colorspace.argtypes = [_fp, _sz, _sz, _i, _i, _i]
+        o.orc_colorspace_ex.argtypes = [_fp, _sz, _sz, _i, _i, _i, C.c_void_p]
         o.orc_sample.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         o.orc_scale.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         o.orc_selective_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d, _d]
@@ -110,6 +111,7 @@ def ref() -> C.CDLL:
         r.ref_resize.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz, _i]
         r.ref_resize_defines.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz, _i, C.c_char_p]
         r.ref_colorspace.argtypes = [_fp, _sz, _sz, _i, _i, _i]
+        r.ref_colorspace_defines.argtypes = [_fp, _sz, _sz, _i, _i, _i, C.c_char_p]
         r.ref_sample.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         r.ref_scale.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         r.ref_selective_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d, _d]
@@ -188,6 +190,23 @@ class FilterOptions(C.Structure):
                 o.keep_filter = int(v)
                 continue
             setattr(o, k, v)
+            o.set |= cls.BITS[k]
+        return o
+
+
+class ColorspaceOptions(C.Structure):
+    """mb200_colorspace_options == orc_colorspace_options: the image settings TransformImageColorspace reads, as values."""
+    _fields_ = [("set", C.c_uint), ("illuminant", C.c_int), ("white_luminance", C.c_double),
+                ("film_gamma", C.c_double), ("reference_black", C.c_double), ("reference_white", C.c_double)]
+
+    BITS = {"illuminant": 1, "white_luminance": 2, "film_gamma": 4, "reference_black": 8, "reference_white": 16}
+    ILLUMINANTS = {"A": 0, "B": 1, "C": 2, "D50": 3, "D55": 4, "D65": 5, "D75": 6, "E": 7, "F2": 8, "F7": 9, "F11": 10}
+
+    @classmethod
+    def of(cls, **kw):
+        o = cls()
+        for k, v in kw.items():
+            setattr(o, k, cls.ILLUMINANTS[v] if k == "illuminant" else v)
             o.set |= cls.BITS[k]
         return o
 
