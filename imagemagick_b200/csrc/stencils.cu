@@ -1,6 +1,6 @@
 // stencils.cu -- the neighbourhood operators next to the convolution path:
-//   StatisticImage       MagickCore/statistic.c:2918-3160   (Gradient, Maximum, Mean, Median, Minimum, RootMeanSquare,
-//                                                             StandardDeviation, Contrast)
+//   StatisticImage       MagickCore/statistic.c:2918-3160   (Gradient, Maximum, Mean, Median, Minimum, Mode, Nonpeak,
+//                                                             RootMeanSquare, StandardDeviation, Contrast)
 //   RotationalBlurImage  MagickCore/effect.c:3129-3400
 //   BilateralBlurImage   MagickCore/effect.c:821-1165
 //   SelectiveBlurImage   MagickCore/effect.c:3406-3700
@@ -68,8 +68,29 @@ __device__ __forceinline__ unsigned scale_quantum_to_short(float q) {      // qu
   return static_cast<unsigned>(q + 0.5f);
 }
 
-// type: statistic.h:141-151 (1 Gradient, 2 Maximum, 3 Mean, 4 Median, 5 Minimum, 8 RootMeanSquare, 9 StandardDeviation,
-// 10 Contrast).  The window's top-left corner is (x - W/2, y - H/2), edge replicated (:3012-3020).
+// The element of sorted index k among the ScaleQuantumToShort values of channel c over the W x H window at (x0, y0),
+// edge replicated: a 16-bit radix select (one pass over the window per bit) -- what the reference reads off its skip list.
+template <int CH>
+__device__ __forceinline__ unsigned window_select(const float *__restrict__ src, int w, int h, int x0, int y0, int W, int H,
+                                                  int c, unsigned k) {
+  unsigned prefix = 0;
+  for (int bit = 15; bit >= 0; --bit) {
+    const unsigned himask = bit == 15 ? 0u : (0xffffu << (bit + 1)) & 0xffffu;
+    unsigned zeros = 0;
+    for (int v = 0; v < H; ++v) {
+      const size_t row = static_cast<size_t>(min(max(y0 + v, 0), h - 1)) * w;
+      for (int u = 0; u < W; ++u) {
+        const unsigned s = scale_quantum_to_short(__ldg(src + (row + min(max(x0 + u, 0), w - 1)) * CH + c));
+        zeros += ((s & himask) == prefix && !(s >> bit & 1u)) ? 1u : 0u;
+      }
+    }
+    if (k >= zeros) { k -= zeros; prefix |= 1u << bit; }
+  }
+  return prefix;
+}
+
+// type: statistic.h:141-151 (1 Gradient, 2 Maximum, 3 Mean, 4 Median, 5 Minimum, 6 Mode, 7 Nonpeak, 8 RootMeanSquare,
+// 9 StandardDeviation, 10 Contrast).  The window's top-left corner is (x - W/2, y - H/2), edge replicated (:3012-3020).
 template <int CH>
 __global__ void __launch_bounds__(128) statistic_kernel(const float *__restrict__ src, float *__restrict__ dst, int w, int h,
                                                         int type, int W, int H) {
@@ -110,21 +131,61 @@ __global__ void __launch_bounds__(128) statistic_kernel(const float *__restrict_
     }
     const unsigned n = static_cast<unsigned>(W) * static_cast<unsigned>(H);
 #pragma unroll
+    for (int c = 0; c < CH; ++c) o[c] = static_cast<float>(static_cast<double>(window_select<CH>(src, w, h, x0, y0, W, H, c, n >> 1)));
+    store_pixel<CH>(dst, static_cast<size_t>(y) * w + x, o);
+    return;
+  }
+  if (type == 6) {
+    // Mode (GetModePixelList :2809): the reference walks the distinct 16-bit values of the window in ascending order and
+    // keeps the first one whose count is strictly the greatest.  Same walk here without the list: one pass over the window
+    // per distinct value finds the next larger value and its count (<= W*H passes, the window stays in L1).
+#pragma unroll
     for (int c = 0; c < CH; ++c) {
-      unsigned prefix = 0, k = n >> 1;
-      for (int bit = 15; bit >= 0; --bit) {
-        const unsigned himask = bit == 15 ? 0u : (0xffffu << (bit + 1)) & 0xffffu;
-        unsigned zeros = 0;
+      const unsigned n = static_cast<unsigned>(W) * static_cast<unsigned>(H);
+      unsigned mode = 65536u, best = 0u, seen = 0u;
+      int current = -1;
+      while (seen < n) {
+        unsigned value = 0x10000u, count = 0u;
         for (int v = 0; v < H; ++v) {
           const size_t row = static_cast<size_t>(min(max(y0 + v, 0), h - 1)) * w;
           for (int u = 0; u < W; ++u) {
             const unsigned s = scale_quantum_to_short(__ldg(src + (row + min(max(x0 + u, 0), w - 1)) * CH + c));
-            zeros += ((s & himask) == prefix && !(s >> bit & 1u)) ? 1u : 0u;
+            if (static_cast<int>(s) > current) {
+              if (s < value) { value = s; count = 1u; }
+              else if (s == value) ++count;
+            }
           }
         }
-        if (k >= zeros) { k -= zeros; prefix |= 1u << bit; }
+        if (count == 0u) break;                  // cannot happen while seen < n; keeps the loop finite regardless
+        if (count > best) { best = count; mode = value; }
+        seen += count;
+        current = static_cast<int>(value);
       }
-      o[c] = static_cast<float>(static_cast<double>(prefix));
+      o[c] = static_cast<float>(static_cast<double>(mode));
+    }
+    store_pixel<CH>(dst, static_cast<size_t>(y) * w + x, o);
+    return;
+  }
+  if (type == 7) {
+    // Nonpeak (GetNonpeakPixelList :2843): the median's value, unless it is the smallest distinct value of the window and
+    // a larger one exists (then that one), or the largest and a smaller one exists (then that one).
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const unsigned n = static_cast<unsigned>(W) * static_cast<unsigned>(H);
+      const unsigned median = window_select<CH>(src, w, h, x0, y0, W, H, c, n >> 1);
+      int previous = -1, next = -1;
+      for (int v = 0; v < H; ++v) {
+        const size_t row = static_cast<size_t>(min(max(y0 + v, 0), h - 1)) * w;
+        for (int u = 0; u < W; ++u) {
+          const int s = static_cast<int>(scale_quantum_to_short(__ldg(src + (row + min(max(x0 + u, 0), w - 1)) * CH + c)));
+          if (s < static_cast<int>(median)) previous = max(previous, s);
+          if (s > static_cast<int>(median)) next = next < 0 ? s : min(next, s);
+        }
+      }
+      unsigned color = median;
+      if (previous < 0 && next >= 0) color = static_cast<unsigned>(next);
+      else if (previous >= 0 && next < 0) color = static_cast<unsigned>(previous);
+      o[c] = static_cast<float>(static_cast<double>(color));
     }
     store_pixel<CH>(dst, static_cast<size_t>(y) * w + x, o);
     return;
@@ -502,8 +563,7 @@ int launch_statistic(const float *src, float *dst, size_t w, size_t h, int chann
                      void *stream) {
   int rc = check_image(src, dst, w, h, channels, "statistic");
   if (rc) return rc;
-  if (type < 1 || type > 10 || type == 6 || type == 7)
-    return fail(MB200_EUNSUPPORTED, "statistic type %d (Mode / Nonpeak walk the reference's skip list) stays on the CPU path", type);
+  if (type < 1 || type > 10) return fail(MB200_EINVAL, "statistic type %d", type);
   const size_t W = width > 1 ? width : 1, H = height > 1 ? height : 1;
   if (W > 255 || H > 255) return fail(MB200_EUNSUPPORTED, "statistic: window larger than 255");
   cudaStream_t s = static_cast<cudaStream_t>(stream);

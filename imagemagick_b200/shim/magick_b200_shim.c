@@ -675,8 +675,9 @@ Image *B200AccelerateStatisticImage(const Image *image, const StatisticType type
   stencil_args a;
   switch (type) {
     case GradientStatistic: case MaximumStatistic: case MeanStatistic: case MedianStatistic: case MinimumStatistic:
+    case ModeStatistic: case NonpeakStatistic:
     case RootMeanSquareStatistic: case StandardDeviationStatistic: case ContrastStatistic: break;
-    default: return (Image *) NULL;               /* Mode / Nonpeak walk the reference's skip list: CPU */
+    default: return (Image *) NULL;
   }
   a.type = (int) type; a.width = width; a.height = height; a.a = a.b = a.c = 0.0;
   return run_same_size(image, op_statistic, &a, exception);

@@ -116,6 +116,8 @@ int main(void)
   CHECK("SharpenImage(0,1) RGBA", 1, SharpenImage(rgba, 0.0, 1.0, ex), CPU(__real_SharpenImage(rgba, 0.0, 1.0, ex)));
   CHECK("EdgeImage(1) RGB", 1, EdgeImage(rgb, 1.0, ex), CPU(__real_EdgeImage(rgb, 1.0, ex)));
   CHECK("StatisticImage Median 3x3 RGBA", 0, StatisticImage(rgba, MedianStatistic, 3, 3, ex), CPU(__real_StatisticImage(rgba, MedianStatistic, 3, 3, ex)));
+  CHECK("StatisticImage Mode 3x3 RGB", 0, StatisticImage(rgb, ModeStatistic, 3, 3, ex), CPU(__real_StatisticImage(rgb, ModeStatistic, 3, 3, ex)));
+  CHECK("StatisticImage Nonpeak 5x5 RGBA", 0, StatisticImage(rgba, NonpeakStatistic, 5, 5, ex), CPU(__real_StatisticImage(rgba, NonpeakStatistic, 5, 5, ex)));
   CHECK("StatisticImage StdDev 5x3 RGB", 0, StatisticImage(rgb, StandardDeviationStatistic, 5, 3, ex), CPU(__real_StatisticImage(rgb, StandardDeviationStatistic, 5, 3, ex)));
   CHECK("RotationalBlurImage(7) RGBA", 0, RotationalBlurImage(rgba, 7.0, ex), CPU(__real_RotationalBlurImage(rgba, 7.0, ex)));
   CHECK("AdaptiveBlurImage 0x1.5 RGBA", 0, AdaptiveBlurImage(rgba, 0.0, 1.5, ex), CPU(__real_AdaptiveBlurImage(rgba, 0.0, 1.5, ex)));

@@ -338,8 +338,8 @@ MB200_API int mb200_equalize_image_dev(float *buf, size_t width, size_t height, 
 MB200_API int mb200_emboss_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
     double radius, double sigma, void *stream);
 /* StatisticImage (MagickCore/statistic.c:2918): `type` is a StatisticType (statistic.h:141-151: 1 Gradient, 2 Maximum,
-   3 Mean, 4 Median, 5 Minimum, 8 RootMeanSquare, 9 StandardDeviation, 10 Contrast; Mode 6 / Nonpeak 7 return
-   MB200_EUNSUPPORTED) over a window_width x window_height neighbourhood, bit exact. */
+   3 Mean, 4 Median, 5 Minimum, 6 Mode, 7 Nonpeak, 8 RootMeanSquare, 9 StandardDeviation, 10 Contrast) over a
+   window_width x window_height neighbourhood, bit exact. */
 MB200_API int mb200_statistic_image_dev(const float *src, float *dst, size_t width, size_t height, int channels,
     int type, size_t window_width, size_t window_height, void *stream);
 /* RotationalBlurImage (MagickCore/effect.c:3129) == AccelerateRotationalBlurImage (accelerate-private.h), bit exact. */

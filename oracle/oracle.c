@@ -2745,8 +2745,10 @@ int orc_rotational_blur(const float *src, float *dst, size_t w, size_t h, int ch
    (x - width/2, y - height/2), edge-replicated.  Gradient / Maximum / Mean / Minimum / RootMeanSquare /
    StandardDeviation / Contrast accumulate in double in row-major window order; Median goes through the
    reference's 16-bit skip list (InsertPixelList :2878 -> ScaleQuantumToShort; GetMedianPixelList :2784
-   returns the element at sorted index length/2), so its result is an integer Quantum.  Mode / Nonpeak
-   are not restated.  type: statistic.h:141-151 numeric values.
+   returns the element at sorted index length/2), so its result is an integer Quantum.  Mode (:2809) walks the
+   distinct values in ascending order and keeps the first one whose count is strictly the greatest; Nonpeak (:2843) is the
+   median's value unless that value is the smallest (largest) distinct value of the window and a larger (smaller) one
+   exists, in which case it steps to that neighbour.  type: statistic.h:141-151 numeric values.
    ------------------------------------------------------------------------------------------ */
 static unsigned short scale_quantum_to_short(float q)
 {
@@ -2765,7 +2767,7 @@ int orc_statistic(const float *src, float *dst, size_t w, size_t h, int ch, int 
 {
   const long W = (long) (width > 1 ? width : 1), Hh = (long) (height > 1 ? height : 1);
   long y;
-  if (type < 1 || type > 10 || type == 6 || type == 7) return -1;
+  if (type < 1 || type > 10) return -1;
 #pragma omp parallel for schedule(static)
   for (y = 0; y < (long) h; y++) {
     unsigned short *list = (unsigned short *) malloc((size_t) (W * Hh) * sizeof(unsigned short));
@@ -2798,6 +2800,31 @@ int orc_statistic(const float *src, float *dst, size_t w, size_t h, int ch, int 
             pixel = (double) list[n >> 1];
             break;
           case 5: pixel = minimum; break;
+          case 6: {                                                                                /* Mode */
+            long i = 0, best = 0;
+            qsort(list, (size_t) n, sizeof(unsigned short), cmp_ushort);
+            pixel = 65536.0;                       /* the root node; unreachable for n >= 1 */
+            while (i < n) {
+              long j = i;
+              while (j < n && list[j] == list[i]) j++;
+              if (j - i > best) { best = j - i; pixel = (double) list[i]; }
+              i = j;
+            }
+            break;
+          }
+          case 7: {                                                                                /* Nonpeak */
+            long i, at = n >> 1;
+            long previous = -1, next = -1;
+            qsort(list, (size_t) n, sizeof(unsigned short), cmp_ushort);
+            for (i = 0; i < n; i++) {
+              if (list[i] < list[at]) previous = list[i];
+              if (list[i] > list[at] && next < 0) next = list[i];
+            }
+            pixel = (double) list[at];
+            if (previous < 0 && next >= 0) pixel = (double) next;
+            else if (previous >= 0 && next < 0) pixel = (double) previous;
+            break;
+          }
           case 8: pixel = sqrt(sum_squared / area); break;
           case 9: pixel = sqrt(sum_squared / area - (sum / area * sum / area)); break;
           case 10: pixel = fabs((maximum - minimum) * perceptible_reciprocal(maximum + minimum)); break;

@@ -341,13 +341,32 @@ def test_emboss(ch, radius, sigma):
 
 # ---- rank-4 stencils: StatisticImage, RotationalBlurImage, BilateralBlurImage (oracles pinned to the reference) ----------
 @pytest.mark.parametrize("ch", [1, 2, 3, 4])
-@pytest.mark.parametrize("stat", [1, 2, 3, 4, 5, 8, 9, 10])
+@pytest.mark.parametrize("stat", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
 @pytest.mark.parametrize("win", [(3, 3), (5, 3), (1, 7), (4, 4)])
 def test_statistic_image_bit_exact(ch, stat, win):
     src = make_image(97, 61, ch, seed=61, kind="hdr" if stat in (1, 10) else "noise")
     want = orc("orc_statistic", src, stat, win[0], win[1])
     got = _host(im.StatisticImage(_dev(src), stat, win[0], win[1]))
     assert_same_specials_and_ulp(got, want, bar=0)
+
+
+@pytest.mark.parametrize("ch", [1, 3, 4])
+@pytest.mark.parametrize("stat", [4, 6, 7])
+@pytest.mark.parametrize("win", [(3, 3), (5, 5), (4, 2), (1, 7), (1, 1), (9, 9)])
+def test_rank_statistics_on_few_levels(ch, stat, win):
+    """Median, Mode and Nonpeak read the reference's 16-bit skip list (statistic.c:2784, :2809, :2843).  A posterised image
+    has few distinct levels: counts tie (the mode is the smallest of the most frequent values), the median sits on the
+    window's smallest / largest level (Nonpeak steps off it), flat regions have one level only."""
+    src = make_image(97, 61, ch, seed=63, kind="noise")
+    poster = (np.round(src / 16384.0) * 16384.0).astype(np.float32)
+    poster[10:30, 10:50] = 32768.0
+    poster[40:50, 60:90] += np.float32(0.4)            # rounds to the same 16-bit value
+    for image in (src, poster):
+        want = orc("orc_statistic", image, stat, win[0], win[1])
+        got = _host(im.StatisticImage(_dev(image), stat, win[0], win[1]))
+        assert np.array_equal(got, want), (ch, stat, win)
+    h = im.StatisticImage(im.Image(poster), stat, win[0], win[1]).pixels          # host-buffer entry point
+    assert np.array_equal(h, orc("orc_statistic", poster, stat, win[0], win[1]))
 
 
 @pytest.mark.parametrize("ch", [1, 2, 3, 4])

@@ -92,14 +92,18 @@ def test_rotational_blur_oracle_bit_exact(ch, kind):
 @pytest.mark.parametrize("kind", ["noise", "hdr", "gradient"])
 def test_statistic_oracle_bit_exact(ch, kind):
     """statistic.c:2918 StatisticImage (Gradient, Maximum, Mean, Median via the 16-bit skip list, Minimum,
-    RootMeanSquare, StandardDeviation, Contrast; odd, even and 1-wide windows) -- groundwork for SURVEY 8f rank 4."""
+    RootMeanSquare, StandardDeviation, Contrast; Mode and Nonpeak walk the same list; odd, even and 1-wide windows).  The
+    posterised copy has few distinct levels, so counts tie and the median sits on the smallest / largest level."""
     src = make_image(47, 33, ch, seed=23, kind=kind)
-    for typ in (1, 2, 3, 4, 5, 8, 9, 10):
+    poster = (np.round(src / 16384.0) * 16384.0).astype(np.float32)
+    poster[10:20, 10:30] = 32768.0
+    for typ in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10):
         for W, H in ((3, 3), (5, 5), (4, 2), (1, 7), (1, 1)):
-            a, b = np.empty_like(src), np.empty_like(src)
-            assert util.ref().ref_statistic(P(src), P(a), 47, 33, ch, typ, W, H) == 0
-            assert oracle().orc_statistic(P(src), P(b), 47, 33, ch, typ, W, H) == 0
-            assert max_ulp(a, b) == 0, (typ, W, H)
+            for image in ((src, poster) if typ in (4, 6, 7) else (src,)):
+                a, b = np.empty_like(image), np.empty_like(image)
+                assert util.ref().ref_statistic(P(image), P(a), 47, 33, ch, typ, W, H) == 0
+                assert oracle().orc_statistic(P(image), P(b), 47, 33, ch, typ, W, H) == 0
+                assert max_ulp(a, b) == 0, (typ, W, H)
 
 
 @pytest.mark.parametrize("ch", [1, 4])
