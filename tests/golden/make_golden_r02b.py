@@ -96,6 +96,13 @@ def main():
                 dst = np.empty((oh, ow, ch), np.float32)
                 assert r.ref_resize(P(src), W, H, ch, P(dst), ow, oh, filt) == 0
                 out[f"c{ch}/resize_{name}_{ow}x{oh}"] = dst
+        poster = (np.round(src / 16384.0) * 16384.0).astype(np.float32)     # few levels: tied counts, medians on the extremes
+        for typ, tname in ((6, "mode"), (7, "nonpeak")):
+            for (ww, wh) in ((3, 3), (5, 5), (4, 2)):
+                for image, iname in ((src, "src"), (poster, "poster")):
+                    dst = np.empty_like(image)
+                    assert r.ref_statistic(P(image), P(dst), W, H, ch, typ, ww, wh) == 0
+                    out[f"c{ch}/statistic_{tname}_{ww}x{wh}_{iname}"] = dst
         for name, cs in HEXCONE.items():
             for frm, to, tag in ((23, cs, f"srgb_{name}"), (cs, 23, f"{name}_srgb")):
                 buf = src.copy()

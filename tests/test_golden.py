@@ -188,6 +188,13 @@ HEXCONE2 = {"hcl": 4, "hclp": 5, "hsb": 6, "hsi": 7, "hsl": 8, "hsv": 9, "hwb": 
 SMOOTH2 = ("hsi", "jzazbz", "lch", "lchab", "lchuv", "oklab", "oklch", "lms", "luv", "xyy", "displayp3", "adobe98", "prophoto", "cat02lms")    # <= 1 ULP; the others bit exact
 
 
+STATISTICS2 = {"mode": 6, "nonpeak": 7}
+
+
+def _poster(src):
+    return (np.round(src / 16384.0) * 16384.0).astype(np.float32)
+
+
 def _r02b_cases(tag):
     return [k for k in G2.files if k.startswith(tag + "/") and not k.endswith("/src")]
 
@@ -229,6 +236,12 @@ def test_oracle_matches_reference_golden_r02b(tag):
             ow, oh = map(int, size.split("x"))
             got = np.empty((oh, ow, ch), np.float32)
             assert o.orc_resize(P(src), w, h, ch, P(got), ow, oh, FILTERS2[f]) == 0
+        elif name.startswith("statistic_"):
+            _, stat, size, which = name.split("_")
+            ww, wh = map(int, size.split("x"))
+            image = src if which == "src" else _poster(src)
+            got = np.empty_like(image)
+            assert o.orc_statistic(P(image), P(got), w, h, ch, STATISTICS2[stat], ww, wh) == 0
         else:
             _, a, b = name.split("_")
             got = src.copy()
@@ -250,6 +263,12 @@ def test_cuda_path_matches_reference_golden_r02b(tag):
             _, f, size = name.split("_")
             ow, oh = map(int, size.split("x"))
             got, bar = im.ResizeImage(img, ow, oh, FILTERS2[f]).pixels.cpu().numpy(), 1
+        elif name.startswith("statistic_"):
+            _, stat, size, which = name.split("_")
+            ww, wh = map(int, size.split("x"))
+            if which == "poster":
+                img = im.Image(torch.from_numpy(_poster(src)).cuda())
+            got, bar = im.StatisticImage(img, STATISTICS2[stat], ww, wh).pixels.cpu().numpy(), 0
         else:
             _, a, b = name.split("_")
             img.colorspace = HEXCONE2[a]
