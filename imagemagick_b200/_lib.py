@@ -101,6 +101,8 @@ PROTOTYPES = {
     "mb200_resize_image": (_i, [_vp, _sz, _sz, _i, _vp, _sz, _sz, _i]),
     "mb200_transform_colorspace": (_i, [_vp, _sz, _sz, _i, _i, _i]),
     "mb200_transform_colorspace_ex": (_i, [_vp, _sz, _sz, _i, _i, _i, _vp]),
+    "mb200_log_colorspace_table": (_i, [_i, _vp, _vp]),
+    "mb200_ycc_table": (_i, [_vp]),
     "mb200_sharpen_kernel": (KernelPtr, [_d, _d]),
     "mb200_edge_kernel": (KernelPtr, [_d]),
     "mb200_restore_channels_dev": (_i, [_vp, _vp, _sz, _sz, _i, C.c_uint, _vp]),

@@ -965,3 +965,20 @@ int launch_colorspace(float *buf, size_t npixels, int channels, int from, int to
 }
 
 }  // namespace mb200
+
+// Host-side table builders, exported so that the tables can be pinned without a GPU (tests/test_host_logic.py).
+extern "C" {
+
+int mb200_log_colorspace_table(int forward, const mb200_colorspace_options *options, float *table) {
+  if (!table) return mb200::fail(MB200_EINVAL, "log table: null buffer");
+  mb200::build_log_table(forward != 0, options, table);
+  return MB200_OK;
+}
+
+int mb200_ycc_table(float *table) {
+  if (!table) return mb200::fail(MB200_EINVAL, "ycc table: null buffer");
+  mb200::build_ycc_table(table);
+  return MB200_OK;
+}
+
+}  // extern "C"

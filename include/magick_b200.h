@@ -408,6 +408,10 @@ typedef struct mb200_colorspace_options {
 } mb200_colorspace_options;
 MB200_API int mb200_transform_colorspace_ex_dev(float *buf, size_t width, size_t height, int channels,
     int from_colorspace, int to_colorspace, const mb200_colorspace_options *options, void *stream);
+/* The host-built tables behind the Log and YCC legs (no device needed): the 65536-entry `logmap` of colorspace.c:1100-1106
+   (forward != 0) / :2431-2440 (inverse) for the given film settings, and the 1389-entry PhotoYCC table of :1828. */
+MB200_API int mb200_log_colorspace_table(int forward, const mb200_colorspace_options *options, float *table65536);
+MB200_API int mb200_ycc_table(float *table1389);
 
 /* Threshold point operators of MagickCore/threshold.c, in place on `buf`, bit exact.
    BilevelImage (:805): every channel (alpha included) := intensity <= threshold ? 0 : QuantumRange,

@@ -2139,6 +2139,18 @@ int orc_colorspace(float *buf, size_t w, size_t h, int ch, int from, int to)
   return orc_colorspace_ex(buf, w, h, ch, from, to, NULL);
 }
 
+/* the two tables on their own (pinned to the reference through the images above) */
+void orc_log_table(int forward, const orc_colorspace_options *o, float *table)
+{
+  cs_log.gamma = 1.0 / 1.7;
+  cs_log.film_gamma = (o && (o->set & ORC_CO_FILM_GAMMA)) ? o->film_gamma : 0.6;
+  cs_log.reference_black = (o && (o->set & ORC_CO_REFERENCE_BLACK)) ? o->reference_black : 95.0;
+  cs_log.reference_white = (o && (o->set & ORC_CO_REFERENCE_WHITE)) ? o->reference_white : 685.0;
+  if (forward) log_forward_table(table); else log_inverse_table(table);
+}
+
+void orc_ycc_table(float *table) { ycc_map(table); }
+
 /* ------------------------------------------------------------------------------------------
    threshold.c point operators (in place).
    BilevelImage :805-897, BlackThresholdImage :927-1053, WhiteThresholdImage :2518-2644,

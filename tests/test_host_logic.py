@@ -113,6 +113,37 @@ def test_expert_filter_settings_match_oracle(filt, values):
     assert util.max_ulp(got.reshape(1, n_out, 1), want) <= 1
 
 
+@pytest.mark.parametrize("values", [dict(), dict(film_gamma=0.5, reference_black=64.0, reference_white=940.0),
+                                    dict(film_gamma=0.65, reference_white=700.0), dict(reference_black=0.0, reference_white=1024.0),
+                                    dict(film_gamma=0.0)])
+def test_log_and_ycc_tables_match_oracle(values):
+    """The host-built tables behind the Log and YCC colourspace legs are the oracle's bit for bit (the oracle is pinned to the
+    reference with the properties set, test_colorspace_settings_bit_exact), and the python mirror parses the image settings
+    into the same values the tests pass directly."""
+    import imagemagick_b200 as im
+    lib, o = _lib.load(), util.oracle()
+    opts = util.ColorspaceOptions.of(**values)
+    for forward in (1, 0):
+        a, b = np.empty(65536, np.float32), np.empty(65536, np.float32)
+        assert lib.mb200_log_colorspace_table(forward, C.byref(opts), a.ctypes.data) == 0
+        o.orc_log_table(forward, C.byref(opts), util.P(b))
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.nan_to_num(a), np.nan_to_num(b)), (forward, values)
+    a, b = np.empty(1389, np.float32), np.empty(1389, np.float32)
+    assert lib.mb200_ycc_table(a.ctypes.data) == 0
+    o.orc_ycc_table(util.P(b))
+    assert np.array_equal(a, b) and a[0] == 0.0 and a[-1] == 1.0 and np.all(np.diff(a) > 0)
+    names = {"film_gamma": "film-gamma", "reference_black": "reference-black", "reference_white": "reference-white"}
+    parsed = im.api.colorspace_options_from_settings({names[k]: repr(v) for k, v in values.items()})
+    if values:
+        assert parsed.set == opts.set
+        assert all(getattr(parsed, k) == getattr(opts, k) for k in values)
+    else:
+        assert parsed is None
+    ill = im.api.colorspace_options_from_settings({"color:illuminant": "d50", "white-luminance": "203"})
+    assert (ill.set, ill.illuminant, ill.white_luminance) == (3, 3, 203.0)
+    assert im.api.colorspace_options_from_settings({"color:illuminant": "nonsense"}).illuminant == 5
+
+
 def test_resize_contributions_lanczos_2x():
     lib = _lib.load()
     n_in, n_out = 64, 32

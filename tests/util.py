@@ -59,6 +59,10 @@ def oracle() -> C.CDLL:
         o.orc_filter_support_ex.restype = _d
         o.orc_colorspace.argtypes = [_fp, _sz, _sz, _i, _i, _i]
         o.orc_colorspace_ex.argtypes = [_fp, _sz, _sz, _i, _i, _i, C.c_void_p]
+        o.orc_log_table.argtypes = [_i, C.c_void_p, _fp]
+        o.orc_log_table.restype = None
+        o.orc_ycc_table.argtypes = [_fp]
+        o.orc_ycc_table.restype = None
         o.orc_sample.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         o.orc_scale.argtypes = [_fp, _sz, _sz, _i, _fp, _sz, _sz]
         o.orc_selective_blur.argtypes = [_fp, _fp, _sz, _sz, _i, _d, _d, _d]
